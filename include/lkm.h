@@ -1,0 +1,204 @@
+/* lkm.h — C ABI of the B200-native K-Means hot path ("linfa k-means", lkm).
+ *
+ * This is the drop-in boundary for linfa-clustering's K-Means.  The reference
+ * (rust-ml/linfa v0.8.1) has no FFI of its own: the path sits behind the linfa
+ * trait system.  Each entry point below names the reference item it replaces;
+ * the Rust crate in rust/linfa-clustering-b200 (and the ctypes binding in
+ * linfa_b200/_ffi.py) bind exactly these symbols.  Paths are relative to the
+ * reference root; KM = algorithms/linfa-clustering/src/k_means.
+ *
+ * Conventions: every function returns an lkm_status (0 = OK) and never throws
+ * or unwinds.  All pointers are plain host pointers unless the name says
+ * `_device`.  The caller owns every output buffer; the library never keeps a
+ * host pointer after the call returns.  One context drives one GPU (one
+ * process per GPU); a context may be used from one thread at a time.
+ * F is float (`_f32`) or double (`_f64`) — linfa::Float is implemented for
+ * exactly these two (src/dataset/mod.rs:68-74).  Matrices are row-major.
+ */
+#ifndef LKM_H
+#define LKM_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct lkm_ctx lkm_ctx;
+
+/* Status codes.  10..14 mirror KMeansParamsError (KM/errors.rs:5-19),
+ * 1 mirrors KMeansError::InertiaError (KM/errors.rs:27-28), 20 mirrors
+ * IncrKMeansError::NotConverged (KM/errors.rs:40-42).  3..6 are the places
+ * where the reference panics (assert!/expect/unwrap). */
+typedef enum lkm_status {
+  LKM_OK = 0,
+  LKM_ERR_INERTIA = 1,        /* no run produced a finite inertia (KM/algorithm.rs:336,365) */
+  LKM_ERR_INVALID_ARG = 2,
+  LKM_ERR_SAMPLE_AMOUNT = 3,  /* Random init with k > n: rand::seq::index::sample panics */
+  LKM_ERR_ZERO_WEIGHTS = 4,   /* assert_ne!(weights.sum(), 0) (KM/init.rs:127) */
+  LKM_ERR_BAD_WEIGHTS = 5,    /* WeightedIndex::new(..).expect("invalid weights") (KM/init.rs:131-133) */
+  LKM_ERR_SHAPE = 6,          /* shape asserts: Precomputed (KM/init.rs:96-97), predict (KM/algorithm.rs:744-748) */
+  LKM_ERR_N_CLUSTERS = 10,    /* KMeansParamsError::NClusters  (KM/hyperparams.rs:125) */
+  LKM_ERR_N_RUNS = 11,        /* KMeansParamsError::NRuns      (KM/hyperparams.rs:127) */
+  LKM_ERR_TOLERANCE = 12,     /* KMeansParamsError::Tolerance  (KM/hyperparams.rs:129) */
+  LKM_ERR_MAX_ITERATIONS = 13,/* KMeansParamsError::MaxIterations (KM/hyperparams.rs:131) */
+  LKM_ERR_INCREMENTAL_HAMERLY = 14, /* KMeansParamsError::IncrementalHamerly (KM/algorithm.rs:640-644) */
+  LKM_NOT_CONVERGED = 20,     /* fit_with: Err(NotConverged(model)); outputs ARE written */
+  LKM_ERR_CUDA = 30,
+  LKM_ERR_NCCL = 31,
+  LKM_ERR_NO_DATA = 32,       /* fit/init called before set_data / gen_blobs */
+  LKM_ERR_UNSUPPORTED = 33
+} lkm_status;
+
+/* KMeansInit (KM/init.rs:22-35) */
+typedef enum lkm_init_method {
+  LKM_INIT_RANDOM = 0,
+  LKM_INIT_PRECOMPUTED = 1,
+  LKM_INIT_KMEANS_PLUSPLUS = 2,
+  LKM_INIT_KMEANS_PARA = 3
+} lkm_init_method;
+
+/* KMeansAlgorithm (KM/init.rs:54-79).  Hamerly is accepted and executed as
+ * Lloyd: the reference documents that both converge to the same result from
+ * the same initial centroids (KM/init.rs:46-47). */
+typedef enum lkm_algorithm { LKM_ALGO_LLOYD = 0, LKM_ALGO_HAMERLY = 1 } lkm_algorithm;
+
+/* How the D^2 / weighted pick of k-means++ walks the prefix sum.
+ * EXACT reproduces rand 0.8.5 WeightedIndex bit for bit (sequential prefix sum
+ * in F on one GPU thread) — same row indices as the reference for the same
+ * RNG.  FAST uses a fixed-order parallel f64 scan with the same uniform draw. */
+typedef enum lkm_pick_mode { LKM_PICK_EXACT = 0, LKM_PICK_FAST = 1 } lkm_pick_mode;
+
+/* Trampolines into the caller's `R: Rng` (KM/hyperparams.rs:37 `rng: R`).
+ * The reference clones the rng at the top of every fit (KM/algorithm.rs:298);
+ * the binding clones before the call and passes the clone here. */
+typedef struct lkm_rng {
+  void* user;
+  uint32_t (*next_u32)(void* user);
+  uint64_t (*next_u64)(void* user);
+} lkm_rng;
+
+/* KMeansValidParams (KM/hyperparams.rs:19-42); defaults at :71-82 are
+ * n_runs 10, tolerance 1e-4, max_n_iterations 300, init KMeansPlusPlus. */
+typedef struct lkm_params {
+  uint64_t n_clusters;
+  uint64_t n_runs;
+  uint64_t max_n_iterations;
+  double tolerance;          /* cast to F inside, like F::cast(1e-4) */
+  int32_t init_method;       /* lkm_init_method */
+  int32_t algorithm;         /* lkm_algorithm */
+  int32_t pick_mode;         /* lkm_pick_mode (not in the reference; default EXACT = 0) */
+  int32_t reserved;
+  const void* precomputed;   /* KMeansInit::Precomputed: k x d of F, host, row-major */
+  uint64_t precomputed_rows; /* shape check against n_clusters / d (KM/init.rs:96-97) */
+  uint64_t precomputed_cols;
+} lkm_params;
+
+/* Timings and counters of the last lkm_lloyd_iters_* / lkm_fit_* call. */
+typedef struct lkm_stats {
+  uint64_t n_iter;           /* Lloyd iterations executed (last run) */
+  double last_shift;         /* ||C_t - C_{t+1}||_F of the last iteration */
+  double inertia_total;      /* sum of min squared distances of the last assignment */
+  float device_ms;           /* CUDA-event time of the iteration loop on the context stream */
+  uint32_t kernel_launches;  /* kernels this library launched in the call */
+  uint32_t assign_path;      /* 0 exact CUDA-core, 1 certified FMA, 2 tcgen05 3xTF32 */
+  uint64_t fallback_rows;    /* rows re-evaluated in exact form by the certified paths */
+} lkm_stats;
+
+/* -- context ------------------------------------------------------------- */
+lkm_status lkm_create(lkm_ctx** out, int device);
+lkm_status lkm_destroy(lkm_ctx* ctx);
+const char* lkm_last_error(const lkm_ctx* ctx);
+/* the CUDA stream (cudaStream_t) every kernel of this context is launched on */
+void* lkm_stream(lkm_ctx* ctx);
+lkm_status lkm_synchronize(lkm_ctx* ctx);
+const char* lkm_version(void);
+
+/* -- multi-GPU (new; the reference is single-process).  Rows are sharded,
+ * every rank holds full centroids, and each Lloyd iteration all-gathers the
+ * per-rank (k*d sums, k counts, inertia) partials and reduces them in rank
+ * order.  id128 is an ncclUniqueId (128 bytes) made on rank 0 and shipped by
+ * the caller (torch.distributed / MPI / a file). */
+lkm_status lkm_comm_unique_id(void* id128);
+lkm_status lkm_comm_init(lkm_ctx* ctx, const void* id128, int rank, int world_size);
+/* global row offset / global row count of this rank's shard, used by seeding
+ * (row indices drawn by the RNG are global) and by inertia = total / n_global */
+lkm_status lkm_set_shard(lkm_ctx* ctx, uint64_t row_offset, uint64_t n_global);
+
+/* -- observations: `dataset.records()` (KM/algorithm.rs:299) -------------- */
+/* copies a host matrix (any row stride, like an ndarray view) to the device */
+lkm_status lkm_set_data_f32(lkm_ctx* ctx, const float* x, uint64_t n, uint64_t d, int64_t row_stride);
+lkm_status lkm_set_data_f64(lkm_ctx* ctx, const double* x, uint64_t n, uint64_t d, int64_t row_stride);
+/* borrows a device-resident contiguous n x d matrix (no copy) */
+lkm_status lkm_set_data_device_f32(lkm_ctx* ctx, const void* x_device, uint64_t n, uint64_t d);
+lkm_status lkm_set_data_device_f64(lkm_ctx* ctx, const void* x_device, uint64_t n, uint64_t d);
+/* device-side linfa_datasets::generate::blobs (datasets/src/generate.rs:28-58):
+ * blob b owns rows [b*m, (b+1)*m) of the GLOBAL matrix (m = n_global / n_blobs,
+ * the last blob takes the remainder), row = centre_b + sigma * N(0, I) from a
+ * counter-based generator keyed by (seed, global row, feature).  This rank
+ * materialises global rows [row_offset, row_offset + n). */
+lkm_status lkm_gen_blobs_f32(lkm_ctx* ctx, uint64_t n, uint64_t d, uint64_t n_blobs, const float* centres,
+                             float sigma, uint64_t seed, uint64_t row_offset, uint64_t n_global);
+lkm_status lkm_gen_blobs_f64(lkm_ctx* ctx, uint64_t n, uint64_t d, uint64_t n_blobs, const double* centres,
+                             double sigma, uint64_t seed, uint64_t row_offset, uint64_t n_global);
+/* copy rows [row0, row0+rows) of the resident matrix back to the host */
+lkm_status lkm_get_data_f32(lkm_ctx* ctx, uint64_t row0, uint64_t rows, float* out);
+lkm_status lkm_get_data_f64(lkm_ctx* ctx, uint64_t row0, uint64_t rows, double* out);
+
+/* -- Fit::fit -> fit_lloyd + get_kmeans_result (KM/algorithm.rs:294-367,370-388)
+ * centroids_out k*d, cluster_count_out k (as F, from the LAST run's final
+ * assignment — KM/algorithm.rs:304,342,355-357), inertia_out = best total / n. */
+lkm_status lkm_fit_f32(lkm_ctx* ctx, const lkm_params* p, lkm_rng rng, float* centroids_out,
+                       float* cluster_count_out, float* inertia_out, lkm_stats* stats_out);
+lkm_status lkm_fit_f64(lkm_ctx* ctx, const lkm_params* p, lkm_rng rng, double* centroids_out,
+                       double* cluster_count_out, double* inertia_out, lkm_stats* stats_out);
+
+/* -- KMeansInit::run (KM/init.rs:83-101): seeding only -------------------- */
+lkm_status lkm_init_f32(lkm_ctx* ctx, const lkm_params* p, lkm_rng rng, float* centroids_out);
+lkm_status lkm_init_f64(lkm_ctx* ctx, const lkm_params* p, lkm_rng rng, double* centroids_out);
+
+/* -- the loop body of fit_lloyd (KM/algorithm.rs:314-331) as a benchmark /
+ * resume entry: runs Lloyd iterations from centroids_inout until the shift
+ * drops below `tolerance` or `max_iters` iterations ran.  cluster_count_out
+ * and inertia_total_out (sum, not mean) may be NULL. */
+lkm_status lkm_lloyd_iters_f32(lkm_ctx* ctx, float* centroids_inout, uint64_t k, uint64_t max_iters,
+                               double tolerance, float* cluster_count_out, float* inertia_total_out,
+                               lkm_stats* stats_out);
+lkm_status lkm_lloyd_iters_f64(lkm_ctx* ctx, double* centroids_inout, uint64_t k, uint64_t max_iters,
+                               double tolerance, double* cluster_count_out, double* inertia_total_out,
+                               lkm_stats* stats_out);
+
+/* -- PredictInplace (KM/algorithm.rs:735-777) -> update_cluster_memberships
+ * (:838-849) and Transformer (:718-733) -> update_min_dists (:852-863).
+ * x == NULL means "the resident matrix" (n and d must match it). */
+lkm_status lkm_predict_f32(lkm_ctx* ctx, const float* centroids, uint64_t k, const float* x, uint64_t n,
+                           uint64_t d, int64_t row_stride, uint64_t* labels_out);
+lkm_status lkm_predict_f64(lkm_ctx* ctx, const double* centroids, uint64_t k, const double* x, uint64_t n,
+                           uint64_t d, int64_t row_stride, uint64_t* labels_out);
+lkm_status lkm_transform_f32(lkm_ctx* ctx, const float* centroids, uint64_t k, const float* x, uint64_t n,
+                             uint64_t d, int64_t row_stride, float* min_sq_dist_out);
+lkm_status lkm_transform_f64(lkm_ctx* ctx, const double* centroids, uint64_t k, const double* x, uint64_t n,
+                             uint64_t d, int64_t row_stride, double* min_sq_dist_out);
+/* update_memberships_and_dists (KM/algorithm.rs:866-881): both at once */
+lkm_status lkm_assign_f32(lkm_ctx* ctx, const float* centroids, uint64_t k, const float* x, uint64_t n,
+                          uint64_t d, int64_t row_stride, uint64_t* labels_out, float* min_sq_dist_out);
+lkm_status lkm_assign_f64(lkm_ctx* ctx, const double* centroids, uint64_t k, const double* x, uint64_t n,
+                          uint64_t d, int64_t row_stride, uint64_t* labels_out, double* min_sq_dist_out);
+
+/* -- FitWith::fit_with (KM/algorithm.rs:635-715): one mini-batch step on the
+ * resident matrix.  has_model = 0 initialises from params (best of n_runs
+ * seedings by dists.sum(), :659-678).  Returns LKM_OK when the shift is below
+ * tolerance, LKM_NOT_CONVERGED otherwise; outputs are written in both cases. */
+lkm_status lkm_fit_with_f32(lkm_ctx* ctx, const lkm_params* p, lkm_rng rng, int has_model,
+                            float* centroids_inout, float* cluster_count_inout, float* inertia_out);
+lkm_status lkm_fit_with_f64(lkm_ctx* ctx, const lkm_params* p, lkm_rng rng, int has_model,
+                            double* centroids_inout, double* cluster_count_inout, double* inertia_out);
+
+/* -- knobs that are not in the reference (all have defaults) --------------- */
+/* force an assignment path: -1 auto (default), 0 exact, 1 certified FMA, 2 tcgen05 */
+lkm_status lkm_set_assign_path(lkm_ctx* ctx, int path);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LKM_H */

@@ -1,0 +1,1016 @@
+// C ABI (include/lkm.h) and host side of the B200-native K-Means path.
+//
+// Host logic mirrors fit_lloyd / get_kmeans_result (KM/algorithm.rs:294-367),
+// KMeansInit::run (KM/init.rs:83-285) and the ParamGuard checks
+// (KM/hyperparams.rs:124-136); every floating-point operation on the data runs
+// in the CUDA kernels of lkm_kernels.cuh.  There is no CPU fallback: without a
+// CUDA device lkm_create fails with LKM_ERR_CUDA.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <string>
+#include <vector>
+
+#include "../../include/lkm.h"
+#include "lkm_kernels.cuh"
+#include "lkm_rand.hpp"
+
+#define LKM_EXPORT extern "C" __attribute__((visibility("default")))
+
+namespace lkm {
+
+// ---- NCCL through dlopen (only needed when world_size > 1) -----------------
+struct NcclUid { char internal[128]; };
+struct NcclApi {
+  void* handle = nullptr;
+  int (*GetUniqueId)(NcclUid*) = nullptr;
+  int (*CommInitRank)(void**, int, NcclUid, int) = nullptr;
+  int (*CommDestroy)(void*) = nullptr;
+  int (*AllGather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+  bool load(std::string& err) {
+    if (handle) return true;
+    const char* names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char* nm : names) {
+      handle = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+      if (handle) break;
+    }
+    if (!handle) { err = std::string("dlopen libnccl failed: ") + dlerror(); return false; }
+    GetUniqueId = (decltype(GetUniqueId))dlsym(handle, "ncclGetUniqueId");
+    CommInitRank = (decltype(CommInitRank))dlsym(handle, "ncclCommInitRank");
+    CommDestroy = (decltype(CommDestroy))dlsym(handle, "ncclCommDestroy");
+    AllGather = (decltype(AllGather))dlsym(handle, "ncclAllGather");
+    GetErrorString = (decltype(GetErrorString))dlsym(handle, "ncclGetErrorString");
+    if (!GetUniqueId || !CommInitRank || !CommDestroy || !AllGather) { err = "libnccl lacks required symbols"; return false; }
+    return true;
+  }
+};
+static NcclApi g_nccl;
+constexpr int kNcclFloat64 = 8, kNcclUint64 = 5, kNcclInt8 = 0;
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaError_t ensure(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr; cap = 0;
+    cudaError_t e = cudaMalloc(&p, bytes);
+    if (e == cudaSuccess) cap = bytes;
+    return e;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+  template <class T> T* as() { return reinterpret_cast<T*>(p); }
+};
+
+}  // namespace lkm
+
+using namespace lkm;
+
+struct lkm_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  std::string err;
+  int sm_count = 148;
+  size_t smem_optin = 227 * 1024;
+  // resident observations
+  int elem = 0;  // 0 none, 4 f32, 8 f64
+  void* X = nullptr;
+  bool own_X = false;
+  DevBuf xbuf;
+  uint64_t n = 0, d = 0;
+  uint64_t row_offset = 0, n_global = 0;
+  int force_path = -1;
+  // workspaces
+  DevBuf cbuf, part_sums, part_counts, part_inertia, shift_part, counts_out, state, gather, labels, dists, wdists,
+      cum, scratch, tmpx, tmpc, idxbuf, bsum, weights;
+  LloydState* h_state = nullptr;  // pinned
+  double* h_pin = nullptr;        // pinned scratch (>= 4096 doubles)
+  // comm
+  void* comm = nullptr;
+  int rank = 0, world = 1;
+  uint32_t launches = 0;
+};
+
+namespace lkm {
+
+#define CK(call)                                                                                      \
+  do {                                                                                                \
+    cudaError_t e__ = (call);                                                                         \
+    if (e__ != cudaSuccess) {                                                                         \
+      ctx->err = std::string(#call) + ": " + cudaGetErrorString(e__);                                 \
+      return LKM_ERR_CUDA;                                                                            \
+    }                                                                                                 \
+  } while (0)
+#define CKN(call)                                                                                     \
+  do {                                                                                                \
+    int r__ = (call);                                                                                 \
+    if (r__ != 0) {                                                                                   \
+      ctx->err = std::string(#call) + ": " + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r__) : "nccl error"); \
+      return LKM_ERR_NCCL;                                                                            \
+    }                                                                                                 \
+  } while (0)
+#define CKS(call)                                                                                     \
+  do {                                                                                                \
+    lkm_status s__ = (call);                                                                          \
+    if (s__ != LKM_OK) return s__;                                                                    \
+  } while (0)
+
+static lkm_status fail(lkm_ctx* ctx, lkm_status s, const char* msg) {
+  ctx->err = msg;
+  return s;
+}
+
+// ---- launch helpers ----------------------------------------------------------
+struct Plan {
+  bool ok = false;
+  int vec = 0, x_stride = 0;
+  size_t tile_bytes = 0;
+  // fused
+  bool fused = false;
+  int n_subsets = 1, kc = 0;
+  size_t smem = 0;
+  int grid = 0;
+};
+
+template <typename F> static void tile_layout(uint64_t d, const void* X, int& vec, int& x_stride, size_t& tile_bytes) {
+  const size_t rowbytes = d * sizeof(F);
+  vec = (rowbytes % 16 == 0) && ((reinterpret_cast<uintptr_t>(X) & 15) == 0);
+  size_t stride_bytes;
+  if (vec) stride_bytes = ((rowbytes / 16) % 2 == 1) ? rowbytes : rowbytes + 16;
+  else stride_bytes = (size_t)(d | 1) * sizeof(F);
+  x_stride = (int)(stride_bytes / sizeof(F));
+  tile_bytes = std::max<size_t>((size_t)kThreads * stride_bytes, 2048);
+  tile_bytes = (tile_bytes + 15) & ~(size_t)15;
+}
+
+static size_t al16(size_t x) { return (x + 15) & ~(size_t)15; }
+
+template <typename F, int D, int MODE>
+static cudaError_t launch_lloyd_t(const LloydArgs<F>& a, int grid, size_t smem, cudaStream_t s) {
+  static size_t configured = 0;
+  if (smem > configured) {
+    cudaError_t e = cudaFuncSetAttribute(lloyd_kernel<F, D, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    configured = smem;
+  }
+  lloyd_kernel<F, D, MODE><<<grid, kThreads, smem, s>>>(a);
+  return cudaGetLastError();
+}
+template <typename F, int D, int MODE> static int occupancy_t(size_t smem) {
+  int nb = 0;
+  cudaFuncSetAttribute(lloyd_kernel<F, D, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, lloyd_kernel<F, D, MODE>, kThreads, smem);
+  return nb;
+}
+#define LKM_DISPATCH_D(d, CALL)          \
+  switch (d) {                           \
+    case 2: { constexpr int DD = 2; CALL; } break;   \
+    case 3: { constexpr int DD = 3; CALL; } break;   \
+    case 4: { constexpr int DD = 4; CALL; } break;   \
+    case 8: { constexpr int DD = 8; CALL; } break;   \
+    case 16: { constexpr int DD = 16; CALL; } break; \
+    case 32: { constexpr int DD = 32; CALL; } break; \
+    default: { constexpr int DD = 0; CALL; } break;  \
+  }
+
+template <typename F, int MODE>
+static cudaError_t launch_lloyd(const LloydArgs<F>& a, int grid, size_t smem, cudaStream_t s) {
+  cudaError_t e = cudaSuccess;
+  LKM_DISPATCH_D(a.d, (e = launch_lloyd_t<F, DD, MODE>(a, grid, smem, s)));
+  return e;
+}
+template <typename F, int MODE> static int occupancy(int d, size_t smem) {
+  int nb = 0;
+  LKM_DISPATCH_D(d, (nb = occupancy_t<F, DD, MODE>(smem)));
+  return nb;
+}
+
+// smem plan for MODE_ASSIGN (assignment only; centroids chunked over k if needed)
+template <typename F> static lkm_status plan_assign(lkm_ctx* ctx, const void* X, uint64_t n, uint64_t d, uint64_t k, Plan& p) {
+  tile_layout<F>(d, X, p.vec, p.x_stride, p.tile_bytes);
+  const size_t limit = ctx->smem_optin - 1024;
+  if (p.tile_bytes + al16(d * sizeof(F)) > limit) return fail(ctx, LKM_ERR_UNSUPPORTED, "row too wide for the shared-memory tile");
+  const size_t c_budget = std::min<size_t>(limit - p.tile_bytes, 96 * 1024);
+  uint64_t kc = std::min<uint64_t>(k, c_budget / (d * sizeof(F)));
+  if (kc == 0) return fail(ctx, LKM_ERR_UNSUPPORTED, "row too wide for the shared-memory tile");
+  p.kc = (int)kc;
+  p.smem = al16(kc * d * sizeof(F)) + p.tile_bytes;
+  const uint64_t n_tiles = (n + kThreads - 1) / kThreads;
+  const int occ = std::max(1, occupancy<F, MODE_ASSIGN>((int)d, p.smem));
+  p.grid = (int)std::min<uint64_t>(std::max<uint64_t>(n_tiles, 1), (uint64_t)ctx->sm_count * occ);
+  p.ok = true;
+  return LKM_OK;
+}
+
+// smem plan for the fused iteration (assignment + accumulation in one pass);
+// p.fused = false means "does not fit: use assign + chunked update passes".
+template <typename F> static lkm_status plan_fused(lkm_ctx* ctx, const void* X, uint64_t n, uint64_t d, uint64_t k, Plan& p) {
+  tile_layout<F>(d, X, p.vec, p.x_stride, p.tile_bytes);
+  const size_t limit = ctx->smem_optin - 1024;
+  const size_t kdF = k * d * sizeof(F);
+  const size_t fixed = p.tile_bytes + al16(kdF) + al16(k * 4) + kThreads * 4 + 64;
+  p.fused = fixed + al16(kdF) <= limit;
+  if (!p.fused) return LKM_OK;
+  int subsets = d <= (uint64_t)kThreads ? (int)(kThreads / d) : 1;
+  // keep the accumulator copies within ~48 KB (or one copy if a single one is larger)
+  const size_t per = al16(kdF) + al16(k * 4);
+  subsets = (int)std::max<size_t>(1, std::min<size_t>(subsets, (48 * 1024) / std::max<size_t>(per, 1)));
+  while (subsets > 1 && fixed + (size_t)subsets * per > limit) --subsets;
+  p.n_subsets = subsets;
+  p.kc = (int)k;
+  p.smem = al16(kdF) + p.tile_bytes + al16((size_t)subsets * kdF) + al16((size_t)subsets * k * 4) + kThreads * 4;
+  const uint64_t n_tiles = (n + kThreads - 1) / kThreads;
+  const int occ = std::max(1, occupancy<F, MODE_FUSED>((int)d, p.smem));
+  p.grid = (int)std::min<uint64_t>(std::max<uint64_t>(n_tiles, 1), (uint64_t)ctx->sm_count * occ);
+  p.ok = true;
+  return LKM_OK;
+}
+
+template <typename F>
+static lkm_status run_assign(lkm_ctx* ctx, const F* dX, uint64_t n, uint64_t d, const F* dC, uint64_t k, uint32_t* labels,
+                             F* dists, int min_combine, const F* weights, F* wdists) {
+  if (n == 0) return LKM_OK;
+  Plan p;
+  CKS(plan_assign<F>(ctx, dX, n, d, k, p));
+  LloydArgs<F> a{};
+  a.X = dX; a.n = n; a.d = (int)d; a.k = (int)k; a.C = dC;
+  a.labels = labels; a.dists = dists; a.min_combine = min_combine; a.weights = weights; a.wdists = wdists;
+  a.n_subsets = 1; a.x_stride = p.x_stride; a.kc = p.kc; a.chunk_base = 0; a.chunk_rows = (int)k; a.vec = p.vec;
+  CK((launch_lloyd<F, MODE_ASSIGN>(a, p.grid, p.smem, ctx->stream)));
+  ctx->launches++;
+  return LKM_OK;
+}
+
+template <typename F, typename S, typename CT, bool UPDATE>
+static cudaError_t launch_finalize(const FinalizeArgs<F, S, CT>& a, cudaStream_t s) {
+  const int grid = (a.k * a.d + kFinElems - 1) / kFinElems;
+  finalize_kernel<F, S, CT, UPDATE><<<grid, 256, 0, s>>>(a);
+  return cudaGetLastError();
+}
+
+struct LloydOut {
+  uint64_t n_iter = 0;
+  double inertia = 0, shift = 0;
+  float ms = 0;
+  int final_buf = 0;
+};
+
+// The loop of fit_lloyd (KM/algorithm.rs:314-331) on the device.  dC2 is a
+// double buffer [2][k*d]; iteration i reads buffer i&1 and writes (i+1)&1.
+// Kernels become no-ops once the device-side `done` flag is set; the host
+// polls the flag once per batch of iterations.
+template <typename F>
+static lkm_status run_lloyd(lkm_ctx* ctx, F* dC2, uint64_t k, uint64_t max_iter, double tol, LloydOut& out) {
+  const uint64_t n = ctx->n, d = ctx->d, kd = k * d;
+  const F* dX = reinterpret_cast<const F*>(ctx->X);
+  if (kd > (uint64_t)std::numeric_limits<int>::max() / 4) return fail(ctx, LKM_ERR_UNSUPPORTED, "k*d too large");
+  Plan pf;
+  CKS(plan_fused<F>(ctx, dX, n, d, k, pf));
+  Plan pa, pu;
+  int n_chunks = 1, chunk_rows = (int)k;
+  if (!pf.fused) {
+    CKS(plan_assign<F>(ctx, dX, n, d, k, pa));
+    // update pass: tile + one accumulator copy for a cluster chunk
+    pu = pa;
+    const size_t limit = ctx->smem_optin - 1024;
+    const size_t avail = limit - pu.tile_bytes - kThreads * 4 - 64;
+    uint64_t cr = std::min<uint64_t>(k, avail / (d * sizeof(F) + 4 + 1));
+    if (cr == 0) return fail(ctx, LKM_ERR_UNSUPPORTED, "row too wide for the update pass");
+    chunk_rows = (int)cr;
+    n_chunks = (int)((k + cr - 1) / cr);
+    pu.n_subsets = 1;
+    pu.smem = pu.tile_bytes + al16(cr * d * sizeof(F)) + al16(cr * 4) + kThreads * 4;
+    const uint64_t n_tiles = (n + kThreads - 1) / kThreads;
+    const int occ = std::max(1, occupancy<F, MODE_UPDATE>((int)d, pu.smem));
+    pu.grid = (int)std::min<uint64_t>(std::max<uint64_t>(n_tiles, 1), (uint64_t)ctx->sm_count * occ);
+    CK(ctx->labels.ensure(std::max<uint64_t>(n, 1) * 4));
+    CK(ctx->dists.ensure(std::max<uint64_t>(n, 1) * sizeof(F)));
+  }
+  const int grid = pf.fused ? pf.grid : pu.grid;
+  CK(ctx->part_sums.ensure((size_t)grid * kd * sizeof(F)));
+  CK(ctx->part_counts.ensure((size_t)grid * k * 4));
+  CK(ctx->part_inertia.ensure((size_t)std::max(grid, 1024) * 8));
+  const int fin_grid = (int)((kd + kFinElems - 1) / kFinElems);
+  CK(ctx->shift_part.ensure((size_t)fin_grid * 8));
+  CK(ctx->counts_out.ensure(k * 8));
+  CK(ctx->state.ensure(sizeof(LloydState)));
+  const size_t L = kd + k + 1;
+  if (ctx->world > 1) CK(ctx->gather.ensure((size_t)ctx->world * L * 8));
+  LloydState* dstate = ctx->state.as<LloydState>();
+  CK(cudaMemsetAsync(dstate, 0, sizeof(LloydState), ctx->stream));
+  CK(cudaEventRecord(ctx->ev0, ctx->stream));
+
+  uint64_t launched = 0;
+  const uint64_t batch = 16;
+  for (;;) {
+    const uint64_t todo = std::min<uint64_t>(batch, max_iter - launched);
+    for (uint64_t q = 0; q < todo; ++q) {
+      const uint64_t it = launched + q;
+      const F* Ccur = dC2 + (it & 1) * kd;
+      F* Cnext = dC2 + ((it + 1) & 1) * kd;
+      if (pf.fused) {
+        LloydArgs<F> a{};
+        a.X = dX; a.n = n; a.d = (int)d; a.k = (int)k; a.C = Ccur;
+        a.part_sums = ctx->part_sums.as<F>(); a.part_counts = ctx->part_counts.as<uint32_t>();
+        a.part_inertia = ctx->part_inertia.as<double>(); a.state = dstate;
+        a.n_subsets = pf.n_subsets; a.x_stride = pf.x_stride; a.kc = pf.kc; a.chunk_base = 0; a.chunk_rows = (int)k;
+        a.vec = pf.vec;
+        CK((launch_lloyd<F, MODE_FUSED>(a, pf.grid, pf.smem, ctx->stream)));
+        ctx->launches++;
+      } else {
+        LloydArgs<F> a{};
+        a.X = dX; a.n = n; a.d = (int)d; a.k = (int)k; a.C = Ccur;
+        a.labels = ctx->labels.as<uint32_t>(); a.dists = ctx->dists.as<F>(); a.state = dstate;
+        a.n_subsets = 1; a.x_stride = pa.x_stride; a.kc = pa.kc; a.chunk_rows = (int)k; a.vec = pa.vec;
+        CK((launch_lloyd<F, MODE_ASSIGN>(a, pa.grid, pa.smem, ctx->stream)));
+        // inertia: fixed-order f64 partial sums of the min distances, one per source slot
+        sum_f64_kernel<F><<<grid, 256, 0, ctx->stream>>>(ctx->dists.as<F>(), n, ctx->part_inertia.as<double>());
+        CK(cudaGetLastError());
+        ctx->launches += 2;
+        for (int ch = 0; ch < n_chunks; ++ch) {
+          LloydArgs<F> u{};
+          u.X = dX; u.n = n; u.d = (int)d; u.k = (int)k; u.labels_in = ctx->labels.as<uint32_t>();
+          u.chunk_base = ch * chunk_rows;
+          u.chunk_rows = (int)std::min<uint64_t>(chunk_rows, k - (uint64_t)ch * chunk_rows);
+          u.part_sums = ctx->part_sums.as<F>(); u.part_counts = ctx->part_counts.as<uint32_t>();
+          u.state = dstate; u.n_subsets = 1; u.x_stride = pu.x_stride; u.vec = pu.vec;
+          CK((launch_lloyd<F, MODE_UPDATE>(u, pu.grid, pu.smem, ctx->stream)));
+          ctx->launches++;
+        }
+      }
+      // combine the per-CTA partials in fixed order, then the m_k-means update
+      if (ctx->world == 1) {
+        FinalizeArgs<F, F, uint32_t> fa{};
+        fa.src_sums = ctx->part_sums.as<F>(); fa.src_counts = ctx->part_counts.as<uint32_t>();
+        fa.src_inertia = ctx->part_inertia.as<double>();
+        fa.sum_stride = kd; fa.cnt_stride = k; fa.inertia_stride = 1; fa.n_src = grid; fa.k = (int)k; fa.d = (int)d;
+        fa.C_old = Ccur; fa.C_new = Cnext; fa.counts_out = ctx->counts_out.as<double>();
+        fa.shift_part = ctx->shift_part.as<double>(); fa.state = dstate; fa.tol = tol; fa.max_iter = max_iter;
+        CK((launch_finalize<F, F, uint32_t, true>(fa, ctx->stream)));
+        ctx->launches++;
+      } else {
+        FinalizeArgs<F, F, uint32_t> ra{};
+        ra.src_sums = ctx->part_sums.as<F>(); ra.src_counts = ctx->part_counts.as<uint32_t>();
+        ra.src_inertia = ctx->part_inertia.as<double>();
+        ra.sum_stride = kd; ra.cnt_stride = k; ra.inertia_stride = 1; ra.n_src = grid; ra.k = (int)k; ra.d = (int)d;
+        ra.rank_out = ctx->gather.as<double>() + (size_t)ctx->rank * L;
+        ra.state = dstate;
+        CK((launch_finalize<F, F, uint32_t, false>(ra, ctx->stream)));
+        CKN(g_nccl.AllGather(ctx->gather.as<double>() + (size_t)ctx->rank * L, ctx->gather.as<double>(), L, kNcclFloat64,
+                             ctx->comm, ctx->stream));
+        FinalizeArgs<F, double, double> fa{};
+        fa.src_sums = ctx->gather.as<double>(); fa.src_counts = ctx->gather.as<double>() + kd;
+        fa.src_inertia = ctx->gather.as<double>() + kd + k;
+        fa.sum_stride = L; fa.cnt_stride = L; fa.inertia_stride = L; fa.n_src = ctx->world; fa.k = (int)k; fa.d = (int)d;
+        fa.C_old = Ccur; fa.C_new = Cnext; fa.counts_out = ctx->counts_out.as<double>();
+        fa.shift_part = ctx->shift_part.as<double>(); fa.state = dstate; fa.tol = tol; fa.max_iter = max_iter;
+        CK((launch_finalize<F, double, double, true>(fa, ctx->stream)));
+        ctx->launches += 3;
+      }
+    }
+    launched += todo;
+    CK(cudaMemcpyAsync(ctx->h_state, dstate, sizeof(LloydState), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (ctx->h_state->done || launched >= max_iter) break;
+  }
+  CK(cudaEventRecord(ctx->ev1, ctx->stream));
+  CK(cudaEventSynchronize(ctx->ev1));
+  CK(cudaEventElapsedTime(&out.ms, ctx->ev0, ctx->ev1));
+  out.n_iter = ctx->h_state->n_iter;
+  out.inertia = ctx->h_state->inertia;
+  out.shift = ctx->h_state->shift;
+  out.final_buf = (int)(out.n_iter & 1);
+  return LKM_OK;
+}
+
+// ---- seeding ---------------------------------------------------------------------
+template <typename F>
+static lkm_status gather_rows(lkm_ctx* ctx, const F* dX, uint64_t d, const std::vector<long long>& idx, F* dOut) {
+  const size_t k = idx.size();
+  CK(ctx->idxbuf.ensure(k * 8));
+  CK(cudaMemcpyAsync(ctx->idxbuf.p, idx.data(), k * 8, cudaMemcpyHostToDevice, ctx->stream));
+  gather_rows_kernel<F><<<(int)std::min<size_t>(k, 1024), 128, 0, ctx->stream>>>(dX, (int)d, ctx->idxbuf.as<long long>(),
+                                                                                  (int)k, dOut);
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(ctx->stream));  // idx (host vector) must outlive the copy
+  ctx->launches++;
+  return LKM_OK;
+}
+
+// WeightedIndex::new(w).sample(rng) on device-resident weights (rand 0.8.5):
+// returns the picked index, or -1 where WeightedIndex::new errors.
+template <typename F>
+static lkm_status weighted_pick(lkm_ctx* ctx, const F* dW, uint64_t n, HostRng& rng, int pick_mode, long long& picked) {
+  if (n == 0) { picked = -1; return LKM_OK; }
+  if (pick_mode == LKM_PICK_EXACT) {
+    CK(ctx->cum.ensure(std::max<uint64_t>(n, 2) * sizeof(F)));
+    CK(ctx->scratch.ensure(64));
+    seq_prefix_kernel<F><<<1, 256, 0, ctx->stream>>>(dW, n, ctx->cum.as<F>(), ctx->scratch.as<F>());
+    CK(cudaGetLastError());
+    F tot[2];
+    CK(cudaMemcpyAsync(tot, ctx->scratch.p, 2 * sizeof(F), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->launches++;
+    if (tot[1] != (F)0 || !(tot[0] >= (F)0)) { picked = -1; return LKM_OK; }  // InvalidWeight
+    if (tot[0] == (F)0) { picked = -1; return LKM_OK; }                       // AllWeightsZero
+    const F chosen = weighted_threshold<F>(rng, tot[0]);
+    unsigned long long* dcnt = reinterpret_cast<unsigned long long*>(ctx->scratch.as<char>() + 32);
+    CK(cudaMemsetAsync(dcnt, 0, 8, ctx->stream));
+    if (n > 1) {
+      count_le_kernel<F><<<(int)std::min<uint64_t>((n + 255) / 256, 2048), 256, 0, ctx->stream>>>(ctx->cum.as<F>(), n - 1,
+                                                                                                   chosen, dcnt);
+      CK(cudaGetLastError());
+      ctx->launches++;
+    }
+    unsigned long long cnt = 0;
+    CK(cudaMemcpyAsync(&cnt, dcnt, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    picked = (long long)cnt;
+    return LKM_OK;
+  }
+  // FAST: fixed-order f64 block sums + single-CTA walk, same uniform draw
+  const uint64_t nb = (n + kPickBlock - 1) / kPickBlock;
+  CK(ctx->bsum.ensure(nb * 8));
+  CK(ctx->scratch.ensure(64));
+  block_sums_kernel<F><<<(int)std::min<uint64_t>(nb, 4096), 256, 0, ctx->stream>>>(dW, n, ctx->bsum.as<double>());
+  CK(cudaGetLastError());
+  // total (host walks the block sums: nb doubles, tiny next to n)
+  std::vector<double> hb(nb);
+  CK(cudaMemcpyAsync(hb.data(), ctx->bsum.p, nb * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  double total = 0.0;
+  for (uint64_t b = 0; b < nb; ++b) total += hb[b];
+  ctx->launches++;
+  if (!(total > 0.0)) { picked = -1; return LKM_OK; }
+  const F u01 = unit<F>(rng);
+  long long* didx = reinterpret_cast<long long*>(ctx->scratch.as<char>() + 48);
+  fast_pick_kernel<F><<<1, 256, 0, ctx->stream>>>(dW, n, ctx->bsum.as<double>(), 0.0, total, u01, didx);
+  CK(cudaGetLastError());
+  ctx->launches++;
+  CK(cudaMemcpyAsync(&picked, didx, 8, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  if (picked < 0) picked = (long long)n - 1;
+  return LKM_OK;
+}
+
+// weighted_k_means_plusplus (KM/init.rs:118-158) over device rows dX (n x d)
+// with optional device weights (null = ones).  The min-distance array is kept
+// as a running minimum over the centroids chosen so far — the same value the
+// reference recomputes from scratch each round (:138-143), since a minimum
+// does not depend on evaluation order.
+template <typename F>
+static lkm_status weighted_kmeanspp(lkm_ctx* ctx, const F* dX, uint64_t n, uint64_t d, const F* dW, uint64_t k,
+                                    HostRng& rng, int pick_mode, F* dC) {
+  CK(ctx->dists.ensure(std::max<uint64_t>(n, 1) * sizeof(F)));
+  CK(ctx->wdists.ensure(std::max<uint64_t>(n, 1) * sizeof(F)));
+  F* dD = ctx->dists.as<F>();
+  F* dWD = ctx->wdists.as<F>();
+  const F* first_w = dW;
+  if (!dW) {
+    // weights = ones: materialise them once so that the first pick walks the
+    // same F prefix sum 1, 2, 3, ... WeightedIndex::new builds
+    CK(ctx->weights.ensure(std::max<uint64_t>(n, 1) * sizeof(F)));
+    std::vector<F> ones(std::min<uint64_t>(n, 1 << 20), (F)1);
+    for (uint64_t o = 0; o < n; o += ones.size())
+      CK(cudaMemcpyAsync(ctx->weights.as<F>() + o, ones.data(), std::min<uint64_t>(ones.size(), n - o) * sizeof(F),
+                         cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    first_w = ctx->weights.as<F>();
+  } else {
+    // assert_ne!(weights.sum(), 0) (KM/init.rs:127): all weights are >= 0 here, so
+    // the sum is zero iff every weight is zero; the pick below reports that case.
+  }
+  long long idx = -1;
+  CKS(weighted_pick<F>(ctx, first_w, n, rng, pick_mode, idx));
+  if (idx < 0) return fail(ctx, dW ? LKM_ERR_ZERO_WEIGHTS : LKM_ERR_BAD_WEIGHTS, "invalid weights for k-means++");
+  CK(cudaMemcpyAsync(dC, dX + (size_t)idx * d, d * sizeof(F), cudaMemcpyDeviceToDevice, ctx->stream));
+  for (uint64_t c = 1; c < k; ++c) {
+    CKS(run_assign<F>(ctx, dX, n, d, dC + (c - 1) * d, 1, nullptr, dD, c > 1 ? 1 : 0, dW, dWD));
+    CKS(weighted_pick<F>(ctx, dWD, n, rng, pick_mode, idx));
+    if (idx < 0) idx = 0;  // .unwrap_or(0) (KM/init.rs:149-152)
+    CK(cudaMemcpyAsync(dC + c * d, dX + (size_t)idx * d, d * sizeof(F), cudaMemcpyDeviceToDevice, ctx->stream));
+  }
+  return LKM_OK;
+}
+
+// k_means_para (KM/init.rs:181-234).  The reference's per-row Bernoulli draws
+// come from rayon-split Xoshiro streams and are not reproducible even there;
+// here each row draws from a counter-based generator keyed by (round seed, row).
+template <typename F>
+static lkm_status kmeans_para(lkm_ctx* ctx, const F* dX, uint64_t n, uint64_t d, uint64_t k, HostRng& rng, int pick_mode,
+                              F* dC) {
+  const uint64_t n_rounds = 8, cap = k * n_rounds;
+  CK(ctx->tmpc.ensure(cap * d * sizeof(F)));
+  F* dCand = ctx->tmpc.as<F>();
+  CK(ctx->dists.ensure(std::max<uint64_t>(n, 1) * sizeof(F)));
+  F* dD = ctx->dists.as<F>();
+  const uint64_t first = range_incl_u64(rng, 0, n - 1);
+  CK(cudaMemcpyAsync(dCand, dX + first * d, d * sizeof(F), cudaMemcpyDeviceToDevice, ctx->stream));
+  uint64_t n_cand = 1, scanned = 0;
+  const unsigned int sel_cap = (unsigned int)std::min<uint64_t>(std::max<uint64_t>(16 * k + 1024, 4096), 1u << 24);
+  CK(ctx->idxbuf.ensure((size_t)sel_cap * 8 + 64));
+  CK(ctx->part_inertia.ensure(1024 * 8));
+  bool full = false;
+  std::vector<unsigned long long> sel;
+  std::vector<double> parts(1024);
+  for (uint64_t r = 0; r < n_rounds && !full; ++r) {
+    // running min against the candidates added since the last round
+    CKS(run_assign<F>(ctx, dX, n, d, dCand + scanned * d, n_cand - scanned, nullptr, dD, scanned > 0 ? 1 : 0, nullptr, nullptr));
+    scanned = n_cand;
+    const uint64_t seed = range_incl_u64(rng, 0, 0xFFFFFFFFFFFFFFFEULL);
+    sum_f64_kernel<F><<<1024, 256, 0, ctx->stream>>>(dD, n, ctx->part_inertia.as<double>());
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(parts.data(), ctx->part_inertia.p, 1024 * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    double cost = 0.0;
+    for (double v : parts) cost += v;
+    unsigned int* dcur = reinterpret_cast<unsigned int*>(ctx->idxbuf.as<char>() + (size_t)sel_cap * 8);
+    CK(cudaMemsetAsync(dcur, 0, 4, ctx->stream));
+    bernoulli_select_kernel<F><<<(int)std::min<uint64_t>((n + 255) / 256, 4096), 256, 0, ctx->stream>>>(
+        dD, n, (F)k, (F)cost, seed, 0ULL, ctx->idxbuf.as<unsigned long long>(), sel_cap, dcur);
+    CK(cudaGetLastError());
+    ctx->launches += 2;
+    unsigned int got = 0;
+    CK(cudaMemcpyAsync(&got, dcur, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    got = std::min(got, sel_cap);
+    sel.resize(got);
+    if (got) CK(cudaMemcpy(sel.data(), ctx->idxbuf.p, (size_t)got * 8, cudaMemcpyDeviceToHost));
+    std::sort(sel.begin(), sel.end());  // the reference collects in ascending row order
+    for (unsigned long long idx : sel) {
+      CK(cudaMemcpyAsync(dCand + n_cand * d, dX + idx * d, d * sizeof(F), cudaMemcpyDeviceToDevice, ctx->stream));
+      n_cand += 1;
+      if (n_cand >= cap) { full = true; break; }
+    }
+  }
+  // weights = cluster_membership_counts (KM/init.rs:273-285): histogram of the
+  // nearest candidate over all rows
+  CK(ctx->labels.ensure(std::max<uint64_t>(n, 1) * 4));
+  CKS(run_assign<F>(ctx, dX, n, d, dCand, n_cand, ctx->labels.as<uint32_t>(), nullptr, 0, nullptr, nullptr));
+  CK(ctx->tmpx.ensure(n_cand * sizeof(F) + n_cand * 4 + 64));
+  unsigned int* dhist = reinterpret_cast<unsigned int*>(ctx->tmpx.as<char>() + ((n_cand * sizeof(F) + 15) & ~(size_t)15));
+  CK(cudaMemsetAsync(dhist, 0, n_cand * 4, ctx->stream));
+  label_hist_kernel<<<(int)std::min<uint64_t>((n + 255) / 256, 4096), 256, 0, ctx->stream>>>(ctx->labels.as<uint32_t>(), n, dhist);
+  CK(cudaGetLastError());
+  u32_to_float_kernel<F><<<(int)((n_cand + 255) / 256), 256, 0, ctx->stream>>>(dhist, (int)n_cand, ctx->tmpx.as<F>());
+  CK(cudaGetLastError());
+  ctx->launches += 2;
+  // weighted k-means++ over the candidates; its scratch arrays are sized for
+  // n_cand <= n rows, and the candidate weights live in tmpx
+  return weighted_kmeanspp<F>(ctx, dCand, n_cand, d, ctx->tmpx.as<F>(), k, rng, pick_mode, dC);
+}
+
+// KMeansInit::run (KM/init.rs:83-101) -> device centroids dC (k x d)
+template <typename F>
+static lkm_status run_init(lkm_ctx* ctx, const lkm_params* p, HostRng& rng, F* dC) {
+  const uint64_t k = p->n_clusters, n = ctx->n, d = ctx->d;
+  const F* dX = reinterpret_cast<const F*>(ctx->X);
+  if (ctx->world > 1 && p->init_method != LKM_INIT_PRECOMPUTED)
+    return fail(ctx, LKM_ERR_UNSUPPORTED, "multi-GPU seeding is not implemented yet: use Precomputed centroids");
+  switch (p->init_method) {
+    case LKM_INIT_PRECOMPUTED:
+      if (!p->precomputed || p->precomputed_rows != k || p->precomputed_cols != d)
+        return fail(ctx, LKM_ERR_SHAPE, "Precomputed centroids must be n_clusters x n_features");
+      CK(cudaMemcpyAsync(dC, p->precomputed, k * d * sizeof(F), cudaMemcpyHostToDevice, ctx->stream));
+      CK(cudaStreamSynchronize(ctx->stream));
+      return LKM_OK;
+    case LKM_INIT_RANDOM: {
+      std::vector<uint64_t> idx;
+      if (!index_sample(rng, n, k, idx)) return fail(ctx, LKM_ERR_SAMPLE_AMOUNT, "Random init: n_clusters > n_samples");
+      std::vector<long long> li(idx.begin(), idx.end());
+      return gather_rows<F>(ctx, dX, d, li, dC);
+    }
+    case LKM_INIT_KMEANS_PLUSPLUS:
+      if (n == 0) return fail(ctx, LKM_ERR_BAD_WEIGHTS, "k-means++ on an empty dataset");
+      return weighted_kmeanspp<F>(ctx, dX, n, d, nullptr, k, rng, p->pick_mode, dC);
+    case LKM_INIT_KMEANS_PARA:
+      if (n == 0) return fail(ctx, LKM_ERR_BAD_WEIGHTS, "k-means|| on an empty dataset");
+      return kmeans_para<F>(ctx, dX, n, d, k, rng, p->pick_mode, dC);
+  }
+  return fail(ctx, LKM_ERR_INVALID_ARG, "unknown init_method");
+}
+
+static lkm_status check_params(lkm_ctx* ctx, const lkm_params* p, bool need_max_iter) {
+  // ParamGuard::check_ref (KM/hyperparams.rs:124-136), same order
+  if (p->n_clusters == 0) return fail(ctx, LKM_ERR_N_CLUSTERS, "n_clusters cannot be 0");
+  if (p->n_runs == 0) return fail(ctx, LKM_ERR_N_RUNS, "n_runs cannot be 0");
+  if (p->tolerance <= 0.0) return fail(ctx, LKM_ERR_TOLERANCE, "tolerance must be greater than 0");
+  if (need_max_iter && p->max_n_iterations == 0) return fail(ctx, LKM_ERR_MAX_ITERATIONS, "max_n_iterations cannot be 0");
+  return LKM_OK;
+}
+
+template <typename F>
+static lkm_status fit_impl(lkm_ctx* ctx, const lkm_params* p, lkm_rng rng_in, F* centroids_out, F* counts_out,
+                           F* inertia_out, lkm_stats* stats) {
+  if (!p || !centroids_out || !counts_out || !inertia_out) return fail(ctx, LKM_ERR_INVALID_ARG, "null argument");
+  CKS(check_params(ctx, p, true));
+  if (ctx->elem != (int)sizeof(F) || !ctx->X) return fail(ctx, LKM_ERR_NO_DATA, "no resident data of this type");
+  CK(cudaSetDevice(ctx->device));
+  const uint64_t k = p->n_clusters, d = ctx->d, kd = k * d;
+  const uint64_t n_glob = ctx->n_global ? ctx->n_global : ctx->n;
+  if (ctx->n == 0 || d == 0) return fail(ctx, LKM_ERR_SHAPE, "empty dataset");
+  HostRng rng{rng_in};
+  CK(ctx->cbuf.ensure(2 * kd * sizeof(F)));
+  F* dC2 = ctx->cbuf.as<F>();
+  ctx->launches = 0;
+  // F tolerance exactly as the reference holds it (tolerance: F)
+  const double tol = (double)(F)p->tolerance;
+  F min_inertia = std::numeric_limits<F>::infinity();
+  bool have = false;
+  std::vector<F> best(kd);
+  LloydOut lo;
+  float ms_total = 0;
+  for (uint64_t run = 0; run < p->n_runs; ++run) {
+    CKS(run_init<F>(ctx, p, rng, dC2));
+    CKS(run_lloyd<F>(ctx, dC2, k, p->max_n_iterations, tol, lo));
+    ms_total += lo.ms;
+    const F inertia = (F)lo.inertia;
+    if (inertia < min_inertia) {  // strict '<' from +inf: NaN never wins (KM/algorithm.rs:336)
+      min_inertia = inertia;
+      CK(cudaMemcpyAsync(best.data(), dC2 + (size_t)lo.final_buf * kd, kd * sizeof(F), cudaMemcpyDeviceToHost, ctx->stream));
+      CK(cudaStreamSynchronize(ctx->stream));
+      have = true;
+    }
+  }
+  if (stats) {
+    std::memset(stats, 0, sizeof(*stats));
+    stats->n_iter = lo.n_iter; stats->last_shift = lo.shift; stats->inertia_total = lo.inertia;
+    stats->device_ms = ms_total; stats->kernel_launches = ctx->launches; stats->assign_path = 0;
+  }
+  if (!have) return fail(ctx, LKM_ERR_INERTIA, "Fitting failed: No inertia improvement (-inf)");
+  // cluster_count from the LAST run's final assignment (KM/algorithm.rs:304,342,355-357)
+  std::vector<double> cnt(k);
+  CK(cudaMemcpyAsync(cnt.data(), ctx->counts_out.p, k * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  for (uint64_t c = 0; c < k; ++c) counts_out[c] = (F)cnt[c];
+  std::memcpy(centroids_out, best.data(), kd * sizeof(F));
+  *inertia_out = min_inertia / (F)n_glob;
+  return LKM_OK;
+}
+
+template <typename F>
+static lkm_status lloyd_iters_impl(lkm_ctx* ctx, F* centroids_inout, uint64_t k, uint64_t max_iters, double tolerance,
+                                   F* counts_out, F* inertia_total_out, lkm_stats* stats) {
+  if (!centroids_inout) return fail(ctx, LKM_ERR_INVALID_ARG, "null argument");
+  if (k == 0) return fail(ctx, LKM_ERR_N_CLUSTERS, "n_clusters cannot be 0");
+  if (tolerance <= 0.0) return fail(ctx, LKM_ERR_TOLERANCE, "tolerance must be greater than 0");
+  if (max_iters == 0) return fail(ctx, LKM_ERR_MAX_ITERATIONS, "max_n_iterations cannot be 0");
+  if (ctx->elem != (int)sizeof(F) || !ctx->X) return fail(ctx, LKM_ERR_NO_DATA, "no resident data of this type");
+  CK(cudaSetDevice(ctx->device));
+  const uint64_t kd = k * ctx->d;
+  CK(ctx->cbuf.ensure(2 * kd * sizeof(F)));
+  F* dC2 = ctx->cbuf.as<F>();
+  ctx->launches = 0;
+  CK(cudaMemcpyAsync(dC2, centroids_inout, kd * sizeof(F), cudaMemcpyHostToDevice, ctx->stream));
+  LloydOut lo;
+  CKS(run_lloyd<F>(ctx, dC2, k, max_iters, (double)(F)tolerance, lo));
+  CK(cudaMemcpyAsync(centroids_inout, dC2 + (size_t)lo.final_buf * kd, kd * sizeof(F), cudaMemcpyDeviceToHost, ctx->stream));
+  std::vector<double> cnt(k);
+  CK(cudaMemcpyAsync(cnt.data(), ctx->counts_out.p, k * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  if (counts_out) for (uint64_t c = 0; c < k; ++c) counts_out[c] = (F)cnt[c];
+  if (inertia_total_out) *inertia_total_out = (F)lo.inertia;
+  if (stats) {
+    std::memset(stats, 0, sizeof(*stats));
+    stats->n_iter = lo.n_iter; stats->last_shift = lo.shift; stats->inertia_total = lo.inertia;
+    stats->device_ms = lo.ms; stats->kernel_launches = ctx->launches; stats->assign_path = 0;
+  }
+  return LKM_OK;
+}
+
+// stage a host matrix (row stride in elements) as a contiguous device matrix
+template <typename F>
+static lkm_status upload(lkm_ctx* ctx, DevBuf& buf, const F* x, uint64_t n, uint64_t d, int64_t row_stride) {
+  CK(buf.ensure(std::max<uint64_t>(n * d, 1) * sizeof(F)));
+  if (n == 0 || d == 0) return LKM_OK;
+  if (row_stride == (int64_t)d) {
+    CK(cudaMemcpyAsync(buf.p, x, n * d * sizeof(F), cudaMemcpyHostToDevice, ctx->stream));
+  } else {
+    CK(cudaMemcpy2DAsync(buf.p, d * sizeof(F), x, (size_t)row_stride * sizeof(F), d * sizeof(F), n, cudaMemcpyHostToDevice,
+                         ctx->stream));
+  }
+  CK(cudaStreamSynchronize(ctx->stream));
+  return LKM_OK;
+}
+
+template <typename F>
+static lkm_status assign_impl(lkm_ctx* ctx, const F* centroids, uint64_t k, const F* x, uint64_t n, uint64_t d,
+                              int64_t row_stride, uint64_t* labels_out, F* dists_out) {
+  if (!centroids) return fail(ctx, LKM_ERR_INVALID_ARG, "null centroids");
+  if (k == 0) return fail(ctx, LKM_ERR_N_CLUSTERS, "n_clusters cannot be 0");
+  if (d == 0) return fail(ctx, LKM_ERR_SHAPE, "n_features cannot be 0");
+  CK(cudaSetDevice(ctx->device));
+  const F* dX;
+  if (x) {
+    if (row_stride < (int64_t)d) return fail(ctx, LKM_ERR_SHAPE, "row_stride < n_features");
+    CKS(upload<F>(ctx, ctx->tmpx, x, n, d, row_stride));
+    dX = ctx->tmpx.as<F>();
+  } else {
+    if (ctx->elem != (int)sizeof(F) || !ctx->X) return fail(ctx, LKM_ERR_NO_DATA, "no resident data of this type");
+    if (n != ctx->n || d != ctx->d) return fail(ctx, LKM_ERR_SHAPE, "shape differs from the resident matrix");
+    dX = reinterpret_cast<const F*>(ctx->X);
+  }
+  if (n == 0) return LKM_OK;
+  CK(ctx->tmpc.ensure(k * d * sizeof(F)));
+  CK(cudaMemcpyAsync(ctx->tmpc.p, centroids, k * d * sizeof(F), cudaMemcpyHostToDevice, ctx->stream));
+  uint32_t* dl = nullptr;
+  F* dd = nullptr;
+  if (labels_out) { CK(ctx->labels.ensure(n * 4)); dl = ctx->labels.as<uint32_t>(); }
+  if (dists_out) { CK(ctx->dists.ensure(n * sizeof(F))); dd = ctx->dists.as<F>(); }
+  ctx->launches = 0;
+  CKS(run_assign<F>(ctx, dX, n, d, ctx->tmpc.as<F>(), k, dl, dd, 0, nullptr, nullptr));
+  if (dists_out) CK(cudaMemcpyAsync(dists_out, dd, n * sizeof(F), cudaMemcpyDeviceToHost, ctx->stream));
+  if (labels_out) {
+    // usize labels on the host (Array1<usize>); u32 on the device
+    std::vector<uint32_t> tmp(n);
+    CK(cudaMemcpyAsync(tmp.data(), dl, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    for (uint64_t i = 0; i < n; ++i) labels_out[i] = tmp[i];
+  }
+  CK(cudaStreamSynchronize(ctx->stream));
+  return LKM_OK;
+}
+
+template <typename F>
+static lkm_status set_data_impl(lkm_ctx* ctx, const F* x, uint64_t n, uint64_t d, int64_t row_stride) {
+  if ((!x && n) || d == 0) return fail(ctx, LKM_ERR_INVALID_ARG, "null data or zero features");
+  if (row_stride < (int64_t)d) return fail(ctx, LKM_ERR_SHAPE, "row_stride < n_features");
+  CK(cudaSetDevice(ctx->device));
+  CKS(upload<F>(ctx, ctx->xbuf, x, n, d, row_stride));
+  ctx->X = ctx->xbuf.p; ctx->own_X = true; ctx->n = n; ctx->d = d; ctx->elem = (int)sizeof(F);
+  if (ctx->world == 1) { ctx->row_offset = 0; ctx->n_global = n; }
+  return LKM_OK;
+}
+
+template <typename F>
+static lkm_status gen_blobs_impl(lkm_ctx* ctx, uint64_t n, uint64_t d, uint64_t n_blobs, const F* centres, F sigma,
+                                 uint64_t seed, uint64_t row_offset, uint64_t n_global) {
+  if (!centres || n_blobs == 0 || d == 0) return fail(ctx, LKM_ERR_INVALID_ARG, "bad blob description");
+  CK(cudaSetDevice(ctx->device));
+  CK(ctx->xbuf.ensure(std::max<uint64_t>(n * d, 1) * sizeof(F)));
+  CK(ctx->tmpc.ensure(n_blobs * d * sizeof(F)));
+  CK(cudaMemcpyAsync(ctx->tmpc.p, centres, n_blobs * d * sizeof(F), cudaMemcpyHostToDevice, ctx->stream));
+  if (n) {
+    gen_blobs_kernel<F><<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(ctx->xbuf.as<F>(), n, (int)d, n_blobs, ctx->tmpc.as<F>(),
+                                                                   sigma, seed, row_offset, n_global ? n_global : n);
+    CK(cudaGetLastError());
+  }
+  CK(cudaStreamSynchronize(ctx->stream));
+  ctx->X = ctx->xbuf.p; ctx->own_X = true; ctx->n = n; ctx->d = d; ctx->elem = (int)sizeof(F);
+  ctx->row_offset = row_offset; ctx->n_global = n_global ? n_global : n;
+  return LKM_OK;
+}
+
+template <typename F> static lkm_status get_data_impl(lkm_ctx* ctx, uint64_t row0, uint64_t rows, F* out) {
+  if (ctx->elem != (int)sizeof(F) || !ctx->X) return fail(ctx, LKM_ERR_NO_DATA, "no resident data of this type");
+  if (row0 + rows > ctx->n) return fail(ctx, LKM_ERR_SHAPE, "row range outside the resident matrix");
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaMemcpyAsync(out, reinterpret_cast<const F*>(ctx->X) + row0 * ctx->d, rows * ctx->d * sizeof(F),
+                     cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return LKM_OK;
+}
+
+// FitWith::fit_with (KM/algorithm.rs:635-715)
+template <typename F>
+static lkm_status fit_with_impl(lkm_ctx* ctx, const lkm_params* p, lkm_rng rng_in, int has_model, F* C_inout,
+                                F* counts_inout, F* inertia_out) {
+  if (!p || !C_inout || !counts_inout || !inertia_out) return fail(ctx, LKM_ERR_INVALID_ARG, "null argument");
+  if (p->algorithm == LKM_ALGO_HAMERLY)
+    return fail(ctx, LKM_ERR_INCREMENTAL_HAMERLY, "only KMeansAlgorithm::Lloyd is supported by fit_with");
+  CKS(check_params(ctx, p, true));
+  if (ctx->elem != (int)sizeof(F) || !ctx->X) return fail(ctx, LKM_ERR_NO_DATA, "no resident data of this type");
+  if (ctx->world > 1) return fail(ctx, LKM_ERR_UNSUPPORTED, "fit_with is single-GPU");
+  CK(cudaSetDevice(ctx->device));
+  const uint64_t k = p->n_clusters, n = ctx->n, d = ctx->d, kd = k * d;
+  const F* dX = reinterpret_cast<const F*>(ctx->X);
+  HostRng rng{rng_in};
+  CK(ctx->cbuf.ensure(2 * kd * sizeof(F)));
+  F* dC = ctx->cbuf.as<F>();
+  CK(ctx->dists.ensure(std::max<uint64_t>(n, 1) * sizeof(F)));
+  CK(ctx->labels.ensure(std::max<uint64_t>(n, 1) * 4));
+  CK(ctx->part_inertia.ensure(1024 * 8));
+  std::vector<double> parts(1024);
+  auto dist_sum = [&](double& s) -> lkm_status {
+    sum_f64_kernel<F><<<1024, 256, 0, ctx->stream>>>(ctx->dists.as<F>(), n, ctx->part_inertia.as<double>());
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(parts.data(), ctx->part_inertia.p, 1024 * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    s = 0.0;
+    for (double v : parts) s += v;
+    return LKM_OK;
+  };
+  std::vector<F> hC(kd);
+  if (!has_model) {
+    if (p->init_method == LKM_INIT_PRECOMPUTED) {
+      if (!p->precomputed || p->precomputed_rows != k || p->precomputed_cols != d)
+        return fail(ctx, LKM_ERR_SHAPE, "Precomputed centroids must be n_clusters x n_features");
+      std::memcpy(hC.data(), p->precomputed, kd * sizeof(F));
+    } else {
+      bool have = false;
+      F best = 0;
+      std::vector<F> cand(kd);
+      for (uint64_t r = 0; r < p->n_runs; ++r) {
+        CKS(run_init<F>(ctx, p, rng, dC));
+        CKS(run_assign<F>(ctx, dX, n, d, dC, k, nullptr, ctx->dists.as<F>(), 0, nullptr, nullptr));
+        double s;
+        CKS(dist_sum(s));
+        const F cost = (F)s;
+        if (!have || !(best < cost)) {  // Iterator::min_by with `d1 < d2 ? Less : Greater`
+          best = cost; have = true;
+          CK(cudaMemcpy(hC.data(), dC, kd * sizeof(F), cudaMemcpyDeviceToHost));
+        }
+      }
+    }
+    for (uint64_t c = 0; c < k; ++c) counts_inout[c] = (F)0;
+  } else {
+    std::memcpy(hC.data(), C_inout, kd * sizeof(F));
+  }
+  CK(cudaMemcpyAsync(dC, hC.data(), kd * sizeof(F), cudaMemcpyHostToDevice, ctx->stream));
+  CKS(run_assign<F>(ctx, dX, n, d, dC, k, ctx->labels.as<uint32_t>(), ctx->dists.as<F>(), 0, nullptr, nullptr));
+  double s;
+  CKS(dist_sum(s));
+  // compute_centroids_incremental (KM/algorithm.rs:815-835): order-dependent running
+  // mean, walked in row order by one CTA (incremental_update_kernel)
+  F* dCn = dC + kd;
+  CK(cudaMemcpyAsync(dCn, dC, kd * sizeof(F), cudaMemcpyDeviceToDevice, ctx->stream));
+  const int threads = (int)std::min<uint64_t>(1024, ((d + 31) / 32) * 32);
+  CK(ctx->tmpc.ensure((k + (size_t)(threads / 32) * k + 8) * sizeof(F)));
+  F* dcounts = ctx->tmpc.as<F>();
+  CK(cudaMemcpyAsync(dcounts, counts_inout, k * sizeof(F), cudaMemcpyHostToDevice, ctx->stream));
+  incremental_update_kernel<F><<<1, threads, 0, ctx->stream>>>(dX, ctx->labels.as<uint32_t>(), n, (int)d, (int)k, dCn, dcounts,
+                                                               dcounts + k + 4);
+  CK(cudaGetLastError());
+  CK(ctx->scratch.ensure(64));
+  seq_l2_distance_kernel<F><<<1, 32, 0, ctx->stream>>>(dC, dCn, (int)kd, ctx->scratch.as<F>());
+  CK(cudaGetLastError());
+  ctx->launches += 2;
+  F shift = (F)0;
+  CK(cudaMemcpyAsync(&shift, ctx->scratch.p, sizeof(F), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(C_inout, dCn, kd * sizeof(F), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(counts_inout, dcounts, k * sizeof(F), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  *inertia_out = (F)s / (F)n;
+  return shift < (F)p->tolerance ? LKM_OK : LKM_NOT_CONVERGED;
+}
+
+}  // namespace lkm
+
+// ------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------
+LKM_EXPORT const char* lkm_version(void) { return "linfa_b200 lkm 0.1 (sm_100a)"; }
+
+LKM_EXPORT lkm_status lkm_create(lkm_ctx** out, int device) {
+  if (!out) return LKM_ERR_INVALID_ARG;
+  *out = nullptr;
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || device < 0 || device >= count) return LKM_ERR_CUDA;
+  lkm_ctx* ctx = new lkm_ctx();
+  ctx->device = device;
+  auto bail = [&](lkm_status s) { delete ctx; return s; };
+  if (cudaSetDevice(device) != cudaSuccess) return bail(LKM_ERR_CUDA);
+  if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) return bail(LKM_ERR_CUDA);
+  cudaEventCreate(&ctx->ev0);
+  cudaEventCreate(&ctx->ev1);
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return bail(LKM_ERR_CUDA);
+  ctx->sm_count = prop.multiProcessorCount;
+  ctx->smem_optin = prop.sharedMemPerBlockOptin;
+  if (cudaMallocHost(&ctx->h_state, sizeof(LloydState)) != cudaSuccess) return bail(LKM_ERR_CUDA);
+  if (cudaMallocHost(&ctx->h_pin, 4096 * sizeof(double)) != cudaSuccess) return bail(LKM_ERR_CUDA);
+  *out = ctx;
+  return LKM_OK;
+}
+
+LKM_EXPORT lkm_status lkm_destroy(lkm_ctx* ctx) {
+  if (!ctx) return LKM_OK;
+  cudaSetDevice(ctx->device);
+  if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+  if (ctx->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->comm);
+  DevBuf* bufs[] = {&ctx->xbuf, &ctx->cbuf, &ctx->part_sums, &ctx->part_counts, &ctx->part_inertia, &ctx->shift_part,
+                    &ctx->counts_out, &ctx->state, &ctx->gather, &ctx->labels, &ctx->dists, &ctx->wdists, &ctx->cum,
+                    &ctx->scratch, &ctx->tmpx, &ctx->tmpc, &ctx->idxbuf, &ctx->bsum, &ctx->weights};
+  for (DevBuf* b : bufs) b->release();
+  if (ctx->h_state) cudaFreeHost(ctx->h_state);
+  if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
+  if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+  if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+  if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+  return LKM_OK;
+}
+
+LKM_EXPORT const char* lkm_last_error(const lkm_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+LKM_EXPORT void* lkm_stream(lkm_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+LKM_EXPORT lkm_status lkm_synchronize(lkm_ctx* ctx) {
+  if (!ctx) return LKM_ERR_INVALID_ARG;
+  CK(cudaStreamSynchronize(ctx->stream));
+  return LKM_OK;
+}
+LKM_EXPORT lkm_status lkm_set_assign_path(lkm_ctx* ctx, int path) {
+  if (!ctx || path < -1 || path > 2) return LKM_ERR_INVALID_ARG;
+  ctx->force_path = path;
+  return LKM_OK;
+}
+
+LKM_EXPORT lkm_status lkm_comm_unique_id(void* id128) {
+  std::string err;
+  if (!id128 || !g_nccl.load(err)) return LKM_ERR_NCCL;
+  return g_nccl.GetUniqueId(reinterpret_cast<NcclUid*>(id128)) == 0 ? LKM_OK : LKM_ERR_NCCL;
+}
+LKM_EXPORT lkm_status lkm_comm_init(lkm_ctx* ctx, const void* id128, int rank, int world_size) {
+  if (!ctx || !id128 || world_size < 1 || rank < 0 || rank >= world_size) return LKM_ERR_INVALID_ARG;
+  if (world_size == 1) { ctx->rank = 0; ctx->world = 1; return LKM_OK; }
+  if (!g_nccl.load(ctx->err)) return LKM_ERR_NCCL;
+  CK(cudaSetDevice(ctx->device));
+  NcclUid uid;
+  std::memcpy(&uid, id128, sizeof(uid));
+  CKN(g_nccl.CommInitRank(&ctx->comm, world_size, uid, rank));
+  ctx->rank = rank;
+  ctx->world = world_size;
+  return LKM_OK;
+}
+LKM_EXPORT lkm_status lkm_set_shard(lkm_ctx* ctx, uint64_t row_offset, uint64_t n_global) {
+  if (!ctx) return LKM_ERR_INVALID_ARG;
+  ctx->row_offset = row_offset;
+  ctx->n_global = n_global;
+  return LKM_OK;
+}
+
+#define LKM_TYPED(F, SFX)                                                                                              \
+  LKM_EXPORT lkm_status lkm_set_data_##SFX(lkm_ctx* ctx, const F* x, uint64_t n, uint64_t d, int64_t row_stride) {     \
+    if (!ctx) return LKM_ERR_INVALID_ARG;                                                                              \
+    return set_data_impl<F>(ctx, x, n, d, row_stride);                                                                 \
+  }                                                                                                                    \
+  LKM_EXPORT lkm_status lkm_set_data_device_##SFX(lkm_ctx* ctx, const void* x_device, uint64_t n, uint64_t d) {        \
+    if (!ctx || (!x_device && n) || d == 0) return LKM_ERR_INVALID_ARG;                                                \
+    ctx->X = const_cast<void*>(x_device); ctx->own_X = false; ctx->n = n; ctx->d = d; ctx->elem = (int)sizeof(F);      \
+    if (ctx->world == 1) { ctx->row_offset = 0; ctx->n_global = n; }                                                   \
+    return LKM_OK;                                                                                                     \
+  }                                                                                                                    \
+  LKM_EXPORT lkm_status lkm_gen_blobs_##SFX(lkm_ctx* ctx, uint64_t n, uint64_t d, uint64_t n_blobs, const F* centres,  \
+                                            F sigma, uint64_t seed, uint64_t row_offset, uint64_t n_global) {          \
+    if (!ctx) return LKM_ERR_INVALID_ARG;                                                                              \
+    return gen_blobs_impl<F>(ctx, n, d, n_blobs, centres, sigma, seed, row_offset, n_global);                          \
+  }                                                                                                                    \
+  LKM_EXPORT lkm_status lkm_get_data_##SFX(lkm_ctx* ctx, uint64_t row0, uint64_t rows, F* out) {                       \
+    if (!ctx || !out) return LKM_ERR_INVALID_ARG;                                                                      \
+    return get_data_impl<F>(ctx, row0, rows, out);                                                                     \
+  }                                                                                                                    \
+  LKM_EXPORT lkm_status lkm_fit_##SFX(lkm_ctx* ctx, const lkm_params* p, lkm_rng rng, F* centroids_out,                \
+                                      F* cluster_count_out, F* inertia_out, lkm_stats* stats_out) {                    \
+    if (!ctx) return LKM_ERR_INVALID_ARG;                                                                              \
+    return fit_impl<F>(ctx, p, rng, centroids_out, cluster_count_out, inertia_out, stats_out);                         \
+  }                                                                                                                    \
+  LKM_EXPORT lkm_status lkm_init_##SFX(lkm_ctx* ctx, const lkm_params* p, lkm_rng rng, F* centroids_out) {             \
+    if (!ctx || !p || !centroids_out) return LKM_ERR_INVALID_ARG;                                                      \
+    if (p->n_clusters == 0) return fail(ctx, LKM_ERR_N_CLUSTERS, "n_clusters cannot be 0");                            \
+    if (ctx->elem != (int)sizeof(F) || !ctx->X) return fail(ctx, LKM_ERR_NO_DATA, "no resident data of this type");    \
+    CK(cudaSetDevice(ctx->device));                                                                                    \
+    const uint64_t kd = p->n_clusters * ctx->d;                                                                        \
+    CK(ctx->cbuf.ensure(2 * kd * sizeof(F)));                                                                          \
+    HostRng rng_{rng};                                                                                                 \
+    ctx->launches = 0;                                                                                                 \
+    CKS(run_init<F>(ctx, p, rng_, ctx->cbuf.as<F>()));                                                                 \
+    CK(cudaMemcpyAsync(centroids_out, ctx->cbuf.p, kd * sizeof(F), cudaMemcpyDeviceToHost, ctx->stream));              \
+    CK(cudaStreamSynchronize(ctx->stream));                                                                            \
+    return LKM_OK;                                                                                                     \
+  }                                                                                                                    \
+  LKM_EXPORT lkm_status lkm_lloyd_iters_##SFX(lkm_ctx* ctx, F* centroids_inout, uint64_t k, uint64_t max_iters,        \
+                                              double tolerance, F* cluster_count_out, F* inertia_total_out,            \
+                                              lkm_stats* stats_out) {                                                  \
+    if (!ctx) return LKM_ERR_INVALID_ARG;                                                                              \
+    return lloyd_iters_impl<F>(ctx, centroids_inout, k, max_iters, tolerance, cluster_count_out, inertia_total_out,    \
+                               stats_out);                                                                             \
+  }                                                                                                                    \
+  LKM_EXPORT lkm_status lkm_predict_##SFX(lkm_ctx* ctx, const F* centroids, uint64_t k, const F* x, uint64_t n,        \
+                                          uint64_t d, int64_t row_stride, uint64_t* labels_out) {                      \
+    if (!ctx || !labels_out) return LKM_ERR_INVALID_ARG;                                                               \
+    return assign_impl<F>(ctx, centroids, k, x, n, d, row_stride, labels_out, nullptr);                                \
+  }                                                                                                                    \
+  LKM_EXPORT lkm_status lkm_transform_##SFX(lkm_ctx* ctx, const F* centroids, uint64_t k, const F* x, uint64_t n,      \
+                                            uint64_t d, int64_t row_stride, F* min_sq_dist_out) {                      \
+    if (!ctx || !min_sq_dist_out) return LKM_ERR_INVALID_ARG;                                                          \
+    return assign_impl<F>(ctx, centroids, k, x, n, d, row_stride, nullptr, min_sq_dist_out);                           \
+  }                                                                                                                    \
+  LKM_EXPORT lkm_status lkm_assign_##SFX(lkm_ctx* ctx, const F* centroids, uint64_t k, const F* x, uint64_t n,         \
+                                         uint64_t d, int64_t row_stride, uint64_t* labels_out, F* min_sq_dist_out) {   \
+    if (!ctx) return LKM_ERR_INVALID_ARG;                                                                              \
+    return assign_impl<F>(ctx, centroids, k, x, n, d, row_stride, labels_out, min_sq_dist_out);                        \
+  }                                                                                                                    \
+  LKM_EXPORT lkm_status lkm_fit_with_##SFX(lkm_ctx* ctx, const lkm_params* p, lkm_rng rng, int has_model,              \
+                                           F* centroids_inout, F* cluster_count_inout, F* inertia_out) {               \
+    if (!ctx) return LKM_ERR_INVALID_ARG;                                                                              \
+    return fit_with_impl<F>(ctx, p, rng, has_model, centroids_inout, cluster_count_inout, inertia_out);                \
+  }
+
+LKM_TYPED(float, f32)
+LKM_TYPED(double, f64)

@@ -1,0 +1,677 @@
+// CUDA-core kernels of the K-Means hot path (sm_100a).
+//
+//   lloyd_kernel<F, D, MODE>   assignment (bit-exact direct form) and/or the
+//                              deterministic per-CTA accumulation of cluster
+//                              sums, counts and inertia      
+//   finalize_kernel<...>       fixed-order combine of the partials, m_k-means
+//                              update, shift, convergence flag   
+//   seq_prefix / count_le      WeightedIndex exact pick       
+//   block_sums / fast_pick     fixed-order f64 scan pick      (fast)
+//   bernoulli_select           k-means|| oversampling         
+//   gather_rows, gen_blobs     row gather; synthetic blobs
+//
+// Reference arithmetic being reproduced (KM = algorithms/linfa-clustering/src/k_means):
+//   KM/algorithm.rs:923-946 closest_centroid: strict '<', lowest index wins
+//   linfa-nn/src/distance.rs:68-70 + ndarray-stats sq_l2_dist: acc += (c_j-x_j)^2
+//     in F, feature order, no FMA  -> __fsub_rn/__fmul_rn/__fadd_rn (never contracted)
+//   KM/algorithm.rs:785-810 compute_centroids: (sum + old) / (count + 1)
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace lkm {
+
+struct LloydState {
+  unsigned long long n_iter;
+  unsigned long long fallback_rows;
+  double inertia;  // sum of min squared distances of the last assignment
+  double shift;    // ||C_t - C_{t+1}||_F of the last iteration
+  int done;
+  unsigned int blocks_done;
+};
+
+enum LloydMode { MODE_ASSIGN = 0, MODE_FUSED = 1, MODE_UPDATE = 2 };
+
+constexpr int kThreads = 256;  // threads per CTA == rows per tile
+
+template <typename F> struct Rn;
+template <> struct Rn<float> {
+  static __device__ __forceinline__ float sub(float a, float b) { return __fsub_rn(a, b); }
+  static __device__ __forceinline__ float mul(float a, float b) { return __fmul_rn(a, b); }
+  static __device__ __forceinline__ float add(float a, float b) { return __fadd_rn(a, b); }
+};
+template <> struct Rn<double> {
+  static __device__ __forceinline__ double sub(double a, double b) { return __dsub_rn(a, b); }
+  static __device__ __forceinline__ double mul(double a, double b) { return __dmul_rn(a, b); }
+  static __device__ __forceinline__ double add(double a, double b) { return __dadd_rn(a, b); }
+};
+
+template <typename F> struct LloydArgs {
+  const F* X;            // n x d row-major (this rank's shard)
+  unsigned long long n;
+  int d;
+  int k;
+  const F* C;            // k x d
+  // assignment outputs (any may be null)
+  uint32_t* labels;
+  F* dists;              // min squared distance; with min_combine: dists = min(dists, new)
+  int min_combine;
+  const F* weights;      // optional: wdists = dists * weights (KM/init.rs:147)
+  F* wdists;
+  const uint32_t* labels_in;  // MODE_UPDATE
+  // accumulation outputs: per-CTA partials
+  F* part_sums;          // CTA b, cluster c, feature j at part_sums[b*k*d + c*d + j]
+  uint32_t* part_counts; // CTA b, cluster c at part_counts[b*k + c]
+  double* part_inertia;  // [grid]
+  const LloydState* state;  // if non-null and state->done: exit at once
+  int n_subsets;         // private accumulator copies per CTA
+  int x_stride;          // smem row stride of the tile, in elements
+  int kc;                // centroid rows resident in smem per chunk
+  int chunk_base;        // clusters [chunk_base, chunk_base+chunk_rows) are accumulated
+  int chunk_rows;
+  int vec;               // rows are 16-byte vectorisable
+};
+
+// ---- squared distance, exact reference order ------------------------------
+template <typename F, int D>
+__device__ __forceinline__ F sqdist_reg(const F* __restrict__ c, const F (&x)[D]) {
+  F acc = (F)0;
+#pragma unroll
+  for (int j = 0; j < D; ++j) {
+    const F diff = Rn<F>::sub(c[j], x[j]);
+    acc = Rn<F>::add(acc, Rn<F>::mul(diff, diff));
+  }
+  return acc;
+}
+template <typename F>
+__device__ __forceinline__ F sqdist_mem(const F* __restrict__ c, const F* __restrict__ x, int d) {
+  F acc = (F)0;
+  for (int j = 0; j < d; ++j) {
+    const F diff = Rn<F>::sub(c[j], x[j]);
+    acc = Rn<F>::add(acc, Rn<F>::mul(diff, diff));
+  }
+  return acc;
+}
+
+// scan `rows_c` centroids at cs (row stride d) in ascending order, strict '<'
+template <typename F, int D>
+__device__ __forceinline__ void scan_centroids(const F* __restrict__ cs, int rows_c, int d, int base,
+                                               const F* __restrict__ xrow, bool first, F& best, int& bidx) {
+  if constexpr (D > 0) {
+    F x[D];
+#pragma unroll
+    for (int j = 0; j < D; ++j) x[j] = xrow[j];
+    int c = 0;
+    if (first) { best = sqdist_reg<F, D>(cs, x); bidx = base; c = 1; }
+    for (; c + 4 <= rows_c; c += 4) {
+      const F v0 = sqdist_reg<F, D>(cs + (c + 0) * D, x);
+      const F v1 = sqdist_reg<F, D>(cs + (c + 1) * D, x);
+      const F v2 = sqdist_reg<F, D>(cs + (c + 2) * D, x);
+      const F v3 = sqdist_reg<F, D>(cs + (c + 3) * D, x);
+      if (v0 < best) { best = v0; bidx = base + c; }
+      if (v1 < best) { best = v1; bidx = base + c + 1; }
+      if (v2 < best) { best = v2; bidx = base + c + 2; }
+      if (v3 < best) { best = v3; bidx = base + c + 3; }
+    }
+    for (; c < rows_c; ++c) {
+      const F v = sqdist_reg<F, D>(cs + c * D, x);
+      if (v < best) { best = v; bidx = base + c; }
+    }
+  } else {
+    int c = 0;
+    if (first) { best = sqdist_mem<F>(cs, xrow, d); bidx = base; c = 1; }
+    for (; c + 2 <= rows_c; c += 2) {
+      const F v0 = sqdist_mem<F>(cs + (size_t)(c + 0) * d, xrow, d);
+      const F v1 = sqdist_mem<F>(cs + (size_t)(c + 1) * d, xrow, d);
+      if (v0 < best) { best = v0; bidx = base + c; }
+      if (v1 < best) { best = v1; bidx = base + c + 1; }
+    }
+    for (; c < rows_c; ++c) {
+      const F v = sqdist_mem<F>(cs + (size_t)c * d, xrow, d);
+      if (v < best) { best = v; bidx = base + c; }
+    }
+  }
+}
+
+// coalesced global -> smem copy of `rows` contiguous rows into a padded tile
+template <typename F>
+__device__ __forceinline__ void load_tile(F* __restrict__ xs, const F* __restrict__ g, int rows, int d, int x_stride,
+                                          int vec) {
+  const int t = threadIdx.x;
+  if (vec) {
+    const int cpr = (d * (int)sizeof(F)) / 16;  // 16-byte chunks per row
+    const int total = rows * cpr;
+    const int4* g4 = reinterpret_cast<const int4*>(g);
+    const int step_r = kThreads / cpr, step_c = kThreads % cpr;
+    int r = t / cpr, c = t % cpr;
+    for (int q = t; q < total; q += kThreads) {
+      const int4 v = __ldg(g4 + q);
+      *reinterpret_cast<int4*>(reinterpret_cast<char*>(xs) + ((size_t)r * x_stride * sizeof(F) + (size_t)c * 16)) = v;
+      r += step_r; c += step_c;
+      if (c >= cpr) { c -= cpr; r += 1; }
+    }
+  } else {
+    const int total = rows * d;
+    const int step_r = kThreads / d, step_c = kThreads % d;
+    int r = t / d, c = t % d;
+    for (int q = t; q < total; q += kThreads) {
+      xs[(size_t)r * x_stride + c] = __ldg(g + q);
+      r += step_r; c += step_c;
+      if (c >= d) { c -= d; r += 1; }
+    }
+  }
+}
+
+template <typename F, int D, int MODE>
+__global__ void __launch_bounds__(kThreads) lloyd_kernel(const LloydArgs<F> a) {
+  if (a.state != nullptr && a.state->done) return;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int d = (D > 0) ? D : a.d;
+  const int t = threadIdx.x;
+  // carve: centroids | tile | accumulators | counts | labels | reduction scratch
+  size_t off = 0;
+  F* cs = reinterpret_cast<F*>(smem_raw + off);
+  if (MODE != MODE_UPDATE) off += ((size_t)a.kc * d * sizeof(F) + 15) & ~(size_t)15;
+  F* xs = reinterpret_cast<F*>(smem_raw + off);
+  off += ((size_t)kThreads * a.x_stride * sizeof(F) + 15) & ~(size_t)15;
+  F* acc = reinterpret_cast<F*>(smem_raw + off);
+  uint32_t* cnt = nullptr;
+  uint32_t* labs = nullptr;
+  if (MODE != MODE_ASSIGN) {
+    off += ((size_t)a.n_subsets * a.chunk_rows * d * sizeof(F) + 15) & ~(size_t)15;
+    cnt = reinterpret_cast<uint32_t*>(smem_raw + off);
+    off += ((size_t)a.n_subsets * a.chunk_rows * sizeof(uint32_t) + 15) & ~(size_t)15;
+    labs = reinterpret_cast<uint32_t*>(smem_raw + off);
+    off += kThreads * sizeof(uint32_t);
+    for (int e = t; e < a.n_subsets * a.chunk_rows * d; e += kThreads) acc[e] = (F)0;
+    for (int e = t; e < a.n_subsets * a.chunk_rows; e += kThreads) cnt[e] = 0u;
+  }
+  const int n_chunks = (MODE == MODE_UPDATE) ? 1 : (a.k + a.kc - 1) / a.kc;
+  if (MODE != MODE_UPDATE && n_chunks == 1) {
+    for (int e = t; e < a.k * d; e += kThreads) cs[e] = a.C[e];
+  }
+  __syncthreads();
+
+  // accumulation role of this thread
+  int sub = 0, feat = t;
+  bool acc_active = false;
+  if (MODE != MODE_ASSIGN) {
+    if (d <= kThreads) { sub = t / d; feat = t - sub * d; acc_active = sub < a.n_subsets; }
+    else { sub = 0; feat = t; acc_active = true; }
+  }
+  int cur_lab = -1;
+  F cur_acc = (F)0;
+  double inert = 0.0;
+
+  const unsigned long long n_tiles = (a.n + kThreads - 1) / kThreads;
+  for (unsigned long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const unsigned long long row0 = tile * kThreads;
+    const int rows = (int)min((unsigned long long)kThreads, a.n - row0);
+    load_tile<F>(xs, a.X + row0 * (unsigned long long)d, rows, d, a.x_stride, a.vec);
+    if (MODE == MODE_UPDATE) {
+      if (t < rows) labs[t] = a.labels_in[row0 + t];
+    }
+    __syncthreads();
+    if (MODE != MODE_UPDATE) {
+      F best = (F)0;
+      int bidx = 0;
+      const F* xrow = xs + (size_t)t * a.x_stride;
+      if (n_chunks == 1) {
+        if (t < rows) scan_centroids<F, D>(cs, a.k, d, 0, xrow, true, best, bidx);
+      } else {
+        for (int ch = 0; ch < n_chunks; ++ch) {
+          const int cb = ch * a.kc, rc = min(a.kc, a.k - cb);
+          __syncthreads();
+          for (int e = t; e < rc * d; e += kThreads) cs[e] = a.C[(size_t)cb * d + e];
+          __syncthreads();
+          if (t < rows) scan_centroids<F, D>(cs, rc, d, cb, xrow, ch == 0, best, bidx);
+        }
+      }
+      if (t < rows) {
+        const unsigned long long row = row0 + t;
+        if (a.labels) a.labels[row] = (uint32_t)bidx;
+        F outd = best;
+        if (a.dists) {
+          if (a.min_combine) {
+            const F old = a.dists[row];
+            if (best < old) a.dists[row] = best; else outd = old;
+          } else {
+            a.dists[row] = best;
+          }
+        }
+        if (a.wdists) a.wdists[row] = a.weights ? outd * a.weights[row] : outd;
+        if (MODE == MODE_FUSED) { labs[t] = (uint32_t)bidx; inert += (double)best; }
+      }
+      if (MODE == MODE_FUSED) __syncthreads();
+    }
+    if (MODE != MODE_ASSIGN) {
+      if (acc_active) {
+        if (d <= kThreads) {
+          for (int r = sub; r < rows; r += a.n_subsets) {
+            const int lab = (int)labs[r] - a.chunk_base;
+            if ((unsigned)lab >= (unsigned)a.chunk_rows) continue;
+            const F xv = xs[(size_t)r * a.x_stride + feat];
+            if (lab == cur_lab) {
+              cur_acc += xv;
+            } else {
+              if (cur_lab >= 0) acc[((size_t)sub * a.chunk_rows + cur_lab) * d + feat] += cur_acc;
+              cur_lab = lab;
+              cur_acc = xv;
+            }
+            if (feat == 0) cnt[sub * a.chunk_rows + lab] += 1u;
+          }
+        } else {
+          for (int r = 0; r < rows; ++r) {
+            const int lab = (int)labs[r] - a.chunk_base;
+            if ((unsigned)lab >= (unsigned)a.chunk_rows) continue;
+            for (int j = t; j < d; j += kThreads) acc[(size_t)lab * d + j] += xs[(size_t)r * a.x_stride + j];
+            if (t == 0) cnt[lab] += 1u;
+          }
+        }
+      }
+    }
+    __syncthreads();
+  }
+
+  if (MODE != MODE_ASSIGN) {
+    if (acc_active && cur_lab >= 0) acc[((size_t)sub * a.chunk_rows + cur_lab) * d + feat] += cur_acc;
+    __syncthreads();
+    const int kd = a.chunk_rows * d;
+    F* ps = a.part_sums + ((size_t)blockIdx.x * a.k + a.chunk_base) * d;
+    for (int e = t; e < kd; e += kThreads) {
+      F s = acc[e];
+      for (int q = 1; q < a.n_subsets; ++q) s += acc[(size_t)q * kd + e];
+      ps[e] = s;
+    }
+    uint32_t* pc = a.part_counts + (size_t)blockIdx.x * a.k + a.chunk_base;
+    for (int e = t; e < a.chunk_rows; e += kThreads) {
+      uint32_t s = cnt[e];
+      for (int q = 1; q < a.n_subsets; ++q) s += cnt[q * a.chunk_rows + e];
+      pc[e] = s;
+    }
+    if (MODE == MODE_FUSED) {
+      double* red = reinterpret_cast<double*>(xs);  // tile is dead now
+      __syncthreads();
+      red[t] = inert;
+      __syncthreads();
+      for (int o = kThreads / 2; o > 0; o >>= 1) {
+        if (t < o) red[t] += red[t + o];
+        __syncthreads();
+      }
+      if (t == 0) a.part_inertia[blockIdx.x] = red[0];
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// finalize: sum `n_src` partial vectors in ascending source order (f64), then
+// either publish the per-rank partial (world > 1, before the all-gather) or do
+// the m_k-means update.  grid = ceil(k*d / 64) CTAs of 256 threads: thread
+// (g, e) sums sources b = g, g+4, ... for element e; the four groups are then
+// added in order.  The last CTA to finish reduces the shift and the inertia.
+// ---------------------------------------------------------------------------
+template <typename F, typename S, typename CT> struct FinalizeArgs {
+  const S* src_sums;          // source b, element e at src_sums[b*sum_stride + e]
+  const CT* src_counts;       // source b, cluster c at src_counts[b*cnt_stride + c]
+  const double* src_inertia;  // source b at src_inertia[b*inertia_stride]
+  size_t sum_stride, cnt_stride, inertia_stride;
+  int n_src;
+  int k, d;
+  // reduce-only output (per-rank partial): [kd sums | k counts | 1 inertia] as f64
+  double* rank_out;
+  // update outputs
+  const F* C_old;
+  F* C_new;
+  double* counts_out;    // k, members per cluster of this assignment (without the +1)
+  double* shift_part;    // [grid]
+  LloydState* state;
+  double tol;
+  unsigned long long max_iter;
+};
+
+constexpr int kFinElems = 64;
+
+__device__ __forceinline__ double block_sum_256(double v, double* red) {
+  const int t = threadIdx.x;
+  __syncthreads();
+  red[t] = v;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (t < o) red[t] += red[t + o];
+    __syncthreads();
+  }
+  return red[0];
+}
+
+template <typename F, typename S, typename CT, bool UPDATE>
+__global__ void __launch_bounds__(256) finalize_kernel(const FinalizeArgs<F, S, CT> a) {
+  if (UPDATE && a.state->done) return;
+  __shared__ double sh[4][kFinElems];
+  __shared__ double shc[4][kFinElems];
+  __shared__ double red[256];
+  __shared__ bool is_last;
+  const int t = threadIdx.x, g = t >> 6, l = t & 63;
+  const int kd = a.k * a.d;
+  const int e = blockIdx.x * kFinElems + l;
+  double s = 0.0;
+  if (e < kd)
+    for (int b = g; b < a.n_src; b += 4) s += (double)a.src_sums[(size_t)b * a.sum_stride + e];
+  sh[g][l] = s;
+  // counts of the clusters this CTA's elements belong to
+  const int c_lo = (blockIdx.x * kFinElems) / a.d;
+  const int c_hi = (min(kd, (int)(blockIdx.x + 1) * kFinElems) - 1) / a.d;
+  const int c = c_lo + l;
+  double cs = 0.0;
+  if (c <= c_hi)
+    for (int b = g; b < a.n_src; b += 4) cs += (double)a.src_counts[(size_t)b * a.cnt_stride + c];
+  shc[g][l] = cs;
+  __syncthreads();
+  // every cluster's count is published by the CTA that holds its first element
+  if (g == 0 && c <= c_hi && (c * a.d) / kFinElems == (int)blockIdx.x) {
+    const double cntv = ((shc[0][l] + shc[1][l]) + shc[2][l]) + shc[3][l];
+    if (UPDATE) a.counts_out[c] = cntv; else a.rank_out[kd + c] = cntv;
+  }
+  double sq = 0.0;
+  if (g == 0 && e < kd) {
+    const double tot = ((sh[0][l] + sh[1][l]) + sh[2][l]) + sh[3][l];
+    if (!UPDATE) {
+      a.rank_out[e] = tot;
+    } else {
+      const int ce = e / a.d - c_lo;
+      const double cntv = ((shc[0][ce] + shc[1][ce]) + shc[2][ce]) + shc[3][ce];
+      const F oldv = a.C_old[e];
+      const F newv = (F)((tot + (double)oldv) / (cntv + 1.0));
+      a.C_new[e] = newv;
+      const double df = (double)(oldv - newv);
+      sq = df * df;
+    }
+  }
+  if (!UPDATE) {
+    if (blockIdx.x == 0) {
+      double v = 0.0;
+      for (int b = t; b < a.n_src; b += 256) v += a.src_inertia[(size_t)b * a.inertia_stride];
+      const double tot = block_sum_256(v, red);
+      if (t == 0) a.rank_out[kd + a.k] = tot;
+    }
+    return;
+  }
+  const double sq_cta = block_sum_256(sq, red);
+  if (t == 0) {
+    a.shift_part[blockIdx.x] = sq_cta;
+    __threadfence();
+    const unsigned int prev = atomicAdd(&a.state->blocks_done, 1u);
+    is_last = (prev == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  // last CTA: shift, inertia, loop control (fixed order)
+  double v = 0.0;
+  for (int b = t; b < (int)gridDim.x; b += 256) v += ((volatile double*)a.shift_part)[b];
+  const double shift_sq = block_sum_256(v, red);
+  v = 0.0;
+  for (int b = t; b < a.n_src; b += 256) v += a.src_inertia[(size_t)b * a.inertia_stride];
+  const double inertia = block_sum_256(v, red);
+  if (t == 0) {
+    const F shift = (F)sqrt(shift_sq);  // L2Dist::distance: sqrt in f64, cast to F
+    a.state->shift = (double)shift;
+    a.state->inertia = inertia;
+    const unsigned long long it = a.state->n_iter + 1;
+    a.state->n_iter = it;
+    a.state->blocks_done = 0u;
+    if (shift < (F)a.tol || it >= a.max_iter) a.state->done = 1;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// small utilities
+// ---------------------------------------------------------------------------
+template <typename F>
+__global__ void gather_rows_kernel(const F* __restrict__ X, int d, const long long* __restrict__ idx, int k,
+                                   F* __restrict__ out) {
+  // idx[c] < 0: row not on this rank, leave out[c] untouched
+  for (int c = blockIdx.x; c < k; c += gridDim.x) {
+    const long long r = idx[c];
+    if (r < 0) continue;
+    for (int j = threadIdx.x; j < d; j += blockDim.x) out[(size_t)c * d + j] = X[(size_t)r * d + j];
+  }
+}
+
+__device__ __forceinline__ unsigned long long mix64(unsigned long long z) {
+  z += 0x9e3779b97f4a7c15ULL;
+  z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ULL;
+  z = (z ^ (z >> 27)) * 0x94d049bb133111ebULL;
+  return z ^ (z >> 31);
+}
+__device__ __forceinline__ double unit_open(unsigned long long bits) {  // (0,1)
+  return ((double)(bits >> 11) + 0.5) * (1.0 / 9007199254740992.0);
+}
+
+// blobs in the sense of datasets/src/generate.rs:28-58; one thread per element,
+// N(0,1) by Box-Muller from two counter-keyed hashes (counter = global element index).
+template <typename F>
+__global__ void gen_blobs_kernel(F* __restrict__ X, unsigned long long n, int d, unsigned long long n_blobs,
+                                 const F* __restrict__ centres, F sigma, unsigned long long seed,
+                                 unsigned long long row_offset, unsigned long long n_global) {
+  const unsigned long long total = n * (unsigned long long)d;
+  const unsigned long long m = n_global / n_blobs;
+  for (unsigned long long e = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; e < total;
+       e += (unsigned long long)gridDim.x * blockDim.x) {
+    const unsigned long long r = e / d, j = e - r * d;
+    const unsigned long long gr = row_offset + r;
+    unsigned long long b = m ? gr / m : 0;
+    if (b >= n_blobs) b = n_blobs - 1;
+    const unsigned long long ctr = gr * (unsigned long long)d + j;
+    const unsigned long long h1 = mix64(seed ^ mix64(2 * ctr)), h2 = mix64(seed ^ mix64(2 * ctr + 1));
+    const double u1 = unit_open(h1), u2 = unit_open(h2);
+    const double z = sqrt(-2.0 * log(u1)) * cospi(2.0 * u2);
+    X[e] = (F)((double)centres[b * d + j] + (double)sigma * z);
+  }
+}
+
+// WeightedIndex::new: sequential prefix sum in F on ONE thread (bit-exact with
+// rand 0.8.5).  cum[i] = w_0 + ... + w_i for i < n-1 ; out[0] = total,
+// out[1] = 1 if any weight is negative/NaN (InvalidWeight).
+template <typename F>
+__global__ void __launch_bounds__(256) seq_prefix_kernel(const F* __restrict__ w, unsigned long long n,
+                                                         F* __restrict__ cum, F* __restrict__ out) {
+  constexpr int CH = 2048;
+  __shared__ F buf[CH];
+  __shared__ F carry;
+  __shared__ int bad;
+  if (threadIdx.x == 0) { carry = (F)0; bad = 0; }
+  __syncthreads();
+  for (unsigned long long base = 0; base < n; base += CH) {
+    const int m = (int)min((unsigned long long)CH, n - base);
+    for (int i = threadIdx.x; i < m; i += blockDim.x) buf[i] = w[base + i];
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      F total = carry;
+      int b = 0;
+      for (int i = 0; i < m; ++i) {
+        const F wi = buf[i];
+        if (!(wi >= (F)0)) b = 1;
+        total = Rn<F>::add(total, wi);
+        buf[i] = total;  // inclusive prefix
+      }
+      carry = total;
+      if (b) bad = 1;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < m; i += blockDim.x)
+      if (base + i < n - 1) cum[base + i] = buf[i];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) { out[0] = carry; out[1] = bad ? (F)1 : (F)0; }
+}
+
+// partition point of the non-decreasing cum[0..m): #{j : cum[j] <= chosen}
+template <typename F>
+__global__ void count_le_kernel(const F* __restrict__ cum, unsigned long long m, F chosen,
+                                unsigned long long* __restrict__ out) {
+  unsigned long long local = 0;
+  for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < m;
+       i += (unsigned long long)gridDim.x * blockDim.x)
+    local += (cum[i] <= chosen) ? 1ull : 0ull;
+  for (int o = 16; o > 0; o >>= 1) local += __shfl_down_sync(0xffffffffu, local, o);
+  if ((threadIdx.x & 31) == 0 && local) atomicAdd(out, local);
+}
+
+// fixed-order f64 block sums of w (blocks of kPickBlock elements) for the fast pick
+constexpr int kPickBlock = 2048;
+template <typename F>
+__global__ void __launch_bounds__(256) block_sums_kernel(const F* __restrict__ w, unsigned long long n,
+                                                         double* __restrict__ bsum) {
+  __shared__ double red[256];
+  const unsigned long long nb = (n + kPickBlock - 1) / kPickBlock;
+  for (unsigned long long b = blockIdx.x; b < nb; b += gridDim.x) {
+    const unsigned long long base = b * kPickBlock;
+    double s = 0.0;
+#pragma unroll
+    for (int q = 0; q < kPickBlock / 256; ++q) {
+      const unsigned long long i = base + threadIdx.x + q * 256;
+      if (i < n) s += (double)w[i];
+    }
+    red[threadIdx.x] = s;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) { if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o]; __syncthreads(); }
+    if (threadIdx.x == 0) bsum[b] = red[0];
+    __syncthreads();
+  }
+}
+
+// fast pick, single CTA: total = sum of block sums (in order), threshold =
+// u01 * (F)total, then the first element whose running f64 prefix exceeds it.
+// out_idx[0] = local row index (or -1 if the threshold falls outside this
+// rank's range [lo, hi) of the global prefix, multi-GPU), out_total[0] = total.
+template <typename F>
+__global__ void __launch_bounds__(256) fast_pick_kernel(const F* __restrict__ w, unsigned long long n,
+                                                        const double* __restrict__ bsum, double prefix_before,
+                                                        double total_global, F u01, long long* __restrict__ out_idx) {
+  __shared__ double red[256];
+  __shared__ long long found_block;
+  __shared__ double found_prefix;
+  const unsigned long long nb = (n + kPickBlock - 1) / kPickBlock;
+  const double thr = (double)(u01 * (F)total_global);  // value0_1 * scale (+ 0)
+  // thread 0 walks the block sums in order (nb <= ~1e5)
+  if (threadIdx.x == 0) {
+    double run = prefix_before;
+    long long fb = -1;
+    double fp = 0.0;
+    for (unsigned long long b = 0; b < nb; ++b) {
+      const double nxt = run + bsum[b];
+      if (nxt > thr) { fb = (long long)b; fp = run; break; }
+      run = nxt;
+    }
+    found_block = fb;
+    found_prefix = fp;
+  }
+  __syncthreads();
+  if (found_block < 0) { if (threadIdx.x == 0) out_idx[0] = -1; return; }
+  (void)red;
+  if (threadIdx.x == 0) {
+    const unsigned long long base = (unsigned long long)found_block * kPickBlock;
+    double run = found_prefix;
+    long long idx = -1;
+    const unsigned long long end = min(n, base + kPickBlock);
+    for (unsigned long long i = base; i < end; ++i) {
+      run += (double)w[i];
+      if (run > thr) { idx = (long long)i; break; }
+    }
+    if (idx < 0) idx = (long long)end - 1;  // rounding slack inside the block
+    out_idx[0] = idx;
+  }
+}
+
+// k-means|| oversampling (KM/init.rs:239-270): keep row i iff U_i < mult * d_i / cost,
+// U_i from a counter-based generator keyed by (seed, global row).  Selected global
+// row ids are appended through an atomic cursor (the host sorts them ascending).
+template <typename F>
+__global__ void bernoulli_select_kernel(const F* __restrict__ dists, unsigned long long n, F mult, F cost,
+                                        unsigned long long seed, unsigned long long row_offset,
+                                        unsigned long long* __restrict__ out, unsigned int cap,
+                                        unsigned int* __restrict__ cursor) {
+  for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < n;
+       i += (unsigned long long)gridDim.x * blockDim.x) {
+    const unsigned long long bits = mix64(seed ^ mix64(row_offset + i));
+    const F rnd = (F)((double)(bits >> 11) * (1.0 / 9007199254740992.0));
+    const F prob = mult * dists[i] / cost;
+    if (rnd < prob) {
+      const unsigned int p = atomicAdd(cursor, 1u);
+      if (p < cap) out[p] = row_offset + i;
+    }
+  }
+}
+
+// histogram of labels (integer atomics: exact, order-independent) -> counts as F
+__global__ void label_hist_kernel(const uint32_t* __restrict__ labels, unsigned long long n,
+                                  unsigned int* __restrict__ hist) {
+  for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < n;
+       i += (unsigned long long)gridDim.x * blockDim.x)
+    atomicAdd(hist + labels[i], 1u);
+}
+template <typename F>
+__global__ void u32_to_float_kernel(const unsigned int* __restrict__ in, int m, F* __restrict__ out) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < m; i += gridDim.x * blockDim.x) out[i] = (F)in[i];
+}
+
+// compute_centroids_incremental (KM/algorithm.rs:815-835): per-sample running
+// mean, order dependent => rows are walked in order by ONE CTA; thread j owns
+// feature j (and j+blockDim, ...).  Every warp keeps its own replica of the
+// counts (wcounts[warp][k]) so no block barrier is needed per row.
+template <typename F>
+__global__ void __launch_bounds__(1024) incremental_update_kernel(const F* __restrict__ X,
+                                                                  const uint32_t* __restrict__ labels,
+                                                                  unsigned long long n, int d, int k, F* __restrict__ C,
+                                                                  F* __restrict__ counts, F* __restrict__ wcounts) {
+  const int t = threadIdx.x, warp = t >> 5, lane = t & 31, nw = blockDim.x >> 5;
+  F* mine = wcounts + (size_t)warp * k;
+  for (int c = lane; c < k; c += 32) mine[c] = counts[c];
+  __syncwarp();
+  for (unsigned long long i = 0; i < n; ++i) {
+    const uint32_t c = labels[i];
+    F cnt = (F)0;
+    if (lane == 0) { cnt = Rn<F>::add(mine[c], (F)1); mine[c] = cnt; }
+    cnt = __shfl_sync(0xffffffffu, cnt, 0);
+    for (int j = t; j < d; j += blockDim.x) {
+      const F cen = C[(size_t)c * d + j];
+      const F shift = Rn<F>::sub(X[i * (unsigned long long)d + j], cen) / cnt;
+      C[(size_t)c * d + j] = Rn<F>::add(cen, shift);
+    }
+  }
+  __syncwarp();
+  if (warp == 0)
+    for (int c = lane; c < k; c += 32) counts[c] = mine[c];
+  (void)nw;
+}
+
+// L2Dist::distance(C_old, C_new) exactly as the reference evaluates it
+// (sequential F accumulation over k*d, sqrt in f64, cast to F); one thread.
+template <typename F>
+__global__ void seq_l2_distance_kernel(const F* __restrict__ a, const F* __restrict__ b, int len, F* __restrict__ out) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    F acc = (F)0;
+    for (int e = 0; e < len; ++e) {
+      const F df = Rn<F>::sub(a[e], b[e]);
+      acc = Rn<F>::add(acc, Rn<F>::mul(df, df));
+    }
+    out[0] = (F)sqrt((double)acc);
+  }
+}
+
+// fixed-order f64 sum of an F vector: per-block partials then a single-CTA pass
+template <typename F>
+__global__ void __launch_bounds__(256) sum_f64_kernel(const F* __restrict__ x, unsigned long long n,
+                                                      double* __restrict__ part) {
+  __shared__ double red[256];
+  double s = 0.0;
+  const unsigned long long per = (n + gridDim.x - 1) / gridDim.x;
+  const unsigned long long lo = blockIdx.x * per, hi = min(n, lo + per);
+  for (unsigned long long i = lo + threadIdx.x; i < hi; i += 256) s += (double)x[i];
+  red[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) { if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o]; __syncthreads(); }
+  if (threadIdx.x == 0) part[blockIdx.x] = red[0];
+}
+
+}  // namespace lkm

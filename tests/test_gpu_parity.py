@@ -1,0 +1,400 @@
+"""GPU parity tests: the CUDA path, called through the C ABI, against the CPU oracle.
+
+Bar (BASELINE.json north_star): labels identical to the reference on the same
+inputs; min squared distances bit-identical (the kernels evaluate the winning
+distance in the reference's direct form); centroids and inertia within 1e-5
+(f32) / 1e-10 (f64) relative of the f64-accumulated oracle.
+"""
+import numpy as np
+import pytest
+
+from tests.oracle_lib import INIT_KMEANSPARA, INIT_KMEANSPP, INIT_PRECOMPUTED, INIT_RANDOM
+
+pytestmark = pytest.mark.gpu
+
+RTOL = {np.float32: 1e-5, np.float64: 1e-10}
+DTYPES = [np.float32, np.float64]
+
+
+@pytest.fixture(scope="module")
+def lb():
+    import torch
+
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    import linfa_b200
+
+    return linfa_b200
+
+
+@pytest.fixture(scope="module")
+def ctx(lb):
+    return lb.Context.default()
+
+
+def blobs(n, d, k_true, dt, seed=0, spread=30.0):
+    g = np.random.default_rng(seed)
+    centres = g.uniform(-spread, spread, (k_true, d))
+    m = n // k_true
+    parts = []
+    for b in range(k_true):
+        rows = m if b < k_true - 1 else n - m * (k_true - 1)
+        parts.append(g.standard_normal((rows, d)) + centres[b])
+    return np.concatenate(parts).astype(dt), centres.astype(dt)
+
+
+def function_test_1d(x):
+    return np.where(x < 0.4, x * x, np.where((x >= 0.4) & (x < 0.8), 3.0 * x + 1.0, np.sin(10.0 * x)))
+
+
+def make_1d_dataset(oracle, seed=42):
+    rng = oracle.rng(seed)
+    xt = rng.uniform_f64(0.0, 1.0, (100, 1))
+    return np.concatenate([xt, function_test_1d(xt)], axis=1)
+
+
+# ---- literal KATs through the C ABI ----
+@pytest.mark.parametrize("dt", DTYPES)
+def test_kat_min_dists_and_argmin(lb, dt):
+    m = lb.KMeans(np.array([[0.0, 1.0], [40.0, 10.0]], dtype=dt), np.zeros(2), 0.0)
+    assert m.transform(np.array([[3.0, 4.0], [1.0, 3.0], [25.0, 15.0]], dtype=dt)).tolist() == [18.0, 5.0, 250.0]
+    m = lb.KMeans(np.array([[0, 0], [1, 2], [20, 0], [0, 20]], dtype=dt), np.zeros(4), 0.0)
+    assert m.predict(np.array([[1, 0.6], [20, 2], [20, 0], [7, 20]], dtype=dt)).tolist() == [0, 2, 2, 3]
+    assert m.predict(np.array([20.0, 2.0], dtype=dt)) == 2  # Ix1 form
+
+
+def test_kat_self_nearest_and_ties(lb, oracle):
+    Cn = oracle.rng(42).uniform_f64(-100.0, 100.0, (20, 5))
+    m = lb.KMeans(Cn, np.zeros(20), 0.0)
+    assert m.predict(Cn).tolist() == list(range(20))
+    assert (m.transform(Cn) == 0).all()
+    m = lb.KMeans(np.array([[2.0, 0.0], [0.0, 2.0], [2.0, 0.0]]), np.zeros(3), 0.0)
+    assert m.predict(np.array([[1.0, 1.0], [2.0, 0.0]])).tolist() == [0, 0]  # strict '<': lowest index
+
+
+def test_kat_membership_counts(lb, ctx):
+    Cn = np.array([[0.0, 1.0], [40.0, 10.0], [3.0, 9.0]])
+    X = np.array([[3.0, 4.0], [1.0, 3.0], [25.0, 15.0]])
+    labels, _ = ctx.assign(Cn, X)
+    assert np.bincount(labels.astype(int), minlength=3).tolist() == [2, 1, 0]
+
+
+@pytest.mark.parametrize("dt", DTYPES)
+def test_kat_tolerance_step(lb, dt):
+    X = np.array([[1.0, 1.0], [11.0, 11.0]], dtype=dt)
+    p = (lb.KMeans.params_with_rng(1, lb.Xoshiro256Plus.seed_from_u64(45)).tolerance(8.5)
+         .init_method(lb.KMeansInit.Precomputed(np.array([[0.0, 0.0]], dtype=dt))))
+    m = p.fit(lb.DatasetBase(X))
+    assert m.centroids().tolist() == [[4.0, 4.0]]
+    assert lb.Context.default().last_stats.n_iter == 1
+    assert p.fit_with(None, lb.DatasetBase(X)) is not None  # converges on the first batch
+
+
+def test_kat_six_points(lb):
+    X = np.array([[0, 0], [1, 0], [0, 1], [10, 10], [11, 10], [10, 11]], dtype=np.float64)
+    m = (lb.KMeans.params(2).n_runs(1).tolerance(1e-4)
+         .init_method(lb.KMeansInit.Precomputed([[0.0, 0.0], [10.0, 10.0]])).fit(lb.DatasetBase(X)))
+    assert lb.Context.default().last_stats.n_iter == 8
+    np.testing.assert_allclose(m.centroids(), [[0.33332825, 0.33332825], [10.33332825, 10.33332825]], atol=1e-8)
+    assert m.predict(X).tolist() == [0, 0, 0, 1, 1, 1]
+    assert m.cluster_count().tolist() == [3.0, 3.0]
+    assert abs(m.inertia() - 0.4444444453) < 1e-9
+
+
+def test_kat_empty_cluster_keeps_centroid(lb, ctx):
+    # algorithm.rs:1117-1125 through one Lloyd iteration
+    ctx.set_data(np.array([[1.0, 2.0]]))
+    c, counts, inertia, st = ctx.lloyd_iters(np.ones((2, 2)), 1, 1e-30)
+    assert c.tolist() == [[1.0, 1.5], [1.0, 1.0]] and counts.tolist() == [1.0, 0.0] and inertia == 1.0
+
+
+def test_kat_incremental(lb):
+    # algorithm.rs:1180-1202
+    model = lb.KMeans(np.array([[-1.0, -1.0], [3.0, 4.0], [7.0, 8.0]]), np.zeros(3), 0.0)
+    p = lb.KMeans.params_with_rng(3, lb.Xoshiro256Plus.seed_from_u64(45)).tolerance(100.0)
+    model = p.fit_with(model, lb.DatasetBase(np.array([[-1.0, -3.0], [0.0, 0.0], [3.0, 5.0], [5.0, 5.0]])))
+    np.testing.assert_allclose(model.centroids(), [[-0.5, -1.5], [4, 5], [7, 8]], atol=1e-12)
+    model = p.fit_with(model, lb.DatasetBase(np.array([[-5.0, -5.0], [0.0, 0.0], [10.0, 10.0]])))
+    np.testing.assert_allclose(model.centroids(), [[-6 / 4, -8 / 4], [4, 5], [10, 10]], atol=1e-12)
+    assert model.cluster_count().tolist() == [3.0, 3.0, 1.0]
+
+
+# ---- assignment parity on random blobs ----
+SHAPES = [(1000, 2, 3), (777, 3, 1), (5000, 8, 16), (3001, 32, 64), (2049, 64, 256), (1500, 128, 256),
+          (900, 5, 7), (4100, 50, 5), (1024, 16, 1024), (300, 1, 4), (2600, 12, 33)]
+
+
+@pytest.mark.parametrize("dt", DTYPES)
+@pytest.mark.parametrize("n,d,k", SHAPES)
+def test_assign_matches_oracle_bitwise(lb, ctx, oracle, n, d, k, dt):
+    X, _ = blobs(n, d, max(1, min(k, 20)), dt, seed=n + d + k)
+    g = np.random.default_rng(k)
+    Cn = X[g.choice(n, size=k, replace=k > n)] + (g.standard_normal((k, d)) * 0.5).astype(dt)
+    labels, dists = ctx.assign(Cn.astype(dt), X)
+    ref_l, ref_d = oracle.assign(X, Cn.astype(dt))
+    assert (labels == ref_l).all()
+    assert (dists == ref_d).all()  # bit-identical
+
+
+@pytest.mark.parametrize("dt", DTYPES)
+def test_assign_strided_and_resident(lb, ctx, oracle, dt):
+    X, _ = blobs(1200, 6, 4, dt, seed=5)
+    wide = np.zeros((1200, 10), dtype=dt)
+    wide[:, :6] = X
+    view = wide[:, :6]  # row stride 10
+    Cn = X[:9].copy()
+    l1, d1 = ctx.assign(Cn, view)
+    ref_l, ref_d = oracle.assign(X, Cn)
+    assert (l1 == ref_l).all() and (d1 == ref_d).all()
+    ctx.set_data(view)
+    l2, d2 = ctx.assign(Cn, None)
+    assert (l2 == ref_l).all() and (d2 == ref_d).all()
+    np.testing.assert_array_equal(ctx.get_data(), X)
+
+
+def test_predict_length_mismatch_rejected(lb):
+    m = lb.KMeans(np.zeros((2, 2)), np.zeros(2), 0.0)
+    with pytest.raises(AssertionError):
+        m.predict_inplace(np.zeros((5, 2)), np.zeros(4, dtype=np.uint64))
+
+
+# ---- Lloyd parity from Precomputed centroids ----
+LLOYD_CASES = [(10000, 2, 3, 3), (4000, 3, 10, 10), (30000, 3, 10, 10), (20000, 32, 64, 64), (6000, 8, 16, 16),
+               (5000, 16, 12, 30), (3000, 64, 8, 8), (2000, 128, 256, 16), (9000, 4, 40, 13)]
+
+
+@pytest.mark.parametrize("dt", DTYPES)
+@pytest.mark.parametrize("n,d,k,k_true", LLOYD_CASES)
+def test_lloyd_matches_oracle(lb, ctx, oracle, n, d, k, k_true, dt):
+    X, _ = blobs(n, d, k_true, dt, seed=n + k)
+    g = np.random.default_rng(d)
+    init = X[g.choice(n, size=k, replace=False)].copy()
+    tol = 1e-4
+    ref = oracle.fit(X, k, oracle.rng(1), n_runs=1, max_iter=25, tol=tol, method=INIT_PRECOMPUTED, precomputed=init,
+                     acc_f64=True)
+    faithful = oracle.fit(X, k, oracle.rng(1), n_runs=1, max_iter=25, tol=tol, method=INIT_PRECOMPUTED,
+                          precomputed=init)
+    m = (lb.KMeans.params(k).n_runs(1).max_n_iterations(25).tolerance(tol)
+         .init_method(lb.KMeansInit.Precomputed(init)).fit(lb.DatasetBase(X)))
+    st = ctx.last_stats
+    assert abs(int(st.n_iter) - ref["n_iter"]) <= 1, (st.n_iter, ref["n_iter"], st.last_shift)
+    rt = RTOL[dt]
+    if int(st.n_iter) == ref["n_iter"]:
+        scale = np.abs(ref["centroids"]).max()
+        np.testing.assert_allclose(m.centroids(), ref["centroids"], rtol=rt, atol=rt * scale)
+        np.testing.assert_allclose(m.inertia(), ref["inertia"], rtol=rt)
+        assert m.cluster_count().tolist() == ref["cluster_count"].tolist()
+        # the F-faithful oracle's own deviation from the f64-accumulated one, for the record
+        dev = np.abs(faithful["centroids"] - ref["centroids"]).max() / scale
+        assert dev < 1e-3
+    # labels: identical to the reference's assignment for the same centroids
+    labels = m.predict(X)
+    ref_l, ref_d = oracle.assign(X, m.centroids())
+    assert (labels == ref_l).all()
+    assert (m.transform(X) == ref_d).all()
+
+
+@pytest.mark.parametrize("dt", DTYPES)
+def test_lloyd_fixed_iterations_no_convergence(lb, ctx, oracle, dt):
+    X, _ = blobs(8000, 8, 5, dt, seed=11)
+    init = X[[1, 50, 900, 4000, 7000, 7999]].copy()
+    tiny = float(np.finfo(dt).tiny)
+    ctx.set_data(X)
+    c, counts, inertia, st = ctx.lloyd_iters(init, 20, tiny)
+    assert st.n_iter == 20
+    ref = oracle.fit(X, 6, oracle.rng(1), n_runs=1, max_iter=20, tol=tiny, method=INIT_PRECOMPUTED, precomputed=init,
+                     acc_f64=True)
+    rt = RTOL[dt]
+    np.testing.assert_allclose(c, ref["centroids"], rtol=rt, atol=rt * np.abs(ref["centroids"]).max())
+    np.testing.assert_allclose(inertia / 8000, ref["inertia"], rtol=rt)
+    assert counts.tolist() == ref["cluster_count"].tolist()
+
+
+def test_lloyd_is_run_to_run_reproducible(lb, ctx):
+    X, _ = blobs(50000, 16, 20, np.float32, seed=3)
+    init = X[::2500].copy()
+    ctx.set_data(X)
+    a = ctx.lloyd_iters(init, 10, 1e-30)
+    b = ctx.lloyd_iters(init, 10, 1e-30)
+    assert (a[0] == b[0]).all() and a[2] == b[2] and (a[1] == b[1]).all()
+
+
+# ---- edge cases ----
+def test_edge_cases(lb, oracle):
+    X = np.array([[1.0, 2.0], [3.0, 4.0], [5.0, 6.0], [7.0, 8.0]])
+    m = lb.KMeans.params(1).fit(lb.DatasetBase(X))
+    np.testing.assert_allclose(m.centroids(), [[4.0, 5.0]], atol=1e-4)
+    Y = np.array([[1.0, 2.0], [10.0, 20.0], [-5.0, -5.0], [100.0, 0.0]])
+    m = lb.KMeans.params(4).init_method(lb.KMeansInit.Precomputed(Y)).fit(lb.DatasetBase(Y))
+    assert m.inertia() == 0.0
+    m = lb.KMeans.params(1).fit(lb.DatasetBase(np.full((4, 2), 5.0)))
+    np.testing.assert_allclose(m.centroids(), [[5.0, 5.0]], atol=1e-10)
+    assert abs(m.inertia()) < 1e-10
+    m = lb.KMeans.params(1).fit(lb.DatasetBase(np.array([[3.0, 7.0]])))
+    assert m.centroids().tolist() == [[3.0, 7.0]] and m.inertia() == 0.0
+
+
+def test_nan_data_is_inertia_error(lb):
+    with pytest.raises(lb.KMeansError) as e:
+        (lb.KMeans.params(2).n_runs(2).init_method(lb.KMeansInit.Precomputed(np.zeros((2, 2))))
+         .fit(lb.DatasetBase(np.full((8, 2), np.nan))))
+    assert e.value.kind == "InertiaError"
+
+
+def test_precomputed_wrong_shape_panics(lb):
+    with pytest.raises(AssertionError):
+        lb.KMeans.params(3).init_method(lb.KMeansInit.Precomputed(np.zeros((2, 2)))).fit(np.zeros((10, 2)))
+
+
+def test_native_param_errors(lb, ctx):
+    # the C ABI validates too (a Rust binding may skip its own ParamGuard)
+    from linfa_b200 import _ffi
+    import ctypes as C
+
+    ctx.set_data(np.zeros((4, 2)))
+    for field, val, code in [("n_clusters", 0, 10), ("n_runs", 0, 11), ("tolerance", 0.0, 12),
+                             ("max_n_iterations", 0, 13)]:
+        p = _ffi.lkm_params(1, 1, 5, 1e-4, _ffi.INIT_RANDOM, 0, 0, 0, None, 0, 0)
+        setattr(p, field, val)
+        out = np.zeros(8)
+        st = _ffi.lib.lkm_fit_f64(ctx.h, C.byref(p), _ffi.make_rng(lb.Xoshiro256Plus.seed_from_u64(1)),
+                                  _ffi.fptr(out, C.c_double), _ffi.fptr(out, C.c_double), _ffi.fptr(out, C.c_double), None)
+        assert st == code
+
+
+# ---- seeding ----
+@pytest.mark.parametrize("dt", DTYPES)
+def test_random_init_matches_oracle(lb, oracle, dt):
+    X, _ = blobs(5000, 4, 5, dt, seed=8)
+    for k, seed in [(3, 42), (11, 7), (40, 9), (200, 3)]:
+        got = lb.KMeans.params_with_rng(k, lb.Xoshiro256Plus.seed_from_u64(seed)).init_method(
+            lb.KMeansInit.Random).check().init_centroids(X)
+        want = oracle.init(INIT_RANDOM, k, X, oracle.rng(seed))
+        assert (got == want).all()
+
+
+@pytest.mark.parametrize("dt", DTYPES)
+@pytest.mark.parametrize("n,d,k", [(3000, 3, 10), (20000, 8, 24), (100000, 32, 16)])
+def test_kmeanspp_exact_matches_oracle(lb, oracle, n, d, k, dt):
+    X, _ = blobs(n, d, k, dt, seed=n)
+    got = lb.KMeans.params_with_rng(k, lb.Xoshiro256Plus.seed_from_u64(40)).init_method(
+        lb.KMeansInit.KMeansPlusPlus).check().init_centroids(X)
+    want = oracle.init(INIT_KMEANSPP, k, X, oracle.rng(40))
+    assert (got == want).all()  # same row picks, in the same order
+
+
+def test_kmeanspp_default_fit_matches_oracle(lb, oracle):
+    # the reference's bench configuration (benches/k_means.rs:36-77): k-means++, n_runs 10, tol 1e-3
+    X, _ = blobs(4000, 3, 10, np.float64, seed=40)
+    m = (lb.KMeans.params_with_rng(10, lb.Xoshiro256Plus.seed_from_u64(40)).max_n_iterations(1000).tolerance(1e-3)
+         .fit(lb.DatasetBase(X)))
+    ref = oracle.fit(X, 10, oracle.rng(40), n_runs=10, max_iter=1000, tol=1e-3, method=INIT_KMEANSPP, acc_f64=True)
+    np.testing.assert_allclose(m.centroids(), ref["centroids"], rtol=1e-9, atol=1e-9)
+    np.testing.assert_allclose(m.inertia(), ref["inertia"], rtol=1e-10)
+    assert m.cluster_count().tolist() == ref["cluster_count"].tolist()
+
+
+def test_weighted_zero_weight_never_picked_via_para(lb):
+    # statistical tests of init.rs:372-449 for ++ (fast mode) and ||
+    g = np.random.default_rng(0)
+    X = np.concatenate([g.standard_normal((50, 2)) + c for c in (20.0, -1000.0, 1000.0)])
+    for init in (lb.KMeansInit.KMeansPlusPlus, lb.KMeansInit.KMeansPara):
+        for mode in (lb.PickMode.Exact, lb.PickMode.Fast):
+            for seed in range(5):
+                out = (lb.KMeans.params_with_rng(3, lb.Xoshiro256Plus.seed_from_u64(seed)).init_method(init)
+                       .pick_mode(mode).check().init_centroids(X))
+                found = set()
+                for row in out:
+                    idx = np.where((X == row).all(axis=1))[0]
+                    assert idx.size >= 1
+                    found.add(int(idx[0]) // 50)
+                assert found == {0, 1, 2}
+    # degenerate n < k does not fail and duplicates the point (init.rs:374-377)
+    for init in (lb.KMeansInit.KMeansPlusPlus, lb.KMeansInit.KMeansPara):
+        out = lb.KMeans.params(2).init_method(init).check().init_centroids(np.array([[1.0, 2.0]]))
+        assert out.tolist() == [[1.0, 2.0], [1.0, 2.0]]
+
+
+def test_init_losses_beat_random(lb, ctx, oracle):
+    g = np.random.default_rng(1)
+    X = np.concatenate([g.standard_normal((50, 2)) + c for c in (20.0, -1000.0, 1000.0)])
+    rng = lb.Xoshiro256Plus.seed_from_u64(42)
+
+    def loss(init, mode=lb.PickMode.Exact):
+        c = lb.KMeans.params_with_rng(3, rng.clone()).init_method(init).pick_mode(mode).check().init_centroids(X)
+        return ctx.assign(c, X)[1].sum()
+
+    l_rand = loss(lb.KMeansInit.Random)
+    assert loss(lb.KMeansInit.KMeansPlusPlus) < l_rand
+    assert loss(lb.KMeansInit.KMeansPlusPlus, lb.PickMode.Fast) < l_rand
+    assert loss(lb.KMeansInit.KMeansPara) < l_rand
+
+
+def test_fast_pick_cost_close_to_exact(lb, ctx):
+    X, _ = blobs(200000, 16, 32, np.float32, seed=2)
+    costs = {}
+    for mode in (lb.PickMode.Exact, lb.PickMode.Fast):
+        c = (lb.KMeans.params_with_rng(32, lb.Xoshiro256Plus.seed_from_u64(5)).pick_mode(mode).check()
+             .init_centroids(X))
+        costs[mode] = float(ctx.assign(c, X)[1].astype(np.float64).sum())
+    assert costs[lb.PickMode.Fast] <= 1.5 * costs[lb.PickMode.Exact]
+
+
+# ---- self-consistency families (algorithm.rs:1015-1077) ----
+@pytest.mark.parametrize("init", ["Random", "KMeansPlusPlus", "KMeansPara"])
+def test_n_runs_consistency(lb, oracle, init):
+    data = make_1d_dataset(oracle)
+    rng = lb.Xoshiro256Plus.seed_from_u64(42)
+    for _ in range(100):
+        rng.next_u64()
+    im = getattr(lb.KMeansInit, init)
+    m = lb.KMeans.params_with(3, rng.clone(), lb.L2Dist()).n_runs(1).init_method(im).fit(lb.DatasetBase(data))
+    clusters = m.predict(lb.DatasetBase(data))
+    inertia = sum(oracle.sq_l2_dist(data[i], m.centroids()[int(clusters.targets[i])]) for i in range(100))
+    assert abs(inertia - m.transform(data).sum()) < 1e-5
+    assert m.predict(data[0]) == clusters.targets[0]
+    m2 = lb.KMeans.params_with(3, rng.clone(), lb.L2Dist()).init_method(im).fit(lb.DatasetBase(data))
+    if init == "Random":
+        assert m2.transform(data).sum() <= m.transform(data).sum()
+    if init != "KMeansPara":  # k-means|| has no deterministic reference
+        ref = oracle.fit(data, 3, _skip100(oracle), n_runs=1,
+                         method=INIT_RANDOM if init == "Random" else INIT_KMEANSPP, acc_f64=True)
+        np.testing.assert_allclose(m.centroids(), ref["centroids"], rtol=1e-9, atol=1e-9)
+
+
+def _skip100(oracle):
+    r = oracle.rng(42)
+    for _ in range(100):
+        r.next_u64()
+    return r
+
+
+def test_max_n_iterations(lb, oracle):
+    data = make_1d_dataset(oracle)
+    m = (lb.KMeans.params_with(6, _py_skip100(lb), lb.L2Dist()).n_runs(1).max_n_iterations(5)
+         .init_method(lb.KMeansInit.Random).fit(lb.DatasetBase(data)))
+    assert lb.Context.default().last_stats.n_iter <= 5 and m.centroids().shape == (6, 2)
+
+
+def _py_skip100(lb):
+    r = lb.Xoshiro256Plus.seed_from_u64(42)
+    for _ in range(100):
+        r.next_u64()
+    return r
+
+
+# ---- device-side blobs ----
+@pytest.mark.parametrize("dt", DTYPES)
+def test_gen_blobs_layout_and_determinism(lb, ctx, dt):
+    centres = np.array([[0.0, 1.0], [-10.0, 20.0], [-1.0, 10.0]], dtype=dt)
+    ctx.gen_blobs(10000, 2, centres, 1.0, seed=7)
+    a = ctx.get_data()
+    ctx.gen_blobs(10000, 2, centres, 1.0, seed=7)
+    assert (ctx.get_data() == a).all()
+    m = 10000 // 3
+    for b in range(3):
+        rows = a[b * m:(b + 1) * m] if b < 2 else a[2 * m:]
+        assert np.abs(rows.mean(0) - centres[b]).max() < 0.1
+        assert np.abs(rows.std(0) - 1.0).max() < 0.05
+    # a shard generated with a row offset equals the same rows of the whole
+    ctx.gen_blobs(3000, 2, centres, 1.0, seed=7, row_offset=2500, n_global=10000)
+    assert (ctx.get_data() == a[2500:5500]).all()
