@@ -103,6 +103,8 @@ typedef struct lkm_stats {
   uint32_t kernel_launches;  /* kernels this library launched in the call */
   uint32_t assign_path;      /* 0 exact CUDA-core, 1 certified FMA, 2 tcgen05 3xTF32 */
   uint64_t fallback_rows;    /* rows re-evaluated in exact form by the certified paths */
+  float main_kernel_ms;      /* with lkm_set_l2_flush: summed duration of the assign/fused kernel alone */
+  uint32_t reserved;
 } lkm_stats;
 
 /* -- context ------------------------------------------------------------- */
@@ -197,6 +199,11 @@ lkm_status lkm_fit_with_f64(lkm_ctx* ctx, const lkm_params* p, lkm_rng rng, int 
 /* -- knobs that are not in the reference (all have defaults) --------------- */
 /* force an assignment path: -1 auto (default), 0 exact, 1 certified FMA, 2 tcgen05 */
 lkm_status lkm_set_assign_path(lkm_ctx* ctx, int path);
+/* measurement hygiene for benchmarks: when bytes > 0 every Lloyd iteration is
+ * timed with its own CUDA events and a scratch buffer of `bytes` is overwritten
+ * between iterations (outside the timed spans) so that the observations are
+ * read from HBM, not from L2.  0 (default) turns it off. */
+lkm_status lkm_set_l2_flush(lkm_ctx* ctx, uint64_t bytes);
 
 #ifdef __cplusplus
 }

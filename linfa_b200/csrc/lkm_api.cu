@@ -87,6 +87,9 @@ struct lkm_ctx {
   uint64_t n = 0, d = 0;
   uint64_t row_offset = 0, n_global = 0;
   int force_path = -1;
+  uint64_t flush_bytes = 0;
+  DevBuf flushbuf;
+  std::vector<cudaEvent_t> iter_events;
   // workspaces
   DevBuf cbuf, part_sums, part_counts, part_inertia, shift_part, counts_out, state, gather, labels, dists, wdists,
       cum, scratch, tmpx, tmpc, idxbuf, bsum, weights;
@@ -258,7 +261,7 @@ static cudaError_t launch_finalize(const FinalizeArgs<F, S, CT>& a, cudaStream_t
 struct LloydOut {
   uint64_t n_iter = 0;
   double inertia = 0, shift = 0;
-  float ms = 0;
+  float ms = 0, main_ms = 0;
   int final_buf = 0;
 };
 
@@ -305,6 +308,16 @@ static lkm_status run_lloyd(lkm_ctx* ctx, F* dC2, uint64_t k, uint64_t max_iter,
   if (ctx->world > 1) CK(ctx->gather.ensure((size_t)ctx->world * L * 8));
   LloydState* dstate = ctx->state.as<LloydState>();
   CK(cudaMemsetAsync(dstate, 0, sizeof(LloydState), ctx->stream));
+  const bool flush = ctx->flush_bytes > 0;
+  if (flush) {
+    if (max_iter > 100000) return fail(ctx, LKM_ERR_INVALID_ARG, "l2 flush mode is for short benchmark runs");
+    CK(ctx->flushbuf.ensure(ctx->flush_bytes));
+    while (ctx->iter_events.size() < 3 * max_iter) {
+      cudaEvent_t e;
+      CK(cudaEventCreate(&e));
+      ctx->iter_events.push_back(e);
+    }
+  }
   CK(cudaEventRecord(ctx->ev0, ctx->stream));
 
   uint64_t launched = 0;
@@ -315,6 +328,10 @@ static lkm_status run_lloyd(lkm_ctx* ctx, F* dC2, uint64_t k, uint64_t max_iter,
       const uint64_t it = launched + q;
       const F* Ccur = dC2 + (it & 1) * kd;
       F* Cnext = dC2 + ((it + 1) & 1) * kd;
+      if (flush) {
+        CK(cudaMemsetAsync(ctx->flushbuf.p, (int)(it & 0xff), ctx->flush_bytes, ctx->stream));
+        CK(cudaEventRecord(ctx->iter_events[3 * it], ctx->stream));
+      }
       if (pf.fused) {
         LloydArgs<F> a{};
         a.X = dX; a.n = n; a.d = (int)d; a.k = (int)k; a.C = Ccur;
@@ -345,6 +362,7 @@ static lkm_status run_lloyd(lkm_ctx* ctx, F* dC2, uint64_t k, uint64_t max_iter,
           ctx->launches++;
         }
       }
+      if (flush) CK(cudaEventRecord(ctx->iter_events[3 * it + 1], ctx->stream));
       // combine the per-CTA partials in fixed order, then the m_k-means update
       if (ctx->world == 1) {
         FinalizeArgs<F, F, uint32_t> fa{};
@@ -374,6 +392,7 @@ static lkm_status run_lloyd(lkm_ctx* ctx, F* dC2, uint64_t k, uint64_t max_iter,
         CK((launch_finalize<F, double, double, true>(fa, ctx->stream)));
         ctx->launches += 3;
       }
+      if (flush) CK(cudaEventRecord(ctx->iter_events[3 * it + 2], ctx->stream));
     }
     launched += todo;
     CK(cudaMemcpyAsync(ctx->h_state, dstate, sizeof(LloydState), cudaMemcpyDeviceToHost, ctx->stream));
@@ -384,6 +403,17 @@ static lkm_status run_lloyd(lkm_ctx* ctx, F* dC2, uint64_t k, uint64_t max_iter,
   CK(cudaEventSynchronize(ctx->ev1));
   CK(cudaEventElapsedTime(&out.ms, ctx->ev0, ctx->ev1));
   out.n_iter = ctx->h_state->n_iter;
+  if (flush) {
+    // per-iteration spans only (the flush writes sit between them)
+    out.ms = 0;
+    for (uint64_t it = 0; it < launched; ++it) {
+      float a = 0, b = 0;
+      CK(cudaEventElapsedTime(&a, ctx->iter_events[3 * it], ctx->iter_events[3 * it + 2]));
+      CK(cudaEventElapsedTime(&b, ctx->iter_events[3 * it], ctx->iter_events[3 * it + 1]));
+      out.ms += a;
+      out.main_ms += b;
+    }
+  }
   out.inertia = ctx->h_state->inertia;
   out.shift = ctx->h_state->shift;
   out.final_buf = (int)(out.n_iter & 1);
@@ -681,6 +711,7 @@ static lkm_status lloyd_iters_impl(lkm_ctx* ctx, F* centroids_inout, uint64_t k,
     std::memset(stats, 0, sizeof(*stats));
     stats->n_iter = lo.n_iter; stats->last_shift = lo.shift; stats->inertia_total = lo.inertia;
     stats->device_ms = lo.ms; stats->kernel_launches = ctx->launches; stats->assign_path = 0;
+    stats->main_kernel_ms = lo.main_ms;
   }
   return LKM_OK;
 }
@@ -897,8 +928,9 @@ LKM_EXPORT lkm_status lkm_destroy(lkm_ctx* ctx) {
   if (ctx->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->comm);
   DevBuf* bufs[] = {&ctx->xbuf, &ctx->cbuf, &ctx->part_sums, &ctx->part_counts, &ctx->part_inertia, &ctx->shift_part,
                     &ctx->counts_out, &ctx->state, &ctx->gather, &ctx->labels, &ctx->dists, &ctx->wdists, &ctx->cum,
-                    &ctx->scratch, &ctx->tmpx, &ctx->tmpc, &ctx->idxbuf, &ctx->bsum, &ctx->weights};
+                    &ctx->scratch, &ctx->tmpx, &ctx->tmpc, &ctx->idxbuf, &ctx->bsum, &ctx->weights, &ctx->flushbuf};
   for (DevBuf* b : bufs) b->release();
+  for (cudaEvent_t e : ctx->iter_events) cudaEventDestroy(e);
   if (ctx->h_state) cudaFreeHost(ctx->h_state);
   if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
@@ -918,6 +950,12 @@ LKM_EXPORT lkm_status lkm_synchronize(lkm_ctx* ctx) {
 LKM_EXPORT lkm_status lkm_set_assign_path(lkm_ctx* ctx, int path) {
   if (!ctx || path < -1 || path > 2) return LKM_ERR_INVALID_ARG;
   ctx->force_path = path;
+  return LKM_OK;
+}
+
+LKM_EXPORT lkm_status lkm_set_l2_flush(lkm_ctx* ctx, uint64_t bytes) {
+  if (!ctx) return LKM_ERR_INVALID_ARG;
+  ctx->flush_bytes = bytes;
   return LKM_OK;
 }
 

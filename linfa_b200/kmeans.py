@@ -177,13 +177,15 @@ class Context:
     def set_assign_path(self, path):
         self.check(_ffi.lib.lkm_set_assign_path(self.h, path))
 
+    def set_l2_flush(self, nbytes):
+        self.check(_ffi.lib.lkm_set_l2_flush(self.h, int(nbytes)))
+
     def set_data(self, x):
         x = np.asarray(x)
         if x.ndim != 2:
             raise ValueError("records must be 2-dimensional (n_observations, n_features)")
         sfx, ct = _ffi.sfx_of(x.dtype)
-        if x.strides[1] != x.itemsize or x.strides[0] < x.shape[1] * x.itemsize or x.strides[0] % x.itemsize:
-            x = np.ascontiguousarray(x)  # arbitrary ndarray layout -> standard layout
+        x = _row_major_view(x)
         self._keep = x
         self.check(getattr(_ffi.lib, f"lkm_set_data_{sfx}")(self.h, _ffi.fptr(x, ct), x.shape[0], x.shape[1],
                                                             x.strides[0] // x.itemsize))
@@ -231,9 +233,7 @@ class Context:
             n, d = self.shape
             xp, stride = None, d
         else:
-            x = np.asarray(x, dtype=c.dtype)
-            if x.strides[1] != x.itemsize or x.strides[0] < x.shape[1] * x.itemsize or x.strides[0] % x.itemsize:
-                x = np.ascontiguousarray(x)
+            x = _row_major_view(np.asarray(x, dtype=c.dtype))
             n, d = x.shape
             xp, stride = _ffi.fptr(x, ct), x.strides[0] // x.itemsize
         if c.shape[1] != d:
@@ -243,6 +243,15 @@ class Context:
         self.check(getattr(_ffi.lib, f"lkm_assign_{sfx}")(self.h, _ffi.fptr(c, ct), c.shape[0], xp, n, d, stride,
                                                           _ffi.fptr(labels, C.c_uint64), _ffi.fptr(dists, ct)))
         return labels, dists
+
+
+def _row_major_view(x):
+    """An ndarray view whose rows are contiguous (any row stride >= n_features) is passed as is,
+    like an ndarray ArrayView2; anything else is copied to standard layout."""
+    if (x.shape[0] <= 1 or x.shape[1] == 0 or x.strides[1] != x.itemsize
+            or x.strides[0] < x.shape[1] * x.itemsize or x.strides[0] % x.itemsize):
+        return np.ascontiguousarray(x)
+    return x
 
 
 def _records(dataset):
