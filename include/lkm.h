@@ -161,7 +161,8 @@ lkm_status lkm_init_f64(lkm_ctx* ctx, const lkm_params* p, lkm_rng rng, double* 
 
 /* -- the loop body of fit_lloyd (KM/algorithm.rs:314-331) as a benchmark /
  * resume entry: runs Lloyd iterations from centroids_inout until the shift
- * drops below `tolerance` or `max_iters` iterations ran.  cluster_count_out
+ * drops below `tolerance` or `max_iters` iterations ran.  tolerance = 0 runs
+ * exactly max_iters iterations (a shift is never < 0).  cluster_count_out
  * and inertia_total_out (sum, not mean) may be NULL. */
 lkm_status lkm_lloyd_iters_f32(lkm_ctx* ctx, float* centroids_inout, uint64_t k, uint64_t max_iters,
                                double tolerance, float* cluster_count_out, float* inertia_total_out,

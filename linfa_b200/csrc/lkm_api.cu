@@ -133,7 +133,7 @@ static lkm_status fail(lkm_ctx* ctx, lkm_status s, const char* msg) {
 // ---- launch helpers ----------------------------------------------------------
 struct Plan {
   bool ok = false;
-  int vec = 0, x_stride = 0;
+  int vec = 0, x_stride = 0, tpr = 1;
   size_t tile_bytes = 0;
   // fused
   bool fused = false;
@@ -142,15 +142,21 @@ struct Plan {
   int grid = 0;
 };
 
-template <typename F> static void tile_layout(uint64_t d, const void* X, int& vec, int& x_stride, size_t& tile_bytes) {
+static bool has_static_d(uint64_t d) { return d == 2 || d == 3 || d == 4 || d == 8 || d == 16 || d == 32; }
+
+template <typename F> static void tile_layout(uint64_t d, const void* X, Plan& p) {
   const size_t rowbytes = d * sizeof(F);
-  vec = (rowbytes % 16 == 0) && ((reinterpret_cast<uintptr_t>(X) & 15) == 0);
+  p.vec = (rowbytes % 16 == 0) && ((reinterpret_cast<uintptr_t>(X) & 15) == 0);
   size_t stride_bytes;
-  if (vec) stride_bytes = ((rowbytes / 16) % 2 == 1) ? rowbytes : rowbytes + 16;
+  if (p.vec) stride_bytes = ((rowbytes / 16) % 2 == 1) ? rowbytes : rowbytes + 16;
   else stride_bytes = (size_t)(d | 1) * sizeof(F);
-  x_stride = (int)(stride_bytes / sizeof(F));
-  tile_bytes = std::max<size_t>((size_t)kThreads * stride_bytes, 2048);
-  tile_bytes = (tile_bytes + 15) & ~(size_t)15;
+  p.x_stride = (int)(stride_bytes / sizeof(F));
+  // wide rows: several threads share a row so that the tile stays near 64 KB
+  p.tpr = 1;
+  if (!has_static_d(d))
+    while (p.tpr < 32 && (size_t)(kThreads / p.tpr) * stride_bytes > 64 * 1024) p.tpr *= 2;
+  p.tile_bytes = std::max<size_t>((size_t)(kThreads / p.tpr) * stride_bytes, 2048);
+  p.tile_bytes = (p.tile_bytes + 15) & ~(size_t)15;
 }
 
 static size_t al16(size_t x) { return (x + 15) & ~(size_t)15; }
@@ -197,7 +203,7 @@ template <typename F, int MODE> static int occupancy(int d, size_t smem) {
 
 // smem plan for MODE_ASSIGN (assignment only; centroids chunked over k if needed)
 template <typename F> static lkm_status plan_assign(lkm_ctx* ctx, const void* X, uint64_t n, uint64_t d, uint64_t k, Plan& p) {
-  tile_layout<F>(d, X, p.vec, p.x_stride, p.tile_bytes);
+  tile_layout<F>(d, X, p);
   const size_t limit = ctx->smem_optin - 1024;
   if (p.tile_bytes + al16(d * sizeof(F)) > limit) return fail(ctx, LKM_ERR_UNSUPPORTED, "row too wide for the shared-memory tile");
   const size_t c_budget = std::min<size_t>(limit - p.tile_bytes, 96 * 1024);
@@ -205,7 +211,7 @@ template <typename F> static lkm_status plan_assign(lkm_ctx* ctx, const void* X,
   if (kc == 0) return fail(ctx, LKM_ERR_UNSUPPORTED, "row too wide for the shared-memory tile");
   p.kc = (int)kc;
   p.smem = al16(kc * d * sizeof(F)) + p.tile_bytes;
-  const uint64_t n_tiles = (n + kThreads - 1) / kThreads;
+  const uint64_t n_tiles = (n + kThreads / p.tpr - 1) / (kThreads / p.tpr);
   const int occ = std::max(1, occupancy<F, MODE_ASSIGN>((int)d, p.smem));
   p.grid = (int)std::min<uint64_t>(std::max<uint64_t>(n_tiles, 1), (uint64_t)ctx->sm_count * occ);
   p.ok = true;
@@ -215,7 +221,7 @@ template <typename F> static lkm_status plan_assign(lkm_ctx* ctx, const void* X,
 // smem plan for the fused iteration (assignment + accumulation in one pass);
 // p.fused = false means "does not fit: use assign + chunked update passes".
 template <typename F> static lkm_status plan_fused(lkm_ctx* ctx, const void* X, uint64_t n, uint64_t d, uint64_t k, Plan& p) {
-  tile_layout<F>(d, X, p.vec, p.x_stride, p.tile_bytes);
+  tile_layout<F>(d, X, p);
   const size_t limit = ctx->smem_optin - 1024;
   const size_t kdF = k * d * sizeof(F);
   const size_t fixed = p.tile_bytes + al16(kdF) + al16(k * 4) + kThreads * 4 + 64;
@@ -229,7 +235,7 @@ template <typename F> static lkm_status plan_fused(lkm_ctx* ctx, const void* X, 
   p.n_subsets = subsets;
   p.kc = (int)k;
   p.smem = al16(kdF) + p.tile_bytes + al16((size_t)subsets * kdF) + al16((size_t)subsets * k * 4) + kThreads * 4;
-  const uint64_t n_tiles = (n + kThreads - 1) / kThreads;
+  const uint64_t n_tiles = (n + kThreads / p.tpr - 1) / (kThreads / p.tpr);
   const int occ = std::max(1, occupancy<F, MODE_FUSED>((int)d, p.smem));
   p.grid = (int)std::min<uint64_t>(std::max<uint64_t>(n_tiles, 1), (uint64_t)ctx->sm_count * occ);
   p.ok = true;
@@ -246,6 +252,7 @@ static lkm_status run_assign(lkm_ctx* ctx, const F* dX, uint64_t n, uint64_t d, 
   a.X = dX; a.n = n; a.d = (int)d; a.k = (int)k; a.C = dC;
   a.labels = labels; a.dists = dists; a.min_combine = min_combine; a.weights = weights; a.wdists = wdists;
   a.n_subsets = 1; a.x_stride = p.x_stride; a.kc = p.kc; a.chunk_base = 0; a.chunk_rows = (int)k; a.vec = p.vec;
+  a.tpr = p.tpr;
   CK((launch_lloyd<F, MODE_ASSIGN>(a, p.grid, p.smem, ctx->stream)));
   ctx->launches++;
   return LKM_OK;
@@ -290,7 +297,7 @@ static lkm_status run_lloyd(lkm_ctx* ctx, F* dC2, uint64_t k, uint64_t max_iter,
     n_chunks = (int)((k + cr - 1) / cr);
     pu.n_subsets = 1;
     pu.smem = pu.tile_bytes + al16(cr * d * sizeof(F)) + al16(cr * 4) + kThreads * 4;
-    const uint64_t n_tiles = (n + kThreads - 1) / kThreads;
+    const uint64_t n_tiles = (n + kThreads / pu.tpr - 1) / (kThreads / pu.tpr);
     const int occ = std::max(1, occupancy<F, MODE_UPDATE>((int)d, pu.smem));
     pu.grid = (int)std::min<uint64_t>(std::max<uint64_t>(n_tiles, 1), (uint64_t)ctx->sm_count * occ);
     CK(ctx->labels.ensure(std::max<uint64_t>(n, 1) * 4));
@@ -338,14 +345,14 @@ static lkm_status run_lloyd(lkm_ctx* ctx, F* dC2, uint64_t k, uint64_t max_iter,
         a.part_sums = ctx->part_sums.as<F>(); a.part_counts = ctx->part_counts.as<uint32_t>();
         a.part_inertia = ctx->part_inertia.as<double>(); a.state = dstate;
         a.n_subsets = pf.n_subsets; a.x_stride = pf.x_stride; a.kc = pf.kc; a.chunk_base = 0; a.chunk_rows = (int)k;
-        a.vec = pf.vec;
+        a.vec = pf.vec; a.tpr = pf.tpr;
         CK((launch_lloyd<F, MODE_FUSED>(a, pf.grid, pf.smem, ctx->stream)));
         ctx->launches++;
       } else {
         LloydArgs<F> a{};
         a.X = dX; a.n = n; a.d = (int)d; a.k = (int)k; a.C = Ccur;
         a.labels = ctx->labels.as<uint32_t>(); a.dists = ctx->dists.as<F>(); a.state = dstate;
-        a.n_subsets = 1; a.x_stride = pa.x_stride; a.kc = pa.kc; a.chunk_rows = (int)k; a.vec = pa.vec;
+        a.n_subsets = 1; a.x_stride = pa.x_stride; a.kc = pa.kc; a.chunk_rows = (int)k; a.vec = pa.vec; a.tpr = pa.tpr;
         CK((launch_lloyd<F, MODE_ASSIGN>(a, pa.grid, pa.smem, ctx->stream)));
         // inertia: fixed-order f64 partial sums of the min distances, one per source slot
         sum_f64_kernel<F><<<grid, 256, 0, ctx->stream>>>(ctx->dists.as<F>(), n, ctx->part_inertia.as<double>());
@@ -357,7 +364,7 @@ static lkm_status run_lloyd(lkm_ctx* ctx, F* dC2, uint64_t k, uint64_t max_iter,
           u.chunk_base = ch * chunk_rows;
           u.chunk_rows = (int)std::min<uint64_t>(chunk_rows, k - (uint64_t)ch * chunk_rows);
           u.part_sums = ctx->part_sums.as<F>(); u.part_counts = ctx->part_counts.as<uint32_t>();
-          u.state = dstate; u.n_subsets = 1; u.x_stride = pu.x_stride; u.vec = pu.vec;
+          u.state = dstate; u.n_subsets = 1; u.x_stride = pu.x_stride; u.vec = pu.vec; u.tpr = pu.tpr;
           CK((launch_lloyd<F, MODE_UPDATE>(u, pu.grid, pu.smem, ctx->stream)));
           ctx->launches++;
         }
@@ -552,7 +559,8 @@ static lkm_status kmeans_para(lkm_ctx* ctx, const F* dX, uint64_t n, uint64_t d,
   std::vector<double> parts(1024);
   for (uint64_t r = 0; r < n_rounds && !full; ++r) {
     // running min against the candidates added since the last round
-    CKS(run_assign<F>(ctx, dX, n, d, dCand + scanned * d, n_cand - scanned, nullptr, dD, scanned > 0 ? 1 : 0, nullptr, nullptr));
+    if (n_cand > scanned)
+      CKS(run_assign<F>(ctx, dX, n, d, dCand + scanned * d, n_cand - scanned, nullptr, dD, scanned > 0 ? 1 : 0, nullptr, nullptr));
     scanned = n_cand;
     const uint64_t seed = range_incl_u64(rng, 0, 0xFFFFFFFFFFFFFFFEULL);
     sum_f64_kernel<F><<<1024, 256, 0, ctx->stream>>>(dD, n, ctx->part_inertia.as<double>());
@@ -690,7 +698,7 @@ static lkm_status lloyd_iters_impl(lkm_ctx* ctx, F* centroids_inout, uint64_t k,
                                    F* counts_out, F* inertia_total_out, lkm_stats* stats) {
   if (!centroids_inout) return fail(ctx, LKM_ERR_INVALID_ARG, "null argument");
   if (k == 0) return fail(ctx, LKM_ERR_N_CLUSTERS, "n_clusters cannot be 0");
-  if (tolerance <= 0.0) return fail(ctx, LKM_ERR_TOLERANCE, "tolerance must be greater than 0");
+  if (tolerance < 0.0) return fail(ctx, LKM_ERR_TOLERANCE, "tolerance must not be negative");
   if (max_iters == 0) return fail(ctx, LKM_ERR_MAX_ITERATIONS, "max_n_iterations cannot be 0");
   if (ctx->elem != (int)sizeof(F) || !ctx->X) return fail(ctx, LKM_ERR_NO_DATA, "no resident data of this type");
   CK(cudaSetDevice(ctx->device));

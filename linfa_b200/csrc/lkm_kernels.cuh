@@ -70,6 +70,7 @@ template <typename F> struct LloydArgs {
   int chunk_base;        // clusters [chunk_base, chunk_base+chunk_rows) are accumulated
   int chunk_rows;
   int vec;               // rows are 16-byte vectorisable
+  int tpr;               // threads cooperating on one row (power of two <= 32); tile = kThreads/tpr rows
 };
 
 // ---- squared distance, exact reference order ------------------------------
@@ -133,6 +134,34 @@ __device__ __forceinline__ void scan_centroids(const F* __restrict__ cs, int row
   }
 }
 
+// strided variant for `tpr` threads sharing one row: thread q looks at centroids
+// q, q+tpr, ...  Only the seeding thread (q == 0 on the first chunk) starts from
+// d(c_0) like the reference; the others start from "no candidate" (+inf, -1).
+template <typename F>
+__device__ __forceinline__ void scan_centroids_strided(const F* __restrict__ cs, int rows_c, int d, int base,
+                                                       const F* __restrict__ xrow, bool seed, int q, int step,
+                                                       F& best, int& bidx) {
+  int c = q;
+  if (seed) { best = sqdist_mem<F>(cs, xrow, d); bidx = base; c = step; }
+  for (; c < rows_c; c += step) {
+    const F v = sqdist_mem<F>(cs + (size_t)c * d, xrow, d);
+    if (v < best) { best = v; bidx = base + c; }
+  }
+}
+
+// butterfly combine of the per-thread candidates of one row.  A NaN can only be
+// held by the seeding thread (sticky NaN of centroid 0, as in the reference).
+template <typename F>
+__device__ __forceinline__ void combine_candidates(int tpr, F& best, int& bidx) {
+  for (int o = tpr >> 1; o > 0; o >>= 1) {
+    const F ov = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, bidx, o);
+    const bool a_nan = best != best, b_nan = ov != ov;
+    const bool b_wins = b_nan || (!a_nan && oi >= 0 && (bidx < 0 || ov < best || (ov == best && oi < bidx)));
+    if (b_wins) { best = ov; bidx = oi; }
+  }
+}
+
 // coalesced global -> smem copy of `rows` contiguous rows into a padded tile
 template <typename F>
 __device__ __forceinline__ void load_tile(F* __restrict__ xs, const F* __restrict__ g, int rows, int d, int x_stride,
@@ -172,8 +201,10 @@ __global__ void __launch_bounds__(kThreads) lloyd_kernel(const LloydArgs<F> a) {
   size_t off = 0;
   F* cs = reinterpret_cast<F*>(smem_raw + off);
   if (MODE != MODE_UPDATE) off += ((size_t)a.kc * d * sizeof(F) + 15) & ~(size_t)15;
+  const int tpr = (D > 0) ? 1 : a.tpr;
+  const int tile_rows = kThreads / tpr;
   F* xs = reinterpret_cast<F*>(smem_raw + off);
-  off += ((size_t)kThreads * a.x_stride * sizeof(F) + 15) & ~(size_t)15;
+  off += max(((size_t)tile_rows * a.x_stride * sizeof(F) + 15) & ~(size_t)15, (size_t)2048);
   F* acc = reinterpret_cast<F*>(smem_raw + off);
   uint32_t* cnt = nullptr;
   uint32_t* labs = nullptr;
@@ -203,32 +234,49 @@ __global__ void __launch_bounds__(kThreads) lloyd_kernel(const LloydArgs<F> a) {
   F cur_acc = (F)0;
   double inert = 0.0;
 
-  const unsigned long long n_tiles = (a.n + kThreads - 1) / kThreads;
+  const unsigned long long n_tiles = (a.n + tile_rows - 1) / tile_rows;
+  const int my_row = t / tpr, my_q = t - my_row * tpr;
   for (unsigned long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-    const unsigned long long row0 = tile * kThreads;
-    const int rows = (int)min((unsigned long long)kThreads, a.n - row0);
+    const unsigned long long row0 = tile * tile_rows;
+    const int rows = (int)min((unsigned long long)tile_rows, a.n - row0);
     load_tile<F>(xs, a.X + row0 * (unsigned long long)d, rows, d, a.x_stride, a.vec);
     if (MODE == MODE_UPDATE) {
-      if (t < rows) labs[t] = a.labels_in[row0 + t];
+      for (int r = t; r < rows; r += kThreads) labs[r] = a.labels_in[row0 + r];
     }
     __syncthreads();
     if (MODE != MODE_UPDATE) {
       F best = (F)0;
       int bidx = 0;
-      const F* xrow = xs + (size_t)t * a.x_stride;
-      if (n_chunks == 1) {
-        if (t < rows) scan_centroids<F, D>(cs, a.k, d, 0, xrow, true, best, bidx);
+      const bool row_ok = my_row < rows;
+      const F* xrow = xs + (size_t)(row_ok ? my_row : 0) * a.x_stride;
+      if (tpr == 1) {
+        if (n_chunks == 1) {
+          if (row_ok) scan_centroids<F, D>(cs, a.k, d, 0, xrow, true, best, bidx);
+        } else {
+          for (int ch = 0; ch < n_chunks; ++ch) {
+            const int cb = ch * a.kc, rc = min(a.kc, a.k - cb);
+            __syncthreads();
+            for (int e = t; e < rc * d; e += kThreads) cs[e] = a.C[(size_t)cb * d + e];
+            __syncthreads();
+            if (row_ok) scan_centroids<F, D>(cs, rc, d, cb, xrow, ch == 0, best, bidx);
+          }
+        }
       } else {
+        best = (F)INFINITY;
+        bidx = -1;
         for (int ch = 0; ch < n_chunks; ++ch) {
           const int cb = ch * a.kc, rc = min(a.kc, a.k - cb);
-          __syncthreads();
-          for (int e = t; e < rc * d; e += kThreads) cs[e] = a.C[(size_t)cb * d + e];
-          __syncthreads();
-          if (t < rows) scan_centroids<F, D>(cs, rc, d, cb, xrow, ch == 0, best, bidx);
+          if (n_chunks > 1) {
+            __syncthreads();
+            for (int e = t; e < rc * d; e += kThreads) cs[e] = a.C[(size_t)cb * d + e];
+            __syncthreads();
+          }
+          if (row_ok) scan_centroids_strided<F>(cs, rc, d, cb, xrow, ch == 0 && my_q == 0, my_q, tpr, best, bidx);
         }
+        combine_candidates<F>(tpr, best, bidx);
       }
-      if (t < rows) {
-        const unsigned long long row = row0 + t;
+      if (row_ok && my_q == 0) {
+        const unsigned long long row = row0 + my_row;
         if (a.labels) a.labels[row] = (uint32_t)bidx;
         F outd = best;
         if (a.dists) {
@@ -240,7 +288,7 @@ __global__ void __launch_bounds__(kThreads) lloyd_kernel(const LloydArgs<F> a) {
           }
         }
         if (a.wdists) a.wdists[row] = a.weights ? outd * a.weights[row] : outd;
-        if (MODE == MODE_FUSED) { labs[t] = (uint32_t)bidx; inert += (double)best; }
+        if (MODE == MODE_FUSED) { labs[my_row] = (uint32_t)bidx; inert += (double)best; }
       }
       if (MODE == MODE_FUSED) __syncthreads();
     }

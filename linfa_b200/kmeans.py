@@ -187,8 +187,8 @@ class Context:
         sfx, ct = _ffi.sfx_of(x.dtype)
         x = _row_major_view(x)
         self._keep = x
-        self.check(getattr(_ffi.lib, f"lkm_set_data_{sfx}")(self.h, _ffi.fptr(x, ct), x.shape[0], x.shape[1],
-                                                            x.strides[0] // x.itemsize))
+        stride = x.strides[0] // x.itemsize if x.shape[0] > 1 else x.shape[1]
+        self.check(getattr(_ffi.lib, f"lkm_set_data_{sfx}")(self.h, _ffi.fptr(x, ct), x.shape[0], x.shape[1], stride))
         self.dtype, self.shape = x.dtype, x.shape
 
     def set_data_device(self, ptr, n, d, dtype):
@@ -235,7 +235,7 @@ class Context:
         else:
             x = _row_major_view(np.asarray(x, dtype=c.dtype))
             n, d = x.shape
-            xp, stride = _ffi.fptr(x, ct), x.strides[0] // x.itemsize
+            xp, stride = _ffi.fptr(x, ct), (x.strides[0] // x.itemsize if n > 1 else d)
         if c.shape[1] != d:
             raise ValueError("centroids and observations disagree on n_features")
         labels = np.empty(n, dtype=np.uint64) if want_labels else None

@@ -103,7 +103,7 @@ def test_kat_six_points(lb):
 def test_kat_empty_cluster_keeps_centroid(lb, ctx):
     # algorithm.rs:1117-1125 through one Lloyd iteration
     ctx.set_data(np.array([[1.0, 2.0]]))
-    c, counts, inertia, st = ctx.lloyd_iters(np.ones((2, 2)), 1, 1e-30)
+    c, counts, inertia, st = ctx.lloyd_iters(np.ones((2, 2)), 1, 0.0)
     assert c.tolist() == [[1.0, 1.5], [1.0, 1.0]] and counts.tolist() == [1.0, 0.0] and inertia == 1.0
 
 
@@ -115,7 +115,7 @@ def test_kat_incremental(lb):
     np.testing.assert_allclose(model.centroids(), [[-0.5, -1.5], [4, 5], [7, 8]], atol=1e-12)
     model = p.fit_with(model, lb.DatasetBase(np.array([[-5.0, -5.0], [0.0, 0.0], [10.0, 10.0]])))
     np.testing.assert_allclose(model.centroids(), [[-6 / 4, -8 / 4], [4, 5], [10, 10]], atol=1e-12)
-    assert model.cluster_count().tolist() == [3.0, 3.0, 1.0]
+    assert model.cluster_count().tolist() == [4.0, 2.0, 1.0]
 
 
 # ---- assignment parity on random blobs ----
@@ -197,12 +197,12 @@ def test_lloyd_matches_oracle(lb, ctx, oracle, n, d, k, k_true, dt):
 def test_lloyd_fixed_iterations_no_convergence(lb, ctx, oracle, dt):
     X, _ = blobs(8000, 8, 5, dt, seed=11)
     init = X[[1, 50, 900, 4000, 7000, 7999]].copy()
-    tiny = float(np.finfo(dt).tiny)
     ctx.set_data(X)
-    c, counts, inertia, st = ctx.lloyd_iters(init, 20, tiny)
-    assert st.n_iter == 20
-    ref = oracle.fit(X, 6, oracle.rng(1), n_runs=1, max_iter=20, tol=tiny, method=INIT_PRECOMPUTED, precomputed=init,
-                     acc_f64=True)
+    c, counts, inertia, st = ctx.lloyd_iters(init, 4, 0.0)  # tolerance 0: exactly 4 iterations
+    assert st.n_iter == 4
+    ref = oracle.fit(X, 6, oracle.rng(1), n_runs=1, max_iter=4, tol=float(np.finfo(dt).tiny), method=INIT_PRECOMPUTED,
+                     precomputed=init, acc_f64=True)
+    assert ref["n_iter"] == 4
     rt = RTOL[dt]
     np.testing.assert_allclose(c, ref["centroids"], rtol=rt, atol=rt * np.abs(ref["centroids"]).max())
     np.testing.assert_allclose(inertia / 8000, ref["inertia"], rtol=rt)
@@ -213,8 +213,8 @@ def test_lloyd_is_run_to_run_reproducible(lb, ctx):
     X, _ = blobs(50000, 16, 20, np.float32, seed=3)
     init = X[::2500].copy()
     ctx.set_data(X)
-    a = ctx.lloyd_iters(init, 10, 1e-30)
-    b = ctx.lloyd_iters(init, 10, 1e-30)
+    a = ctx.lloyd_iters(init, 10, 0.0)
+    b = ctx.lloyd_iters(init, 10, 0.0)
     assert (a[0] == b[0]).all() and a[2] == b[2] and (a[1] == b[1]).all()
 
 
