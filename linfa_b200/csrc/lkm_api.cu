@@ -19,6 +19,7 @@
 #include "../../include/lkm.h"
 #include "lkm_kernels.cuh"
 #include "lkm_rand.hpp"
+#include "lkm_tc.cuh"
 
 #define LKM_EXPORT extern "C" __attribute__((visibility("default")))
 
@@ -1060,3 +1061,35 @@ LKM_EXPORT lkm_status lkm_set_shard(lkm_ctx* ctx, uint64_t row_offset, uint64_t 
 
 LKM_TYPED(float, f32)
 LKM_TYPED(double, f64)
+
+// ---- development probes (not part of include/lkm.h) ---------------------------------------
+// S[128 x n_c] = X[128 x 32] * C[n_c x 32]^T through the tcgen05 3xTF32 building blocks.
+LKM_EXPORT int lkm_debug_tc_scores(lkm_ctx* ctx, const float* x, const float* c, int n_c, float* s_out) {
+  if (!ctx || !x || !c || !s_out) return LKM_ERR_INVALID_ARG;
+  if (n_c != 64 && n_c != 16 && n_c != 128 && n_c != 256) return LKM_ERR_INVALID_ARG;
+  CK(cudaSetDevice(ctx->device));
+  CK(ctx->tmpx.ensure(128 * 32 * 4));
+  CK(ctx->tmpc.ensure((size_t)n_c * 32 * 4));
+  CK(ctx->dists.ensure((size_t)128 * n_c * 4));
+  CK(ctx->scratch.ensure(64));
+  CK(cudaMemcpyAsync(ctx->tmpx.p, x, 128 * 32 * 4, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->tmpc.p, c, (size_t)n_c * 32 * 4, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemsetAsync(ctx->scratch.p, 0xff, 4, ctx->stream));
+  const size_t smem = 32768 + (size_t)n_c * 256 + 1024;
+  int* st = ctx->scratch.as<int>();
+#define LKM_DBG_LAUNCH(NN)                                                                                          \
+  {                                                                                                                 \
+    CK(cudaFuncSetAttribute(tc_scores_debug_kernel<NN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   \
+    tc_scores_debug_kernel<NN><<<1, 128, smem, ctx->stream>>>(ctx->tmpx.as<float>(), ctx->tmpc.as<float>(),        \
+                                                               ctx->dists.as<float>(), st);                         \
+  }
+  if (n_c == 16) LKM_DBG_LAUNCH(16) else if (n_c == 64) LKM_DBG_LAUNCH(64) else if (n_c == 128) LKM_DBG_LAUNCH(128) else LKM_DBG_LAUNCH(256)
+#undef LKM_DBG_LAUNCH
+  CK(cudaGetLastError());
+  int hst = -1;
+  CK(cudaMemcpyAsync(&hst, st, 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(s_out, ctx->dists.p, (size_t)128 * n_c * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  if (hst != 0) return fail(ctx, LKM_ERR_CUDA, hst == 1 ? "tcgen05 probe: mbarrier wait timed out" : "tcgen05 probe: kernel did not report");
+  return LKM_OK;
+}
