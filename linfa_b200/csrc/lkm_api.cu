@@ -14,6 +14,7 @@
 #include <cstring>
 #include <limits>
 #include <string>
+#include <type_traits>
 #include <vector>
 
 #include "../../include/lkm.h"
@@ -88,6 +89,7 @@ struct lkm_ctx {
   uint64_t n = 0, d = 0;
   uint64_t row_offset = 0, n_global = 0;
   int force_path = -1;
+  int last_path = 0;
   uint64_t flush_bytes = 0;
   DevBuf flushbuf;
   std::vector<cudaEvent_t> iter_events;
@@ -267,7 +269,7 @@ static cudaError_t launch_finalize(const FinalizeArgs<F, S, CT>& a, cudaStream_t
 }
 
 struct LloydOut {
-  uint64_t n_iter = 0;
+  uint64_t n_iter = 0, fallback_rows = 0;
   double inertia = 0, shift = 0;
   float ms = 0, main_ms = 0;
   int final_buf = 0;
@@ -282,8 +284,41 @@ static lkm_status run_lloyd(lkm_ctx* ctx, F* dC2, uint64_t k, uint64_t max_iter,
   const uint64_t n = ctx->n, d = ctx->d, kd = k * d;
   const F* dX = reinterpret_cast<const F*>(ctx->X);
   if (kd > (uint64_t)std::numeric_limits<int>::max() / 4) return fail(ctx, LKM_ERR_UNSUPPORTED, "k*d too large");
+  // tensor-core path: f32, d = 32, k <= 256, everything resident in shared memory
+  bool use_tc = false;
+  int tc_grid = 0, tc_kp = 0, tc_cols = 0;
+  size_t tc_smem = 0;
+  if constexpr (std::is_same<F, float>::value) {
+    if ((ctx->force_path == -1 || ctx->force_path == 2) && d == 32 && k <= 256 && n >= 1 &&
+        (reinterpret_cast<uintptr_t>(dX) & 15) == 0) {
+      tc_kp = (int)((k + 31) / 32 * 32);
+      tc_cols = 32;
+      while (tc_cols < tc_kp) tc_cols *= 2;
+      tc_smem = tc_smem_bytes((int)k, tc_kp, 1);
+      if (tc_smem <= ctx->smem_optin) {
+        static size_t configured = 0;
+        if (tc_smem > configured) {
+          CK(cudaFuncSetAttribute(lloyd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem));
+          configured = tc_smem;
+        }
+        int occ = 0;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, lloyd_tc_kernel, 128, tc_smem));
+        occ = std::min(occ, 512 / tc_cols);  // TMEM columns per SM
+        if (occ >= 1) {
+          const uint64_t n_tiles = (n + kTcRows - 1) / kTcRows;
+          tc_grid = (int)std::min<uint64_t>(n_tiles, (uint64_t)ctx->sm_count * occ);
+          use_tc = true;
+        }
+      }
+    }
+    if (ctx->force_path == 2 && !use_tc) return fail(ctx, LKM_ERR_UNSUPPORTED, "tcgen05 path needs f32, d = 32, k <= 256");
+  } else {
+    if (ctx->force_path == 2) return fail(ctx, LKM_ERR_UNSUPPORTED, "tcgen05 path needs f32, d = 32, k <= 256");
+  }
   Plan pf;
   CKS(plan_fused<F>(ctx, dX, n, d, k, pf));
+  if (use_tc) { pf.fused = true; pf.grid = tc_grid; }
+  ctx->last_path = use_tc ? 2 : 0;
   Plan pa, pu;
   int n_chunks = 1, chunk_rows = (int)k;
   if (!pf.fused) {
@@ -340,7 +375,17 @@ static lkm_status run_lloyd(lkm_ctx* ctx, F* dC2, uint64_t k, uint64_t max_iter,
         CK(cudaMemsetAsync(ctx->flushbuf.p, (int)(it & 0xff), ctx->flush_bytes, ctx->stream));
         CK(cudaEventRecord(ctx->iter_events[3 * it], ctx->stream));
       }
-      if (pf.fused) {
+      if (use_tc) {
+        if constexpr (std::is_same<F, float>::value) {
+          TcArgs ta{};
+          ta.X = dX; ta.n = n; ta.k = (int)k; ta.kp = tc_kp; ta.tcols = tc_cols; ta.C = Ccur;
+          ta.part_sums = ctx->part_sums.as<float>(); ta.part_counts = ctx->part_counts.as<uint32_t>();
+          ta.part_inertia = ctx->part_inertia.as<double>(); ta.state = dstate; ta.accumulate = 1;
+          lloyd_tc_kernel<<<tc_grid, 128, tc_smem, ctx->stream>>>(ta);
+          CK(cudaGetLastError());
+          ctx->launches++;
+        }
+      } else if (pf.fused) {
         LloydArgs<F> a{};
         a.X = dX; a.n = n; a.d = (int)d; a.k = (int)k; a.C = Ccur;
         a.part_sums = ctx->part_sums.as<F>(); a.part_counts = ctx->part_counts.as<uint32_t>();
@@ -411,6 +456,7 @@ static lkm_status run_lloyd(lkm_ctx* ctx, F* dC2, uint64_t k, uint64_t max_iter,
   CK(cudaEventSynchronize(ctx->ev1));
   CK(cudaEventElapsedTime(&out.ms, ctx->ev0, ctx->ev1));
   out.n_iter = ctx->h_state->n_iter;
+  out.fallback_rows = ctx->h_state->fallback_rows;
   if (flush) {
     // per-iteration spans only (the flush writes sit between them)
     out.ms = 0;
@@ -681,7 +727,8 @@ static lkm_status fit_impl(lkm_ctx* ctx, const lkm_params* p, lkm_rng rng_in, F*
   if (stats) {
     std::memset(stats, 0, sizeof(*stats));
     stats->n_iter = lo.n_iter; stats->last_shift = lo.shift; stats->inertia_total = lo.inertia;
-    stats->device_ms = ms_total; stats->kernel_launches = ctx->launches; stats->assign_path = 0;
+    stats->device_ms = ms_total; stats->kernel_launches = ctx->launches; stats->assign_path = (uint32_t)ctx->last_path;
+    stats->fallback_rows = lo.fallback_rows;
   }
   if (!have) return fail(ctx, LKM_ERR_INERTIA, "Fitting failed: No inertia improvement (-inf)");
   // cluster_count from the LAST run's final assignment (KM/algorithm.rs:304,342,355-357)
@@ -719,8 +766,8 @@ static lkm_status lloyd_iters_impl(lkm_ctx* ctx, F* centroids_inout, uint64_t k,
   if (stats) {
     std::memset(stats, 0, sizeof(*stats));
     stats->n_iter = lo.n_iter; stats->last_shift = lo.shift; stats->inertia_total = lo.inertia;
-    stats->device_ms = lo.ms; stats->kernel_launches = ctx->launches; stats->assign_path = 0;
-    stats->main_kernel_ms = lo.main_ms;
+    stats->device_ms = lo.ms; stats->kernel_launches = ctx->launches; stats->assign_path = (uint32_t)ctx->last_path;
+    stats->main_kernel_ms = lo.main_ms; stats->fallback_rows = lo.fallback_rows;
   }
   return LKM_OK;
 }

@@ -193,4 +193,324 @@ __global__ void __launch_bounds__(128) tc_scores_debug_kernel(const float* __res
   if (warp == 0) tc::tmem_dealloc(tmem, TCOLS);
 }
 
+// =============================================================================================
+// Fused Lloyd iteration on tensor cores, f32, d = 32 (one 128-byte SW128 atom per row).
+//
+// Per 128-row tile: the scores S = X * C^T come from tcgen05 3xTF32 MMAs (accumulator in
+// TMEM); each thread then owns one row: w_c = ||c||^2 - 2 S_c, running best / second best,
+// and a CERTIFIED argmin — if (second - best) exceeds a rigorous bound on the rounding error of
+// both this path and the reference's direct-form evaluation, the winner is the reference's
+// winner; otherwise the row is queued and re-scanned in the reference's exact arithmetic
+// (direct form, feature order, no FMA, strict '<').  The winner's distance is always
+// re-evaluated in that exact form, so labels and min-distances are bit-identical to
+// KM/algorithm.rs:923-946 + linfa-nn/src/distance.rs:68-70.  Sums / counts / inertia are then
+// accumulated exactly as in lloyd_kernel (thread-owned shared-memory accumulators, fixed order).
+// =============================================================================================
+struct TcArgs {
+  const float* X;
+  unsigned long long n;
+  int k;       // clusters
+  int kp;      // k rounded up to a multiple of 32 (<= 256): UMMA N and TMEM columns used
+  int tcols;   // TMEM columns to allocate (power of two >= kp)
+  const float* C;
+  float* part_sums;
+  uint32_t* part_counts;
+  double* part_inertia;
+  LloydState* state;
+  uint32_t* labels;  // optional global outputs (assign-only use)
+  float* dists;
+  int accumulate;    // 0: assignment only
+};
+
+constexpr int kTcRows = 128;
+constexpr int kTcSubsets = 4;
+
+__host__ __device__ inline size_t tc_smem_bytes(int k, int kp, int accumulate) {
+  size_t b = 0;
+  b += 16384 * 2;                 // A_hi, A_lo
+  b += (size_t)kp * 128 * 2;      // B_hi, B_lo
+  b += 16384;                     // raw tile
+  b += ((size_t)k * 33 * 4 + 15) & ~(size_t)15;   // raw centroids, row stride 33 words
+  b += (size_t)kp * 4;            // ||c||^2
+  if (accumulate) {
+    b += (size_t)kTcSubsets * k * 32 * 4;   // sums
+    b += (size_t)kTcSubsets * k * 4;        // counts
+  }
+  b += kTcRows * 4 * 3 + 16;      // labels, dists, flag list
+  b += kTcRows * 8;               // f64 reduction scratch
+  return b + 1024;                // slack for the 1024-byte alignment of the operand tiles
+}
+
+__global__ void __launch_bounds__(128, 2) lloyd_tc_kernel(const TcArgs a) {
+  if (a.state != nullptr && a.state->done) return;
+  extern __shared__ unsigned char smem_unaligned[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_unaligned) + 1023) & ~(uintptr_t)1023);
+  const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+  const int k = a.k, kp = a.kp;
+  unsigned char* a_hi = smem;
+  unsigned char* a_lo = a_hi + 16384;
+  unsigned char* b_hi = a_lo + 16384;
+  unsigned char* b_lo = b_hi + (size_t)kp * 128;
+  unsigned char* raw = b_lo + (size_t)kp * 128;
+  float* rawc = reinterpret_cast<float*>(raw + 16384);
+  float* cn = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(rawc) + (((size_t)k * 33 * 4 + 15) & ~(size_t)15));
+  float* acc = cn + kp;
+  uint32_t* cnt = reinterpret_cast<uint32_t*>(acc + (a.accumulate ? (size_t)kTcSubsets * k * 32 : 0));
+  uint32_t* labs = cnt + (a.accumulate ? (size_t)kTcSubsets * k : 0);
+  float* dist_s = reinterpret_cast<float*>(labs + kTcRows);
+  uint32_t* flags = reinterpret_cast<uint32_t*>(dist_s + kTcRows);
+  double* red = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(flags + kTcRows + 4) + 7) & ~(uintptr_t)7);
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ uint32_t tmem_slot;
+  __shared__ uint32_t n_flag;
+  __shared__ uint32_t cmax_bits;
+
+  if (warp == 0) tc::tmem_alloc(&tmem_slot, (uint32_t)a.tcols);
+  if (t == 0) { tc::mbar_init(&bar, 1); tc::fence_mbar_init(); n_flag = 0; cmax_bits = 0; }
+  __syncthreads();
+  // ---- centroids: split into TF32 hi/lo operand tiles, padded raw copy, squared norms ----
+  for (int r = t; r < kp; r += 128) {
+    if (r < k) {
+      double nn = 0.0;
+      for (int c = 0; c < 8; ++c) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(a.C + (size_t)r * 32) + c);
+        float4 h, l;
+        tc::split_tf32(v.x, h.x, l.x); tc::split_tf32(v.y, h.y, l.y);
+        tc::split_tf32(v.z, h.z, l.z); tc::split_tf32(v.w, h.w, l.w);
+        const uint32_t o = tc::sw128_offset(r, c);
+        *reinterpret_cast<float4*>(b_hi + o) = h;
+        *reinterpret_cast<float4*>(b_lo + o) = l;
+        rawc[r * 33 + 4 * c + 0] = v.x; rawc[r * 33 + 4 * c + 1] = v.y;
+        rawc[r * 33 + 4 * c + 2] = v.z; rawc[r * 33 + 4 * c + 3] = v.w;
+        nn += (double)v.x * v.x + (double)v.y * v.y + (double)v.z * v.z + (double)v.w * v.w;
+      }
+      const float nf = (float)nn;
+      cn[r] = nf;
+      if (nf == nf) atomicMax(&cmax_bits, __float_as_uint(nf));  // non-negative floats order like their bits
+    } else {
+      const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int c = 0; c < 8; ++c) {
+        const uint32_t o = tc::sw128_offset(r, c);
+        *reinterpret_cast<float4*>(b_hi + o) = z;
+        *reinterpret_cast<float4*>(b_lo + o) = z;
+      }
+      cn[r] = INFINITY;  // padded centroid never wins
+    }
+  }
+  if (a.accumulate) {
+    for (int e = t; e < kTcSubsets * k * 32; e += 128) acc[e] = 0.f;
+    for (int e = t; e < kTcSubsets * k; e += 128) cnt[e] = 0u;
+  }
+  // ---- first tile into registers ----
+  const unsigned long long n_tiles = (a.n + kTcRows - 1) / kTcRows;
+  int4 pre[8];
+  auto prefetch = [&](unsigned long long tile) {
+    const unsigned long long row0 = tile * kTcRows;
+    const int rows = (int)min((unsigned long long)kTcRows, a.n - row0);
+    const int4* g = reinterpret_cast<const int4*>(a.X + row0 * 32);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int q = t + 128 * i;  // 16-byte chunk q of the tile: row q/8, chunk q%8
+      pre[i] = (q >> 3) < rows ? __ldg(g + q) : make_int4(0, 0, 0, 0);
+    }
+  };
+  if (blockIdx.x < n_tiles) prefetch(blockIdx.x);
+  tc::fence_async_smem();
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+  const float cmax2 = __uint_as_float(cmax_bits);
+  const float cmax = sqrtf(cmax2) * 1.000001f;
+  // rigorous margin (see DESIGN.md "certified argmin"): eta bounds the 3xTF32 dot error relative to
+  // |x||c|, gamma the reference's own direct-form rounding relative to the true squared distance
+  const float eta = (3.f * 32.f + 12.f) * 2.3841858e-7f;  // (3d + 12) * 2^-22
+  const float gamma = (32.f + 2.f) * 5.9604645e-8f;       // (d + 2) * 2^-24
+  const float m_a0 = 2.3841858e-7f * cmax2;
+  const float m_a1 = (4.f * eta + 4.7683716e-7f) * cmax;
+  const float m_g2 = 2.f * gamma;
+
+  const int sub = t >> 5, feat = t & 31;
+  int cur_lab = -1;
+  float cur_acc = 0.f;
+  double inert = 0.0;
+  unsigned int my_fallbacks = 0;
+  uint32_t parity = 0;
+
+  for (unsigned long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const unsigned long long row0 = tile * kTcRows;
+    const int rows = (int)min((unsigned long long)kTcRows, a.n - row0);
+    // ---- stage the tile: raw copy + TF32 hi/lo operand tiles, same swizzled position ----
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int q = t + 128 * i;
+      const uint32_t o = tc::sw128_offset((uint32_t)(q >> 3), (uint32_t)(q & 7));
+      const float4 v = *reinterpret_cast<const float4*>(&pre[i]);
+      float4 h, l;
+      tc::split_tf32(v.x, h.x, l.x); tc::split_tf32(v.y, h.y, l.y);
+      tc::split_tf32(v.z, h.z, l.z); tc::split_tf32(v.w, h.w, l.w);
+      *reinterpret_cast<float4*>(raw + o) = v;
+      *reinterpret_cast<float4*>(a_hi + o) = h;
+      *reinterpret_cast<float4*>(a_lo + o) = l;
+    }
+    if (tile + gridDim.x < n_tiles) prefetch(tile + gridDim.x);
+    tc::fence_async_smem();
+    tc::tc_fence_before();
+    __syncthreads();
+    if (t == 0) {
+      tc::tc_fence_after();
+      const uint32_t idesc = tc::idesc_tf32(128, (uint32_t)kp);
+      const uint32_t sa_hi = tc::smem_u32(a_hi), sa_lo = tc::smem_u32(a_lo), sb_hi = tc::smem_u32(b_hi), sb_lo = tc::smem_u32(b_lo);
+      uint32_t accf = 0;
+#pragma unroll
+      for (int pass = 0; pass < 3; ++pass) {
+        const uint32_t sa = pass == 2 ? sa_lo : sa_hi;
+        const uint32_t sb = pass == 1 ? sb_lo : sb_hi;
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+          tc::mma_tf32(tmem, tc::smem_desc_sw128(sa + ks * 32), tc::smem_desc_sw128(sb + ks * 32), idesc, accf);
+          accf = 1;
+        }
+      }
+      tc::mma_commit(&bar);
+    }
+    // ---- this thread's row (exact data) while the tensor core works ----
+    float xr[32];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      const float4 v = *reinterpret_cast<const float4*>(raw + tc::sw128_offset((uint32_t)t, (uint32_t)c));
+      xr[4 * c] = v.x; xr[4 * c + 1] = v.y; xr[4 * c + 2] = v.z; xr[4 * c + 3] = v.w;
+    }
+    float xx = 0.f;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) xx = fmaf(xr[j], xr[j], xx);
+    const float xn = sqrtf(xx) * 1.000001f;
+    const float margin = 1.1f * (m_a0 + xn * m_a1 + m_g2 * (xn + cmax) * (xn + cmax));
+
+    const bool ok = tc::mbar_wait(&bar, parity);
+    parity ^= 1u;
+    tc::tc_fence_after();
+    if (!ok) {  // never expected; leave a trace instead of hanging
+      if (t == 0 && a.state) atomicAdd(&a.state->fallback_rows, 1ull << 40);
+    }
+    float best0 = INFINITY, second0 = INFINITY, best1 = INFINITY, second1 = INFINITY;
+    int idx0 = 0, idx1 = 1;
+    for (int c0 = 0; c0 < kp; c0 += 32) {
+      uint32_t r[32];
+      tc::tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, r);
+      tc::tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 32; j += 2) {
+        const float w0 = fmaf(-2.f, __uint_as_float(r[j]), cn[c0 + j]);
+        const float w1 = fmaf(-2.f, __uint_as_float(r[j + 1]), cn[c0 + j + 1]);
+        second0 = fminf(second0, fmaxf(w0, best0));
+        idx0 = (w0 < best0) ? (c0 + j) : idx0;
+        best0 = fminf(best0, w0);
+        second1 = fminf(second1, fmaxf(w1, best1));
+        idx1 = (w1 < best1) ? (c0 + j + 1) : idx1;
+        best1 = fminf(best1, w1);
+      }
+    }
+    // merge the even / odd trackers (ties: lowest index)
+    float best, second;
+    int bidx;
+    if (best1 < best0 || (best1 == best0 && idx1 < idx0)) {
+      best = best1; bidx = idx1; second = fminf(second1, best0);
+    } else {
+      best = best0; bidx = idx0; second = fminf(second0, best1);
+    }
+    const bool row_ok = t < rows;
+    const bool certified = (second - best) > margin;  // NaN anywhere -> not certified
+    float dist = 0.f;
+    if (row_ok) {
+      if (certified) {
+        dist = sqdist_reg<float, 32>(rawc + bidx * 33, xr);
+        labs[t] = (uint32_t)bidx;
+        dist_s[t] = dist;
+      } else {
+        const uint32_t p = atomicAdd(&n_flag, 1u);
+        flags[p] = (uint32_t)t;
+      }
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    // ---- uncertified rows: exact scan, one warp per row, lanes split the centroids ----
+    const uint32_t nf = n_flag;
+    for (uint32_t f = warp; f < nf; f += 4) {
+      const uint32_t row = flags[f];
+      float x2[32];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        const float4 v = *reinterpret_cast<const float4*>(raw + tc::sw128_offset(row, (uint32_t)c));
+        x2[4 * c] = v.x; x2[4 * c + 1] = v.y; x2[4 * c + 2] = v.z; x2[4 * c + 3] = v.w;
+      }
+      float fb = INFINITY;
+      int fi = -1;
+      int c = lane;
+      if (lane == 0) { fb = sqdist_reg<float, 32>(rawc, x2); fi = 0; c = 32; }
+      for (; c < k; c += 32) {
+        const float v = sqdist_reg<float, 32>(rawc + c * 33, x2);
+        if (v < fb) { fb = v; fi = c; }
+      }
+      combine_candidates<float>(32, fb, fi);
+      if (lane == 0) { labs[row] = (uint32_t)fi; dist_s[row] = fb; }
+    }
+    my_fallbacks += (t == 0) ? nf : 0u;
+    __syncthreads();
+    if (t == 0) n_flag = 0;
+    if (row_ok) {
+      inert += (double)dist_s[t];
+      if (a.labels) a.labels[row0 + t] = labs[t];
+      if (a.dists) a.dists[row0 + t] = dist_s[t];
+    }
+    // ---- deterministic accumulation: thread (sub, feat) walks rows sub, sub+4, ... in order ----
+    if (a.accumulate) {
+      for (int r = sub; r < rows; r += kTcSubsets) {
+        const int lab = (int)labs[r];
+        const float xv = *reinterpret_cast<const float*>(raw + tc::sw128_offset((uint32_t)r, (uint32_t)(feat >> 2)) + (feat & 3) * 4);
+        if (lab == cur_lab) {
+          cur_acc += xv;
+        } else {
+          if (cur_lab >= 0) acc[((size_t)sub * k + cur_lab) * 32 + feat] += cur_acc;
+          cur_lab = lab;
+          cur_acc = xv;
+        }
+        if (feat == 0) cnt[sub * k + lab] += 1u;
+      }
+    }
+    __syncthreads();
+  }
+
+  if (a.accumulate) {
+    if (cur_lab >= 0) acc[((size_t)sub * k + cur_lab) * 32 + feat] += cur_acc;
+    __syncthreads();
+    const int kd = k * 32;
+    float* ps = a.part_sums + (size_t)blockIdx.x * kd;
+    for (int e = t; e < kd; e += 128) {
+      float s = acc[e];
+#pragma unroll
+      for (int q = 1; q < kTcSubsets; ++q) s += acc[(size_t)q * kd + e];
+      ps[e] = s;
+    }
+    uint32_t* pc = a.part_counts + (size_t)blockIdx.x * k;
+    for (int e = t; e < k; e += 128) {
+      uint32_t s = cnt[e];
+#pragma unroll
+      for (int q = 1; q < kTcSubsets; ++q) s += cnt[q * k + e];
+      pc[e] = s;
+    }
+    red[t] = inert;
+    __syncthreads();
+    for (int o = 64; o > 0; o >>= 1) {
+      if (t < o) red[t] += red[t + o];
+      __syncthreads();
+    }
+    if (t == 0) a.part_inertia[blockIdx.x] = red[0];
+  }
+  if (t == 0 && a.state && my_fallbacks) atomicAdd(&a.state->fallback_rows, (unsigned long long)my_fallbacks);
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tc::tmem_dealloc(tmem, (uint32_t)a.tcols);
+}
+
 }  // namespace lkm

@@ -398,3 +398,78 @@ def test_gen_blobs_layout_and_determinism(lb, ctx, dt):
     # a shard generated with a row offset equals the same rows of the whole
     ctx.gen_blobs(3000, 2, centres, 1.0, seed=7, row_offset=2500, n_global=10000)
     assert (ctx.get_data() == a[2500:5500]).all()
+
+
+# ---- tcgen05 3xTF32 path (f32, d = 32): certified argmin + exact re-evaluation ----
+TC_CASES = [(20000, 64, 64, 30.0), (5000, 1, 4, 30.0), (7777, 3, 3, 30.0), (33333, 100, 40, 30.0),
+            (12800, 256, 256, 30.0), (15000, 64, 8, 2.0), (9000, 37, 5, 0.5), (129, 2, 2, 30.0)]
+
+
+@pytest.mark.parametrize("n,k,k_true,spread", TC_CASES)
+def test_tc_path_matches_oracle(lb, ctx, oracle, n, k, k_true, spread):
+    """spread 2.0 / 0.5 make the blobs overlap heavily, so many rows fall inside the certification
+    margin and take the exact fallback; labels must still be identical."""
+    dt = np.float32
+    X, _ = blobs(n, 32, k_true, dt, seed=n + k, spread=spread)
+    g = np.random.default_rng(k)
+    init = X[g.choice(n, size=k, replace=False)].copy()
+    ctx.set_assign_path(2)
+    try:
+        ctx.set_data(X)
+        c, counts, inertia, st = ctx.lloyd_iters(init, 3, 0.0)
+        assert st.assign_path == 2 and st.n_iter == 3
+    finally:
+        ctx.set_assign_path(-1)
+    # replay the three iterations with the oracle, checking the assignment of every iteration
+    cur = init
+    for it in range(3):
+        lab, d = oracle.assign(X, cur)
+        nxt = oracle.compute_centroids(cur, X, lab, acc_f64=True)
+        if it == 2:
+            ref_counts = np.bincount(lab.astype(np.int64), minlength=k)
+            ref_inertia = d.astype(np.float64).sum()
+        cur = nxt
+    scale = np.abs(cur).max()
+    np.testing.assert_allclose(c, cur, rtol=1e-5, atol=1e-5 * scale)
+    assert counts.tolist() == ref_counts.tolist()  # identical labels in the last assignment
+    np.testing.assert_allclose(inertia, ref_inertia, rtol=1e-5)
+    print(f"fallback rows over 3 iterations: {st.fallback_rows} of {3 * n}")
+
+
+def test_tc_path_ties_and_duplicates(lb, ctx, oracle):
+    # duplicate centroids => exact ties => the lowest index must win, as in the reference
+    X, _ = blobs(4096, 32, 4, np.float32, seed=1)
+    init = np.concatenate([X[:3], X[:3], X[5:6]]).copy()
+    ctx.set_assign_path(2)
+    try:
+        ctx.set_data(X)
+        c, counts, inertia, st = ctx.lloyd_iters(init, 1, 0.0)
+    finally:
+        ctx.set_assign_path(-1)
+    lab, d = oracle.assign(X, init)
+    assert counts.tolist() == np.bincount(lab.astype(np.int64), minlength=7).tolist()
+    assert counts[3:6].sum() == 0
+    np.testing.assert_allclose(inertia, d.astype(np.float64).sum(), rtol=1e-6)
+
+
+def test_tc_path_nan_rows(lb, ctx):
+    X, _ = blobs(1000, 32, 4, np.float32, seed=2)
+    X[17, 5] = np.nan
+    ctx.set_assign_path(2)
+    try:
+        ctx.set_data(X)
+        c, counts, inertia, st = ctx.lloyd_iters(X[:4].copy(), 1, 0.0)
+    finally:
+        ctx.set_assign_path(-1)
+    assert np.isnan(inertia)  # a NaN row poisons the inertia, as dists.sum() does in the reference
+    assert counts.sum() == 1000
+
+
+def test_tc_path_is_reproducible(lb, ctx):
+    X, _ = blobs(100000, 32, 64, np.float32, seed=3)
+    init = X[::1563][:64].copy()
+    ctx.set_data(X)
+    a = ctx.lloyd_iters(init, 5, 0.0)
+    b = ctx.lloyd_iters(init, 5, 0.0)
+    assert a[3].assign_path == 2
+    assert (a[0] == b[0]).all() and a[2] == b[2] and (a[1] == b[1]).all()
