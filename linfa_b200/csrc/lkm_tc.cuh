@@ -224,27 +224,28 @@ struct TcArgs {
 
 constexpr int kTcRows = 128;
 constexpr int kTcSubsets = 4;
+constexpr int kTcCStride = 36;  // raw centroid row stride in words (16-byte aligned rows)
 
 __host__ __device__ inline size_t tc_smem_bytes(int k, int kp, int accumulate) {
   size_t b = 0;
   b += 16384 * 2;                 // A_hi, A_lo
   b += (size_t)kp * 128 * 2;      // B_hi, B_lo
   b += 16384;                     // raw tile
-  b += ((size_t)k * 33 * 4 + 15) & ~(size_t)15;   // raw centroids, row stride 33 words
+  b += (size_t)k * kTcCStride * 4;  // raw centroids
   b += (size_t)kp * 4;            // ||c||^2
   if (accumulate) {
-    b += (size_t)kTcSubsets * k * 32 * 4;   // sums
-    b += (size_t)kTcSubsets * k * 4;        // counts
+    b += (size_t)kTcSubsets * (k + 1) * 32 * 4;   // sums (+1 dummy row per subset)
+    b += (((size_t)k * 4) + 15) & ~(size_t)15;    // counts
   }
   b += kTcRows * 4 * 3 + 16;      // labels, dists, flag list
-  b += kTcRows * 8;               // f64 reduction scratch
   return b + 1024;                // slack for the 1024-byte alignment of the operand tiles
 }
 
 __global__ void __launch_bounds__(128, 2) lloyd_tc_kernel(const TcArgs a) {
   if (a.state != nullptr && a.state->done) return;
-  extern __shared__ unsigned char smem_unaligned[];
-  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_unaligned) + 1023) & ~(uintptr_t)1023);
+  extern __shared__ __align__(16) unsigned char smem_unaligned[];
+  // keep the shared address space visible to the compiler: offset, do not re-cast
+  unsigned char* smem = smem_unaligned + ((1024u - (tc::smem_u32(smem_unaligned) & 1023u)) & 1023u);
   const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
   const int k = a.k, kp = a.kp;
   unsigned char* a_hi = smem;
@@ -253,13 +254,13 @@ __global__ void __launch_bounds__(128, 2) lloyd_tc_kernel(const TcArgs a) {
   unsigned char* b_lo = b_hi + (size_t)kp * 128;
   unsigned char* raw = b_lo + (size_t)kp * 128;
   float* rawc = reinterpret_cast<float*>(raw + 16384);
-  float* cn = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(rawc) + (((size_t)k * 33 * 4 + 15) & ~(size_t)15));
+  float* cn = rawc + (size_t)k * kTcCStride;
   float* acc = cn + kp;
-  uint32_t* cnt = reinterpret_cast<uint32_t*>(acc + (a.accumulate ? (size_t)kTcSubsets * k * 32 : 0));
-  uint32_t* labs = cnt + (a.accumulate ? (size_t)kTcSubsets * k : 0);
+  uint32_t* cnt = reinterpret_cast<uint32_t*>(acc + (a.accumulate ? (size_t)kTcSubsets * (k + 1) * 32 : 0));
+  uint32_t* labs = cnt + (a.accumulate ? ((k + 3) & ~3) : 0);
   float* dist_s = reinterpret_cast<float*>(labs + kTcRows);
   uint32_t* flags = reinterpret_cast<uint32_t*>(dist_s + kTcRows);
-  double* red = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(flags + kTcRows + 4) + 7) & ~(uintptr_t)7);
+  double* red = reinterpret_cast<double*>(a_hi);  // only used after the last tile
   __shared__ __align__(8) uint64_t bar;
   __shared__ uint32_t tmem_slot;
   __shared__ uint32_t n_flag;
@@ -272,6 +273,7 @@ __global__ void __launch_bounds__(128, 2) lloyd_tc_kernel(const TcArgs a) {
   for (int r = t; r < kp; r += 128) {
     if (r < k) {
       double nn = 0.0;
+#pragma unroll
       for (int c = 0; c < 8; ++c) {
         const float4 v = __ldg(reinterpret_cast<const float4*>(a.C + (size_t)r * 32) + c);
         float4 h, l;
@@ -280,8 +282,7 @@ __global__ void __launch_bounds__(128, 2) lloyd_tc_kernel(const TcArgs a) {
         const uint32_t o = tc::sw128_offset(r, c);
         *reinterpret_cast<float4*>(b_hi + o) = h;
         *reinterpret_cast<float4*>(b_lo + o) = l;
-        rawc[r * 33 + 4 * c + 0] = v.x; rawc[r * 33 + 4 * c + 1] = v.y;
-        rawc[r * 33 + 4 * c + 2] = v.z; rawc[r * 33 + 4 * c + 3] = v.w;
+        *reinterpret_cast<float4*>(rawc + r * kTcCStride + 4 * c) = v;
         nn += (double)v.x * v.x + (double)v.y * v.y + (double)v.z * v.z + (double)v.w * v.w;
       }
       const float nf = (float)nn;
@@ -289,6 +290,7 @@ __global__ void __launch_bounds__(128, 2) lloyd_tc_kernel(const TcArgs a) {
       if (nf == nf) atomicMax(&cmax_bits, __float_as_uint(nf));  // non-negative floats order like their bits
     } else {
       const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
       for (int c = 0; c < 8; ++c) {
         const uint32_t o = tc::sw128_offset(r, c);
         *reinterpret_cast<float4*>(b_hi + o) = z;
@@ -298,8 +300,8 @@ __global__ void __launch_bounds__(128, 2) lloyd_tc_kernel(const TcArgs a) {
     }
   }
   if (a.accumulate) {
-    for (int e = t; e < kTcSubsets * k * 32; e += 128) acc[e] = 0.f;
-    for (int e = t; e < kTcSubsets * k; e += 128) cnt[e] = 0u;
+    for (int e = t; e < kTcSubsets * (k + 1) * 32; e += 128) acc[e] = 0.f;
+    for (int e = t; e < k; e += 128) cnt[e] = 0u;
   }
   // ---- first tile into registers ----
   const unsigned long long n_tiles = (a.n + kTcRows - 1) / kTcRows;
@@ -307,12 +309,11 @@ __global__ void __launch_bounds__(128, 2) lloyd_tc_kernel(const TcArgs a) {
   auto prefetch = [&](unsigned long long tile) {
     const unsigned long long row0 = tile * kTcRows;
     const int rows = (int)min((unsigned long long)kTcRows, a.n - row0);
-    const int4* g = reinterpret_cast<const int4*>(a.X + row0 * 32);
+    const int4* g = reinterpret_cast<const int4*>(a.X + row0 * 32) + t;
+    const int my_row = t >> 3;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int q = t + 128 * i;  // 16-byte chunk q of the tile: row q/8, chunk q%8
-      pre[i] = (q >> 3) < rows ? __ldg(g + q) : make_int4(0, 0, 0, 0);
-    }
+    for (int i = 0; i < 8; ++i)  // 16-byte chunk t + 128 i of the tile: row t/8 + 16 i, chunk t%8
+      pre[i] = (my_row + 16 * i) < rows ? __ldg(g + 128 * i) : make_int4(0, 0, 0, 0);
   };
   if (blockIdx.x < n_tiles) prefetch(blockIdx.x);
   tc::fence_async_smem();
@@ -330,8 +331,17 @@ __global__ void __launch_bounds__(128, 2) lloyd_tc_kernel(const TcArgs a) {
   const float m_a1 = (4.f * eta + 4.7683716e-7f) * cmax;
   const float m_g2 = 2.f * gamma;
 
+  // staging position of this thread's chunks: chunk t + 128 i -> st_off + 2048 i
+  const uint32_t st_off = tc::sw128_offset((uint32_t)(t >> 3), (uint32_t)(t & 7));
+  // this thread's row in the swizzled tile
+  const uint32_t row_off = (uint32_t)(t >> 3) * 1024u + (uint32_t)(t & 7) * 128u;
+  const uint32_t row_x = (uint32_t)(t & 7);
+  // accumulation role: feature `feat` of rows sub, sub+4, ... ; two precomputed offsets (row&7 = sub / sub+4)
   const int sub = t >> 5, feat = t & 31;
-  int cur_lab = -1;
+  const uint32_t acc_off_e = (uint32_t)sub * 128u + ((((uint32_t)feat >> 2) ^ (uint32_t)sub) << 4) + ((uint32_t)feat & 3u) * 4u;
+  const uint32_t acc_off_o = (uint32_t)(sub + 4) * 128u + ((((uint32_t)feat >> 2) ^ (uint32_t)(sub + 4)) << 4) + ((uint32_t)feat & 3u) * 4u;
+  float* my_acc = acc + (size_t)sub * (k + 1) * 32 + feat;
+  int cur_lab = k;  // dummy row: the first flush adds 0 to it
   float cur_acc = 0.f;
   double inert = 0.0;
   unsigned int my_fallbacks = 0;
@@ -343,15 +353,16 @@ __global__ void __launch_bounds__(128, 2) lloyd_tc_kernel(const TcArgs a) {
     // ---- stage the tile: raw copy + TF32 hi/lo operand tiles, same swizzled position ----
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      const int q = t + 128 * i;
-      const uint32_t o = tc::sw128_offset((uint32_t)(q >> 3), (uint32_t)(q & 7));
+      const uint32_t o = st_off + 2048u * i;
       const float4 v = *reinterpret_cast<const float4*>(&pre[i]);
       float4 h, l;
-      tc::split_tf32(v.x, h.x, l.x); tc::split_tf32(v.y, h.y, l.y);
-      tc::split_tf32(v.z, h.z, l.z); tc::split_tf32(v.w, h.w, l.w);
+      h.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u); l.x = v.x - h.x;
+      h.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u); l.y = v.y - h.y;
+      h.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u); l.z = v.z - h.z;
+      h.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u); l.w = v.w - h.w;
       *reinterpret_cast<float4*>(raw + o) = v;
       *reinterpret_cast<float4*>(a_hi + o) = h;
-      *reinterpret_cast<float4*>(a_lo + o) = l;
+      *reinterpret_cast<float4*>(a_lo + o) = l;   // low bits beyond TF32 are dropped by the tensor core
     }
     if (tile + gridDim.x < n_tiles) prefetch(tile + gridDim.x);
     tc::fence_async_smem();
@@ -378,13 +389,13 @@ __global__ void __launch_bounds__(128, 2) lloyd_tc_kernel(const TcArgs a) {
     float xr[32];
 #pragma unroll
     for (int c = 0; c < 8; ++c) {
-      const float4 v = *reinterpret_cast<const float4*>(raw + tc::sw128_offset((uint32_t)t, (uint32_t)c));
+      const float4 v = *reinterpret_cast<const float4*>(raw + row_off + (((uint32_t)c ^ row_x) << 4));
       xr[4 * c] = v.x; xr[4 * c + 1] = v.y; xr[4 * c + 2] = v.z; xr[4 * c + 3] = v.w;
     }
-    float xx = 0.f;
+    float xx0 = 0.f, xx1 = 0.f;
 #pragma unroll
-    for (int j = 0; j < 32; ++j) xx = fmaf(xr[j], xr[j], xx);
-    const float xn = sqrtf(xx) * 1.000001f;
+    for (int j = 0; j < 32; j += 2) { xx0 = fmaf(xr[j], xr[j], xx0); xx1 = fmaf(xr[j + 1], xr[j + 1], xx1); }
+    const float xn = sqrtf(xx0 + xx1) * 1.000001f;
     const float margin = 1.1f * (m_a0 + xn * m_a1 + m_g2 * (xn + cmax) * (xn + cmax));
 
     const bool ok = tc::mbar_wait(&bar, parity);
@@ -400,18 +411,27 @@ __global__ void __launch_bounds__(128, 2) lloyd_tc_kernel(const TcArgs a) {
       tc::tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, r);
       tc::tmem_ld_wait();
 #pragma unroll
-      for (int j = 0; j < 32; j += 2) {
-        const float w0 = fmaf(-2.f, __uint_as_float(r[j]), cn[c0 + j]);
-        const float w1 = fmaf(-2.f, __uint_as_float(r[j + 1]), cn[c0 + j + 1]);
+      for (int j = 0; j < 32; j += 4) {
+        const float4 cn4 = *reinterpret_cast<const float4*>(cn + c0 + j);
+        const float w0 = fmaf(-2.f, __uint_as_float(r[j]), cn4.x);
+        const float w1 = fmaf(-2.f, __uint_as_float(r[j + 1]), cn4.y);
+        const float w2 = fmaf(-2.f, __uint_as_float(r[j + 2]), cn4.z);
+        const float w3 = fmaf(-2.f, __uint_as_float(r[j + 3]), cn4.w);
         second0 = fminf(second0, fmaxf(w0, best0));
         idx0 = (w0 < best0) ? (c0 + j) : idx0;
         best0 = fminf(best0, w0);
         second1 = fminf(second1, fmaxf(w1, best1));
         idx1 = (w1 < best1) ? (c0 + j + 1) : idx1;
         best1 = fminf(best1, w1);
+        second0 = fminf(second0, fmaxf(w2, best0));
+        idx0 = (w2 < best0) ? (c0 + j + 2) : idx0;
+        best0 = fminf(best0, w2);
+        second1 = fminf(second1, fmaxf(w3, best1));
+        idx1 = (w3 < best1) ? (c0 + j + 3) : idx1;
+        best1 = fminf(best1, w3);
       }
     }
-    // merge the even / odd trackers (ties: lowest index)
+    // merge the two trackers (ties: lowest index)
     float best, second;
     int bidx;
     if (best1 < best0 || (best1 == best0 && idx1 < idx0)) {
@@ -421,12 +441,22 @@ __global__ void __launch_bounds__(128, 2) lloyd_tc_kernel(const TcArgs a) {
     }
     const bool row_ok = t < rows;
     const bool certified = (second - best) > margin;  // NaN anywhere -> not certified
-    float dist = 0.f;
     if (row_ok) {
       if (certified) {
-        dist = sqdist_reg<float, 32>(rawc + bidx * 33, xr);
+        // the winner's distance in the reference's exact arithmetic
+        const float* cw = rawc + bidx * kTcCStride;
+        float dacc = 0.f;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const float4 cv = *reinterpret_cast<const float4*>(cw + 4 * c);
+          float df;
+          df = __fsub_rn(cv.x, xr[4 * c]);     dacc = __fadd_rn(dacc, __fmul_rn(df, df));
+          df = __fsub_rn(cv.y, xr[4 * c + 1]); dacc = __fadd_rn(dacc, __fmul_rn(df, df));
+          df = __fsub_rn(cv.z, xr[4 * c + 2]); dacc = __fadd_rn(dacc, __fmul_rn(df, df));
+          df = __fsub_rn(cv.w, xr[4 * c + 3]); dacc = __fadd_rn(dacc, __fmul_rn(df, df));
+        }
         labs[t] = (uint32_t)bidx;
-        dist_s[t] = dist;
+        dist_s[t] = dacc;
       } else {
         const uint32_t p = atomicAdd(&n_flag, 1u);
         flags[p] = (uint32_t)t;
@@ -436,69 +466,76 @@ __global__ void __launch_bounds__(128, 2) lloyd_tc_kernel(const TcArgs a) {
     __syncthreads();
     // ---- uncertified rows: exact scan, one warp per row, lanes split the centroids ----
     const uint32_t nf = n_flag;
-    for (uint32_t f = warp; f < nf; f += 4) {
-      const uint32_t row = flags[f];
-      float x2[32];
+    if (nf) {
+      for (uint32_t f = warp; f < nf; f += 4) {
+        const uint32_t row = flags[f];
+        float x2[32];
 #pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        const float4 v = *reinterpret_cast<const float4*>(raw + tc::sw128_offset(row, (uint32_t)c));
-        x2[4 * c] = v.x; x2[4 * c + 1] = v.y; x2[4 * c + 2] = v.z; x2[4 * c + 3] = v.w;
+        for (int c = 0; c < 8; ++c) {
+          const float4 v = *reinterpret_cast<const float4*>(raw + tc::sw128_offset(row, (uint32_t)c));
+          x2[4 * c] = v.x; x2[4 * c + 1] = v.y; x2[4 * c + 2] = v.z; x2[4 * c + 3] = v.w;
+        }
+        float fb = INFINITY;
+        int fi = -1;
+        int c = lane;
+        if (lane == 0) { fb = sqdist_reg<float, 32>(rawc, x2); fi = 0; c = 32; }
+        for (; c < k; c += 32) {
+          const float v = sqdist_reg<float, 32>(rawc + c * kTcCStride, x2);
+          if (v < fb) { fb = v; fi = c; }
+        }
+        combine_candidates<float>(32, fb, fi);
+        if (lane == 0) { labs[row] = (uint32_t)fi; dist_s[row] = fb; }
       }
-      float fb = INFINITY;
-      int fi = -1;
-      int c = lane;
-      if (lane == 0) { fb = sqdist_reg<float, 32>(rawc, x2); fi = 0; c = 32; }
-      for (; c < k; c += 32) {
-        const float v = sqdist_reg<float, 32>(rawc + c * 33, x2);
-        if (v < fb) { fb = v; fi = c; }
-      }
-      combine_candidates<float>(32, fb, fi);
-      if (lane == 0) { labs[row] = (uint32_t)fi; dist_s[row] = fb; }
+      my_fallbacks += (t == 0) ? nf : 0u;
+      __syncthreads();
+      if (t == 0) n_flag = 0;
     }
-    my_fallbacks += (t == 0) ? nf : 0u;
-    __syncthreads();
-    if (t == 0) n_flag = 0;
     if (row_ok) {
+      const uint32_t lab = labs[t];
       inert += (double)dist_s[t];
-      if (a.labels) a.labels[row0 + t] = labs[t];
+      if (a.accumulate) atomicAdd(&cnt[lab], 1u);  // integer atomics: exact, order-independent
+      if (a.labels) a.labels[row0 + t] = lab;
       if (a.dists) a.dists[row0 + t] = dist_s[t];
     }
     // ---- deterministic accumulation: thread (sub, feat) walks rows sub, sub+4, ... in order ----
     if (a.accumulate) {
-      for (int r = sub; r < rows; r += kTcSubsets) {
-        const int lab = (int)labs[r];
-        const float xv = *reinterpret_cast<const float*>(raw + tc::sw128_offset((uint32_t)r, (uint32_t)(feat >> 2)) + (feat & 3) * 4);
-        if (lab == cur_lab) {
-          cur_acc += xv;
-        } else {
-          if (cur_lab >= 0) acc[((size_t)sub * k + cur_lab) * 32 + feat] += cur_acc;
-          cur_lab = lab;
-          cur_acc = xv;
+      if (rows == kTcRows) {
+#pragma unroll 4
+        for (int ii = 0; ii < 16; ++ii) {
+          const int l0 = (int)labs[sub + 8 * ii], l1 = (int)labs[sub + 8 * ii + 4];
+          const float x0 = *reinterpret_cast<const float*>(raw + 1024u * ii + acc_off_e);
+          const float x1 = *reinterpret_cast<const float*>(raw + 1024u * ii + acc_off_o);
+          if (l0 != cur_lab) { my_acc[cur_lab * 32] += cur_acc; cur_lab = l0; cur_acc = 0.f; }
+          cur_acc += x0;
+          if (l1 != cur_lab) { my_acc[cur_lab * 32] += cur_acc; cur_lab = l1; cur_acc = 0.f; }
+          cur_acc += x1;
         }
-        if (feat == 0) cnt[sub * k + lab] += 1u;
+      } else {
+        for (int r = sub; r < rows; r += kTcSubsets) {
+          const int lab = (int)labs[r];
+          const float xv = *reinterpret_cast<const float*>(raw + tc::sw128_offset((uint32_t)r, (uint32_t)(feat >> 2)) + (feat & 3) * 4);
+          if (lab != cur_lab) { my_acc[cur_lab * 32] += cur_acc; cur_lab = lab; cur_acc = 0.f; }
+          cur_acc += xv;
+        }
       }
     }
     __syncthreads();
   }
 
   if (a.accumulate) {
-    if (cur_lab >= 0) acc[((size_t)sub * k + cur_lab) * 32 + feat] += cur_acc;
+    my_acc[cur_lab * 32] += cur_acc;
     __syncthreads();
-    const int kd = k * 32;
+    const int kd = k * 32, sstride = (k + 1) * 32;
     float* ps = a.part_sums + (size_t)blockIdx.x * kd;
     for (int e = t; e < kd; e += 128) {
       float s = acc[e];
 #pragma unroll
-      for (int q = 1; q < kTcSubsets; ++q) s += acc[(size_t)q * kd + e];
+      for (int q = 1; q < kTcSubsets; ++q) s += acc[(size_t)q * sstride + e];
       ps[e] = s;
     }
     uint32_t* pc = a.part_counts + (size_t)blockIdx.x * k;
-    for (int e = t; e < k; e += 128) {
-      uint32_t s = cnt[e];
-#pragma unroll
-      for (int q = 1; q < kTcSubsets; ++q) s += cnt[q * k + e];
-      pc[e] = s;
-    }
+    for (int e = t; e < k; e += 128) pc[e] = cnt[e];
+    __syncthreads();
     red[t] = inert;
     __syncthreads();
     for (int o = 64; o > 0; o >>= 1) {
