@@ -264,7 +264,7 @@ static lkm_status run_assign(lkm_ctx* ctx, const F* dX, uint64_t n, uint64_t d, 
 template <typename F, typename S, typename CT, bool UPDATE>
 static cudaError_t launch_finalize(const FinalizeArgs<F, S, CT>& a, cudaStream_t s) {
   const int grid = (a.k * a.d + kFinElems - 1) / kFinElems;
-  finalize_kernel<F, S, CT, UPDATE><<<grid, 256, 0, s>>>(a);
+  finalize_kernel<F, S, CT, UPDATE><<<grid, kFinThreads, 0, s>>>(a);
   return cudaGetLastError();
 }
 
@@ -301,9 +301,14 @@ static lkm_status run_lloyd(lkm_ctx* ctx, F* dC2, uint64_t k, uint64_t max_iter,
           CK(cudaFuncSetAttribute(lloyd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem));
           configured = tc_smem;
         }
+        CK(cudaFuncSetAttribute(lloyd_tc_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                (int)cudaSharedmemCarveoutMaxShared));
         int occ = 0;
         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, lloyd_tc_kernel, 128, tc_smem));
-        occ = std::min(occ, 512 / tc_cols);  // TMEM columns per SM
+        // with the carve-out at its maximum, 228 KB per SM hold floor(228K / (dynamic + static + 1K reserved)) CTAs
+        occ = std::max(occ, (int)((228 * 1024) / (tc_smem + 2048)));
+        occ = std::min(occ, 2);                // 188 registers x 128 threads: two CTAs fill the register file
+        occ = std::min(occ, 512 / tc_cols);    // TMEM columns per SM
         if (occ >= 1) {
           const uint64_t n_tiles = (n + kTcRows - 1) / kTcRows;
           tc_grid = (int)std::min<uint64_t>(n_tiles, (uint64_t)ctx->sm_count * occ);
@@ -533,9 +538,22 @@ static lkm_status weighted_pick(lkm_ctx* ctx, const F* dW, uint64_t n, HostRng& 
   for (uint64_t b = 0; b < nb; ++b) total += hb[b];
   ctx->launches++;
   if (!(total > 0.0)) { picked = -1; return LKM_OK; }
+  // Uniform<F>::new(0, total).sample: value0_1 * scale with scale = (F)total
   const F u01 = unit<F>(rng);
+  const double thr = (double)(u01 * (F)total);
+  // walk the block sums in order on the host (nb doubles), the kernel finishes inside the block
+  double run = 0.0;
+  uint64_t fb = nb - 1;
+  double fp = 0.0;
+  bool hit = false;
+  for (uint64_t b = 0; b < nb; ++b) {
+    const double nxt = run + hb[b];
+    if (nxt > thr) { fb = b; fp = run; hit = true; break; }
+    run = nxt;
+  }
+  if (!hit) { fp = run - hb[nb - 1]; }
   long long* didx = reinterpret_cast<long long*>(ctx->scratch.as<char>() + 48);
-  fast_pick_kernel<F><<<1, 256, 0, ctx->stream>>>(dW, n, ctx->bsum.as<double>(), 0.0, total, u01, didx);
+  fast_pick_kernel<F><<<1, 256, 0, ctx->stream>>>(dW, n, fb, fp, thr, didx);
   CK(cudaGetLastError());
   ctx->launches++;
   CK(cudaMemcpyAsync(&picked, didx, 8, cudaMemcpyDeviceToHost, ctx->stream));

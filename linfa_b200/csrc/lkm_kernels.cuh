@@ -377,56 +377,75 @@ template <typename F, typename S, typename CT> struct FinalizeArgs {
   unsigned long long max_iter;
 };
 
-constexpr int kFinElems = 64;
+constexpr int kFinElems = 64;    // elements (of the k*d sums) per CTA
+constexpr int kFinGroups = 16;   // source groups per element; CTA = kFinElems * kFinGroups threads
+constexpr int kFinThreads = kFinElems * kFinGroups;
 
-__device__ __forceinline__ double block_sum_256(double v, double* red) {
+__device__ __forceinline__ double block_sum(double v, double* red) {
   const int t = threadIdx.x;
   __syncthreads();
   red[t] = v;
   __syncthreads();
-  for (int o = 128; o > 0; o >>= 1) {
+  for (int o = kFinThreads / 2; o > 0; o >>= 1) {
     if (t < o) red[t] += red[t + o];
     __syncthreads();
   }
   return red[0];
 }
 
+// sum of src[b*stride + e] over b = g, g+G, g+2G, ... with four independent chains so the
+// loads overlap; the association is fixed, hence reproducible
+template <typename S>
+__device__ __forceinline__ double strided_sum(const S* __restrict__ src, size_t stride, size_t e, int g, int n_src) {
+  double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+  int b = g;
+  for (; b + 3 * kFinGroups < n_src; b += 4 * kFinGroups) {
+    const S v0 = src[(size_t)b * stride + e];
+    const S v1 = src[(size_t)(b + kFinGroups) * stride + e];
+    const S v2 = src[(size_t)(b + 2 * kFinGroups) * stride + e];
+    const S v3 = src[(size_t)(b + 3 * kFinGroups) * stride + e];
+    s0 += (double)v0; s1 += (double)v1; s2 += (double)v2; s3 += (double)v3;
+  }
+  for (; b < n_src; b += kFinGroups) s0 += (double)src[(size_t)b * stride + e];
+  return (s0 + s1) + (s2 + s3);
+}
+
 template <typename F, typename S, typename CT, bool UPDATE>
-__global__ void __launch_bounds__(256) finalize_kernel(const FinalizeArgs<F, S, CT> a) {
+__global__ void __launch_bounds__(kFinThreads) finalize_kernel(const FinalizeArgs<F, S, CT> a) {
   if (UPDATE && a.state->done) return;
-  __shared__ double sh[4][kFinElems];
-  __shared__ double shc[4][kFinElems];
-  __shared__ double red[256];
+  __shared__ double sh[kFinGroups][kFinElems];
+  __shared__ double shc[kFinGroups][kFinElems];
+  __shared__ double red[kFinThreads];
   __shared__ bool is_last;
-  const int t = threadIdx.x, g = t >> 6, l = t & 63;
+  const int t = threadIdx.x, g = t / kFinElems, l = t % kFinElems;
   const int kd = a.k * a.d;
   const int e = blockIdx.x * kFinElems + l;
-  double s = 0.0;
-  if (e < kd)
-    for (int b = g; b < a.n_src; b += 4) s += (double)a.src_sums[(size_t)b * a.sum_stride + e];
-  sh[g][l] = s;
+  sh[g][l] = (e < kd) ? strided_sum<S>(a.src_sums, a.sum_stride, (size_t)e, g, a.n_src) : 0.0;
   // counts of the clusters this CTA's elements belong to
   const int c_lo = (blockIdx.x * kFinElems) / a.d;
   const int c_hi = (min(kd, (int)(blockIdx.x + 1) * kFinElems) - 1) / a.d;
   const int c = c_lo + l;
-  double cs = 0.0;
-  if (c <= c_hi)
-    for (int b = g; b < a.n_src; b += 4) cs += (double)a.src_counts[(size_t)b * a.cnt_stride + c];
-  shc[g][l] = cs;
+  shc[g][l] = (c <= c_hi) ? strided_sum<CT>(a.src_counts, a.cnt_stride, (size_t)c, g, a.n_src) : 0.0;
   __syncthreads();
   // every cluster's count is published by the CTA that holds its first element
   if (g == 0 && c <= c_hi && (c * a.d) / kFinElems == (int)blockIdx.x) {
-    const double cntv = ((shc[0][l] + shc[1][l]) + shc[2][l]) + shc[3][l];
+    double cntv = 0.0;
+#pragma unroll
+    for (int q = 0; q < kFinGroups; ++q) cntv += shc[q][l];
     if (UPDATE) a.counts_out[c] = cntv; else a.rank_out[kd + c] = cntv;
   }
   double sq = 0.0;
   if (g == 0 && e < kd) {
-    const double tot = ((sh[0][l] + sh[1][l]) + sh[2][l]) + sh[3][l];
+    double tot = 0.0;
+#pragma unroll
+    for (int q = 0; q < kFinGroups; ++q) tot += sh[q][l];
     if (!UPDATE) {
       a.rank_out[e] = tot;
     } else {
       const int ce = e / a.d - c_lo;
-      const double cntv = ((shc[0][ce] + shc[1][ce]) + shc[2][ce]) + shc[3][ce];
+      double cntv = 0.0;
+#pragma unroll
+      for (int q = 0; q < kFinGroups; ++q) cntv += shc[q][ce];
       const F oldv = a.C_old[e];
       const F newv = (F)((tot + (double)oldv) / (cntv + 1.0));
       a.C_new[e] = newv;
@@ -437,13 +456,13 @@ __global__ void __launch_bounds__(256) finalize_kernel(const FinalizeArgs<F, S, 
   if (!UPDATE) {
     if (blockIdx.x == 0) {
       double v = 0.0;
-      for (int b = t; b < a.n_src; b += 256) v += a.src_inertia[(size_t)b * a.inertia_stride];
-      const double tot = block_sum_256(v, red);
+      for (int b = t; b < a.n_src; b += kFinThreads) v += a.src_inertia[(size_t)b * a.inertia_stride];
+      const double tot = block_sum(v, red);
       if (t == 0) a.rank_out[kd + a.k] = tot;
     }
     return;
   }
-  const double sq_cta = block_sum_256(sq, red);
+  const double sq_cta = block_sum(sq, red);
   if (t == 0) {
     a.shift_part[blockIdx.x] = sq_cta;
     __threadfence();
@@ -455,11 +474,11 @@ __global__ void __launch_bounds__(256) finalize_kernel(const FinalizeArgs<F, S, 
   __threadfence();
   // last CTA: shift, inertia, loop control (fixed order)
   double v = 0.0;
-  for (int b = t; b < (int)gridDim.x; b += 256) v += ((volatile double*)a.shift_part)[b];
-  const double shift_sq = block_sum_256(v, red);
+  for (int b = t; b < (int)gridDim.x; b += kFinThreads) v += ((volatile double*)a.shift_part)[b];
+  const double shift_sq = block_sum(v, red);
   v = 0.0;
-  for (int b = t; b < a.n_src; b += 256) v += a.src_inertia[(size_t)b * a.inertia_stride];
-  const double inertia = block_sum_256(v, red);
+  for (int b = t; b < a.n_src; b += kFinThreads) v += a.src_inertia[(size_t)b * a.inertia_stride];
+  const double inertia = block_sum(v, red);
   if (t == 0) {
     const F shift = (F)sqrt(shift_sq);  // L2Dist::distance: sqrt in f64, cast to F
     a.state->shift = (double)shift;
@@ -588,47 +607,47 @@ __global__ void __launch_bounds__(256) block_sums_kernel(const F* __restrict__ w
   }
 }
 
-// fast pick, single CTA: total = sum of block sums (in order), threshold =
-// u01 * (F)total, then the first element whose running f64 prefix exceeds it.
-// out_idx[0] = local row index (or -1 if the threshold falls outside this
-// rank's range [lo, hi) of the global prefix, multi-GPU), out_total[0] = total.
+// fast pick inside ONE block of kPickBlock weights (the host has already walked the block sums
+// in order and found the block whose running prefix crosses the threshold): 256 threads, 8
+// elements each, fixed-association prefix (thread-serial, warp shuffle scan, warp totals), first
+// element whose running prefix exceeds thr.  out_idx[0] = row index (the block's last row if
+// rounding hides the crossing).
 template <typename F>
 __global__ void __launch_bounds__(256) fast_pick_kernel(const F* __restrict__ w, unsigned long long n,
-                                                        const double* __restrict__ bsum, double prefix_before,
-                                                        double total_global, F u01, long long* __restrict__ out_idx) {
-  __shared__ double red[256];
-  __shared__ long long found_block;
-  __shared__ double found_prefix;
-  const unsigned long long nb = (n + kPickBlock - 1) / kPickBlock;
-  const double thr = (double)(u01 * (F)total_global);  // value0_1 * scale (+ 0)
-  // thread 0 walks the block sums in order (nb <= ~1e5)
-  if (threadIdx.x == 0) {
-    double run = prefix_before;
-    long long fb = -1;
-    double fp = 0.0;
-    for (unsigned long long b = 0; b < nb; ++b) {
-      const double nxt = run + bsum[b];
-      if (nxt > thr) { fb = (long long)b; fp = run; break; }
-      run = nxt;
-    }
-    found_block = fb;
-    found_prefix = fp;
+                                                        unsigned long long block, double prefix_before, double thr,
+                                                        long long* __restrict__ out_idx) {
+  constexpr int PER = kPickBlock / 256;
+  __shared__ double wsum[8];
+  __shared__ unsigned long long found;
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  const unsigned long long base = block * kPickBlock + (unsigned long long)t * PER;
+  const unsigned long long end = min(n, (block + 1) * (unsigned long long)kPickBlock);
+  double v[PER];
+  double local = 0.0;
+#pragma unroll
+  for (int i = 0; i < PER; ++i) {
+    v[i] = (base + i < end) ? (double)w[base + i] : 0.0;
+    local += v[i];
+  }
+  if (t == 0) found = ~0ull;
+  double incl = local;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const double up = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += up;
+  }
+  if (lane == 31) wsum[warp] = incl;
+  __syncthreads();
+  double woff = 0.0;
+  for (int q = 0; q < warp; ++q) woff += wsum[q];
+  double run = prefix_before + woff + (incl - local);
+#pragma unroll
+  for (int i = 0; i < PER; ++i) {
+    run += v[i];
+    if (run > thr && base + i < end) { atomicMin(&found, base + i); break; }
   }
   __syncthreads();
-  if (found_block < 0) { if (threadIdx.x == 0) out_idx[0] = -1; return; }
-  (void)red;
-  if (threadIdx.x == 0) {
-    const unsigned long long base = (unsigned long long)found_block * kPickBlock;
-    double run = found_prefix;
-    long long idx = -1;
-    const unsigned long long end = min(n, base + kPickBlock);
-    for (unsigned long long i = base; i < end; ++i) {
-      run += (double)w[i];
-      if (run > thr) { idx = (long long)i; break; }
-    }
-    if (idx < 0) idx = (long long)end - 1;  // rounding slack inside the block
-    out_idx[0] = idx;
-  }
+  if (t == 0) out_idx[0] = (found == ~0ull) ? (long long)end - 1 : (long long)found;
 }
 
 // k-means|| oversampling (KM/init.rs:239-270): keep row i iff U_i < mult * d_i / cost,

@@ -402,7 +402,7 @@ def test_gen_blobs_layout_and_determinism(lb, ctx, dt):
 
 # ---- tcgen05 3xTF32 path (f32, d = 32): certified argmin + exact re-evaluation ----
 TC_CASES = [(20000, 64, 64, 30.0), (5000, 1, 4, 30.0), (7777, 3, 3, 30.0), (33333, 100, 40, 30.0),
-            (12800, 256, 256, 30.0), (15000, 64, 8, 2.0), (9000, 37, 5, 0.5), (129, 2, 2, 30.0)]
+            (12800, 128, 128, 30.0), (15000, 64, 8, 2.0), (9000, 37, 5, 0.5), (129, 2, 2, 30.0)]
 
 
 @pytest.mark.parametrize("n,k,k_true,spread", TC_CASES)
