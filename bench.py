@@ -218,14 +218,9 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     ctx = lb.Context(local_rank)
     if world > 1:
-        uid = torch.zeros(128, dtype=torch.uint8)
-        if rank == 0:
-            buf = C.create_string_buffer(128)
-            assert _ffi.lib.lkm_comm_unique_id(buf) == 0
-            uid = torch.frombuffer(bytearray(buf.raw), dtype=torch.uint8).clone()
-        uid = uid.cuda()
-        dist.broadcast(uid, 0)
-        ctx.comm_init(bytes(uid.cpu().numpy().tobytes()), rank, world)
+        from linfa_b200 import distributed as D
+
+        D.init_comm(ctx, device=torch.device("cuda", local_rank))
 
     n, d, k, dtype = WORKLOADS[args.workload]
     itemsize = np.dtype(dtype).itemsize

@@ -1,0 +1,64 @@
+"""Multi-GPU parity check, run under torchrun on a box with >= 2 GPUs:
+
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 \
+      tests/multi_gpu_check.py
+
+Row-sharded Lloyd iterations (NCCL all-gather of the per-rank partials inside the library) must
+give the same labels (counts), and centroids / inertia within tolerance, as one GPU holding the
+whole matrix.  Every rank must end with bit-identical centroids."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    import linfa_b200 as lb
+    from linfa_b200 import distributed as D
+
+    ok = True
+    for dtype, n, d, k, rtol in [(np.float32, 400_003, 32, 64, 1e-5), (np.float64, 300_001, 8, 16, 1e-10),
+                                 (np.float32, 100_000, 20, 12, 1e-5)]:
+        ctx = lb.Context(local)
+        D.init_comm(ctx, device=torch.device("cuda", local))
+        g = np.random.default_rng(5)
+        centres = g.uniform(-30, 30, (k, d)).astype(dtype)
+        init = (centres + 0.5 * g.standard_normal((k, d))).astype(dtype)
+        lo, hi = D.shard_range(n, rank, world)
+        ctx.gen_blobs(hi - lo, d, centres, 1.0, seed=11, row_offset=lo, n_global=n)
+        c, counts, inertia, st = ctx.lloyd_iters(init, 6, 0.0)
+        # bit-identical across ranks
+        t = torch.from_numpy(c.copy()).cuda()
+        allc = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(allc, t)
+        same = all(torch.equal(allc[0], x) for x in allc)
+        if rank == 0:
+            solo = lb.Context(local)
+            solo.gen_blobs(n, d, centres, 1.0, seed=11)
+            c1, counts1, inertia1, st1 = solo.lloyd_iters(init, 6, 0.0)
+            scale = np.abs(c1).max()
+            good = (same and st.n_iter == 6 and counts.tolist() == counts1.tolist()
+                    and np.allclose(c, c1, rtol=rtol, atol=rtol * scale) and np.isclose(inertia, inertia1, rtol=rtol))
+            print(f"[multi_gpu_check] {np.dtype(dtype).name} n={n} d={d} k={k} world={world}: "
+                  f"{'ok' if good else 'MISMATCH'} path={st.assign_path} "
+                  f"max|dC|/scale={np.abs(c - c1).max() / scale:.3e} counts_equal={counts.tolist() == counts1.tolist()}",
+                  flush=True)
+            ok = ok and good
+            solo.close()
+        ctx.close()
+    flag = torch.tensor([1 if ok else 0], device="cuda")
+    dist.broadcast(flag, 0)
+    dist.barrier()
+    dist.destroy_process_group()
+    sys.exit(0 if int(flag.item()) == 1 else 1)
+
+
+if __name__ == "__main__":
+    main()
