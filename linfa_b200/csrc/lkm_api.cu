@@ -448,7 +448,7 @@ static lkm_status run_lloyd(lkm_ctx* ctx, F* dC2, uint64_t k, uint64_t max_iter,
         fa.C_old = Ccur; fa.C_new = Cnext; fa.counts_out = ctx->counts_out.as<double>();
         fa.shift_part = ctx->shift_part.as<double>(); fa.state = dstate; fa.tol = tol; fa.max_iter = max_iter;
         CK((launch_finalize<F, double, double, true>(fa, ctx->stream)));
-        ctx->launches += 3;
+        ctx->launches += 2;  // reduce + update (the all-gather kernel is NCCL's, not counted)
       }
       if (flush) CK(cudaEventRecord(ctx->iter_events[3 * it + 2], ctx->stream));
     }
