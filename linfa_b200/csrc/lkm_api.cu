@@ -1158,3 +1158,59 @@ LKM_EXPORT int lkm_debug_tc_scores(lkm_ctx* ctx, const float* x, const float* c,
   if (hst != 0) return fail(ctx, LKM_ERR_CUDA, hst == 1 ? "tcgen05 probe: mbarrier wait timed out" : "tcgen05 probe: kernel did not report");
   return LKM_OK;
 }
+
+// D2 = onehot(labels)^T * X through the MN-major tcgen05 accumulation probe; dumps 128 lanes x 32 columns
+LKM_EXPORT int lkm_debug_tc_accum(lkm_ctx* ctx, const float* x, const int* labels, int m, float* dump_out) {
+  if (!ctx || !x || !labels || !dump_out || (m != 64 && m != 128)) return LKM_ERR_INVALID_ARG;
+  CK(cudaSetDevice(ctx->device));
+  CK(ctx->tmpx.ensure(128 * 32 * 4));
+  CK(ctx->tmpc.ensure(128 * 4));
+  CK(ctx->dists.ensure(128 * 32 * 4));
+  CK(ctx->scratch.ensure(64));
+  CK(cudaMemcpyAsync(ctx->tmpx.p, x, 128 * 32 * 4, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->tmpc.p, labels, 128 * 4, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemsetAsync(ctx->scratch.p, 0xff, 4, ctx->stream));
+  CK(cudaMemsetAsync(ctx->dists.p, 0, 128 * 32 * 4, ctx->stream));
+  const size_t smem = 16384 + (size_t)(m / 32) * 16384 + 1024;
+  if (m == 64) {
+    CK(cudaFuncSetAttribute(tc_accum_debug_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    tc_accum_debug_kernel<64><<<1, 128, smem, ctx->stream>>>(ctx->tmpx.as<float>(), ctx->tmpc.as<int>(), ctx->dists.as<float>(), ctx->scratch.as<int>());
+  } else {
+    CK(cudaFuncSetAttribute(tc_accum_debug_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    tc_accum_debug_kernel<128><<<1, 128, smem, ctx->stream>>>(ctx->tmpx.as<float>(), ctx->tmpc.as<int>(), ctx->dists.as<float>(), ctx->scratch.as<int>());
+  }
+  CK(cudaGetLastError());
+  int hst = -1;
+  CK(cudaMemcpyAsync(&hst, ctx->scratch.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(dump_out, ctx->dists.p, 128 * 32 * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  if (hst != 0) return fail(ctx, LKM_ERR_CUDA, hst == 1 ? "tcgen05 accumulation probe: timeout" : "tcgen05 accumulation probe: no report");
+  return LKM_OK;
+}
+
+LKM_EXPORT int lkm_debug_umma_raw(lkm_ctx* ctx, const void* a_img, int a_bytes, const void* b_img, int b_bytes,
+                                  unsigned long long a_desc_hi, unsigned long long b_desc_hi, int a_step, int b_step,
+                                  unsigned int idesc, int ksteps, int ncols, float* dump_out) {
+  if (!ctx || !a_img || !b_img || !dump_out || a_bytes % 16 || b_bytes % 16 || ncols % 32 || ncols > 256) return LKM_ERR_INVALID_ARG;
+  CK(cudaSetDevice(ctx->device));
+  CK(ctx->tmpx.ensure(a_bytes));
+  CK(ctx->tmpc.ensure(b_bytes));
+  CK(ctx->dists.ensure((size_t)128 * ncols * 4));
+  CK(ctx->scratch.ensure(64));
+  CK(cudaMemcpyAsync(ctx->tmpx.p, a_img, a_bytes, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->tmpc.p, b_img, b_bytes, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemsetAsync(ctx->scratch.p, 0xff, 4, ctx->stream));
+  CK(cudaMemsetAsync(ctx->dists.p, 0, (size_t)128 * ncols * 4, ctx->stream));
+  const size_t smem = (size_t)((a_bytes + 1023) & ~1023) + b_bytes + 2048;
+  CK(cudaFuncSetAttribute(umma_raw_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  umma_raw_probe_kernel<<<1, 128, smem, ctx->stream>>>(ctx->tmpx.as<unsigned char>(), a_bytes, ctx->tmpc.as<unsigned char>(), b_bytes,
+                                                       a_desc_hi, b_desc_hi, a_step, b_step, idesc, ksteps, ncols,
+                                                       ctx->dists.as<float>(), ctx->scratch.as<int>());
+  CK(cudaGetLastError());
+  int hst = -1;
+  CK(cudaMemcpyAsync(&hst, ctx->scratch.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(dump_out, ctx->dists.p, (size_t)128 * ncols * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  if (hst != 0) return fail(ctx, LKM_ERR_CUDA, "umma raw probe: timeout or no report");
+  return LKM_OK;
+}

@@ -193,6 +193,129 @@ __global__ void __launch_bounds__(128) tc_scores_debug_kernel(const float* __res
   if (warp == 0) tc::tmem_dealloc(tmem, TCOLS);
 }
 
+// ---------------------------------------------------------------------------------------------
+// Probe for the tensor-core centroid accumulation: D2[M x 32] = onehot^T[M x 128] * X[128 x 32]
+// (M = 64 or 128 clusters).  A = one-hot, MN-major (cluster contiguous per data row), groups of 32
+// clusters 16 KB apart; B = the X tile as staged for the assignment MMA, read MN-major (feature
+// contiguous per data row).  Dumps all 128 TMEM lanes x 32 columns so that the host can learn the
+// accumulator layout.  status: 0 ok, 1 timeout.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t smem_desc_mn_sw128(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;   // stride between 128-byte MN groups
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;   // stride between 8-row K groups
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+__host__ __device__ constexpr uint32_t idesc_tf32_mn(uint32_t m, uint32_t n) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((n >> 3) << 17) | ((m >> 4) << 24);
+}
+
+template <int M>
+__global__ void __launch_bounds__(128) tc_accum_debug_kernel(const float* __restrict__ X, const int* __restrict__ labels,
+                                                             float* __restrict__ dump, int* __restrict__ status) {
+  extern __shared__ __align__(16) unsigned char smem_unaligned[];
+  unsigned char* smem = smem_unaligned + ((1024u - (tc::smem_u32(smem_unaligned) & 1023u)) & 1023u);
+  unsigned char* xt = smem;              // [128 rows][128 B] SW128
+  unsigned char* oh = smem + 16384;      // M/32 groups of [128 rows][128 B] SW128
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ uint32_t tmem_slot;
+  const int t = threadIdx.x, warp = t >> 5;
+  if (warp == 0) tc::tmem_alloc(&tmem_slot, 32);
+  if (t == 0) { tc::mbar_init(&bar, 1); tc::fence_mbar_init(); }
+  for (int i = t; i < (M / 32) * 16384 / 16; i += 128) reinterpret_cast<int4*>(oh)[i] = make_int4(0, 0, 0, 0);
+  for (int c = 0; c < 8; ++c)
+    *reinterpret_cast<float4*>(xt + tc::sw128_offset(t, c)) = reinterpret_cast<const float4*>(X + (size_t)t * 32)[c];
+  __syncthreads();
+  {
+    const int lab = labels[t];
+    const uint32_t g = (uint32_t)lab >> 5, w = (uint32_t)lab & 31u;
+    *reinterpret_cast<float*>(oh + g * 16384u + tc::sw128_offset(t, w >> 2) + (w & 3u) * 4u) = 1.0f;
+  }
+  tc::fence_async_smem();
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+  if (t == 0) {
+    constexpr uint32_t idesc = idesc_tf32_mn(M, 32);
+    uint32_t acc = 0;
+    for (int ks = 0; ks < 16; ++ks) {  // 8 data rows per MMA
+      tc::mma_tf32(tmem, smem_desc_mn_sw128(tc::smem_u32(oh) + ks * 1024, 16384, 1024),
+                   smem_desc_mn_sw128(tc::smem_u32(xt) + ks * 1024, 16384, 1024), idesc, acc);
+      acc = 1;
+    }
+    tc::mma_commit(&bar);
+  }
+  const bool ok = tc::mbar_wait(&bar, 0);
+  tc::tc_fence_after();
+  if (ok) {
+    uint32_t r[32];
+    tc::tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16), r);
+    tc::tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 32; ++j) dump[(size_t)t * 32 + j] = __uint_as_float(r[j]);
+  }
+  if (t == 0) status[0] = ok ? 0 : 1;
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tc::tmem_dealloc(tmem, 32);
+}
+
+// Raw UMMA probe: the host supplies byte images of the A and B operand regions, the two
+// descriptors (without start address), the per-k-step byte advance and the instruction
+// descriptor; the kernel copies the images to 1024-aligned shared memory, issues `ksteps` MMAs and
+// dumps 128 TMEM lanes x `ncols` columns.  Used to pin down operand layouts from Python.
+__global__ void __launch_bounds__(128) umma_raw_probe_kernel(const unsigned char* __restrict__ a_img, int a_bytes,
+                                                             const unsigned char* __restrict__ b_img, int b_bytes,
+                                                             unsigned long long a_desc_hi, unsigned long long b_desc_hi,
+                                                             int a_step, int b_step, unsigned int idesc, int ksteps,
+                                                             int ncols, float* __restrict__ dump, int* __restrict__ status) {
+  extern __shared__ __align__(16) unsigned char smem_unaligned[];
+  unsigned char* smem = smem_unaligned + ((1024u - (tc::smem_u32(smem_unaligned) & 1023u)) & 1023u);
+  unsigned char* sa = smem;
+  unsigned char* sb = smem + ((a_bytes + 1023) & ~1023);
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ uint32_t tmem_slot;
+  const int t = threadIdx.x, warp = t >> 5;
+  if (warp == 0) tc::tmem_alloc(&tmem_slot, 256);
+  if (t == 0) { tc::mbar_init(&bar, 1); tc::fence_mbar_init(); }
+  for (int i = t; i < a_bytes / 16; i += 128) reinterpret_cast<int4*>(sa)[i] = reinterpret_cast<const int4*>(a_img)[i];
+  for (int i = t; i < b_bytes / 16; i += 128) reinterpret_cast<int4*>(sb)[i] = reinterpret_cast<const int4*>(b_img)[i];
+  tc::fence_async_smem();
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+  if (t == 0) {
+    uint32_t acc = 0;
+    for (int ks = 0; ks < ksteps; ++ks) {
+      const uint64_t da = a_desc_hi | (uint64_t)(((tc::smem_u32(sa) + ks * a_step) & 0x3FFFFu) >> 4);
+      const uint64_t db = b_desc_hi | (uint64_t)(((tc::smem_u32(sb) + ks * b_step) & 0x3FFFFu) >> 4);
+      tc::mma_tf32(tmem, da, db, idesc, acc);
+      acc = 1;
+    }
+    tc::mma_commit(&bar);
+  }
+  const bool ok = tc::mbar_wait(&bar, 0);
+  tc::tc_fence_after();
+  if (ok) {
+    for (int c0 = 0; c0 < ncols; c0 += 32) {
+      uint32_t r[32];
+      tc::tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + c0, r);
+      tc::tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 32; ++j) dump[(size_t)t * ncols + c0 + j] = __uint_as_float(r[j]);
+    }
+  }
+  if (t == 0) status[0] = ok ? 0 : 1;
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tc::tmem_dealloc(tmem, 256);
+}
+
 // =============================================================================================
 // Fused Lloyd iteration on tensor cores, f32, d = 32 (one 128-byte SW128 atom per row).
 //
