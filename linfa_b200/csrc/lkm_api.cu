@@ -94,7 +94,7 @@ struct lkm_ctx {
   DevBuf flushbuf;
   std::vector<cudaEvent_t> iter_events;
   // workspaces
-  DevBuf cbuf, part_sums, part_counts, part_inertia, shift_part, counts_out, state, gather, labels, dists, wdists,
+  DevBuf cbuf, part_sums, part_counts, part_inertia, shift_part, counts_out, state, gather, gather2, labels, dists, wdists,
       cum, scratch, tmpx, tmpc, idxbuf, bsum, weights;
   LloydState* h_state = nullptr;  // pinned
   double* h_pin = nullptr;        // pinned scratch (>= 4096 doubles)
@@ -501,7 +501,7 @@ static lkm_status weighted_pick(lkm_ctx* ctx, const F* dW, uint64_t n, HostRng& 
   if (pick_mode == LKM_PICK_EXACT) {
     CK(ctx->cum.ensure(std::max<uint64_t>(n, 2) * sizeof(F)));
     CK(ctx->scratch.ensure(64));
-    seq_prefix_kernel<F><<<1, 256, 0, ctx->stream>>>(dW, n, ctx->cum.as<F>(), ctx->scratch.as<F>());
+    seq_prefix_kernel<F><<<1, 256, 0, ctx->stream>>>(dW, n, ctx->cum.as<F>(), ctx->scratch.as<F>(), (F)0, n - 1);
     CK(cudaGetLastError());
     F tot[2];
     CK(cudaMemcpyAsync(tot, ctx->scratch.p, 2 * sizeof(F), cudaMemcpyDeviceToHost, ctx->stream));
@@ -670,13 +670,313 @@ static lkm_status kmeans_para(lkm_ctx* ctx, const F* dX, uint64_t n, uint64_t d,
   return weighted_kmeanspp<F>(ctx, dCand, n_cand, d, ctx->tmpx.as<F>(), k, rng, pick_mode, dC);
 }
 
+// ---- row-sharded seeding (world > 1): every rank draws the same random numbers from its copy of
+// the rng; row indices are GLOBAL; the owner of a picked row publishes it through an all-gather ----
+static lkm_status comm_allgather_host(lkm_ctx* ctx, const void* src, size_t bytes, std::vector<unsigned char>& out) {
+  const size_t w = (size_t)ctx->world;
+  out.resize(bytes * w);
+  CK(ctx->gather2.ensure(bytes * w));
+  unsigned char* g = ctx->gather2.as<unsigned char>();
+  CK(cudaMemcpyAsync(g + (size_t)ctx->rank * bytes, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  CKN(g_nccl.AllGather(g + (size_t)ctx->rank * bytes, g, bytes, kNcclInt8, ctx->comm, ctx->stream));
+  CK(cudaMemcpyAsync(out.data(), g, bytes * w, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return LKM_OK;
+}
+
+struct ShardMap {
+  std::vector<uint64_t> lo, n;
+  int owner(uint64_t g) const {
+    for (size_t r = 0; r < lo.size(); ++r)
+      if (g >= lo[r] && g < lo[r] + n[r]) return (int)r;
+    return -1;
+  }
+};
+static lkm_status shard_map(lkm_ctx* ctx, ShardMap& m) {
+  uint64_t mine[2] = {ctx->row_offset, ctx->n};
+  std::vector<unsigned char> all;
+  CKS(comm_allgather_host(ctx, mine, sizeof(mine), all));
+  m.lo.resize(ctx->world); m.n.resize(ctx->world);
+  for (int r = 0; r < ctx->world; ++r) {
+    uint64_t v[2];
+    std::memcpy(v, all.data() + (size_t)r * 16, 16);
+    m.lo[r] = v[0]; m.n[r] = v[1];
+  }
+  return LKM_OK;
+}
+
+// every rank ends with row `g` (global index) of the sharded matrix in dDst (device, d values)
+template <typename F>
+static lkm_status fetch_global_row(lkm_ctx* ctx, const ShardMap& sm, uint64_t g, F* dDst) {
+  const uint64_t d = ctx->d;
+  const int own = sm.owner(g);
+  if (own < 0) return fail(ctx, LKM_ERR_INVALID_ARG, "picked row outside every shard");
+  std::vector<F> row(d, (F)0);
+  if (own == ctx->rank) {
+    CK(cudaMemcpyAsync(row.data(), reinterpret_cast<const F*>(ctx->X) + (g - ctx->row_offset) * d, d * sizeof(F),
+                       cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+  }
+  std::vector<unsigned char> all;
+  CKS(comm_allgather_host(ctx, row.data(), d * sizeof(F), all));
+  CK(cudaMemcpyAsync(dDst, all.data() + (size_t)own * d * sizeof(F), d * sizeof(F), cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return LKM_OK;
+}
+
+// WeightedIndex::new(w).sample(rng) over the row-sharded weight vector; picked = GLOBAL index or -1
+template <typename F>
+static lkm_status weighted_pick_sharded(lkm_ctx* ctx, const ShardMap& sm, const F* dW, HostRng& rng, int pick_mode,
+                                        long long& picked) {
+  const uint64_t n = ctx->n;
+  const int world = ctx->world, rank = ctx->rank;
+  std::vector<unsigned char> all;
+  if (pick_mode == LKM_PICK_EXACT) {
+    // the sequential F prefix runs rank after rank, each continuing from the carry of the one before
+    CK(ctx->cum.ensure(std::max<uint64_t>(n, 2) * sizeof(F)));
+    CK(ctx->scratch.ensure(64));
+    F carry = (F)0;
+    bool bad = false;
+    for (int s = 0; s < world; ++s) {
+      F tot[2] = {carry, (F)0};
+      if (s == rank && n > 0) {
+        const uint64_t n_cum = (rank == world - 1) ? n - 1 : n;
+        seq_prefix_kernel<F><<<1, 256, 0, ctx->stream>>>(dW, n, ctx->cum.as<F>(), ctx->scratch.as<F>(), carry, n_cum);
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(tot, ctx->scratch.p, 2 * sizeof(F), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        ctx->launches++;
+      }
+      CKS(comm_allgather_host(ctx, tot, sizeof(tot), all));
+      F got[2];
+      std::memcpy(got, all.data() + (size_t)s * sizeof(tot), sizeof(tot));
+      carry = got[0];
+      bad = bad || got[1] != (F)0;
+    }
+    if (bad || !(carry >= (F)0) || carry == (F)0) { picked = -1; return LKM_OK; }
+    const F chosen = weighted_threshold<F>(rng, carry);
+    unsigned long long* dcnt = reinterpret_cast<unsigned long long*>(ctx->scratch.as<char>() + 32);
+    CK(cudaMemsetAsync(dcnt, 0, 8, ctx->stream));
+    const uint64_t n_cum = (rank == world - 1) ? (n ? n - 1 : 0) : n;
+    if (n_cum) {
+      count_le_kernel<F><<<(int)std::min<uint64_t>((n_cum + 255) / 256, 2048), 256, 0, ctx->stream>>>(ctx->cum.as<F>(), n_cum, chosen, dcnt);
+      CK(cudaGetLastError());
+      ctx->launches++;
+    }
+    unsigned long long cnt = 0;
+    CK(cudaMemcpyAsync(&cnt, dcnt, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    CKS(comm_allgather_host(ctx, &cnt, 8, all));
+    unsigned long long total_cnt = 0;
+    for (int r = 0; r < world; ++r) { unsigned long long v; std::memcpy(&v, all.data() + (size_t)r * 8, 8); total_cnt += v; }
+    picked = (long long)total_cnt;
+    return LKM_OK;
+  }
+  // FAST: per-rank fixed-order f64 block sums; rank totals combined in rank order
+  const uint64_t nb = (n + kPickBlock - 1) / kPickBlock;
+  std::vector<double> hb(std::max<uint64_t>(nb, 1), 0.0);
+  CK(ctx->scratch.ensure(64));
+  if (nb) {
+    CK(ctx->bsum.ensure(nb * 8));
+    block_sums_kernel<F><<<(int)std::min<uint64_t>(nb, 4096), 256, 0, ctx->stream>>>(dW, n, ctx->bsum.as<double>());
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(hb.data(), ctx->bsum.p, nb * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->launches++;
+  }
+  double local = 0.0;
+  for (uint64_t b = 0; b < nb; ++b) local += hb[b];
+  CKS(comm_allgather_host(ctx, &local, 8, all));
+  std::vector<double> tot(world);
+  for (int r = 0; r < world; ++r) std::memcpy(&tot[r], all.data() + (size_t)r * 8, 8);
+  double total = 0.0, before = 0.0;
+  for (int r = 0; r < world; ++r) { if (r == rank) before = total; total += tot[r]; }
+  if (!(total > 0.0)) { picked = -1; return LKM_OK; }
+  const F u01 = unit<F>(rng);
+  const double thr = (double)(u01 * (F)total);
+  long long mine = -1;
+  const bool last_nonempty = [&] { for (int r = world - 1; r >= 0; --r) if (sm.n[r]) return r == rank; return false; }();
+  if (n && ((thr >= before && thr < before + local) || (last_nonempty && thr >= before + local))) {
+    double run = before;
+    uint64_t fb = nb - 1;
+    double fp = 0.0;
+    bool hit = false;
+    for (uint64_t b = 0; b < nb; ++b) {
+      const double nxt = run + hb[b];
+      if (nxt > thr) { fb = b; fp = run; hit = true; break; }
+      run = nxt;
+    }
+    if (!hit) fp = run - hb[nb - 1];
+    long long* didx = reinterpret_cast<long long*>(ctx->scratch.as<char>() + 48);
+    fast_pick_kernel<F><<<1, 256, 0, ctx->stream>>>(dW, n, fb, fp, thr, didx);
+    CK(cudaGetLastError());
+    ctx->launches++;
+    CK(cudaMemcpyAsync(&mine, didx, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    mine += (long long)ctx->row_offset;
+  }
+  CKS(comm_allgather_host(ctx, &mine, 8, all));
+  picked = -1;
+  for (int r = 0; r < world; ++r) { long long v; std::memcpy(&v, all.data() + (size_t)r * 8, 8); if (v >= 0 && picked < 0) picked = v; }
+  return LKM_OK;
+}
+
+// k_means_plusplus (weights = ones) over the sharded matrix
+template <typename F>
+static lkm_status kmeanspp_sharded(lkm_ctx* ctx, const ShardMap& sm, uint64_t k, HostRng& rng, int pick_mode, F* dC) {
+  const uint64_t n = ctx->n, d = ctx->d;
+  const F* dX = reinterpret_cast<const F*>(ctx->X);
+  CK(ctx->dists.ensure(std::max<uint64_t>(n, 1) * sizeof(F)));
+  CK(ctx->wdists.ensure(std::max<uint64_t>(n, 1) * sizeof(F)));
+  CK(ctx->weights.ensure(std::max<uint64_t>(n, 1) * sizeof(F)));
+  std::vector<F> ones(std::min<uint64_t>(std::max<uint64_t>(n, 1), 1 << 20), (F)1);
+  for (uint64_t o = 0; o < n; o += ones.size())
+    CK(cudaMemcpyAsync(ctx->weights.as<F>() + o, ones.data(), std::min<uint64_t>(ones.size(), n - o) * sizeof(F),
+                       cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  long long idx = -1;
+  CKS(weighted_pick_sharded<F>(ctx, sm, ctx->weights.as<F>(), rng, pick_mode, idx));
+  if (idx < 0) return fail(ctx, LKM_ERR_BAD_WEIGHTS, "invalid weights for k-means++");
+  CKS(fetch_global_row<F>(ctx, sm, (uint64_t)idx, dC));
+  for (uint64_t c = 1; c < k; ++c) {
+    if (n) CKS(run_assign<F>(ctx, dX, n, d, dC + (c - 1) * d, 1, nullptr, ctx->dists.as<F>(), c > 1 ? 1 : 0, nullptr, ctx->wdists.as<F>()));
+    CKS(weighted_pick_sharded<F>(ctx, sm, ctx->wdists.as<F>(), rng, pick_mode, idx));
+    if (idx < 0) idx = 0;
+    CKS(fetch_global_row<F>(ctx, sm, (uint64_t)idx, dC + c * d));
+  }
+  return LKM_OK;
+}
+
+template <typename F>
+static lkm_status random_init_sharded(lkm_ctx* ctx, const ShardMap& sm, uint64_t k, HostRng& rng, F* dC) {
+  const uint64_t n_glob = ctx->n_global;
+  std::vector<uint64_t> idx;
+  if (!index_sample(rng, n_glob, k, idx)) return fail(ctx, LKM_ERR_SAMPLE_AMOUNT, "Random init: n_clusters > n_samples");
+  for (uint64_t c = 0; c < k; ++c) CKS(fetch_global_row<F>(ctx, sm, idx[c], dC + c * ctx->d));
+  return LKM_OK;
+}
+
+template <typename F>
+static lkm_status kmeans_para_sharded(lkm_ctx* ctx, const ShardMap& sm, uint64_t k, HostRng& rng, int pick_mode, F* dC) {
+  const uint64_t n = ctx->n, d = ctx->d, n_glob = ctx->n_global;
+  const int world = ctx->world;
+  const F* dX = reinterpret_cast<const F*>(ctx->X);
+  const uint64_t n_rounds = 8, cap = k * n_rounds;
+  CK(ctx->tmpc.ensure(cap * d * sizeof(F)));
+  F* dCand = ctx->tmpc.as<F>();
+  CK(ctx->dists.ensure(std::max<uint64_t>(n, 1) * sizeof(F)));
+  F* dD = ctx->dists.as<F>();
+  const uint64_t first = range_incl_u64(rng, 0, n_glob - 1);
+  CKS(fetch_global_row<F>(ctx, sm, first, dCand));
+  uint64_t n_cand = 1, scanned = 0;
+  const unsigned int sel_cap = (unsigned int)std::min<uint64_t>(std::max<uint64_t>(16 * k + 1024, 4096), 1u << 22);
+  CK(ctx->idxbuf.ensure((size_t)sel_cap * 8 + 64));
+  CK(ctx->part_inertia.ensure(1024 * 8));
+  std::vector<double> parts(1024);
+  std::vector<unsigned char> all;
+  bool full = false;
+  for (uint64_t r = 0; r < n_rounds && !full; ++r) {
+    if (n && n_cand > scanned)
+      CKS(run_assign<F>(ctx, dX, n, d, dCand + scanned * d, n_cand - scanned, nullptr, dD, scanned > 0 ? 1 : 0, nullptr, nullptr));
+    scanned = n_cand;
+    const uint64_t seed = range_incl_u64(rng, 0, 0xFFFFFFFFFFFFFFFEULL);
+    double local_cost = 0.0;
+    if (n) {
+      sum_f64_kernel<F><<<1024, 256, 0, ctx->stream>>>(dD, n, ctx->part_inertia.as<double>());
+      CK(cudaGetLastError());
+      CK(cudaMemcpyAsync(parts.data(), ctx->part_inertia.p, 1024 * 8, cudaMemcpyDeviceToHost, ctx->stream));
+      CK(cudaStreamSynchronize(ctx->stream));
+      for (double v : parts) local_cost += v;
+      ctx->launches++;
+    }
+    CKS(comm_allgather_host(ctx, &local_cost, 8, all));
+    double cost = 0.0;
+    for (int q = 0; q < world; ++q) { double v; std::memcpy(&v, all.data() + (size_t)q * 8, 8); cost += v; }
+    std::vector<unsigned long long> sel;
+    if (n) {
+      unsigned int* dcur = reinterpret_cast<unsigned int*>(ctx->idxbuf.as<char>() + (size_t)sel_cap * 8);
+      CK(cudaMemsetAsync(dcur, 0, 4, ctx->stream));
+      bernoulli_select_kernel<F><<<(int)std::min<uint64_t>((n + 255) / 256, 4096), 256, 0, ctx->stream>>>(
+          dD, n, (F)k, (F)cost, seed, ctx->row_offset, ctx->idxbuf.as<unsigned long long>(), sel_cap, dcur);
+      CK(cudaGetLastError());
+      ctx->launches++;
+      unsigned int got = 0;
+      CK(cudaMemcpyAsync(&got, dcur, 4, cudaMemcpyDeviceToHost, ctx->stream));
+      CK(cudaStreamSynchronize(ctx->stream));
+      got = std::min(got, sel_cap);
+      sel.resize(got);
+      if (got) CK(cudaMemcpy(sel.data(), ctx->idxbuf.p, (size_t)got * 8, cudaMemcpyDeviceToHost));
+      std::sort(sel.begin(), sel.end());
+    }
+    // publish the selected rows: counts first, then padded (index, row) records, merged in rank order
+    // (shards are contiguous and ordered by rank, so the concatenation is globally ascending)
+    uint64_t my_cnt = sel.size();
+    CKS(comm_allgather_host(ctx, &my_cnt, 8, all));
+    std::vector<uint64_t> cnts(world);
+    uint64_t max_cnt = 0;
+    for (int q = 0; q < world; ++q) { std::memcpy(&cnts[q], all.data() + (size_t)q * 8, 8); max_cnt = std::max(max_cnt, cnts[q]); }
+    if (max_cnt == 0) continue;
+    const size_t rec = d * sizeof(F);
+    std::vector<unsigned char> mine(max_cnt * rec, 0);
+    for (uint64_t i = 0; i < my_cnt; ++i)
+      CK(cudaMemcpyAsync(mine.data() + i * rec, dX + (sel[i] - ctx->row_offset) * d, rec, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    CKS(comm_allgather_host(ctx, mine.data(), mine.size(), all));
+    for (int q = 0; q < world && !full; ++q)
+      for (uint64_t i = 0; i < cnts[q]; ++i) {
+        CK(cudaMemcpyAsync(dCand + n_cand * d, all.data() + ((size_t)q * max_cnt + i) * rec, rec, cudaMemcpyHostToDevice, ctx->stream));
+        n_cand += 1;
+        if (n_cand >= cap) { full = true; break; }
+      }
+    CK(cudaStreamSynchronize(ctx->stream));
+  }
+  // weights = global histogram of the nearest candidate
+  std::vector<double> hist(n_cand, 0.0);
+  if (n) {
+    CK(ctx->labels.ensure(n * 4));
+    CKS(run_assign<F>(ctx, dX, n, d, dCand, n_cand, ctx->labels.as<uint32_t>(), nullptr, 0, nullptr, nullptr));
+    CK(ctx->tmpx.ensure(n_cand * 4 + 64));
+    unsigned int* dhist = ctx->tmpx.as<unsigned int>();
+    CK(cudaMemsetAsync(dhist, 0, n_cand * 4, ctx->stream));
+    label_hist_kernel<<<(int)std::min<uint64_t>((n + 255) / 256, 4096), 256, 0, ctx->stream>>>(ctx->labels.as<uint32_t>(), n, dhist);
+    CK(cudaGetLastError());
+    ctx->launches++;
+    std::vector<unsigned int> hh(n_cand);
+    CK(cudaMemcpyAsync(hh.data(), dhist, n_cand * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    for (uint64_t c = 0; c < n_cand; ++c) hist[c] = (double)hh[c];
+  }
+  CKS(comm_allgather_host(ctx, hist.data(), n_cand * 8, all));
+  std::vector<F> w(n_cand, (F)0);
+  for (uint64_t c = 0; c < n_cand; ++c) {
+    double s = 0.0;
+    for (int q = 0; q < world; ++q) { double v; std::memcpy(&v, all.data() + ((size_t)q * n_cand + c) * 8, 8); s += v; }
+    w[c] = (F)s;
+  }
+  CK(ctx->tmpx.ensure(n_cand * sizeof(F) + 64));
+  CK(cudaMemcpyAsync(ctx->tmpx.p, w.data(), n_cand * sizeof(F), cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  // the candidates are replicated on every rank: weighted k-means++ over them is rank-local and,
+  // with identical rng streams, identical everywhere
+  return weighted_kmeanspp<F>(ctx, dCand, n_cand, d, ctx->tmpx.as<F>(), k, rng, pick_mode, dC);
+}
+
 // KMeansInit::run (KM/init.rs:83-101) -> device centroids dC (k x d)
 template <typename F>
 static lkm_status run_init(lkm_ctx* ctx, const lkm_params* p, HostRng& rng, F* dC) {
   const uint64_t k = p->n_clusters, n = ctx->n, d = ctx->d;
   const F* dX = reinterpret_cast<const F*>(ctx->X);
-  if (ctx->world > 1 && p->init_method != LKM_INIT_PRECOMPUTED)
-    return fail(ctx, LKM_ERR_UNSUPPORTED, "multi-GPU seeding is not implemented yet: use Precomputed centroids");
+  if (ctx->world > 1 && p->init_method != LKM_INIT_PRECOMPUTED) {
+    if (ctx->n_global == 0) return fail(ctx, LKM_ERR_BAD_WEIGHTS, "seeding on an empty dataset");
+    ShardMap sm;
+    CKS(shard_map(ctx, sm));
+    switch (p->init_method) {
+      case LKM_INIT_RANDOM: return random_init_sharded<F>(ctx, sm, k, rng, dC);
+      case LKM_INIT_KMEANS_PLUSPLUS: return kmeanspp_sharded<F>(ctx, sm, k, rng, p->pick_mode, dC);
+      case LKM_INIT_KMEANS_PARA: return kmeans_para_sharded<F>(ctx, sm, k, rng, p->pick_mode, dC);
+      default: return fail(ctx, LKM_ERR_INVALID_ARG, "unknown init_method");
+    }
+  }
   switch (p->init_method) {
     case LKM_INIT_PRECOMPUTED:
       if (!p->precomputed || p->precomputed_rows != k || p->precomputed_cols != d)
@@ -1001,7 +1301,7 @@ LKM_EXPORT lkm_status lkm_destroy(lkm_ctx* ctx) {
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   if (ctx->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->comm);
   DevBuf* bufs[] = {&ctx->xbuf, &ctx->cbuf, &ctx->part_sums, &ctx->part_counts, &ctx->part_inertia, &ctx->shift_part,
-                    &ctx->counts_out, &ctx->state, &ctx->gather, &ctx->labels, &ctx->dists, &ctx->wdists, &ctx->cum,
+                    &ctx->counts_out, &ctx->state, &ctx->gather, &ctx->gather2, &ctx->labels, &ctx->dists, &ctx->wdists, &ctx->cum,
                     &ctx->scratch, &ctx->tmpx, &ctx->tmpc, &ctx->idxbuf, &ctx->bsum, &ctx->weights, &ctx->flushbuf};
   for (DevBuf* b : bufs) b->release();
   for (cudaEvent_t e : ctx->iter_events) cudaEventDestroy(e);

@@ -541,12 +541,15 @@ __global__ void gen_blobs_kernel(F* __restrict__ X, unsigned long long n, int d,
 // out[1] = 1 if any weight is negative/NaN (InvalidWeight).
 template <typename F>
 __global__ void __launch_bounds__(256) seq_prefix_kernel(const F* __restrict__ w, unsigned long long n,
-                                                         F* __restrict__ cum, F* __restrict__ out) {
+                                                         F* __restrict__ cum, F* __restrict__ out, F carry_in,
+                                                         unsigned long long n_cum) {
+  // carry_in / n_cum: row-sharded use — this rank continues the prefix of the ranks before it and
+  // writes cum entries for its first n_cum rows (n for inner ranks, n-1 on the last rank)
   constexpr int CH = 2048;
   __shared__ F buf[CH];
   __shared__ F carry;
   __shared__ int bad;
-  if (threadIdx.x == 0) { carry = (F)0; bad = 0; }
+  if (threadIdx.x == 0) { carry = carry_in; bad = 0; }
   __syncthreads();
   for (unsigned long long base = 0; base < n; base += CH) {
     const int m = (int)min((unsigned long long)CH, n - base);
@@ -566,7 +569,7 @@ __global__ void __launch_bounds__(256) seq_prefix_kernel(const F* __restrict__ w
     }
     __syncthreads();
     for (int i = threadIdx.x; i < m; i += blockDim.x)
-      if (base + i < n - 1) cum[base + i] = buf[i];
+      if (base + i < n_cum) cum[base + i] = buf[i];
     __syncthreads();
   }
   if (threadIdx.x == 0) { out[0] = carry; out[1] = bad ? (F)1 : (F)0; }

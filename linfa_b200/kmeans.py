@@ -191,6 +191,11 @@ class Context:
         self.check(getattr(_ffi.lib, f"lkm_set_data_{sfx}")(self.h, _ffi.fptr(x, ct), x.shape[0], x.shape[1], stride))
         self.dtype, self.shape = x.dtype, x.shape
 
+    def set_data_sharded(self, x_local, row_offset, n_global):
+        """This rank's row block [row_offset, row_offset + len(x_local)) of an n_global-row matrix."""
+        self.set_data(x_local)
+        self.set_shard(row_offset, n_global)
+
     def set_data_device(self, ptr, n, d, dtype):
         sfx, _ = _ffi.sfx_of(dtype)
         self.check(getattr(_ffi.lib, f"lkm_set_data_device_{sfx}")(self.h, C.c_void_p(ptr), n, d))

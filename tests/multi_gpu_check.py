@@ -53,6 +53,42 @@ def main():
             ok = ok and good
             solo.close()
         ctx.close()
+    # ---- sharded seeding: same rng => same picks as one GPU holding every row ----
+    for dtype, n, d, k in [(np.float64, 50_001, 6, 9), (np.float32, 120_000, 32, 16)]:
+        ctx = lb.Context(local)
+        D.init_comm(ctx, device=torch.device("cuda", local))
+        g = np.random.default_rng(9)
+        centres = g.uniform(-30, 30, (k, d)).astype(dtype)
+        lo, hi = D.shard_range(n, rank, world)
+        ctx.gen_blobs(hi - lo, d, centres, 1.0, seed=21, row_offset=lo, n_global=n)
+        solo = lb.Context(local)
+        solo.gen_blobs(n, d, centres, 1.0, seed=21)
+        res = {}
+        for name, init, mode in [("random", lb.KMeansInit.Random, lb.PickMode.Exact),
+                                 ("kmeans++ exact", lb.KMeansInit.KMeansPlusPlus, lb.PickMode.Exact),
+                                 ("kmeans++ fast", lb.KMeansInit.KMeansPlusPlus, lb.PickMode.Fast),
+                                 ("kmeans||", lb.KMeansInit.KMeansPara, lb.PickMode.Fast)]:
+            p = (lb.KMeans.params_with_rng(k, lb.Xoshiro256Plus.seed_from_u64(40)).n_runs(1).max_n_iterations(10)
+                 .init_method(init).pick_mode(mode).check())
+            m_sh = p.fit_resident(ctx)
+            m_1 = p.fit_resident(solo)
+            t = torch.from_numpy(m_sh.centroids().copy()).cuda()
+            allc = [torch.zeros_like(t) for _ in range(world)]
+            dist.all_gather(allc, t)
+            same = all(torch.equal(allc[0], x) for x in allc)
+            scale = np.abs(m_1.centroids()).max()
+            if name in ("random", "kmeans++ exact"):
+                good = same and np.allclose(m_sh.centroids(), m_1.centroids(), rtol=1e-5, atol=1e-5 * scale) \
+                    and m_sh.cluster_count().tolist() == m_1.cluster_count().tolist()
+            else:  # different (but legal) picks: compare quality
+                good = same and float(m_sh.inertia()) <= 1.5 * float(m_1.inertia()) + 1e-9
+            res[name] = good
+            if rank == 0:
+                print(f"[multi_gpu_check] seeding {np.dtype(dtype).name} n={n} k={k} {name}: {'ok' if good else 'MISMATCH'} "
+                      f"inertia sharded={float(m_sh.inertia()):.6g} solo={float(m_1.inertia()):.6g}", flush=True)
+            ok = ok and good
+        ctx.close()
+        solo.close()
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.broadcast(flag, 0)
     dist.barrier()
