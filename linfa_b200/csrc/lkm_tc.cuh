@@ -360,7 +360,7 @@ __host__ __device__ inline size_t tc_smem_bytes(int k, int kp, int accumulate) {
     b += (size_t)kTcSubsets * (k + 1) * 32 * 4;   // sums (+1 dummy row per subset)
     b += (((size_t)k * 4) + 15) & ~(size_t)15;    // counts
   }
-  b += kTcRows * 4 * 3 + 16;      // labels, dists, flag list
+  b += kTcRows * 4 * 4 + 16;      // labels, subset-major labels, dists, flag list
   return b + 1024;                // slack for the 1024-byte alignment of the operand tiles
 }
 
@@ -381,7 +381,8 @@ __global__ void __launch_bounds__(128, 2) lloyd_tc_kernel(const TcArgs a) {
   float* acc = cn + kp;
   uint32_t* cnt = reinterpret_cast<uint32_t*>(acc + (a.accumulate ? (size_t)kTcSubsets * (k + 1) * 32 : 0));
   uint32_t* labs = cnt + (a.accumulate ? ((k + 3) & ~3) : 0);
-  float* dist_s = reinterpret_cast<float*>(labs + kTcRows);
+  uint32_t* labs2 = labs + kTcRows;  // labs2[sub * 32 + i] = label of row sub + 4 i
+  float* dist_s = reinterpret_cast<float*>(labs2 + kTcRows);
   uint32_t* flags = reinterpret_cast<uint32_t*>(dist_s + kTcRows);
   double* red = reinterpret_cast<double*>(a_hi);  // only used after the last tile
   __shared__ __align__(8) uint64_t bar;
@@ -515,10 +516,13 @@ __global__ void __launch_bounds__(128, 2) lloyd_tc_kernel(const TcArgs a) {
       const float4 v = *reinterpret_cast<const float4*>(raw + row_off + (((uint32_t)c ^ row_x) << 4));
       xr[4 * c] = v.x; xr[4 * c + 1] = v.y; xr[4 * c + 2] = v.z; xr[4 * c + 3] = v.w;
     }
-    float xx0 = 0.f, xx1 = 0.f;
+    float xx0 = 0.f, xx1 = 0.f, xx2 = 0.f, xx3 = 0.f;
 #pragma unroll
-    for (int j = 0; j < 32; j += 2) { xx0 = fmaf(xr[j], xr[j], xx0); xx1 = fmaf(xr[j + 1], xr[j + 1], xx1); }
-    const float xn = sqrtf(xx0 + xx1) * 1.000001f;
+    for (int j = 0; j < 32; j += 4) {
+      xx0 = fmaf(xr[j], xr[j], xx0); xx1 = fmaf(xr[j + 1], xr[j + 1], xx1);
+      xx2 = fmaf(xr[j + 2], xr[j + 2], xx2); xx3 = fmaf(xr[j + 3], xr[j + 3], xx3);
+    }
+    const float xn = sqrtf((xx0 + xx1) + (xx2 + xx3)) * 1.000001f;
     const float margin = 1.1f * (m_a0 + xn * m_a1 + m_g2 * (xn + cmax) * (xn + cmax));
 
     const bool ok = tc::mbar_wait(&bar, parity);
@@ -615,6 +619,7 @@ __global__ void __launch_bounds__(128, 2) lloyd_tc_kernel(const TcArgs a) {
     }
     if (row_ok) {
       const uint32_t lab = labs[t];
+      labs2[(t & 3) * 32 + (t >> 2)] = lab;
       inert += (double)dist_s[t];
       if (a.accumulate) atomicAdd(&cnt[lab], 1u);  // integer atomics: exact, order-independent
       if (a.labels) a.labels[row0 + t] = lab;
@@ -622,16 +627,39 @@ __global__ void __launch_bounds__(128, 2) lloyd_tc_kernel(const TcArgs a) {
     }
     // ---- deterministic accumulation: thread (sub, feat) walks rows sub, sub+4, ... in order ----
     if (a.accumulate) {
+      __syncthreads();  // labs2 complete
       if (rows == kTcRows) {
-#pragma unroll 4
-        for (int ii = 0; ii < 16; ++ii) {
-          const int l0 = (int)labs[sub + 8 * ii], l1 = (int)labs[sub + 8 * ii + 4];
-          const float x0 = *reinterpret_cast<const float*>(raw + 1024u * ii + acc_off_e);
-          const float x1 = *reinterpret_cast<const float*>(raw + 1024u * ii + acc_off_o);
-          if (l0 != cur_lab) { my_acc[cur_lab * 32] += cur_acc; cur_lab = l0; cur_acc = 0.f; }
-          cur_acc += x0;
-          if (l1 != cur_lab) { my_acc[cur_lab * 32] += cur_acc; cur_lab = l1; cur_acc = 0.f; }
-          cur_acc += x1;
+        // the 32 labels of this subset (identical for the 32 lanes of the warp -> uniform branches)
+        uint4 lv[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) lv[q] = *reinterpret_cast<const uint4*>(labs2 + sub * 32 + 4 * q);
+        const uint32_t first = lv[0].x;
+        uint32_t diff = 0;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) diff |= (lv[q].x ^ first) | (lv[q].y ^ first) | (lv[q].z ^ first) | (lv[q].w ^ first);
+        if (diff == 0) {
+          // one label for the whole subset: sum its 32 rows in registers, in row order
+          if ((int)first != cur_lab) { my_acc[cur_lab * 32] += cur_acc; cur_lab = (int)first; cur_acc = 0.f; }
+#pragma unroll
+          for (int ii = 0; ii < 16; ++ii) {
+            cur_acc += *reinterpret_cast<const float*>(raw + 1024u * ii + acc_off_e);
+            cur_acc += *reinterpret_cast<const float*>(raw + 1024u * ii + acc_off_o);
+          }
+        } else {
+          // mixed labels: flush the run and add row by row into the thread-owned accumulators
+          my_acc[cur_lab * 32] += cur_acc;
+          cur_lab = k;
+          cur_acc = 0.f;
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const uint32_t l4[4] = {lv[q].x, lv[q].y, lv[q].z, lv[q].w};
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const int i = 4 * q + u;  // row sub + 4 i
+              const float xv = *reinterpret_cast<const float*>(raw + 1024u * (i >> 1) + ((i & 1) ? acc_off_o : acc_off_e));
+              my_acc[l4[u] * 32] += xv;
+            }
+          }
         }
       } else {
         for (int r = sub; r < rows; r += kTcSubsets) {
