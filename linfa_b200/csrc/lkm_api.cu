@@ -136,6 +136,7 @@ static lkm_status fail(lkm_ctx* ctx, lkm_status s, const char* msg) {
 // ---- launch helpers ----------------------------------------------------------
 struct Plan {
   bool ok = false;
+  int certified = 0;
   int vec = 0, x_stride = 0, tpr = 1;
   size_t tile_bytes = 0;
   // fused
@@ -213,7 +214,9 @@ template <typename F> static lkm_status plan_assign(lkm_ctx* ctx, const void* X,
   uint64_t kc = std::min<uint64_t>(k, c_budget / (d * sizeof(F)));
   if (kc == 0) return fail(ctx, LKM_ERR_UNSUPPORTED, "row too wide for the shared-memory tile");
   p.kc = (int)kc;
-  p.smem = al16(kc * d * sizeof(F)) + p.tile_bytes;
+  // certified FMA path: compile-time d, every centroid resident, not forced to the exact path
+  p.certified = (has_static_d(d) && kc == k && ctx->force_path != 0) ? 1 : 0;
+  p.smem = al16(kc * d * sizeof(F)) + p.tile_bytes + (p.certified ? al16((k + 1) * sizeof(F)) : 0);
   const uint64_t n_tiles = (n + kThreads / p.tpr - 1) / (kThreads / p.tpr);
   const int occ = std::max(1, occupancy<F, MODE_ASSIGN>((int)d, p.smem));
   p.grid = (int)std::min<uint64_t>(std::max<uint64_t>(n_tiles, 1), (uint64_t)ctx->sm_count * occ);
@@ -227,7 +230,7 @@ template <typename F> static lkm_status plan_fused(lkm_ctx* ctx, const void* X, 
   tile_layout<F>(d, X, p);
   const size_t limit = ctx->smem_optin - 1024;
   const size_t kdF = k * d * sizeof(F);
-  const size_t fixed = p.tile_bytes + al16(kdF) + al16(k * 4) + kThreads * 4 + 64;
+  const size_t fixed = p.tile_bytes + al16(kdF) + al16(k * 4) + kThreads * 4 + 64 + al16((k + 1) * sizeof(F));
   p.fused = fixed + al16(kdF) <= limit;
   if (!p.fused) return LKM_OK;
   int subsets = d <= (uint64_t)kThreads ? (int)(kThreads / d) : 1;
@@ -237,7 +240,9 @@ template <typename F> static lkm_status plan_fused(lkm_ctx* ctx, const void* X, 
   while (subsets > 1 && fixed + (size_t)subsets * per > limit) --subsets;
   p.n_subsets = subsets;
   p.kc = (int)k;
-  p.smem = al16(kdF) + p.tile_bytes + al16((size_t)subsets * kdF) + al16((size_t)subsets * k * 4) + kThreads * 4;
+  p.certified = (has_static_d(d) && ctx->force_path != 0) ? 1 : 0;
+  p.smem = al16(kdF) + p.tile_bytes + al16((size_t)subsets * kdF) + al16((size_t)subsets * k * 4) + kThreads * 4 +
+           (p.certified ? al16((k + 1) * sizeof(F)) : 0);
   const uint64_t n_tiles = (n + kThreads / p.tpr - 1) / (kThreads / p.tpr);
   const int occ = std::max(1, occupancy<F, MODE_FUSED>((int)d, p.smem));
   p.grid = (int)std::min<uint64_t>(std::max<uint64_t>(n_tiles, 1), (uint64_t)ctx->sm_count * occ);
@@ -255,7 +260,7 @@ static lkm_status run_assign(lkm_ctx* ctx, const F* dX, uint64_t n, uint64_t d, 
   a.X = dX; a.n = n; a.d = (int)d; a.k = (int)k; a.C = dC;
   a.labels = labels; a.dists = dists; a.min_combine = min_combine; a.weights = weights; a.wdists = wdists;
   a.n_subsets = 1; a.x_stride = p.x_stride; a.kc = p.kc; a.chunk_base = 0; a.chunk_rows = (int)k; a.vec = p.vec;
-  a.tpr = p.tpr;
+  a.tpr = p.tpr; a.certified = p.certified;
   CK((launch_lloyd<F, MODE_ASSIGN>(a, p.grid, p.smem, ctx->stream)));
   ctx->launches++;
   return LKM_OK;
@@ -323,7 +328,7 @@ static lkm_status run_lloyd(lkm_ctx* ctx, F* dC2, uint64_t k, uint64_t max_iter,
   Plan pf;
   CKS(plan_fused<F>(ctx, dX, n, d, k, pf));
   if (use_tc) { pf.fused = true; pf.grid = tc_grid; }
-  ctx->last_path = use_tc ? 2 : 0;
+  ctx->last_path = use_tc ? 2 : ((pf.fused && pf.certified) ? 1 : 0);
   Plan pa, pu;
   int n_chunks = 1, chunk_rows = (int)k;
   if (!pf.fused) {
@@ -396,14 +401,14 @@ static lkm_status run_lloyd(lkm_ctx* ctx, F* dC2, uint64_t k, uint64_t max_iter,
         a.part_sums = ctx->part_sums.as<F>(); a.part_counts = ctx->part_counts.as<uint32_t>();
         a.part_inertia = ctx->part_inertia.as<double>(); a.state = dstate;
         a.n_subsets = pf.n_subsets; a.x_stride = pf.x_stride; a.kc = pf.kc; a.chunk_base = 0; a.chunk_rows = (int)k;
-        a.vec = pf.vec; a.tpr = pf.tpr;
+        a.vec = pf.vec; a.tpr = pf.tpr; a.certified = pf.certified; a.state_rw = dstate;
         CK((launch_lloyd<F, MODE_FUSED>(a, pf.grid, pf.smem, ctx->stream)));
         ctx->launches++;
       } else {
         LloydArgs<F> a{};
         a.X = dX; a.n = n; a.d = (int)d; a.k = (int)k; a.C = Ccur;
         a.labels = ctx->labels.as<uint32_t>(); a.dists = ctx->dists.as<F>(); a.state = dstate;
-        a.n_subsets = 1; a.x_stride = pa.x_stride; a.kc = pa.kc; a.chunk_rows = (int)k; a.vec = pa.vec; a.tpr = pa.tpr;
+        a.n_subsets = 1; a.x_stride = pa.x_stride; a.kc = pa.kc; a.chunk_rows = (int)k; a.vec = pa.vec; a.tpr = pa.tpr; a.certified = pa.certified; a.state_rw = dstate;
         CK((launch_lloyd<F, MODE_ASSIGN>(a, pa.grid, pa.smem, ctx->stream)));
         // inertia: fixed-order f64 partial sums of the min distances, one per source slot
         sum_f64_kernel<F><<<grid, 256, 0, ctx->stream>>>(ctx->dists.as<F>(), n, ctx->part_inertia.as<double>());

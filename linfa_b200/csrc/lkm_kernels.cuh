@@ -71,6 +71,8 @@ template <typename F> struct LloydArgs {
   int chunk_rows;
   int vec;               // rows are 16-byte vectorisable
   int tpr;               // threads cooperating on one row (power of two <= 32); tile = kThreads/tpr rows
+  int certified;         // 1: expanded-form FMA scores + certified argmin (D > 0, all centroids resident)
+  LloydState* state_rw;  // fallback-row counter of the certified path (may be null)
 };
 
 // ---- squared distance, exact reference order ------------------------------
@@ -162,6 +164,67 @@ __device__ __forceinline__ void combine_candidates(int tpr, F& best, int& bidx) 
   }
 }
 
+// Certified argmin on CUDA cores (expanded form): w_c = ||c||^2 - 2 x.c with FMA chains, running best
+// and second best.  With eps = 2^-24 (f32) / 2^-53 (f64), |w_c - W_c| <= eps[(2d+2)|x|C + 2C^2]
+// (d FMA roundings on the dot, one on ||c||^2, one on the final fma; C = max|c|) and the
+// reference's direct form is within (d+2) eps of the true squared distance <= (|x|+C)^2, so
+//   second - best > 1.1 eps [ (4d+4)|x|C + 4C^2 + 2(d+2)(|x|+C)^2 ]
+// proves that the reference's strict-'<' scan picks the same centroid.  Otherwise (near ties,
+// exact ties, NaN) the row is re-scanned in the reference's exact arithmetic.  The winner's
+// distance is always evaluated in the exact direct form.
+template <typename F, int D>
+__device__ __forceinline__ bool scan_centroids_certified(const F* __restrict__ cs, const F* __restrict__ cn, int k,
+                                                         F cmax, const F* __restrict__ xrow, F& best_dist, int& bidx) {
+  F x[D];
+#pragma unroll
+  for (int j = 0; j < D; ++j) x[j] = xrow[j];
+  F xx = (F)0;
+#pragma unroll
+  for (int j = 0; j < D; ++j) xx = fma(x[j], x[j], xx);
+  F b0 = (F)INFINITY, s0 = (F)INFINITY, b1 = (F)INFINITY, s1 = (F)INFINITY;
+  int i0 = 0, i1 = 1;
+  int c = 0;
+  for (; c + 2 <= k; c += 2) {
+    F d0 = (F)0, d1 = (F)0;
+#pragma unroll
+    for (int j = 0; j < D; ++j) {
+      d0 = fma(cs[c * D + j], x[j], d0);
+      d1 = fma(cs[(c + 1) * D + j], x[j], d1);
+    }
+    const F w0 = fma((F)-2, d0, cn[c]);
+    const F w1 = fma((F)-2, d1, cn[c + 1]);
+    s0 = fmin(s0, fmax(w0, b0));
+    i0 = (w0 < b0) ? c : i0;
+    b0 = fmin(b0, w0);
+    s1 = fmin(s1, fmax(w1, b1));
+    i1 = (w1 < b1) ? (c + 1) : i1;
+    b1 = fmin(b1, w1);
+  }
+  if (c < k) {
+    F d0 = (F)0;
+#pragma unroll
+    for (int j = 0; j < D; ++j) d0 = fma(cs[c * D + j], x[j], d0);
+    const F w0 = fma((F)-2, d0, cn[c]);
+    s0 = fmin(s0, fmax(w0, b0));
+    i0 = (w0 < b0) ? c : i0;
+    b0 = fmin(b0, w0);
+  }
+  F best, second;
+  int bi;
+  if (b1 < b0 || (b1 == b0 && i1 < i0)) { best = b1; bi = i1; second = fmin(s1, b0); }
+  else { best = b0; bi = i0; second = fmin(s0, b1); }
+  const F eps = sizeof(F) == 4 ? (F)5.9604645e-8 : (F)1.1102230246251565e-16;
+  const F xn = sqrt(xx) * (F)1.000001;
+  const F margin = (F)1.1 * eps * ((F)(4 * D + 4) * xn * cmax + (F)4 * cmax * cmax + (F)(2 * (D + 2)) * (xn + cmax) * (xn + cmax));
+  if ((second - best) > margin) {  // NaN anywhere -> not certified
+    bidx = bi;
+    best_dist = sqdist_reg<F, D>(cs + bi * D, x);
+    return true;
+  }
+  scan_centroids<F, D>(cs, k, D, 0, xrow, true, best_dist, bidx);
+  return false;
+}
+
 // coalesced global -> smem copy of `rows` contiguous rows into a padded tile
 template <typename F>
 __device__ __forceinline__ void load_tile(F* __restrict__ xs, const F* __restrict__ g, int rows, int d, int x_stride,
@@ -201,6 +264,8 @@ __global__ void __launch_bounds__(kThreads) lloyd_kernel(const LloydArgs<F> a) {
   size_t off = 0;
   F* cs = reinterpret_cast<F*>(smem_raw + off);
   if (MODE != MODE_UPDATE) off += ((size_t)a.kc * d * sizeof(F) + 15) & ~(size_t)15;
+  F* cnorm = reinterpret_cast<F*>(smem_raw + off);  // squared norms (+ max norm at [k]) of the certified path
+  if (MODE != MODE_UPDATE && a.certified) off += ((size_t)(a.k + 1) * sizeof(F) + 15) & ~(size_t)15;
   const int tpr = (D > 0) ? 1 : a.tpr;
   const int tile_rows = kThreads / tpr;
   F* xs = reinterpret_cast<F*>(smem_raw + off);
@@ -222,6 +287,21 @@ __global__ void __launch_bounds__(kThreads) lloyd_kernel(const LloydArgs<F> a) {
     for (int e = t; e < a.k * d; e += kThreads) cs[e] = a.C[e];
   }
   __syncthreads();
+  if (MODE != MODE_UPDATE && D > 0 && a.certified) {
+    for (int c = t; c < a.k; c += kThreads) {
+      double nn = 0.0;
+      for (int j = 0; j < d; ++j) nn += (double)cs[c * d + j] * (double)cs[c * d + j];
+      cnorm[c] = (F)nn;
+    }
+    __syncthreads();
+    if (t == 0) {
+      F m = (F)0;
+      for (int c = 0; c < a.k; ++c) m = (cnorm[c] > m) ? cnorm[c] : m;  // NaN norms are skipped: such rows fall back
+      cnorm[a.k] = sqrt(m) * (F)1.000001;
+    }
+    __syncthreads();
+  }
+  unsigned int my_fallbacks = 0;
 
   // accumulation role of this thread
   int sub = 0, feat = t;
@@ -251,7 +331,14 @@ __global__ void __launch_bounds__(kThreads) lloyd_kernel(const LloydArgs<F> a) {
       const F* xrow = xs + (size_t)(row_ok ? my_row : 0) * a.x_stride;
       if (tpr == 1) {
         if (n_chunks == 1) {
-          if (row_ok) scan_centroids<F, D>(cs, a.k, d, 0, xrow, true, best, bidx);
+          if constexpr (D > 0) {
+            if (row_ok) {
+              if (a.certified) my_fallbacks += scan_centroids_certified<F, D>(cs, cnorm, a.k, cnorm[a.k], xrow, best, bidx) ? 0u : 1u;
+              else scan_centroids<F, D>(cs, a.k, d, 0, xrow, true, best, bidx);
+            }
+          } else {
+            if (row_ok) scan_centroids<F, D>(cs, a.k, d, 0, xrow, true, best, bidx);
+          }
         } else {
           for (int ch = 0; ch < n_chunks; ++ch) {
             const int cb = ch * a.kc, rc = min(a.kc, a.k - cb);
@@ -321,6 +408,8 @@ __global__ void __launch_bounds__(kThreads) lloyd_kernel(const LloydArgs<F> a) {
     __syncthreads();
   }
 
+  if (MODE != MODE_UPDATE && a.certified && a.state_rw != nullptr && my_fallbacks)
+    atomicAdd(&a.state_rw->fallback_rows, (unsigned long long)my_fallbacks);
   if (MODE != MODE_ASSIGN) {
     if (acc_active && cur_lab >= 0) acc[((size_t)sub * a.chunk_rows + cur_lab) * d + feat] += cur_acc;
     __syncthreads();
