@@ -164,6 +164,15 @@ __device__ __forceinline__ void combine_candidates(int tpr, F& best, int& bidx) 
   }
 }
 
+// running (best, second best, index of best): two compares per element.  A NaN score leaves the
+// state untouched; a row whose scores are all NaN ends with best = second = +inf and is not certified.
+template <typename F> __device__ __forceinline__ void top2_update(F w, int c, F& best, F& second, int& idx) {
+  const bool lt_b = w < best, lt_s = w < second;
+  second = lt_b ? best : (lt_s ? w : second);
+  best = lt_b ? w : best;
+  idx = lt_b ? c : idx;
+}
+
 // Certified argmin on CUDA cores (expanded form): w_c = ||c||^2 - 2 x.c with FMA chains, running best
 // and second best.  With eps = 2^-24 (f32) / 2^-53 (f64), |w_c - W_c| <= eps[(2d+2)|x|C + 2C^2]
 // (d FMA roundings on the dot, one on ||c||^2, one on the final fma; C = max|c|) and the
@@ -193,26 +202,20 @@ __device__ __forceinline__ bool scan_centroids_certified(const F* __restrict__ c
     }
     const F w0 = fma((F)-2, d0, cn[c]);
     const F w1 = fma((F)-2, d1, cn[c + 1]);
-    s0 = fmin(s0, fmax(w0, b0));
-    i0 = (w0 < b0) ? c : i0;
-    b0 = fmin(b0, w0);
-    s1 = fmin(s1, fmax(w1, b1));
-    i1 = (w1 < b1) ? (c + 1) : i1;
-    b1 = fmin(b1, w1);
+    top2_update<F>(w0, c, b0, s0, i0);
+    top2_update<F>(w1, c + 1, b1, s1, i1);
   }
   if (c < k) {
     F d0 = (F)0;
 #pragma unroll
     for (int j = 0; j < D; ++j) d0 = fma(cs[c * D + j], x[j], d0);
     const F w0 = fma((F)-2, d0, cn[c]);
-    s0 = fmin(s0, fmax(w0, b0));
-    i0 = (w0 < b0) ? c : i0;
-    b0 = fmin(b0, w0);
+    top2_update<F>(w0, c, b0, s0, i0);
   }
   F best, second;
   int bi;
-  if (b1 < b0 || (b1 == b0 && i1 < i0)) { best = b1; bi = i1; second = fmin(s1, b0); }
-  else { best = b0; bi = i0; second = fmin(s0, b1); }
+  if (b1 < b0 || (b1 == b0 && i1 < i0)) { best = b1; bi = i1; second = (b0 < s1) ? b0 : s1; }
+  else { best = b0; bi = i0; second = (b1 < s0) ? b1 : s0; }
   const F eps = sizeof(F) == 4 ? (F)5.9604645e-8 : (F)1.1102230246251565e-16;
   const F xn = sqrt(xx) * (F)1.000001;
   const F margin = (F)1.1 * eps * ((F)(4 * D + 4) * xn * cmax + (F)4 * cmax * cmax + (F)(2 * (D + 2)) * (xn + cmax) * (xn + cmax));
@@ -321,7 +324,12 @@ __global__ void __launch_bounds__(kThreads) lloyd_kernel(const LloydArgs<F> a) {
     const int rows = (int)min((unsigned long long)tile_rows, a.n - row0);
     load_tile<F>(xs, a.X + row0 * (unsigned long long)d, rows, d, a.x_stride, a.vec);
     if (MODE == MODE_UPDATE) {
-      for (int r = t; r < rows; r += kThreads) labs[r] = a.labels_in[row0 + r];
+      for (int r = t; r < rows; r += kThreads) {
+        const uint32_t lab = a.labels_in[row0 + r];
+        labs[r] = lab;
+        const int lc = (int)lab - a.chunk_base;
+        if ((unsigned)lc < (unsigned)a.chunk_rows) atomicAdd(&cnt[lc], 1u);
+      }
     }
     __syncthreads();
     if (MODE != MODE_UPDATE) {
@@ -375,7 +383,11 @@ __global__ void __launch_bounds__(kThreads) lloyd_kernel(const LloydArgs<F> a) {
           }
         }
         if (a.wdists) a.wdists[row] = a.weights ? outd * a.weights[row] : outd;
-        if (MODE == MODE_FUSED) { labs[my_row] = (uint32_t)bidx; inert += (double)best; }
+        if (MODE == MODE_FUSED) {
+          labs[my_row] = (uint32_t)bidx;
+          inert += (double)best;
+          atomicAdd(&cnt[bidx], 1u);  // integer atomics: exact, order-independent (copy 0 of the counts)
+        }
       }
       if (MODE == MODE_FUSED) __syncthreads();
     }
@@ -386,21 +398,18 @@ __global__ void __launch_bounds__(kThreads) lloyd_kernel(const LloydArgs<F> a) {
             const int lab = (int)labs[r] - a.chunk_base;
             if ((unsigned)lab >= (unsigned)a.chunk_rows) continue;
             const F xv = xs[(size_t)r * a.x_stride + feat];
-            if (lab == cur_lab) {
-              cur_acc += xv;
-            } else {
+            if (lab != cur_lab) {
               if (cur_lab >= 0) acc[((size_t)sub * a.chunk_rows + cur_lab) * d + feat] += cur_acc;
               cur_lab = lab;
-              cur_acc = xv;
+              cur_acc = (F)0;
             }
-            if (feat == 0) cnt[sub * a.chunk_rows + lab] += 1u;
+            cur_acc += xv;
           }
         } else {
           for (int r = 0; r < rows; ++r) {
             const int lab = (int)labs[r] - a.chunk_base;
             if ((unsigned)lab >= (unsigned)a.chunk_rows) continue;
             for (int j = t; j < d; j += kThreads) acc[(size_t)lab * d + j] += xs[(size_t)r * a.x_stride + j];
-            if (t == 0) cnt[lab] += 1u;
           }
         }
       }
