@@ -11,6 +11,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <string>
@@ -90,6 +91,7 @@ struct lkm_ctx {
   uint64_t row_offset = 0, n_global = 0;
   int force_path = -1;
   int last_path = 0;
+  int tc_variant = 256;  // LKM_TC_VARIANT=128 selects the 128-thread tensor-core kernel
   uint64_t flush_bytes = 0;
   DevBuf flushbuf;
   std::vector<cudaEvent_t> iter_events;
@@ -291,7 +293,7 @@ static lkm_status run_lloyd(lkm_ctx* ctx, F* dC2, uint64_t k, uint64_t max_iter,
   if (kd > (uint64_t)std::numeric_limits<int>::max() / 4) return fail(ctx, LKM_ERR_UNSUPPORTED, "k*d too large");
   // tensor-core path: f32, d = 32, k <= 256, everything resident in shared memory
   bool use_tc = false;
-  int tc_grid = 0, tc_kp = 0, tc_cols = 0;
+  int tc_grid = 0, tc_kp = 0, tc_cols = 0, tc_threads = 128;
   size_t tc_smem = 0;
   if constexpr (std::is_same<F, float>::value) {
     if ((ctx->force_path == -1 || ctx->force_path == 2) && d == 32 && k <= 256 && n >= 1 &&
@@ -299,25 +301,21 @@ static lkm_status run_lloyd(lkm_ctx* ctx, F* dC2, uint64_t k, uint64_t max_iter,
       tc_kp = (int)((k + 31) / 32 * 32);
       tc_cols = 32;
       while (tc_cols < tc_kp) tc_cols *= 2;
-      tc_smem = tc_smem_bytes((int)k, tc_kp, 1);
+      const bool v256 = ctx->tc_variant != 128;
+      tc_smem = v256 ? tc256_smem_bytes((int)k, tc_kp, 1) : tc_smem_bytes((int)k, tc_kp, 1);
       if (tc_smem <= ctx->smem_optin) {
-        static size_t configured = 0;
-        if (tc_smem > configured) {
-          CK(cudaFuncSetAttribute(lloyd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem));
-          configured = tc_smem;
-        }
-        CK(cudaFuncSetAttribute(lloyd_tc_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                (int)cudaSharedmemCarveoutMaxShared));
-        int occ = 0;
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, lloyd_tc_kernel, 128, tc_smem));
+        const void* fn = v256 ? (const void*)lloyd_tc256_kernel : (const void*)lloyd_tc_kernel;
+        CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem));
+        CK(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
         // with the carve-out at its maximum, 228 KB per SM hold floor(228K / (dynamic + static + 1K reserved)) CTAs
-        occ = std::max(occ, (int)((228 * 1024) / (tc_smem + 2048)));
-        occ = std::min(occ, 2);                // 188 registers x 128 threads: two CTAs fill the register file
+        int occ = (int)((228 * 1024) / (tc_smem + 2048));
+        occ = std::min(occ, 2);                // register file: two CTAs per SM
         occ = std::min(occ, 512 / tc_cols);    // TMEM columns per SM
         if (occ >= 1) {
           const uint64_t n_tiles = (n + kTcRows - 1) / kTcRows;
           tc_grid = (int)std::min<uint64_t>(n_tiles, (uint64_t)ctx->sm_count * occ);
           use_tc = true;
+          tc_threads = v256 ? 256 : 128;
         }
       }
     }
@@ -391,7 +389,8 @@ static lkm_status run_lloyd(lkm_ctx* ctx, F* dC2, uint64_t k, uint64_t max_iter,
           ta.X = dX; ta.n = n; ta.k = (int)k; ta.kp = tc_kp; ta.tcols = tc_cols; ta.C = Ccur;
           ta.part_sums = ctx->part_sums.as<float>(); ta.part_counts = ctx->part_counts.as<uint32_t>();
           ta.part_inertia = ctx->part_inertia.as<double>(); ta.state = dstate; ta.accumulate = 1;
-          lloyd_tc_kernel<<<tc_grid, 128, tc_smem, ctx->stream>>>(ta);
+          if (tc_threads == 256) lloyd_tc256_kernel<<<tc_grid, 256, tc_smem, ctx->stream>>>(ta);
+          else lloyd_tc_kernel<<<tc_grid, 128, tc_smem, ctx->stream>>>(ta);
           CK(cudaGetLastError());
           ctx->launches++;
         }
@@ -1292,6 +1291,7 @@ LKM_EXPORT lkm_status lkm_create(lkm_ctx** out, int device) {
   cudaEventCreate(&ctx->ev1);
   cudaDeviceProp prop;
   if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return bail(LKM_ERR_CUDA);
+  if (const char* v = std::getenv("LKM_TC_VARIANT")) ctx->tc_variant = std::atoi(v);
   ctx->sm_count = prop.multiProcessorCount;
   ctx->smem_optin = prop.sharedMemPerBlockOptin;
   if (cudaMallocHost(&ctx->h_state, sizeof(LloydState)) != cudaSuccess) return bail(LKM_ERR_CUDA);
