@@ -91,7 +91,7 @@ struct lkm_ctx {
   uint64_t row_offset = 0, n_global = 0;
   int force_path = -1;
   int last_path = 0;
-  int tc_variant = 256;  // LKM_TC_VARIANT=128 selects the 128-thread tensor-core kernel
+  int tc_variant = 128;  // LKM_TC_VARIANT=256 selects the 256-thread tensor-core kernel (measured slower: 95 vs 85 us)
   uint64_t flush_bytes = 0;
   DevBuf flushbuf;
   std::vector<cudaEvent_t> iter_events;
@@ -301,7 +301,7 @@ static lkm_status run_lloyd(lkm_ctx* ctx, F* dC2, uint64_t k, uint64_t max_iter,
       tc_kp = (int)((k + 31) / 32 * 32);
       tc_cols = 32;
       while (tc_cols < tc_kp) tc_cols *= 2;
-      const bool v256 = ctx->tc_variant != 128;
+      const bool v256 = ctx->tc_variant == 256;
       tc_smem = v256 ? tc256_smem_bytes((int)k, tc_kp, 1) : tc_smem_bytes((int)k, tc_kp, 1);
       if (tc_smem <= ctx->smem_optin) {
         const void* fn = v256 ? (const void*)lloyd_tc256_kernel : (const void*)lloyd_tc_kernel;
