@@ -96,6 +96,7 @@ struct lkm_ctx {
   DevBuf flushbuf;
   std::vector<cudaEvent_t> iter_events;
   // workspaces
+  DevBuf tca_bsplit, tca_cn, tca_cmax;
   DevBuf cbuf, part_sums, part_counts, part_inertia, shift_part, counts_out, state, gather, gather2, labels, dists, wdists,
       cum, scratch, tmpx, tmpc, idxbuf, bsum, weights;
   LloydState* h_state = nullptr;  // pinned
@@ -347,6 +348,31 @@ static lkm_status run_lloyd(lkm_ctx* ctx, F* dC2, uint64_t k, uint64_t max_iter,
     CK(ctx->labels.ensure(std::max<uint64_t>(n, 1) * 4));
     CK(ctx->dists.ensure(std::max<uint64_t>(n, 1) * sizeof(F)));
   }
+  // two-pass shapes: tensor-core assignment when f32 and d is 32, 64 or 128
+  bool use_tca = false;
+  int tca_ka = 0, tca_chunks = 0, tca_grid = 0;
+  size_t tca_smem = 0;
+  if constexpr (std::is_same<F, float>::value) {
+    if (!pf.fused && (ctx->force_path == -1 || ctx->force_path == 2) && (d == 32 || d == 64 || d == 128) &&
+        (reinterpret_cast<uintptr_t>(dX) & 15) == 0) {
+      tca_ka = (int)(d / 32);
+      tca_chunks = (int)((k + kAsgChunk - 1) / kAsgChunk);
+      tca_smem = tc_assign_smem_bytes(tca_ka);
+      if (tca_smem <= ctx->smem_optin) {
+        CK(cudaFuncSetAttribute(tc_assign_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tca_smem));
+        CK(cudaFuncSetAttribute(tc_assign_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
+        int occ = (int)((228 * 1024) / (tca_smem + 2048));
+        occ = std::max(1, std::min(occ, 3));
+        const uint64_t n_tiles = (n + 127) / 128;
+        tca_grid = (int)std::min<uint64_t>(std::max<uint64_t>(n_tiles, 1), (uint64_t)ctx->sm_count * occ);
+        CK(ctx->tca_bsplit.ensure((size_t)tca_chunks * tca_ka * 16384));
+        CK(ctx->tca_cn.ensure((size_t)tca_chunks * kAsgChunk * 4));
+        CK(ctx->tca_cmax.ensure(16));
+        use_tca = true;
+        ctx->last_path = 2;
+      }
+    }
+  }
   const int grid = pf.fused ? pf.grid : pu.grid;
   CK(ctx->part_sums.ensure((size_t)grid * kd * sizeof(F)));
   CK(ctx->part_counts.ensure((size_t)grid * k * 4));
@@ -404,15 +430,37 @@ static lkm_status run_lloyd(lkm_ctx* ctx, F* dC2, uint64_t k, uint64_t max_iter,
         CK((launch_lloyd<F, MODE_FUSED>(a, pf.grid, pf.smem, ctx->stream)));
         ctx->launches++;
       } else {
+        bool assigned = false;
+        if constexpr (std::is_same<F, float>::value) {
+          if (use_tca) {
+            // tensor-core assignment: split the centroids into TF32 operand tiles, then score
+            CK(cudaMemsetAsync(ctx->tca_cmax.p, 0, 4, ctx->stream));
+            tc_prep_centroids_kernel<<<tca_chunks * tca_ka, 64, 0, ctx->stream>>>(Ccur, (int)k, (int)d, tca_ka, ctx->tca_bsplit.as<unsigned char>(),
+                                                                              ctx->tca_cn.as<float>(), ctx->tca_cmax.as<unsigned int>());
+            CK(cudaGetLastError());
+            TcAssignArgs ta{};
+            ta.X = dX; ta.n = n; ta.k = (int)k; ta.d = (int)d; ta.ka = tca_ka; ta.n_chunks = tca_chunks;
+            ta.bsplit = ctx->tca_bsplit.as<unsigned char>(); ta.cn = ctx->tca_cn.as<float>();
+            ta.cmax_bits = ctx->tca_cmax.as<unsigned int>(); ta.C = Ccur;
+            ta.labels = ctx->labels.as<uint32_t>(); ta.dists = ctx->dists.as<float>(); ta.state = dstate;
+            tc_assign_kernel<<<tca_grid, 128, tca_smem, ctx->stream>>>(ta);
+            CK(cudaGetLastError());
+            ctx->launches += 2;
+            assigned = true;
+          }
+        }
+        if (!assigned) {
         LloydArgs<F> a{};
         a.X = dX; a.n = n; a.d = (int)d; a.k = (int)k; a.C = Ccur;
         a.labels = ctx->labels.as<uint32_t>(); a.dists = ctx->dists.as<F>(); a.state = dstate;
         a.n_subsets = 1; a.x_stride = pa.x_stride; a.kc = pa.kc; a.chunk_rows = (int)k; a.vec = pa.vec; a.tpr = pa.tpr; a.certified = pa.certified; a.state_rw = dstate;
         CK((launch_lloyd<F, MODE_ASSIGN>(a, pa.grid, pa.smem, ctx->stream)));
+        ctx->launches++;
+        }
         // inertia: fixed-order f64 partial sums of the min distances, one per source slot
         sum_f64_kernel<F><<<grid, 256, 0, ctx->stream>>>(ctx->dists.as<F>(), n, ctx->part_inertia.as<double>());
         CK(cudaGetLastError());
-        ctx->launches += 2;
+        ctx->launches += 1;
         for (int ch = 0; ch < n_chunks; ++ch) {
           LloydArgs<F> u{};
           u.X = dX; u.n = n; u.d = (int)d; u.k = (int)k; u.labels_in = ctx->labels.as<uint32_t>();
@@ -1307,7 +1355,7 @@ LKM_EXPORT lkm_status lkm_destroy(lkm_ctx* ctx) {
   if (ctx->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->comm);
   DevBuf* bufs[] = {&ctx->xbuf, &ctx->cbuf, &ctx->part_sums, &ctx->part_counts, &ctx->part_inertia, &ctx->shift_part,
                     &ctx->counts_out, &ctx->state, &ctx->gather, &ctx->gather2, &ctx->labels, &ctx->dists, &ctx->wdists, &ctx->cum,
-                    &ctx->scratch, &ctx->tmpx, &ctx->tmpc, &ctx->idxbuf, &ctx->bsum, &ctx->weights, &ctx->flushbuf};
+                    &ctx->scratch, &ctx->tmpx, &ctx->tmpc, &ctx->idxbuf, &ctx->bsum, &ctx->weights, &ctx->flushbuf, &ctx->tca_bsplit, &ctx->tca_cn, &ctx->tca_cmax};
   for (DevBuf* b : bufs) b->release();
   for (cudaEvent_t e : ctx->iter_events) cudaEventDestroy(e);
   if (ctx->h_state) cudaFreeHost(ctx->h_state);

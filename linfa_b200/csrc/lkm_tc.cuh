@@ -1092,4 +1092,280 @@ __global__ void __launch_bounds__(256, 2) lloyd_tc256_kernel(const TcArgs a) {
   if (warp == 0) tc::tmem_dealloc(tmem, (uint32_t)a.tcols);
 }
 
+// =============================================================================================
+// Tensor-core ASSIGNMENT for wide rows / many clusters (f32, d = 32 * ka with ka in {1, 2, 4}, any k):
+// labels and exact min distances to global memory; the centroid update then runs as the
+// cluster-chunked MODE_UPDATE pass of lloyd_kernel.  Centroids are pre-split once per iteration
+// into TF32 hi / lo operand tiles (tc_prep_centroids_kernel) and streamed from L2 in chunks of 64;
+// the 128-row X tile stays resident as hi / lo (x = hi + lo exactly, lo is kept unmasked).
+// =============================================================================================
+constexpr int kAsgChunk = 64;
+
+struct TcAssignArgs {
+  const float* X;
+  unsigned long long n;
+  int k, d, ka, n_chunks;
+  const unsigned char* bsplit;  // [chunk][atom][hi 8 KB | lo 8 KB], rows in SW128 K-major order
+  const float* cn;              // n_chunks * 64 squared norms (+inf for padding)
+  const unsigned int* cmax_bits;
+  const float* C;               // k x d, for the exact winner distance and the exact fallback
+  uint32_t* labels;
+  float* dists;
+  LloydState* state;
+};
+
+// grid = n_chunks * ka CTAs of 64 threads: CTA (chunk, atom) writes one hi and one lo tile
+__global__ void __launch_bounds__(64) tc_prep_centroids_kernel(const float* __restrict__ C, int k, int d, int ka,
+                                                               unsigned char* __restrict__ bsplit, float* __restrict__ cn,
+                                                               unsigned int* __restrict__ cmax_bits) {
+  const int chunk = blockIdx.x / ka, atom = blockIdx.x % ka, r = threadIdx.x;
+  const int c = chunk * kAsgChunk + r;
+  unsigned char* hi = bsplit + ((size_t)chunk * ka + atom) * 16384;
+  unsigned char* lo = hi + 8192;
+  if (c < k) {
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(C + (size_t)c * d + atom * 32) + q);
+      float4 h, l;
+      tc::split_tf32(v.x, h.x, l.x); tc::split_tf32(v.y, h.y, l.y);
+      tc::split_tf32(v.z, h.z, l.z); tc::split_tf32(v.w, h.w, l.w);
+      const uint32_t o = tc::sw128_offset(r, q);
+      *reinterpret_cast<float4*>(hi + o) = h;
+      *reinterpret_cast<float4*>(lo + o) = l;
+    }
+  } else {
+    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const uint32_t o = tc::sw128_offset(r, q);
+      *reinterpret_cast<float4*>(hi + o) = z;
+      *reinterpret_cast<float4*>(lo + o) = z;
+    }
+  }
+  if (atom == 0) {
+    if (c < k) {
+      double nn = 0.0;
+      for (int j = 0; j < d; ++j) { const double v = (double)C[(size_t)c * d + j]; nn += v * v; }
+      const float nf = (float)nn;
+      cn[c] = nf;
+      atomicMax(cmax_bits, __float_as_uint(nf));  // a NaN norm wins the max and voids every certificate
+    } else {
+      cn[c] = INFINITY;
+    }
+  }
+}
+
+__host__ __device__ inline size_t tc_assign_smem_bytes(int ka) {
+  return (size_t)ka * 16384 * 2 /* A_hi, A_lo */ + (size_t)ka * 16384 /* B chunk */ + 256 /* cn chunk */ + 640 /* flags */ + 1024;
+}
+
+__global__ void __launch_bounds__(128) tc_assign_kernel(const TcAssignArgs a) {
+  if (a.state != nullptr && a.state->done) return;
+  extern __shared__ __align__(16) unsigned char smem_unaligned[];
+  unsigned char* smem = smem_unaligned + ((1024u - (tc::smem_u32(smem_unaligned) & 1023u)) & 1023u);
+  const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+  const int ka = a.ka, d = a.d, k = a.k;
+  unsigned char* a_hi = smem;
+  unsigned char* a_lo = a_hi + (size_t)ka * 16384;
+  unsigned char* bb = a_lo + (size_t)ka * 16384;   // [atom][hi 8 KB | lo 8 KB]
+  float* cnb = reinterpret_cast<float*>(bb + (size_t)ka * 16384);
+  uint32_t* flags = reinterpret_cast<uint32_t*>(cnb + kAsgChunk);
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ uint32_t tmem_slot;
+  __shared__ uint32_t n_flag;
+
+  if (warp == 0) tc::tmem_alloc(&tmem_slot, 64);
+  if (t == 0) { tc::mbar_init(&bar, 1); tc::fence_mbar_init(); n_flag = 0; }
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+  const float cmax2 = __uint_as_float(*a.cmax_bits);
+  const float cmax = sqrtf(cmax2) * 1.000001f;
+  const float eta = (3.f * (float)d + 12.f) * 2.3841858e-7f;
+  const float gamma = ((float)d + 2.f) * 5.9604645e-8f;
+  const float m_a0 = 2.3841858e-7f * cmax2;
+  const float m_a1 = (4.f * eta + 4.7683716e-7f) * cmax;
+  const float m_g2 = 2.f * gamma;
+  const uint32_t st_off = tc::sw128_offset((uint32_t)(t >> 3), (uint32_t)(t & 7));
+  const uint32_t row_off = (uint32_t)(t >> 3) * 1024u + (uint32_t)(t & 7) * 128u;
+  const uint32_t row_x = (uint32_t)(t & 7);
+  const uint32_t idesc = tc::idesc_tf32(128, kAsgChunk);
+  uint32_t parity = 0;
+  unsigned int my_fallbacks = 0;
+
+  const unsigned long long n_tiles = (a.n + 127) / 128;
+  for (unsigned long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const unsigned long long row0 = tile * 128;
+    const int rows = (int)min(128ull, a.n - row0);
+    // ---- stage the X tile as TF32 hi / lo atoms (x = hi + lo exactly) ----
+    for (int atom = 0; atom < ka; ++atom) {
+      const float* g = a.X + row0 * (unsigned long long)d + atom * 32 + (t & 7) * 4;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int row = (t >> 3) + 16 * i;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (row < rows) v = __ldg(reinterpret_cast<const float4*>(g + (size_t)row * d));
+        float4 h, l;
+        h.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u); l.x = v.x - h.x;
+        h.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u); l.y = v.y - h.y;
+        h.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u); l.z = v.z - h.z;
+        h.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u); l.w = v.w - h.w;
+        const uint32_t o = (uint32_t)atom * 16384u + st_off + 2048u * i;
+        *reinterpret_cast<float4*>(a_hi + o) = h;
+        *reinterpret_cast<float4*>(a_lo + o) = l;
+      }
+    }
+    float best0 = INFINITY, second0 = INFINITY, best1 = INFINITY, second1 = INFINITY;
+    int idx0 = 0, idx1 = 1;
+    for (int ch = 0; ch < a.n_chunks; ++ch) {
+      // ---- centroid chunk: ka atoms of (hi | lo) tiles + 64 squared norms, flat copy from L2 ----
+      const int4* src = reinterpret_cast<const int4*>(a.bsplit + (size_t)ch * ka * 16384);
+      for (int q = t; q < ka * 1024; q += 128) cp_async16_zfill(bb + (size_t)q * 16, src + q, true);
+      if (t < 16) cp_async16_zfill(cnb + t * 4, a.cn + (size_t)ch * kAsgChunk + t * 4, true);
+      cp_async_commit();
+      cp_async_wait_all();
+      tc::fence_async_smem();
+      tc::tc_fence_before();
+      __syncthreads();
+      if (t == 0) {
+        tc::tc_fence_after();
+        uint32_t accf = 0;
+        for (int pass = 0; pass < 3; ++pass) {
+          const uint32_t sa = tc::smem_u32(pass == 2 ? a_lo : a_hi);
+          const uint32_t sb = tc::smem_u32(bb) + (pass == 1 ? 8192u : 0u);
+          for (int atom = 0; atom < ka; ++atom) {
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {
+              tc::mma_tf32(tmem, tc::smem_desc_sw128(sa + atom * 16384 + ks * 32), tc::smem_desc_sw128(sb + atom * 16384 + ks * 32),
+                           idesc, accf);
+              accf = 1;
+            }
+          }
+        }
+        tc::mma_commit(&bar);
+      }
+      const bool ok = tc::mbar_wait(&bar, parity);
+      parity ^= 1u;
+      tc::tc_fence_after();
+      if (!ok && t == 0 && a.state) atomicAdd(&a.state->fallback_rows, 1ull << 40);
+      const int cbase = ch * kAsgChunk;
+#pragma unroll
+      for (int c0 = 0; c0 < kAsgChunk; c0 += 32) {
+        uint32_t r[32];
+        tc::tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, r);
+        tc::tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          const float4 cn4 = *reinterpret_cast<const float4*>(cnb + c0 + j);
+          const float w0 = fmaf(-2.f, __uint_as_float(r[j]), cn4.x);
+          const float w1 = fmaf(-2.f, __uint_as_float(r[j + 1]), cn4.y);
+          const float w2 = fmaf(-2.f, __uint_as_float(r[j + 2]), cn4.z);
+          const float w3 = fmaf(-2.f, __uint_as_float(r[j + 3]), cn4.w);
+          second0 = fminf(second0, fmaxf(w0, best0));
+          idx0 = (w0 < best0) ? (cbase + c0 + j) : idx0;
+          best0 = fminf(best0, w0);
+          second1 = fminf(second1, fmaxf(w1, best1));
+          idx1 = (w1 < best1) ? (cbase + c0 + j + 1) : idx1;
+          best1 = fminf(best1, w1);
+          second0 = fminf(second0, fmaxf(w2, best0));
+          idx0 = (w2 < best0) ? (cbase + c0 + j + 2) : idx0;
+          best0 = fminf(best0, w2);
+          second1 = fminf(second1, fmaxf(w3, best1));
+          idx1 = (w3 < best1) ? (cbase + c0 + j + 3) : idx1;
+          best1 = fminf(best1, w3);
+        }
+      }
+      tc::tc_fence_before();
+      __syncthreads();  // chunk buffer and accumulator are free again
+    }
+    float best, second;
+    int bidx;
+    if (best1 < best0 || (best1 == best0 && idx1 < idx0)) { best = best1; bidx = idx1; second = fminf(second1, best0); }
+    else { best = best0; bidx = idx0; second = fminf(second0, best1); }
+    // ---- margin from ||x||, exact winner distance (direct form, feature order) ----
+    float xx = 0.f;
+    for (int atom = 0; atom < ka; ++atom) {
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        const uint32_t o = (uint32_t)atom * 16384u + row_off + (((uint32_t)c ^ row_x) << 4);
+        const float4 h = *reinterpret_cast<const float4*>(a_hi + o);
+        const float4 l = *reinterpret_cast<const float4*>(a_lo + o);
+        const float x0 = h.x + l.x, x1 = h.y + l.y, x2 = h.z + l.z, x3 = h.w + l.w;
+        xx = fmaf(x0, x0, xx); xx = fmaf(x1, x1, xx); xx = fmaf(x2, x2, xx); xx = fmaf(x3, x3, xx);
+      }
+    }
+    const float xn = sqrtf(xx) * 1.000001f;
+    const float margin = 1.1f * (m_a0 + xn * m_a1 + m_g2 * (xn + cmax) * (xn + cmax));
+    const bool row_ok = t < rows;
+    const bool certified = (second - best) > margin;
+    if (row_ok) {
+      if (certified) {
+        const float* cw = a.C + (size_t)bidx * d;
+        float dacc = 0.f;
+        for (int atom = 0; atom < ka; ++atom) {
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            const uint32_t o = (uint32_t)atom * 16384u + row_off + (((uint32_t)c ^ row_x) << 4);
+            const float4 h = *reinterpret_cast<const float4*>(a_hi + o);
+            const float4 l = *reinterpret_cast<const float4*>(a_lo + o);
+            const float4 cv = __ldg(reinterpret_cast<const float4*>(cw + atom * 32 + 4 * c));
+            float df;
+            df = __fsub_rn(cv.x, h.x + l.x); dacc = __fadd_rn(dacc, __fmul_rn(df, df));
+            df = __fsub_rn(cv.y, h.y + l.y); dacc = __fadd_rn(dacc, __fmul_rn(df, df));
+            df = __fsub_rn(cv.z, h.z + l.z); dacc = __fadd_rn(dacc, __fmul_rn(df, df));
+            df = __fsub_rn(cv.w, h.w + l.w); dacc = __fadd_rn(dacc, __fmul_rn(df, df));
+          }
+        }
+        a.labels[row0 + t] = (uint32_t)bidx;
+        a.dists[row0 + t] = dacc;
+      } else {
+        const uint32_t p = atomicAdd(&n_flag, 1u);
+        flags[p] = (uint32_t)t;
+      }
+    }
+    __syncthreads();
+    // ---- uncertified rows: exact scan over all k centroids (from L2), one warp per row ----
+    const uint32_t nf = n_flag;
+    if (nf) {
+      for (uint32_t f = warp; f < nf; f += 4) {
+        const uint32_t row = flags[f];
+        const uint32_t ro = (row >> 3) * 1024u + (row & 7u) * 128u, rx = row & 7u;
+        float fb = INFINITY;
+        int fi = -1;
+        for (int c = lane; c < k; c += 32) {
+          const float* cw = a.C + (size_t)c * d;
+          float dacc = 0.f;
+          for (int atom = 0; atom < ka; ++atom) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              const uint32_t o = (uint32_t)atom * 16384u + ro + (((uint32_t)q ^ rx) << 4);
+              const float4 h = *reinterpret_cast<const float4*>(a_hi + o);
+              const float4 l = *reinterpret_cast<const float4*>(a_lo + o);
+              const float4 cv = __ldg(reinterpret_cast<const float4*>(cw + atom * 32 + 4 * q));
+              float df;
+              df = __fsub_rn(cv.x, h.x + l.x); dacc = __fadd_rn(dacc, __fmul_rn(df, df));
+              df = __fsub_rn(cv.y, h.y + l.y); dacc = __fadd_rn(dacc, __fmul_rn(df, df));
+              df = __fsub_rn(cv.z, h.z + l.z); dacc = __fadd_rn(dacc, __fmul_rn(df, df));
+              df = __fsub_rn(cv.w, h.w + l.w); dacc = __fadd_rn(dacc, __fmul_rn(df, df));
+            }
+          }
+          // lane 0 starts with centroid 0 (sticky NaN like the reference); the others only take v < best
+          if (c == 0) { fb = dacc; fi = 0; }
+          else if (dacc < fb) { fb = dacc; fi = c; }
+        }
+        combine_candidates<float>(32, fb, fi);
+        if (lane == 0) { a.labels[row0 + row] = (uint32_t)fi; a.dists[row0 + row] = fb; }
+      }
+      my_fallbacks += (t == 0) ? nf : 0u;
+    }
+    __syncthreads();
+    if (t == 0) n_flag = 0;
+  }
+  if (t == 0 && a.state && my_fallbacks) atomicAdd(&a.state->fallback_rows, (unsigned long long)my_fallbacks);
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tc::tmem_dealloc(tmem, 64);
+}
+
 }  // namespace lkm

@@ -473,3 +473,34 @@ def test_tc_path_is_reproducible(lb, ctx):
     b = ctx.lloyd_iters(init, 5, 0.0)
     assert a[3].assign_path == 2
     assert (a[0] == b[0]).all() and a[2] == b[2] and (a[1] == b[1]).all()
+
+
+# ---- tensor-core assignment for wide rows / many clusters (two-pass: tc_assign_kernel + update pass) ----
+TCA_CASES = [(6000, 128, 256, 16, 30.0), (5000, 64, 1024, 40, 30.0), (3000, 128, 300, 10, 1.0), (2500, 64, 700, 5, 0.5),
+             (1000, 128, 1024, 7, 30.0)]
+
+
+@pytest.mark.parametrize("n,d,k,k_true,spread", TCA_CASES)
+def test_tc_assign_path_matches_oracle(lb, ctx, oracle, n, d, k, k_true, spread):
+    dt = np.float32
+    X, _ = blobs(n, d, k_true, dt, seed=n + k, spread=spread)
+    g = np.random.default_rng(k)
+    init = X[g.choice(n, size=k, replace=k > n)].copy()
+    if k > n:
+        init += (g.standard_normal(init.shape) * 0.01).astype(dt)
+    ctx.set_data(X)
+    c, counts, inertia, st = ctx.lloyd_iters(init, 2, 0.0)
+    assert st.assign_path == 2 and st.n_iter == 2
+    cur = init
+    for it in range(2):
+        lab, dd = oracle.assign(X, cur)
+        nxt = oracle.compute_centroids(cur, X, lab, acc_f64=True)
+        if it == 1:
+            ref_counts = np.bincount(lab.astype(np.int64), minlength=k)
+            ref_inertia = dd.astype(np.float64).sum()
+        cur = nxt
+    scale = np.abs(cur).max()
+    np.testing.assert_allclose(c, cur, rtol=1e-5, atol=1e-5 * scale)
+    assert counts.tolist() == ref_counts.tolist()
+    np.testing.assert_allclose(inertia, ref_inertia, rtol=1e-5)
+    print(f"fallback rows over 2 iterations: {st.fallback_rows} of {2 * n}")
