@@ -104,6 +104,14 @@ struct lkm_ctx {
   // comm
   void* comm = nullptr;
   int rank = 0, world = 1;
+  // NVLink one-shot exchange: this rank's gather buffer [2 parities][world][p2p_cap doubles] followed by
+  // [2][world] flags, mapped into every peer through CUDA IPC
+  void* p2p_local = nullptr;
+  std::vector<void*> p2p_peer;
+  size_t p2p_cap = 0;
+  unsigned long long p2p_epoch = 0;
+  int p2p_enabled = 1;  // LKM_P2P=0 falls back to ncclAllGather
+  DevBuf publish_done;
   uint32_t launches = 0;
 };
 
@@ -276,6 +284,64 @@ static cudaError_t launch_finalize(const FinalizeArgs<F, S, CT>& a, cudaStream_t
   return cudaGetLastError();
 }
 
+static lkm_status comm_allgather_host(lkm_ctx* ctx, const void* src, size_t bytes, std::vector<unsigned char>& out);
+
+// (re)creates the IPC-shared gather buffers for partial vectors of up to L doubles.  Collective:
+// every rank calls it with the same L.  On any failure the run falls back to ncclAllGather.
+static lkm_status p2p_setup(lkm_ctx* ctx, size_t L) {
+  if (!ctx->p2p_enabled || ctx->world > 8) return LKM_OK;
+  if (ctx->p2p_local && L <= ctx->p2p_cap) return LKM_OK;
+  const int world = ctx->world;
+  // release the old mapping
+  for (int r = 0; r < (int)ctx->p2p_peer.size(); ++r)
+    if (r != ctx->rank && ctx->p2p_peer[r]) cudaIpcCloseMemHandle(ctx->p2p_peer[r]);
+  ctx->p2p_peer.clear();
+  if (ctx->p2p_local) { cudaFree(ctx->p2p_local); ctx->p2p_local = nullptr; }
+  const size_t cap = std::max<size_t>(L, 4096);
+  const size_t bytes = (2 * (size_t)world * cap + 2 * (size_t)world) * 8;
+  int ok = 1;
+  cudaIpcMemHandle_t mine;
+  std::memset(&mine, 0, sizeof(mine));
+  if (cudaMalloc(&ctx->p2p_local, bytes) != cudaSuccess) { ok = 0; ctx->p2p_local = nullptr; cudaGetLastError(); }
+  if (ok) {
+    cudaMemset(ctx->p2p_local, 0, bytes);
+    if (cudaIpcGetMemHandle(&mine, ctx->p2p_local) != cudaSuccess) { ok = 0; cudaGetLastError(); }
+  }
+  std::vector<unsigned char> all;
+  struct Rec { cudaIpcMemHandle_t h; int ok; int pad; } rec{mine, ok, 0};
+  CKS(comm_allgather_host(ctx, &rec, sizeof(rec), all));
+  bool all_ok = true;
+  for (int r = 0; r < world; ++r) { Rec q; std::memcpy(&q, all.data() + (size_t)r * sizeof(Rec), sizeof(Rec)); all_ok = all_ok && q.ok; }
+  int open_ok = 1;
+  if (all_ok) {
+    ctx->p2p_peer.assign(world, nullptr);
+    for (int r = 0; r < world; ++r) {
+      if (r == ctx->rank) { ctx->p2p_peer[r] = ctx->p2p_local; continue; }
+      Rec q;
+      std::memcpy(&q, all.data() + (size_t)r * sizeof(Rec), sizeof(Rec));
+      if (cudaIpcOpenMemHandle(&ctx->p2p_peer[r], q.h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { open_ok = 0; cudaGetLastError(); ctx->p2p_peer[r] = nullptr; }
+    }
+  }
+  // agree on the outcome so that every rank takes the same path
+  int mine_ok = (all_ok && open_ok) ? 1 : 0;
+  CKS(comm_allgather_host(ctx, &mine_ok, sizeof(int), all));
+  bool everyone = true;
+  for (int r = 0; r < world; ++r) { int v; std::memcpy(&v, all.data() + (size_t)r * 4, 4); everyone = everyone && v; }
+  if (!everyone) {
+    for (int r = 0; r < (int)ctx->p2p_peer.size(); ++r)
+      if (r != ctx->rank && ctx->p2p_peer[r]) cudaIpcCloseMemHandle(ctx->p2p_peer[r]);
+    ctx->p2p_peer.clear();
+    if (ctx->p2p_local) { cudaFree(ctx->p2p_local); ctx->p2p_local = nullptr; }
+    ctx->p2p_enabled = 0;
+    return LKM_OK;
+  }
+  ctx->p2p_cap = cap;
+  CK(ctx->publish_done.ensure(16));
+  CK(cudaMemsetAsync(ctx->publish_done.p, 0, 16, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return LKM_OK;
+}
+
 struct LloydOut {
   uint64_t n_iter = 0, fallback_rows = 0;
   double inertia = 0, shift = 0;
@@ -382,7 +448,11 @@ static lkm_status run_lloyd(lkm_ctx* ctx, F* dC2, uint64_t k, uint64_t max_iter,
   CK(ctx->counts_out.ensure(k * 8));
   CK(ctx->state.ensure(sizeof(LloydState)));
   const size_t L = kd + k + 1;
-  if (ctx->world > 1) CK(ctx->gather.ensure((size_t)ctx->world * L * 8));
+  if (ctx->world > 1) {
+    CK(ctx->gather.ensure((size_t)ctx->world * L * 8));
+    CKS(p2p_setup(ctx, L));
+  }
+  const bool use_p2p = ctx->world > 1 && ctx->p2p_enabled && ctx->p2p_local != nullptr && L <= ctx->p2p_cap;
   LloydState* dstate = ctx->state.as<LloydState>();
   CK(cudaMemsetAsync(dstate, 0, sizeof(LloydState), ctx->stream));
   const bool flush = ctx->flush_bytes > 0;
@@ -490,13 +560,36 @@ static lkm_status run_lloyd(lkm_ctx* ctx, F* dC2, uint64_t k, uint64_t max_iter,
         ra.sum_stride = kd; ra.cnt_stride = k; ra.inertia_stride = 1; ra.n_src = grid; ra.k = (int)k; ra.d = (int)d;
         ra.rank_out = ctx->gather.as<double>() + (size_t)ctx->rank * L;
         ra.state = dstate;
-        CK((launch_finalize<F, F, uint32_t, false>(ra, ctx->stream)));
-        CKN(g_nccl.AllGather(ctx->gather.as<double>() + (size_t)ctx->rank * L, ctx->gather.as<double>(), L, kNcclFloat64,
-                             ctx->comm, ctx->stream));
         FinalizeArgs<F, double, double> fa{};
-        fa.src_sums = ctx->gather.as<double>(); fa.src_counts = ctx->gather.as<double>() + kd;
-        fa.src_inertia = ctx->gather.as<double>() + kd + k;
-        fa.sum_stride = L; fa.cnt_stride = L; fa.inertia_stride = L; fa.n_src = ctx->world; fa.k = (int)k; fa.d = (int)d;
+        const double* gbase = ctx->gather.as<double>();
+        size_t gstride = L;
+        if (use_p2p) {
+          // one-shot exchange over NVLink: store this rank's partial into every peer's slot, raise flags
+          const unsigned long long epoch = ++ctx->p2p_epoch;
+          const size_t par = (size_t)(epoch & 1);
+          const size_t cap = ctx->p2p_cap, w = (size_t)ctx->world;
+          ra.n_peers = ctx->world;
+          ra.flag_value = epoch;
+          ra.publish_done = ctx->publish_done.as<unsigned int>();
+          for (int pr = 0; pr < ctx->world; ++pr) {
+            double* base = reinterpret_cast<double*>(ctx->p2p_peer[pr]);
+            ra.peer_out[pr] = base + (par * w + (size_t)ctx->rank) * cap;
+            ra.peer_flags[pr] = reinterpret_cast<unsigned long long*>(base + 2 * w * cap) + par * w + (size_t)ctx->rank;
+          }
+          double* mine = reinterpret_cast<double*>(ctx->p2p_local);
+          gbase = mine + par * w * cap;
+          gstride = cap;
+          fa.wait_flags = reinterpret_cast<const unsigned long long*>(mine + 2 * w * cap) + par * w;
+          fa.n_wait = ctx->world;
+          fa.flag_value = epoch;
+        }
+        CK((launch_finalize<F, F, uint32_t, false>(ra, ctx->stream)));
+        if (!use_p2p)
+          CKN(g_nccl.AllGather(ctx->gather.as<double>() + (size_t)ctx->rank * L, ctx->gather.as<double>(), L, kNcclFloat64,
+                               ctx->comm, ctx->stream));
+        fa.src_sums = gbase; fa.src_counts = gbase + kd;
+        fa.src_inertia = gbase + kd + k;
+        fa.sum_stride = gstride; fa.cnt_stride = gstride; fa.inertia_stride = gstride; fa.n_src = ctx->world; fa.k = (int)k; fa.d = (int)d;
         fa.C_old = Ccur; fa.C_new = Cnext; fa.counts_out = ctx->counts_out.as<double>();
         fa.shift_part = ctx->shift_part.as<double>(); fa.state = dstate; fa.tol = tol; fa.max_iter = max_iter;
         CK((launch_finalize<F, double, double, true>(fa, ctx->stream)));
@@ -514,6 +607,7 @@ static lkm_status run_lloyd(lkm_ctx* ctx, F* dC2, uint64_t k, uint64_t max_iter,
   CK(cudaEventElapsedTime(&out.ms, ctx->ev0, ctx->ev1));
   out.n_iter = ctx->h_state->n_iter;
   out.fallback_rows = ctx->h_state->fallback_rows;
+  if (out.fallback_rows & (3ull << 40)) return fail(ctx, LKM_ERR_CUDA, "device-side wait timed out (tensor-core barrier or NVLink exchange flag)");
   if (flush) {
     // per-iteration spans only (the flush writes sit between them)
     out.ms = 0;
@@ -1340,6 +1434,7 @@ LKM_EXPORT lkm_status lkm_create(lkm_ctx** out, int device) {
   cudaDeviceProp prop;
   if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return bail(LKM_ERR_CUDA);
   if (const char* v = std::getenv("LKM_TC_VARIANT")) ctx->tc_variant = std::atoi(v);
+  if (const char* v = std::getenv("LKM_P2P")) ctx->p2p_enabled = std::atoi(v);
   ctx->sm_count = prop.multiProcessorCount;
   ctx->smem_optin = prop.sharedMemPerBlockOptin;
   if (cudaMallocHost(&ctx->h_state, sizeof(LloydState)) != cudaSuccess) return bail(LKM_ERR_CUDA);
@@ -1352,10 +1447,13 @@ LKM_EXPORT lkm_status lkm_destroy(lkm_ctx* ctx) {
   if (!ctx) return LKM_OK;
   cudaSetDevice(ctx->device);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+  for (int r = 0; r < (int)ctx->p2p_peer.size(); ++r)
+    if (r != ctx->rank && ctx->p2p_peer[r]) cudaIpcCloseMemHandle(ctx->p2p_peer[r]);
+  if (ctx->p2p_local) cudaFree(ctx->p2p_local);
   if (ctx->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->comm);
   DevBuf* bufs[] = {&ctx->xbuf, &ctx->cbuf, &ctx->part_sums, &ctx->part_counts, &ctx->part_inertia, &ctx->shift_part,
                     &ctx->counts_out, &ctx->state, &ctx->gather, &ctx->gather2, &ctx->labels, &ctx->dists, &ctx->wdists, &ctx->cum,
-                    &ctx->scratch, &ctx->tmpx, &ctx->tmpc, &ctx->idxbuf, &ctx->bsum, &ctx->weights, &ctx->flushbuf, &ctx->tca_bsplit, &ctx->tca_cn, &ctx->tca_cmax};
+                    &ctx->scratch, &ctx->tmpx, &ctx->tmpc, &ctx->idxbuf, &ctx->bsum, &ctx->weights, &ctx->flushbuf, &ctx->tca_bsplit, &ctx->tca_cn, &ctx->tca_cmax, &ctx->publish_done};
   for (DevBuf* b : bufs) b->release();
   for (cudaEvent_t e : ctx->iter_events) cudaEventDestroy(e);
   if (ctx->h_state) cudaFreeHost(ctx->h_state);

@@ -465,6 +465,16 @@ template <typename F, typename S, typename CT> struct FinalizeArgs {
   int k, d;
   // reduce-only output (per-rank partial): [kd sums | k counts | 1 inertia] as f64
   double* rank_out;
+  // NVLink one-shot exchange (row-sharded runs): the partial is stored straight into every peer's
+  // gather slot for this rank (peer memory mapped through CUDA IPC), then a flag is raised there
+  double* peer_out[8];
+  unsigned long long* peer_flags[8];
+  int n_peers;
+  unsigned long long flag_value;
+  unsigned int* publish_done;   // CTA counter for the last-block-raises-flags pattern
+  // update side: wait until every rank's flag shows flag_value before reading the gathered partials
+  const unsigned long long* wait_flags;
+  int n_wait;
   // update outputs
   const F* C_old;
   F* C_new;
@@ -510,7 +520,7 @@ __device__ __forceinline__ double strided_sum(const S* __restrict__ src, size_t 
 
 template <typename F, typename S, typename CT, bool UPDATE>
 __global__ void __launch_bounds__(kFinThreads) finalize_kernel(const FinalizeArgs<F, S, CT> a) {
-  if (UPDATE && a.state->done) return;
+  if (a.state->done) return;
   __shared__ double sh[kFinGroups][kFinElems];
   __shared__ double shc[kFinGroups][kFinElems];
   __shared__ double red[kFinThreads];
@@ -518,6 +528,17 @@ __global__ void __launch_bounds__(kFinThreads) finalize_kernel(const FinalizeArg
   const int t = threadIdx.x, g = t / kFinElems, l = t % kFinElems;
   const int kd = a.k * a.d;
   const int e = blockIdx.x * kFinElems + l;
+  if (UPDATE && a.wait_flags != nullptr) {
+    // partials arrive over NVLink: one thread per rank polls that rank's flag (bounded)
+    if (t < a.n_wait) {
+      const volatile unsigned long long* f = a.wait_flags + t;
+      unsigned int spins = 0;
+      while (*f != a.flag_value && ++spins < (1u << 22)) {}
+      if (*f != a.flag_value) atomicOr(&a.state->fallback_rows, 1ull << 41);  // timeout marker, reported by the host
+    }
+    __syncthreads();
+    __threadfence();
+  }
   sh[g][l] = (e < kd) ? strided_sum<S>(a.src_sums, a.sum_stride, (size_t)e, g, a.n_src) : 0.0;
   // counts of the clusters this CTA's elements belong to
   const int c_lo = (blockIdx.x * kFinElems) / a.d;
@@ -530,7 +551,9 @@ __global__ void __launch_bounds__(kFinThreads) finalize_kernel(const FinalizeArg
     double cntv = 0.0;
 #pragma unroll
     for (int q = 0; q < kFinGroups; ++q) cntv += shc[q][l];
-    if (UPDATE) a.counts_out[c] = cntv; else a.rank_out[kd + c] = cntv;
+    if (UPDATE) a.counts_out[c] = cntv;
+    else if (a.n_peers > 0) { for (int p = 0; p < a.n_peers; ++p) a.peer_out[p][kd + c] = cntv; }
+    else a.rank_out[kd + c] = cntv;
   }
   double sq = 0.0;
   if (g == 0 && e < kd) {
@@ -538,7 +561,8 @@ __global__ void __launch_bounds__(kFinThreads) finalize_kernel(const FinalizeArg
 #pragma unroll
     for (int q = 0; q < kFinGroups; ++q) tot += sh[q][l];
     if (!UPDATE) {
-      a.rank_out[e] = tot;
+      if (a.n_peers > 0) { for (int p = 0; p < a.n_peers; ++p) a.peer_out[p][e] = tot; }
+      else a.rank_out[e] = tot;
     } else {
       const int ce = e / a.d - c_lo;
       double cntv = 0.0;
@@ -556,7 +580,25 @@ __global__ void __launch_bounds__(kFinThreads) finalize_kernel(const FinalizeArg
       double v = 0.0;
       for (int b = t; b < a.n_src; b += kFinThreads) v += a.src_inertia[(size_t)b * a.inertia_stride];
       const double tot = block_sum(v, red);
-      if (t == 0) a.rank_out[kd + a.k] = tot;
+      if (t == 0) {
+        if (a.n_peers > 0) { for (int p = 0; p < a.n_peers; ++p) a.peer_out[p][kd + a.k] = tot; }
+        else a.rank_out[kd + a.k] = tot;
+      }
+    }
+    if (a.n_peers > 0) {
+      // all of this CTA's peer stores are issued: fence system-wide, and the last CTA raises the flags
+      __threadfence_system();
+      __syncthreads();
+      if (t == 0) {
+        const unsigned int prev = atomicAdd(a.publish_done, 1u);
+        is_last = (prev == gridDim.x - 1);
+      }
+      __syncthreads();
+      if (is_last) {
+        __threadfence_system();
+        if (t < a.n_peers) *((volatile unsigned long long*)a.peer_flags[t]) = a.flag_value;
+        if (t == 0) *a.publish_done = 0u;
+      }
     }
     return;
   }
