@@ -205,6 +205,10 @@ lkm_status lkm_set_assign_path(lkm_ctx* ctx, int path);
  * between iterations (outside the timed spans) so that the observations are
  * read from HBM, not from L2.  0 (default) turns it off. */
 lkm_status lkm_set_l2_flush(lkm_ctx* ctx, uint64_t bytes);
+/* with lkm_set_l2_flush active: also time the assign/fused kernel on its own (lkm_stats.main_kernel_ms).
+ * The extra event between the fused kernel and the combine kernel defeats their programmatic
+ * dependent launch, so it is off by default and used only for the roofline figure. */
+lkm_status lkm_set_kernel_timing(lkm_ctx* ctx, int on);
 
 #ifdef __cplusplus
 }

@@ -93,6 +93,7 @@ struct lkm_ctx {
   int last_path = 0;
   int tc_variant = 128;  // LKM_TC_VARIANT=256 selects the 256-thread tensor-core kernel (measured slower: 95 vs 85 us)
   uint64_t flush_bytes = 0;
+  int kernel_timing = 0;
   DevBuf flushbuf;
   std::vector<cudaEvent_t> iter_events;
   // workspaces
@@ -176,6 +177,22 @@ template <typename F> static void tile_layout(uint64_t d, const void* X, Plan& p
 
 static size_t al16(size_t x) { return (x + 15) & ~(size_t)15; }
 
+// launch with programmatic stream serialization (see pdl_wait / pdl_launch_dependents)
+template <typename Kern, typename Arg>
+static cudaError_t launch_pdl(Kern kern, int grid, int block, size_t smem, cudaStream_t s, const Arg& arg, bool pdl) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3((unsigned)block);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, arg);
+}
+
 template <typename F, int D, int MODE>
 static cudaError_t launch_lloyd_t(const LloydArgs<F>& a, int grid, size_t smem, cudaStream_t s) {
   static size_t configured = 0;
@@ -184,8 +201,7 @@ static cudaError_t launch_lloyd_t(const LloydArgs<F>& a, int grid, size_t smem, 
     if (e != cudaSuccess) return e;
     configured = smem;
   }
-  lloyd_kernel<F, D, MODE><<<grid, kThreads, smem, s>>>(a);
-  return cudaGetLastError();
+  return launch_pdl(lloyd_kernel<F, D, MODE>, grid, kThreads, smem, s, a, MODE == MODE_FUSED);
 }
 template <typename F, int D, int MODE> static int occupancy_t(size_t smem) {
   int nb = 0;
@@ -280,8 +296,7 @@ static lkm_status run_assign(lkm_ctx* ctx, const F* dX, uint64_t n, uint64_t d, 
 template <typename F, typename S, typename CT, bool UPDATE>
 static cudaError_t launch_finalize(const FinalizeArgs<F, S, CT>& a, cudaStream_t s) {
   const int grid = (a.k * a.d + kFinElems - 1) / kFinElems;
-  finalize_kernel<F, S, CT, UPDATE><<<grid, kFinThreads, 0, s>>>(a);
-  return cudaGetLastError();
+  return launch_pdl(finalize_kernel<F, S, CT, UPDATE>, grid, kFinThreads, 0, s, a, true);
 }
 
 static lkm_status comm_allgather_host(lkm_ctx* ctx, const void* src, size_t bytes, std::vector<unsigned char>& out);
@@ -485,9 +500,8 @@ static lkm_status run_lloyd(lkm_ctx* ctx, F* dC2, uint64_t k, uint64_t max_iter,
           ta.X = dX; ta.n = n; ta.k = (int)k; ta.kp = tc_kp; ta.tcols = tc_cols; ta.C = Ccur;
           ta.part_sums = ctx->part_sums.as<float>(); ta.part_counts = ctx->part_counts.as<uint32_t>();
           ta.part_inertia = ctx->part_inertia.as<double>(); ta.state = dstate; ta.accumulate = 1;
-          if (tc_threads == 256) lloyd_tc256_kernel<<<tc_grid, 256, tc_smem, ctx->stream>>>(ta);
-          else lloyd_tc_kernel<<<tc_grid, 128, tc_smem, ctx->stream>>>(ta);
-          CK(cudaGetLastError());
+          if (tc_threads == 256) CK(launch_pdl(lloyd_tc256_kernel, tc_grid, 256, tc_smem, ctx->stream, ta, true));
+          else CK(launch_pdl(lloyd_tc_kernel, tc_grid, 128, tc_smem, ctx->stream, ta, true));
           ctx->launches++;
         }
       } else if (pf.fused) {
@@ -542,7 +556,7 @@ static lkm_status run_lloyd(lkm_ctx* ctx, F* dC2, uint64_t k, uint64_t max_iter,
           ctx->launches++;
         }
       }
-      if (flush) CK(cudaEventRecord(ctx->iter_events[3 * it + 1], ctx->stream));
+      if (flush && ctx->kernel_timing) CK(cudaEventRecord(ctx->iter_events[3 * it + 1], ctx->stream));
       // combine the per-CTA partials in fixed order, then the m_k-means update
       if (ctx->world == 1) {
         FinalizeArgs<F, F, uint32_t> fa{};
@@ -614,7 +628,7 @@ static lkm_status run_lloyd(lkm_ctx* ctx, F* dC2, uint64_t k, uint64_t max_iter,
     for (uint64_t it = 0; it < launched; ++it) {
       float a = 0, b = 0;
       CK(cudaEventElapsedTime(&a, ctx->iter_events[3 * it], ctx->iter_events[3 * it + 2]));
-      CK(cudaEventElapsedTime(&b, ctx->iter_events[3 * it], ctx->iter_events[3 * it + 1]));
+      if (ctx->kernel_timing) CK(cudaEventElapsedTime(&b, ctx->iter_events[3 * it], ctx->iter_events[3 * it + 1]));
       out.ms += a;
       out.main_ms += b;
     }
@@ -1481,6 +1495,12 @@ LKM_EXPORT lkm_status lkm_set_assign_path(lkm_ctx* ctx, int path) {
 LKM_EXPORT lkm_status lkm_set_l2_flush(lkm_ctx* ctx, uint64_t bytes) {
   if (!ctx) return LKM_ERR_INVALID_ARG;
   ctx->flush_bytes = bytes;
+  return LKM_OK;
+}
+
+LKM_EXPORT lkm_status lkm_set_kernel_timing(lkm_ctx* ctx, int on) {
+  if (!ctx) return LKM_ERR_INVALID_ARG;
+  ctx->kernel_timing = on ? 1 : 0;
   return LKM_OK;
 }
 

@@ -32,6 +32,13 @@ struct LloydState {
 
 enum LloydMode { MODE_ASSIGN = 0, MODE_FUSED = 1, MODE_UPDATE = 2 };
 
+// Programmatic dependent launch: a kernel launched with the stream-serialization attribute may be
+// scheduled while its predecessor drains; pdl_wait() blocks until the predecessor grid has completed
+// and its writes are visible, pdl_launch_dependents() lets the successor start its own launch early.
+// Both are no-ops for ordinary launches.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 constexpr int kThreads = 256;  // threads per CTA == rows per tile
 
 template <typename F> struct Rn;
@@ -259,6 +266,8 @@ __device__ __forceinline__ void load_tile(F* __restrict__ xs, const F* __restric
 
 template <typename F, int D, int MODE>
 __global__ void __launch_bounds__(kThreads) lloyd_kernel(const LloydArgs<F> a) {
+  pdl_launch_dependents();
+  pdl_wait();
   if (a.state != nullptr && a.state->done) return;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int d = (D > 0) ? D : a.d;
@@ -485,8 +494,8 @@ template <typename F, typename S, typename CT> struct FinalizeArgs {
   unsigned long long max_iter;
 };
 
-constexpr int kFinElems = 64;    // elements (of the k*d sums) per CTA
-constexpr int kFinGroups = 16;   // source groups per element; CTA = kFinElems * kFinGroups threads
+constexpr int kFinElems = 16;    // elements (of the k*d sums) per CTA
+constexpr int kFinGroups = 64;   // source groups per element; CTA = kFinElems * kFinGroups threads
 constexpr int kFinThreads = kFinElems * kFinGroups;
 
 __device__ __forceinline__ double block_sum(double v, double* red) {
@@ -520,6 +529,8 @@ __device__ __forceinline__ double strided_sum(const S* __restrict__ src, size_t 
 
 template <typename F, typename S, typename CT, bool UPDATE>
 __global__ void __launch_bounds__(kFinThreads) finalize_kernel(const FinalizeArgs<F, S, CT> a) {
+  pdl_launch_dependents();
+  pdl_wait();
   if (a.state->done) return;
   __shared__ double sh[kFinGroups][kFinElems];
   __shared__ double shc[kFinGroups][kFinElems];

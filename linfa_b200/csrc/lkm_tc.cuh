@@ -365,6 +365,8 @@ __host__ __device__ inline size_t tc_smem_bytes(int k, int kp, int accumulate) {
 }
 
 __global__ void __launch_bounds__(128, 2) lloyd_tc_kernel(const TcArgs a) {
+  pdl_launch_dependents();
+  pdl_wait();
   if (a.state != nullptr && a.state->done) return;
   extern __shared__ __align__(16) unsigned char smem_unaligned[];
   // keep the shared address space visible to the compiler: offset, do not re-cast
@@ -734,6 +736,8 @@ __host__ __device__ inline size_t tc256_smem_bytes(int k, int kp, int accumulate
 }
 
 __global__ void __launch_bounds__(256, 2) lloyd_tc256_kernel(const TcArgs a) {
+  pdl_launch_dependents();
+  pdl_wait();
   if (a.state != nullptr && a.state->done) return;
   extern __shared__ __align__(16) unsigned char smem_unaligned[];
   unsigned char* smem = smem_unaligned + ((1024u - (tc::smem_u32(smem_unaligned) & 1023u)) & 1023u);

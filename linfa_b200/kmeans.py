@@ -180,6 +180,9 @@ class Context:
     def set_l2_flush(self, nbytes):
         self.check(_ffi.lib.lkm_set_l2_flush(self.h, int(nbytes)))
 
+    def set_kernel_timing(self, on):
+        self.check(_ffi.lib.lkm_set_kernel_timing(self.h, int(bool(on))))
+
     def set_data(self, x):
         x = np.asarray(x)
         if x.ndim != 2:
