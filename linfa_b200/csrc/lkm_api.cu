@@ -384,20 +384,21 @@ static lkm_status run_lloyd(lkm_ctx* ctx, F* dC2, uint64_t k, uint64_t max_iter,
       tc_cols = 32;
       while (tc_cols < tc_kp) tc_cols *= 2;
       const bool v256 = ctx->tc_variant == 256;
-      tc_smem = v256 ? tc256_smem_bytes((int)k, tc_kp, 1) : tc_smem_bytes((int)k, tc_kp, 1);
+      const bool vws = ctx->tc_variant == 544 && tc_kp <= 64 && tcws_smem_bytes((int)k, tc_kp) <= ctx->smem_optin;
+      tc_smem = vws ? tcws_smem_bytes((int)k, tc_kp) : (v256 ? tc256_smem_bytes((int)k, tc_kp, 1) : tc_smem_bytes((int)k, tc_kp, 1));
       if (tc_smem <= ctx->smem_optin) {
-        const void* fn = v256 ? (const void*)lloyd_tc256_kernel : (const void*)lloyd_tc_kernel;
+        const void* fn = vws ? (const void*)lloyd_tcws_kernel : (v256 ? (const void*)lloyd_tc256_kernel : (const void*)lloyd_tc_kernel);
         CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem));
         CK(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
         // with the carve-out at its maximum, 228 KB per SM hold floor(228K / (dynamic + static + 1K reserved)) CTAs
         int occ = (int)((228 * 1024) / (tc_smem + 2048));
-        occ = std::min(occ, 2);                // register file: two CTAs per SM
+        occ = std::min(occ, vws ? 1 : 2);      // register file: two CTAs per SM (one for the 544-thread kernel)
         occ = std::min(occ, 512 / tc_cols);    // TMEM columns per SM
         if (occ >= 1) {
           const uint64_t n_tiles = (n + kTcRows - 1) / kTcRows;
           tc_grid = (int)std::min<uint64_t>(n_tiles, (uint64_t)ctx->sm_count * occ);
           use_tc = true;
-          tc_threads = v256 ? 256 : 128;
+          tc_threads = vws ? kWsThreads : (v256 ? 256 : 128);
         }
       }
     }
@@ -500,7 +501,8 @@ static lkm_status run_lloyd(lkm_ctx* ctx, F* dC2, uint64_t k, uint64_t max_iter,
           ta.X = dX; ta.n = n; ta.k = (int)k; ta.kp = tc_kp; ta.tcols = tc_cols; ta.C = Ccur;
           ta.part_sums = ctx->part_sums.as<float>(); ta.part_counts = ctx->part_counts.as<uint32_t>();
           ta.part_inertia = ctx->part_inertia.as<double>(); ta.state = dstate; ta.accumulate = 1;
-          if (tc_threads == 256) CK(launch_pdl(lloyd_tc256_kernel, tc_grid, 256, tc_smem, ctx->stream, ta, true));
+          if (tc_threads == kWsThreads) CK(launch_pdl(lloyd_tcws_kernel, tc_grid, kWsThreads, tc_smem, ctx->stream, ta, true));
+          else if (tc_threads == 256) CK(launch_pdl(lloyd_tc256_kernel, tc_grid, 256, tc_smem, ctx->stream, ta, true));
           else CK(launch_pdl(lloyd_tc_kernel, tc_grid, 128, tc_smem, ctx->stream, ta, true));
           ctx->launches++;
         }
