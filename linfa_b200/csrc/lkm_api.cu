@@ -22,6 +22,7 @@
 #include "lkm_kernels.cuh"
 #include "lkm_rand.hpp"
 #include "lkm_tc.cuh"
+#include "lkm_tc3.cuh"
 
 #define LKM_EXPORT extern "C" __attribute__((visibility("default")))
 
@@ -91,7 +92,11 @@ struct lkm_ctx {
   uint64_t row_offset = 0, n_global = 0;
   int force_path = -1;
   int last_path = 0;
-  int tc_variant = 128;  // LKM_TC_VARIANT=256 selects the 256-thread tensor-core kernel (measured slower: 95 vs 85 us)
+  // fused tcgen05 kernel for d = 32: 3 = TMA + three worker groups (k <= 64; larger k falls back to 128),
+  // 128 / 256 / 544 = the earlier generations (LKM_TC_VARIANT)
+  int tc_variant = 3;
+  uint64_t data_epoch = 1, xmax2_epoch = 0;  // resident-data version / version the cached max row norm belongs to
+  DevBuf xmax2;
   uint64_t flush_bytes = 0;
   int kernel_timing = 0;
   DevBuf flushbuf;
@@ -357,6 +362,45 @@ static lkm_status p2p_setup(lkm_ctx* ctx, size_t L) {
   return LKM_OK;
 }
 
+// ---- TMA descriptor of the resident f32 matrix (d = 32): 128-row x 128-byte boxes, SWIZZLE_128B ----
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static lkm_status make_row_tile_map(lkm_ctx* ctx, const float* dX, uint64_t n, CUtensorMap& map) {
+  static EncodeTiledFn encode = nullptr;
+  if (!encode) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    CK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+    if (!fn || qres != cudaDriverEntryPointSuccess) return fail(ctx, LKM_ERR_CUDA, "cuTensorMapEncodeTiled not available");
+    encode = reinterpret_cast<EncodeTiledFn>(fn);
+  }
+  const cuuint64_t dims[2] = {32, (cuuint64_t)n};
+  const cuuint64_t strides[1] = {128};
+  const cuuint32_t box[2] = {32, (cuuint32_t)kTcRows};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = encode(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(dX), dims, strides, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(ctx, LKM_ERR_CUDA, "cuTensorMapEncodeTiled failed");
+  return LKM_OK;
+}
+
+static cudaError_t launch_tc3(int kp, int grid, size_t smem, cudaStream_t s, const Tc3Args& arg, const CUtensorMap& map) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3((unsigned)kT3Threads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  if (kp == 32) return cudaLaunchKernelEx(&cfg, lloyd_tc3_kernel<32>, arg, map);
+  return cudaLaunchKernelEx(&cfg, lloyd_tc3_kernel<64>, arg, map);
+}
+
 struct LloydOut {
   uint64_t n_iter = 0, fallback_rows = 0;
   double inertia = 0, shift = 0;
@@ -377,14 +421,38 @@ static lkm_status run_lloyd(lkm_ctx* ctx, F* dC2, uint64_t k, uint64_t max_iter,
   bool use_tc = false;
   int tc_grid = 0, tc_kp = 0, tc_cols = 0, tc_threads = 128;
   size_t tc_smem = 0;
+  CUtensorMap tc3_map;
+  std::memset(&tc3_map, 0, sizeof(tc3_map));
   if constexpr (std::is_same<F, float>::value) {
     if ((ctx->force_path == -1 || ctx->force_path == 2) && d == 32 && k <= 256 && n >= 1 &&
         (reinterpret_cast<uintptr_t>(dX) & 15) == 0) {
       tc_kp = (int)((k + 31) / 32 * 32);
       tc_cols = 32;
       while (tc_cols < tc_kp) tc_cols *= 2;
+      const bool v3 = ctx->tc_variant == 3 && k <= 64 && n + kTcRows < (1ull << 31) &&
+                      tc3_smem_bytes((int)k, tc_kp) <= ctx->smem_optin;
       const bool v256 = ctx->tc_variant == 256;
       const bool vws = ctx->tc_variant == 544 && tc_kp <= 64 && tcws_smem_bytes((int)k, tc_kp) <= ctx->smem_optin;
+      if (v3) {
+        tc_smem = tc3_smem_bytes((int)k, tc_kp);
+        const void* fn = tc_kp == 32 ? (const void*)lloyd_tc3_kernel<32> : (const void*)lloyd_tc3_kernel<64>;
+        CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem));
+        CK(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
+        CKS(make_row_tile_map(ctx, dX, n, tc3_map));
+        // max row norm of the resident matrix (cached for owned data; external pointers are rescanned)
+        if (!ctx->own_X || ctx->xmax2_epoch != ctx->data_epoch) {
+          CK(ctx->xmax2.ensure(16));
+          CK(cudaMemsetAsync(ctx->xmax2.p, 0, 4, ctx->stream));
+          row_norm2_max_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(dX, n, ctx->xmax2.as<unsigned int>());
+          CK(cudaGetLastError());
+          ctx->launches++;
+          ctx->xmax2_epoch = ctx->data_epoch;
+        }
+        const uint64_t n_tiles = (n + kTcRows - 1) / kTcRows;
+        tc_grid = (int)std::min<uint64_t>(n_tiles, (uint64_t)ctx->sm_count);
+        use_tc = true;
+        tc_threads = kT3Threads;
+      } else {
       tc_smem = vws ? tcws_smem_bytes((int)k, tc_kp) : (v256 ? tc256_smem_bytes((int)k, tc_kp, 1) : tc_smem_bytes((int)k, tc_kp, 1));
       if (tc_smem <= ctx->smem_optin) {
         const void* fn = vws ? (const void*)lloyd_tcws_kernel : (v256 ? (const void*)lloyd_tc256_kernel : (const void*)lloyd_tc_kernel);
@@ -400,6 +468,7 @@ static lkm_status run_lloyd(lkm_ctx* ctx, F* dC2, uint64_t k, uint64_t max_iter,
           use_tc = true;
           tc_threads = vws ? kWsThreads : (v256 ? 256 : 128);
         }
+      }
       }
     }
     if (ctx->force_path == 2 && !use_tc) return fail(ctx, LKM_ERR_UNSUPPORTED, "tcgen05 path needs f32, d = 32, k <= 256");
@@ -501,7 +570,12 @@ static lkm_status run_lloyd(lkm_ctx* ctx, F* dC2, uint64_t k, uint64_t max_iter,
           ta.X = dX; ta.n = n; ta.k = (int)k; ta.kp = tc_kp; ta.tcols = tc_cols; ta.C = Ccur;
           ta.part_sums = ctx->part_sums.as<float>(); ta.part_counts = ctx->part_counts.as<uint32_t>();
           ta.part_inertia = ctx->part_inertia.as<double>(); ta.state = dstate; ta.accumulate = 1;
-          if (tc_threads == kWsThreads) CK(launch_pdl(lloyd_tcws_kernel, tc_grid, kWsThreads, tc_smem, ctx->stream, ta, true));
+          if (tc_threads == kT3Threads) {
+            Tc3Args t3{};
+            t3.X = dX; t3.n = n; t3.k = (int)k; t3.C = Ccur; t3.xmax2_bits = ctx->xmax2.as<unsigned int>();
+            t3.part_sums = ta.part_sums; t3.part_counts = ta.part_counts; t3.part_inertia = ta.part_inertia; t3.state = dstate;
+            CK(launch_tc3(tc_kp, tc_grid, tc_smem, ctx->stream, t3, tc3_map));
+          } else if (tc_threads == kWsThreads) CK(launch_pdl(lloyd_tcws_kernel, tc_grid, kWsThreads, tc_smem, ctx->stream, ta, true));
           else if (tc_threads == 256) CK(launch_pdl(lloyd_tc256_kernel, tc_grid, 256, tc_smem, ctx->stream, ta, true));
           else CK(launch_pdl(lloyd_tc_kernel, tc_grid, 128, tc_smem, ctx->stream, ta, true));
           ctx->launches++;
@@ -1312,6 +1386,7 @@ static lkm_status set_data_impl(lkm_ctx* ctx, const F* x, uint64_t n, uint64_t d
   CK(cudaSetDevice(ctx->device));
   CKS(upload<F>(ctx, ctx->xbuf, x, n, d, row_stride));
   ctx->X = ctx->xbuf.p; ctx->own_X = true; ctx->n = n; ctx->d = d; ctx->elem = (int)sizeof(F);
+  ctx->data_epoch++;
   if (ctx->world == 1) { ctx->row_offset = 0; ctx->n_global = n; }
   return LKM_OK;
 }
@@ -1331,6 +1406,7 @@ static lkm_status gen_blobs_impl(lkm_ctx* ctx, uint64_t n, uint64_t d, uint64_t 
   }
   CK(cudaStreamSynchronize(ctx->stream));
   ctx->X = ctx->xbuf.p; ctx->own_X = true; ctx->n = n; ctx->d = d; ctx->elem = (int)sizeof(F);
+  ctx->data_epoch++;
   ctx->row_offset = row_offset; ctx->n_global = n_global ? n_global : n;
   return LKM_OK;
 }
@@ -1538,6 +1614,7 @@ LKM_EXPORT lkm_status lkm_set_shard(lkm_ctx* ctx, uint64_t row_offset, uint64_t 
   LKM_EXPORT lkm_status lkm_set_data_device_##SFX(lkm_ctx* ctx, const void* x_device, uint64_t n, uint64_t d) {        \
     if (!ctx || (!x_device && n) || d == 0) return LKM_ERR_INVALID_ARG;                                                \
     ctx->X = const_cast<void*>(x_device); ctx->own_X = false; ctx->n = n; ctx->d = d; ctx->elem = (int)sizeof(F);      \
+    ctx->data_epoch++;                                                                                                 \
     if (ctx->world == 1) { ctx->row_offset = 0; ctx->n_global = n; }                                                   \
     return LKM_OK;                                                                                                     \
   }                                                                                                                    \
