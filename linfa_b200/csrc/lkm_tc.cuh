@@ -20,6 +20,7 @@ __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier
 // bounded wait: returns false if the phase did not complete within `spins` polls
 __device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity, uint32_t spins = 1u << 22) {
   const uint32_t addr = smem_u32(bar);
+#pragma unroll 1
   for (uint32_t i = 0; i < spins; ++i) {
     uint32_t ok;
     asm volatile(

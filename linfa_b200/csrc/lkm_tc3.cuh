@@ -119,10 +119,14 @@ __global__ void __launch_bounds__(kT3Threads, 1) lloyd_tc3_kernel(const Tc3Args 
   pdl_launch_dependents();
   extern __shared__ __align__(16) unsigned char smem_unaligned[];
   unsigned char* smem = smem_unaligned + ((1024u - (tc::smem_u32(smem_unaligned) & 1023u)) & 1023u);
-  const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
-  const int w = t >> 7;          // worker group
+  const int t = threadIdx.x, lane = t & 31;
+  const int warp = __shfl_sync(0xffffffffu, t >> 5, 0);   // warp-uniform by construction: lets ptxas use uniform registers
+  const int w = warp >> 2;       // worker group
   const int wt = t & 127;        // thread within the group = row of the tile in E
   const int wwarp = warp & 3;    // TMEM lane quadrant
+  // the one thread of the group that issues TMA / MMA / token arrivals: lane 0 of warp w, so that the
+  // three groups' issuers sit on three different schedulers
+  const bool issuer = (wwarp == w) && (lane == 0);
   const int k = a.k;
   unsigned char* raw = smem;                                   // [group][2][16 KB]
   unsigned char* alo = raw + (size_t)kT3Groups * 2 * 16384;    // [group][16 KB]
@@ -164,7 +168,7 @@ __global__ void __launch_bounds__(kT3Threads, 1) lloyd_tc3_kernel(const Tc3Args 
   __syncthreads();
   // The observations do not depend on the previous kernel: request the first two tiles of every
   // group before waiting for it.
-  if (wt == 0) {
+  if (issuer) {
     for (int b = 0; b < 2; ++b)
       if ((unsigned long long)b < my_cnt) {
         tc::mbar_expect_tx(&bar_full[w][b], 16384u);
@@ -252,11 +256,21 @@ __global__ void __launch_bounds__(kT3Threads, 1) lloyd_tc3_kernel(const Tc3Args 
   const uint32_t acc_off_o = (uint32_t)(sub + 4) * 128u + ((((uint32_t)feat >> 2) ^ (uint32_t)(sub + 4)) << 4) + ((uint32_t)feat & 3u) * 4u;
   float* my_acc = acc + (size_t)sub * (k + 1) * 32 + feat;
   double inert = 0.0;
+  float inert_f = 0.f;   // per-tile partials, flushed into the f64 sum every 8 tiles
   unsigned int my_fallbacks = 0;
+  // operand descriptors of this group (start address in the low 14 bits, 16-byte units)
+  constexpr uint32_t idesc = tc::idesc_tf32(128, (uint32_t)KP);
+  const uint64_t desc_raw = tc::smem_desc_sw128(tc::smem_u32(my_raw));
+  const uint64_t desc_alo = tc::smem_desc_sw128(tc::smem_u32(my_alo));
+  const uint64_t desc_bhi = tc::smem_desc_sw128(tc::smem_u32(b_hi));
+  const uint64_t desc_blo = tc::smem_desc_sw128(tc::smem_u32(b_lo));
+  const uint64_t desc_bias = tc::smem_desc_sw128(tc::smem_u32(b_bias));
+  const uint64_t desc_ones = tc::smem_desc_sw128_alias(tc::smem_u32(ones));
+  const uint32_t dcol = tmem + (uint32_t)w * 64u;
 
   if (done) {
     // nothing to do, but the requested tiles must land before the CTA may exit
-    if (wt == 0)
+    if (issuer)
       for (int b = 0; b < 2; ++b)
         if ((unsigned long long)b < my_cnt) tc::mbar_wait_or_trap(&bar_full[w][b], 0);
   } else {
@@ -268,37 +282,33 @@ __global__ void __launch_bounds__(kT3Threads, 1) lloyd_tc3_kernel(const Tc3Args 
       unsigned char* rw = my_raw + (size_t)b * 16384;
       tc::mbar_wait_or_trap(&bar_full[w][b], ph);
       // ---- S: A_lo = x - trunc_tf32(x), chunk by chunk at the same (swizzled) position ----
+      {
+        float4 v[8];
 #pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        const uint32_t o = (uint32_t)wt * 16u + 2048u * q;
-        const float4 v = *reinterpret_cast<const float4*>(rw + o);
-        float4 l;
-        l.x = v.x - tc::trunc_tf32(v.x); l.y = v.y - tc::trunc_tf32(v.y);
-        l.z = v.z - tc::trunc_tf32(v.z); l.w = v.w - tc::trunc_tf32(v.w);
-        *reinterpret_cast<float4*>(my_alo + o) = l;
+        for (int q = 0; q < 8; ++q) v[q] = *reinterpret_cast<const float4*>(rw + (uint32_t)wt * 16u + 2048u * q);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          float4 l;
+          l.x = v[q].x - tc::trunc_tf32(v[q].x); l.y = v[q].y - tc::trunc_tf32(v[q].y);
+          l.z = v[q].z - tc::trunc_tf32(v[q].z); l.w = v[q].w - tc::trunc_tf32(v[q].w);
+          *reinterpret_cast<float4*>(my_alo + (uint32_t)wt * 16u + 2048u * q) = l;
+        }
       }
       tc::fence_async_smem();
       tc::tc_fence_before();
       tc::group_sync(bar_id);
       // ---- M ----
-      if (wt == 0) {
+      if (issuer) {
         tc::tc_fence_after();
-        constexpr uint32_t idesc = tc::idesc_tf32(128, (uint32_t)KP);
-        const uint32_t sa_hi = tc::smem_u32(rw), sa_lo = tc::smem_u32(my_alo);
-        const uint32_t sb_hi = tc::smem_u32(b_hi), sb_lo = tc::smem_u32(b_lo);
-        const uint32_t dcol = tmem + (uint32_t)w * 64u;
-        uint32_t accf = 0;
+        const uint64_t da_hi = desc_raw + (uint64_t)(b ? 1024u : 0u);   // 16 KB further, in 16-byte units
+        // x_lo.c_hi, x_hi.c_lo, x_hi.c_hi; one K-step of 8 TF32 = 32 bytes = 2 descriptor units
 #pragma unroll
-        for (int pass = 0; pass < 3; ++pass) {       // x_lo.c_hi, x_hi.c_lo, x_hi.c_hi
-          const uint32_t sa = pass == 0 ? sa_lo : sa_hi;
-          const uint32_t sb = pass == 1 ? sb_lo : sb_hi;
+        for (int ks = 0; ks < 4; ++ks) tc::mma_tf32(dcol, desc_alo + 2u * ks, desc_bhi + 2u * ks, idesc, ks ? 1u : 0u);
 #pragma unroll
-          for (int ks = 0; ks < 4; ++ks) {
-            tc::mma_tf32(dcol, tc::smem_desc_sw128(sa + ks * 32), tc::smem_desc_sw128(sb + ks * 32), idesc, accf);
-            accf = 1;
-          }
-        }
-        tc::mma_tf32(dcol, tc::smem_desc_sw128_alias(tc::smem_u32(ones)), tc::smem_desc_sw128(tc::smem_u32(b_bias)), idesc, 1u);
+        for (int ks = 0; ks < 4; ++ks) tc::mma_tf32(dcol, da_hi + 2u * ks, desc_blo + 2u * ks, idesc, 1u);
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) tc::mma_tf32(dcol, da_hi + 2u * ks, desc_bhi + 2u * ks, idesc, 1u);
+        tc::mma_tf32(dcol, desc_ones, desc_bias, idesc, 1u);
         tc::mma_commit(&bar_mma[w]);
       }
       tc::mbar_wait_or_trap(&bar_mma[w], (uint32_t)i & 1u);
@@ -447,10 +457,11 @@ __global__ void __launch_bounds__(kT3Threads, 1) lloyd_tc3_kernel(const Tc3Args 
           }
           my_acc[cur_lab * 32] += cur;
         }
-        inert += (double)(e0 + e1);
+        inert_f += e0 + e1;
+        if ((i & 7) == 7) { inert += (double)inert_f; inert_f = 0.f; }
       }
       tc::group_sync(bar_id);
-      if (wt == 0) {
+      if (issuer) {
         tc::mbar_arrive(&bar_tok[(w + 1) % kT3Groups]);
         if (i + 2 < my_cnt) {
           tc::mbar_expect_tx(&bar_full[w][b], 16384u);
@@ -473,7 +484,7 @@ __global__ void __launch_bounds__(kT3Threads, 1) lloyd_tc3_kernel(const Tc3Args 
     uint32_t* pc = a.part_counts + (size_t)blockIdx.x * k;
     for (int e = t; e < k; e += kT3Threads) pc[e] = cnt[e];
     double* red = reinterpret_cast<double*>(raw);
-    red[t] = inert;
+    red[t] = inert + (double)inert_f;
     __syncthreads();
     if (t < 128) red[t] += red[t + 128] + red[t + 256];
     __syncthreads();
