@@ -41,7 +41,7 @@ def needs_build():
 def build(force=False, verbose=False):
     if not force and not needs_build():
         return OUT
-    cmd = [nvcc()] + NVCC_FLAGS + ["-o", OUT] + SRC + ["-ldl"]
+    cmd = [nvcc()] + NVCC_FLAGS + os.environ.get("LKM_EXTRA_NVCC", "").split() + ["-o", OUT] + SRC + ["-ldl"]
     if verbose:
         print(" ".join(cmd))
     res = subprocess.run(cmd, capture_output=True, text=True)

@@ -23,6 +23,7 @@
 #include "lkm_rand.hpp"
 #include "lkm_tc.cuh"
 #include "lkm_tc3.cuh"
+#include "lkm_tc4.cuh"
 
 #define LKM_EXPORT extern "C" __attribute__((visibility("default")))
 
@@ -92,11 +93,11 @@ struct lkm_ctx {
   uint64_t row_offset = 0, n_global = 0;
   int force_path = -1;
   int last_path = 0;
-  // fused tcgen05 kernel for d = 32: 3 = TMA + three worker groups (k <= 64; larger k falls back to 128),
-  // 128 / 256 / 544 = the earlier generations (LKM_TC_VARIANT)
-  int tc_variant = 3;
+  // fused tcgen05 kernel for d = 32: 4 = TMA + warp-specialised pipeline, 3 = TMA + three worker groups
+  // (both k <= 64; larger k falls back to 128), 128 / 256 / 544 = the earlier generations (LKM_TC_VARIANT)
+  int tc_variant = 4;
   uint64_t data_epoch = 1, xmax2_epoch = 0;  // resident-data version / version the cached max row norm belongs to
-  DevBuf xmax2;
+  DevBuf xmax2, t4prof;
   uint64_t flush_bytes = 0;
   int kernel_timing = 0;
   DevBuf flushbuf;
@@ -401,6 +402,21 @@ static cudaError_t launch_tc3(int kp, int grid, size_t smem, cudaStream_t s, con
   return cudaLaunchKernelEx(&cfg, lloyd_tc3_kernel<64>, arg, map);
 }
 
+static cudaError_t launch_tc4(int kp, int grid, size_t smem, cudaStream_t s, const Tc4Args& arg, const CUtensorMap& map) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3((unsigned)kT4Threads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  if (kp == 32) return cudaLaunchKernelEx(&cfg, lloyd_tc4_kernel<32>, arg, map);
+  return cudaLaunchKernelEx(&cfg, lloyd_tc4_kernel<64>, arg, map);
+}
+
 struct LloydOut {
   uint64_t n_iter = 0, fallback_rows = 0;
   double inertia = 0, shift = 0;
@@ -421,6 +437,7 @@ static lkm_status run_lloyd(lkm_ctx* ctx, F* dC2, uint64_t k, uint64_t max_iter,
   bool use_tc = false;
   int tc_grid = 0, tc_kp = 0, tc_cols = 0, tc_threads = 128;
   size_t tc_smem = 0;
+  int tc4_nstages = 0;
   CUtensorMap tc3_map;
   std::memset(&tc3_map, 0, sizeof(tc3_map));
   if constexpr (std::is_same<F, float>::value) {
@@ -429,13 +446,17 @@ static lkm_status run_lloyd(lkm_ctx* ctx, F* dC2, uint64_t k, uint64_t max_iter,
       tc_kp = (int)((k + 31) / 32 * 32);
       tc_cols = 32;
       while (tc_cols < tc_kp) tc_cols *= 2;
-      const bool v3 = ctx->tc_variant == 3 && k <= 64 && n + kTcRows < (1ull << 31) &&
-                      tc3_smem_bytes((int)k, tc_kp) <= ctx->smem_optin;
+      const bool v4 = ctx->tc_variant == 4 && k <= 64 && n + kTcRows < (1ull << 31) &&
+                      tc4_smem_bytes((int)k, tc_kp, 3) <= ctx->smem_optin - 1024;
+      const bool v3 = v4 || (ctx->tc_variant == 3 && k <= 64 && n + kTcRows < (1ull << 31) &&
+                             tc3_smem_bytes((int)k, tc_kp) <= ctx->smem_optin);
       const bool v256 = ctx->tc_variant == 256;
       const bool vws = ctx->tc_variant == 544 && tc_kp <= 64 && tcws_smem_bytes((int)k, tc_kp) <= ctx->smem_optin;
       if (v3) {
-        tc_smem = tc3_smem_bytes((int)k, tc_kp);
-        const void* fn = tc_kp == 32 ? (const void*)lloyd_tc3_kernel<32> : (const void*)lloyd_tc3_kernel<64>;
+        if (v4) tc4_nstages = tc4_stages((int)k, tc_kp, ctx->smem_optin - 1024);
+        tc_smem = v4 ? tc4_smem_bytes((int)k, tc_kp, tc4_nstages) : tc3_smem_bytes((int)k, tc_kp);
+        const void* fn = v4 ? (tc_kp == 32 ? (const void*)lloyd_tc4_kernel<32> : (const void*)lloyd_tc4_kernel<64>)
+                            : (tc_kp == 32 ? (const void*)lloyd_tc3_kernel<32> : (const void*)lloyd_tc3_kernel<64>);
         CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem));
         CK(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
         CKS(make_row_tile_map(ctx, dX, n, tc3_map));
@@ -451,7 +472,7 @@ static lkm_status run_lloyd(lkm_ctx* ctx, F* dC2, uint64_t k, uint64_t max_iter,
         const uint64_t n_tiles = (n + kTcRows - 1) / kTcRows;
         tc_grid = (int)std::min<uint64_t>(n_tiles, (uint64_t)ctx->sm_count);
         use_tc = true;
-        tc_threads = kT3Threads;
+        tc_threads = v4 ? kT4Threads : kT3Threads;
       } else {
       tc_smem = vws ? tcws_smem_bytes((int)k, tc_kp) : (v256 ? tc256_smem_bytes((int)k, tc_kp, 1) : tc_smem_bytes((int)k, tc_kp, 1));
       if (tc_smem <= ctx->smem_optin) {
@@ -570,7 +591,16 @@ static lkm_status run_lloyd(lkm_ctx* ctx, F* dC2, uint64_t k, uint64_t max_iter,
           ta.X = dX; ta.n = n; ta.k = (int)k; ta.kp = tc_kp; ta.tcols = tc_cols; ta.C = Ccur;
           ta.part_sums = ctx->part_sums.as<float>(); ta.part_counts = ctx->part_counts.as<uint32_t>();
           ta.part_inertia = ctx->part_inertia.as<double>(); ta.state = dstate; ta.accumulate = 1;
-          if (tc_threads == kT3Threads) {
+          if (tc_threads == kT4Threads) {
+            Tc4Args t4{};
+            t4.X = dX; t4.n = n; t4.k = (int)k; t4.stages = tc4_nstages; t4.C = Ccur; t4.xmax2_bits = ctx->xmax2.as<unsigned int>();
+#ifdef LKM_T4_PROF
+            CK(ctx->t4prof.ensure(48 * 8));
+            t4.prof = ctx->t4prof.as<long long>();
+#endif
+            t4.part_sums = ta.part_sums; t4.part_counts = ta.part_counts; t4.part_inertia = ta.part_inertia; t4.state = dstate;
+            CK(launch_tc4(tc_kp, tc_grid, tc_smem, ctx->stream, t4, tc3_map));
+          } else if (tc_threads == kT3Threads) {
             Tc3Args t3{};
             t3.X = dX; t3.n = n; t3.k = (int)k; t3.C = Ccur; t3.xmax2_bits = ctx->xmax2.as<unsigned int>();
             t3.part_sums = ta.part_sums; t3.part_counts = ta.part_counts; t3.part_inertia = ta.part_inertia; t3.state = dstate;
@@ -709,6 +739,16 @@ static lkm_status run_lloyd(lkm_ctx* ctx, F* dC2, uint64_t k, uint64_t max_iter,
       out.main_ms += b;
     }
   }
+#ifdef LKM_T4_PROF
+  if (use_tc && tc_threads == kT4Threads) {
+    long long hp[48];
+    CK(cudaMemcpy(hp, ctx->t4prof.p, sizeof(hp), cudaMemcpyDeviceToHost));
+    const char* names[6] = {"P", "M", "S", "E0", "E1", "U"};
+    for (int r = 0; r < 6; ++r)
+      std::fprintf(stderr, "t4prof %-2s wait0 %9lld wait1 %9lld s2 %9lld s3 %9lld s4 %9lld total %9lld\n", names[r], hp[r * 8], hp[r * 8 + 1],
+                   hp[r * 8 + 2], hp[r * 8 + 3], hp[r * 8 + 4], hp[r * 8 + 7]);
+  }
+#endif
   out.inertia = ctx->h_state->inertia;
   out.shift = ctx->h_state->shift;
   out.final_buf = (int)(out.n_iter & 1);
@@ -1762,5 +1802,54 @@ LKM_EXPORT int lkm_debug_umma_raw(lkm_ctx* ctx, const void* a_img, int a_bytes, 
   CK(cudaMemcpyAsync(dump_out, ctx->dists.p, (size_t)128 * ncols * 4, cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
   if (hst != 0) return fail(ctx, LKM_ERR_CUDA, "umma raw probe: timeout or no report");
+  return LKM_OK;
+}
+
+LKM_EXPORT int lkm_debug_mma_bench(lkm_ctx* ctx, int n_cols, int reps, int per_batch, int mode, int grid, long long* cycles_out) {
+  if (!ctx || !cycles_out || n_cols % 16 || n_cols < 16 || n_cols > 256 || grid < 1 || grid > 1024) return LKM_ERR_INVALID_ARG;
+  CK(cudaSetDevice(ctx->device));
+  CK(ctx->scratch.ensure((size_t)grid * 8));
+  const size_t smem = 32768 + (size_t)n_cols * 128 + 2048;
+  CK(cudaFuncSetAttribute(mma_bench_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  if (mode == 32) {   // TMEM load throughput: n_cols = warps, per_batch unused
+    CK(cudaMemsetAsync(ctx->scratch.p, 0, (size_t)grid * 8, ctx->stream));
+    CK(ctx->dists.ensure((size_t)grid * 64));
+    ldtm_bench_kernel<<<grid, 256, 0, ctx->stream>>>(n_cols / 16, reps, ctx->dists.as<long long>());
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(cycles_out, ctx->dists.p, (size_t)std::min(grid, 1) * 64, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return LKM_OK;
+  }
+  if (mode >= 16 && mode < 20) {
+    auto kern = mode == 16 ? mma_bench2_kernel<0> : mode == 17 ? mma_bench2_kernel<1> : mode == 18 ? mma_bench2_kernel<2> : mma_bench2_kernel<3>;
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, 128, smem, ctx->stream>>>(n_cols, reps, ctx->scratch.as<long long>());
+  } else
+  mma_bench_kernel<<<grid, 128, smem, ctx->stream>>>(n_cols, reps, per_batch, mode, ctx->scratch.as<long long>());
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(cycles_out, ctx->scratch.p, (size_t)grid * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return LKM_OK;
+}
+
+LKM_EXPORT int lkm_debug_tc_ts(lkm_ctx* ctx, const float* x, const float* c, float* s_out) {
+  if (!ctx || !x || !c || !s_out) return LKM_ERR_INVALID_ARG;
+  CK(cudaSetDevice(ctx->device));
+  CK(ctx->tmpx.ensure(128 * 32 * 4));
+  CK(ctx->tmpc.ensure(64 * 32 * 4));
+  CK(ctx->dists.ensure(128 * 64 * 4));
+  CK(ctx->scratch.ensure(64));
+  CK(cudaMemcpyAsync(ctx->tmpx.p, x, 128 * 32 * 4, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->tmpc.p, c, 64 * 32 * 4, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemsetAsync(ctx->scratch.p, 0xff, 4, ctx->stream));
+  const size_t smem = 64 * 128 + 2048;
+  tc_ts_probe_kernel<64><<<1, 128, smem, ctx->stream>>>(ctx->tmpx.as<float>(), ctx->tmpc.as<float>(), ctx->dists.as<float>(),
+                                                       ctx->scratch.as<int>());
+  CK(cudaGetLastError());
+  int hst = -1;
+  CK(cudaMemcpyAsync(&hst, ctx->scratch.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(s_out, ctx->dists.p, 128 * 64 * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  if (hst != 0) return fail(ctx, LKM_ERR_CUDA, "TS probe: timeout");
   return LKM_OK;
 }

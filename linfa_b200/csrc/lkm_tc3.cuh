@@ -50,9 +50,24 @@ __device__ __forceinline__ uint64_t smem_desc_sw128_alias(uint32_t saddr) {
   d |= (uint64_t)2 << 61;
   return d;
 }
-// bounded wait; a barrier that never completes is a protocol bug: kill the kernel instead of hanging the GPU
+// bounded wait; a barrier that never completes is a protocol bug: kill the kernel instead of hanging the GPU.
+// The suspend-time hint lets the hardware park the warp until the phase completes instead of re-polling every
+// few cycles (polling warps steal issue slots and mbarrier bandwidth from the working roles).
 __device__ __forceinline__ void mbar_wait_or_trap(uint64_t* bar, uint32_t parity) {
-  if (!mbar_wait(bar, parity, 1u << 24)) __trap();
+  const uint32_t addr = smem_u32(bar);
+#pragma unroll 1
+  for (uint32_t i = 0; i < (1u << 18); ++i) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(addr), "r"(parity), "r"(10000u)
+        : "memory");
+    if (ok) return;
+  }
+  __trap();
 }
 __device__ __forceinline__ float trunc_tf32(float x) { return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
 }  // namespace tc

@@ -1,0 +1,12 @@
+import ctypes as C, os, sys
+import numpy as np
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import linfa_b200 as lb
+from linfa_b200 import _ffi
+ctx = lb.Context.default()
+bf = _ffi.lib.lkm_debug_mma_bench
+bf.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_longlong)]
+for nw in (1, 2, 4, 8):
+    out = np.zeros(8, dtype=np.int64)
+    assert bf(ctx.h, nw * 16, 100, 0, 32, 1, out.ctypes.data_as(C.POINTER(C.c_longlong))) == 0, ctx.error()
+    print(f"{nw} warps: cycles per 4 KB tcgen05.ld (per warp):", (out[:nw] / 800).round(1))
