@@ -29,6 +29,7 @@ constexpr int kT4Threads = 18 * 32;
 constexpr int kT4TmemCols = 512;   // D 2 x 64 | A_hi 2 x 32 | A_lo 2 x 32 | ones 8
 constexpr uint32_t kT4ColAhi = 128, kT4ColAlo = 192, kT4ColOnes = 256;
 constexpr int kT4MaxStages = 12;
+constexpr int kNbLab = 2, kNbLfree = 4, kNbAlo = 6, kNbTfree = 8;   // named barrier ids (+ parity); 1 = U-internal
 constexpr int kT4Subsets = 8;      // U role: thread = (row subset of 8, feature pair)
 
 __host__ __device__ inline size_t tc4_smem_bytes(int k, int kp, int stages) {
@@ -95,6 +96,10 @@ __device__ __forceinline__ unsigned long long f2_pack(float lo, float hi) {
 }
 __device__ __forceinline__ float f2_lo(unsigned long long v) { return __uint_as_float((uint32_t)v); }
 __device__ __forceinline__ float f2_hi(unsigned long long v) { return __uint_as_float((uint32_t)(v >> 32)); }
+// Named-barrier hand-offs between roles: the consumer blocks in the barrier unit (no polling, no issue
+// slots), the producer only arrives.  `threads` = producer threads + consumer threads.
+__device__ __forceinline__ void nb_sync(int id, int threads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
+__device__ __forceinline__ void nb_arrive(int id, int threads) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
 // one arrival per warp: every lane has finished its part (memory ordered by __syncwarp)
 __device__ __forceinline__ void warp_arrive(uint64_t* bar, int lane) {
   __syncwarp();
@@ -353,14 +358,14 @@ __global__ void __launch_bounds__(kT4Threads, 1) lloyd_tc4_kernel(const Tc4Args 
       };
       for (unsigned long long j = 0; j < my_tiles; j += 2) {
         const uint32_t u = (uint32_t)(j >> 1);
-        T4WAIT(0, &bar_alo[0], u & 1u);
-        if (u > 0) T4WAIT(1, &bar_tfree[0], (u - 1u) & 1u);   // accumulator drained by E
+        tc::nb_sync(kNbAlo + 0, 160);
+        if (u > 0) tc::nb_sync(kNbTfree + 0, 160);   // accumulator drained by E
         tc::tc_fence_after();
         issue(0u);
         tc::mma_commit_elect(&bar_mma[0]);
         if (j + 1 < my_tiles) {
-          T4WAIT(0, &bar_alo[1], u & 1u);
-          if (u > 0) T4WAIT(1, &bar_tfree[1], (u - 1u) & 1u);
+          tc::nb_sync(kNbAlo + 1, 160);
+          if (u > 0) tc::nb_sync(kNbTfree + 1, 160);
           tc::tc_fence_after();
           issue(1u);
           tc::mma_commit_elect(&bar_mma[1]);
@@ -399,7 +404,7 @@ __global__ void __launch_bounds__(kT4Threads, 1) lloyd_tc4_kernel(const Tc4Args 
       tc::tmem_st32(lane_base + kT4ColAlo + p2 * 32u, xr);
       tc::tmem_st_wait();
       tc::tc_fence_before();
-      tc::warp_arrive(&bar_alo[p2], lane);
+      tc::nb_arrive(kNbAlo + (int)p2, 160);
       if (++s == R) { s = 0; full_ph ^= 1u; }
     }
   } else if (warp < 12) {
@@ -437,7 +442,7 @@ __global__ void __launch_bounds__(kT4Threads, 1) lloyd_tc4_kernel(const Tc4Args 
       T4MARK(te0);
       T4ADD(3, te_a, te0);
       tc::tc_fence_before();
-      tc::warp_arrive(&bar_tfree[g], lane);    // the accumulator may be overwritten by tile j + 2
+      tc::nb_arrive(kNbTfree + g, 160);        // the accumulator may be overwritten by tile j + 2
       uint32_t m0 = q[0], m1 = q[1], m2 = q[2], m3 = q[3];
 #pragma unroll
       for (int c = 4; c + 7 < KP; c += 8) {
@@ -474,7 +479,7 @@ __global__ void __launch_bounds__(kT4Threads, 1) lloyd_tc4_kernel(const Tc4Args 
       const bool uni = __all_sync(0xffffffffu, lab == lab0) && lab0 < 0xFFFFFFFEu;
       T4MARK(te1);
       T4ADD(2, te0, te1);
-      if (u > 0) T4WAIT(1, &bar_lfree[g], (u - 1u) & 1u);   // U is done with this label slot
+      if (u > 0) tc::nb_sync(kNbLfree + g, 256);   // U is done with this label slot
       T4MARK(te2);
       if (uni) {
         if (lane == 0) atomicAdd(&cnt[lab0], 32u);
@@ -487,7 +492,7 @@ __global__ void __launch_bounds__(kT4Threads, 1) lloyd_tc4_kernel(const Tc4Args 
         const uint32_t p = atomicAdd(&n_flag[g], 1u);
         flags[p] = (uint32_t)row;
       }
-      tc::warp_arrive(&bar_lab[g], lane);
+      tc::nb_arrive(kNbLab + g, 256);
       T4MARK(te3);
       T4ADD(4, te2, te3);
     }
@@ -510,7 +515,7 @@ __global__ void __launch_bounds__(kT4Threads, 1) lloyd_tc4_kernel(const Tc4Args 
       const unsigned char* rw = raw + (size_t)s * 16384;
       uint32_t* labs2 = labs2_all + g * kTcRows;
       const uint32_t* flags = flags_all + g * kTcRows;
-      T4WAIT(0, &bar_lab[g], u & 1u);
+      tc::nb_sync(kNbLab + g, 256);
       T4MARK(tu_a);
       const uint32_t nf = n_flag[g];
       const uint4 wu = *reinterpret_cast<const uint4*>(wuni_all + g * 4);
@@ -604,11 +609,8 @@ __global__ void __launch_bounds__(kT4Threads, 1) lloyd_tc4_kernel(const Tc4Args 
       inert_f += tc::f2_lo(e2) + tc::f2_hi(e2);
       if ((j & 7) == 7) { inert_g += inert_f; inert_f = 0.f; }
       if ((j & 63) == 63) { inert_h += inert_g; inert_g = 0.f; }
-      __syncwarp();
-      if (lane == 0) {
-        tc::mbar_arrive(&bar_free[s]);      // the raw stage may be refilled
-        tc::mbar_arrive(&bar_lfree[g]);     // the label slot may be rewritten
-      }
+      tc::warp_arrive(&bar_free[s], lane);   // the raw stage may be refilled
+      tc::nb_arrive(kNbLfree + g, 256);      // the label slot may be rewritten
       T4MARK(tu2);
       T4ADD(3, tu1, tu2);
       if (++s == R) s = 0;
