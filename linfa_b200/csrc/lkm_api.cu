@@ -594,8 +594,8 @@ static lkm_status run_lloyd(lkm_ctx* ctx, F* dC2, uint64_t k, uint64_t max_iter,
           if (tc_threads == kT4Threads) {
             Tc4Args t4{};
             t4.X = dX; t4.n = n; t4.k = (int)k; t4.stages = tc4_nstages; t4.C = Ccur; t4.xmax2_bits = ctx->xmax2.as<unsigned int>();
-#ifdef LKM_T4_PROF
-            CK(ctx->t4prof.ensure(48 * 8));
+#if defined(LKM_T4_PROF) || defined(LKM_T4_TRACE)
+            CK(ctx->t4prof.ensure((64 + 40 * 16) * 8));
             t4.prof = ctx->t4prof.as<long long>();
 #endif
             t4.part_sums = ta.part_sums; t4.part_counts = ta.part_counts; t4.part_inertia = ta.part_inertia; t4.state = dstate;
@@ -739,6 +739,20 @@ static lkm_status run_lloyd(lkm_ctx* ctx, F* dC2, uint64_t k, uint64_t max_iter,
       out.main_ms += b;
     }
   }
+#ifdef LKM_T4_TRACE
+  if (use_tc && tc_threads == kT4Threads) {
+    static long long ht[64 + 40 * 16];
+    CK(cudaMemcpy(ht, ctx->t4prof.p, sizeof(ht), cudaMemcpyDeviceToHost));
+    std::fprintf(stderr, "t4kern init %lld pdl %lld staged %lld sync %lld ready %lld loopend(t0) %lld allend %lld reduced %lld dealloc %lld\n",
+                 ht[0], ht[1], ht[2], ht[3], ht[4], ht[5], ht[6], ht[7], ht[8]);
+    std::fprintf(stderr, "t4trace tile  tma  Sbeg Send  Mbeg Mend  Ewake Eld Ecomp Epub  Ubeg Uacc Uend  Malo Mtfree\n");
+    for (int j = 0; j < 40; ++j) {
+      std::fprintf(stderr, "t4trace %3d", j);
+      for (int e = 0; e < 14; ++e) std::fprintf(stderr, " %6lld", ht[64 + j * 16 + e]);
+      std::fprintf(stderr, "\n");
+    }
+  }
+#endif
 #ifdef LKM_T4_PROF
   if (use_tc && tc_threads == kT4Threads) {
     long long hp[48];

@@ -71,6 +71,12 @@ struct Tc4Args {
 #else
 #define T4WAIT(slot, bar, ph) tc::mbar_wait_or_trap(bar, ph)
 #endif
+// LKM_T4_TRACE: CTA 0 stamps event `ev` of tile `j` (cycles since the roles started) into a.prof[64 + j * 16 + ev]
+#ifdef LKM_T4_TRACE
+#define T4TRACE(j, ev) do { if (blockIdx.x == 0 && lane == 0 && (j) < 40 && a.prof) a.prof[64 + (j) * 16 + (ev)] = clock64() - trace_t0; } while (0)
+#else
+#define T4TRACE(j, ev)
+#endif
 #ifdef LKM_T4_PROF
 #define T4MARK(var) const long long var = clock64()
 #define T4ADD(slot, a, b) prof_acc[slot] += (b) - (a)
@@ -89,6 +95,23 @@ __device__ __forceinline__ unsigned long long f2_add(unsigned long long a, unsig
 __device__ __forceinline__ unsigned long long f2_fma(unsigned long long a, unsigned long long b, unsigned long long c) {
   unsigned long long d;
   asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+// (d0, d1) = (a0, a1) + (b0, b1) as one FADD2 on explicit 32-bit halves (keeps ptxas from doing 64-bit integer
+// arithmetic on the packed value)
+__device__ __forceinline__ void f2_add_parts(uint32_t a0, uint32_t a1, uint32_t b0, uint32_t b1, uint32_t& d0, uint32_t& d1) {
+  asm("{\n\t.reg .b64 a, b, d;\n\t"
+      "mov.b64 a, {%2, %3};\n\t"
+      "mov.b64 b, {%4, %5};\n\t"
+      "add.rn.f32x2 d, a, b;\n\t"
+      "mov.b64 {%0, %1}, d;\n\t}"
+      : "=r"(d0), "=r"(d1)
+      : "r"(a0), "r"(a1), "r"(b0), "r"(b1));
+}
+// -(x with the 13 low mantissa bits cleared): (x & mask) ^ sign in one LOP3
+__device__ __forceinline__ uint32_t neg_trunc_tf32_bits(uint32_t x, uint32_t mask, uint32_t sign) {
+  uint32_t d;
+  asm("lop3.b32 %0, %1, %2, %3, 0x6A;" : "=r"(d) : "r"(x), "r"(mask), "r"(sign));
   return d;
 }
 __device__ __forceinline__ unsigned long long f2_pack(float lo, float hi) {
@@ -190,6 +213,12 @@ __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.
 template <int KP>
 __global__ void __launch_bounds__(kT4Threads, 1) lloyd_tc4_kernel(const Tc4Args a, const __grid_constant__ CUtensorMap tmap) {
   static_assert(KP == 32 || KP == 64, "score columns");
+#ifdef LKM_T4_TRACE
+  const long long k_t0 = clock64();
+#define T4K(ev) do { if (blockIdx.x == 0 && threadIdx.x == 0 && a.prof) a.prof[ev] = clock64() - k_t0; } while (0)
+#else
+#define T4K(ev)
+#endif
   pdl_launch_dependents();
   extern __shared__ __align__(16) unsigned char smem_unaligned[];
   unsigned char* smem = smem_unaligned + ((1024u - (tc::smem_u32(smem_unaligned) & 1023u)) & 1023u);
@@ -204,8 +233,8 @@ __global__ void __launch_bounds__(kT4Threads, 1) lloyd_tc4_kernel(const Tc4Args 
   float* rawc = reinterpret_cast<float*>(b_bias + KP * 128);
   float* acc = rawc + (size_t)k * kTcCStride;
   uint32_t* cnt = reinterpret_cast<uint32_t*>(acc + (size_t)kT4Subsets * (k + 1) * 32);
-  double* nn_s = reinterpret_cast<double*>(cnt + ((k + 3) & ~3));
-  uint32_t* labs2_all = reinterpret_cast<uint32_t*>(nn_s + KP);  // [slot][128], index (row & 3) * 32 + (row >> 2)
+  float* nn_s = reinterpret_cast<float*>(cnt + ((k + 3) & ~3));   // [KP] (the f64-sized slot of the layout is kept)
+  uint32_t* labs2_all = reinterpret_cast<uint32_t*>(nn_s + 2 * KP);  // [slot][128], index (row & 3) * 32 + (row >> 2)
   uint32_t* flags_all = labs2_all + 2 * kTcRows;                // [slot][128]
   uint32_t* wuni_all = flags_all + 2 * kTcRows;                 // [slot][4]
   __shared__ __align__(8) uint64_t bar_full[kT4MaxStages], bar_free[kT4MaxStages], bar_alo[2], bar_mma[2], bar_tfree[2], bar_lab[2], bar_lfree[2];
@@ -221,7 +250,7 @@ __global__ void __launch_bounds__(kT4Threads, 1) lloyd_tc4_kernel(const Tc4Args 
   if (t == 32) {
     for (int s = 0; s < kT4MaxStages; ++s) {
       tc::mbar_init(&bar_full[s], 1);
-      tc::mbar_init(&bar_free[s], 4);
+      tc::mbar_init(&bar_free[s], 2);
     }
     for (int s = 0; s < 2; ++s) {
       tc::mbar_init(&bar_alo[s], 4);
@@ -235,18 +264,27 @@ __global__ void __launch_bounds__(kT4Threads, 1) lloyd_tc4_kernel(const Tc4Args 
     cmax_bits = 0;
   }
   __syncthreads();
+  T4K(0);
   // The observations do not depend on the previous kernel: fill the ring before waiting for it.
+  // Only three tiles up front: a full ring (16 KB x stages x 148 CTAs) ahead of the centroid loads would delay
+  // those by the whole burst; the P role requests the rest as soon as it starts.
   unsigned long long produced = 0;
   if (warp == 16 && lane == 0) {
-    for (; produced < my_tiles && produced < (unsigned long long)R; ++produced) {
+    for (; produced < my_tiles && produced < 3ull; ++produced) {
       tc::mbar_expect_tx(&bar_full[produced], 16384u);
       tc::tma_load_2d(raw + (size_t)produced * 16384, &tmap, 0, (int)(tile_of(produced) * kTcRows), &bar_full[produced]);
     }
   }
+  // everything that does not depend on the previous kernel's centroids happens before the dependency wait
+  for (int e = t; e < kT4Subsets * (k + 1) * 32; e += kT4Threads) acc[e] = 0.f;
+  for (int e = t; e < k; e += kT4Threads) cnt[e] = 0u;
+  for (int e = t; e < KP * 8; e += kT4Threads) reinterpret_cast<float4*>(b_bias)[e] = make_float4(0.f, 0.f, 0.f, 0.f);
   pdl_wait();
+  T4K(1);
   const bool done = a.state != nullptr && a.state->done;
+  const float xmax2 = __uint_as_float(__ldg(a.xmax2_bits));   // issued together with the centroid loads
 
-  // ---- centroids: TF32 hi/lo operand tiles, padded raw copy, squared norms (8 threads per row) ----
+  // ---- centroids: TF32 hi/lo operand tiles, padded raw copy, squared norms (8 threads per row, f32) ----
   for (int item = t; item < KP * 8; item += kT4Threads) {
     const int r = item >> 3, c = item & 7;
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -257,24 +295,22 @@ __global__ void __launch_bounds__(kT4Threads, 1) lloyd_tc4_kernel(const Tc4Args 
     const uint32_t o = tc::sw128_offset(r, c);
     *reinterpret_cast<float4*>(b_hi + o) = h;
     *reinterpret_cast<float4*>(b_lo + o) = l;
-    *reinterpret_cast<float4*>(b_bias + o) = make_float4(0.f, 0.f, 0.f, 0.f);
     if (r < k) *reinterpret_cast<float4*>(rawc + r * kTcCStride + 4 * c) = v;
-    double nn = (double)v.x * v.x + (double)v.y * v.y + (double)v.z * v.z + (double)v.w * v.w;
+    float nn = fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, v.w * v.w)));
     nn += __shfl_xor_sync(0xffffffffu, nn, 1);
     nn += __shfl_xor_sync(0xffffffffu, nn, 2);
     nn += __shfl_xor_sync(0xffffffffu, nn, 4);
     if (c == 0) {
-      nn_s[r] = nn;
-      if (r < k) atomicMax(&cmax_bits, __float_as_uint(__double2float_ru(nn)));  // a NaN norm wins and voids every certificate
+      nn_s[r] = nn;   // |nn - |c|^2| <= (d + 1) 2^-24 |c|^2 whatever the summation order
+      if (r < k) atomicMax(&cmax_bits, __float_as_uint(nn));  // a NaN norm wins and voids every certificate
     }
   }
-  for (int e = t; e < kT4Subsets * (k + 1) * 32; e += kT4Threads) acc[e] = 0.f;
-  for (int e = t; e < k; e += kT4Threads) cnt[e] = 0u;
+  T4K(2);
   __syncthreads();
+  T4K(3);
   // ---- window, bias, margin (identical in every thread; see lkm_tc3.cuh) ----
-  const float cmax2 = __uint_as_float(cmax_bits);
+  const float cmax2 = __uint_as_float(cmax_bits) * 1.00001f;
   const float cmax = sqrtf(cmax2) * 1.000001f;
-  const float xmax2 = __uint_as_float(__ldg(a.xmax2_bits));
   const float xmax = sqrtf(xmax2) * 1.000001f;
   const float Rb = 1.01f * (xmax * cmax + 0.5f * cmax2) + 1e-30f;   // |x.c - |c|^2/2| <= Rb
   const bool params_ok = Rb < 1e30f;  // false for NaN / Inf: every row then takes the exact scan
@@ -287,21 +323,25 @@ __global__ void __launch_bounds__(kT4Threads, 1) lloyd_tc4_kernel(const Tc4Args 
   const float gamma = (32.f + 2.f) * 5.9604645e-8f;       // (d + 2) * 2^-24
   const float m_w = 1.1f * (2.3841858e-7f * cmax2 + xmax * (4.f * eta + 4.7683716e-7f) * cmax +
                             2.f * gamma * (xmax + cmax) * (xmax + cmax));
-  const float m_v = 0.5f * m_w + 6.f * 1.1920929e-7f * (K0 + Rb);
+  // v is half a squared distance.  On each of the two candidates: the bias K-step rounds at most 3 ulp(v), the
+  // f32 bias K0 - nn/2 is off by at most 2^-24 K0 + (d + 1) 2^-25 |c|^2 (rounding of the norm and of the subtraction)
+  const float m_v = 0.5f * m_w + 7.f * 1.1920929e-7f * (K0 + Rb) + 33.f * 5.9604645e-8f * cmax2;
   if (t < KP) {
-    const double b = (t < k) ? ((double)K0 - 0.5 * nn_s[t]) : (double)two_lo;
-    const float h = tc::trunc_tf32((float)b);
-    const double r1 = b - (double)h;
-    const float l = tc::trunc_tf32((float)r1);
-    const float l2 = tc::trunc_tf32((float)(r1 - (double)l));
+    // bias row t: K0 - |c|^2/2 as three TF32 pieces that add up to the f32 value exactly, K-step 0 of the tile
+    const float b = (t < k) ? (K0 - 0.5f * nn_s[t]) : two_lo;
+    const float h = tc::trunc_tf32(b);
+    const float l = b - h;
+    const float l1 = tc::trunc_tf32(l);
+    const float l2 = l - l1;
     float* p = reinterpret_cast<float*>(b_bias + tc::sw128_offset(t, 0));
-    p[0] = h; p[1] = l; p[2] = l2;
+    p[0] = h; p[1] = l1; p[2] = l2;
   }
   tc::fence_async_smem();
   tc::tc_fence_before();
   __syncthreads();
   tc::tc_fence_after();
   const uint32_t tmem = tmem_slot;
+  T4K(4);
   if (warp < 4) {
     // the constant A operand of the bias K-step: every lane holds [1, 1, 1, 0, 0, 0, 0, 0]
     const uint32_t one = __float_as_uint(1.f);
@@ -313,6 +353,9 @@ __global__ void __launch_bounds__(kT4Threads, 1) lloyd_tc4_kernel(const Tc4Args 
     tc::tc_fence_before();
   }
   double inert = 0.0;            // U role
+#ifdef LKM_T4_TRACE
+  const long long trace_t0 = clock64();
+#endif
 #ifdef LKM_T4_PROF
   long long prof_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   const long long prof_t0 = clock64();
@@ -328,10 +371,11 @@ __global__ void __launch_bounds__(kT4Threads, 1) lloyd_tc4_kernel(const Tc4Args 
     if (lane == 0) {
       for (unsigned long long j = produced; j < my_tiles; ++j) {
         const int s = (int)(j % (unsigned long long)R);
-        const uint32_t use = (uint32_t)(j / (unsigned long long)R);       // >= 1 here
-        T4WAIT(0, &bar_free[s], (use - 1u) & 1u);
+        const uint32_t use = (uint32_t)(j / (unsigned long long)R);
+        if (use > 0) T4WAIT(0, &bar_free[s], (use - 1u) & 1u);
         tc::mbar_expect_tx(&bar_full[s], 16384u);
         tc::tma_load_2d(raw + (size_t)s * 16384, &tmap, 0, (int)(tile_of(j) * kTcRows), &bar_full[s]);
+        T4TRACE(j, 0);
       }
     }
   } else if (warp == 17) {
@@ -359,16 +403,24 @@ __global__ void __launch_bounds__(kT4Threads, 1) lloyd_tc4_kernel(const Tc4Args 
       for (unsigned long long j = 0; j < my_tiles; j += 2) {
         const uint32_t u = (uint32_t)(j >> 1);
         tc::nb_sync(kNbAlo + 0, 160);
+        T4TRACE(j, 12);
         if (u > 0) tc::nb_sync(kNbTfree + 0, 160);   // accumulator drained by E
+        T4TRACE(j, 13);
         tc::tc_fence_after();
+        T4TRACE(j, 3);
         issue(0u);
         tc::mma_commit_elect(&bar_mma[0]);
+        T4TRACE(j, 4);
         if (j + 1 < my_tiles) {
           tc::nb_sync(kNbAlo + 1, 160);
+          T4TRACE(j + 1, 12);
           if (u > 0) tc::nb_sync(kNbTfree + 1, 160);
+          T4TRACE(j + 1, 13);
           tc::tc_fence_after();
+          T4TRACE(j + 1, 3);
           issue(1u);
           tc::mma_commit_elect(&bar_mma[1]);
+          T4TRACE(j + 1, 4);
         }
       }
     }
@@ -379,10 +431,13 @@ __global__ void __launch_bounds__(kT4Threads, 1) lloyd_tc4_kernel(const Tc4Args 
     const uint32_t row_off = (uint32_t)(t >> 3) * 1024u + (uint32_t)(t & 7) * 128u;   // row t of a SW128 tile
     const uint32_t row_x = (uint32_t)(t & 7);
     const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);
+    uint32_t tf32_mask = 0xFFFFE000u, sign_bit = 0x80000000u;
+    asm volatile("" : "+r"(tf32_mask), "+r"(sign_bit));   // keep both in registers: one LOP3 per element
     for (unsigned long long j = 0; j < my_tiles; ++j) {
       const uint32_t p2 = (uint32_t)j & 1u, u = (uint32_t)(j >> 1);
       const unsigned char* rw = raw + (size_t)s * 16384;
       T4WAIT(0, &bar_full[s], full_ph);
+      if (warp == 0) T4TRACE(j, 1);
       uint32_t xr[32];
 #pragma unroll
       for (int c = 0; c < 8; ++c) {
@@ -395,16 +450,15 @@ __global__ void __launch_bounds__(kT4Threads, 1) lloyd_tc4_kernel(const Tc4Args 
 #pragma unroll
       for (int q = 0; q < 32; q += 2) {
         // x_lo = x + (-trunc_tf32(x)), two features per FADD2
-        const uint32_t n0 = (xr[q] & 0xFFFFE000u) ^ 0x80000000u, n1 = (xr[q + 1] & 0xFFFFE000u) ^ 0x80000000u;
-        const unsigned long long lo2 = tc::f2_add((unsigned long long)xr[q] | ((unsigned long long)xr[q + 1] << 32),
-                                                  (unsigned long long)n0 | ((unsigned long long)n1 << 32));
-        xr[q] = (uint32_t)lo2;
-        xr[q + 1] = (uint32_t)(lo2 >> 32);
+        const uint32_t n0 = tc::neg_trunc_tf32_bits(xr[q], tf32_mask, sign_bit);
+        const uint32_t n1 = tc::neg_trunc_tf32_bits(xr[q + 1], tf32_mask, sign_bit);
+        tc::f2_add_parts(xr[q], xr[q + 1], n0, n1, xr[q], xr[q + 1]);
       }
       tc::tmem_st32(lane_base + kT4ColAlo + p2 * 32u, xr);
       tc::tmem_st_wait();
       tc::tc_fence_before();
       tc::nb_arrive(kNbAlo + (int)p2, 160);
+      if (warp == 0) T4TRACE(j, 2);
       if (++s == R) { s = 0; full_ph ^= 1u; }
     }
   } else if (warp < 12) {
@@ -421,6 +475,7 @@ __global__ void __launch_bounds__(kT4Threads, 1) lloyd_tc4_kernel(const Tc4Args 
       const unsigned long long row0 = tile_of(j) * kTcRows;
       const int rows = (int)min((unsigned long long)kTcRows, a.n - row0);
       T4WAIT(0, &bar_mma[g], u & 1u);
+      if (wq == 0) T4TRACE(j, 5);
       T4MARK(te_a);
       tc::tc_fence_after();
       uint32_t q[KP];
@@ -443,6 +498,7 @@ __global__ void __launch_bounds__(kT4Threads, 1) lloyd_tc4_kernel(const Tc4Args 
       T4ADD(3, te_a, te0);
       tc::tc_fence_before();
       tc::nb_arrive(kNbTfree + g, 160);        // the accumulator may be overwritten by tile j + 2
+      if (wq == 0) T4TRACE(j, 6);
       uint32_t m0 = q[0], m1 = q[1], m2 = q[2], m3 = q[3];
 #pragma unroll
       for (int c = 4; c + 7 < KP; c += 8) {
@@ -479,7 +535,8 @@ __global__ void __launch_bounds__(kT4Threads, 1) lloyd_tc4_kernel(const Tc4Args 
       const bool uni = __all_sync(0xffffffffu, lab == lab0) && lab0 < 0xFFFFFFFEu;
       T4MARK(te1);
       T4ADD(2, te0, te1);
-      if (u > 0) tc::nb_sync(kNbLfree + g, 256);   // U is done with this label slot
+      if (wq == 0) T4TRACE(j, 7);
+      if (u > 0) tc::nb_sync(kNbLfree + g, 192);   // U group g is done with this label slot
       T4MARK(te2);
       if (uni) {
         if (lane == 0) atomicAdd(&cnt[lab0], 32u);
@@ -487,41 +544,46 @@ __global__ void __launch_bounds__(kT4Threads, 1) lloyd_tc4_kernel(const Tc4Args 
         atomicAdd(&cnt[lab], 1u);
       }
       if (lane == 0) wuni[wq] = uni ? lab0 : 0xFFFFFFFFu;
-      labs2[(row & 7) * 16 + (row >> 3)] = lab;
+      labs2[(row & 3) * 32 + (row >> 2)] = lab;
       if (lab == 0xFFFFFFFFu) {
         const uint32_t p = atomicAdd(&n_flag[g], 1u);
         flags[p] = (uint32_t)row;
       }
-      tc::nb_arrive(kNbLab + g, 256);
+      tc::nb_arrive(kNbLab + g, 192);
+      if (wq == 0) T4TRACE(j, 8);
       T4MARK(te3);
       T4ADD(4, te2, te3);
     }
   } else {
     // =============================== U: exact re-scans, sums, inertia ===============================
-    const int tu = t - 384;                   // 0..127
-    const int uw = warp - 12;
-    // thread = (row subset sub8 of 8, feature pair fp): features 2 fp, 2 fp + 1 of rows sub8, sub8 + 8, ...
-    const int sub8 = uw * 2 + (lane >> 4), fp = lane & 15;
-    // byte offset of (row sub8, feature 2 fp) in a SW128 tile; rows sub8 + 8 i are 1024 i bytes further
-    const uint32_t x_off = (uint32_t)sub8 * 128u + ((((uint32_t)fp >> 1) ^ (uint32_t)sub8) << 4) + ((uint32_t)fp & 1u) * 8u;
-    float* my_acc = acc + (size_t)sub8 * (k + 1) * 32 + 2 * fp;
+    // Two independent U groups of two warps: group g takes the tiles j = g (mod 2) scored by E group g and owns
+    // its own accumulator subsets, so the even and the odd tiles form two pipelines that only share P, S and M.
+    const int g = (warp - 12) >> 1;           // tile parity
+    const int wl = (warp - 12) & 1;           // warp within the group
+    const int tg = wl * 32 + lane;            // 0..63
+    // thread = (row subset sub4 of 4, feature pair fp): features 2 fp, 2 fp + 1 of rows sub4, sub4 + 4, ...
+    const int sub4 = wl * 2 + (lane >> 4), fp = lane & 15;
+    // byte offsets of (row, feature 2 fp) for row & 7 = sub4 (even i) and sub4 + 4 (odd i); + 1024 (i >> 1)
+    const uint32_t off_e = (uint32_t)sub4 * 128u + ((((uint32_t)fp >> 1) ^ (uint32_t)sub4) << 4) + ((uint32_t)fp & 1u) * 8u;
+    const uint32_t off_o = (uint32_t)(sub4 + 4) * 128u + ((((uint32_t)fp >> 1) ^ (uint32_t)(sub4 + 4)) << 4) + ((uint32_t)fp & 1u) * 8u;
+    float* my_acc = acc + (size_t)(g * 4 + sub4) * (k + 1) * 32 + 2 * fp;
+    uint32_t* labs2 = labs2_all + g * kTcRows;
+    const uint32_t* flags = flags_all + g * kTcRows;
+    const int ubar = g ? 10 : 1;              // group-internal named barrier
     float inert_f = 0.f, inert_g = 0.f, inert_h = 0.f;   // per-tile partials -> 8-tile -> 64-tile partials -> f64 at the end
-    int s = 0;
-    for (unsigned long long j = 0; j < my_tiles; ++j) {
-      const int g = (int)(j & 1);
-      const uint32_t u = (uint32_t)(j >> 1);
+    int s = g;
+    for (unsigned long long j = g; j < my_tiles; j += 2) {
       const unsigned long long row0 = tile_of(j) * kTcRows;
       const int rows = (int)min((unsigned long long)kTcRows, a.n - row0);
       const unsigned char* rw = raw + (size_t)s * 16384;
-      uint32_t* labs2 = labs2_all + g * kTcRows;
-      const uint32_t* flags = flags_all + g * kTcRows;
-      tc::nb_sync(kNbLab + g, 256);
+      tc::nb_sync(kNbLab + g, 192);
+      if (wl == 0) T4TRACE(j, 9);
       T4MARK(tu_a);
       const uint32_t nf = n_flag[g];
       const uint4 wu = *reinterpret_cast<const uint4*>(wuni_all + g * 4);
       if (nf) {
         // uncertified rows: exact scan, one warp per row, lanes split the centroids
-        for (uint32_t f = uw; f < nf; f += 4) {
+        for (uint32_t f = wl; f < nf; f += 2) {
           const uint32_t frow = flags[f];
           float x2[32];
 #pragma unroll
@@ -539,13 +601,13 @@ __global__ void __launch_bounds__(kT4Threads, 1) lloyd_tc4_kernel(const Tc4Args 
           }
           combine_candidates<float>(32, fb, fi);
           if (lane == 0) {
-            labs2[(frow & 7) * 16 + (frow >> 3)] = (uint32_t)fi;
+            labs2[(frow & 3) * 32 + (frow >> 2)] = (uint32_t)fi;
             atomicAdd(&cnt[fi], 1u);
           }
         }
-        my_fallbacks += (tu == 0) ? nf : 0u;
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        if (tu == 0) n_flag[g] = 0;
+        my_fallbacks += (tg == 0) ? nf : 0u;
+        tc::nb_sync(ubar, 64);
+        if (tg == 0) n_flag[g] = 0;
       }
       T4MARK(tu0);
       T4ADD(4, tu_a, tu0);
@@ -557,9 +619,9 @@ __global__ void __launch_bounds__(kT4Threads, 1) lloyd_tc4_kernel(const Tc4Args 
         const unsigned long long ncf = tc::f2_pack(-cf.x, -cf.y);
         unsigned long long s0 = 0ull, s1 = 0ull, e3 = 0ull;
 #pragma unroll
-        for (int ii = 0; ii < 16; ii += 2) {
-          const unsigned long long x0 = *reinterpret_cast<const unsigned long long*>(rw + 1024u * ii + x_off);
-          const unsigned long long x1 = *reinterpret_cast<const unsigned long long*>(rw + 1024u * (ii + 1) + x_off);
+        for (int ii = 0; ii < 16; ++ii) {
+          const unsigned long long x0 = *reinterpret_cast<const unsigned long long*>(rw + 1024u * ii + off_e);
+          const unsigned long long x1 = *reinterpret_cast<const unsigned long long*>(rw + 1024u * ii + off_o);
           const unsigned long long d0 = tc::f2_add(x0, ncf), d1 = tc::f2_add(x1, ncf);
           s0 = tc::f2_add(s0, x0); s1 = tc::f2_add(s1, x1);
           e2 = tc::f2_fma(d0, d0, e2); e3 = tc::f2_fma(d1, d1, e3);
@@ -575,14 +637,15 @@ __global__ void __launch_bounds__(kT4Threads, 1) lloyd_tc4_kernel(const Tc4Args 
         uint32_t cur_lab = (uint32_t)k;   // dummy accumulator row
         unsigned long long cur = 0ull, ncf = 0ull;
 #pragma unroll
-        for (int qq = 0; qq < 4; ++qq) {
-          const uint4 lv = *reinterpret_cast<const uint4*>(labs2 + sub8 * 16 + 4 * qq);
+        for (int qq = 0; qq < 8; ++qq) {
+          const uint4 lv = *reinterpret_cast<const uint4*>(labs2 + sub4 * 32 + 4 * qq);
           const uint32_t l4[4] = {lv.x, lv.y, lv.z, lv.w};
 #pragma unroll
           for (int uu = 0; uu < 4; ++uu) {
-            const int ii = 4 * qq + uu;  // row sub8 + 8 ii
-            if (sub8 + 8 * ii < rows) {
-              const unsigned long long xv = *reinterpret_cast<const unsigned long long*>(rw + 1024u * ii + x_off);
+            const int ii = 4 * qq + uu;  // row sub4 + 4 ii
+            if (sub4 + 4 * ii < rows) {
+              const unsigned long long xv =
+                  *reinterpret_cast<const unsigned long long*>(rw + 1024u * (ii >> 1) + ((ii & 1) ? off_o : off_e));
               if (l4[uu] != cur_lab) {
                 float2* ap = reinterpret_cast<float2*>(my_acc + cur_lab * 32);
                 float2 av = *ap;
@@ -606,14 +669,17 @@ __global__ void __launch_bounds__(kT4Threads, 1) lloyd_tc4_kernel(const Tc4Args 
       }
       T4MARK(tu1);
       T4ADD(2, tu0, tu1);
+      if (wl == 0) T4TRACE(j, 10);
       inert_f += tc::f2_lo(e2) + tc::f2_hi(e2);
-      if ((j & 7) == 7) { inert_g += inert_f; inert_f = 0.f; }
-      if ((j & 63) == 63) { inert_h += inert_g; inert_g = 0.f; }
+      if ((j & 14) == 14) { inert_g += inert_f; inert_f = 0.f; }
+      if ((j & 126) == 126) { inert_h += inert_g; inert_g = 0.f; }
       tc::warp_arrive(&bar_free[s], lane);   // the raw stage may be refilled
-      tc::nb_arrive(kNbLfree + g, 256);      // the label slot may be rewritten
+      tc::nb_arrive(kNbLfree + g, 192);      // the label slot may be rewritten
+      if (wl == 0) T4TRACE(j, 11);
       T4MARK(tu2);
       T4ADD(3, tu1, tu2);
-      if (++s == R) s = 0;
+      s += 2;
+      if (s >= R) s -= R;
     }
     inert = (double)inert_h + (double)inert_g + (double)inert_f;
   }
@@ -625,7 +691,9 @@ __global__ void __launch_bounds__(kT4Threads, 1) lloyd_tc4_kernel(const Tc4Args 
       for (int q = 0; q < 8; ++q) a.prof[role * 8 + q] = prof_acc[q];
   }
 #endif
+  T4K(5);
   __syncthreads();
+  T4K(6);
   if (!done) {
     // ---- per-CTA partials (same layout as the other fused kernels) ----
     const int kd = k * 32, sstride = (k + 1) * 32;
@@ -638,19 +706,22 @@ __global__ void __launch_bounds__(kT4Threads, 1) lloyd_tc4_kernel(const Tc4Args 
     }
     uint32_t* pc = a.part_counts + (size_t)blockIdx.x * k;
     for (int e = t; e < k; e += kT4Threads) pc[e] = cnt[e];
+    // inertia: the 128 U threads' partials, fixed order (warp butterfly, then the four warp sums)
     double* red = reinterpret_cast<double*>(raw);
-    if (t >= 384 && t < 512) red[t - 384] = inert;
-    __syncthreads();
-    for (int o = 64; o > 0; o >>= 1) {
-      if (t < o) red[t] += red[t + o];
-      __syncthreads();
+    if (t >= 384 && t < 512) {
+      float v = (float)inert;
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (lane == 0) red[(t - 384) >> 5] = (double)v;
     }
-    if (t == 0) a.part_inertia[blockIdx.x] = red[0];
-    if (a.state && t == 384 && my_fallbacks) atomicAdd(&a.state->fallback_rows, (unsigned long long)my_fallbacks);
+    __syncthreads();
+    if (t == 0) a.part_inertia[blockIdx.x] = (red[0] + red[1]) + (red[2] + red[3]);
+    if (a.state && (t == 384 || t == 448) && my_fallbacks) atomicAdd(&a.state->fallback_rows, (unsigned long long)my_fallbacks);
   }
+  T4K(7);
   tc::tc_fence_before();
   __syncthreads();
   if (warp == 0) tc::tmem_dealloc(tmem, kT4TmemCols);
+  T4K(8);
 }
 
 
