@@ -633,39 +633,63 @@ __global__ void __launch_bounds__(kT4Threads, 1) lloyd_tc4_kernel(const Tc4Args 
         av.x += tc::f2_lo(s0); av.y += tc::f2_hi(s0);
         *ap = av;
       } else {
-        // mixed labels (or a tail tile): runs of equal labels are summed in registers, then flushed
-        uint32_t cur_lab = (uint32_t)k;   // dummy accumulator row
-        unsigned long long cur = 0ull, ncf = 0ull;
-#pragma unroll
+        // mixed labels (or a tail tile), four rows at a time.  Four different labels touch four different
+        // accumulators, so their read-modify-writes are independent and overlap; batches with repeated labels
+        // (sorted data at a cluster boundary) sum runs of equal labels in registers and flush on a change.
+#pragma unroll 2
         for (int qq = 0; qq < 8; ++qq) {
           const uint4 lv = *reinterpret_cast<const uint4*>(labs2 + sub4 * 32 + 4 * qq);
           const uint32_t l4[4] = {lv.x, lv.y, lv.z, lv.w};
+          const unsigned char* rq = rw + 2048u * qq;       // rows sub4 + 16 qq + {0, 4, 8, 12}
+          const bool full4 = sub4 + 16 * qq + 12 < rows;
+          const bool distinct = l4[0] != l4[1] && l4[0] != l4[2] && l4[0] != l4[3] && l4[1] != l4[2] && l4[1] != l4[3] && l4[2] != l4[3];
+          if (full4 && distinct) {
+            unsigned long long xv[4];
+            float2 av[4], cv[4];
+            xv[0] = *reinterpret_cast<const unsigned long long*>(rq + off_e);
+            xv[1] = *reinterpret_cast<const unsigned long long*>(rq + off_o);
+            xv[2] = *reinterpret_cast<const unsigned long long*>(rq + 1024u + off_e);
+            xv[3] = *reinterpret_cast<const unsigned long long*>(rq + 1024u + off_o);
 #pragma unroll
-          for (int uu = 0; uu < 4; ++uu) {
-            const int ii = 4 * qq + uu;  // row sub4 + 4 ii
-            if (sub4 + 4 * ii < rows) {
-              const unsigned long long xv =
-                  *reinterpret_cast<const unsigned long long*>(rw + 1024u * (ii >> 1) + ((ii & 1) ? off_o : off_e));
-              if (l4[uu] != cur_lab) {
-                float2* ap = reinterpret_cast<float2*>(my_acc + cur_lab * 32);
-                float2 av = *ap;
-                av.x += tc::f2_lo(cur); av.y += tc::f2_hi(cur);
-                *ap = av;
-                cur_lab = l4[uu];
-                cur = 0ull;
-                const float2 cf = *reinterpret_cast<const float2*>(rawc + cur_lab * kTcCStride + 2 * fp);
-                ncf = tc::f2_pack(-cf.x, -cf.y);
-              }
-              const unsigned long long dv = tc::f2_add(xv, ncf);
-              cur = tc::f2_add(cur, xv);
+            for (int uu = 0; uu < 4; ++uu) {
+              av[uu] = *reinterpret_cast<const float2*>(my_acc + l4[uu] * 32);
+              cv[uu] = *reinterpret_cast<const float2*>(rawc + l4[uu] * kTcCStride + 2 * fp);
+            }
+#pragma unroll
+            for (int uu = 0; uu < 4; ++uu) {
+              av[uu].x += tc::f2_lo(xv[uu]); av[uu].y += tc::f2_hi(xv[uu]);
+              *reinterpret_cast<float2*>(my_acc + l4[uu] * 32) = av[uu];
+              const unsigned long long dv = tc::f2_add(xv[uu], tc::f2_pack(-cv[uu].x, -cv[uu].y));
               e2 = tc::f2_fma(dv, dv, e2);
             }
+          } else {
+            uint32_t cur_lab = (uint32_t)k;   // dummy accumulator row
+            unsigned long long cur = 0ull, ncf = 0ull;
+#pragma unroll
+            for (int uu = 0; uu < 4; ++uu) {
+              if (sub4 + 16 * qq + 4 * uu < rows) {
+                const unsigned long long xv = *reinterpret_cast<const unsigned long long*>(rq + 1024u * (uu >> 1) + ((uu & 1) ? off_o : off_e));
+                if (l4[uu] != cur_lab) {
+                  float2* ap = reinterpret_cast<float2*>(my_acc + cur_lab * 32);
+                  float2 a2 = *ap;
+                  a2.x += tc::f2_lo(cur); a2.y += tc::f2_hi(cur);
+                  *ap = a2;
+                  cur_lab = l4[uu];
+                  cur = 0ull;
+                  const float2 cf = *reinterpret_cast<const float2*>(rawc + cur_lab * kTcCStride + 2 * fp);
+                  ncf = tc::f2_pack(-cf.x, -cf.y);
+                }
+                const unsigned long long dv = tc::f2_add(xv, ncf);
+                cur = tc::f2_add(cur, xv);
+                e2 = tc::f2_fma(dv, dv, e2);
+              }
+            }
+            float2* ap = reinterpret_cast<float2*>(my_acc + cur_lab * 32);
+            float2 a2 = *ap;
+            a2.x += tc::f2_lo(cur); a2.y += tc::f2_hi(cur);
+            *ap = a2;
           }
         }
-        float2* ap = reinterpret_cast<float2*>(my_acc + cur_lab * 32);
-        float2 av = *ap;
-        av.x += tc::f2_lo(cur); av.y += tc::f2_hi(cur);
-        *ap = av;
       }
       T4MARK(tu1);
       T4ADD(2, tu0, tu1);

@@ -504,3 +504,104 @@ def test_tc_assign_path_matches_oracle(lb, ctx, oracle, n, d, k, k_true, spread)
     assert counts.tolist() == ref_counts.tolist()
     np.testing.assert_allclose(inertia, ref_inertia, rtol=1e-5)
     print(f"fallback rows over 2 iterations: {st.fallback_rows} of {2 * n}")
+
+
+# ---- warp-specialised pipeline kernel (tc4: f32, d = 32, k <= 64) ----
+def _oracle_iters(oracle, X, init, iters):
+    cur = init
+    for _ in range(iters):
+        lab, d = oracle.assign(X, cur)
+        nxt = oracle.compute_centroids(cur, X, lab, acc_f64=True)
+        last = (lab, d)
+        cur = nxt
+    return cur, last
+
+
+PIPE_CASES = [
+    # n, k, k_true, spread, shuffle
+    (40000, 64, 64, 30.0, True),     # every tile has mixed labels: general accumulation path
+    (40000, 64, 64, 30.0, False),    # blob order: uniform tiles, register fast path
+    (128 * 148 * 3 + 77, 33, 33, 30.0, True),   # three tiles per CTA plus a tail tile, k padded to 64
+    (1000, 17, 17, 5.0, True),       # fewer tiles than CTAs, k <= 32 (32-column variant)
+    (127, 2, 2, 30.0, False),        # a single partial tile
+    (128, 64, 8, 1.0, True),         # exactly one tile, many near ties
+    (50000, 48, 6, 0.7, True),       # heavy overlap: a large share of rows takes the exact re-scan
+]
+
+
+@pytest.mark.parametrize("n,k,k_true,spread,shuffle", PIPE_CASES)
+def test_pipeline_kernel_matches_oracle(lb, ctx, oracle, n, k, k_true, spread, shuffle):
+    dt = np.float32
+    X, _ = blobs(n, 32, k_true, dt, seed=7 * n + k, spread=spread)
+    g = np.random.default_rng(n + k)
+    if shuffle:
+        X = X[g.permutation(n)].copy()
+    init = X[g.choice(n, size=k, replace=False)].copy()
+    ctx.set_assign_path(2)
+    try:
+        ctx.set_data(X)
+        c, counts, inertia, st = ctx.lloyd_iters(init, 4, 0.0)
+        assert st.assign_path == 2 and st.n_iter == 4
+    finally:
+        ctx.set_assign_path(-1)
+    cur, (lab, d) = _oracle_iters(oracle, X, init, 4)
+    scale = np.abs(cur).max()
+    np.testing.assert_allclose(c, cur, rtol=1e-5, atol=1e-5 * scale)
+    assert counts.tolist() == np.bincount(lab.astype(np.int64), minlength=k).tolist()
+    np.testing.assert_allclose(inertia, d.astype(np.float64).sum(), rtol=1e-5)
+    print(f"re-scanned rows over 4 iterations: {st.fallback_rows} of {4 * n}")
+
+
+@pytest.mark.parametrize("scale,offset", [(1e-3, 0.0), (1e3, 0.0), (1.0, 5e3), (1e-20, 0.0), (1e15, 0.0)])
+def test_pipeline_kernel_magnitudes(lb, ctx, oracle, scale, offset):
+    """The binade window of the packed scores follows max|x|, max|c|: tiny, huge and far-from-origin data."""
+    dt = np.float32
+    X, _ = blobs(20000, 32, 10, dt, seed=11, spread=30.0)
+    X = (X.astype(np.float64) * scale + offset).astype(dt)
+    g = np.random.default_rng(5)
+    X = X[g.permutation(len(X))].copy()
+    init = X[g.choice(len(X), size=10, replace=False)].copy()
+    ctx.set_assign_path(2)
+    try:
+        ctx.set_data(X)
+        c, counts, inertia, st = ctx.lloyd_iters(init, 2, 0.0)
+    finally:
+        ctx.set_assign_path(-1)
+    cur, (lab, d) = _oracle_iters(oracle, X, init, 2)
+    assert counts.tolist() == np.bincount(lab.astype(np.int64), minlength=10).tolist()
+    np.testing.assert_allclose(c, cur, rtol=1e-5, atol=1e-5 * np.abs(cur).max())
+    ref_inertia = d.astype(np.float64).sum()
+    if np.isfinite(ref_inertia):
+        np.testing.assert_allclose(inertia, ref_inertia, rtol=2e-5)
+
+
+def test_pipeline_kernel_inf_rows(lb, ctx, oracle):
+    dt = np.float32
+    X, _ = blobs(3000, 32, 5, dt, seed=3)
+    X[100, 3] = np.inf
+    X[2000, 30] = -np.inf
+    init = X[[0, 700, 1300, 1900, 2500]].copy()
+    ctx.set_assign_path(2)
+    try:
+        ctx.set_data(X)
+        c, counts, inertia, st = ctx.lloyd_iters(init, 1, 0.0)
+    finally:
+        ctx.set_assign_path(-1)
+    lab, d = oracle.assign(X, init)
+    assert counts.tolist() == np.bincount(lab.astype(np.int64), minlength=5).tolist()
+    assert not np.isfinite(inertia)
+
+
+def test_pipeline_kernel_full_fit_matches_oracle(lb, oracle):
+    """Through the public API (fit -> predict), convergence by tolerance, k-means++ seeding shared with the oracle."""
+    X, _ = blobs(30000, 32, 12, np.float32, seed=21, spread=10.0)
+    rng = lb.Xoshiro256Plus.seed_from_u64(9)
+    model = (lb.KMeans.params_with_rng(12, rng).n_runs(2).max_n_iterations(50).tolerance(1e-4)
+             .init_method(lb.KMeansInit.KMeansPlusPlus).fit(lb.DatasetBase(X)))
+    ref = oracle.fit(X, 12, oracle.rng(9), n_runs=2, max_iter=50, tol=1e-4, method=INIT_KMEANSPP, acc_f64=True)
+    assert ref["status"] == 0
+    np.testing.assert_allclose(model.centroids(), ref["centroids"], rtol=1e-5, atol=1e-4)
+    np.testing.assert_allclose(model.inertia(), ref["inertia"], rtol=1e-5)
+    assert model.cluster_count().tolist() == ref["cluster_count"].tolist()
+    lab, _ = oracle.assign(X, model.centroids())
+    assert (model.predict(X) == lab).all()
