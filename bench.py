@@ -57,6 +57,16 @@ def load_peaks():
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def load_traffic(workload):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu capture (None if not captured)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as f:
+            t = json.load(f).get(workload)
+        return (int(t["dram_bytes_read"]) + int(t["dram_bytes_write"]), t["kernel"]) if t else (None, None)
+    except Exception:
+        return None, None
+
+
 def centres_for(k, d, dtype, seed=1234):
     g = np.random.default_rng(seed)
     return g.uniform(-30.0, 30.0, (k, d)).astype(dtype)  # benches/k_means.rs:48-49: Uniform(-30, 30)
@@ -301,8 +311,9 @@ def main():
     if main_ms:
         per_launch_s = main_ms * 1e-3 / args.steps
         achieved = n * d * itemsize / per_launch_s / 1e9
+        traffic, kname = load_traffic(args.workload)
         roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                    "traffic": None, "kernel": "lloyd_kernel (fused assign+update)",
+                    "traffic": traffic, "kernel": kname or "fused assign+update kernel (lloyd_kernel / lloyd_tc_kernel)",
                     "algorithmic_bytes_per_launch": n * d * itemsize, "mean_launch_us": per_launch_s * 1e6,
                     "peak_source": peak_src}
 

@@ -495,19 +495,20 @@ template <typename F, typename S, typename CT> struct FinalizeArgs {
 };
 
 constexpr int kFinElems = 16;    // elements (of the k*d sums) per CTA
-constexpr int kFinGroups = 64;   // source groups per element; CTA = kFinElems * kFinGroups threads
+constexpr int kFinGroups = 16;   // source groups per element; CTA = kFinElems * kFinGroups threads
 constexpr int kFinThreads = kFinElems * kFinGroups;
 
+// fixed-order sum over the CTA: warp butterflies, then the warp sums in warp order
 __device__ __forceinline__ double block_sum(double v, double* red) {
   const int t = threadIdx.x;
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   __syncthreads();
-  red[t] = v;
+  if ((t & 31) == 0) red[t >> 5] = v;
   __syncthreads();
-  for (int o = kFinThreads / 2; o > 0; o >>= 1) {
-    if (t < o) red[t] += red[t + o];
-    __syncthreads();
-  }
-  return red[0];
+  double tot = 0.0;
+#pragma unroll
+  for (int w = 0; w < kFinThreads / 32; ++w) tot += red[w];
+  return tot;
 }
 
 // sum of src[b*stride + e] over b = g, g+G, g+2G, ... with four independent chains so the
