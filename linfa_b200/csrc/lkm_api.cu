@@ -98,6 +98,8 @@ struct lkm_ctx {
   int tc_variant = 4;
   uint64_t data_epoch = 1, xmax2_epoch = 0;  // resident-data version / version the cached max row norm belongs to
   DevBuf xmax2, t4prof;
+  int tc4_passes_forced = 0;              // LKM_TC4_PASSES = 2 / 3 pins the scoring passes of the pipeline kernel
+  uint64_t tc4_hard_epoch = 0, tc4_easy_epoch = 0;   // data versions seen to need 3 passes / to be fine with 2
   uint64_t flush_bytes = 0;
   int kernel_timing = 0;
   DevBuf flushbuf;
@@ -402,7 +404,7 @@ static cudaError_t launch_tc3(int kp, int grid, size_t smem, cudaStream_t s, con
   return cudaLaunchKernelEx(&cfg, lloyd_tc3_kernel<64>, arg, map);
 }
 
-static cudaError_t launch_tc4(int kp, int grid, size_t smem, cudaStream_t s, const Tc4Args& arg, const CUtensorMap& map) {
+static cudaError_t launch_tc4(int kp, int passes, int grid, size_t smem, cudaStream_t s, const Tc4Args& arg, const CUtensorMap& map) {
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)grid);
   cfg.blockDim = dim3((unsigned)kT4Threads);
@@ -413,8 +415,12 @@ static cudaError_t launch_tc4(int kp, int grid, size_t smem, cudaStream_t s, con
   at[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = at;
   cfg.numAttrs = 1;
-  if (kp == 32) return cudaLaunchKernelEx(&cfg, lloyd_tc4_kernel<32>, arg, map);
-  return cudaLaunchKernelEx(&cfg, lloyd_tc4_kernel<64>, arg, map);
+  if (passes == 2) {
+    if (kp == 32) return cudaLaunchKernelEx(&cfg, lloyd_tc4_kernel<32, 2>, arg, map);
+    return cudaLaunchKernelEx(&cfg, lloyd_tc4_kernel<64, 2>, arg, map);
+  }
+  if (kp == 32) return cudaLaunchKernelEx(&cfg, lloyd_tc4_kernel<32, 3>, arg, map);
+  return cudaLaunchKernelEx(&cfg, lloyd_tc4_kernel<64, 3>, arg, map);
 }
 
 struct LloydOut {
@@ -455,8 +461,13 @@ static lkm_status run_lloyd(lkm_ctx* ctx, F* dC2, uint64_t k, uint64_t max_iter,
       if (v3) {
         if (v4) tc4_nstages = tc4_stages((int)k, tc_kp, ctx->smem_optin - 1024);
         tc_smem = v4 ? tc4_smem_bytes((int)k, tc_kp, tc4_nstages) : tc3_smem_bytes((int)k, tc_kp);
-        const void* fn = v4 ? (tc_kp == 32 ? (const void*)lloyd_tc4_kernel<32> : (const void*)lloyd_tc4_kernel<64>)
+        const void* fn = v4 ? (tc_kp == 32 ? (const void*)lloyd_tc4_kernel<32, 3> : (const void*)lloyd_tc4_kernel<64, 3>)
                             : (tc_kp == 32 ? (const void*)lloyd_tc3_kernel<32> : (const void*)lloyd_tc3_kernel<64>);
+        if (v4) {
+          const void* fn2 = tc_kp == 32 ? (const void*)lloyd_tc4_kernel<32, 2> : (const void*)lloyd_tc4_kernel<64, 2>;
+          CK(cudaFuncSetAttribute(fn2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem));
+          CK(cudaFuncSetAttribute(fn2, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
+        }
         CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem));
         CK(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
         CKS(make_row_tile_map(ctx, dX, n, tc3_map));
@@ -575,8 +586,18 @@ static lkm_status run_lloyd(lkm_ctx* ctx, F* dC2, uint64_t k, uint64_t max_iter,
 
   uint64_t launched = 0;
   const uint64_t batch = 16;
+  // pipeline kernel: scoring passes.  Two passes (x_hi only) certify well-separated data at a lower cost; when more
+  // than 2 % of the rows of a batch need the exact re-scan the loop switches to the 3xTF32 variant.  A data set that
+  // has not been seen with two passes yet gets a one-iteration first batch, so a bad guess costs one iteration.
+  const bool is_tc4 = use_tc && tc_threads == kT4Threads;
+  int tc4_passes = 3;
+  if (is_tc4) {
+    tc4_passes = ctx->tc4_passes_forced ? ctx->tc4_passes_forced : ((ctx->tc4_hard_epoch == ctx->data_epoch && ctx->own_X) ? 3 : 2);
+  }
+  bool tc4_probe = is_tc4 && !ctx->tc4_passes_forced && tc4_passes == 2 && !(ctx->tc4_easy_epoch == ctx->data_epoch && ctx->own_X);
+  unsigned long long fb_seen = 0;
   for (;;) {
-    const uint64_t todo = std::min<uint64_t>(batch, max_iter - launched);
+    const uint64_t todo = std::min<uint64_t>(tc4_probe ? 1 : batch, max_iter - launched);
     for (uint64_t q = 0; q < todo; ++q) {
       const uint64_t it = launched + q;
       const F* Ccur = dC2 + (it & 1) * kd;
@@ -599,7 +620,7 @@ static lkm_status run_lloyd(lkm_ctx* ctx, F* dC2, uint64_t k, uint64_t max_iter,
             t4.prof = ctx->t4prof.as<long long>();
 #endif
             t4.part_sums = ta.part_sums; t4.part_counts = ta.part_counts; t4.part_inertia = ta.part_inertia; t4.state = dstate;
-            CK(launch_tc4(tc_kp, tc_grid, tc_smem, ctx->stream, t4, tc3_map));
+            CK(launch_tc4(tc_kp, tc4_passes, tc_grid, tc_smem, ctx->stream, t4, tc3_map));
           } else if (tc_threads == kT3Threads) {
             Tc3Args t3{};
             t3.X = dX; t3.n = n; t3.k = (int)k; t3.C = Ccur; t3.xmax2_bits = ctx->xmax2.as<unsigned int>();
@@ -718,8 +739,16 @@ static lkm_status run_lloyd(lkm_ctx* ctx, F* dC2, uint64_t k, uint64_t max_iter,
       if (flush) CK(cudaEventRecord(ctx->iter_events[3 * it + 2], ctx->stream));
     }
     launched += todo;
+    const uint64_t todo_done = todo;
     CK(cudaMemcpyAsync(ctx->h_state, dstate, sizeof(LloydState), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
+    if (is_tc4 && !ctx->tc4_passes_forced && tc4_passes == 2) {
+      const unsigned long long fb = (ctx->h_state->fallback_rows & ((1ull << 40) - 1)) - fb_seen;
+      if ((double)fb > 0.02 * (double)n * (double)todo_done) { tc4_passes = 3; ctx->tc4_hard_epoch = ctx->data_epoch; }
+      else ctx->tc4_easy_epoch = ctx->data_epoch;
+      tc4_probe = false;
+    }
+    fb_seen = ctx->h_state->fallback_rows & ((1ull << 40) - 1);
     if (ctx->h_state->done || launched >= max_iter) break;
   }
   CK(cudaEventRecord(ctx->ev1, ctx->stream));
@@ -1581,6 +1610,7 @@ LKM_EXPORT lkm_status lkm_create(lkm_ctx** out, int device) {
   if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return bail(LKM_ERR_CUDA);
   if (const char* v = std::getenv("LKM_TC_VARIANT")) ctx->tc_variant = std::atoi(v);
   if (const char* v = std::getenv("LKM_P2P")) ctx->p2p_enabled = std::atoi(v);
+  if (const char* v = std::getenv("LKM_TC4_PASSES")) ctx->tc4_passes_forced = std::atoi(v);
   ctx->sm_count = prop.multiProcessorCount;
   ctx->smem_optin = prop.sharedMemPerBlockOptin;
   if (cudaMallocHost(&ctx->h_state, sizeof(LloydState)) != cudaSuccess) return bail(LKM_ERR_CUDA);

@@ -210,7 +210,11 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 }  // namespace tc
 
-template <int KP>
+// PASSES = 3: x_lo.c_hi + x_hi.c_lo + x_hi.c_hi (3xTF32, A operands staged in TMEM by the S role).
+// PASSES = 2: x_hi.c_lo + x_hi.c_hi only — the raw tile in shared memory is the A operand, the S role is idle, and the
+// dropped x_lo.c term (|x_lo.c| <= 2^-11 |x||c|) widens the certificate; rows it no longer certifies take the exact
+// re-scan, so results are identical.  The host starts with 2 passes and switches to 3 when too many rows fall back.
+template <int KP, int PASSES>
 __global__ void __launch_bounds__(kT4Threads, 1) lloyd_tc4_kernel(const Tc4Args a, const __grid_constant__ CUtensorMap tmap) {
   static_assert(KP == 32 || KP == 64, "score columns");
 #ifdef LKM_T4_TRACE
@@ -325,7 +329,8 @@ __global__ void __launch_bounds__(kT4Threads, 1) lloyd_tc4_kernel(const Tc4Args 
                             2.f * gamma * (xmax + cmax) * (xmax + cmax));
   // v is half a squared distance.  On each of the two candidates: the bias K-step rounds at most 3 ulp(v), the
   // f32 bias K0 - nn/2 is off by at most 2^-24 K0 + (d + 1) 2^-25 |c|^2 (rounding of the norm and of the subtraction)
-  const float m_v = 0.5f * m_w + 7.f * 1.1920929e-7f * (K0 + Rb) + 33.f * 5.9604645e-8f * cmax2;
+  const float m_v = 0.5f * m_w + 7.f * 1.1920929e-7f * (K0 + Rb) + 33.f * 5.9604645e-8f * cmax2 +
+                    (PASSES == 2 ? 1.001f * 9.765625e-4f * xmax * cmax : 0.f);   // + 2 * 2^-11 |x||c| without the x_lo pass
   if (t < KP) {
     // bias row t: K0 - |c|^2/2 as three TF32 pieces that add up to the f32 value exactly, K-step 0 of the tile
     const float b = (t < k) ? (K0 - 0.5f * nn_s[t]) : two_lo;
@@ -389,43 +394,46 @@ __global__ void __launch_bounds__(kT4Threads, 1) lloyd_tc4_kernel(const Tc4Args 
       const uint64_t desc_bias = tc::smem_desc_sw128(tc::smem_u32(b_bias));
       const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem, 0);
       // x_lo.c_hi, x_hi.c_lo, x_hi.c_hi, bias; A K-step ks = 8 TMEM columns, B K-step = 32 bytes = 2 descriptor units
-      auto issue = [&](const uint32_t p2) {
+      const uint64_t desc_raw = tc::smem_desc_sw128(tc::smem_u32(raw));
+      auto issue = [&](const uint32_t p2, const int stage) {
         const uint32_t dcol = tmem_u + p2 * 64u;
-        const uint32_t a_hi = tmem_u + kT4ColAhi + p2 * 32u, a_lo = tmem_u + kT4ColAlo + p2 * 32u;
+        if constexpr (PASSES == 3) {
+          const uint32_t a_hi = tmem_u + kT4ColAhi + p2 * 32u, a_lo = tmem_u + kT4ColAlo + p2 * 32u;
 #pragma unroll
-        for (int ks = 0; ks < 4; ++ks) tc::mma_tf32_ts_elect(dcol, a_lo + 8u * ks, desc_bhi + 2u * ks, idesc, ks ? 1u : 0u);
+          for (int ks = 0; ks < 4; ++ks) tc::mma_tf32_ts_elect(dcol, a_lo + 8u * ks, desc_bhi + 2u * ks, idesc, ks ? 1u : 0u);
 #pragma unroll
-        for (int ks = 0; ks < 4; ++ks) tc::mma_tf32_ts_elect(dcol, a_hi + 8u * ks, desc_blo + 2u * ks, idesc, 1u);
+          for (int ks = 0; ks < 4; ++ks) tc::mma_tf32_ts_elect(dcol, a_hi + 8u * ks, desc_blo + 2u * ks, idesc, 1u);
 #pragma unroll
-        for (int ks = 0; ks < 4; ++ks) tc::mma_tf32_ts_elect(dcol, a_hi + 8u * ks, desc_bhi + 2u * ks, idesc, 1u);
+          for (int ks = 0; ks < 4; ++ks) tc::mma_tf32_ts_elect(dcol, a_hi + 8u * ks, desc_bhi + 2u * ks, idesc, 1u);
+        } else {
+          const uint64_t da = desc_raw + (uint64_t)stage * 1024u;   // 16 KB per stage, 16-byte units
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) tc::mma_tf32_elect(dcol, da + 2u * ks, desc_blo + 2u * ks, idesc, ks ? 1u : 0u);
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) tc::mma_tf32_elect(dcol, da + 2u * ks, desc_bhi + 2u * ks, idesc, 1u);
+        }
         tc::mma_tf32_ts_elect(dcol, tmem_u + kT4ColOnes, desc_bias, idesc, 1u);
       };
-      for (unsigned long long j = 0; j < my_tiles; j += 2) {
-        const uint32_t u = (uint32_t)(j >> 1);
-        tc::nb_sync(kNbAlo + 0, 160);
+      int s = 0;
+      uint32_t full_ph = 0;
+      for (unsigned long long j = 0; j < my_tiles; ++j) {
+        const uint32_t p2 = (uint32_t)j & 1u, u = (uint32_t)(j >> 1);
+        if constexpr (PASSES == 3) tc::nb_sync(kNbAlo + (int)p2, 160);
+        else tc::mbar_wait_or_trap(&bar_full[s], full_ph);      // the raw tile has landed
         T4TRACE(j, 12);
-        if (u > 0) tc::nb_sync(kNbTfree + 0, 160);   // accumulator drained by E
+        if (u > 0) tc::nb_sync(kNbTfree + (int)p2, 160);   // accumulator drained by E
         T4TRACE(j, 13);
         tc::tc_fence_after();
         T4TRACE(j, 3);
-        issue(0u);
-        tc::mma_commit_elect(&bar_mma[0]);
+        if (p2) issue(1u, s); else issue(0u, s);
+        tc::mma_commit_elect(&bar_mma[p2]);
         T4TRACE(j, 4);
-        if (j + 1 < my_tiles) {
-          tc::nb_sync(kNbAlo + 1, 160);
-          T4TRACE(j + 1, 12);
-          if (u > 0) tc::nb_sync(kNbTfree + 1, 160);
-          T4TRACE(j + 1, 13);
-          tc::tc_fence_after();
-          T4TRACE(j + 1, 3);
-          issue(1u);
-          tc::mma_commit_elect(&bar_mma[1]);
-          T4TRACE(j + 1, 4);
-        }
+        if (++s == R) { s = 0; full_ph ^= 1u; }
       }
     }
   } else if (warp < 4) {
     // =============================== S: the A operands of tile j into TMEM ===============================
+    if constexpr (PASSES == 3) {
     int s = 0;
     uint32_t full_ph = 0;
     const uint32_t row_off = (uint32_t)(t >> 3) * 1024u + (uint32_t)(t & 7) * 128u;   // row t of a SW128 tile
@@ -460,6 +468,7 @@ __global__ void __launch_bounds__(kT4Threads, 1) lloyd_tc4_kernel(const Tc4Args 
       tc::nb_arrive(kNbAlo + (int)p2, 160);
       if (warp == 0) T4TRACE(j, 2);
       if (++s == R) { s = 0; full_ph ^= 1u; }
+    }
     }
   } else if (warp < 12) {
     // =============================== E: score the rows of tiles j = g (mod 2) ===============================
