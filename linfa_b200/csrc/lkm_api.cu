@@ -24,6 +24,7 @@
 #include "lkm_tc.cuh"
 #include "lkm_tc3.cuh"
 #include "lkm_tc4.cuh"
+#include "lkm_upd.cuh"
 
 #define LKM_EXPORT extern "C" __attribute__((visibility("default")))
 
@@ -96,6 +97,7 @@ struct lkm_ctx {
   // fused tcgen05 kernel for d = 32: 4 = TMA + warp-specialised pipeline, 3 = TMA + three worker groups
   // (both k <= 64; larger k falls back to 128), 128 / 256 / 544 = the earlier generations (LKM_TC_VARIANT)
   int tc_variant = 4;
+  int upd_variant = 1;   // LKM_UPD=0: cluster-chunked lloyd_kernel<MODE_UPDATE> instead of update_rows_kernel
   uint64_t data_epoch = 1, xmax2_epoch = 0;  // resident-data version / version the cached max row norm belongs to
   DevBuf xmax2, t4prof;
   int tc4_passes_forced = 0;              // LKM_TC4_PASSES = 2 / 3 pins the scoring passes of the pipeline kernel
@@ -389,6 +391,28 @@ static lkm_status make_row_tile_map(lkm_ctx* ctx, const float* dX, uint64_t n, C
   return LKM_OK;
 }
 
+// TMA descriptor of the resident f32 matrix for any row width: box_cols x box_rows boxes, no swizzle
+static lkm_status make_plain_tile_map(lkm_ctx* ctx, const float* dX, uint64_t n, uint64_t d, uint32_t box_cols, uint32_t box_rows,
+                                      CUtensorMap& map) {
+  static EncodeTiledFn encode = nullptr;
+  if (!encode) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    CK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+    if (!fn || qres != cudaDriverEntryPointSuccess) return fail(ctx, LKM_ERR_CUDA, "cuTensorMapEncodeTiled not available");
+    encode = reinterpret_cast<EncodeTiledFn>(fn);
+  }
+  const cuuint64_t dims[2] = {(cuuint64_t)d, (cuuint64_t)n};
+  const cuuint64_t strides[1] = {(cuuint64_t)d * 4};
+  const cuuint32_t box[2] = {box_cols, box_rows};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = encode(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(dX), dims, strides, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(ctx, LKM_ERR_CUDA, "cuTensorMapEncodeTiled failed");
+  return LKM_OK;
+}
+
 static cudaError_t launch_tc3(int kp, int grid, size_t smem, cudaStream_t s, const Tc3Args& arg, const CUtensorMap& map) {
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)grid);
@@ -556,7 +580,38 @@ static lkm_status run_lloyd(lkm_ctx* ctx, F* dC2, uint64_t k, uint64_t max_iter,
       }
     }
   }
-  const int grid = pf.fused ? pf.grid : pu.grid;
+  // streaming update pass (lkm_upd.cuh) behind the tensor-core assignment: the accumulators of a cluster chunk stay in
+  // shared memory, blockIdx.y walks the chunks (X is re-read once per chunk)
+  bool use_upd = false;
+  int upd_ny = 1, upd_chunk = (int)k, upd_stages = 0, upd_gx = 0;
+  size_t upd_smem = 0;
+  CUtensorMap upd_map;
+  std::memset(&upd_map, 0, sizeof(upd_map));
+  if constexpr (std::is_same<F, float>::value) {
+    if (use_tca && ctx->upd_variant != 0 && n + 64 < (1ull << 31)) {
+      const size_t limit = ctx->smem_optin - 1024;
+      int ny = 1;
+      for (; ny <= ctx->sm_count; ++ny)
+        if (upd_smem_bytes((int)d, (int)((k + ny - 1) / ny), 3) <= limit) break;
+      if (ny <= ctx->sm_count) {
+        upd_ny = ny;
+        upd_chunk = (int)((k + ny - 1) / ny);
+        upd_ny = (int)((k + upd_chunk - 1) / upd_chunk);
+        upd_stages = 3;
+        while (upd_stages < kUpdMaxStages && upd_smem_bytes((int)d, upd_chunk, upd_stages + 1) <= limit) ++upd_stages;
+        upd_smem = upd_smem_bytes((int)d, upd_chunk, upd_stages);
+        const uint64_t n_sub = (n + kUpdSubRows - 1) / kUpdSubRows;
+        upd_gx = (int)std::max<uint64_t>(1, std::min<uint64_t>(n_sub, (uint64_t)(ctx->sm_count / upd_ny)));
+        const void* fn = d == 32 ? (const void*)update_rows_kernel<32> : (d == 64 ? (const void*)update_rows_kernel<64> : (const void*)update_rows_kernel<128>);
+        CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)upd_smem));
+        CK(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
+        CKS(make_plain_tile_map(ctx, dX, n, d, 32, kUpdSubRows, upd_map));
+        CK(ctx->labels.ensure((n + 64) * 4));
+        use_upd = true;
+      }
+    }
+  }
+  const int grid = pf.fused ? pf.grid : (use_upd ? upd_gx : pu.grid);
   CK(ctx->part_sums.ensure((size_t)grid * kd * sizeof(F)));
   CK(ctx->part_counts.ensure((size_t)grid * k * 4));
   CK(ctx->part_inertia.ensure((size_t)std::max(grid, 1024) * 8));
@@ -668,11 +723,33 @@ static lkm_status run_lloyd(lkm_ctx* ctx, F* dC2, uint64_t k, uint64_t max_iter,
         CK((launch_lloyd<F, MODE_ASSIGN>(a, pa.grid, pa.smem, ctx->stream)));
         ctx->launches++;
         }
+        bool updated = false;
+        if constexpr (std::is_same<F, float>::value) {
+          if (use_upd) {
+            UpdArgs ua{};
+            ua.n = n; ua.k = (int)k; ua.chunk_rows = upd_chunk; ua.stages = upd_stages;
+            ua.labels = ctx->labels.as<uint32_t>(); ua.C = Ccur;
+            ua.part_sums = ctx->part_sums.as<float>(); ua.part_counts = ctx->part_counts.as<uint32_t>();
+            ua.part_inertia = ctx->part_inertia.as<double>(); ua.state = dstate;
+            cudaLaunchConfig_t cfg{};
+            cfg.gridDim = dim3((unsigned)upd_gx, (unsigned)upd_ny);
+            cfg.blockDim = dim3((unsigned)kUpdThreads);
+            cfg.dynamicSmemBytes = upd_smem;
+            cfg.stream = ctx->stream;
+            if (d == 32) CK(cudaLaunchKernelEx(&cfg, update_rows_kernel<32>, ua, upd_map));
+            else if (d == 64) CK(cudaLaunchKernelEx(&cfg, update_rows_kernel<64>, ua, upd_map));
+            else CK(cudaLaunchKernelEx(&cfg, update_rows_kernel<128>, ua, upd_map));
+            ctx->launches++;
+            updated = true;
+          }
+        }
+        if (!updated) {
         // inertia: fixed-order f64 partial sums of the min distances, one per source slot
         sum_f64_kernel<F><<<grid, 256, 0, ctx->stream>>>(ctx->dists.as<F>(), n, ctx->part_inertia.as<double>());
         CK(cudaGetLastError());
         ctx->launches += 1;
-        for (int ch = 0; ch < n_chunks; ++ch) {
+        }
+        for (int ch = 0; ch < (updated ? 0 : n_chunks); ++ch) {
           LloydArgs<F> u{};
           u.X = dX; u.n = n; u.d = (int)d; u.k = (int)k; u.labels_in = ctx->labels.as<uint32_t>();
           u.chunk_base = ch * chunk_rows;
@@ -690,6 +767,7 @@ static lkm_status run_lloyd(lkm_ctx* ctx, F* dC2, uint64_t k, uint64_t max_iter,
         fa.src_sums = ctx->part_sums.as<F>(); fa.src_counts = ctx->part_counts.as<uint32_t>();
         fa.src_inertia = ctx->part_inertia.as<double>();
         fa.sum_stride = kd; fa.cnt_stride = k; fa.inertia_stride = 1; fa.n_src = grid; fa.k = (int)k; fa.d = (int)d;
+        fa.n_src_inertia = use_upd ? upd_gx * upd_ny : 0;
         fa.C_old = Ccur; fa.C_new = Cnext; fa.counts_out = ctx->counts_out.as<double>();
         fa.shift_part = ctx->shift_part.as<double>(); fa.state = dstate; fa.tol = tol; fa.max_iter = max_iter;
         CK((launch_finalize<F, F, uint32_t, true>(fa, ctx->stream)));
@@ -699,6 +777,7 @@ static lkm_status run_lloyd(lkm_ctx* ctx, F* dC2, uint64_t k, uint64_t max_iter,
         ra.src_sums = ctx->part_sums.as<F>(); ra.src_counts = ctx->part_counts.as<uint32_t>();
         ra.src_inertia = ctx->part_inertia.as<double>();
         ra.sum_stride = kd; ra.cnt_stride = k; ra.inertia_stride = 1; ra.n_src = grid; ra.k = (int)k; ra.d = (int)d;
+        ra.n_src_inertia = use_upd ? upd_gx * upd_ny : 0;
         ra.rank_out = ctx->gather.as<double>() + (size_t)ctx->rank * L;
         ra.state = dstate;
         FinalizeArgs<F, double, double> fa{};
@@ -1609,6 +1688,7 @@ LKM_EXPORT lkm_status lkm_create(lkm_ctx** out, int device) {
   cudaDeviceProp prop;
   if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return bail(LKM_ERR_CUDA);
   if (const char* v = std::getenv("LKM_TC_VARIANT")) ctx->tc_variant = std::atoi(v);
+  if (const char* v = std::getenv("LKM_UPD")) ctx->upd_variant = std::atoi(v);
   if (const char* v = std::getenv("LKM_P2P")) ctx->p2p_enabled = std::atoi(v);
   if (const char* v = std::getenv("LKM_TC4_PASSES")) ctx->tc4_passes_forced = std::atoi(v);
   ctx->sm_count = prop.multiProcessorCount;

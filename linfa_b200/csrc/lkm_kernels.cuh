@@ -471,6 +471,7 @@ template <typename F, typename S, typename CT> struct FinalizeArgs {
   const double* src_inertia;  // source b at src_inertia[b*inertia_stride]
   size_t sum_stride, cnt_stride, inertia_stride;
   int n_src;
+  int n_src_inertia;   // inertia partials when their number differs from n_src (0 = n_src)
   int k, d;
   // reduce-only output (per-rank partial): [kd sums | k counts | 1 inertia] as f64
   double* rank_out;
@@ -590,7 +591,8 @@ __global__ void __launch_bounds__(kFinThreads) finalize_kernel(const FinalizeArg
   if (!UPDATE) {
     if (blockIdx.x == 0) {
       double v = 0.0;
-      for (int b = t; b < a.n_src; b += kFinThreads) v += a.src_inertia[(size_t)b * a.inertia_stride];
+      const int n_in = a.n_src_inertia ? a.n_src_inertia : a.n_src;
+      for (int b = t; b < n_in; b += kFinThreads) v += a.src_inertia[(size_t)b * a.inertia_stride];
       const double tot = block_sum(v, red);
       if (t == 0) {
         if (a.n_peers > 0) { for (int p = 0; p < a.n_peers; ++p) a.peer_out[p][kd + a.k] = tot; }
@@ -629,7 +631,8 @@ __global__ void __launch_bounds__(kFinThreads) finalize_kernel(const FinalizeArg
   for (int b = t; b < (int)gridDim.x; b += kFinThreads) v += ((volatile double*)a.shift_part)[b];
   const double shift_sq = block_sum(v, red);
   v = 0.0;
-  for (int b = t; b < a.n_src; b += kFinThreads) v += a.src_inertia[(size_t)b * a.inertia_stride];
+  const int n_in = a.n_src_inertia ? a.n_src_inertia : a.n_src;
+  for (int b = t; b < n_in; b += kFinThreads) v += a.src_inertia[(size_t)b * a.inertia_stride];
   const double inertia = block_sum(v, red);
   if (t == 0) {
     const F shift = (F)sqrt(shift_sq);  // L2Dist::distance: sqrt in f64, cast to F

@@ -1,0 +1,197 @@
+// Centroid-update pass of the two-pass Lloyd iteration for wide rows / many clusters (f32, d = 32, 64 or 128):
+// given the labels of the assignment pass, per-CTA partial sums, counts and inertia for finalize_kernel
+// (compute_centroids, KM/algorithm.rs:785-810, and dists.sum(), :329).  HBM-bound: X is streamed once per
+// cluster chunk through a TMA ring; the accumulators of the whole chunk (chunk_rows x d f32) stay in shared memory.
+//
+// Deterministic without atomics: every accumulator element has ONE owning thread.  A 32-row sub-tile is handled
+// by 16 consumer warps; warp w = (class, feature slice) owns the clusters c with c % NCLS == class and the 32
+// features of its slice (lane = feature), walks the sub-tiles of the CTA in ascending order and, per sub-tile,
+// sums the rows of each of its clusters in registers (row order) before ONE read-modify-write of the shared
+// accumulator.  Blob-ordered data gives one segment of 32 rows per sub-tile; shuffled data gives many one-row
+// segments, taken four at a time so that their centroid loads and read-modify-writes overlap.
+//
+//   P  warp 16      one thread keeps the ring full: d/32 TMA boxes (32 rows x 32 features, row-major) and the
+//                   128 label bytes of the sub-tile per stage
+//   C  warps 0-15   as above; the stage is released when all 16 warps have arrived on its `empty` barrier
+#pragma once
+#include "lkm_tc3.cuh"
+
+namespace lkm {
+
+constexpr int kUpdConsumers = 16;
+constexpr int kUpdThreads = (kUpdConsumers + 1) * 32;
+constexpr int kUpdSubRows = 32;
+constexpr int kUpdMaxStages = 8;
+
+struct UpdArgs {
+  unsigned long long n;
+  int k;
+  int chunk_rows;              // clusters per chunk; blockIdx.y = chunk, chunk c owns [c * chunk_rows, ...)
+  int stages;
+  const uint32_t* labels;      // n labels; the allocation is readable up to the next multiple of 32 rows
+  const float* C;              // k x d, the centroids the labels were computed against (inertia)
+  float* part_sums;            // [gridDim.x][k * d]
+  uint32_t* part_counts;       // [gridDim.x][k]
+  double* part_inertia;        // [gridDim.y][gridDim.x]
+  const LloydState* state;
+};
+
+__host__ __device__ inline size_t upd_stage_bytes(int d) { return (size_t)kUpdSubRows * d * 4 + 128; }
+__host__ __device__ inline size_t upd_smem_bytes(int d, int chunk_rows, int stages) {
+  return (size_t)stages * upd_stage_bytes(d) + (size_t)chunk_rows * d * 4 + (size_t)chunk_rows * 4 + kUpdThreads * 8 + 256;
+}
+
+namespace tc {
+// 1-D bulk copy global -> shared, completion on an mbarrier (bytes and both addresses multiples of 16)
+__device__ __forceinline__ void bulk_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+}  // namespace tc
+
+template <int D>
+__global__ void __launch_bounds__(kUpdThreads, 1) update_rows_kernel(const UpdArgs a, const __grid_constant__ CUtensorMap tmap) {
+  static_assert(D == 32 || D == 64 || D == 128, "row width");
+  constexpr int QF = D / 32;                 // feature slices
+  constexpr int NCLS = kUpdConsumers / QF;   // cluster classes
+  constexpr uint32_t kStage = (uint32_t)kUpdSubRows * D * 4 + 128;
+  if (a.state != nullptr && a.state->done) return;
+  extern __shared__ __align__(16) unsigned char smem_unaligned[];
+  unsigned char* smem = smem_unaligned + ((128u - (tc::smem_u32(smem_unaligned) & 127u)) & 127u);
+  const int t = threadIdx.x, lane = t & 31;
+  const int warp = __shfl_sync(0xffffffffu, t >> 5, 0);
+  const int R = a.stages;
+  const int chunk_base = (int)blockIdx.y * a.chunk_rows;
+  const int chunk_rows = min(a.chunk_rows, a.k - chunk_base);
+  unsigned char* ring = smem;                                                // [R][32 x D f32 | 32 labels]
+  float* acc = reinterpret_cast<float*>(ring + (size_t)R * kStage);          // [chunk_rows][D]
+  uint32_t* cnt = reinterpret_cast<uint32_t*>(acc + (size_t)a.chunk_rows * D);
+  double* red = reinterpret_cast<double*>(cnt + ((a.chunk_rows + 1) & ~1));
+  __shared__ __align__(8) uint64_t bar_full[kUpdMaxStages], bar_empty[kUpdMaxStages];
+
+  // contiguous range of sub-tiles per CTA column (ascending row order inside every accumulator)
+  const unsigned long long n_sub = (a.n + kUpdSubRows - 1) / kUpdSubRows;
+  const unsigned long long per = (n_sub + gridDim.x - 1) / gridDim.x;
+  const unsigned long long j0 = min(n_sub, per * blockIdx.x), j1 = min(n_sub, j0 + per);
+
+  if (t == 0) {
+    for (int s = 0; s < kUpdMaxStages; ++s) {
+      tc::mbar_init(&bar_full[s], 1);
+      tc::mbar_init(&bar_empty[s], kUpdConsumers);
+    }
+    tc::fence_mbar_init();
+  }
+  for (int e = t; e < chunk_rows * D; e += kUpdThreads) acc[e] = 0.f;
+  for (int e = t; e < chunk_rows; e += kUpdThreads) cnt[e] = 0u;
+  __syncthreads();
+
+  double inert = 0.0;
+  if (warp == kUpdConsumers) {
+    if (lane == 0) {
+      int s = 0;
+      uint32_t use = 0;
+      for (unsigned long long j = j0; j < j1; ++j) {
+        if (use > 0) tc::mbar_wait_or_trap(&bar_empty[s], (use - 1u) & 1u);
+        unsigned char* st = ring + (size_t)s * kStage;
+        tc::mbar_expect_tx(&bar_full[s], kStage);
+#pragma unroll
+        for (int q = 0; q < QF; ++q) tc::tma_load_2d(st + q * 4096, &tmap, q * 32, (int)(j * kUpdSubRows), &bar_full[s]);
+        tc::bulk_load_1d(st + QF * 4096, a.labels + j * kUpdSubRows, 128u, &bar_full[s]);
+        if (++s == R) { s = 0; ++use; }
+      }
+    }
+  } else {
+    const int fs = warp % QF, cls = warp / QF;
+    const int fo = fs * 32 + lane;             // feature owned by this lane
+    const float* Cf = a.C + (size_t)chunk_base * D + fo;
+    float* accf = acc + fo;
+    int s = 0;
+    uint32_t ph = 0;
+    for (unsigned long long j = j0; j < j1; ++j) {
+      const unsigned char* st = ring + (size_t)s * kStage;
+      tc::mbar_wait_or_trap(&bar_full[s], ph);
+      const float* xs = reinterpret_cast<const float*>(st + fs * 4096) + lane;   // row r at xs[r * 32]
+      uint32_t lab = reinterpret_cast<const uint32_t*>(st + QF * 4096)[lane];
+      if (j * kUpdSubRows + (unsigned)lane >= a.n) lab = 0xFFFFFFFFu;
+      const uint32_t c = lab - (uint32_t)chunk_base;
+      const bool mine = c < (uint32_t)chunk_rows && (int)(c % (uint32_t)NCLS) == cls;
+      uint32_t m = __ballot_sync(0xffffffffu, mine);
+      while (m) {
+        // up to four segments (clusters of this warp present in the sub-tile) at a time
+        uint32_t pm[4], L[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          pm[q] = 0u; L[q] = 0u;
+          if (m) {
+            L[q] = __shfl_sync(0xffffffffu, c, __ffs(m) - 1);
+            pm[q] = __ballot_sync(0xffffffffu, mine && c == L[q]);
+            m &= ~pm[q];
+          }
+        }
+        float cv[4], av[4], sv[4], ev[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          cv[q] = 0.f; av[q] = 0.f;
+          if (pm[q]) { cv[q] = __ldg(Cf + (size_t)L[q] * D); av[q] = accf[(size_t)L[q] * D]; }
+        }
+        if (pm[0] == 0xffffffffu) {
+          // the whole sub-tile belongs to one cluster: two interleaved chains (even / odd rows), fixed order
+          float s0 = 0.f, s1 = 0.f, e0 = 0.f, e1 = 0.f;
+#pragma unroll
+          for (int r = 0; r < kUpdSubRows; r += 2) {
+            const float x0 = xs[r * 32], x1 = xs[(r + 1) * 32];
+            s0 += x0; s1 += x1;
+            const float d0 = x0 - cv[0], d1 = x1 - cv[0];
+            e0 = fmaf(d0, d0, e0); e1 = fmaf(d1, d1, e1);
+          }
+          sv[0] = s0 + s1; ev[0] = e0 + e1;
+          sv[1] = sv[2] = sv[3] = 0.f; ev[1] = ev[2] = ev[3] = 0.f;
+        } else {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            float sq = 0.f, eq = 0.f;
+            uint32_t p = pm[q];
+            while (p) {
+              const int r = __ffs(p) - 1;
+              p &= p - 1u;
+              const float x = xs[r * 32];
+              sq += x;
+              const float df = x - cv[q];
+              eq = fmaf(df, df, eq);
+            }
+            sv[q] = sq; ev[q] = eq;
+          }
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          if (pm[q]) {
+            accf[(size_t)L[q] * D] = av[q] + sv[q];
+            inert += (double)ev[q];
+            if (fs == 0 && lane == 0) cnt[L[q]] += (uint32_t)__popc(pm[q]);
+          }
+        }
+      }
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(&bar_empty[s]);
+      if (++s == R) { s = 0; ph ^= 1u; }
+    }
+  }
+  // ---- per-CTA partials: accumulators as they are, inertia by warp butterflies and then in warp order ----
+  for (int o = 16; o > 0; o >>= 1) inert += __shfl_xor_sync(0xffffffffu, inert, o);
+  if (lane == 0) red[warp] = inert;
+  __syncthreads();
+  const size_t kd = (size_t)a.k * D;
+  float* ps = a.part_sums + (size_t)blockIdx.x * kd + (size_t)chunk_base * D;
+  for (int e = t; e < chunk_rows * D / 4; e += kUpdThreads)
+    reinterpret_cast<float4*>(ps)[e] = reinterpret_cast<const float4*>(acc)[e];
+  uint32_t* pc = a.part_counts + (size_t)blockIdx.x * a.k + chunk_base;
+  for (int e = t; e < chunk_rows; e += kUpdThreads) pc[e] = cnt[e];
+  if (t == 0) {
+    double tot = 0.0;
+    for (int e = 0; e < kUpdConsumers; ++e) tot += red[e];
+    a.part_inertia[(size_t)blockIdx.y * gridDim.x + blockIdx.x] = tot;
+  }
+}
+
+}  // namespace lkm

@@ -476,14 +476,21 @@ def test_tc_path_is_reproducible(lb, ctx):
 
 
 # ---- tensor-core assignment for wide rows / many clusters (two-pass: tc_assign_kernel + update pass) ----
-TCA_CASES = [(6000, 128, 256, 16, 30.0), (5000, 64, 1024, 40, 30.0), (3000, 128, 300, 10, 1.0), (2500, 64, 700, 5, 0.5),
-             (1000, 128, 1024, 7, 30.0)]
+TCA_CASES = [(6000, 128, 256, 16, 30.0, False), (5000, 64, 1024, 40, 30.0, False), (3000, 128, 300, 10, 1.0, False),
+             (2500, 64, 700, 5, 0.5, False), (1000, 128, 1024, 7, 30.0, False),
+             # update_rows_kernel: several sub-tiles per CTA with a ragged tail, blob order (one segment per sub-tile) and
+             # shuffled rows (many one-row segments), one / two / four cluster chunks
+             (148 * 32 * 3 + 19, 128, 256, 256, 30.0, False), (148 * 32 * 3 + 19, 128, 256, 256, 30.0, True),
+             (40000, 64, 1024, 64, 30.0, True), (30001, 128, 1000, 50, 30.0, True), (20000, 64, 512, 300, 30.0, True),
+             (2047, 64, 300, 3, 30.0, False)]
 
 
-@pytest.mark.parametrize("n,d,k,k_true,spread", TCA_CASES)
-def test_tc_assign_path_matches_oracle(lb, ctx, oracle, n, d, k, k_true, spread):
+@pytest.mark.parametrize("n,d,k,k_true,spread,shuffle", TCA_CASES)
+def test_tc_assign_path_matches_oracle(lb, ctx, oracle, n, d, k, k_true, spread, shuffle):
     dt = np.float32
     X, _ = blobs(n, d, k_true, dt, seed=n + k, spread=spread)
+    if shuffle:
+        X = X[np.random.default_rng(5).permutation(n)].copy()
     g = np.random.default_rng(k)
     init = X[g.choice(n, size=k, replace=k > n)].copy()
     if k > n:
