@@ -25,6 +25,7 @@
 #include "lkm_tc3.cuh"
 #include "lkm_tc4.cuh"
 #include "lkm_upd.cuh"
+#include "lkm_tc5.cuh"
 
 #define LKM_EXPORT extern "C" __attribute__((visibility("default")))
 
@@ -97,6 +98,7 @@ struct lkm_ctx {
   // fused tcgen05 kernel for d = 32: 4 = TMA + warp-specialised pipeline, 3 = TMA + three worker groups
   // (both k <= 64; larger k falls back to 128), 128 / 256 / 544 = the earlier generations (LKM_TC_VARIANT)
   int tc_variant = 4;
+  int tc5_enabled = 1;   // LKM_TC5=0: tc_assign_kernel instead of the CTA-pair assignment kernel
   int upd_variant = 1;   // LKM_UPD=0: cluster-chunked lloyd_kernel<MODE_UPDATE> instead of update_rows_kernel
   uint64_t data_epoch = 1, xmax2_epoch = 0;  // resident-data version / version the cached max row norm belongs to
   DevBuf xmax2, t4prof;
@@ -371,7 +373,7 @@ static lkm_status p2p_setup(lkm_ctx* ctx, size_t L) {
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-static lkm_status make_row_tile_map(lkm_ctx* ctx, const float* dX, uint64_t n, CUtensorMap& map) {
+static lkm_status make_row_tile_map(lkm_ctx* ctx, const float* dX, uint64_t n, CUtensorMap& map, uint64_t d = 32) {
   static EncodeTiledFn encode = nullptr;
   if (!encode) {
     void* fn = nullptr;
@@ -380,8 +382,8 @@ static lkm_status make_row_tile_map(lkm_ctx* ctx, const float* dX, uint64_t n, C
     if (!fn || qres != cudaDriverEntryPointSuccess) return fail(ctx, LKM_ERR_CUDA, "cuTensorMapEncodeTiled not available");
     encode = reinterpret_cast<EncodeTiledFn>(fn);
   }
-  const cuuint64_t dims[2] = {32, (cuuint64_t)n};
-  const cuuint64_t strides[1] = {128};
+  const cuuint64_t dims[2] = {(cuuint64_t)d, (cuuint64_t)n};
+  const cuuint64_t strides[1] = {(cuuint64_t)d * 4};
   const cuuint32_t box[2] = {32, (cuuint32_t)kTcRows};
   const cuuint32_t estr[2] = {1, 1};
   const CUresult r = encode(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(dX), dims, strides, box, estr,
@@ -534,6 +536,13 @@ static lkm_status run_lloyd(lkm_ctx* ctx, F* dC2, uint64_t k, uint64_t max_iter,
   Plan pf;
   CKS(plan_fused<F>(ctx, dX, n, d, k, pf));
   if (use_tc) { pf.fused = true; pf.grid = tc_grid; }
+  if constexpr (std::is_same<F, float>::value) {
+    // shapes of the CTA-pair assignment kernel: two-pass (tensor-core assignment + streaming update) even when the
+    // centroids would fit the fused CUDA-core kernel, unless the contraction is tiny
+    if (!use_tc && (ctx->force_path == -1 || ctx->force_path == 2) && ctx->tc5_enabled && ctx->upd_variant != 0 &&
+        (d == 64 || d == 128) && k <= (uint64_t)kT5K && kd >= 2048 && n >= 1 && (reinterpret_cast<uintptr_t>(dX) & 15) == 0)
+      pf.fused = false;
+  }
   ctx->last_path = use_tc ? 2 : ((pf.fused && pf.certified) ? 1 : 0);
   Plan pa, pu;
   int n_chunks = 1, chunk_rows = (int)k;
@@ -609,6 +618,33 @@ static lkm_status run_lloyd(lkm_ctx* ctx, F* dC2, uint64_t k, uint64_t max_iter,
         CK(ctx->labels.ensure((n + 64) * 4));
         use_upd = true;
       }
+    }
+  }
+  // CTA-pair assignment kernel (lkm_tc5.cuh): all centroid operand tiles resident across the two CTAs of a cluster
+  bool use_tc5 = false;
+  int tc5_grid = 0;
+  size_t tc5_smem = 0;
+  CUtensorMap tc5_map;
+  std::memset(&tc5_map, 0, sizeof(tc5_map));
+  if constexpr (std::is_same<F, float>::value) {
+    if (use_upd && ctx->tc5_enabled && (d == 64 || d == 128) && k <= (uint64_t)kT5K && n + 512 < (1ull << 31) &&
+        tc5_smem_bytes((int)d) <= ctx->smem_optin) {
+      tc5_smem = tc5_smem_bytes((int)d);
+      const void* fn = d == 64 ? (const void*)assign_tc5_kernel<64> : (const void*)assign_tc5_kernel<128>;
+      CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc5_smem));
+      CK(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
+      CKS(make_row_tile_map(ctx, dX, n, tc5_map, d));
+      if (!ctx->own_X || ctx->xmax2_epoch != ctx->data_epoch) {
+        CK(ctx->xmax2.ensure(16));
+        CK(cudaMemsetAsync(ctx->xmax2.p, 0, 4, ctx->stream));
+        row_norm2_max_wide_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(dX, n, (int)d, ctx->xmax2.as<unsigned int>());
+        CK(cudaGetLastError());
+        ctx->launches++;
+        ctx->xmax2_epoch = ctx->data_epoch;
+      }
+      const uint64_t n_pt = ((n + 127) / 128 + 1) / 2;
+      tc5_grid = 2 * (int)std::max<uint64_t>(1, std::min<uint64_t>(n_pt, (uint64_t)(ctx->sm_count / 2)));
+      use_tc5 = true;
     }
   }
   const int grid = pf.fused ? pf.grid : (use_upd ? upd_gx : pu.grid);
@@ -698,7 +734,16 @@ static lkm_status run_lloyd(lkm_ctx* ctx, F* dC2, uint64_t k, uint64_t max_iter,
       } else {
         bool assigned = false;
         if constexpr (std::is_same<F, float>::value) {
-          if (use_tca) {
+          if (use_tc5) {
+            Tc5Args t5{};
+            t5.X = dX; t5.n = n; t5.k = (int)k; t5.C = Ccur; t5.xmax2_bits = ctx->xmax2.as<unsigned int>();
+            t5.labels = ctx->labels.as<uint32_t>(); t5.state = dstate;
+            if (d == 64) assign_tc5_kernel<64><<<tc5_grid, kT5Threads, tc5_smem, ctx->stream>>>(t5, tc5_map);
+            else assign_tc5_kernel<128><<<tc5_grid, kT5Threads, tc5_smem, ctx->stream>>>(t5, tc5_map);
+            CK(cudaGetLastError());
+            ctx->launches++;
+            assigned = true;
+          } else if (use_tca) {
             // tensor-core assignment: split the centroids into TF32 operand tiles, then score
             CK(cudaMemsetAsync(ctx->tca_cmax.p, 0, 4, ctx->stream));
             tc_prep_centroids_kernel<<<tca_chunks * tca_ka, 64, 0, ctx->stream>>>(Ccur, (int)k, (int)d, tca_ka, ctx->tca_bsplit.as<unsigned char>(),
@@ -1689,6 +1734,7 @@ LKM_EXPORT lkm_status lkm_create(lkm_ctx** out, int device) {
   if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return bail(LKM_ERR_CUDA);
   if (const char* v = std::getenv("LKM_TC_VARIANT")) ctx->tc_variant = std::atoi(v);
   if (const char* v = std::getenv("LKM_UPD")) ctx->upd_variant = std::atoi(v);
+  if (const char* v = std::getenv("LKM_TC5")) ctx->tc5_enabled = std::atoi(v);
   if (const char* v = std::getenv("LKM_P2P")) ctx->p2p_enabled = std::atoi(v);
   if (const char* v = std::getenv("LKM_TC4_PASSES")) ctx->tc4_passes_forced = std::atoi(v);
   ctx->sm_count = prop.multiProcessorCount;

@@ -1,0 +1,455 @@
+// Tensor-core ASSIGNMENT for wide rows (f32, d = 64 or 128, k <= 256) on CTA PAIRS — cfg3 shape.
+//
+// update_memberships_and_dists / closest_centroid (KM/algorithm.rs:866-881, 923-946) as one 256 x 256 x d
+// 3xTF32 contraction per pair of 128-row tiles: the two CTAs of a cluster run tcgen05.mma.cta_group::2, each
+// supplying its own 128 rows of X (A operand, in its TMEM) and HALF of the centroids (B operand, 128 rows of
+// hi / lo / bias tiles resident in its shared memory for the whole launch), so the 2 x k x d x 4 bytes of
+// centroid operands fit on chip once and no operand is re-staged per tile.  Per CTA, 10 warps:
+//
+//   P  warp 9     one thread streams the tile through a ring of four 32-feature slabs (TMA, SWIZZLE_128B)
+//   S  warps 0-3  thread = row: slab -> TMEM, once as raw bits (= x_hi: kind::tf32 ignores the 13 low mantissa
+//                 bits) and once as x_lo = x - trunc(x)
+//   M  warp 8     (leader CTA only) 3 d/8 + 1 MMAs of M = 256, N = 256 into the 256 accumulator columns of both
+//                 CTAs:  x_lo.c_hi + x_hi.c_lo + x_hi.c_hi + ones.(K0 - |c|^2/2)  ->  v_c = x.c - |c|^2/2 + K0;
+//                 one multicast commit signals both CTAs
+//   E  warps 4-7  thread = row: packed integer top-2 of the 256 scores (q = bits(v) << 8 | c, every v inside
+//                 one 4x window so that the shifted bits stay monotone), certificate (v-form), label;
+//                 uncertified rows are re-scanned in the reference's exact arithmetic, one warp per row
+//
+// TMEM (512 columns): accumulator 256 | A_hi d | A_lo d.  The roles of the two CTAs meet at three barriers of
+// the leader (A operands ready: 8 S warps; accumulator drained: 8 E warps) and at the multicast MMA commit.
+// Labels only: the update pass (lkm_upd.cuh) reads X again and produces sums, counts and inertia.
+#pragma once
+#include "lkm_tc4.cuh"
+
+namespace lkm {
+
+constexpr int kT5Threads = 10 * 32;
+constexpr int kT5Stages = 4;
+constexpr uint32_t kT5ColAcc = 0, kT5ColA = 256;
+constexpr int kT5K = 256;   // score columns = centroid rows of one MMA (128 per CTA)
+
+struct Tc5Args {
+  const float* X;
+  unsigned long long n;
+  int k;
+  const float* C;
+  const unsigned int* xmax2_bits;   // max_i |x_i|^2 of the resident matrix (row_norm2_max_wide_kernel)
+  uint32_t* labels;
+  LloydState* state;
+};
+
+__host__ __device__ inline size_t tc5_smem_bytes(int d) {
+  return (size_t)kT5Stages * 16384 + (size_t)(d / 32) * 16384 * 2 + 16384 + 1024 + kT5K * 4 + 2 * 128 * 4 + 1024;
+}
+
+// max_i |x_i|^2 for any row width (d % 4 == 0): one warp per row; a non-finite norm is published as NaN bits
+__global__ void __launch_bounds__(256) row_norm2_max_wide_kernel(const float* __restrict__ X, unsigned long long n, int d,
+                                                                 unsigned int* __restrict__ out_bits) {
+  const int lane = threadIdx.x & 31;
+  const unsigned long long w0 = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const unsigned long long nw = ((unsigned long long)gridDim.x * blockDim.x) >> 5;
+  float m = 0.f;
+  bool bad = false;
+  for (unsigned long long r = w0; r < n; r += nw) {
+    const float4* p = reinterpret_cast<const float4*>(X + r * (unsigned long long)d);
+    float s = 0.f;
+    for (int q = lane; q < d / 4; q += 32) {
+      const float4 v = __ldg(p + q);
+      s = fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, fmaf(v.w, v.w, s))));
+    }
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    bad |= !(s <= 3.0e38f);
+    m = fmaxf(m, s);
+  }
+  if (lane == 0) atomicMax(out_bits, bad ? 0x7FC00000u : __float_as_uint(m));
+}
+
+namespace tc {
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive on the mbarrier at the same shared-memory offset in CTA `cta` of the cluster
+__device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t cta) {
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}"
+      ::"r"(smem_u32(bar)), "r"(cta)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t* slot, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(cols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+// M = 256 over the CTA pair; the whole (leader) warp executes these, one elected lane issues
+__device__ __forceinline__ void mma2_tf32_ts_elect(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "@q tcgen05.mma.cta_group::2.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accum)
+      : "memory");
+}
+__device__ __forceinline__ void mma2_tf32_elect(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "@q tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accum)
+      : "memory");
+}
+// one arrival on the mbarrier at this offset in BOTH CTAs once every MMA issued so far has completed
+__device__ __forceinline__ void mma2_commit_elect(uint64_t* bar) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\t.reg .b16 m;\n\t"
+      "mov.b16 m, 3;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "@q tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], m;\n\t}"
+      ::"r"(smem_u32(bar))
+      : "memory");
+}
+}  // namespace tc
+
+template <int D>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kT5Threads, 1)
+    assign_tc5_kernel(const Tc5Args a, const __grid_constant__ CUtensorMap tmap) {
+  static_assert(D == 64 || D == 128, "row width");
+  constexpr int NS = D / 32;    // 32-feature slabs per tile
+  constexpr int KS = D / 8;     // K-steps per product
+  if (a.state != nullptr && a.state->done) return;
+  extern __shared__ __align__(16) unsigned char smem_unaligned[];
+  unsigned char* smem = smem_unaligned + ((1024u - (tc::smem_u32(smem_unaligned) & 1023u)) & 1023u);
+  const int t = threadIdx.x, lane = t & 31;
+  const int warp = __shfl_sync(0xffffffffu, t >> 5, 0);
+  const int k = a.k;
+  const uint32_t rank = tc::cluster_ctarank();
+  unsigned char* ring = smem;                                   // [kT5Stages][16 KB] raw slabs
+  unsigned char* b_hi = ring + (size_t)kT5Stages * 16384;       // [NS][16 KB]: this CTA's 128 centroids, K-major SW128
+  unsigned char* b_lo = b_hi + (size_t)NS * 16384;
+  unsigned char* b_bias = b_lo + (size_t)NS * 16384;            // K-step 0 only
+  unsigned char* ones = b_bias + 16384;                         // constant A operand of the bias K-step (1 KB atom)
+  float* nn_s = reinterpret_cast<float*>(ones + 1024);          // [256] squared norms of all centroids
+  uint32_t* flags_all = reinterpret_cast<uint32_t*>(nn_s + kT5K);   // [2][128] uncertified rows of the current / previous tile
+  __shared__ __align__(8) uint64_t bar_full[kT5Stages], bar_empty[kT5Stages], bar_aready, bar_mma, bar_accfree;
+  __shared__ uint32_t tmem_slot, n_flag[2], cmax_bits;
+
+  // pair-tile pt = two consecutive 128-row tiles; CTA `rank` of the pair takes tile 2 pt + rank
+  const unsigned long long n_tiles = (a.n + 127) / 128;
+  const unsigned long long n_pt = (n_tiles + 1) / 2;
+  const unsigned long long pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+  const unsigned long long my_pt = pair < n_pt ? (n_pt - pair + n_pairs - 1) / n_pairs : 0;
+  auto tile_of = [&](unsigned long long it) { return 2ull * (pair + it * n_pairs) + rank; };
+
+  if (warp == 8) tc::tmem_alloc_pair(&tmem_slot, 512);
+  if (t == 0) {
+    for (int s = 0; s < kT5Stages; ++s) {
+      tc::mbar_init(&bar_full[s], 1);
+      tc::mbar_init(&bar_empty[s], 4);
+    }
+    tc::mbar_init(&bar_aready, 8);
+    tc::mbar_init(&bar_mma, 1);
+    tc::mbar_init(&bar_accfree, 8);
+    tc::fence_mbar_init();
+    n_flag[0] = 0;
+    n_flag[1] = 0;
+    cmax_bits = 0;
+  }
+  for (int e = t; e < 1024 + 64; e += kT5Threads) reinterpret_cast<float4*>(b_bias)[e] = make_float4(0.f, 0.f, 0.f, 0.f);   // bias tile + ones atom
+  __syncthreads();
+  // ---- squared norms of all centroids (8 threads per row), max norm ----
+  for (int base = 0; base < kT5K * 8; base += kT5Threads) {
+    const int item = base + t;
+    const int r = item >> 3, c8 = item & 7;
+    float nn = 0.f;
+    if (item < kT5K * 8 && r < k) {
+#pragma unroll
+      for (int q = 0; q < D / 32; ++q) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(a.C + (size_t)r * D) + c8 + 8 * q);
+        nn = fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, fmaf(v.w, v.w, nn))));
+      }
+    }
+    nn += __shfl_xor_sync(0xffffffffu, nn, 1);
+    nn += __shfl_xor_sync(0xffffffffu, nn, 2);
+    nn += __shfl_xor_sync(0xffffffffu, nn, 4);
+    if (item < kT5K * 8 && c8 == 0) {
+      nn_s[r] = nn;   // |nn - |c|^2| <= (d + 1) 2^-24 |c|^2 whatever the summation order
+      if (r < k) atomicMax(&cmax_bits, __float_as_uint(nn));   // a NaN norm wins and voids every certificate
+    }
+  }
+  // ---- this CTA's half of the centroids as TF32 hi / lo operand slabs ----
+  for (int item = t; item < 128 * NS * 8; item += kT5Threads) {
+    const int q = item & 7, s = (item >> 3) % NS, r = item / (8 * NS);
+    const int c = (int)rank * 128 + r;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (c < k) v = __ldg(reinterpret_cast<const float4*>(a.C + (size_t)c * D + s * 32) + q);
+    float4 h, l;
+    tc::split_tf32(v.x, h.x, l.x); tc::split_tf32(v.y, h.y, l.y);
+    tc::split_tf32(v.z, h.z, l.z); tc::split_tf32(v.w, h.w, l.w);
+    const uint32_t o = (uint32_t)s * 16384u + tc::sw128_offset((uint32_t)r, (uint32_t)q);
+    *reinterpret_cast<float4*>(b_hi + o) = h;
+    *reinterpret_cast<float4*>(b_lo + o) = l;
+  }
+  __syncthreads();
+  // ---- window, bias, margin (identical in every thread of both CTAs) ----
+  const float xmax2 = __uint_as_float(__ldg(a.xmax2_bits));
+  const float cmax2 = __uint_as_float(cmax_bits) * 1.00001f;
+  const float cmax = sqrtf(cmax2) * 1.000001f;
+  const float xmax = sqrtf(xmax2) * 1.000001f;
+  const float Rb = 1.01f * (xmax * cmax + 0.5f * cmax2) + 1e-30f;   // |x.c - |c|^2/2| <= Rb
+  const bool params_ok = Rb < 1e30f;   // false for NaN / Inf: every row then takes the exact scan
+  // smallest even exponent field e with 2^e >= Rb; K0 = 2^(e+1), so v = x.c - |c|^2/2 + K0 lies in [2^e, 3 * 2^e):
+  // exponent field e or e + 1, the top 8 bits of every score are the same and (bits << 8) stays monotone
+  uint32_t e_w = ((__float_as_uint(Rb) >> 23) + 2u) & ~1u;
+  e_w = min(max(e_w, 2u), 250u);
+  const float K0 = __uint_as_float((e_w + 1u) << 23);
+  const uint32_t top_bits = (e_w << 23) & 0xFF000000u;
+  const float eta = (3.f * (float)D + 12.f) * 2.3841858e-7f;   // (3d + 12) * 2^-22
+  const float gamma = ((float)D + 2.f) * 5.9604645e-8f;        // (d + 2) * 2^-24
+  const float m_w = 1.1f * (2.3841858e-7f * cmax2 + xmax * (4.f * eta + 4.7683716e-7f) * cmax +
+                            2.f * gamma * (xmax + cmax) * (xmax + cmax));
+  const float m_v = 0.5f * m_w + 7.f * 1.1920929e-7f * (K0 + Rb) + ((float)D + 1.f) * 5.9604645e-8f * cmax2;
+  if (t < 128) {
+    // bias row t: K0 - |c|^2/2 as three TF32 pieces that add up to the f32 value exactly
+    const int c = (int)rank * 128 + t;
+    const float b = (c < k) ? (K0 - 0.5f * nn_s[c]) : __uint_as_float(e_w << 23);
+    const float h = tc::trunc_tf32(b);
+    const float l = b - h;
+    const float l1 = tc::trunc_tf32(l);
+    const float l2 = l - l1;
+    float* p = reinterpret_cast<float*>(b_bias + tc::sw128_offset((uint32_t)t, 0));
+    p[0] = h; p[1] = l1; p[2] = l2;
+    if (t < 8) {
+      float* o1 = reinterpret_cast<float*>(ones + tc::sw128_offset((uint32_t)t, 0));
+      o1[0] = 1.f; o1[1] = 1.f; o1[2] = 1.f;
+    }
+  }
+  tc::fence_async_smem();
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::cluster_sync_all();   // both CTAs: barriers initialised, operand tiles written, TMEM allocated
+  tc::tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+  unsigned int my_fallbacks = 0;
+
+  if (warp == 9) {
+    // =============================== P: stream the slabs ===============================
+    if (lane == 0) {
+      int s = 0;
+      uint32_t use = 0;
+      for (unsigned long long it = 0; it < my_pt; ++it) {
+        const unsigned long long tile = min(tile_of(it), n_tiles - 1);   // a pair-tile past the end re-reads the last tile
+        for (int sl = 0; sl < NS; ++sl) {
+          if (use > 0) tc::mbar_wait_or_trap(&bar_empty[s], (use - 1u) & 1u);
+          tc::mbar_expect_tx(&bar_full[s], 16384u);
+          tc::tma_load_2d(ring + (size_t)s * 16384, &tmap, sl * 32, (int)(tile * 128), &bar_full[s]);
+          if (++s == kT5Stages) { s = 0; ++use; }
+        }
+      }
+    }
+  } else if (warp == 8) {
+    // =============================== M: issue the MMAs (leader CTA) ===============================
+    if (rank == 0) {
+      constexpr uint32_t idesc = tc::idesc_tf32(256, (uint32_t)kT5K);
+      const uint64_t desc_bhi = tc::smem_desc_sw128(tc::smem_u32(b_hi));
+      const uint64_t desc_blo = tc::smem_desc_sw128(tc::smem_u32(b_lo));
+      const uint64_t desc_bias = tc::smem_desc_sw128(tc::smem_u32(b_bias));
+      const uint64_t desc_ones = tc::smem_desc_sw128_alias(tc::smem_u32(ones));
+      const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem, 0);
+      const uint32_t dcol = tmem_u + kT5ColAcc, a_hi = tmem_u + kT5ColA, a_lo = tmem_u + kT5ColA + (uint32_t)D;
+      for (unsigned long long it = 0; it < my_pt; ++it) {
+        tc::mbar_wait_or_trap(&bar_aready, (uint32_t)it & 1u);
+        if (it > 0) tc::mbar_wait_or_trap(&bar_accfree, (uint32_t)(it - 1) & 1u);
+        tc::tc_fence_after();
+        // B K-step ks: slab ks / 4 (16 KB = 1024 descriptor units), 32 bytes = 2 units inside the slab
+#pragma unroll
+        for (int ks = 0; ks < KS; ++ks)
+          tc::mma2_tf32_ts_elect(dcol, a_lo + 8u * ks, desc_bhi + (uint64_t)((ks >> 2) * 1024 + (ks & 3) * 2), idesc, ks ? 1u : 0u);
+#pragma unroll
+        for (int ks = 0; ks < KS; ++ks)
+          tc::mma2_tf32_ts_elect(dcol, a_hi + 8u * ks, desc_blo + (uint64_t)((ks >> 2) * 1024 + (ks & 3) * 2), idesc, 1u);
+#pragma unroll
+        for (int ks = 0; ks < KS; ++ks)
+          tc::mma2_tf32_ts_elect(dcol, a_hi + 8u * ks, desc_bhi + (uint64_t)((ks >> 2) * 1024 + (ks & 3) * 2), idesc, 1u);
+        tc::mma2_tf32_elect(dcol, desc_ones, desc_bias, idesc, 1u);
+        tc::mma2_commit_elect(&bar_mma);
+      }
+    }
+  } else if (warp < 4) {
+    // =============================== S: the A operands of the tile into TMEM ===============================
+    int s = 0;
+    uint32_t full_ph = 0;
+    const uint32_t row_off = (uint32_t)(t >> 3) * 1024u + (uint32_t)(t & 7) * 128u;   // row t of a SW128 slab
+    const uint32_t row_x = (uint32_t)(t & 7);
+    const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);
+    uint32_t tf32_mask = 0xFFFFE000u, sign_bit = 0x80000000u;
+    asm volatile("" : "+r"(tf32_mask), "+r"(sign_bit));
+    for (unsigned long long it = 0; it < my_pt; ++it) {
+      if (it > 0) tc::mbar_wait_or_trap(&bar_mma, (uint32_t)(it - 1) & 1u);   // the MMAs of the previous tile have read A
+      tc::tc_fence_after();
+#pragma unroll 1
+      for (int sl = 0; sl < NS; ++sl) {
+        const unsigned char* rw = ring + (size_t)s * 16384;
+        tc::mbar_wait_or_trap(&bar_full[s], full_ph);
+        uint32_t xr[32];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const uint4 v = *reinterpret_cast<const uint4*>(rw + row_off + (((uint32_t)c ^ row_x) << 4));
+          xr[4 * c] = v.x; xr[4 * c + 1] = v.y; xr[4 * c + 2] = v.z; xr[4 * c + 3] = v.w;
+        }
+        tc::tmem_st32(lane_base + kT5ColA + 32u * sl, xr);
+#pragma unroll
+        for (int q = 0; q < 32; q += 2) {
+          const uint32_t n0 = tc::neg_trunc_tf32_bits(xr[q], tf32_mask, sign_bit);
+          const uint32_t n1 = tc::neg_trunc_tf32_bits(xr[q + 1], tf32_mask, sign_bit);
+          tc::f2_add_parts(xr[q], xr[q + 1], n0, n1, xr[q], xr[q + 1]);
+        }
+        tc::tmem_st32(lane_base + kT5ColA + (uint32_t)D + 32u * sl, xr);
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(&bar_empty[s]);
+        if (++s == kT5Stages) { s = 0; full_ph ^= 1u; }
+      }
+      tc::tmem_st_wait();
+      tc::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive_cluster(&bar_aready, 0u);
+    }
+  } else {
+    // =============================== E: score the rows ===============================
+    const int wq = warp & 3;
+    const int row = t - 128;
+    const uint32_t taddr = tmem + ((uint32_t)(wq * 32) << 16) + kT5ColAcc;
+    for (unsigned long long it = 0; it < my_pt; ++it) {
+      const unsigned long long row0 = tile_of(it) * 128ull;
+      tc::mbar_wait_or_trap(&bar_mma, (uint32_t)it & 1u);
+      tc::tc_fence_after();
+      uint32_t m1 = 0u, m2 = 0u;   // running best / runner-up (packed); real scores are >= 2^e > 0
+#pragma unroll 1
+      for (int c0 = 0; c0 < kT5K; c0 += 32) {
+        uint32_t q[32];
+        tc::tmem_ld32(taddr + (uint32_t)c0, q);
+        tc::tmem_ld_wait();
+#pragma unroll
+        for (int c = 0; c < 32; ++c) q[c] = (q[c] << 8) | (uint32_t)(c0 + c);
+        uint32_t b0 = __vimax3_u32(q[0], q[1], q[2]), b1 = __vimax3_u32(q[3], q[4], q[5]);
+        uint32_t b2 = __vimax3_u32(q[6], q[7], q[8]), b3 = __vimax3_u32(q[9], q[10], q[11]);
+#pragma unroll
+        for (int c = 12; c + 7 < 32; c += 8) {
+          b0 = __vimax3_u32(b0, q[c], q[c + 1]);
+          b1 = __vimax3_u32(b1, q[c + 2], q[c + 3]);
+          b2 = __vimax3_u32(b2, q[c + 4], q[c + 5]);
+          b3 = __vimax3_u32(b3, q[c + 6], q[c + 7]);
+        }
+        b0 = __vimax3_u32(b0, q[28], q[29]);
+        b1 = __vimax3_u32(b1, q[30], q[31]);
+        const uint32_t cb = max(__vimax3_u32(b0, b1, b2), b3);
+        const uint32_t cm1 = cb - 1u;
+#pragma unroll
+        for (int c = 0; c < 32; ++c) q[c] = cm1 - q[c];   // the chunk's best wraps to 0xFFFFFFFF, the others are gap - 1
+        b0 = __vimin3_u32(q[0], q[1], q[2]); b1 = __vimin3_u32(q[3], q[4], q[5]);
+        b2 = __vimin3_u32(q[6], q[7], q[8]); b3 = __vimin3_u32(q[9], q[10], q[11]);
+#pragma unroll
+        for (int c = 12; c + 7 < 32; c += 8) {
+          b0 = __vimin3_u32(b0, q[c], q[c + 1]);
+          b1 = __vimin3_u32(b1, q[c + 2], q[c + 3]);
+          b2 = __vimin3_u32(b2, q[c + 4], q[c + 5]);
+          b3 = __vimin3_u32(b3, q[c + 6], q[c + 7]);
+        }
+        b0 = __vimin3_u32(b0, q[28], q[29]);
+        b1 = __vimin3_u32(b1, q[30], q[31]);
+        const uint32_t cs = cm1 - min(__vimin3_u32(b0, b1, b2), b3);   // runner-up of the chunk
+        // merge (cb, cs) into (m1, m2)
+        m2 = max(max(m2, cs), min(m1, cb));
+        m1 = max(m1, cb);
+      }
+      tc::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive_cluster(&bar_accfree, 0u);   // the accumulator may be overwritten
+      const float v_best = __uint_as_float((m1 >> 8) | top_bits);
+      const float v_second = __uint_as_float((m2 >> 8) | top_bits);
+      const uint32_t bidx = m1 & 255u;
+      const bool certified = params_ok && ((v_best - v_second) > m_v) && bidx < (uint32_t)k;
+      const unsigned long long grow = row0 + (unsigned long long)row;
+      // flag lists are double-buffered by tile parity: the other list's counter is cleared before this tile's
+      // barrier, so that clearing and the next tile's appends are ordered by it
+      uint32_t* flags = flags_all + (it & 1) * 128;
+      if (grow < a.n) {
+        if (certified) a.labels[grow] = bidx;
+        else flags[atomicAdd(&n_flag[it & 1], 1u)] = (uint32_t)row;
+      }
+      if (row == 0) n_flag[(it + 1) & 1] = 0u;
+      tc::nb_sync(1, 128);
+      const uint32_t nf = n_flag[it & 1];
+      if (nf) {
+        // uncertified rows: the reference's scan (direct form in feature order, strict <), one warp per row; each
+        // lane walks the centroids c = lane, lane + 32, ... with the row read from global memory 32 features at a time
+        for (uint32_t f = (uint32_t)wq; f < nf; f += 4) {
+          const unsigned long long fr = row0 + flags[f];
+          const float* xrow = a.X + fr * (unsigned long long)D;
+          float dacc[kT5K / 32];
+#pragma unroll
+          for (int i = 0; i < kT5K / 32; ++i) dacc[i] = 0.f;
+#pragma unroll 1
+          for (int j0 = 0; j0 < D; j0 += 32) {
+            float x2[32];
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+              const float4 v = __ldg(reinterpret_cast<const float4*>(xrow + j0) + c);
+              x2[4 * c] = v.x; x2[4 * c + 1] = v.y; x2[4 * c + 2] = v.z; x2[4 * c + 3] = v.w;
+            }
+#pragma unroll
+            for (int i = 0; i < kT5K / 32; ++i) {
+              const int c = lane + 32 * i;
+              if (c < k) {
+                const float* cw = a.C + (size_t)c * D + j0;
+                float dd = dacc[i];
+#pragma unroll
+                for (int q4 = 0; q4 < 8; ++q4) {
+                  const float4 cv = __ldg(reinterpret_cast<const float4*>(cw) + q4);
+                  float df;
+                  df = __fsub_rn(cv.x, x2[4 * q4]); dd = __fadd_rn(dd, __fmul_rn(df, df));
+                  df = __fsub_rn(cv.y, x2[4 * q4 + 1]); dd = __fadd_rn(dd, __fmul_rn(df, df));
+                  df = __fsub_rn(cv.z, x2[4 * q4 + 2]); dd = __fadd_rn(dd, __fmul_rn(df, df));
+                  df = __fsub_rn(cv.w, x2[4 * q4 + 3]); dd = __fadd_rn(dd, __fmul_rn(df, df));
+                }
+                dacc[i] = dd;
+              }
+            }
+          }
+          float fb = INFINITY;
+          int fi = -1;
+#pragma unroll
+          for (int i = 0; i < kT5K / 32; ++i) {
+            const int c = lane + 32 * i;
+            if (c < k) {
+              // lane 0 starts with centroid 0 (sticky NaN like the reference); the others only take v < best
+              if (c == 0) { fb = dacc[i]; fi = 0; }
+              else if (dacc[i] < fb) { fb = dacc[i]; fi = c; }
+            }
+          }
+          combine_candidates<float>(32, fb, fi);
+          if (lane == 0) a.labels[fr] = (uint32_t)fi;
+        }
+        my_fallbacks += (row == 0) ? nf : 0u;
+      }
+    }
+    if (row == 0 && a.state && my_fallbacks) atomicAdd(&a.state->fallback_rows, (unsigned long long)my_fallbacks);
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::cluster_sync_all();   // the peer may still be reading this CTA's operands / arriving on its barriers
+  if (warp == 8) tc::tmem_dealloc_pair(tmem, 512);
+}
+
+}  // namespace lkm

@@ -482,7 +482,11 @@ TCA_CASES = [(6000, 128, 256, 16, 30.0, False), (5000, 64, 1024, 40, 30.0, False
              # shuffled rows (many one-row segments), one / two / four cluster chunks
              (148 * 32 * 3 + 19, 128, 256, 256, 30.0, False), (148 * 32 * 3 + 19, 128, 256, 256, 30.0, True),
              (40000, 64, 1024, 64, 30.0, True), (30001, 128, 1000, 50, 30.0, True), (20000, 64, 512, 300, 30.0, True),
-             (2047, 64, 300, 3, 30.0, False)]
+             (2047, 64, 4000, 3, 30.0, False),
+             # CTA-pair assignment kernel (assign_tc5_kernel: d in {64, 128}, k <= 256): heavy overlap (many exact re-scans),
+             # k below one CTA's half, a single partial tile (the second CTA of the pair idles), odd tile counts
+             (128 * 7 + 5, 128, 200, 20, 1.0, True), (100, 64, 256, 4, 30.0, False), (128 * 148 * 2 + 1, 64, 130, 130, 30.0, True),
+             (5000, 128, 100, 100, 0.3, True), (128 * 75, 128, 256, 64, 30.0, False), (4000, 64, 40, 3, 30.0, True)]
 
 
 @pytest.mark.parametrize("n,d,k,k_true,spread,shuffle", TCA_CASES)
@@ -511,6 +515,49 @@ def test_tc_assign_path_matches_oracle(lb, ctx, oracle, n, d, k, k_true, spread,
     assert counts.tolist() == ref_counts.tolist()
     np.testing.assert_allclose(inertia, ref_inertia, rtol=1e-5)
     print(f"fallback rows over 2 iterations: {st.fallback_rows} of {2 * n}")
+
+
+@pytest.mark.parametrize("scale,offset", [(1e-3, 0.0), (1e3, 0.0), (1.0, 5e3), (1e-20, 0.0), (1e15, 0.0)])
+def test_pair_kernel_magnitudes(lb, ctx, oracle, scale, offset):
+    """assign_tc5_kernel: score window and certificate over 35 orders of magnitude and far from the origin."""
+    dt = np.float32
+    X, _ = blobs(9000, 128, 40, dt, seed=13, spread=30.0)
+    X = (X.astype(np.float64) * scale + offset).astype(dt)
+    g = np.random.default_rng(6)
+    X = X[g.permutation(len(X))].copy()
+    init = X[g.choice(len(X), size=40, replace=False)].copy()
+    ctx.set_data(X)
+    c, counts, inertia, st = ctx.lloyd_iters(init, 2, 0.0)
+    assert st.assign_path == 2
+    cur = init
+    for _ in range(2):
+        lab, d = oracle.assign(X, cur)
+        cur = oracle.compute_centroids(cur, X, lab, acc_f64=True)
+    assert counts.tolist() == np.bincount(lab.astype(np.int64), minlength=40).tolist()
+    np.testing.assert_allclose(c, cur, rtol=1e-5, atol=1e-5 * np.abs(cur).max())
+    ref_inertia = d.astype(np.float64).sum()
+    if np.isfinite(ref_inertia):
+        np.testing.assert_allclose(inertia, ref_inertia, rtol=2e-5)
+
+
+def test_pair_kernel_nan_inf_and_duplicates(lb, ctx, oracle):
+    dt = np.float32
+    X, _ = blobs(3000, 64, 6, dt, seed=4)
+    idx = list(range(0, 3000, 100)) + [0, 600]                  # 32 centroids, the last two duplicate earlier ones:
+    init = X[idx].copy()                                        # exact ties, the lowest index wins
+    ctx.set_data(X)
+    c, counts, inertia, st = ctx.lloyd_iters(init, 1, 0.0)
+    assert st.assign_path == 2
+    lab, d = oracle.assign(X, init)
+    assert counts.tolist() == np.bincount(lab.astype(np.int64), minlength=32).tolist()
+    assert counts[30] == 0 and counts[31] == 0
+    X[100, 3] = np.inf
+    X[2000, 30] = np.nan
+    ctx.set_data(X)
+    c, counts, inertia, st = ctx.lloyd_iters(init, 1, 0.0)
+    lab, d = oracle.assign(X, init)
+    assert counts.tolist() == np.bincount(lab.astype(np.int64), minlength=32).tolist()
+    assert not np.isfinite(inertia)
 
 
 # ---- warp-specialised pipeline kernel (tc4: f32, d = 32, k <= 64) ----
