@@ -10,7 +10,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "liblkm.so")
+LIB_PATH = os.environ.get("LKM_LIB_PATH") or os.path.join(HERE, "liblkm.so")   # LKM_LIB_PATH: A/B builds while tuning
 
 if not os.path.exists(LIB_PATH):
     raise ImportError(
@@ -70,7 +70,7 @@ PICK_EXACT, PICK_FAST = 0, 1
 # every symbol include/lkm.h declares (tests check that the library exports them all)
 UNTYPED_SYMBOLS = [
     "lkm_create", "lkm_destroy", "lkm_last_error", "lkm_stream", "lkm_synchronize", "lkm_version",
-    "lkm_comm_unique_id", "lkm_comm_init", "lkm_set_shard", "lkm_set_assign_path", "lkm_set_l2_flush", "lkm_set_kernel_timing",
+    "lkm_comm_unique_id", "lkm_comm_init", "lkm_set_shard", "lkm_set_assign_path", "lkm_set_l2_flush", "lkm_set_kernel_timing", "lkm_set_scoring_passes",
 ]
 TYPED_SYMBOLS = [
     "lkm_set_data", "lkm_set_data_device", "lkm_gen_blobs", "lkm_get_data", "lkm_fit", "lkm_init",
@@ -96,6 +96,7 @@ lib.lkm_set_shard.argtypes = [_vp, _u64, _u64]
 lib.lkm_set_assign_path.argtypes = [_vp, _i32]
 lib.lkm_set_l2_flush.argtypes = [_vp, _u64]
 lib.lkm_set_kernel_timing.argtypes = [_vp, _i32]
+lib.lkm_set_scoring_passes.argtypes = [_vp, _i32]
 
 for _sfx, _ct in (("f32", C.c_float), ("f64", C.c_double)):
     _fp = C.POINTER(_ct)

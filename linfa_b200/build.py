@@ -12,7 +12,7 @@ ROOT = os.path.dirname(HERE)
 SRC = [os.path.join(HERE, "csrc", "lkm_api.cu")]
 DEPS = [os.path.join(HERE, "csrc", f) for f in os.listdir(os.path.join(HERE, "csrc"))] + [
     os.path.join(ROOT, "include", "lkm.h")]
-OUT = os.path.join(HERE, "liblkm.so")
+OUT = os.environ.get("LKM_BUILD_OUT") or os.path.join(HERE, "liblkm.so")
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

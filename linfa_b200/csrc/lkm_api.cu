@@ -98,6 +98,8 @@ struct lkm_ctx {
   // fused tcgen05 kernel for d = 32: 4 = TMA + warp-specialised pipeline, 3 = TMA + three worker groups
   // (both k <= 64; larger k falls back to 128), 128 / 256 / 544 = the earlier generations (LKM_TC_VARIANT)
   int tc_variant = 4;
+  int tc5_passes_forced = 0;            // LKM_TC5_PASSES = 1 / 3 pins the screening / 3xTF32 variant of the pair kernel
+  uint64_t tc5_hard_epoch = 0, tc5_easy_epoch = 0;
   int tc5_enabled = 1;   // LKM_TC5=0: tc_assign_kernel instead of the CTA-pair assignment kernel
   int upd_variant = 1;   // LKM_UPD=0: cluster-chunked lloyd_kernel<MODE_UPDATE> instead of update_rows_kernel
   uint64_t data_epoch = 1, xmax2_epoch = 0;  // resident-data version / version the cached max row norm belongs to
@@ -614,7 +616,7 @@ static lkm_status run_lloyd(lkm_ctx* ctx, F* dC2, uint64_t k, uint64_t max_iter,
         const void* fn = d == 32 ? (const void*)update_rows_kernel<32> : (d == 64 ? (const void*)update_rows_kernel<64> : (const void*)update_rows_kernel<128>);
         CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)upd_smem));
         CK(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
-        CKS(make_plain_tile_map(ctx, dX, n, d, 32, kUpdSubRows, upd_map));
+        CKS(make_plain_tile_map(ctx, dX, n, d, (uint32_t)d, kUpdSubRows, upd_map));
         CK(ctx->labels.ensure((n + 64) * 4));
         use_upd = true;
       }
@@ -628,11 +630,14 @@ static lkm_status run_lloyd(lkm_ctx* ctx, F* dC2, uint64_t k, uint64_t max_iter,
   std::memset(&tc5_map, 0, sizeof(tc5_map));
   if constexpr (std::is_same<F, float>::value) {
     if (use_upd && ctx->tc5_enabled && (d == 64 || d == 128) && k <= (uint64_t)kT5K && n + 512 < (1ull << 31) &&
-        tc5_smem_bytes((int)d) <= ctx->smem_optin) {
+        tc5_smem_bytes((int)d) <= ctx->smem_optin && tc5s_smem_bytes((int)d) <= ctx->smem_optin) {
       tc5_smem = tc5_smem_bytes((int)d);
       const void* fn = d == 64 ? (const void*)assign_tc5_kernel<64> : (const void*)assign_tc5_kernel<128>;
       CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc5_smem));
       CK(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
+      const void* fns = d == 64 ? (const void*)assign_tc5s_kernel<64> : (const void*)assign_tc5s_kernel<128>;
+      CK(cudaFuncSetAttribute(fns, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc5s_smem_bytes((int)d)));
+      CK(cudaFuncSetAttribute(fns, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
       CKS(make_row_tile_map(ctx, dX, n, tc5_map, d));
       if (!ctx->own_X || ctx->xmax2_epoch != ctx->data_epoch) {
         CK(ctx->xmax2.ensure(16));
@@ -686,9 +691,13 @@ static lkm_status run_lloyd(lkm_ctx* ctx, F* dC2, uint64_t k, uint64_t max_iter,
     tc4_passes = ctx->tc4_passes_forced ? ctx->tc4_passes_forced : ((ctx->tc4_hard_epoch == ctx->data_epoch && ctx->own_X) ? 3 : 2);
   }
   bool tc4_probe = is_tc4 && !ctx->tc4_passes_forced && tc4_passes == 2 && !(ctx->tc4_easy_epoch == ctx->data_epoch && ctx->own_X);
+  // pair kernel: the screening variant (one TF32 product) first, 3xTF32 when too many rows needed the exact re-scan
+  int tc5_passes = 3;
+  if (use_tc5) tc5_passes = ctx->tc5_passes_forced ? ctx->tc5_passes_forced : ((ctx->tc5_hard_epoch == ctx->data_epoch && ctx->own_X) ? 3 : 1);
+  bool tc5_probe = use_tc5 && !ctx->tc5_passes_forced && tc5_passes == 1 && !(ctx->tc5_easy_epoch == ctx->data_epoch && ctx->own_X);
   unsigned long long fb_seen = 0;
   for (;;) {
-    const uint64_t todo = std::min<uint64_t>(tc4_probe ? 1 : batch, max_iter - launched);
+    const uint64_t todo = std::min<uint64_t>((tc4_probe || tc5_probe) ? 1 : batch, max_iter - launched);
     for (uint64_t q = 0; q < todo; ++q) {
       const uint64_t it = launched + q;
       const F* Ccur = dC2 + (it & 1) * kd;
@@ -737,8 +746,15 @@ static lkm_status run_lloyd(lkm_ctx* ctx, F* dC2, uint64_t k, uint64_t max_iter,
           if (use_tc5) {
             Tc5Args t5{};
             t5.X = dX; t5.n = n; t5.k = (int)k; t5.C = Ccur; t5.xmax2_bits = ctx->xmax2.as<unsigned int>();
-            t5.labels = ctx->labels.as<uint32_t>(); t5.state = dstate;
-            if (d == 64) assign_tc5_kernel<64><<<tc5_grid, kT5Threads, tc5_smem, ctx->stream>>>(t5, tc5_map);
+            t5.labels = ctx->labels.as<uint32_t>(); t5.state = dstate; t5.pack_mult = 256u;
+#ifdef LKM_T5_TRACE
+            CK(ctx->t4prof.ensure(2 * 16 * 16 * 8));
+            t5.prof = ctx->t4prof.as<long long>();
+#endif
+            if (tc5_passes == 1) {
+              if (d == 64) assign_tc5s_kernel<64><<<tc5_grid, kT5Threads, tc5s_smem_bytes(64), ctx->stream>>>(t5, tc5_map);
+              else assign_tc5s_kernel<128><<<tc5_grid, kT5Threads, tc5s_smem_bytes(128), ctx->stream>>>(t5, tc5_map);
+            } else if (d == 64) assign_tc5_kernel<64><<<tc5_grid, kT5Threads, tc5_smem, ctx->stream>>>(t5, tc5_map);
             else assign_tc5_kernel<128><<<tc5_grid, kT5Threads, tc5_smem, ctx->stream>>>(t5, tc5_map);
             CK(cudaGetLastError());
             ctx->launches++;
@@ -872,6 +888,12 @@ static lkm_status run_lloyd(lkm_ctx* ctx, F* dC2, uint64_t k, uint64_t max_iter,
       else ctx->tc4_easy_epoch = ctx->data_epoch;
       tc4_probe = false;
     }
+    if (use_tc5 && !ctx->tc5_passes_forced && tc5_passes == 1) {
+      const unsigned long long fb = (ctx->h_state->fallback_rows & ((1ull << 40) - 1)) - fb_seen;
+      if ((double)fb > 0.02 * (double)n * (double)todo_done) { tc5_passes = 3; ctx->tc5_hard_epoch = ctx->data_epoch; }
+      else ctx->tc5_easy_epoch = ctx->data_epoch;
+      tc5_probe = false;
+    }
     fb_seen = ctx->h_state->fallback_rows & ((1ull << 40) - 1);
     if (ctx->h_state->done || launched >= max_iter) break;
   }
@@ -892,6 +914,19 @@ static lkm_status run_lloyd(lkm_ctx* ctx, F* dC2, uint64_t k, uint64_t max_iter,
       out.main_ms += b;
     }
   }
+#ifdef LKM_T5_TRACE
+  if (use_tc5) {
+    static long long ht[2 * 16 * 16];
+    CK(cudaMemcpy(ht, ctx->t4prof.p, sizeof(ht), cudaMemcpyDeviceToHost));
+    std::fprintf(stderr, "t5trace cta tile  (3xTF32) Maready Maccfree Mcommit  Sbeg Sissued Sarrived  Ewake Edrained Elabels | (screening) Ptma0 Ptma3 Maccfree Mfull0 Mpfull0 Mfull3 Mpfull3 Mcommit Ewake Edrained Edone\n");
+    for (int c = 0; c < 2; ++c)
+      for (int j = 0; j < 16; ++j) {
+        std::fprintf(stderr, "t5trace %d %3d", c, j);
+        for (int e = 0; e < 11; ++e) std::fprintf(stderr, " %7lld", ht[(c * 16 + j) * 16 + e]);
+        std::fprintf(stderr, "\n");
+      }
+  }
+#endif
 #ifdef LKM_T4_TRACE
   if (use_tc && tc_threads == kT4Threads) {
     static long long ht[64 + 40 * 16];
@@ -1735,6 +1770,7 @@ LKM_EXPORT lkm_status lkm_create(lkm_ctx** out, int device) {
   if (const char* v = std::getenv("LKM_TC_VARIANT")) ctx->tc_variant = std::atoi(v);
   if (const char* v = std::getenv("LKM_UPD")) ctx->upd_variant = std::atoi(v);
   if (const char* v = std::getenv("LKM_TC5")) ctx->tc5_enabled = std::atoi(v);
+  if (const char* v = std::getenv("LKM_TC5_PASSES")) ctx->tc5_passes_forced = std::atoi(v);
   if (const char* v = std::getenv("LKM_P2P")) ctx->p2p_enabled = std::atoi(v);
   if (const char* v = std::getenv("LKM_TC4_PASSES")) ctx->tc4_passes_forced = std::atoi(v);
   ctx->sm_count = prop.multiProcessorCount;
@@ -1777,6 +1813,13 @@ LKM_EXPORT lkm_status lkm_synchronize(lkm_ctx* ctx) {
 LKM_EXPORT lkm_status lkm_set_assign_path(lkm_ctx* ctx, int path) {
   if (!ctx || path < -1 || path > 2) return LKM_ERR_INVALID_ARG;
   ctx->force_path = path;
+  return LKM_OK;
+}
+
+LKM_EXPORT lkm_status lkm_set_scoring_passes(lkm_ctx* ctx, int passes) {
+  if (!ctx || passes < 0 || passes > 3) return LKM_ERR_INVALID_ARG;
+  ctx->tc5_passes_forced = (passes == 1 || passes == 3) ? passes : 0;
+  ctx->tc4_passes_forced = (passes == 2 || passes == 3) ? passes : 0;
   return LKM_OK;
 }
 
@@ -1981,6 +2024,15 @@ LKM_EXPORT int lkm_debug_mma_bench(lkm_ctx* ctx, int n_cols, int reps, int per_b
   CK(ctx->scratch.ensure((size_t)grid * 8));
   const size_t smem = 32768 + (size_t)n_cols * 128 + 2048;
   CK(cudaFuncSetAttribute(mma_bench_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  if (mode == 33 || mode == 34) {   // TMEM store throughput / stores and loads at the same time: n_cols / 16 = warps
+    CK(ctx->dists.ensure((size_t)grid * 64));
+    CK(cudaMemsetAsync(ctx->dists.p, 0, (size_t)grid * 64, ctx->stream));
+    sttm_bench_kernel<<<grid, 256, 0, ctx->stream>>>(n_cols / 16, reps, mode - 32, ctx->dists.as<long long>());
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(cycles_out, ctx->dists.p, 64, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return LKM_OK;
+  }
   if (mode == 32) {   // TMEM load throughput: n_cols = warps, per_batch unused
     CK(cudaMemsetAsync(ctx->scratch.p, 0, (size_t)grid * 8, ctx->stream));
     CK(ctx->dists.ensure((size_t)grid * 64));

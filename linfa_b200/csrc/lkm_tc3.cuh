@@ -53,18 +53,31 @@ __device__ __forceinline__ uint64_t smem_desc_sw128_alias(uint32_t saddr) {
 // bounded wait; a barrier that never completes is a protocol bug: kill the kernel instead of hanging the GPU.
 // The suspend-time hint lets the hardware park the warp until the phase completes instead of re-polling every
 // few cycles (polling warps steal issue slots and mbarrier bandwidth from the working roles).
+#ifndef LKM_WAIT_HINT_NS
+#define LKM_WAIT_HINT_NS 10000
+#endif
 __device__ __forceinline__ void mbar_wait_or_trap(uint64_t* bar, uint32_t parity) {
   const uint32_t addr = smem_u32(bar);
 #pragma unroll 1
-  for (uint32_t i = 0; i < (1u << 18); ++i) {
+  for (uint32_t i = 0; i < (LKM_WAIT_HINT_NS ? (1u << 18) : (1u << 28)); ++i) {
     uint32_t ok;
+#if LKM_WAIT_HINT_NS
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(ok)
-        : "r"(addr), "r"(parity), "r"(10000u)
+        : "r"(addr), "r"(parity), "r"((uint32_t)LKM_WAIT_HINT_NS)
         : "memory");
+#else
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(addr), "r"(parity)
+        : "memory");
+#endif
     if (ok) return;
   }
   __trap();

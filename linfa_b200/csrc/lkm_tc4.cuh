@@ -212,7 +212,7 @@ __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.
 
 // PASSES = 3: x_lo.c_hi + x_hi.c_lo + x_hi.c_hi (3xTF32, A operands staged in TMEM by the S role).
 // PASSES = 2: x_hi.c_lo + x_hi.c_hi only — the raw tile in shared memory is the A operand, the S role is idle, and the
-// dropped x_lo.c term (|x_lo.c| <= 2^-11 |x||c|) widens the certificate; rows it no longer certifies take the exact
+// dropped x_lo.c term (|x_lo.c| <= 2^-10 |x||c|) widens the certificate; rows it no longer certifies take the exact
 // re-scan, so results are identical.  The host starts with 2 passes and switches to 3 when too many rows fall back.
 template <int KP, int PASSES>
 __global__ void __launch_bounds__(kT4Threads, 1) lloyd_tc4_kernel(const Tc4Args a, const __grid_constant__ CUtensorMap tmap) {
@@ -330,7 +330,7 @@ __global__ void __launch_bounds__(kT4Threads, 1) lloyd_tc4_kernel(const Tc4Args 
   // v is half a squared distance.  On each of the two candidates: the bias K-step rounds at most 3 ulp(v), the
   // f32 bias K0 - nn/2 is off by at most 2^-24 K0 + (d + 1) 2^-25 |c|^2 (rounding of the norm and of the subtraction)
   const float m_v = 0.5f * m_w + 7.f * 1.1920929e-7f * (K0 + Rb) + 33.f * 5.9604645e-8f * cmax2 +
-                    (PASSES == 2 ? 1.001f * 9.765625e-4f * xmax * cmax : 0.f);   // + 2 * 2^-11 |x||c| without the x_lo pass
+                    (PASSES == 2 ? 1.001f * 1.953125e-3f * xmax * cmax : 0.f);   // + 2 * 2^-10 |x||c| without the x_lo pass (|x_lo| < 2^-10 |x| element-wise)
   if (t < KP) {
     // bias row t: K0 - |c|^2/2 as three TF32 pieces that add up to the f32 value exactly, K-step 0 of the tile
     const float b = (t < k) ? (K0 - 0.5f * nn_s[t]) : two_lo;
@@ -862,6 +862,47 @@ __global__ void __launch_bounds__(256) ldtm_bench_kernel(int nwarps, int reps, l
         tc::tmem_ld32(base + 32u * (uint32_t)i, v);
         tc::tmem_ld_wait();
         sink += v[0] ^ v[31];
+      }
+    }
+    const long long t1 = clock64();
+    if ((t & 31) == 0) out[blockIdx.x * 8 + warp] = t1 - t0 + (sink == 0x12345u ? 1 : 0);
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tc::tmem_dealloc(tmem, 512);
+}
+
+// TMEM store throughput (what = 1): `nwarps` warps each issue `reps` x 8 tcgen05.st.32x32b.x32 back to back, one
+// tcgen05.wait::st per 8; what = 2: warps 0-3 store while warps 4-7 load (the S / E mix of the pair kernel).
+__global__ void __launch_bounds__(256) sttm_bench_kernel(int nwarps, int reps, int what, long long* out) {
+  __shared__ uint32_t tmem_slot;
+  const int t = threadIdx.x, warp = t >> 5;
+  if (warp == 0) tc::tmem_alloc(&tmem_slot, 512);
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+  uint32_t sink = 0;
+  if (warp < nwarps) {
+    const bool storing = what == 1 || warp < 4;
+    const uint32_t base = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (storing ? 256u : 0u);
+    uint32_t v[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = (uint32_t)(t * 32 + i);
+    const long long t0 = clock64();
+    for (int r = 0; r < reps; ++r) {
+      if (storing) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) tc::tmem_st32(base + 32u * (uint32_t)i, v);
+        tc::tmem_st_wait();
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          uint32_t w[32];
+          tc::tmem_ld32(base + 32u * (uint32_t)i, w);
+          tc::tmem_ld_wait();
+          sink += w[0] ^ w[31];
+        }
       }
     }
     const long long t1 = clock64();

@@ -37,7 +37,16 @@ struct Tc5Args {
   const unsigned int* xmax2_bits;   // max_i |x_i|^2 of the resident matrix (row_norm2_max_wide_kernel)
   uint32_t* labels;
   LloydState* state;
+  long long* prof;   // LKM_T5_TRACE builds only
+  uint32_t pack_mult;   // 256, passed as an argument so that the score pack stays an IMAD (see the E role)
 };
+
+// LKM_T5_TRACE: CTA 0 / 1 stamp event `ev` of tile `it` (cycles since the roles started) into a.prof[(cta * 16 + it) * 16 + ev]
+#ifdef LKM_T5_TRACE
+#define T5TRACE(it, ev) do { if (blockIdx.x < 2 && lane == 0 && (it) < 16 && a.prof) a.prof[((blockIdx.x * 16) + (it)) * 16 + (ev)] = clock64() - trace_t0; } while (0)
+#else
+#define T5TRACE(it, ev)
+#endif
 
 __host__ __device__ inline size_t tc5_smem_bytes(int d) {
   return (size_t)kT5Stages * 16384 + (size_t)(d / 32) * 16384 * 2 + 16384 + 1024 + kT5K * 4 + 2 * 128 * 4 + 1024;
@@ -77,6 +86,15 @@ __device__ __forceinline__ void cluster_sync_all() {
 }
 // arrive on the mbarrier at the same shared-memory offset in CTA `cta` of the cluster
 __device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t cta) {
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}"
+      ::"r"(smem_u32(bar)), "r"(cta)
+      : "memory");
+}
+// the same with cluster-scope release: orders this thread's earlier observations (a landed TMA slab) before the arrival
+__device__ __forceinline__ void mbar_arrive_cluster_release(uint64_t* bar, uint32_t cta) {
   asm volatile(
       "{\n\t.reg .b32 ra;\n\t"
       "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
@@ -121,6 +139,172 @@ __device__ __forceinline__ void mma2_commit_elect(uint64_t* bar) {
       : "memory");
 }
 }  // namespace tc
+
+
+// ---- pieces shared by the pair kernels -------------------------------------------------------------------------------
+struct T5Win {
+  float K0, pad_bias, m_v;
+  uint32_t top_bits;
+  bool ok;
+};
+// Score window and certificate margin (identical in every thread of both CTAs).  `dropped` = bound, in units of
+// max|x| max|c|, on the product terms the scoring leaves out for BOTH candidates together (0 for 3xTF32).
+template <int D>
+__device__ __forceinline__ T5Win t5_window(float xmax2, float cmax2_raw, float dropped) {
+  T5Win w;
+  const float cmax2 = cmax2_raw * 1.00001f;
+  const float cmax = sqrtf(cmax2) * 1.000001f;
+  const float xmax = sqrtf(xmax2) * 1.000001f;
+  const float Rb = 1.01f * (xmax * cmax + 0.5f * cmax2) + 1e-30f;   // |x.c - |c|^2/2| <= Rb
+  w.ok = Rb < 1e30f;   // false for NaN / Inf: every row then takes the exact scan
+  // smallest even exponent field e with 2^e >= Rb; K0 = 2^(e+1), so v = x.c - |c|^2/2 + K0 lies in [2^e, 3 * 2^e):
+  // exponent field e or e + 1, the top 8 bits of every score are the same and (bits << 8) stays monotone
+  uint32_t e_w = ((__float_as_uint(Rb) >> 23) + 2u) & ~1u;
+  e_w = min(max(e_w, 2u), 250u);
+  w.K0 = __uint_as_float((e_w + 1u) << 23);
+  w.pad_bias = __uint_as_float(e_w << 23);
+  w.top_bits = (e_w << 23) & 0xFF000000u;
+  const float eta = (3.f * (float)D + 12.f) * 2.3841858e-7f;   // (3d + 12) * 2^-22
+  const float gamma = ((float)D + 2.f) * 5.9604645e-8f;        // (d + 2) * 2^-24
+  const float m_w = 1.1f * (2.3841858e-7f * cmax2 + xmax * (4.f * eta + 4.7683716e-7f) * cmax +
+                            2.f * gamma * (xmax + cmax) * (xmax + cmax));
+  w.m_v = 0.5f * m_w + 7.f * 1.1920929e-7f * (w.K0 + Rb) + ((float)D + 1.f) * 5.9604645e-8f * cmax2 + dropped * xmax * cmax;
+  return w;
+}
+
+// squared norms of all centroids into nn_s[256] (8 threads per row) and their maximum (bits) into *cmax_bits; all
+// threads of the CTA call it
+template <int D>
+__device__ __forceinline__ void t5_centroid_norms(const float* __restrict__ C, int k, float* nn_s, uint32_t* cmax_bits, int t) {
+  for (int base = 0; base < kT5K * 8; base += kT5Threads) {
+    const int item = base + t;
+    const int r = item >> 3, c8 = item & 7;
+    float nn = 0.f;
+    if (item < kT5K * 8 && r < k) {
+#pragma unroll
+      for (int q = 0; q < D / 32; ++q) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(C + (size_t)r * D) + c8 + 8 * q);
+        nn = fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, fmaf(v.w, v.w, nn))));
+      }
+    }
+    nn += __shfl_xor_sync(0xffffffffu, nn, 1);
+    nn += __shfl_xor_sync(0xffffffffu, nn, 2);
+    nn += __shfl_xor_sync(0xffffffffu, nn, 4);
+    if (item < kT5K * 8 && c8 == 0) {
+      nn_s[r] = nn;   // |nn - |c|^2| <= (d + 1) 2^-24 |c|^2 whatever the summation order
+      if (r < k) atomicMax(cmax_bits, __float_as_uint(nn));   // a NaN norm wins and voids every certificate
+    }
+  }
+}
+
+// bias row t (K0 - |c|^2/2 as three TF32 pieces that add up to the f32 value exactly) and the constant ones atom
+__device__ __forceinline__ void t5_write_bias(unsigned char* b_bias, unsigned char* ones, const float* nn_s, const T5Win& w,
+                                              int c, int k, int t) {
+  const float b = (c < k) ? (w.K0 - 0.5f * nn_s[c]) : w.pad_bias;
+  const float h = tc::trunc_tf32(b);
+  const float l = b - h;
+  const float l1 = tc::trunc_tf32(l);
+  const float l2 = l - l1;
+  float* p = reinterpret_cast<float*>(b_bias + tc::sw128_offset((uint32_t)t, 0));
+  p[0] = h; p[1] = l1; p[2] = l2;
+  if (t < 8) {
+    float* o1 = reinterpret_cast<float*>(ones + tc::sw128_offset((uint32_t)t, 0));
+    o1[0] = 1.f; o1[1] = 1.f; o1[2] = 1.f;
+  }
+}
+
+// Packed top-2 of the 256 scores of this thread's row: q = bits(v) << 8 | c.  Integer min / max / add run on the
+// 16-lane ALU pipe (two cycles per warp instruction), which this role saturates: the pack is kept an IMAD (FMA
+// pipe) by passing the multiplier (256) as a kernel argument, and the runner-up pass is written as chains of
+// min(m, cb - 1 - q) so that each step is one fused VIADDMNMX.
+__device__ __forceinline__ void t5_top2(uint32_t taddr, uint32_t mult, uint32_t& m1, uint32_t& m2) {
+  m1 = 0u; m2 = 0u;   // real scores are >= 2^e > 0
+#pragma unroll 1
+  for (int c0 = 0; c0 < kT5K; c0 += 32) {
+    uint32_t q[32];
+    tc::tmem_ld32(taddr + (uint32_t)c0, q);
+    tc::tmem_ld_wait();
+#pragma unroll
+    for (int c = 0; c < 32; ++c) q[c] = q[c] * mult + (uint32_t)c;   // index inside the chunk; c0 is added to the winners
+    uint32_t b0 = __vimax3_u32(q[0], q[1], q[2]), b1 = __vimax3_u32(q[3], q[4], q[5]);
+    uint32_t b2 = __vimax3_u32(q[6], q[7], q[8]), b3 = __vimax3_u32(q[9], q[10], q[11]);
+#pragma unroll
+    for (int c = 12; c + 7 < 32; c += 8) {
+      b0 = __vimax3_u32(b0, q[c], q[c + 1]);
+      b1 = __vimax3_u32(b1, q[c + 2], q[c + 3]);
+      b2 = __vimax3_u32(b2, q[c + 4], q[c + 5]);
+      b3 = __vimax3_u32(b3, q[c + 6], q[c + 7]);
+    }
+    b0 = __vimax3_u32(b0, q[28], q[29]);
+    b1 = __vimax3_u32(b1, q[30], q[31]);
+    const uint32_t cb = max(__vimax3_u32(b0, b1, b2), b3);
+    const uint32_t cm1 = cb - 1u;
+    // the chunk's best wraps to 0xFFFFFFFF, the others become gap - 1
+    uint32_t t0 = 0xFFFFFFFFu, t1 = 0xFFFFFFFFu, t2 = 0xFFFFFFFFu, t3 = 0xFFFFFFFFu;
+#pragma unroll
+    for (int c = 0; c < 32; c += 4) {
+      t0 = min(t0, cm1 - q[c]);
+      t1 = min(t1, cm1 - q[c + 1]);
+      t2 = min(t2, cm1 - q[c + 2]);
+      t3 = min(t3, cm1 - q[c + 3]);
+    }
+    const uint32_t cs = cm1 - min(min(t0, t1), min(t2, t3)) + (uint32_t)c0;   // runner-up of the chunk
+    const uint32_t cbg = cb + (uint32_t)c0;
+    m2 = max(max(m2, cs), min(m1, cbg));
+    m1 = max(m1, cbg);
+  }
+}
+
+// The reference's scan of row fr (direct form in feature order, strict <) by one warp: each lane walks the centroids
+// c = lane, lane + 32, ... with the row read from global memory 32 features at a time.  Returns the label.
+template <int D>
+__device__ __forceinline__ int t5_exact_label(const float* __restrict__ X, const float* __restrict__ C, int k, unsigned long long fr,
+                                              int lane) {
+  const float* xrow = X + fr * (unsigned long long)D;
+  float dacc[kT5K / 32];
+#pragma unroll
+  for (int i = 0; i < kT5K / 32; ++i) dacc[i] = 0.f;
+#pragma unroll 1
+  for (int j0 = 0; j0 < D; j0 += 32) {
+    float x2[32];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(xrow + j0) + c);
+      x2[4 * c] = v.x; x2[4 * c + 1] = v.y; x2[4 * c + 2] = v.z; x2[4 * c + 3] = v.w;
+    }
+#pragma unroll
+    for (int i = 0; i < kT5K / 32; ++i) {
+      const int c = lane + 32 * i;
+      if (c < k) {
+        const float* cw = C + (size_t)c * D + j0;
+        float dd = dacc[i];
+#pragma unroll
+        for (int q4 = 0; q4 < 8; ++q4) {
+          const float4 cv = __ldg(reinterpret_cast<const float4*>(cw) + q4);
+          float df;
+          df = __fsub_rn(cv.x, x2[4 * q4]); dd = __fadd_rn(dd, __fmul_rn(df, df));
+          df = __fsub_rn(cv.y, x2[4 * q4 + 1]); dd = __fadd_rn(dd, __fmul_rn(df, df));
+          df = __fsub_rn(cv.z, x2[4 * q4 + 2]); dd = __fadd_rn(dd, __fmul_rn(df, df));
+          df = __fsub_rn(cv.w, x2[4 * q4 + 3]); dd = __fadd_rn(dd, __fmul_rn(df, df));
+        }
+        dacc[i] = dd;
+      }
+    }
+  }
+  float fb = INFINITY;
+  int fi = -1;
+#pragma unroll
+  for (int i = 0; i < kT5K / 32; ++i) {
+    const int c = lane + 32 * i;
+    if (c < k) {
+      // lane 0 starts with centroid 0 (sticky NaN like the reference); the others only take v < best
+      if (c == 0) { fb = dacc[i]; fi = 0; }
+      else if (dacc[i] < fb) { fb = dacc[i]; fi = c; }
+    }
+  }
+  combine_candidates<float>(32, fb, fi);
+  return fi;
+}
 
 template <int D>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kT5Threads, 1)
@@ -168,26 +352,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kT5Threads, 1)
   }
   for (int e = t; e < 1024 + 64; e += kT5Threads) reinterpret_cast<float4*>(b_bias)[e] = make_float4(0.f, 0.f, 0.f, 0.f);   // bias tile + ones atom
   __syncthreads();
-  // ---- squared norms of all centroids (8 threads per row), max norm ----
-  for (int base = 0; base < kT5K * 8; base += kT5Threads) {
-    const int item = base + t;
-    const int r = item >> 3, c8 = item & 7;
-    float nn = 0.f;
-    if (item < kT5K * 8 && r < k) {
-#pragma unroll
-      for (int q = 0; q < D / 32; ++q) {
-        const float4 v = __ldg(reinterpret_cast<const float4*>(a.C + (size_t)r * D) + c8 + 8 * q);
-        nn = fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, fmaf(v.w, v.w, nn))));
-      }
-    }
-    nn += __shfl_xor_sync(0xffffffffu, nn, 1);
-    nn += __shfl_xor_sync(0xffffffffu, nn, 2);
-    nn += __shfl_xor_sync(0xffffffffu, nn, 4);
-    if (item < kT5K * 8 && c8 == 0) {
-      nn_s[r] = nn;   // |nn - |c|^2| <= (d + 1) 2^-24 |c|^2 whatever the summation order
-      if (r < k) atomicMax(&cmax_bits, __float_as_uint(nn));   // a NaN norm wins and voids every certificate
-    }
-  }
+  t5_centroid_norms<D>(a.C, k, nn_s, &cmax_bits, t);
   // ---- this CTA's half of the centroids as TF32 hi / lo operand slabs ----
   for (int item = t; item < 128 * NS * 8; item += kT5Threads) {
     const int q = item & 7, s = (item >> 3) % NS, r = item / (8 * NS);
@@ -202,39 +367,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kT5Threads, 1)
     *reinterpret_cast<float4*>(b_lo + o) = l;
   }
   __syncthreads();
-  // ---- window, bias, margin (identical in every thread of both CTAs) ----
-  const float xmax2 = __uint_as_float(__ldg(a.xmax2_bits));
-  const float cmax2 = __uint_as_float(cmax_bits) * 1.00001f;
-  const float cmax = sqrtf(cmax2) * 1.000001f;
-  const float xmax = sqrtf(xmax2) * 1.000001f;
-  const float Rb = 1.01f * (xmax * cmax + 0.5f * cmax2) + 1e-30f;   // |x.c - |c|^2/2| <= Rb
-  const bool params_ok = Rb < 1e30f;   // false for NaN / Inf: every row then takes the exact scan
-  // smallest even exponent field e with 2^e >= Rb; K0 = 2^(e+1), so v = x.c - |c|^2/2 + K0 lies in [2^e, 3 * 2^e):
-  // exponent field e or e + 1, the top 8 bits of every score are the same and (bits << 8) stays monotone
-  uint32_t e_w = ((__float_as_uint(Rb) >> 23) + 2u) & ~1u;
-  e_w = min(max(e_w, 2u), 250u);
-  const float K0 = __uint_as_float((e_w + 1u) << 23);
-  const uint32_t top_bits = (e_w << 23) & 0xFF000000u;
-  const float eta = (3.f * (float)D + 12.f) * 2.3841858e-7f;   // (3d + 12) * 2^-22
-  const float gamma = ((float)D + 2.f) * 5.9604645e-8f;        // (d + 2) * 2^-24
-  const float m_w = 1.1f * (2.3841858e-7f * cmax2 + xmax * (4.f * eta + 4.7683716e-7f) * cmax +
-                            2.f * gamma * (xmax + cmax) * (xmax + cmax));
-  const float m_v = 0.5f * m_w + 7.f * 1.1920929e-7f * (K0 + Rb) + ((float)D + 1.f) * 5.9604645e-8f * cmax2;
-  if (t < 128) {
-    // bias row t: K0 - |c|^2/2 as three TF32 pieces that add up to the f32 value exactly
-    const int c = (int)rank * 128 + t;
-    const float b = (c < k) ? (K0 - 0.5f * nn_s[c]) : __uint_as_float(e_w << 23);
-    const float h = tc::trunc_tf32(b);
-    const float l = b - h;
-    const float l1 = tc::trunc_tf32(l);
-    const float l2 = l - l1;
-    float* p = reinterpret_cast<float*>(b_bias + tc::sw128_offset((uint32_t)t, 0));
-    p[0] = h; p[1] = l1; p[2] = l2;
-    if (t < 8) {
-      float* o1 = reinterpret_cast<float*>(ones + tc::sw128_offset((uint32_t)t, 0));
-      o1[0] = 1.f; o1[1] = 1.f; o1[2] = 1.f;
-    }
-  }
+  const T5Win win = t5_window<D>(__uint_as_float(__ldg(a.xmax2_bits)), __uint_as_float(cmax_bits), 0.f);
+  if (t < 128) t5_write_bias(b_bias, ones, nn_s, win, (int)rank * 128 + t, k, t);
   tc::fence_async_smem();
   tc::tc_fence_before();
   __syncthreads();
@@ -242,6 +376,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kT5Threads, 1)
   tc::tc_fence_after();
   const uint32_t tmem = tmem_slot;
   unsigned int my_fallbacks = 0;
+#ifdef LKM_T5_TRACE
+  const long long trace_t0 = clock64();
+#endif
 
   if (warp == 9) {
     // =============================== P: stream the slabs ===============================
@@ -270,7 +407,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kT5Threads, 1)
       const uint32_t dcol = tmem_u + kT5ColAcc, a_hi = tmem_u + kT5ColA, a_lo = tmem_u + kT5ColA + (uint32_t)D;
       for (unsigned long long it = 0; it < my_pt; ++it) {
         tc::mbar_wait_or_trap(&bar_aready, (uint32_t)it & 1u);
+        T5TRACE(it, 0);
         if (it > 0) tc::mbar_wait_or_trap(&bar_accfree, (uint32_t)(it - 1) & 1u);
+        T5TRACE(it, 1);
         tc::tc_fence_after();
         // B K-step ks: slab ks / 4 (16 KB = 1024 descriptor units), 32 bytes = 2 units inside the slab
 #pragma unroll
@@ -284,6 +423,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kT5Threads, 1)
           tc::mma2_tf32_ts_elect(dcol, a_hi + 8u * ks, desc_bhi + (uint64_t)((ks >> 2) * 1024 + (ks & 3) * 2), idesc, 1u);
         tc::mma2_tf32_elect(dcol, desc_ones, desc_bias, idesc, 1u);
         tc::mma2_commit_elect(&bar_mma);
+        T5TRACE(it, 2);
       }
     }
   } else if (warp < 4) {
@@ -297,6 +437,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kT5Threads, 1)
     asm volatile("" : "+r"(tf32_mask), "+r"(sign_bit));
     for (unsigned long long it = 0; it < my_pt; ++it) {
       if (it > 0) tc::mbar_wait_or_trap(&bar_mma, (uint32_t)(it - 1) & 1u);   // the MMAs of the previous tile have read A
+      if (warp == 0) T5TRACE(it, 3);
       tc::tc_fence_after();
 #pragma unroll 1
       for (int sl = 0; sl < NS; ++sl) {
@@ -320,10 +461,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kT5Threads, 1)
         if (lane == 0) tc::mbar_arrive(&bar_empty[s]);
         if (++s == kT5Stages) { s = 0; full_ph ^= 1u; }
       }
+      if (warp == 0) T5TRACE(it, 4);
       tc::tmem_st_wait();
       tc::tc_fence_before();
       __syncwarp();
       if (lane == 0) tc::mbar_arrive_cluster(&bar_aready, 0u);
+      if (warp == 0) T5TRACE(it, 5);
     }
   } else {
     // =============================== E: score the rows ===============================
@@ -333,53 +476,18 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kT5Threads, 1)
     for (unsigned long long it = 0; it < my_pt; ++it) {
       const unsigned long long row0 = tile_of(it) * 128ull;
       tc::mbar_wait_or_trap(&bar_mma, (uint32_t)it & 1u);
+      if (wq == 0) T5TRACE(it, 6);
       tc::tc_fence_after();
-      uint32_t m1 = 0u, m2 = 0u;   // running best / runner-up (packed); real scores are >= 2^e > 0
-#pragma unroll 1
-      for (int c0 = 0; c0 < kT5K; c0 += 32) {
-        uint32_t q[32];
-        tc::tmem_ld32(taddr + (uint32_t)c0, q);
-        tc::tmem_ld_wait();
-#pragma unroll
-        for (int c = 0; c < 32; ++c) q[c] = (q[c] << 8) | (uint32_t)(c0 + c);
-        uint32_t b0 = __vimax3_u32(q[0], q[1], q[2]), b1 = __vimax3_u32(q[3], q[4], q[5]);
-        uint32_t b2 = __vimax3_u32(q[6], q[7], q[8]), b3 = __vimax3_u32(q[9], q[10], q[11]);
-#pragma unroll
-        for (int c = 12; c + 7 < 32; c += 8) {
-          b0 = __vimax3_u32(b0, q[c], q[c + 1]);
-          b1 = __vimax3_u32(b1, q[c + 2], q[c + 3]);
-          b2 = __vimax3_u32(b2, q[c + 4], q[c + 5]);
-          b3 = __vimax3_u32(b3, q[c + 6], q[c + 7]);
-        }
-        b0 = __vimax3_u32(b0, q[28], q[29]);
-        b1 = __vimax3_u32(b1, q[30], q[31]);
-        const uint32_t cb = max(__vimax3_u32(b0, b1, b2), b3);
-        const uint32_t cm1 = cb - 1u;
-#pragma unroll
-        for (int c = 0; c < 32; ++c) q[c] = cm1 - q[c];   // the chunk's best wraps to 0xFFFFFFFF, the others are gap - 1
-        b0 = __vimin3_u32(q[0], q[1], q[2]); b1 = __vimin3_u32(q[3], q[4], q[5]);
-        b2 = __vimin3_u32(q[6], q[7], q[8]); b3 = __vimin3_u32(q[9], q[10], q[11]);
-#pragma unroll
-        for (int c = 12; c + 7 < 32; c += 8) {
-          b0 = __vimin3_u32(b0, q[c], q[c + 1]);
-          b1 = __vimin3_u32(b1, q[c + 2], q[c + 3]);
-          b2 = __vimin3_u32(b2, q[c + 4], q[c + 5]);
-          b3 = __vimin3_u32(b3, q[c + 6], q[c + 7]);
-        }
-        b0 = __vimin3_u32(b0, q[28], q[29]);
-        b1 = __vimin3_u32(b1, q[30], q[31]);
-        const uint32_t cs = cm1 - min(__vimin3_u32(b0, b1, b2), b3);   // runner-up of the chunk
-        // merge (cb, cs) into (m1, m2)
-        m2 = max(max(m2, cs), min(m1, cb));
-        m1 = max(m1, cb);
-      }
+      uint32_t m1, m2;   // best / runner-up (packed)
+      t5_top2(taddr, a.pack_mult, m1, m2);
       tc::tc_fence_before();
       __syncwarp();
       if (lane == 0) tc::mbar_arrive_cluster(&bar_accfree, 0u);   // the accumulator may be overwritten
-      const float v_best = __uint_as_float((m1 >> 8) | top_bits);
-      const float v_second = __uint_as_float((m2 >> 8) | top_bits);
+      if (wq == 0) T5TRACE(it, 7);
+      const float v_best = __uint_as_float((m1 >> 8) | win.top_bits);
+      const float v_second = __uint_as_float((m2 >> 8) | win.top_bits);
       const uint32_t bidx = m1 & 255u;
-      const bool certified = params_ok && ((v_best - v_second) > m_v) && bidx < (uint32_t)k;
+      const bool certified = win.ok && ((v_best - v_second) > win.m_v) && bidx < (uint32_t)k;
       const unsigned long long grow = row0 + (unsigned long long)row;
       // flag lists are double-buffered by tile parity: the other list's counter is cleared before this tile's
       // barrier, so that clearing and the next tile's appends are ordered by it
@@ -390,55 +498,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kT5Threads, 1)
       }
       if (row == 0) n_flag[(it + 1) & 1] = 0u;
       tc::nb_sync(1, 128);
+      if (wq == 0) T5TRACE(it, 8);
       const uint32_t nf = n_flag[it & 1];
       if (nf) {
-        // uncertified rows: the reference's scan (direct form in feature order, strict <), one warp per row; each
-        // lane walks the centroids c = lane, lane + 32, ... with the row read from global memory 32 features at a time
+        // uncertified rows: the reference's exact scan, one warp per row
         for (uint32_t f = (uint32_t)wq; f < nf; f += 4) {
           const unsigned long long fr = row0 + flags[f];
-          const float* xrow = a.X + fr * (unsigned long long)D;
-          float dacc[kT5K / 32];
-#pragma unroll
-          for (int i = 0; i < kT5K / 32; ++i) dacc[i] = 0.f;
-#pragma unroll 1
-          for (int j0 = 0; j0 < D; j0 += 32) {
-            float x2[32];
-#pragma unroll
-            for (int c = 0; c < 8; ++c) {
-              const float4 v = __ldg(reinterpret_cast<const float4*>(xrow + j0) + c);
-              x2[4 * c] = v.x; x2[4 * c + 1] = v.y; x2[4 * c + 2] = v.z; x2[4 * c + 3] = v.w;
-            }
-#pragma unroll
-            for (int i = 0; i < kT5K / 32; ++i) {
-              const int c = lane + 32 * i;
-              if (c < k) {
-                const float* cw = a.C + (size_t)c * D + j0;
-                float dd = dacc[i];
-#pragma unroll
-                for (int q4 = 0; q4 < 8; ++q4) {
-                  const float4 cv = __ldg(reinterpret_cast<const float4*>(cw) + q4);
-                  float df;
-                  df = __fsub_rn(cv.x, x2[4 * q4]); dd = __fadd_rn(dd, __fmul_rn(df, df));
-                  df = __fsub_rn(cv.y, x2[4 * q4 + 1]); dd = __fadd_rn(dd, __fmul_rn(df, df));
-                  df = __fsub_rn(cv.z, x2[4 * q4 + 2]); dd = __fadd_rn(dd, __fmul_rn(df, df));
-                  df = __fsub_rn(cv.w, x2[4 * q4 + 3]); dd = __fadd_rn(dd, __fmul_rn(df, df));
-                }
-                dacc[i] = dd;
-              }
-            }
-          }
-          float fb = INFINITY;
-          int fi = -1;
-#pragma unroll
-          for (int i = 0; i < kT5K / 32; ++i) {
-            const int c = lane + 32 * i;
-            if (c < k) {
-              // lane 0 starts with centroid 0 (sticky NaN like the reference); the others only take v < best
-              if (c == 0) { fb = dacc[i]; fi = 0; }
-              else if (dacc[i] < fb) { fb = dacc[i]; fi = c; }
-            }
-          }
-          combine_candidates<float>(32, fb, fi);
+          const int fi = t5_exact_label<D>(a.X, a.C, k, fr, lane);
           if (lane == 0) a.labels[fr] = (uint32_t)fi;
         }
         my_fallbacks += (row == 0) ? nf : 0u;
@@ -449,6 +515,207 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kT5Threads, 1)
   tc::tc_fence_before();
   __syncthreads();
   tc::cluster_sync_all();   // the peer may still be reading this CTA's operands / arriving on its barriers
+  if (warp == 8) tc::tmem_dealloc_pair(tmem, 512);
+}
+
+
+// =============================================================================================================
+// SCREENING variant of the pair kernel: ONE TF32 product (x_hi . c_hi + bias), the raw TMA slabs are the A operand.
+// The terms it leaves out (x_lo.c_hi, x_hi.c_lo, x_lo.c_lo <= (2^-9 + 2^-20) |x||c| per candidate) widen the
+// certificate; rows it cannot certify take the exact re-scan, so the labels are the same as with 3xTF32.  On data whose
+// clusters are separated by more than ~1 % of max|x| max|c| every row certifies and the kernel is HBM-bound
+// (17 MMAs per pair of tiles instead of 49, no operand staging by threads); the host probes one iteration and
+// falls back to the 3xTF32 kernel when more than 2 % of the rows had to be re-scanned.
+//
+//   P  warp 9     TMA ring of eight 32-feature slabs (two tiles in flight)
+//   M  warp 8     leader: per slab, waits for its own and (relayed by the peer's warp 8) the peer's copy, issues the
+//                 slab's 4 K-steps, and commits the slab back to both rings; after the tile's bias K-step a second
+//                 commit hands accumulator it & 1 to the E group of that parity.  Peer: relays its `full` barriers.
+//   E  warps 0-3 (even tiles) / 4-7 (odd tiles): as in the 3xTF32 kernel, double-buffered accumulators
+// =============================================================================================================
+constexpr int kT5sStages = 8;
+
+__host__ __device__ inline size_t tc5s_smem_bytes(int d) {
+  return (size_t)kT5sStages * 16384 + (size_t)(d / 32) * 16384 + 16384 + 1024 + kT5K * 4 + 4 * 128 * 4 + 1024;
+}
+
+template <int D>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kT5Threads, 1)
+    assign_tc5s_kernel(const Tc5Args a, const __grid_constant__ CUtensorMap tmap) {
+  static_assert(D == 64 || D == 128, "row width");
+  constexpr int NS = D / 32;
+  if (a.state != nullptr && a.state->done) return;
+  extern __shared__ __align__(16) unsigned char smem_unaligned[];
+  unsigned char* smem = smem_unaligned + ((1024u - (tc::smem_u32(smem_unaligned) & 1023u)) & 1023u);
+  const int t = threadIdx.x, lane = t & 31;
+  const int warp = __shfl_sync(0xffffffffu, t >> 5, 0);
+  const int k = a.k;
+  const uint32_t rank = tc::cluster_ctarank();
+  unsigned char* ring = smem;                                    // [kT5sStages][16 KB] raw slabs = A operands
+  unsigned char* b_hi = ring + (size_t)kT5sStages * 16384;       // [NS][16 KB]
+  unsigned char* b_bias = b_hi + (size_t)NS * 16384;
+  unsigned char* ones = b_bias + 16384;
+  float* nn_s = reinterpret_cast<float*>(ones + 1024);
+  uint32_t* flags_all = reinterpret_cast<uint32_t*>(nn_s + kT5K);   // [group][2][128]
+  __shared__ __align__(8) uint64_t bar_full[kT5sStages], bar_pfull[kT5sStages], bar_empty[kT5sStages], bar_mma[2], bar_accfree[2];
+  __shared__ uint32_t tmem_slot, n_flag[2][2], cmax_bits;
+
+  const unsigned long long n_tiles = (a.n + 127) / 128;
+  const unsigned long long n_pt = (n_tiles + 1) / 2;
+  const unsigned long long pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+  const unsigned long long my_pt = pair < n_pt ? (n_pt - pair + n_pairs - 1) / n_pairs : 0;
+  auto tile_of = [&](unsigned long long it) { return 2ull * (pair + it * n_pairs) + rank; };
+
+  if (warp == 8) tc::tmem_alloc_pair(&tmem_slot, 512);
+  if (t == 0) {
+    for (int s = 0; s < kT5sStages; ++s) {
+      tc::mbar_init(&bar_full[s], 1);
+      tc::mbar_init(&bar_pfull[s], 1);
+      tc::mbar_init(&bar_empty[s], 1);
+    }
+    for (int g = 0; g < 2; ++g) {
+      tc::mbar_init(&bar_mma[g], 1);
+      tc::mbar_init(&bar_accfree[g], 8);
+      n_flag[g][0] = 0;
+      n_flag[g][1] = 0;
+    }
+    tc::fence_mbar_init();
+    cmax_bits = 0;
+  }
+  for (int e = t; e < 1024 + 64; e += kT5Threads) reinterpret_cast<float4*>(b_bias)[e] = make_float4(0.f, 0.f, 0.f, 0.f);
+  __syncthreads();
+  t5_centroid_norms<D>(a.C, k, nn_s, &cmax_bits, t);
+  // this CTA's half of the centroids, raw: kind::tf32 reads them as c_hi
+  for (int item = t; item < 128 * NS * 8; item += kT5Threads) {
+    const int q = item & 7, s = (item >> 3) % NS, r = item / (8 * NS);
+    const int c = (int)rank * 128 + r;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (c < k) v = __ldg(reinterpret_cast<const float4*>(a.C + (size_t)c * D + s * 32) + q);
+    *reinterpret_cast<float4*>(b_hi + (uint32_t)s * 16384u + tc::sw128_offset((uint32_t)r, (uint32_t)q)) = v;
+  }
+  __syncthreads();
+  // both candidates together: 2 (2^-10 + 2^-10 + 2^-20) = 2^-8 (1 + 2^-11)
+  const T5Win win = t5_window<D>(__uint_as_float(__ldg(a.xmax2_bits)), __uint_as_float(cmax_bits), 1.001f * 3.90625e-3f);
+  if (t < 128) t5_write_bias(b_bias, ones, nn_s, win, (int)rank * 128 + t, k, t);
+  tc::fence_async_smem();
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::cluster_sync_all();
+  tc::tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+  unsigned int my_fallbacks = 0;
+#ifdef LKM_T5_TRACE
+  const long long trace_t0 = clock64();
+#endif
+
+  if (warp == 9) {
+    // =============================== P ===============================
+    if (lane == 0) {
+      int s = 0;
+      uint32_t use = 0;
+      for (unsigned long long it = 0; it < my_pt; ++it) {
+        const unsigned long long tile = min(tile_of(it), n_tiles - 1);
+        for (int sl = 0; sl < NS; ++sl) {
+          if (use > 0) tc::mbar_wait_or_trap(&bar_empty[s], (use - 1u) & 1u);
+          if (sl == 0) T5TRACE(it, 0);
+          if (sl == NS - 1) T5TRACE(it, 1);
+          tc::mbar_expect_tx(&bar_full[s], 16384u);
+          tc::tma_load_2d(ring + (size_t)s * 16384, &tmap, sl * 32, (int)(tile * 128), &bar_full[s]);
+          if (++s == kT5sStages) { s = 0; ++use; }
+        }
+      }
+    }
+  } else if (warp == 8) {
+    if (rank != 0) {
+      // =============================== relay: this CTA's slab has landed -> leader ===============================
+      int s = 0;
+      uint32_t ph = 0;
+      for (unsigned long long j = 0; j < my_pt * NS; ++j) {
+        tc::mbar_wait_or_trap(&bar_full[s], ph);
+        if (lane == 0) tc::mbar_arrive_cluster(&bar_pfull[s], 0u);   // plain arrive: a cluster-scope release costs a MEMBAR.GPU per slab (measured: 1000+ cycles, the bottleneck)
+        __syncwarp();
+        if (++s == kT5sStages) { s = 0; ph ^= 1u; }
+      }
+    } else {
+      // =============================== M ===============================
+      constexpr uint32_t idesc = tc::idesc_tf32(256, (uint32_t)kT5K);
+      const uint64_t desc_ring = tc::smem_desc_sw128(tc::smem_u32(ring));
+      const uint64_t desc_bhi = tc::smem_desc_sw128(tc::smem_u32(b_hi));
+      const uint64_t desc_bias = tc::smem_desc_sw128(tc::smem_u32(b_bias));
+      const uint64_t desc_ones = tc::smem_desc_sw128_alias(tc::smem_u32(ones));
+      const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem, 0);
+      int s = 0;
+      uint32_t ph = 0;
+      for (unsigned long long it = 0; it < my_pt; ++it) {
+        const uint32_t g = (uint32_t)it & 1u, u = (uint32_t)(it >> 1);
+        const uint32_t dcol = tmem_u + g * 256u;
+        if (u > 0) tc::mbar_wait_or_trap(&bar_accfree[g], (u - 1u) & 1u);
+        T5TRACE(it, 2);
+#pragma unroll 1
+        for (int sl = 0; sl < NS; ++sl) {
+          tc::mbar_wait_or_trap(&bar_full[s], ph);
+          if (sl == 0) T5TRACE(it, 3);
+          if (sl == NS - 1) T5TRACE(it, 5);
+          tc::mbar_wait_or_trap(&bar_pfull[s], ph);
+          if (sl == 0) T5TRACE(it, 4);
+          if (sl == NS - 1) T5TRACE(it, 6);
+          tc::tc_fence_after();
+          const uint64_t da = desc_ring + (uint64_t)(s * 1024), db = desc_bhi + (uint64_t)(sl * 1024);
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) tc::mma2_tf32_elect(dcol, da + 2u * ks, db + 2u * ks, idesc, (sl | ks) ? 1u : 0u);
+          tc::mma2_commit_elect(&bar_empty[s]);   // both CTAs: the slab may be refilled
+          if (++s == kT5sStages) { s = 0; ph ^= 1u; }
+        }
+        tc::mma2_tf32_elect(dcol, desc_ones, desc_bias, idesc, 1u);
+        tc::mma2_commit_elect(&bar_mma[g]);
+        T5TRACE(it, 7);
+      }
+    }
+  } else {
+    // =============================== E: group g scores the tiles it = g (mod 2) ===============================
+    const int g = warp >> 2, wq = warp & 3;
+    const int row = t & 127;
+    const uint32_t taddr = tmem + ((uint32_t)(wq * 32) << 16) + (uint32_t)g * 256u;
+    for (unsigned long long it = g; it < my_pt; it += 2) {
+      const uint32_t u = (uint32_t)(it >> 1);
+      const unsigned long long row0 = tile_of(it) * 128ull;
+      tc::mbar_wait_or_trap(&bar_mma[g], u & 1u);
+      if (wq == 0) T5TRACE(it, 8);
+      tc::tc_fence_after();
+      uint32_t m1, m2;
+      t5_top2(taddr, a.pack_mult, m1, m2);
+      tc::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive_cluster(&bar_accfree[g], 0u);
+      if (wq == 0) T5TRACE(it, 9);
+      const float v_best = __uint_as_float((m1 >> 8) | win.top_bits);
+      const float v_second = __uint_as_float((m2 >> 8) | win.top_bits);
+      const uint32_t bidx = m1 & 255u;
+      const bool certified = win.ok && ((v_best - v_second) > win.m_v) && bidx < (uint32_t)k;
+      const unsigned long long grow = row0 + (unsigned long long)row;
+      uint32_t* flags = flags_all + (g * 2 + (u & 1u)) * 128;
+      if (grow < a.n) {
+        if (certified) a.labels[grow] = bidx;
+        else flags[atomicAdd(&n_flag[g][u & 1u], 1u)] = (uint32_t)row;
+      }
+      if (row == 0) n_flag[g][(u + 1u) & 1u] = 0u;
+      tc::nb_sync(1 + g, 128);
+      const uint32_t nf = n_flag[g][u & 1u];
+      if (nf) {
+        for (uint32_t f = (uint32_t)wq; f < nf; f += 4) {
+          const unsigned long long fr = row0 + flags[f];
+          const int fi = t5_exact_label<D>(a.X, a.C, k, fr, lane);
+          if (lane == 0) a.labels[fr] = (uint32_t)fi;
+        }
+        my_fallbacks += (row == 0) ? nf : 0u;
+      }
+      if (wq == 0) T5TRACE(it, 10);
+    }
+    if (row == 0 && a.state && my_fallbacks) atomicAdd(&a.state->fallback_rows, (unsigned long long)my_fallbacks);
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::cluster_sync_all();
   if (warp == 8) tc::tmem_dealloc_pair(tmem, 512);
 }
 

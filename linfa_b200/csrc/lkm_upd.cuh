@@ -10,7 +10,7 @@
 // accumulator.  Blob-ordered data gives one segment of 32 rows per sub-tile; shuffled data gives many one-row
 // segments, taken four at a time so that their centroid loads and read-modify-writes overlap.
 //
-//   P  warp 16      one thread keeps the ring full: d/32 TMA boxes (32 rows x 32 features, row-major) and the
+//   P  warp 16      one thread keeps the ring full: one TMA box (32 full rows, row-major) and the
 //                   128 label bytes of the sub-tile per stage
 //   C  warps 0-15   as above; the stage is released when all 16 warps have arrived on its `empty` barrier
 #pragma once
@@ -95,8 +95,9 @@ __global__ void __launch_bounds__(kUpdThreads, 1) update_rows_kernel(const UpdAr
         if (use > 0) tc::mbar_wait_or_trap(&bar_empty[s], (use - 1u) & 1u);
         unsigned char* st = ring + (size_t)s * kStage;
         tc::mbar_expect_tx(&bar_full[s], kStage);
-#pragma unroll
-        for (int q = 0; q < QF; ++q) tc::tma_load_2d(st + q * 4096, &tmap, q * 32, (int)(j * kUpdSubRows), &bar_full[s]);
+        // one box of 32 full rows: the TMA unit works through a box one inner line at a time (measured ~8 cycles per
+        // line whatever its length), so 512-byte lines move four times as many bytes per cycle as 128-byte lines
+        tc::tma_load_2d(st, &tmap, 0, (int)(j * kUpdSubRows), &bar_full[s]);
         tc::bulk_load_1d(st + QF * 4096, a.labels + j * kUpdSubRows, 128u, &bar_full[s]);
         if (++s == R) { s = 0; ++use; }
       }
@@ -108,10 +109,12 @@ __global__ void __launch_bounds__(kUpdThreads, 1) update_rows_kernel(const UpdAr
     float* accf = acc + fo;
     int s = 0;
     uint32_t ph = 0;
+    uint32_t last_L = 0xFFFFFFFFu;
+    float last_cv = 0.f;
     for (unsigned long long j = j0; j < j1; ++j) {
       const unsigned char* st = ring + (size_t)s * kStage;
       tc::mbar_wait_or_trap(&bar_full[s], ph);
-      const float* xs = reinterpret_cast<const float*>(st + fs * 4096) + lane;   // row r at xs[r * 32]
+      const float* xs = reinterpret_cast<const float*>(st) + fs * 32 + lane;     // row r at xs[r * D]
       uint32_t lab = reinterpret_cast<const uint32_t*>(st + QF * 4096)[lane];
       if (j * kUpdSubRows + (unsigned)lane >= a.n) lab = 0xFFFFFFFFu;
       const uint32_t c = lab - (uint32_t)chunk_base;
@@ -130,8 +133,15 @@ __global__ void __launch_bounds__(kUpdThreads, 1) update_rows_kernel(const UpdAr
           }
         }
         float cv[4], av[4], sv[4], ev[4];
+        // the centroid coordinate comes from L2 (hundreds of cycles under load) and sits in front of the first
+        // subtraction: keep the last one, which is the one needed again while the rows of a cluster are contiguous
+        cv[0] = last_cv; av[0] = 0.f;
+        if (pm[0]) {
+          if (L[0] != last_L) { cv[0] = __ldg(Cf + (size_t)L[0] * D); last_L = L[0]; last_cv = cv[0]; }
+          av[0] = accf[(size_t)L[0] * D];
+        }
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
+        for (int q = 1; q < 4; ++q) {
           cv[q] = 0.f; av[q] = 0.f;
           if (pm[q]) { cv[q] = __ldg(Cf + (size_t)L[q] * D); av[q] = accf[(size_t)L[q] * D]; }
         }
@@ -140,7 +150,7 @@ __global__ void __launch_bounds__(kUpdThreads, 1) update_rows_kernel(const UpdAr
           float s0 = 0.f, s1 = 0.f, e0 = 0.f, e1 = 0.f;
 #pragma unroll
           for (int r = 0; r < kUpdSubRows; r += 2) {
-            const float x0 = xs[r * 32], x1 = xs[(r + 1) * 32];
+            const float x0 = xs[r * D], x1 = xs[(r + 1) * D];
             s0 += x0; s1 += x1;
             const float d0 = x0 - cv[0], d1 = x1 - cv[0];
             e0 = fmaf(d0, d0, e0); e1 = fmaf(d1, d1, e1);
@@ -155,7 +165,7 @@ __global__ void __launch_bounds__(kUpdThreads, 1) update_rows_kernel(const UpdAr
             while (p) {
               const int r = __ffs(p) - 1;
               p &= p - 1u;
-              const float x = xs[r * 32];
+              const float x = xs[r * D];
               sq += x;
               const float df = x - cv[q];
               eq = fmaf(df, df, eq);

@@ -183,6 +183,10 @@ class Context:
     def set_kernel_timing(self, on):
         self.check(_ffi.lib.lkm_set_kernel_timing(self.h, int(bool(on))))
 
+    def set_scoring_passes(self, passes):
+        """0 adaptive (default), 1 / 2 / 3 pin the tensor-core scoring variant (speed only, never results)."""
+        self.check(_ffi.lib.lkm_set_scoring_passes(self.h, int(passes)))
+
     def set_data(self, x):
         x = np.asarray(x)
         if x.ndim != 2:

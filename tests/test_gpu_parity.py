@@ -489,8 +489,12 @@ TCA_CASES = [(6000, 128, 256, 16, 30.0, False), (5000, 64, 1024, 40, 30.0, False
              (5000, 128, 100, 100, 0.3, True), (128 * 75, 128, 256, 64, 30.0, False), (4000, 64, 40, 3, 30.0, True)]
 
 
+@pytest.mark.parametrize("passes", [0, 1, 3])
 @pytest.mark.parametrize("n,d,k,k_true,spread,shuffle", TCA_CASES)
-def test_tc_assign_path_matches_oracle(lb, ctx, oracle, n, d, k, k_true, spread, shuffle):
+def test_tc_assign_path_matches_oracle(lb, ctx, oracle, n, d, k, k_true, spread, shuffle, passes):
+    """passes: 0 = adaptive, 1 = one-product screening variant of the pair kernel, 3 = 3xTF32 (same results)."""
+    if passes and not (d in (64, 128) and k <= 256):
+        pytest.skip("scoring passes only select between the variants of the pair kernel")
     dt = np.float32
     X, _ = blobs(n, d, k_true, dt, seed=n + k, spread=spread)
     if shuffle:
@@ -500,7 +504,11 @@ def test_tc_assign_path_matches_oracle(lb, ctx, oracle, n, d, k, k_true, spread,
     if k > n:
         init += (g.standard_normal(init.shape) * 0.01).astype(dt)
     ctx.set_data(X)
-    c, counts, inertia, st = ctx.lloyd_iters(init, 2, 0.0)
+    ctx.set_scoring_passes(passes)
+    try:
+        c, counts, inertia, st = ctx.lloyd_iters(init, 2, 0.0)
+    finally:
+        ctx.set_scoring_passes(0)
     assert st.assign_path == 2 and st.n_iter == 2
     cur = init
     for it in range(2):
@@ -517,8 +525,9 @@ def test_tc_assign_path_matches_oracle(lb, ctx, oracle, n, d, k, k_true, spread,
     print(f"fallback rows over 2 iterations: {st.fallback_rows} of {2 * n}")
 
 
+@pytest.mark.parametrize("passes", [1, 3])
 @pytest.mark.parametrize("scale,offset", [(1e-3, 0.0), (1e3, 0.0), (1.0, 5e3), (1e-20, 0.0), (1e15, 0.0)])
-def test_pair_kernel_magnitudes(lb, ctx, oracle, scale, offset):
+def test_pair_kernel_magnitudes(lb, ctx, oracle, scale, offset, passes):
     """assign_tc5_kernel: score window and certificate over 35 orders of magnitude and far from the origin."""
     dt = np.float32
     X, _ = blobs(9000, 128, 40, dt, seed=13, spread=30.0)
@@ -527,7 +536,11 @@ def test_pair_kernel_magnitudes(lb, ctx, oracle, scale, offset):
     X = X[g.permutation(len(X))].copy()
     init = X[g.choice(len(X), size=40, replace=False)].copy()
     ctx.set_data(X)
-    c, counts, inertia, st = ctx.lloyd_iters(init, 2, 0.0)
+    ctx.set_scoring_passes(passes)
+    try:
+        c, counts, inertia, st = ctx.lloyd_iters(init, 2, 0.0)
+    finally:
+        ctx.set_scoring_passes(0)
     assert st.assign_path == 2
     cur = init
     for _ in range(2):
@@ -540,7 +553,17 @@ def test_pair_kernel_magnitudes(lb, ctx, oracle, scale, offset):
         np.testing.assert_allclose(inertia, ref_inertia, rtol=2e-5)
 
 
-def test_pair_kernel_nan_inf_and_duplicates(lb, ctx, oracle):
+@pytest.mark.parametrize("passes", [1, 3])
+def test_pair_kernel_nan_inf_and_duplicates(lb, ctx, oracle, passes):
+    dt = np.float32
+    ctx.set_scoring_passes(passes)
+    try:
+        _pair_kernel_nan_inf_and_duplicates(ctx, oracle)
+    finally:
+        ctx.set_scoring_passes(0)
+
+
+def _pair_kernel_nan_inf_and_duplicates(ctx, oracle):
     dt = np.float32
     X, _ = blobs(3000, 64, 6, dt, seed=4)
     idx = list(range(0, 3000, 100)) + [0, 600]                  # 32 centroids, the last two duplicate earlier ones:
