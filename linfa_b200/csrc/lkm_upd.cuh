@@ -12,6 +12,9 @@
 //
 //   P  warp 16      one thread keeps the ring full: one TMA box (32 full rows, row-major) and the
 //                   128 label bytes of the sub-tile per stage
+//   R  warp 17      waits for the stage's `full` mbarrier and hands the stage to the consumers through a named
+//                   barrier: the 16 consumer warps block in the barrier unit instead of polling the mbarrier
+//                   (with all of them polling, two thirds of the executed instructions were wait loops)
 //   C  warps 0-15   as above; the stage is released when all 16 warps have arrived on its `empty` barrier
 #pragma once
 #include "lkm_tc3.cuh"
@@ -19,7 +22,7 @@
 namespace lkm {
 
 constexpr int kUpdConsumers = 16;
-constexpr int kUpdThreads = (kUpdConsumers + 1) * 32;
+constexpr int kUpdThreads = (kUpdConsumers + 2) * 32;
 constexpr int kUpdSubRows = 32;
 constexpr int kUpdMaxStages = 8;
 
@@ -102,18 +105,25 @@ __global__ void __launch_bounds__(kUpdThreads, 1) update_rows_kernel(const UpdAr
         if (++s == R) { s = 0; ++use; }
       }
     }
+  } else if (warp == kUpdConsumers + 1) {
+    int s = 0;
+    uint32_t ph = 0;
+    for (unsigned long long j = j0; j < j1; ++j) {
+      tc::mbar_wait_or_trap(&bar_full[s], ph);
+      tc::nb_arrive(1 + s, (kUpdConsumers + 1) * 32);
+      if (++s == R) { s = 0; ph ^= 1u; }
+    }
   } else {
     const int fs = warp % QF, cls = warp / QF;
     const int fo = fs * 32 + lane;             // feature owned by this lane
     const float* Cf = a.C + (size_t)chunk_base * D + fo;
     float* accf = acc + fo;
     int s = 0;
-    uint32_t ph = 0;
     uint32_t last_L = 0xFFFFFFFFu;
     float last_cv = 0.f;
     for (unsigned long long j = j0; j < j1; ++j) {
       const unsigned char* st = ring + (size_t)s * kStage;
-      tc::mbar_wait_or_trap(&bar_full[s], ph);
+      tc::nb_sync(1 + s, (kUpdConsumers + 1) * 32);
       const float* xs = reinterpret_cast<const float*>(st) + fs * 32 + lane;     // row r at xs[r * D]
       uint32_t lab = reinterpret_cast<const uint32_t*>(st + QF * 4096)[lane];
       if (j * kUpdSubRows + (unsigned)lane >= a.n) lab = 0xFFFFFFFFu;
@@ -184,7 +194,7 @@ __global__ void __launch_bounds__(kUpdThreads, 1) update_rows_kernel(const UpdAr
       }
       __syncwarp();
       if (lane == 0) tc::mbar_arrive(&bar_empty[s]);
-      if (++s == R) { s = 0; ph ^= 1u; }
+      if (++s == R) s = 0;
     }
   }
   // ---- per-CTA partials: accumulators as they are, inertia by warp butterflies and then in warp order ----
