@@ -211,8 +211,8 @@ lkm_status lkm_set_l2_flush(lkm_ctx* ctx, uint64_t bytes);
 lkm_status lkm_set_kernel_timing(lkm_ctx* ctx, int on);
 /* tensor-core scoring passes of the certified assignment kernels: 0 (default) adaptive — start with the cheapest
  * variant and switch to 3xTF32 when more than 2 % of the rows of an iteration needed the exact re-scan; 1 pins the
- * one-product screening variant (pair kernel, d in {64, 128}), 2 the two-product variant (d = 32 pipeline kernel),
- * 3 pins 3xTF32.  Results do not depend on it (uncertified rows are re-scanned exactly); only speed does. */
+ * one-product screening variant (pair kernel for d in {64, 128}, pipeline kernel for d = 32), 2 the two-product
+ * variant (d = 32 pipeline kernel only; the pair kernel then runs 3xTF32), 3 pins 3xTF32.  Results do not depend on it (uncertified rows are re-scanned exactly); only speed does. */
 lkm_status lkm_set_scoring_passes(lkm_ctx* ctx, int passes);
 
 #ifdef __cplusplus

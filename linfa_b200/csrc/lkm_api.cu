@@ -447,6 +447,10 @@ static cudaError_t launch_tc4(int kp, int passes, int grid, size_t smem, cudaStr
     if (kp == 32) return cudaLaunchKernelEx(&cfg, lloyd_tc4_kernel<32, 2>, arg, map);
     return cudaLaunchKernelEx(&cfg, lloyd_tc4_kernel<64, 2>, arg, map);
   }
+  if (passes == 1) {
+    if (kp == 32) return cudaLaunchKernelEx(&cfg, lloyd_tc4_kernel<32, 1>, arg, map);
+    return cudaLaunchKernelEx(&cfg, lloyd_tc4_kernel<64, 1>, arg, map);
+  }
   if (kp == 32) return cudaLaunchKernelEx(&cfg, lloyd_tc4_kernel<32, 3>, arg, map);
   return cudaLaunchKernelEx(&cfg, lloyd_tc4_kernel<64, 3>, arg, map);
 }
@@ -488,6 +492,7 @@ static lkm_status run_lloyd(lkm_ctx* ctx, F* dC2, uint64_t k, uint64_t max_iter,
       const bool vws = ctx->tc_variant == 544 && tc_kp <= 64 && tcws_smem_bytes((int)k, tc_kp) <= ctx->smem_optin;
       if (v3) {
         if (v4) tc4_nstages = tc4_stages((int)k, tc_kp, ctx->smem_optin - 1024);
+        if (v4) if (const char* ev = std::getenv("LKM_TC4_STAGES")) tc4_nstages = std::max(3, std::min(tc4_nstages, std::atoi(ev)));   // tuning aid
         tc_smem = v4 ? tc4_smem_bytes((int)k, tc_kp, tc4_nstages) : tc3_smem_bytes((int)k, tc_kp);
         const void* fn = v4 ? (tc_kp == 32 ? (const void*)lloyd_tc4_kernel<32, 3> : (const void*)lloyd_tc4_kernel<64, 3>)
                             : (tc_kp == 32 ? (const void*)lloyd_tc3_kernel<32> : (const void*)lloyd_tc3_kernel<64>);
@@ -495,6 +500,9 @@ static lkm_status run_lloyd(lkm_ctx* ctx, F* dC2, uint64_t k, uint64_t max_iter,
           const void* fn2 = tc_kp == 32 ? (const void*)lloyd_tc4_kernel<32, 2> : (const void*)lloyd_tc4_kernel<64, 2>;
           CK(cudaFuncSetAttribute(fn2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem));
           CK(cudaFuncSetAttribute(fn2, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
+          const void* fn1 = tc_kp == 32 ? (const void*)lloyd_tc4_kernel<32, 1> : (const void*)lloyd_tc4_kernel<64, 1>;
+          CK(cudaFuncSetAttribute(fn1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem));
+          CK(cudaFuncSetAttribute(fn1, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
         }
         CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem));
         CK(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
@@ -682,15 +690,15 @@ static lkm_status run_lloyd(lkm_ctx* ctx, F* dC2, uint64_t k, uint64_t max_iter,
 
   uint64_t launched = 0;
   const uint64_t batch = 16;
-  // pipeline kernel: scoring passes.  Two passes (x_hi only) certify well-separated data at a lower cost; when more
+  // pipeline kernel: scoring passes.  One pass (x_hi.c_hi) certifies well-separated data at the lowest cost; when more
   // than 2 % of the rows of a batch need the exact re-scan the loop switches to the 3xTF32 variant.  A data set that
   // has not been seen with two passes yet gets a one-iteration first batch, so a bad guess costs one iteration.
   const bool is_tc4 = use_tc && tc_threads == kT4Threads;
   int tc4_passes = 3;
   if (is_tc4) {
-    tc4_passes = ctx->tc4_passes_forced ? ctx->tc4_passes_forced : ((ctx->tc4_hard_epoch == ctx->data_epoch && ctx->own_X) ? 3 : 2);
+    tc4_passes = ctx->tc4_passes_forced ? ctx->tc4_passes_forced : ((ctx->tc4_hard_epoch == ctx->data_epoch && ctx->own_X) ? 3 : 1);
   }
-  bool tc4_probe = is_tc4 && !ctx->tc4_passes_forced && tc4_passes == 2 && !(ctx->tc4_easy_epoch == ctx->data_epoch && ctx->own_X);
+  bool tc4_probe = is_tc4 && !ctx->tc4_passes_forced && tc4_passes < 3 && !(ctx->tc4_easy_epoch == ctx->data_epoch && ctx->own_X);
   // pair kernel: the screening variant (one TF32 product) first, 3xTF32 when too many rows needed the exact re-scan
   int tc5_passes = 3;
   if (use_tc5) tc5_passes = ctx->tc5_passes_forced ? ctx->tc5_passes_forced : ((ctx->tc5_hard_epoch == ctx->data_epoch && ctx->own_X) ? 3 : 1);
@@ -788,7 +796,7 @@ static lkm_status run_lloyd(lkm_ctx* ctx, F* dC2, uint64_t k, uint64_t max_iter,
         if constexpr (std::is_same<F, float>::value) {
           if (use_upd) {
             UpdArgs ua{};
-            ua.n = n; ua.k = (int)k; ua.chunk_rows = upd_chunk; ua.stages = upd_stages;
+            ua.X = dX; ua.n = n; ua.k = (int)k; ua.chunk_rows = upd_chunk; ua.stages = upd_stages;
             ua.labels = ctx->labels.as<uint32_t>(); ua.C = Ccur;
             ua.part_sums = ctx->part_sums.as<float>(); ua.part_counts = ctx->part_counts.as<uint32_t>();
             ua.part_inertia = ctx->part_inertia.as<double>(); ua.state = dstate;
@@ -882,7 +890,7 @@ static lkm_status run_lloyd(lkm_ctx* ctx, F* dC2, uint64_t k, uint64_t max_iter,
     const uint64_t todo_done = todo;
     CK(cudaMemcpyAsync(ctx->h_state, dstate, sizeof(LloydState), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
-    if (is_tc4 && !ctx->tc4_passes_forced && tc4_passes == 2) {
+    if (is_tc4 && !ctx->tc4_passes_forced && tc4_passes < 3) {
       const unsigned long long fb = (ctx->h_state->fallback_rows & ((1ull << 40) - 1)) - fb_seen;
       if ((double)fb > 0.02 * (double)n * (double)todo_done) { tc4_passes = 3; ctx->tc4_hard_epoch = ctx->data_epoch; }
       else ctx->tc4_easy_epoch = ctx->data_epoch;
@@ -1818,8 +1826,8 @@ LKM_EXPORT lkm_status lkm_set_assign_path(lkm_ctx* ctx, int path) {
 
 LKM_EXPORT lkm_status lkm_set_scoring_passes(lkm_ctx* ctx, int passes) {
   if (!ctx || passes < 0 || passes > 3) return LKM_ERR_INVALID_ARG;
-  ctx->tc5_passes_forced = (passes == 1 || passes == 3) ? passes : 0;
-  ctx->tc4_passes_forced = (passes == 2 || passes == 3) ? passes : 0;
+  ctx->tc5_passes_forced = passes == 1 ? 1 : (passes >= 2 ? 3 : 0);
+  ctx->tc4_passes_forced = passes;
   return LKM_OK;
 }
 

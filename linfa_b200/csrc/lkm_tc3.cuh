@@ -41,6 +41,11 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* tmap, 
       ::"r"(smem_u32(dst)), "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
 }
+// hint: bring `bytes` (multiple of 16) at `src` into L2; the later TMA load of the same lines then sees L2 latency, so a
+// shared-memory ring of a few stages covers it (the ring alone would need HBM latency x bandwidth bytes in flight)
+__device__ __forceinline__ void l2_prefetch(const void* src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ void group_sync(int id) { asm volatile("bar.sync %0, 128;" ::"r"(id) : "memory"); }
 // K-major SW128 descriptor whose 8-row groups all alias the same 1 KB atom (SBO = 0): a constant tile
 __device__ __forceinline__ uint64_t smem_desc_sw128_alias(uint32_t saddr) {

@@ -29,6 +29,10 @@ constexpr int kT4Threads = 18 * 32;
 constexpr int kT4TmemCols = 512;   // D 2 x 64 | A_hi 2 x 32 | A_lo 2 x 32 | ones 8
 constexpr uint32_t kT4ColAhi = 128, kT4ColAlo = 192, kT4ColOnes = 256;
 constexpr int kT4MaxStages = 12;
+#ifndef LKM_T4_PREFETCH
+#define LKM_T4_PREFETCH 0
+#endif
+constexpr unsigned long long kT4Prefetch = LKM_T4_PREFETCH;   // L2 prefetch distance of the P role, in tiles beyond the ring's newest request
 constexpr int kNbLab = 2, kNbLfree = 4, kNbAlo = 6, kNbTfree = 8;   // named barrier ids (+ parity); 1 = U-internal
 constexpr int kT4Subsets = 8;      // U role: thread = (row subset of 8, feature pair)
 
@@ -211,6 +215,7 @@ __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.
 }  // namespace tc
 
 // PASSES = 3: x_lo.c_hi + x_hi.c_lo + x_hi.c_hi (3xTF32, A operands staged in TMEM by the S role).
+// PASSES = 1: x_hi.c_hi only (screening: 5 MMAs per tile instead of 13; same structure as PASSES = 2).
 // PASSES = 2: x_hi.c_lo + x_hi.c_hi only — the raw tile in shared memory is the A operand, the S role is idle, and the
 // dropped x_lo.c term (|x_lo.c| <= 2^-10 |x||c|) widens the certificate; rows it no longer certifies take the exact
 // re-scan, so results are identical.  The host starts with 2 passes and switches to 3 when too many rows fall back.
@@ -278,6 +283,10 @@ __global__ void __launch_bounds__(kT4Threads, 1) lloyd_tc4_kernel(const Tc4Args 
       tc::mbar_expect_tx(&bar_full[produced], 16384u);
       tc::tma_load_2d(raw + (size_t)produced * 16384, &tmap, 0, (int)(tile_of(produced) * kTcRows), &bar_full[produced]);
     }
+    for (unsigned long long j = produced; j < my_tiles && j < produced + kT4Prefetch; ++j) {
+      const unsigned long long r0 = tile_of(j) * kTcRows;
+      tc::l2_prefetch(a.X + r0 * 32ull, (uint32_t)min((unsigned long long)kTcRows, a.n - r0) * 128u);
+    }
   }
   // everything that does not depend on the previous kernel's centroids happens before the dependency wait
   for (int e = t; e < kT4Subsets * (k + 1) * 32; e += kT4Threads) acc[e] = 0.f;
@@ -330,7 +339,8 @@ __global__ void __launch_bounds__(kT4Threads, 1) lloyd_tc4_kernel(const Tc4Args 
   // v is half a squared distance.  On each of the two candidates: the bias K-step rounds at most 3 ulp(v), the
   // f32 bias K0 - nn/2 is off by at most 2^-24 K0 + (d + 1) 2^-25 |c|^2 (rounding of the norm and of the subtraction)
   const float m_v = 0.5f * m_w + 7.f * 1.1920929e-7f * (K0 + Rb) + 33.f * 5.9604645e-8f * cmax2 +
-                    (PASSES == 2 ? 1.001f * 1.953125e-3f * xmax * cmax : 0.f);   // + 2 * 2^-10 |x||c| without the x_lo pass (|x_lo| < 2^-10 |x| element-wise)
+                    (PASSES == 2 ? 1.001f * 1.953125e-3f * xmax * cmax : 0.f) +   // + 2 * 2^-10 |x||c| without the x_lo pass (|x_lo| < 2^-10 |x| element-wise)
+                    (PASSES == 1 ? 1.001f * 3.90625e-3f * xmax * cmax : 0.f);     // + 2 (2^-9 + 2^-20) |x||c| with x_hi.c_hi alone
   if (t < KP) {
     // bias row t: K0 - |c|^2/2 as three TF32 pieces that add up to the f32 value exactly, K-step 0 of the tile
     const float b = (t < k) ? (K0 - 0.5f * nn_s[t]) : two_lo;
@@ -381,6 +391,10 @@ __global__ void __launch_bounds__(kT4Threads, 1) lloyd_tc4_kernel(const Tc4Args 
         tc::mbar_expect_tx(&bar_full[s], 16384u);
         tc::tma_load_2d(raw + (size_t)s * 16384, &tmap, 0, (int)(tile_of(j) * kTcRows), &bar_full[s]);
         T4TRACE(j, 0);
+        if (j + kT4Prefetch < my_tiles) {
+          const unsigned long long r0 = tile_of(j + kT4Prefetch) * kTcRows;
+          tc::l2_prefetch(a.X + r0 * 32ull, (uint32_t)min((unsigned long long)kTcRows, a.n - r0) * 128u);
+        }
       }
     }
   } else if (warp == 17) {
@@ -407,10 +421,12 @@ __global__ void __launch_bounds__(kT4Threads, 1) lloyd_tc4_kernel(const Tc4Args 
           for (int ks = 0; ks < 4; ++ks) tc::mma_tf32_ts_elect(dcol, a_hi + 8u * ks, desc_bhi + 2u * ks, idesc, 1u);
         } else {
           const uint64_t da = desc_raw + (uint64_t)stage * 1024u;   // 16 KB per stage, 16-byte units
+          if constexpr (PASSES == 2) {
 #pragma unroll
-          for (int ks = 0; ks < 4; ++ks) tc::mma_tf32_elect(dcol, da + 2u * ks, desc_blo + 2u * ks, idesc, ks ? 1u : 0u);
+            for (int ks = 0; ks < 4; ++ks) tc::mma_tf32_elect(dcol, da + 2u * ks, desc_blo + 2u * ks, idesc, ks ? 1u : 0u);
+          }
 #pragma unroll
-          for (int ks = 0; ks < 4; ++ks) tc::mma_tf32_elect(dcol, da + 2u * ks, desc_bhi + 2u * ks, idesc, 1u);
+          for (int ks = 0; ks < 4; ++ks) tc::mma_tf32_elect(dcol, da + 2u * ks, desc_bhi + 2u * ks, idesc, (PASSES == 2 || ks) ? 1u : 0u);
         }
         tc::mma_tf32_ts_elect(dcol, tmem_u + kT4ColOnes, desc_bias, idesc, 1u);
       };

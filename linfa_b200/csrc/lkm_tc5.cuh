@@ -27,6 +27,7 @@ namespace lkm {
 constexpr int kT5Threads = 10 * 32;
 constexpr int kT5Stages = 4;
 constexpr uint32_t kT5ColAcc = 0, kT5ColA = 256;
+constexpr unsigned long long kT5Prefetch = 3;   // L2 prefetch distance of the P roles, in tiles
 constexpr int kT5K = 256;   // score columns = centroid rows of one MMA (128 per CTA)
 
 struct Tc5Args {
@@ -391,6 +392,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kT5Threads, 1)
           if (use > 0) tc::mbar_wait_or_trap(&bar_empty[s], (use - 1u) & 1u);
           tc::mbar_expect_tx(&bar_full[s], 16384u);
           tc::tma_load_2d(ring + (size_t)s * 16384, &tmap, sl * 32, (int)(tile * 128), &bar_full[s]);
+          if (sl == 0 && it + kT5Prefetch < my_pt) {
+            const unsigned long long r0 = tile_of(it + kT5Prefetch) * 128ull;   // 128 full rows are contiguous
+            if (r0 < a.n) tc::l2_prefetch(a.X + r0 * (unsigned long long)D, (uint32_t)min(128ull, a.n - r0) * (uint32_t)(D * 4));
+          }
           if (++s == kT5Stages) { s = 0; ++use; }
         }
       }
@@ -621,6 +626,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kT5Threads, 1)
           if (sl == NS - 1) T5TRACE(it, 1);
           tc::mbar_expect_tx(&bar_full[s], 16384u);
           tc::tma_load_2d(ring + (size_t)s * 16384, &tmap, sl * 32, (int)(tile * 128), &bar_full[s]);
+          if (sl == 0 && it + kT5Prefetch < my_pt) {
+            const unsigned long long r0 = tile_of(it + kT5Prefetch) * 128ull;   // 128 full rows are contiguous
+            if (r0 < a.n) tc::l2_prefetch(a.X + r0 * (unsigned long long)D, (uint32_t)min(128ull, a.n - r0) * (uint32_t)(D * 4));
+          }
           if (++s == kT5sStages) { s = 0; ++use; }
         }
       }

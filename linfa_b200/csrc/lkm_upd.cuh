@@ -25,8 +25,10 @@ constexpr int kUpdConsumers = 16;
 constexpr int kUpdThreads = (kUpdConsumers + 2) * 32;
 constexpr int kUpdSubRows = 32;
 constexpr int kUpdMaxStages = 8;
+constexpr unsigned long long kUpdPrefetch = 12;   // L2 prefetch distance in sub-tiles beyond the ring's newest request
 
 struct UpdArgs {
+  const float* X;              // for L2 prefetches (the loads themselves go through the tensor map)
   unsigned long long n;
   int k;
   int chunk_rows;              // clusters per chunk; blockIdx.y = chunk, chunk c owns [c * chunk_rows, ...)
@@ -101,6 +103,10 @@ __global__ void __launch_bounds__(kUpdThreads, 1) update_rows_kernel(const UpdAr
         // one box of 32 full rows: the TMA unit works through a box one inner line at a time (measured ~8 cycles per
         // line whatever its length), so 512-byte lines move four times as many bytes per cycle as 128-byte lines
         tc::tma_load_2d(st, &tmap, 0, (int)(j * kUpdSubRows), &bar_full[s]);
+        if (j + kUpdPrefetch < j1) {
+          const unsigned long long r0 = (j + kUpdPrefetch) * kUpdSubRows;
+          tc::l2_prefetch(a.X + r0 * (unsigned long long)D, (uint32_t)min((unsigned long long)kUpdSubRows, a.n - r0) * (uint32_t)(D * 4));
+        }
         tc::bulk_load_1d(st + QF * 4096, a.labels + j * kUpdSubRows, 128u, &bar_full[s]);
         if (++s == R) { s = 0; ++use; }
       }

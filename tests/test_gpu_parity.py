@@ -606,8 +606,9 @@ PIPE_CASES = [
 ]
 
 
+@pytest.mark.parametrize("passes", [0, 1, 2, 3])
 @pytest.mark.parametrize("n,k,k_true,spread,shuffle", PIPE_CASES)
-def test_pipeline_kernel_matches_oracle(lb, ctx, oracle, n, k, k_true, spread, shuffle):
+def test_pipeline_kernel_matches_oracle(lb, ctx, oracle, n, k, k_true, spread, shuffle, passes):
     dt = np.float32
     X, _ = blobs(n, 32, k_true, dt, seed=7 * n + k, spread=spread)
     g = np.random.default_rng(n + k)
@@ -615,12 +616,14 @@ def test_pipeline_kernel_matches_oracle(lb, ctx, oracle, n, k, k_true, spread, s
         X = X[g.permutation(n)].copy()
     init = X[g.choice(n, size=k, replace=False)].copy()
     ctx.set_assign_path(2)
+    ctx.set_scoring_passes(passes)
     try:
         ctx.set_data(X)
         c, counts, inertia, st = ctx.lloyd_iters(init, 4, 0.0)
         assert st.assign_path == 2 and st.n_iter == 4
     finally:
         ctx.set_assign_path(-1)
+        ctx.set_scoring_passes(0)
     cur, (lab, d) = _oracle_iters(oracle, X, init, 4)
     scale = np.abs(cur).max()
     np.testing.assert_allclose(c, cur, rtol=1e-5, atol=1e-5 * scale)
