@@ -103,7 +103,7 @@ struct lkm_ctx {
   int tc5_enabled = 1;   // LKM_TC5=0: tc_assign_kernel instead of the CTA-pair assignment kernel
   int upd_variant = 1;   // LKM_UPD=0: cluster-chunked lloyd_kernel<MODE_UPDATE> instead of update_rows_kernel
   uint64_t data_epoch = 1, xmax2_epoch = 0;  // resident-data version / version the cached max row norm belongs to
-  DevBuf xmax2, t4prof;
+  DevBuf xmax2, t4prof, t5merge;
   int tc4_passes_forced = 0;              // LKM_TC4_PASSES = 2 / 3 pins the scoring passes of the pipeline kernel
   uint64_t tc4_hard_epoch = 0, tc4_easy_epoch = 0;   // data versions seen to need 3 passes / to be fine with 2
   uint64_t flush_bytes = 0;
@@ -550,7 +550,7 @@ static lkm_status run_lloyd(lkm_ctx* ctx, F* dC2, uint64_t k, uint64_t max_iter,
     // shapes of the CTA-pair assignment kernel: two-pass (tensor-core assignment + streaming update) even when the
     // centroids would fit the fused CUDA-core kernel, unless the contraction is tiny
     if (!use_tc && (ctx->force_path == -1 || ctx->force_path == 2) && ctx->tc5_enabled && ctx->upd_variant != 0 &&
-        (d == 64 || d == 128) && k <= (uint64_t)kT5K && kd >= 2048 && n >= 1 && (reinterpret_cast<uintptr_t>(dX) & 15) == 0)
+        (d == 64 || d == 128) && k <= (uint64_t)kT5K * 16 && kd >= 2048 && n >= 1 && (reinterpret_cast<uintptr_t>(dX) & 15) == 0)
       pf.fused = false;
   }
   ctx->last_path = use_tc ? 2 : ((pf.fused && pf.certified) ? 1 : 0);
@@ -632,12 +632,12 @@ static lkm_status run_lloyd(lkm_ctx* ctx, F* dC2, uint64_t k, uint64_t max_iter,
   }
   // CTA-pair assignment kernel (lkm_tc5.cuh): all centroid operand tiles resident across the two CTAs of a cluster
   bool use_tc5 = false;
-  int tc5_grid = 0;
+  int tc5_grid = 0, tc5_chunks = 1;
   size_t tc5_smem = 0;
   CUtensorMap tc5_map;
   std::memset(&tc5_map, 0, sizeof(tc5_map));
   if constexpr (std::is_same<F, float>::value) {
-    if (use_upd && ctx->tc5_enabled && (d == 64 || d == 128) && k <= (uint64_t)kT5K && n + 512 < (1ull << 31) &&
+    if (use_upd && ctx->tc5_enabled && (d == 64 || d == 128) && k <= (uint64_t)kT5K * 16 && n + 512 < (1ull << 31) &&
         tc5_smem_bytes((int)d) <= ctx->smem_optin && tc5s_smem_bytes((int)d) <= ctx->smem_optin) {
       tc5_smem = tc5_smem_bytes((int)d);
       const void* fn = d == 64 ? (const void*)assign_tc5_kernel<64> : (const void*)assign_tc5_kernel<128>;
@@ -657,6 +657,8 @@ static lkm_status run_lloyd(lkm_ctx* ctx, F* dC2, uint64_t k, uint64_t max_iter,
       }
       const uint64_t n_pt = ((n + 127) / 128 + 1) / 2;
       tc5_grid = 2 * (int)std::max<uint64_t>(1, std::min<uint64_t>(n_pt, (uint64_t)(ctx->sm_count / 2)));
+      tc5_chunks = (int)((k + kT5K - 1) / kT5K);
+      if (tc5_chunks > 1) CK(ctx->t5merge.ensure((n + 256) * 16));
       use_tc5 = true;
     }
   }
@@ -755,17 +757,22 @@ static lkm_status run_lloyd(lkm_ctx* ctx, F* dC2, uint64_t k, uint64_t max_iter,
             Tc5Args t5{};
             t5.X = dX; t5.n = n; t5.k = (int)k; t5.C = Ccur; t5.xmax2_bits = ctx->xmax2.as<unsigned int>();
             t5.labels = ctx->labels.as<uint32_t>(); t5.state = dstate; t5.pack_mult = 256u;
+            t5.n_chunks = tc5_chunks; t5.merge = tc5_chunks > 1 ? ctx->t5merge.as<uint4>() : nullptr;
 #ifdef LKM_T5_TRACE
             CK(ctx->t4prof.ensure(2 * 16 * 16 * 8));
             t5.prof = ctx->t4prof.as<long long>();
 #endif
-            if (tc5_passes == 1) {
-              if (d == 64) assign_tc5s_kernel<64><<<tc5_grid, kT5Threads, tc5s_smem_bytes(64), ctx->stream>>>(t5, tc5_map);
-              else assign_tc5s_kernel<128><<<tc5_grid, kT5Threads, tc5s_smem_bytes(128), ctx->stream>>>(t5, tc5_map);
-            } else if (d == 64) assign_tc5_kernel<64><<<tc5_grid, kT5Threads, tc5_smem, ctx->stream>>>(t5, tc5_map);
-            else assign_tc5_kernel<128><<<tc5_grid, kT5Threads, tc5_smem, ctx->stream>>>(t5, tc5_map);
-            CK(cudaGetLastError());
-            ctx->launches++;
+            // one launch per chunk of 256 centroids; the per-row (best, runner-up) state travels through t5merge
+            for (int ch = 0; ch < tc5_chunks; ++ch) {
+              t5.chunk_idx = ch;
+              if (tc5_passes == 1) {
+                if (d == 64) assign_tc5s_kernel<64><<<tc5_grid, kT5Threads, tc5s_smem_bytes(64), ctx->stream>>>(t5, tc5_map);
+                else assign_tc5s_kernel<128><<<tc5_grid, kT5Threads, tc5s_smem_bytes(128), ctx->stream>>>(t5, tc5_map);
+              } else if (d == 64) assign_tc5_kernel<64><<<tc5_grid, kT5Threads, tc5_smem, ctx->stream>>>(t5, tc5_map);
+              else assign_tc5_kernel<128><<<tc5_grid, kT5Threads, tc5_smem, ctx->stream>>>(t5, tc5_map);
+              CK(cudaGetLastError());
+              ctx->launches++;
+            }
             assigned = true;
           } else if (use_tca) {
             // tensor-core assignment: split the centroids into TF32 operand tiles, then score

@@ -33,7 +33,9 @@ constexpr int kT5K = 256;   // score columns = centroid rows of one MMA (128 per
 struct Tc5Args {
   const float* X;
   unsigned long long n;
-  int k;
+  int k;                            // all centroids
+  int chunk_idx, n_chunks;          // this launch scores centroids [256 chunk_idx, min(k, 256 (chunk_idx + 1)))
+  uint4* merge;                     // n_chunks > 1: per row {best, runner-up, chunk of best, -} carried between the launches
   const float* C;
   const unsigned int* xmax2_bits;   // max_i |x_i|^2 of the resident matrix (row_norm2_max_wide_kernel)
   uint32_t* labels;
@@ -173,15 +175,16 @@ __device__ __forceinline__ T5Win t5_window(float xmax2, float cmax2_raw, float d
   return w;
 }
 
-// squared norms of all centroids into nn_s[256] (8 threads per row) and their maximum (bits) into *cmax_bits; all
-// threads of the CTA call it
+// squared norms (8 threads per row): their maximum over ALL k centroids (bits) into *cmax_bits — every chunk launch
+// must use the same score window —, the norms of this launch's chunk into nn_s[256]; all threads of the CTA call it
 template <int D>
-__device__ __forceinline__ void t5_centroid_norms(const float* __restrict__ C, int k, float* nn_s, uint32_t* cmax_bits, int t) {
-  for (int base = 0; base < kT5K * 8; base += kT5Threads) {
+__device__ __forceinline__ void t5_centroid_norms(const float* __restrict__ C, int k, int chunk_base, float* nn_s, uint32_t* cmax_bits,
+                                                  int t) {
+  for (int base = 0; base < k * 8; base += kT5Threads) {
     const int item = base + t;
     const int r = item >> 3, c8 = item & 7;
     float nn = 0.f;
-    if (item < kT5K * 8 && r < k) {
+    if (r < k) {
 #pragma unroll
       for (int q = 0; q < D / 32; ++q) {
         const float4 v = __ldg(reinterpret_cast<const float4*>(C + (size_t)r * D) + c8 + 8 * q);
@@ -191,9 +194,9 @@ __device__ __forceinline__ void t5_centroid_norms(const float* __restrict__ C, i
     nn += __shfl_xor_sync(0xffffffffu, nn, 1);
     nn += __shfl_xor_sync(0xffffffffu, nn, 2);
     nn += __shfl_xor_sync(0xffffffffu, nn, 4);
-    if (item < kT5K * 8 && c8 == 0) {
-      nn_s[r] = nn;   // |nn - |c|^2| <= (d + 1) 2^-24 |c|^2 whatever the summation order
-      if (r < k) atomicMax(cmax_bits, __float_as_uint(nn));   // a NaN norm wins and voids every certificate
+    if (r < k && c8 == 0) {
+      if (r >= chunk_base && r < chunk_base + kT5K) nn_s[r - chunk_base] = nn;   // |nn - |c|^2| <= (d + 1) 2^-24 |c|^2
+      atomicMax(cmax_bits, __float_as_uint(nn));   // a NaN norm wins and voids every certificate
     }
   }
 }
@@ -257,54 +260,79 @@ __device__ __forceinline__ void t5_top2(uint32_t taddr, uint32_t mult, uint32_t&
 }
 
 // The reference's scan of row fr (direct form in feature order, strict <) by one warp: each lane walks the centroids
-// c = lane, lane + 32, ... with the row read from global memory 32 features at a time.  Returns the label.
+// c = lane, lane + 32, ... (256 at a time) with the row read from global memory 32 features at a time.  Returns the label.
 template <int D>
 __device__ __forceinline__ int t5_exact_label(const float* __restrict__ X, const float* __restrict__ C, int k, unsigned long long fr,
                                               int lane) {
   const float* xrow = X + fr * (unsigned long long)D;
-  float dacc[kT5K / 32];
-#pragma unroll
-  for (int i = 0; i < kT5K / 32; ++i) dacc[i] = 0.f;
+  float fb = INFINITY;
+  int fi = -1;
 #pragma unroll 1
-  for (int j0 = 0; j0 < D; j0 += 32) {
-    float x2[32];
+  for (int cb = 0; cb < k; cb += kT5K) {
+    float dacc[kT5K / 32];
 #pragma unroll
-    for (int c = 0; c < 8; ++c) {
-      const float4 v = __ldg(reinterpret_cast<const float4*>(xrow + j0) + c);
-      x2[4 * c] = v.x; x2[4 * c + 1] = v.y; x2[4 * c + 2] = v.z; x2[4 * c + 3] = v.w;
+    for (int i = 0; i < kT5K / 32; ++i) dacc[i] = 0.f;
+#pragma unroll 1
+    for (int j0 = 0; j0 < D; j0 += 32) {
+      float x2[32];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(xrow + j0) + c);
+        x2[4 * c] = v.x; x2[4 * c + 1] = v.y; x2[4 * c + 2] = v.z; x2[4 * c + 3] = v.w;
+      }
+#pragma unroll
+      for (int i = 0; i < kT5K / 32; ++i) {
+        const int c = cb + lane + 32 * i;
+        if (c < k) {
+          const float* cw = C + (size_t)c * D + j0;
+          float dd = dacc[i];
+#pragma unroll
+          for (int q4 = 0; q4 < 8; ++q4) {
+            const float4 cv = __ldg(reinterpret_cast<const float4*>(cw) + q4);
+            float df;
+            df = __fsub_rn(cv.x, x2[4 * q4]); dd = __fadd_rn(dd, __fmul_rn(df, df));
+            df = __fsub_rn(cv.y, x2[4 * q4 + 1]); dd = __fadd_rn(dd, __fmul_rn(df, df));
+            df = __fsub_rn(cv.z, x2[4 * q4 + 2]); dd = __fadd_rn(dd, __fmul_rn(df, df));
+            df = __fsub_rn(cv.w, x2[4 * q4 + 3]); dd = __fadd_rn(dd, __fmul_rn(df, df));
+          }
+          dacc[i] = dd;
+        }
+      }
     }
 #pragma unroll
     for (int i = 0; i < kT5K / 32; ++i) {
-      const int c = lane + 32 * i;
+      const int c = cb + lane + 32 * i;
       if (c < k) {
-        const float* cw = C + (size_t)c * D + j0;
-        float dd = dacc[i];
-#pragma unroll
-        for (int q4 = 0; q4 < 8; ++q4) {
-          const float4 cv = __ldg(reinterpret_cast<const float4*>(cw) + q4);
-          float df;
-          df = __fsub_rn(cv.x, x2[4 * q4]); dd = __fadd_rn(dd, __fmul_rn(df, df));
-          df = __fsub_rn(cv.y, x2[4 * q4 + 1]); dd = __fadd_rn(dd, __fmul_rn(df, df));
-          df = __fsub_rn(cv.z, x2[4 * q4 + 2]); dd = __fadd_rn(dd, __fmul_rn(df, df));
-          df = __fsub_rn(cv.w, x2[4 * q4 + 3]); dd = __fadd_rn(dd, __fmul_rn(df, df));
-        }
-        dacc[i] = dd;
+        // lane 0 starts with centroid 0 (sticky NaN like the reference); the others only take v < best
+        if (c == 0) { fb = dacc[i]; fi = 0; }
+        else if (dacc[i] < fb) { fb = dacc[i]; fi = c; }
       }
-    }
-  }
-  float fb = INFINITY;
-  int fi = -1;
-#pragma unroll
-  for (int i = 0; i < kT5K / 32; ++i) {
-    const int c = lane + 32 * i;
-    if (c < k) {
-      // lane 0 starts with centroid 0 (sticky NaN like the reference); the others only take v < best
-      if (c == 0) { fb = dacc[i]; fi = 0; }
-      else if (dacc[i] < fb) { fb = dacc[i]; fi = c; }
     }
   }
   combine_candidates<float>(32, fb, fi);
   return fi;
+}
+
+// Folds this launch's packed (best, runner-up) of row `grow` into the state of the earlier chunks; on the last chunk
+// decides: 1 = certified (label set), 2 = needs the exact re-scan, 0 = nothing to do yet / row past the end.
+__device__ __forceinline__ int t5_merge_certify(const Tc5Args& a, const T5Win& win, unsigned long long grow, uint32_t m1, uint32_t m2,
+                                                uint32_t& label) {
+  if (grow >= a.n) return 0;
+  uint32_t ch1 = (uint32_t)a.chunk_idx;
+  if (a.chunk_idx > 0) {
+    const uint4 p = a.merge[grow];
+    // packed values order by score first; equal scores in different chunks end as best / runner-up with gap 0: uncertified
+    if (m1 > p.x) { m2 = max(p.x, m2); }
+    else { m2 = max(p.y, m1); m1 = p.x; ch1 = p.z; }
+  }
+  if (a.chunk_idx + 1 < a.n_chunks) {
+    a.merge[grow] = make_uint4(m1, m2, ch1, 0u);
+    return 0;
+  }
+  const float v_best = __uint_as_float((m1 >> 8) | win.top_bits);
+  const float v_second = __uint_as_float((m2 >> 8) | win.top_bits);
+  label = ch1 * (uint32_t)kT5K + (m1 & 255u);
+  return (win.ok && ((v_best - v_second) > win.m_v) && label < (uint32_t)a.k) ? 1 : 2;
 }
 
 template <int D>
@@ -318,7 +346,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kT5Threads, 1)
   unsigned char* smem = smem_unaligned + ((1024u - (tc::smem_u32(smem_unaligned) & 1023u)) & 1023u);
   const int t = threadIdx.x, lane = t & 31;
   const int warp = __shfl_sync(0xffffffffu, t >> 5, 0);
-  const int k = a.k;
+  const int chunk_base = a.chunk_idx * kT5K;
+  const int k = min(kT5K, a.k - chunk_base);   // centroids of this launch's chunk
+  const float* Cc = a.C + (size_t)chunk_base * D;
   const uint32_t rank = tc::cluster_ctarank();
   unsigned char* ring = smem;                                   // [kT5Stages][16 KB] raw slabs
   unsigned char* b_hi = ring + (size_t)kT5Stages * 16384;       // [NS][16 KB]: this CTA's 128 centroids, K-major SW128
@@ -353,13 +383,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kT5Threads, 1)
   }
   for (int e = t; e < 1024 + 64; e += kT5Threads) reinterpret_cast<float4*>(b_bias)[e] = make_float4(0.f, 0.f, 0.f, 0.f);   // bias tile + ones atom
   __syncthreads();
-  t5_centroid_norms<D>(a.C, k, nn_s, &cmax_bits, t);
+  t5_centroid_norms<D>(a.C, a.k, chunk_base, nn_s, &cmax_bits, t);
   // ---- this CTA's half of the centroids as TF32 hi / lo operand slabs ----
   for (int item = t; item < 128 * NS * 8; item += kT5Threads) {
     const int q = item & 7, s = (item >> 3) % NS, r = item / (8 * NS);
     const int c = (int)rank * 128 + r;
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (c < k) v = __ldg(reinterpret_cast<const float4*>(a.C + (size_t)c * D + s * 32) + q);
+    if (c < k) v = __ldg(reinterpret_cast<const float4*>(Cc + (size_t)c * D + s * 32) + q);
     float4 h, l;
     tc::split_tf32(v.x, h.x, l.x); tc::split_tf32(v.y, h.y, l.y);
     tc::split_tf32(v.z, h.z, l.z); tc::split_tf32(v.w, h.w, l.w);
@@ -489,16 +519,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kT5Threads, 1)
       __syncwarp();
       if (lane == 0) tc::mbar_arrive_cluster(&bar_accfree, 0u);   // the accumulator may be overwritten
       if (wq == 0) T5TRACE(it, 7);
-      const float v_best = __uint_as_float((m1 >> 8) | win.top_bits);
-      const float v_second = __uint_as_float((m2 >> 8) | win.top_bits);
-      const uint32_t bidx = m1 & 255u;
-      const bool certified = win.ok && ((v_best - v_second) > win.m_v) && bidx < (uint32_t)k;
       const unsigned long long grow = row0 + (unsigned long long)row;
+      uint32_t bidx = 0u;
+      const int verdict = t5_merge_certify(a, win, grow, m1, m2, bidx);
       // flag lists are double-buffered by tile parity: the other list's counter is cleared before this tile's
       // barrier, so that clearing and the next tile's appends are ordered by it
       uint32_t* flags = flags_all + (it & 1) * 128;
-      if (grow < a.n) {
-        if (certified) a.labels[grow] = bidx;
+      if (verdict) {
+        if (verdict == 1) a.labels[grow] = bidx;
         else flags[atomicAdd(&n_flag[it & 1], 1u)] = (uint32_t)row;
       }
       if (row == 0) n_flag[(it + 1) & 1] = 0u;
@@ -509,7 +537,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kT5Threads, 1)
         // uncertified rows: the reference's exact scan, one warp per row
         for (uint32_t f = (uint32_t)wq; f < nf; f += 4) {
           const unsigned long long fr = row0 + flags[f];
-          const int fi = t5_exact_label<D>(a.X, a.C, k, fr, lane);
+          const int fi = t5_exact_label<D>(a.X, a.C, a.k, fr, lane);
           if (lane == 0) a.labels[fr] = (uint32_t)fi;
         }
         my_fallbacks += (row == 0) ? nf : 0u;
@@ -554,7 +582,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kT5Threads, 1)
   unsigned char* smem = smem_unaligned + ((1024u - (tc::smem_u32(smem_unaligned) & 1023u)) & 1023u);
   const int t = threadIdx.x, lane = t & 31;
   const int warp = __shfl_sync(0xffffffffu, t >> 5, 0);
-  const int k = a.k;
+  const int chunk_base = a.chunk_idx * kT5K;
+  const int k = min(kT5K, a.k - chunk_base);   // centroids of this launch's chunk
+  const float* Cc = a.C + (size_t)chunk_base * D;
   const uint32_t rank = tc::cluster_ctarank();
   unsigned char* ring = smem;                                    // [kT5sStages][16 KB] raw slabs = A operands
   unsigned char* b_hi = ring + (size_t)kT5sStages * 16384;       // [NS][16 KB]
@@ -589,13 +619,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kT5Threads, 1)
   }
   for (int e = t; e < 1024 + 64; e += kT5Threads) reinterpret_cast<float4*>(b_bias)[e] = make_float4(0.f, 0.f, 0.f, 0.f);
   __syncthreads();
-  t5_centroid_norms<D>(a.C, k, nn_s, &cmax_bits, t);
+  t5_centroid_norms<D>(a.C, a.k, chunk_base, nn_s, &cmax_bits, t);
   // this CTA's half of the centroids, raw: kind::tf32 reads them as c_hi
   for (int item = t; item < 128 * NS * 8; item += kT5Threads) {
     const int q = item & 7, s = (item >> 3) % NS, r = item / (8 * NS);
     const int c = (int)rank * 128 + r;
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (c < k) v = __ldg(reinterpret_cast<const float4*>(a.C + (size_t)c * D + s * 32) + q);
+    if (c < k) v = __ldg(reinterpret_cast<const float4*>(Cc + (size_t)c * D + s * 32) + q);
     *reinterpret_cast<float4*>(b_hi + (uint32_t)s * 16384u + tc::sw128_offset((uint32_t)r, (uint32_t)q)) = v;
   }
   __syncthreads();
@@ -697,14 +727,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kT5Threads, 1)
       __syncwarp();
       if (lane == 0) tc::mbar_arrive_cluster(&bar_accfree[g], 0u);
       if (wq == 0) T5TRACE(it, 9);
-      const float v_best = __uint_as_float((m1 >> 8) | win.top_bits);
-      const float v_second = __uint_as_float((m2 >> 8) | win.top_bits);
-      const uint32_t bidx = m1 & 255u;
-      const bool certified = win.ok && ((v_best - v_second) > win.m_v) && bidx < (uint32_t)k;
       const unsigned long long grow = row0 + (unsigned long long)row;
+      uint32_t bidx = 0u;
+      const int verdict = t5_merge_certify(a, win, grow, m1, m2, bidx);
       uint32_t* flags = flags_all + (g * 2 + (u & 1u)) * 128;
-      if (grow < a.n) {
-        if (certified) a.labels[grow] = bidx;
+      if (verdict) {
+        if (verdict == 1) a.labels[grow] = bidx;
         else flags[atomicAdd(&n_flag[g][u & 1u], 1u)] = (uint32_t)row;
       }
       if (row == 0) n_flag[g][(u + 1u) & 1u] = 0u;
@@ -713,7 +741,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kT5Threads, 1)
       if (nf) {
         for (uint32_t f = (uint32_t)wq; f < nf; f += 4) {
           const unsigned long long fr = row0 + flags[f];
-          const int fi = t5_exact_label<D>(a.X, a.C, k, fr, lane);
+          const int fi = t5_exact_label<D>(a.X, a.C, a.k, fr, lane);
           if (lane == 0) a.labels[fr] = (uint32_t)fi;
         }
         my_fallbacks += (row == 0) ? nf : 0u;

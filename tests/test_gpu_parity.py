@@ -493,7 +493,7 @@ TCA_CASES = [(6000, 128, 256, 16, 30.0, False), (5000, 64, 1024, 40, 30.0, False
 @pytest.mark.parametrize("n,d,k,k_true,spread,shuffle", TCA_CASES)
 def test_tc_assign_path_matches_oracle(lb, ctx, oracle, n, d, k, k_true, spread, shuffle, passes):
     """passes: 0 = adaptive, 1 = one-product screening variant of the pair kernel, 3 = 3xTF32 (same results)."""
-    if passes and not (d in (64, 128) and k <= 256):
+    if passes and not (d in (64, 128) and k <= 4096):
         pytest.skip("scoring passes only select between the variants of the pair kernel")
     dt = np.float32
     X, _ = blobs(n, d, k_true, dt, seed=n + k, spread=spread)
