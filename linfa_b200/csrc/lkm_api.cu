@@ -619,13 +619,13 @@ static lkm_status run_lloyd(lkm_ctx* ctx, F* dC2, uint64_t k, uint64_t max_iter,
         upd_stages = 3;
         while (upd_stages < kUpdMaxStages && upd_smem_bytes((int)d, upd_chunk, upd_stages + 1) <= limit) ++upd_stages;
         upd_smem = upd_smem_bytes((int)d, upd_chunk, upd_stages);
-        const uint64_t n_sub = (n + kUpdSubRows - 1) / kUpdSubRows;
+        const uint64_t n_sub = (n + upd_stage_rows((int)d) - 1) / upd_stage_rows((int)d);
         upd_gx = (int)std::max<uint64_t>(1, std::min<uint64_t>(n_sub, (uint64_t)(ctx->sm_count / upd_ny)));
         const void* fn = d == 32 ? (const void*)update_rows_kernel<32> : (d == 64 ? (const void*)update_rows_kernel<64> : (const void*)update_rows_kernel<128>);
         CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)upd_smem));
         CK(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
-        CKS(make_plain_tile_map(ctx, dX, n, d, (uint32_t)d, kUpdSubRows, upd_map));
-        CK(ctx->labels.ensure((n + 64) * 4));
+        CKS(make_plain_tile_map(ctx, dX, n, d, (uint32_t)d, (uint32_t)upd_stage_rows((int)d), upd_map));
+        CK(ctx->labels.ensure((n + 256) * 4));
         use_upd = true;
       }
     }

@@ -316,11 +316,10 @@ __device__ __forceinline__ int t5_exact_label(const float* __restrict__ X, const
 // Folds this launch's packed (best, runner-up) of row `grow` into the state of the earlier chunks; on the last chunk
 // decides: 1 = certified (label set), 2 = needs the exact re-scan, 0 = nothing to do yet / row past the end.
 __device__ __forceinline__ int t5_merge_certify(const Tc5Args& a, const T5Win& win, unsigned long long grow, uint32_t m1, uint32_t m2,
-                                                uint32_t& label) {
+                                                const uint4 p, uint32_t& label) {
   if (grow >= a.n) return 0;
   uint32_t ch1 = (uint32_t)a.chunk_idx;
   if (a.chunk_idx > 0) {
-    const uint4 p = a.merge[grow];
     // packed values order by score first; equal scores in different chunks end as best / runner-up with gap 0: uncertified
     if (m1 > p.x) { m2 = max(p.x, m2); }
     else { m2 = max(p.y, m1); m1 = p.x; ch1 = p.z; }
@@ -510,6 +509,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kT5Threads, 1)
     const uint32_t taddr = tmem + ((uint32_t)(wq * 32) << 16) + kT5ColAcc;
     for (unsigned long long it = 0; it < my_pt; ++it) {
       const unsigned long long row0 = tile_of(it) * 128ull;
+      // state of the earlier chunks: requested before the wait so that its latency hides behind the MMAs
+      uint4 prev = make_uint4(0u, 0u, 0u, 0u);
+      if (a.chunk_idx > 0 && row0 + (unsigned long long)row < a.n) prev = a.merge[row0 + (unsigned long long)row];
       tc::mbar_wait_or_trap(&bar_mma, (uint32_t)it & 1u);
       if (wq == 0) T5TRACE(it, 6);
       tc::tc_fence_after();
@@ -521,7 +523,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kT5Threads, 1)
       if (wq == 0) T5TRACE(it, 7);
       const unsigned long long grow = row0 + (unsigned long long)row;
       uint32_t bidx = 0u;
-      const int verdict = t5_merge_certify(a, win, grow, m1, m2, bidx);
+      const int verdict = t5_merge_certify(a, win, grow, m1, m2, prev, bidx);
       // flag lists are double-buffered by tile parity: the other list's counter is cleared before this tile's
       // barrier, so that clearing and the next tile's appends are ordered by it
       uint32_t* flags = flags_all + (it & 1) * 128;
@@ -718,6 +720,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kT5Threads, 1)
     for (unsigned long long it = g; it < my_pt; it += 2) {
       const uint32_t u = (uint32_t)(it >> 1);
       const unsigned long long row0 = tile_of(it) * 128ull;
+      uint4 prev = make_uint4(0u, 0u, 0u, 0u);
+      if (a.chunk_idx > 0 && row0 + (unsigned long long)row < a.n) prev = a.merge[row0 + (unsigned long long)row];
       tc::mbar_wait_or_trap(&bar_mma[g], u & 1u);
       if (wq == 0) T5TRACE(it, 8);
       tc::tc_fence_after();
@@ -729,7 +733,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kT5Threads, 1)
       if (wq == 0) T5TRACE(it, 9);
       const unsigned long long grow = row0 + (unsigned long long)row;
       uint32_t bidx = 0u;
-      const int verdict = t5_merge_certify(a, win, grow, m1, m2, bidx);
+      const int verdict = t5_merge_certify(a, win, grow, m1, m2, prev, bidx);
       uint32_t* flags = flags_all + (g * 2 + (u & 1u)) * 128;
       if (verdict) {
         if (verdict == 1) a.labels[grow] = bidx;

@@ -33,7 +33,7 @@ struct UpdArgs {
   int k;
   int chunk_rows;              // clusters per chunk; blockIdx.y = chunk, chunk c owns [c * chunk_rows, ...)
   int stages;
-  const uint32_t* labels;      // n labels; the allocation is readable up to the next multiple of 32 rows
+  const uint32_t* labels;      // n labels; the allocation is readable up to the next multiple of 128 rows
   const float* C;              // k x d, the centroids the labels were computed against (inertia)
   float* part_sums;            // [gridDim.x][k * d]
   uint32_t* part_counts;       // [gridDim.x][k]
@@ -41,7 +41,8 @@ struct UpdArgs {
   const LloydState* state;
 };
 
-__host__ __device__ inline size_t upd_stage_bytes(int d) { return (size_t)kUpdSubRows * d * 4 + 128; }
+__host__ __device__ inline int upd_stage_rows(int d) { return kUpdSubRows * (128 / d); }   // 16 KB of rows per TMA operation
+__host__ __device__ inline size_t upd_stage_bytes(int d) { return (size_t)upd_stage_rows(d) * d * 4 + 512; }
 __host__ __device__ inline size_t upd_smem_bytes(int d, int chunk_rows, int stages) {
   return (size_t)stages * upd_stage_bytes(d) + (size_t)chunk_rows * d * 4 + (size_t)chunk_rows * 4 + kUpdThreads * 8 + 256;
 }
@@ -60,7 +61,11 @@ __global__ void __launch_bounds__(kUpdThreads, 1) update_rows_kernel(const UpdAr
   static_assert(D == 32 || D == 64 || D == 128, "row width");
   constexpr int QF = D / 32;                 // feature slices
   constexpr int NCLS = kUpdConsumers / QF;   // cluster classes
-  constexpr uint32_t kStage = (uint32_t)kUpdSubRows * D * 4 + 128;
+  constexpr int SUBS = 128 / D;                            // 32-row sub-tiles per stage (a TMA operation moves 16 KB:
+                                                           // smaller ones are bound by the per-operation cost of the copy engine)
+  constexpr int kStageRows = kUpdSubRows * SUBS;
+  constexpr uint32_t kStageX = (uint32_t)kStageRows * D * 4;
+  constexpr uint32_t kStage = kStageX + 512;
   if (a.state != nullptr && a.state->done) return;
   extern __shared__ __align__(16) unsigned char smem_unaligned[];
   unsigned char* smem = smem_unaligned + ((128u - (tc::smem_u32(smem_unaligned) & 127u)) & 127u);
@@ -76,7 +81,7 @@ __global__ void __launch_bounds__(kUpdThreads, 1) update_rows_kernel(const UpdAr
   __shared__ __align__(8) uint64_t bar_full[kUpdMaxStages], bar_empty[kUpdMaxStages];
 
   // contiguous range of sub-tiles per CTA column (ascending row order inside every accumulator)
-  const unsigned long long n_sub = (a.n + kUpdSubRows - 1) / kUpdSubRows;
+  const unsigned long long n_sub = (a.n + kStageRows - 1) / kStageRows;   // stages
   const unsigned long long per = (n_sub + gridDim.x - 1) / gridDim.x;
   const unsigned long long j0 = min(n_sub, per * blockIdx.x), j1 = min(n_sub, j0 + per);
 
@@ -99,15 +104,15 @@ __global__ void __launch_bounds__(kUpdThreads, 1) update_rows_kernel(const UpdAr
       for (unsigned long long j = j0; j < j1; ++j) {
         if (use > 0) tc::mbar_wait_or_trap(&bar_empty[s], (use - 1u) & 1u);
         unsigned char* st = ring + (size_t)s * kStage;
-        tc::mbar_expect_tx(&bar_full[s], kStage);
+        tc::mbar_expect_tx(&bar_full[s], kStageX + 128u * SUBS);
         // one box of 32 full rows: the TMA unit works through a box one inner line at a time (measured ~8 cycles per
         // line whatever its length), so 512-byte lines move four times as many bytes per cycle as 128-byte lines
-        tc::tma_load_2d(st, &tmap, 0, (int)(j * kUpdSubRows), &bar_full[s]);
+        tc::tma_load_2d(st, &tmap, 0, (int)(j * kStageRows), &bar_full[s]);
         if (j + kUpdPrefetch < j1) {
-          const unsigned long long r0 = (j + kUpdPrefetch) * kUpdSubRows;
-          tc::l2_prefetch(a.X + r0 * (unsigned long long)D, (uint32_t)min((unsigned long long)kUpdSubRows, a.n - r0) * (uint32_t)(D * 4));
+          const unsigned long long r0 = (j + kUpdPrefetch) * kStageRows;
+          tc::l2_prefetch(a.X + r0 * (unsigned long long)D, (uint32_t)min((unsigned long long)kStageRows, a.n - r0) * (uint32_t)(D * 4));
         }
-        tc::bulk_load_1d(st + QF * 4096, a.labels + j * kUpdSubRows, 128u, &bar_full[s]);
+        tc::bulk_load_1d(st + kStageX, a.labels + j * kStageRows, 128u * SUBS, &bar_full[s]);
         if (++s == R) { s = 0; ++use; }
       }
     }
@@ -130,9 +135,11 @@ __global__ void __launch_bounds__(kUpdThreads, 1) update_rows_kernel(const UpdAr
     for (unsigned long long j = j0; j < j1; ++j) {
       const unsigned char* st = ring + (size_t)s * kStage;
       tc::nb_sync(1 + s, (kUpdConsumers + 1) * 32);
-      const float* xs = reinterpret_cast<const float*>(st) + fs * 32 + lane;     // row r at xs[r * D]
-      uint32_t lab = reinterpret_cast<const uint32_t*>(st + QF * 4096)[lane];
-      if (j * kUpdSubRows + (unsigned)lane >= a.n) lab = 0xFFFFFFFFu;
+#pragma unroll 1
+      for (int sub = 0; sub < SUBS; ++sub) {
+      const float* xs = reinterpret_cast<const float*>(st) + (size_t)sub * kUpdSubRows * D + fs * 32 + lane;     // row r at xs[r * D]
+      uint32_t lab = reinterpret_cast<const uint32_t*>(st + kStageX)[sub * kUpdSubRows + lane];
+      if (j * kStageRows + (unsigned)(sub * kUpdSubRows + lane) >= a.n) lab = 0xFFFFFFFFu;
       const uint32_t c = lab - (uint32_t)chunk_base;
       const bool mine = c < (uint32_t)chunk_rows && (int)(c % (uint32_t)NCLS) == cls;
       uint32_t m = __ballot_sync(0xffffffffu, mine);
@@ -197,6 +204,7 @@ __global__ void __launch_bounds__(kUpdThreads, 1) update_rows_kernel(const UpdAr
             if (fs == 0 && lane == 0) cnt[L[q]] += (uint32_t)__popc(pm[q]);
           }
         }
+      }
       }
       __syncwarp();
       if (lane == 0) tc::mbar_arrive(&bar_empty[s]);
