@@ -48,6 +48,15 @@ WORKLOAD_TEXT = {
 }
 
 
+DEFAULT_KERNELS = {
+    "cfg2": "lloyd_tc4_kernel (fused assign+update, tcgen05 pipeline)",
+    "cfg3": "assign_tc5s_kernel + update_rows_kernel (CTA-pair tcgen05 assignment, then the streaming update: two passes over X)",
+    "cfg4": "4 x assign_tc5s_kernel (one per 256 centroids) + update_rows_kernel x 2 cluster chunks (six passes over X)",
+    "cfg5": "lloyd_kernel<double> (certified FMA, CUDA cores)",
+    "cfg1": "lloyd_kernel<double> (exact, CUDA cores)",
+}
+
+
 def load_peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -313,7 +322,7 @@ def main():
         achieved = n * d * itemsize / per_launch_s / 1e9
         traffic, kname = load_traffic(args.workload)
         roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                    "traffic": traffic, "kernel": kname or "fused assign+update kernel (lloyd_kernel / lloyd_tc_kernel)",
+                    "traffic": traffic, "kernel": kname or DEFAULT_KERNELS.get(args.workload, "fused assign+update kernel"),
                     "algorithmic_bytes_per_launch": n * d * itemsize, "mean_launch_us": per_launch_s * 1e6,
                     "peak_source": peak_src}
 

@@ -87,6 +87,24 @@ __device__ __forceinline__ void mbar_wait_or_trap(uint64_t* bar, uint32_t parity
   }
   __trap();
 }
+// the same without a suspend-time hint, for single-warp roles on the critical path (producer, relay, MMA issuer):
+// they re-test as soon as the try_wait returns instead of sleeping in 10 us slices woken by unrelated barrier events
+__device__ __forceinline__ void mbar_wait_spin(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+#pragma unroll 1
+  for (uint32_t i = 0; i < (1u << 28); ++i) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (ok) return;
+  }
+  __trap();
+}
 __device__ __forceinline__ float trunc_tf32(float x) { return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
 }  // namespace tc
 

@@ -653,7 +653,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kT5Threads, 1)
       for (unsigned long long it = 0; it < my_pt; ++it) {
         const unsigned long long tile = min(tile_of(it), n_tiles - 1);
         for (int sl = 0; sl < NS; ++sl) {
-          if (use > 0) tc::mbar_wait_or_trap(&bar_empty[s], (use - 1u) & 1u);
+          if (use > 0) tc::mbar_wait_spin(&bar_empty[s], (use - 1u) & 1u);
           if (sl == 0) T5TRACE(it, 0);
           if (sl == NS - 1) T5TRACE(it, 1);
           tc::mbar_expect_tx(&bar_full[s], 16384u);
@@ -672,7 +672,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kT5Threads, 1)
       int s = 0;
       uint32_t ph = 0;
       for (unsigned long long j = 0; j < my_pt * NS; ++j) {
-        tc::mbar_wait_or_trap(&bar_full[s], ph);
+        tc::mbar_wait_spin(&bar_full[s], ph);
         if (lane == 0) tc::mbar_arrive_cluster(&bar_pfull[s], 0u);   // plain arrive: a cluster-scope release costs a MEMBAR.GPU per slab (measured: 1000+ cycles, the bottleneck)
         __syncwarp();
         if (++s == kT5sStages) { s = 0; ph ^= 1u; }
@@ -690,14 +690,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kT5Threads, 1)
       for (unsigned long long it = 0; it < my_pt; ++it) {
         const uint32_t g = (uint32_t)it & 1u, u = (uint32_t)(it >> 1);
         const uint32_t dcol = tmem_u + g * 256u;
-        if (u > 0) tc::mbar_wait_or_trap(&bar_accfree[g], (u - 1u) & 1u);
+        if (u > 0) tc::mbar_wait_spin(&bar_accfree[g], (u - 1u) & 1u);
         T5TRACE(it, 2);
 #pragma unroll 1
         for (int sl = 0; sl < NS; ++sl) {
-          tc::mbar_wait_or_trap(&bar_full[s], ph);
+          tc::mbar_wait_spin(&bar_full[s], ph);
           if (sl == 0) T5TRACE(it, 3);
           if (sl == NS - 1) T5TRACE(it, 5);
-          tc::mbar_wait_or_trap(&bar_pfull[s], ph);
+          tc::mbar_wait_spin(&bar_pfull[s], ph);
           if (sl == 0) T5TRACE(it, 4);
           if (sl == NS - 1) T5TRACE(it, 6);
           tc::tc_fence_after();

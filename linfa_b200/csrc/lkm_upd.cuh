@@ -102,7 +102,7 @@ __global__ void __launch_bounds__(kUpdThreads, 1) update_rows_kernel(const UpdAr
       int s = 0;
       uint32_t use = 0;
       for (unsigned long long j = j0; j < j1; ++j) {
-        if (use > 0) tc::mbar_wait_or_trap(&bar_empty[s], (use - 1u) & 1u);
+        if (use > 0) tc::mbar_wait_spin(&bar_empty[s], (use - 1u) & 1u);
         unsigned char* st = ring + (size_t)s * kStage;
         tc::mbar_expect_tx(&bar_full[s], kStageX + 128u * SUBS);
         // one box of 32 full rows: the TMA unit works through a box one inner line at a time (measured ~8 cycles per
@@ -120,7 +120,7 @@ __global__ void __launch_bounds__(kUpdThreads, 1) update_rows_kernel(const UpdAr
     int s = 0;
     uint32_t ph = 0;
     for (unsigned long long j = j0; j < j1; ++j) {
-      tc::mbar_wait_or_trap(&bar_full[s], ph);
+      tc::mbar_wait_spin(&bar_full[s], ph);
       tc::nb_arrive(1 + s, (kUpdConsumers + 1) * 32);
       if (++s == R) { s = 0; ph ^= 1u; }
     }
