@@ -486,7 +486,9 @@ TCA_CASES = [(6000, 128, 256, 16, 30.0, False), (5000, 64, 1024, 40, 30.0, False
              # CTA-pair assignment kernel (assign_tc5_kernel: d in {64, 128}, k <= 256): heavy overlap (many exact re-scans),
              # k below one CTA's half, a single partial tile (the second CTA of the pair idles), odd tile counts
              (128 * 7 + 5, 128, 200, 20, 1.0, True), (100, 64, 256, 4, 30.0, False), (128 * 148 * 2 + 1, 64, 130, 130, 30.0, True),
-             (5000, 128, 100, 100, 0.3, True), (128 * 75, 128, 256, 64, 30.0, False), (4000, 64, 40, 3, 30.0, True)]
+             (5000, 128, 100, 100, 0.3, True), (128 * 75, 128, 256, 64, 30.0, False), (4000, 64, 40, 3, 30.0, True),
+             # several launches per iteration (one per 256 centroids): a last chunk of one centroid, of 255; one row; one tile + 1
+             (129, 128, 257, 5, 30.0, False), (3000, 64, 511, 20, 5.0, True), (1, 128, 40, 1, 30.0, False), (20000, 128, 600, 600, 30.0, False)]
 
 
 @pytest.mark.parametrize("passes", [0, 1, 3])
