@@ -100,10 +100,11 @@ struct lkm_ctx {
   int tc_variant = 4;
   int tc5_passes_forced = 0;            // LKM_TC5_PASSES = 1 / 3 pins the screening / 3xTF32 variant of the pair kernel
   uint64_t tc5_hard_epoch = 0, tc5_easy_epoch = 0;
+  int tc5_fuse = 1;      // LKM_TC5_FUSE=0: screening kernel without the fused update of uniform tiles
   int tc5_enabled = 1;   // LKM_TC5=0: tc_assign_kernel instead of the CTA-pair assignment kernel
   int upd_variant = 1;   // LKM_UPD=0: cluster-chunked lloyd_kernel<MODE_UPDATE> instead of update_rows_kernel
   uint64_t data_epoch = 1, xmax2_epoch = 0;  // resident-data version / version the cached max row norm belongs to
-  DevBuf xmax2, t4prof, t5merge;
+  DevBuf xmax2, t4prof, t5merge, t5list;
   int tc4_passes_forced = 0;              // LKM_TC4_PASSES = 2 / 3 pins the scoring passes of the pipeline kernel
   uint64_t tc4_hard_epoch = 0, tc4_easy_epoch = 0;   // data versions seen to need 3 passes / to be fine with 2
   uint64_t flush_bytes = 0;
@@ -632,7 +633,8 @@ static lkm_status run_lloyd(lkm_ctx* ctx, F* dC2, uint64_t k, uint64_t max_iter,
   }
   // CTA-pair assignment kernel (lkm_tc5.cuh): all centroid operand tiles resident across the two CTAs of a cluster
   bool use_tc5 = false;
-  int tc5_grid = 0, tc5_chunks = 1;
+  int tc5_grid = 0, tc5_chunks = 1, tc5_list_cap = 0;
+  bool tc5_can_fuse = false;
   size_t tc5_smem = 0;
   CUtensorMap tc5_map;
   std::memset(&tc5_map, 0, sizeof(tc5_map));
@@ -643,9 +645,11 @@ static lkm_status run_lloyd(lkm_ctx* ctx, F* dC2, uint64_t k, uint64_t max_iter,
       const void* fn = d == 64 ? (const void*)assign_tc5_kernel<64> : (const void*)assign_tc5_kernel<128>;
       CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc5_smem));
       CK(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
-      const void* fns = d == 64 ? (const void*)assign_tc5s_kernel<64> : (const void*)assign_tc5s_kernel<128>;
+      const void* fns = d == 64 ? (const void*)assign_tc5s_kernel<64, false> : (const void*)assign_tc5s_kernel<128, false>;
       CK(cudaFuncSetAttribute(fns, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc5s_smem_bytes((int)d)));
       CK(cudaFuncSetAttribute(fns, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
+      CK(cudaFuncSetAttribute(assign_tc5s_kernel<128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc5s_smem_bytes(128)));
+      CK(cudaFuncSetAttribute(assign_tc5s_kernel<128, true>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
       CKS(make_row_tile_map(ctx, dX, n, tc5_map, d));
       if (!ctx->own_X || ctx->xmax2_epoch != ctx->data_epoch) {
         CK(ctx->xmax2.ensure(16));
@@ -659,10 +663,16 @@ static lkm_status run_lloyd(lkm_ctx* ctx, F* dC2, uint64_t k, uint64_t max_iter,
       tc5_grid = 2 * (int)std::max<uint64_t>(1, std::min<uint64_t>(n_pt, (uint64_t)(ctx->sm_count / 2)));
       tc5_chunks = (int)((k + kT5K - 1) / kT5K);
       if (tc5_chunks > 1) CK(ctx->t5merge.ensure((n + 256) * 16));
+      // fused update of uniform tiles inside the screening kernel (d = 128, one chunk, one cluster chunk of the update pass)
+      tc5_can_fuse = ctx->tc5_fuse && d == 128 && tc5_chunks == 1 && upd_ny == 1;
+      if (tc5_can_fuse) {
+        tc5_list_cap = (int)((n_pt + (uint64_t)(tc5_grid / 2) - 1) / (uint64_t)(tc5_grid / 2)) + 1;
+        CK(ctx->t5list.ensure(((size_t)tc5_grid * tc5_list_cap + (size_t)tc5_grid + 64) * 4));
+      }
       use_tc5 = true;
     }
   }
-  const int grid = pf.fused ? pf.grid : (use_upd ? upd_gx : pu.grid);
+  const int grid = pf.fused ? pf.grid : (use_upd ? (tc5_can_fuse ? std::max(upd_gx, 2 * tc5_grid) : upd_gx) : pu.grid);
   CK(ctx->part_sums.ensure((size_t)grid * kd * sizeof(F)));
   CK(ctx->part_counts.ensure((size_t)grid * k * 4));
   CK(ctx->part_inertia.ensure((size_t)std::max(grid, 1024) * 8));
@@ -716,6 +726,7 @@ static lkm_status run_lloyd(lkm_ctx* ctx, F* dC2, uint64_t k, uint64_t max_iter,
         CK(cudaMemsetAsync(ctx->flushbuf.p, (int)(it & 0xff), ctx->flush_bytes, ctx->stream));
         CK(cudaEventRecord(ctx->iter_events[3 * it], ctx->stream));
       }
+      int fin_src = grid, fin_src_inertia = use_upd ? upd_gx * upd_ny : 0;   // partial sources of this iteration's finalize
       if (use_tc) {
         if constexpr (std::is_same<F, float>::value) {
           TcArgs ta{};
@@ -752,6 +763,7 @@ static lkm_status run_lloyd(lkm_ctx* ctx, F* dC2, uint64_t k, uint64_t max_iter,
         ctx->launches++;
       } else {
         bool assigned = false;
+        bool fused_now = false;   // this iteration's screening kernel also accumulated the uniform tiles
         if constexpr (std::is_same<F, float>::value) {
           if (use_tc5) {
             Tc5Args t5{};
@@ -765,9 +777,16 @@ static lkm_status run_lloyd(lkm_ctx* ctx, F* dC2, uint64_t k, uint64_t max_iter,
             // one launch per chunk of 256 centroids; the per-row (best, runner-up) state travels through t5merge
             for (int ch = 0; ch < tc5_chunks; ++ch) {
               t5.chunk_idx = ch;
-              if (tc5_passes == 1) {
-                if (d == 64) assign_tc5s_kernel<64><<<tc5_grid, kT5Threads, tc5s_smem_bytes(64), ctx->stream>>>(t5, tc5_map);
-                else assign_tc5s_kernel<128><<<tc5_grid, kT5Threads, tc5s_smem_bytes(128), ctx->stream>>>(t5, tc5_map);
+              if (tc5_passes == 1 && tc5_can_fuse) {
+                t5.part_sums = ctx->part_sums.as<float>(); t5.part_counts = ctx->part_counts.as<uint32_t>();
+                t5.part_inertia = ctx->part_inertia.as<double>();
+                t5.mixed_list = ctx->t5list.as<uint32_t>() + tc5_grid; t5.mixed_count = ctx->t5list.as<uint32_t>();
+                t5.list_cap = tc5_list_cap;
+                assign_tc5s_kernel<128, true><<<tc5_grid, kT5FuseThreads, tc5s_smem_bytes(128), ctx->stream>>>(t5, tc5_map);
+                fused_now = true;
+              } else if (tc5_passes == 1) {
+                if (d == 64) assign_tc5s_kernel<64, false><<<tc5_grid, kT5Threads, tc5s_smem_bytes(64), ctx->stream>>>(t5, tc5_map);
+                else assign_tc5s_kernel<128, false><<<tc5_grid, kT5Threads, tc5s_smem_bytes(128), ctx->stream>>>(t5, tc5_map);
               } else if (d == 64) assign_tc5_kernel<64><<<tc5_grid, kT5Threads, tc5_smem, ctx->stream>>>(t5, tc5_map);
               else assign_tc5_kernel<128><<<tc5_grid, kT5Threads, tc5_smem, ctx->stream>>>(t5, tc5_map);
               CK(cudaGetLastError());
@@ -807,8 +826,18 @@ static lkm_status run_lloyd(lkm_ctx* ctx, F* dC2, uint64_t k, uint64_t max_iter,
             ua.labels = ctx->labels.as<uint32_t>(); ua.C = Ccur;
             ua.part_sums = ctx->part_sums.as<float>(); ua.part_counts = ctx->part_counts.as<uint32_t>();
             ua.part_inertia = ctx->part_inertia.as<double>(); ua.state = dstate;
+            int ugx = upd_gx;
+            if (fused_now) {
+              // only the tiles the screening kernel listed; its own partials are sources [0, tc5_grid), these follow
+              ua.tile_list = ctx->t5list.as<uint32_t>() + tc5_grid; ua.tile_count = ctx->t5list.as<uint32_t>();
+              ua.list_cap = tc5_list_cap;
+              ua.part_sums += (size_t)tc5_grid * kd; ua.part_counts += (size_t)tc5_grid * k; ua.part_inertia += tc5_grid;
+              ugx = tc5_grid;
+            }
+            fin_src = fused_now ? 2 * tc5_grid : upd_gx;
+            fin_src_inertia = fused_now ? 2 * tc5_grid : upd_gx * upd_ny;
             cudaLaunchConfig_t cfg{};
-            cfg.gridDim = dim3((unsigned)upd_gx, (unsigned)upd_ny);
+            cfg.gridDim = dim3((unsigned)ugx, (unsigned)upd_ny);
             cfg.blockDim = dim3((unsigned)kUpdThreads);
             cfg.dynamicSmemBytes = upd_smem;
             cfg.stream = ctx->stream;
@@ -842,8 +871,8 @@ static lkm_status run_lloyd(lkm_ctx* ctx, F* dC2, uint64_t k, uint64_t max_iter,
         FinalizeArgs<F, F, uint32_t> fa{};
         fa.src_sums = ctx->part_sums.as<F>(); fa.src_counts = ctx->part_counts.as<uint32_t>();
         fa.src_inertia = ctx->part_inertia.as<double>();
-        fa.sum_stride = kd; fa.cnt_stride = k; fa.inertia_stride = 1; fa.n_src = grid; fa.k = (int)k; fa.d = (int)d;
-        fa.n_src_inertia = use_upd ? upd_gx * upd_ny : 0;
+        fa.sum_stride = kd; fa.cnt_stride = k; fa.inertia_stride = 1; fa.n_src = fin_src; fa.k = (int)k; fa.d = (int)d;
+        fa.n_src_inertia = fin_src_inertia;
         fa.C_old = Ccur; fa.C_new = Cnext; fa.counts_out = ctx->counts_out.as<double>();
         fa.shift_part = ctx->shift_part.as<double>(); fa.state = dstate; fa.tol = tol; fa.max_iter = max_iter;
         CK((launch_finalize<F, F, uint32_t, true>(fa, ctx->stream)));
@@ -852,8 +881,8 @@ static lkm_status run_lloyd(lkm_ctx* ctx, F* dC2, uint64_t k, uint64_t max_iter,
         FinalizeArgs<F, F, uint32_t> ra{};
         ra.src_sums = ctx->part_sums.as<F>(); ra.src_counts = ctx->part_counts.as<uint32_t>();
         ra.src_inertia = ctx->part_inertia.as<double>();
-        ra.sum_stride = kd; ra.cnt_stride = k; ra.inertia_stride = 1; ra.n_src = grid; ra.k = (int)k; ra.d = (int)d;
-        ra.n_src_inertia = use_upd ? upd_gx * upd_ny : 0;
+        ra.sum_stride = kd; ra.cnt_stride = k; ra.inertia_stride = 1; ra.n_src = fin_src; ra.k = (int)k; ra.d = (int)d;
+        ra.n_src_inertia = fin_src_inertia;
         ra.rank_out = ctx->gather.as<double>() + (size_t)ctx->rank * L;
         ra.state = dstate;
         FinalizeArgs<F, double, double> fa{};
@@ -1785,6 +1814,7 @@ LKM_EXPORT lkm_status lkm_create(lkm_ctx** out, int device) {
   if (const char* v = std::getenv("LKM_TC_VARIANT")) ctx->tc_variant = std::atoi(v);
   if (const char* v = std::getenv("LKM_UPD")) ctx->upd_variant = std::atoi(v);
   if (const char* v = std::getenv("LKM_TC5")) ctx->tc5_enabled = std::atoi(v);
+  if (const char* v = std::getenv("LKM_TC5_FUSE")) ctx->tc5_fuse = std::atoi(v);
   if (const char* v = std::getenv("LKM_TC5_PASSES")) ctx->tc5_passes_forced = std::atoi(v);
   if (const char* v = std::getenv("LKM_P2P")) ctx->p2p_enabled = std::atoi(v);
   if (const char* v = std::getenv("LKM_TC4_PASSES")) ctx->tc4_passes_forced = std::atoi(v);

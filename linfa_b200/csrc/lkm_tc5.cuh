@@ -25,6 +25,7 @@
 namespace lkm {
 
 constexpr int kT5Threads = 10 * 32;
+constexpr int kT5FuseThreads = 14 * 32;   // screening kernel with the fused update: + four U warps
 constexpr int kT5Stages = 4;
 constexpr uint32_t kT5ColAcc = 0, kT5ColA = 256;
 constexpr unsigned long long kT5Prefetch = 3;   // L2 prefetch distance of the P roles, in tiles
@@ -41,6 +42,14 @@ struct Tc5Args {
   uint32_t* labels;
   LloydState* state;
   long long* prof;   // LKM_T5_TRACE builds only
+  // fused update of the screening kernel (FUSE = true): per-CTA partials for finalize_kernel and the list of the tiles
+  // whose rows did not all certify to one cluster (those go through update_rows_kernel)
+  float* part_sums;         // [gridDim.x][k * d], zeroed by the kernel
+  uint32_t* part_counts;    // [gridDim.x][k]
+  double* part_inertia;     // [gridDim.x]
+  uint32_t* mixed_list;     // [gridDim.x][list_cap] tile indices
+  uint32_t* mixed_count;    // [gridDim.x]
+  int list_cap;
   uint32_t pack_mult;   // 256, passed as an argument so that the score pack stays an IMAD (see the E role)
 };
 
@@ -180,7 +189,7 @@ __device__ __forceinline__ T5Win t5_window(float xmax2, float cmax2_raw, float d
 template <int D>
 __device__ __forceinline__ void t5_centroid_norms(const float* __restrict__ C, int k, int chunk_base, float* nn_s, uint32_t* cmax_bits,
                                                   int t) {
-  for (int base = 0; base < k * 8; base += kT5Threads) {
+  for (int base = 0; base < k * 8; base += (int)blockDim.x) {
     const int item = base + t;
     const int r = item >> 3, c8 = item & 7;
     float nn = 0.f;
@@ -574,11 +583,13 @@ __host__ __device__ inline size_t tc5s_smem_bytes(int d) {
   return (size_t)kT5sStages * 16384 + (size_t)(d / 32) * 16384 + 16384 + 1024 + kT5K * 4 + 4 * 128 * 4 + 1024;
 }
 
-template <int D>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kT5Threads, 1)
+template <int D, bool FUSE>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(FUSE ? kT5FuseThreads : kT5Threads, 1)
     assign_tc5s_kernel(const Tc5Args a, const __grid_constant__ CUtensorMap tmap) {
   static_assert(D == 64 || D == 128, "row width");
+  static_assert(!FUSE || D == 128, "the fused update maps one U warp to each of the four slabs of a tile");
   constexpr int NS = D / 32;
+  constexpr int NT = FUSE ? kT5FuseThreads : kT5Threads;
   if (a.state != nullptr && a.state->done) return;
   extern __shared__ __align__(16) unsigned char smem_unaligned[];
   unsigned char* smem = smem_unaligned + ((1024u - (tc::smem_u32(smem_unaligned) & 1023u)) & 1023u);
@@ -596,6 +607,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kT5Threads, 1)
   uint32_t* flags_all = reinterpret_cast<uint32_t*>(nn_s + kT5K);   // [group][2][128]
   __shared__ __align__(8) uint64_t bar_full[kT5sStages], bar_pfull[kT5sStages], bar_empty[kT5sStages], bar_mma[2], bar_accfree[2];
   __shared__ uint32_t tmem_slot, n_flag[2][2], cmax_bits;
+  __shared__ __align__(8) uint64_t bar_verdict[4];   // FUSE: E -> U, one per tile slot (it & 3)
+  __shared__ __align__(16) uint32_t warp_verdict[4][4];            // [tile slot][E warp]: common label of the warp's 32 rows, or a marker
+  __shared__ double u_red[4];
 
   const unsigned long long n_tiles = (a.n + 127) / 128;
   const unsigned long long n_pt = (n_tiles + 1) / 2;
@@ -608,8 +622,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kT5Threads, 1)
     for (int s = 0; s < kT5sStages; ++s) {
       tc::mbar_init(&bar_full[s], 1);
       tc::mbar_init(&bar_pfull[s], 1);
-      tc::mbar_init(&bar_empty[s], 1);
+      tc::mbar_init(&bar_empty[s], FUSE ? 2 : 1);   // MMA commit (+ the U warp that sums the slab)
     }
+    for (int q = 0; q < 4; ++q) tc::mbar_init(&bar_verdict[q], 4);
     for (int g = 0; g < 2; ++g) {
       tc::mbar_init(&bar_mma[g], 1);
       tc::mbar_init(&bar_accfree[g], 8);
@@ -619,11 +634,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kT5Threads, 1)
     tc::fence_mbar_init();
     cmax_bits = 0;
   }
-  for (int e = t; e < 1024 + 64; e += kT5Threads) reinterpret_cast<float4*>(b_bias)[e] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int e = t; e < 1024 + 64; e += NT) reinterpret_cast<float4*>(b_bias)[e] = make_float4(0.f, 0.f, 0.f, 0.f);
+  if constexpr (FUSE) {
+    float4* ps4 = reinterpret_cast<float4*>(a.part_sums + (size_t)blockIdx.x * a.k * D);
+    for (int e = t; e < a.k * D / 4; e += NT) ps4[e] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int e = t; e < a.k; e += NT) a.part_counts[(size_t)blockIdx.x * a.k + e] = 0u;
+  }
   __syncthreads();
   t5_centroid_norms<D>(a.C, a.k, chunk_base, nn_s, &cmax_bits, t);
   // this CTA's half of the centroids, raw: kind::tf32 reads them as c_hi
-  for (int item = t; item < 128 * NS * 8; item += kT5Threads) {
+  for (int item = t; item < 128 * NS * 8; item += NT) {
     const int q = item & 7, s = (item >> 3) % NS, r = item / (8 * NS);
     const int c = (int)rank * 128 + r;
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -712,6 +732,97 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kT5Threads, 1)
         T5TRACE(it, 7);
       }
     }
+  } else if (warp >= 10) {
+    // =============================== U: column sums of the raw slabs (FUSE) ===============================
+    // U warp u owns slab u (features 32 u + lane).  For every tile it keeps, relative to the tile's first row x0,
+    // S' = sum (x - x0) and Q' = sum (x - x0)^2 over the 128 rows (no cancellation: rows of one cluster differ by O(sigma)).
+    // Two tiles later the E group has published whether the tile's rows all certified to ONE cluster L; then
+    // sum += S' + 128 x0, count += 128 and inertia += Q' + d (128 d - 2 S') with d = c_L - x0 go to the register
+    // accumulators of the current cluster (flushed to the CTA's partial sums when the cluster changes); any other tile is
+    // listed for update_rows_kernel.  Tiles and clusters are visited in a fixed order: reproducible.
+    if constexpr (FUSE) {
+      const int u = warp - 10;
+      const int feat = 32 * u + lane;
+      uint32_t off[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) off[q] = (uint32_t)q * 128u + ((((uint32_t)lane >> 2) ^ (uint32_t)q) << 4) + ((uint32_t)lane & 3u) * 4u;
+      float xa0 = 0.f, xa1 = 0.f, xa2 = 0.f, xa3 = 0.f, Sa0 = 0.f, Sa1 = 0.f, Sa2 = 0.f, Sa3 = 0.f, Qa0 = 0.f, Qa1 = 0.f, Qa2 = 0.f, Qa3 = 0.f;
+      uint32_t cur_L = 0xFFFFFFFFu, cur_cnt = 0u, n_mixed = 0u;
+      float cur_sum = 0.f, cur_c = 0.f, inert_f = 0.f;
+      double inert_d = 0.0;
+      float* my_sums = a.part_sums + (size_t)blockIdx.x * a.k * D + feat;
+      uint32_t* my_counts = a.part_counts + (size_t)blockIdx.x * a.k;
+      uint32_t* my_list = a.mixed_list + (size_t)blockIdx.x * a.list_cap;
+      auto flush = [&]() {
+        if (cur_L != 0xFFFFFFFFu) {
+          my_sums[(size_t)cur_L * D] += cur_sum;
+          if (u == 0 && lane == 0) my_counts[cur_L] += cur_cnt;
+        }
+      };
+      auto consume = [&](unsigned long long v) {
+        // verdict of tile v (slot v & 3), published by the four E warps of group v & 1
+        tc::mbar_wait_or_trap(&bar_verdict[v & 3], (uint32_t)(v >> 2) & 1u);
+        const uint4 wv = *reinterpret_cast<const uint4*>(warp_verdict[v & 3]);
+        const int vs = (int)(v & 3);
+        const float x0 = vs == 0 ? xa0 : (vs == 1 ? xa1 : (vs == 2 ? xa2 : xa3));
+        const float S = vs == 0 ? Sa0 : (vs == 1 ? Sa1 : (vs == 2 ? Sa2 : Sa3));
+        const float Q = vs == 0 ? Qa0 : (vs == 1 ? Qa1 : (vs == 2 ? Qa2 : Qa3));
+        if (wv.x < 0xFFFFFFFEu && wv.x == wv.y && wv.x == wv.z && wv.x == wv.w) {
+          const uint32_t L = wv.x;
+          if (L != cur_L) {
+            flush();
+            cur_L = L; cur_sum = 0.f; cur_cnt = 0u;
+            cur_c = __ldg(a.C + (size_t)L * D + feat);
+          }
+          cur_sum += fmaf(128.f, x0, S);
+          cur_cnt += 128u;
+          const float dl = cur_c - x0;
+          inert_f += fmaf(dl, fmaf(128.f, dl, -2.f * S), Q);
+          if ((v & 15) == 15) { inert_d += (double)inert_f; inert_f = 0.f; }
+        } else if (wv.x != 0xFFFFFFFEu || wv.y != 0xFFFFFFFEu || wv.z != 0xFFFFFFFEu || wv.w != 0xFFFFFFFEu) {
+          if (u == 0 && lane == 0) my_list[n_mixed] = (uint32_t)tile_of(v);
+          ++n_mixed;
+        }
+      };
+      int s = u;   // ring stage of slab u of tile 0
+      uint32_t ph = 0;
+      for (unsigned long long it = 0; it < my_pt; ++it) {
+        const unsigned char* sl = ring + (size_t)s * 16384;
+        tc::mbar_wait_or_trap(&bar_full[s], ph);
+        const float x0 = *reinterpret_cast<const float*>(sl + off[0]);
+        float S0 = 0.f, S1 = 0.f, Q0 = 0.f, Q1 = 0.f;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+#pragma unroll
+          for (int q = 0; q < 8; q += 2) {
+            const float xa = *reinterpret_cast<const float*>(sl + i * 1024 + off[q]);
+            const float xb = *reinterpret_cast<const float*>(sl + i * 1024 + off[q + 1]);
+            const float da = xa - x0, db = xb - x0;
+            S0 += da; S1 += db;
+            Q0 = fmaf(da, da, Q0); Q1 = fmaf(db, db, Q1);
+          }
+        }
+        if (it >= 2) consume(it - 2);   // before the slab is released: keeps verdict slot (it + 2) & 3 from being rewritten early
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(&bar_empty[s]);
+        {
+          const int is = (int)(it & 3);
+          const float St = S0 + S1, Qt = Q0 + Q1;
+          if (is == 0) { xa0 = x0; Sa0 = St; Qa0 = Qt; }
+          else if (is == 1) { xa1 = x0; Sa1 = St; Qa1 = Qt; }
+          else if (is == 2) { xa2 = x0; Sa2 = St; Qa2 = Qt; }
+          else { xa3 = x0; Sa3 = St; Qa3 = Qt; }
+        }
+        s += NS;
+        if (s >= kT5sStages) { s -= kT5sStages; ph ^= 1u; }
+      }
+      for (unsigned long long v = my_pt >= 2 ? my_pt - 2 : 0; v < my_pt; ++v) consume(v);
+      flush();
+      if (u == 0 && lane == 0) a.mixed_count[blockIdx.x] = n_mixed;
+      inert_d += (double)inert_f;
+      for (int o = 16; o > 0; o >>= 1) inert_d += __shfl_xor_sync(0xffffffffu, inert_d, o);
+      if (lane == 0) u_red[u] = inert_d;
+    }
   } else {
     // =============================== E: group g scores the tiles it = g (mod 2) ===============================
     const int g = warp >> 2, wq = warp & 3;
@@ -739,6 +850,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kT5Threads, 1)
         if (verdict == 1) a.labels[grow] = bidx;
         else flags[atomicAdd(&n_flag[g][u & 1u], 1u)] = (uint32_t)row;
       }
+      if constexpr (FUSE) {
+        // one label for the warp's 32 rows (all certified, full tile) -> U adds the tile's column sums to that cluster
+        const uint32_t lab0 = __shfl_sync(0xffffffffu, bidx, 0);
+        const bool uni = __all_sync(0xffffffffu, verdict == 1 && bidx == lab0) && row0 + 128ull <= a.n;
+        if (lane == 0) warp_verdict[it & 3][wq] = uni ? lab0 : (row0 < a.n ? 0xFFFFFFFFu : 0xFFFFFFFEu);
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(&bar_verdict[it & 3]);
+      }
       if (row == 0) n_flag[g][(u + 1u) & 1u] = 0u;
       tc::nb_sync(1 + g, 128);
       const uint32_t nf = n_flag[g][u & 1u];
@@ -756,6 +875,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kT5Threads, 1)
   }
   tc::tc_fence_before();
   __syncthreads();
+  if constexpr (FUSE) {
+    if (t == 0) a.part_inertia[blockIdx.x] = (u_red[0] + u_red[1]) + (u_red[2] + u_red[3]);
+  }
   tc::cluster_sync_all();
   if (warp == 8) tc::tmem_dealloc_pair(tmem, 512);
 }

@@ -39,6 +39,11 @@ struct UpdArgs {
   uint32_t* part_counts;       // [gridDim.x][k]
   double* part_inertia;        // [gridDim.y][gridDim.x]
   const LloydState* state;
+  // list mode (behind the fused screening kernel): CTA b only visits the 128-row tiles tile_list[b * list_cap + i],
+  // i < tile_count[b], in that order
+  const uint32_t* tile_list;
+  const uint32_t* tile_count;
+  int list_cap;
 };
 
 __host__ __device__ inline int upd_stage_rows(int d) { return kUpdSubRows * (128 / d); }   // 16 KB of rows per TMA operation
@@ -83,7 +88,15 @@ __global__ void __launch_bounds__(kUpdThreads, 1) update_rows_kernel(const UpdAr
   // contiguous range of sub-tiles per CTA column (ascending row order inside every accumulator)
   const unsigned long long n_sub = (a.n + kStageRows - 1) / kStageRows;   // stages
   const unsigned long long per = (n_sub + gridDim.x - 1) / gridDim.x;
-  const unsigned long long j0 = min(n_sub, per * blockIdx.x), j1 = min(n_sub, j0 + per);
+  constexpr int SPT = 128 / kStageRows;                                    // stages per listed tile
+  const bool listed = a.tile_list != nullptr;
+  const uint32_t* my_list = listed ? a.tile_list + (size_t)blockIdx.x * a.list_cap : nullptr;
+  const unsigned long long j0 = listed ? 0ull : min(n_sub, per * blockIdx.x);
+  const unsigned long long j1 = listed ? (unsigned long long)a.tile_count[blockIdx.x] * SPT : min(n_sub, j0 + per);
+  // stage index (units of kStageRows rows) of loop position j
+  auto stage_of = [&](unsigned long long j) -> unsigned long long {
+    return listed ? (unsigned long long)my_list[j / SPT] * SPT + (j % SPT) : j;
+  };
 
   if (t == 0) {
     for (int s = 0; s < kUpdMaxStages; ++s) {
@@ -107,12 +120,13 @@ __global__ void __launch_bounds__(kUpdThreads, 1) update_rows_kernel(const UpdAr
         tc::mbar_expect_tx(&bar_full[s], kStageX + 128u * SUBS);
         // one box of 32 full rows: the TMA unit works through a box one inner line at a time (measured ~8 cycles per
         // line whatever its length), so 512-byte lines move four times as many bytes per cycle as 128-byte lines
-        tc::tma_load_2d(st, &tmap, 0, (int)(j * kStageRows), &bar_full[s]);
-        if (j + kUpdPrefetch < j1) {
+        const unsigned long long sj = stage_of(j);
+        tc::tma_load_2d(st, &tmap, 0, (int)(sj * kStageRows), &bar_full[s]);
+        if (!listed && j + kUpdPrefetch < j1) {
           const unsigned long long r0 = (j + kUpdPrefetch) * kStageRows;
           tc::l2_prefetch(a.X + r0 * (unsigned long long)D, (uint32_t)min((unsigned long long)kStageRows, a.n - r0) * (uint32_t)(D * 4));
         }
-        tc::bulk_load_1d(st + kStageX, a.labels + j * kStageRows, 128u * SUBS, &bar_full[s]);
+        tc::bulk_load_1d(st + kStageX, a.labels + sj * kStageRows, 128u * SUBS, &bar_full[s]);
         if (++s == R) { s = 0; ++use; }
       }
     }
@@ -134,12 +148,13 @@ __global__ void __launch_bounds__(kUpdThreads, 1) update_rows_kernel(const UpdAr
     float last_cv = 0.f;
     for (unsigned long long j = j0; j < j1; ++j) {
       const unsigned char* st = ring + (size_t)s * kStage;
+      const unsigned long long sj = stage_of(j);
       tc::nb_sync(1 + s, (kUpdConsumers + 1) * 32);
 #pragma unroll 1
       for (int sub = 0; sub < SUBS; ++sub) {
       const float* xs = reinterpret_cast<const float*>(st) + (size_t)sub * kUpdSubRows * D + fs * 32 + lane;     // row r at xs[r * D]
       uint32_t lab = reinterpret_cast<const uint32_t*>(st + kStageX)[sub * kUpdSubRows + lane];
-      if (j * kStageRows + (unsigned)(sub * kUpdSubRows + lane) >= a.n) lab = 0xFFFFFFFFu;
+      if (sj * kStageRows + (unsigned)(sub * kUpdSubRows + lane) >= a.n) lab = 0xFFFFFFFFu;
       const uint32_t c = lab - (uint32_t)chunk_base;
       const bool mine = c < (uint32_t)chunk_rows && (int)(c % (uint32_t)NCLS) == cls;
       uint32_t m = __ballot_sync(0xffffffffu, mine);

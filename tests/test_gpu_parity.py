@@ -488,7 +488,10 @@ TCA_CASES = [(6000, 128, 256, 16, 30.0, False), (5000, 64, 1024, 40, 30.0, False
              (128 * 7 + 5, 128, 200, 20, 1.0, True), (100, 64, 256, 4, 30.0, False), (128 * 148 * 2 + 1, 64, 130, 130, 30.0, True),
              (5000, 128, 100, 100, 0.3, True), (128 * 75, 128, 256, 64, 30.0, False), (4000, 64, 40, 3, 30.0, True),
              # several launches per iteration (one per 256 centroids): a last chunk of one centroid, of 255; one row; one tile + 1
-             (129, 128, 257, 5, 30.0, False), (3000, 64, 511, 20, 5.0, True), (1, 128, 40, 1, 30.0, False), (20000, 128, 600, 600, 30.0, False)]
+             (129, 128, 257, 5, 30.0, False), (3000, 64, 511, 20, 5.0, True), (1, 128, 40, 1, 30.0, False), (20000, 128, 600, 600, 30.0, False),
+             # fused update of the screening kernel: long runs of uniform tiles, cluster changes inside a CTA's tile sequence,
+             # a ragged last tile, more tiles than one pass over the CTA pairs
+             (40000, 128, 32, 16, 30.0, False), (128 * 74 * 2 * 3 + 70, 128, 20, 7, 30.0, False), (60000, 128, 256, 3, 30.0, False)]
 
 
 @pytest.mark.parametrize("passes", [0, 1, 3])
@@ -583,6 +586,26 @@ def _pair_kernel_nan_inf_and_duplicates(ctx, oracle):
     lab, d = oracle.assign(X, init)
     assert counts.tolist() == np.bincount(lab.astype(np.int64), minlength=32).tolist()
     assert not np.isfinite(inertia)
+
+
+def test_pair_kernel_fused_update_is_reproducible_and_matches_two_pass(lb, ctx, oracle):
+    """The fused update (uniform tiles summed inside the screening kernel) against the two-pass path (3xTF32 + update pass):
+    same labels, so the same counts; sums within the f32 tolerance; run-to-run bit-identical."""
+    X, _ = blobs(50000, 128, 20, np.float32, seed=17, spread=30.0)
+    init = X[::2500][:20].copy()
+    ctx.set_data(X)
+    a = ctx.lloyd_iters(init, 3, 0.0)
+    b = ctx.lloyd_iters(init, 3, 0.0)
+    assert a[3].assign_path == 2
+    assert (a[0] == b[0]).all() and a[2] == b[2] and (a[1] == b[1]).all()
+    ctx.set_scoring_passes(3)
+    try:
+        c = ctx.lloyd_iters(init, 3, 0.0)
+    finally:
+        ctx.set_scoring_passes(0)
+    assert (a[1] == c[1]).all()
+    np.testing.assert_allclose(a[0], c[0], rtol=1e-5, atol=1e-5 * np.abs(c[0]).max())
+    np.testing.assert_allclose(a[2], c[2], rtol=1e-5)
 
 
 # ---- warp-specialised pipeline kernel (tc4: f32, d = 32, k <= 64) ----
