@@ -648,8 +648,9 @@ static lkm_status run_lloyd(lkm_ctx* ctx, F* dC2, uint64_t k, uint64_t max_iter,
       const void* fns = d == 64 ? (const void*)assign_tc5s_kernel<64, false> : (const void*)assign_tc5s_kernel<128, false>;
       CK(cudaFuncSetAttribute(fns, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc5s_smem_bytes((int)d)));
       CK(cudaFuncSetAttribute(fns, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
-      CK(cudaFuncSetAttribute(assign_tc5s_kernel<128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc5s_smem_bytes(128)));
-      CK(cudaFuncSetAttribute(assign_tc5s_kernel<128, true>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
+      const void* fnf = d == 64 ? (const void*)assign_tc5s_kernel<64, true> : (const void*)assign_tc5s_kernel<128, true>;
+      CK(cudaFuncSetAttribute(fnf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc5s_smem_bytes((int)d)));
+      CK(cudaFuncSetAttribute(fnf, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
       CKS(make_row_tile_map(ctx, dX, n, tc5_map, d));
       if (!ctx->own_X || ctx->xmax2_epoch != ctx->data_epoch) {
         CK(ctx->xmax2.ensure(16));
@@ -663,8 +664,8 @@ static lkm_status run_lloyd(lkm_ctx* ctx, F* dC2, uint64_t k, uint64_t max_iter,
       tc5_grid = 2 * (int)std::max<uint64_t>(1, std::min<uint64_t>(n_pt, (uint64_t)(ctx->sm_count / 2)));
       tc5_chunks = (int)((k + kT5K - 1) / kT5K);
       if (tc5_chunks > 1) CK(ctx->t5merge.ensure((n + 256) * 16));
-      // fused update of uniform tiles inside the screening kernel (d = 128, one chunk, one cluster chunk of the update pass)
-      tc5_can_fuse = ctx->tc5_fuse && d == 128 && tc5_chunks == 1 && upd_ny == 1;
+      // fused update of uniform tiles inside the screening kernel
+      tc5_can_fuse = ctx->tc5_fuse != 0;   // in the launch of the last chunk, where the merged verdicts are known
       if (tc5_can_fuse) {
         tc5_list_cap = (int)((n_pt + (uint64_t)(tc5_grid / 2) - 1) / (uint64_t)(tc5_grid / 2)) + 1;
         CK(ctx->t5list.ensure(((size_t)tc5_grid * tc5_list_cap + (size_t)tc5_grid + 64) * 4));
@@ -673,6 +674,7 @@ static lkm_status run_lloyd(lkm_ctx* ctx, F* dC2, uint64_t k, uint64_t max_iter,
     }
   }
   const int grid = pf.fused ? pf.grid : (use_upd ? (tc5_can_fuse ? std::max(upd_gx, 2 * tc5_grid) : upd_gx) : pu.grid);
+  if (tc5_can_fuse) CK(ctx->part_inertia.ensure((size_t)std::max(1024, tc5_grid * (1 + upd_ny)) * 8));
   CK(ctx->part_sums.ensure((size_t)grid * kd * sizeof(F)));
   CK(ctx->part_counts.ensure((size_t)grid * k * 4));
   CK(ctx->part_inertia.ensure((size_t)std::max(grid, 1024) * 8));
@@ -777,12 +779,13 @@ static lkm_status run_lloyd(lkm_ctx* ctx, F* dC2, uint64_t k, uint64_t max_iter,
             // one launch per chunk of 256 centroids; the per-row (best, runner-up) state travels through t5merge
             for (int ch = 0; ch < tc5_chunks; ++ch) {
               t5.chunk_idx = ch;
-              if (tc5_passes == 1 && tc5_can_fuse) {
+              if (tc5_passes == 1 && tc5_can_fuse && ch == tc5_chunks - 1) {
                 t5.part_sums = ctx->part_sums.as<float>(); t5.part_counts = ctx->part_counts.as<uint32_t>();
                 t5.part_inertia = ctx->part_inertia.as<double>();
                 t5.mixed_list = ctx->t5list.as<uint32_t>() + tc5_grid; t5.mixed_count = ctx->t5list.as<uint32_t>();
                 t5.list_cap = tc5_list_cap;
-                assign_tc5s_kernel<128, true><<<tc5_grid, kT5FuseThreads, tc5s_smem_bytes(128), ctx->stream>>>(t5, tc5_map);
+                if (d == 64) assign_tc5s_kernel<64, true><<<tc5_grid, t5_fuse_threads(64), tc5s_smem_bytes(64), ctx->stream>>>(t5, tc5_map);
+                else assign_tc5s_kernel<128, true><<<tc5_grid, t5_fuse_threads(128), tc5s_smem_bytes(128), ctx->stream>>>(t5, tc5_map);
                 fused_now = true;
               } else if (tc5_passes == 1) {
                 if (d == 64) assign_tc5s_kernel<64, false><<<tc5_grid, kT5Threads, tc5s_smem_bytes(64), ctx->stream>>>(t5, tc5_map);
@@ -835,7 +838,7 @@ static lkm_status run_lloyd(lkm_ctx* ctx, F* dC2, uint64_t k, uint64_t max_iter,
               ugx = tc5_grid;
             }
             fin_src = fused_now ? 2 * tc5_grid : upd_gx;
-            fin_src_inertia = fused_now ? 2 * tc5_grid : upd_gx * upd_ny;
+            fin_src_inertia = fused_now ? tc5_grid * (1 + upd_ny) : upd_gx * upd_ny;
             cudaLaunchConfig_t cfg{};
             cfg.gridDim = dim3((unsigned)ugx, (unsigned)upd_ny);
             cfg.blockDim = dim3((unsigned)kUpdThreads);

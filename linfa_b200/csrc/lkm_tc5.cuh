@@ -25,7 +25,7 @@
 namespace lkm {
 
 constexpr int kT5Threads = 10 * 32;
-constexpr int kT5FuseThreads = 14 * 32;   // screening kernel with the fused update: + four U warps
+__host__ __device__ constexpr int t5_fuse_threads(int d) { return (10 + d / 32) * 32; }   // screening kernel with the fused update: + one U warp per slab
 constexpr int kT5Stages = 4;
 constexpr uint32_t kT5ColAcc = 0, kT5ColA = 256;
 constexpr unsigned long long kT5Prefetch = 3;   // L2 prefetch distance of the P roles, in tiles
@@ -42,7 +42,7 @@ struct Tc5Args {
   uint32_t* labels;
   LloydState* state;
   long long* prof;   // LKM_T5_TRACE builds only
-  // fused update of the screening kernel (FUSE = true): per-CTA partials for finalize_kernel and the list of the tiles
+  // fused update of the screening kernel (FUSE = true; with several chunks: the launch of the last one): per-CTA partials for finalize_kernel and the list of the tiles
   // whose rows did not all certify to one cluster (those go through update_rows_kernel)
   float* part_sums;         // [gridDim.x][k * d], zeroed by the kernel
   uint32_t* part_counts;    // [gridDim.x][k]
@@ -584,12 +584,11 @@ __host__ __device__ inline size_t tc5s_smem_bytes(int d) {
 }
 
 template <int D, bool FUSE>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(FUSE ? kT5FuseThreads : kT5Threads, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(FUSE ? t5_fuse_threads(D) : kT5Threads, 1)
     assign_tc5s_kernel(const Tc5Args a, const __grid_constant__ CUtensorMap tmap) {
   static_assert(D == 64 || D == 128, "row width");
-  static_assert(!FUSE || D == 128, "the fused update maps one U warp to each of the four slabs of a tile");
   constexpr int NS = D / 32;
-  constexpr int NT = FUSE ? kT5FuseThreads : kT5Threads;
+  constexpr int NT = FUSE ? t5_fuse_threads(D) : kT5Threads;
   if (a.state != nullptr && a.state->done) return;
   extern __shared__ __align__(16) unsigned char smem_unaligned[];
   unsigned char* smem = smem_unaligned + ((1024u - (tc::smem_u32(smem_unaligned) & 1023u)) & 1023u);
@@ -876,7 +875,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(FUSE ? kT5FuseThread
   tc::tc_fence_before();
   __syncthreads();
   if constexpr (FUSE) {
-    if (t == 0) a.part_inertia[blockIdx.x] = (u_red[0] + u_red[1]) + (u_red[2] + u_red[3]);
+    if (t == 0) {
+      double tot = 0.0;
+      for (int q = 0; q < NS; ++q) tot += u_red[q];
+      a.part_inertia[blockIdx.x] = tot;
+    }
   }
   tc::cluster_sync_all();
   if (warp == 8) tc::tmem_dealloc_pair(tmem, 512);
