@@ -101,7 +101,7 @@ typedef struct lkm_stats {
   double inertia_total;      /* sum of min squared distances of the last assignment */
   float device_ms;           /* CUDA-event time of the iteration loop on the context stream */
   uint32_t kernel_launches;  /* kernels this library launched in the call */
-  uint32_t assign_path;      /* 0 exact CUDA-core, 1 certified FMA, 2 tcgen05 3xTF32 */
+  uint32_t assign_path;      /* 0 exact CUDA-core, 1 certified FMA, 2 tcgen05 3xTF32, 3 f32-screened f64 (small d) */
   uint64_t fallback_rows;    /* rows re-evaluated in exact form by the certified paths */
   float main_kernel_ms;      /* with lkm_set_l2_flush: summed duration of the assign/fused kernel alone */
   uint32_t reserved;
@@ -198,7 +198,7 @@ lkm_status lkm_fit_with_f64(lkm_ctx* ctx, const lkm_params* p, lkm_rng rng, int 
                             double* centroids_inout, double* cluster_count_inout, double* inertia_out);
 
 /* -- knobs that are not in the reference (all have defaults) --------------- */
-/* force an assignment path: -1 auto (default), 0 exact, 1 certified FMA, 2 tcgen05 */
+/* force an assignment path: -1 auto (default), 0 exact, 1 certified FMA, 2 tcgen05, 3 f32-screened f64 (lkm_f64s.cuh) */
 lkm_status lkm_set_assign_path(lkm_ctx* ctx, int path);
 /* measurement hygiene for benchmarks: when bytes > 0 every Lloyd iteration is
  * timed with its own CUDA events and a scratch buffer of `bytes` is overwritten

@@ -26,6 +26,7 @@
 #include "lkm_tc4.cuh"
 #include "lkm_upd.cuh"
 #include "lkm_tc5.cuh"
+#include "lkm_f64s.cuh"
 
 #define LKM_EXPORT extern "C" __attribute__((visibility("default")))
 
@@ -100,6 +101,9 @@ struct lkm_ctx {
   int tc_variant = 4;
   int tc5_passes_forced = 0;            // LKM_TC5_PASSES = 1 / 3 pins the screening / 3xTF32 variant of the pair kernel
   uint64_t tc5_hard_epoch = 0, tc5_easy_epoch = 0;
+  int f64s_enabled = 1;  // LKM_F64S=0: lloyd_kernel<double> instead of the f32-screened small-d f64 kernel (lkm_f64s.cuh)
+  int f64s_packed = 1;   // LKM_F64S_PACKED=0: scalar FFMA instead of FFMA2 in that kernel
+  int pair32 = 0;        // LKM_PAIR32=1: d = 32, k <= 64 through the CTA-pair screening kernel instead of the pipeline kernel
   int tc5_fuse = 1;      // LKM_TC5_FUSE=0: screening kernel without the fused update of uniform tiles
   int tc5_enabled = 1;   // LKM_TC5=0: tc_assign_kernel instead of the CTA-pair assignment kernel
   int upd_variant = 1;   // LKM_UPD=0: cluster-chunked lloyd_kernel<MODE_UPDATE> instead of update_rows_kernel
@@ -473,14 +477,17 @@ static lkm_status run_lloyd(lkm_ctx* ctx, F* dC2, uint64_t k, uint64_t max_iter,
   const F* dX = reinterpret_cast<const F*>(ctx->X);
   if (kd > (uint64_t)std::numeric_limits<int>::max() / 4) return fail(ctx, LKM_ERR_UNSUPPORTED, "k*d too large");
   // tensor-core path: f32, d = 32, k <= 256, everything resident in shared memory
-  bool use_tc = false;
+  bool use_tc = false, pair32 = false;
   int tc_grid = 0, tc_kp = 0, tc_cols = 0, tc_threads = 128;
   size_t tc_smem = 0;
   int tc4_nstages = 0;
   CUtensorMap tc3_map;
   std::memset(&tc3_map, 0, sizeof(tc3_map));
   if constexpr (std::is_same<F, float>::value) {
-    if ((ctx->force_path == -1 || ctx->force_path == 2) && d == 32 && k <= 256 && n >= 1 &&
+    pair32 = ctx->pair32 && ctx->tc5_enabled && ctx->upd_variant != 0 && (ctx->force_path == -1 || ctx->force_path == 2) && d == 32 &&
+             k <= 64 && kd >= 512 && n >= 1 && (reinterpret_cast<uintptr_t>(dX) & 15) == 0 &&
+             !(ctx->tc5_hard_epoch == ctx->data_epoch && ctx->own_X);   // data that screening cannot certify: pipeline kernel
+    if (!pair32 && (ctx->force_path == -1 || ctx->force_path == 2) && d == 32 && k <= 256 && n >= 1 &&
         (reinterpret_cast<uintptr_t>(dX) & 15) == 0) {
       tc_kp = (int)((k + 31) / 32 * 32);
       tc_cols = 32;
@@ -540,7 +547,7 @@ static lkm_status run_lloyd(lkm_ctx* ctx, F* dC2, uint64_t k, uint64_t max_iter,
       }
       }
     }
-    if (ctx->force_path == 2 && !use_tc) return fail(ctx, LKM_ERR_UNSUPPORTED, "tcgen05 path needs f32, d = 32, k <= 256");
+    if (ctx->force_path == 2 && !use_tc && !pair32) return fail(ctx, LKM_ERR_UNSUPPORTED, "tcgen05 path needs f32, d = 32, k <= 256");
   } else {
     if (ctx->force_path == 2) return fail(ctx, LKM_ERR_UNSUPPORTED, "tcgen05 path needs f32, d = 32, k <= 256");
   }
@@ -553,8 +560,41 @@ static lkm_status run_lloyd(lkm_ctx* ctx, F* dC2, uint64_t k, uint64_t max_iter,
     if (!use_tc && (ctx->force_path == -1 || ctx->force_path == 2) && ctx->tc5_enabled && ctx->upd_variant != 0 &&
         (d == 64 || d == 128) && k <= (uint64_t)kT5K * 16 && kd >= 2048 && n >= 1 && (reinterpret_cast<uintptr_t>(dX) & 15) == 0)
       pf.fused = false;
+    if (pair32) pf.fused = false;
   }
   ctx->last_path = use_tc ? 2 : ((pf.fused && pf.certified) ? 1 : 0);
+  // f64, 2 / 4 / 8 / 16 features, few centroids: f32-screened warp-per-tile kernel (lkm_f64s.cuh)
+  bool use_f6 = false;
+  size_t f6_smem = 0;
+  if constexpr (std::is_same<F, double>::value) {
+    const bool shape_ok = (d == 2 || d == 4 || d == 8 || d == 16) && k <= 64 && kd <= 512 && n >= 1 &&
+                          (reinterpret_cast<uintptr_t>(dX) & 15) == 0;
+    if (shape_ok && ((ctx->force_path == -1 && ctx->f64s_enabled && n >= 32768) || ctx->force_path == 3)) {
+      const void* fn = nullptr;
+      switch (d) {
+        case 2: f6_smem = f6::smem_bytes<2>((int)k); fn = ctx->f64s_packed ? (const void*)f6::lloyd_f64s_kernel<2, true> : (const void*)f6::lloyd_f64s_kernel<2, false>; break;
+        case 4: f6_smem = f6::smem_bytes<4>((int)k); fn = ctx->f64s_packed ? (const void*)f6::lloyd_f64s_kernel<4, true> : (const void*)f6::lloyd_f64s_kernel<4, false>; break;
+        case 8: f6_smem = f6::smem_bytes<8>((int)k); fn = ctx->f64s_packed ? (const void*)f6::lloyd_f64s_kernel<8, true> : (const void*)f6::lloyd_f64s_kernel<8, false>; break;
+        default: f6_smem = f6::smem_bytes<16>((int)k); fn = ctx->f64s_packed ? (const void*)f6::lloyd_f64s_kernel<16, true> : (const void*)f6::lloyd_f64s_kernel<16, false>; break;
+      }
+      if (f6_smem <= ctx->smem_optin) {
+        CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)f6_smem));
+        CK(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
+        int occ = 0;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, f6::kThreads, f6_smem));
+        occ = std::max(1, occ);
+        const uint64_t n_tiles = (n + f6::kTileRows - 1) / f6::kTileRows;
+        const uint64_t want = (n_tiles + f6::kWarps - 1) / f6::kWarps;
+        pf.fused = true;
+        pf.grid = (int)std::max<uint64_t>(1, std::min<uint64_t>(want, (uint64_t)ctx->sm_count * occ));
+        use_f6 = true;
+        ctx->last_path = 3;
+      }
+    }
+    if (ctx->force_path == 3 && !use_f6) return fail(ctx, LKM_ERR_UNSUPPORTED, "f32-screened f64 path needs d in {2,4,8,16}, k <= 64, k*d <= 512");
+  } else {
+    if (ctx->force_path == 3) return fail(ctx, LKM_ERR_UNSUPPORTED, "f32-screened f64 path needs f64 data");
+  }
   Plan pa, pu;
   int n_chunks = 1, chunk_rows = (int)k;
   if (!pf.fused) {
@@ -633,22 +673,28 @@ static lkm_status run_lloyd(lkm_ctx* ctx, F* dC2, uint64_t k, uint64_t max_iter,
   }
   // CTA-pair assignment kernel (lkm_tc5.cuh): all centroid operand tiles resident across the two CTAs of a cluster
   bool use_tc5 = false;
-  int tc5_grid = 0, tc5_chunks = 1, tc5_list_cap = 0;
+  int tc5_grid = 0, tc5_chunks = 1, tc5_list_cap = 0, tc5_chunk_n = kT5K;
   bool tc5_can_fuse = false;
   size_t tc5_smem = 0;
   CUtensorMap tc5_map;
   std::memset(&tc5_map, 0, sizeof(tc5_map));
   if constexpr (std::is_same<F, float>::value) {
-    if (use_upd && ctx->tc5_enabled && (d == 64 || d == 128) && k <= (uint64_t)kT5K * 16 && n + 512 < (1ull << 31) &&
+    if (use_upd && ctx->tc5_enabled && (d == 64 || d == 128 || pair32) && k <= (uint64_t)kT5K * 16 && n + 512 < (1ull << 31) &&
         tc5_smem_bytes((int)d) <= ctx->smem_optin && tc5s_smem_bytes((int)d) <= ctx->smem_optin) {
       tc5_smem = tc5_smem_bytes((int)d);
       const void* fn = d == 64 ? (const void*)assign_tc5_kernel<64> : (const void*)assign_tc5_kernel<128>;
       CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc5_smem));
       CK(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
-      const void* fns = d == 64 ? (const void*)assign_tc5s_kernel<64, false> : (const void*)assign_tc5s_kernel<128, false>;
+      const void* fns = d == 64 ? (const void*)assign_tc5s_kernel<64, false, 256> : (const void*)assign_tc5s_kernel<128, false, 256>;
       CK(cudaFuncSetAttribute(fns, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc5s_smem_bytes((int)d)));
       CK(cudaFuncSetAttribute(fns, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
-      const void* fnf = d == 64 ? (const void*)assign_tc5s_kernel<64, true> : (const void*)assign_tc5s_kernel<128, true>;
+      if (pair32) {
+        CK(cudaFuncSetAttribute(assign_tc5s_kernel<32, true, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc5s_smem_bytes(32)));
+        CK(cudaFuncSetAttribute(assign_tc5s_kernel<32, true, 64>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
+        CK(cudaFuncSetAttribute(assign_tc5s_kernel<32, false, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc5s_smem_bytes(32)));
+        CK(cudaFuncSetAttribute(assign_tc5s_kernel<32, false, 64>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
+      }
+      const void* fnf = d == 64 ? (const void*)assign_tc5s_kernel<64, true, 256> : (const void*)assign_tc5s_kernel<128, true, 256>;
       CK(cudaFuncSetAttribute(fnf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc5s_smem_bytes((int)d)));
       CK(cudaFuncSetAttribute(fnf, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
       CKS(make_row_tile_map(ctx, dX, n, tc5_map, d));
@@ -662,7 +708,8 @@ static lkm_status run_lloyd(lkm_ctx* ctx, F* dC2, uint64_t k, uint64_t max_iter,
       }
       const uint64_t n_pt = ((n + 127) / 128 + 1) / 2;
       tc5_grid = 2 * (int)std::max<uint64_t>(1, std::min<uint64_t>(n_pt, (uint64_t)(ctx->sm_count / 2)));
-      tc5_chunks = (int)((k + kT5K - 1) / kT5K);
+      tc5_chunk_n = pair32 ? 64 : kT5K;
+      tc5_chunks = (int)((k + tc5_chunk_n - 1) / tc5_chunk_n);
       if (tc5_chunks > 1) CK(ctx->t5merge.ensure((n + 256) * 16));
       // fused update of uniform tiles inside the screening kernel
       tc5_can_fuse = ctx->tc5_fuse != 0;   // in the launch of the last chunk, where the merged verdicts are known
@@ -716,6 +763,7 @@ static lkm_status run_lloyd(lkm_ctx* ctx, F* dC2, uint64_t k, uint64_t max_iter,
   // pair kernel: the screening variant (one TF32 product) first, 3xTF32 when too many rows needed the exact re-scan
   int tc5_passes = 3;
   if (use_tc5) tc5_passes = ctx->tc5_passes_forced ? ctx->tc5_passes_forced : ((ctx->tc5_hard_epoch == ctx->data_epoch && ctx->own_X) ? 3 : 1);
+  if (use_tc5 && d == 32) tc5_passes = 1;   // the d = 32 instantiation only exists as the screening variant
   bool tc5_probe = use_tc5 && !ctx->tc5_passes_forced && tc5_passes == 1 && !(ctx->tc5_easy_epoch == ctx->data_epoch && ctx->own_X);
   unsigned long long fb_seen = 0;
   for (;;) {
@@ -754,6 +802,22 @@ static lkm_status run_lloyd(lkm_ctx* ctx, F* dC2, uint64_t k, uint64_t max_iter,
           else CK(launch_pdl(lloyd_tc_kernel, tc_grid, 128, tc_smem, ctx->stream, ta, true));
           ctx->launches++;
         }
+      } else if (use_f6) {
+        if constexpr (std::is_same<F, double>::value) {
+          f6::Args fa6{};
+          fa6.X = dX; fa6.n = n; fa6.k = (int)k; fa6.C = Ccur;
+          fa6.part_sums = ctx->part_sums.as<double>(); fa6.part_counts = ctx->part_counts.as<uint32_t>();
+          fa6.part_inertia = ctx->part_inertia.as<double>(); fa6.state = dstate; fa6.state_rw = dstate;
+          const bool pk = ctx->f64s_packed != 0;
+          switch (d) {
+            case 2: if (pk) f6::lloyd_f64s_kernel<2, true><<<pf.grid, f6::kThreads, f6_smem, ctx->stream>>>(fa6); else f6::lloyd_f64s_kernel<2, false><<<pf.grid, f6::kThreads, f6_smem, ctx->stream>>>(fa6); break;
+            case 4: if (pk) f6::lloyd_f64s_kernel<4, true><<<pf.grid, f6::kThreads, f6_smem, ctx->stream>>>(fa6); else f6::lloyd_f64s_kernel<4, false><<<pf.grid, f6::kThreads, f6_smem, ctx->stream>>>(fa6); break;
+            case 8: if (pk) f6::lloyd_f64s_kernel<8, true><<<pf.grid, f6::kThreads, f6_smem, ctx->stream>>>(fa6); else f6::lloyd_f64s_kernel<8, false><<<pf.grid, f6::kThreads, f6_smem, ctx->stream>>>(fa6); break;
+            default: if (pk) f6::lloyd_f64s_kernel<16, true><<<pf.grid, f6::kThreads, f6_smem, ctx->stream>>>(fa6); else f6::lloyd_f64s_kernel<16, false><<<pf.grid, f6::kThreads, f6_smem, ctx->stream>>>(fa6); break;
+          }
+          CK(cudaGetLastError());
+          ctx->launches++;
+        }
       } else if (pf.fused) {
         LloydArgs<F> a{};
         a.X = dX; a.n = n; a.d = (int)d; a.k = (int)k; a.C = Ccur;
@@ -771,7 +835,7 @@ static lkm_status run_lloyd(lkm_ctx* ctx, F* dC2, uint64_t k, uint64_t max_iter,
             Tc5Args t5{};
             t5.X = dX; t5.n = n; t5.k = (int)k; t5.C = Ccur; t5.xmax2_bits = ctx->xmax2.as<unsigned int>();
             t5.labels = ctx->labels.as<uint32_t>(); t5.state = dstate; t5.pack_mult = 256u;
-            t5.n_chunks = tc5_chunks; t5.merge = tc5_chunks > 1 ? ctx->t5merge.as<uint4>() : nullptr;
+            t5.n_chunks = tc5_chunks; t5.chunk_n = tc5_chunk_n; t5.merge = tc5_chunks > 1 ? ctx->t5merge.as<uint4>() : nullptr;
 #ifdef LKM_T5_TRACE
             CK(ctx->t4prof.ensure(2 * 16 * 16 * 8));
             t5.prof = ctx->t4prof.as<long long>();
@@ -784,12 +848,14 @@ static lkm_status run_lloyd(lkm_ctx* ctx, F* dC2, uint64_t k, uint64_t max_iter,
                 t5.part_inertia = ctx->part_inertia.as<double>();
                 t5.mixed_list = ctx->t5list.as<uint32_t>() + tc5_grid; t5.mixed_count = ctx->t5list.as<uint32_t>();
                 t5.list_cap = tc5_list_cap;
-                if (d == 64) assign_tc5s_kernel<64, true><<<tc5_grid, t5_fuse_threads(64), tc5s_smem_bytes(64), ctx->stream>>>(t5, tc5_map);
-                else assign_tc5s_kernel<128, true><<<tc5_grid, t5_fuse_threads(128), tc5s_smem_bytes(128), ctx->stream>>>(t5, tc5_map);
+                if (d == 32) assign_tc5s_kernel<32, true, 64><<<tc5_grid, t5_fuse_threads(32), tc5s_smem_bytes(32), ctx->stream>>>(t5, tc5_map);
+                else if (d == 64) assign_tc5s_kernel<64, true, 256><<<tc5_grid, t5_fuse_threads(64), tc5s_smem_bytes(64), ctx->stream>>>(t5, tc5_map);
+                else assign_tc5s_kernel<128, true, 256><<<tc5_grid, t5_fuse_threads(128), tc5s_smem_bytes(128), ctx->stream>>>(t5, tc5_map);
                 fused_now = true;
               } else if (tc5_passes == 1) {
-                if (d == 64) assign_tc5s_kernel<64, false><<<tc5_grid, kT5Threads, tc5s_smem_bytes(64), ctx->stream>>>(t5, tc5_map);
-                else assign_tc5s_kernel<128, false><<<tc5_grid, kT5Threads, tc5s_smem_bytes(128), ctx->stream>>>(t5, tc5_map);
+                if (d == 32) assign_tc5s_kernel<32, false, 64><<<tc5_grid, kT5Threads, tc5s_smem_bytes(32), ctx->stream>>>(t5, tc5_map);
+                else if (d == 64) assign_tc5s_kernel<64, false, 256><<<tc5_grid, kT5Threads, tc5s_smem_bytes(64), ctx->stream>>>(t5, tc5_map);
+                else assign_tc5s_kernel<128, false, 256><<<tc5_grid, kT5Threads, tc5s_smem_bytes(128), ctx->stream>>>(t5, tc5_map);
               } else if (d == 64) assign_tc5_kernel<64><<<tc5_grid, kT5Threads, tc5_smem, ctx->stream>>>(t5, tc5_map);
               else assign_tc5_kernel<128><<<tc5_grid, kT5Threads, tc5_smem, ctx->stream>>>(t5, tc5_map);
               CK(cudaGetLastError());
@@ -937,7 +1003,7 @@ static lkm_status run_lloyd(lkm_ctx* ctx, F* dC2, uint64_t k, uint64_t max_iter,
     }
     if (use_tc5 && !ctx->tc5_passes_forced && tc5_passes == 1) {
       const unsigned long long fb = (ctx->h_state->fallback_rows & ((1ull << 40) - 1)) - fb_seen;
-      if ((double)fb > 0.02 * (double)n * (double)todo_done) { tc5_passes = 3; ctx->tc5_hard_epoch = ctx->data_epoch; }
+      if ((double)fb > 0.02 * (double)n * (double)todo_done) { if (d != 32) tc5_passes = 3; ctx->tc5_hard_epoch = ctx->data_epoch; }
       else ctx->tc5_easy_epoch = ctx->data_epoch;
       tc5_probe = false;
     }
@@ -1818,6 +1884,9 @@ LKM_EXPORT lkm_status lkm_create(lkm_ctx** out, int device) {
   if (const char* v = std::getenv("LKM_UPD")) ctx->upd_variant = std::atoi(v);
   if (const char* v = std::getenv("LKM_TC5")) ctx->tc5_enabled = std::atoi(v);
   if (const char* v = std::getenv("LKM_TC5_FUSE")) ctx->tc5_fuse = std::atoi(v);
+  if (const char* v = std::getenv("LKM_PAIR32")) ctx->pair32 = std::atoi(v);
+  if (const char* v = std::getenv("LKM_F64S")) ctx->f64s_enabled = std::atoi(v);
+  if (const char* v = std::getenv("LKM_F64S_PACKED")) ctx->f64s_packed = std::atoi(v);
   if (const char* v = std::getenv("LKM_TC5_PASSES")) ctx->tc5_passes_forced = std::atoi(v);
   if (const char* v = std::getenv("LKM_P2P")) ctx->p2p_enabled = std::atoi(v);
   if (const char* v = std::getenv("LKM_TC4_PASSES")) ctx->tc4_passes_forced = std::atoi(v);
@@ -1859,7 +1928,7 @@ LKM_EXPORT lkm_status lkm_synchronize(lkm_ctx* ctx) {
   return LKM_OK;
 }
 LKM_EXPORT lkm_status lkm_set_assign_path(lkm_ctx* ctx, int path) {
-  if (!ctx || path < -1 || path > 2) return LKM_ERR_INVALID_ARG;
+  if (!ctx || path < -1 || path > 3) return LKM_ERR_INVALID_ARG;
   ctx->force_path = path;
   return LKM_OK;
 }

@@ -1,0 +1,387 @@
+// Fused Lloyd iteration for f64 rows of 2 / 4 / 8 / 16 features and few centroids (BASELINE cfg5: 125M x 8 per GPU, k = 16).
+//
+// Replaces, for that shape, lloyd_kernel<double, D, MODE_FUSED> (lkm_kernels.cuh), whose 128 DFMA + 32 DSETP per row keep
+// the FP64 pipe (64 lanes / clk / SM) 4x over the HBM budget of 2.8 cycles per row and SM.  Reference semantics:
+// KM/algorithm.rs:866-881, 923-946 (assignment, strict '<'), :785-810 (update), :329 (inertia).
+//
+//   * one warp = one 64-row tile (two rows per lane), no CTA-wide barrier in the loop; tiles are dealt round-robin to
+//     the warps of the grid (static schedule => bit-reproducible sums)
+//   * rows arrive by cp.async (16-byte chunks, fully coalesced) into a per-warp double-buffered stage whose layout has
+//     one 16-byte pad per 128 bytes: the row-per-lane reads (LDS.128) and the feature-per-lane reads of the update walk
+//     (LDS.64) are both bank-conflict-free
+//   * SCREENING IN F32: w_c = |c|^2 - 2 x.c with x, -2c, |c|^2 rounded to f32 (FFMA2: two centroids per instruction),
+//     running best / runner-up by FMNMX on scores that carry the centroid index in their low mantissa bits.  The row is
+//     certified when runner-up - best exceeds a rigorous bound on everything that separates this arithmetic from the
+//     reference's f64 direct form (derivation at f6_margin); then the reference's strict-'<' scan picks the same centroid.
+//     Uncertified rows (near ties, ties, NaN / Inf, f32 overflow / underflow) go through scan_centroids_certified<double>
+//     (f64 FMA scores, own certificate, exact re-scan in the reference's arithmetic) exactly like the kernel this one replaces.
+//   * winner's distance in f64 (direct form), inertia per lane in f64
+//   * update: lane = (feature f, row group h) walks the tile's rows h, h + H, ... straight from the stage, keeps the
+//     running sum of the current cluster in a register and touches the warp's accumulator copy in shared memory only when
+//     the label changes (blob-ordered data: once per blob); concurrent flushes of one cluster by different row groups are
+//     detected (match.any) and serialised.  Per-CTA partials in warp order -> finalize_kernel as for every other path.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "lkm_kernels.cuh"
+
+namespace lkm {
+namespace f6 {
+
+constexpr int kWarps = 8;
+constexpr int kThreads = kWarps * 32;
+constexpr int kTileRows = 64;   // per warp and step: two rows per lane
+constexpr int kStages = 2;
+
+struct Args {
+  const double* X;
+  unsigned long long n;
+  int k;
+  const double* C;
+  double* part_sums;        // [grid][k * D]
+  uint32_t* part_counts;    // [grid][k]
+  double* part_inertia;     // [grid]
+  const LloydState* state;
+  LloydState* state_rw;     // fallback_rows += rows that needed the exact re-scan
+};
+
+template <int D> __host__ __device__ constexpr int stage_bytes() { return kTileRows * D * 8 + (kTileRows * D * 8 / 128) * 16; }
+// byte offset of a row inside a stage: 16 bytes of padding after every 128 bytes of rows
+template <int D> __device__ __forceinline__ uint32_t row_off(int row) {
+  constexpr int RP = 16 / D;   // rows per 128 bytes
+  return (uint32_t)(row * (D * 8) + (row / RP) * 16);
+}
+
+__host__ __device__ inline size_t al16(size_t x) { return (x + 15) & ~(size_t)15; }
+// dynamic shared memory: exact centroids | norms + max | f32 pair operands | f32 pair norms | per warp {stages, sums, counts}
+template <int D> __host__ __device__ inline size_t smem_bytes(int k) {
+  const int kp = (k + 1) & ~1;
+  return al16((size_t)k * D * 8) + al16((size_t)(k + 1) * 8) + al16((size_t)kp * D * 4) + al16((size_t)kp * 4) + 16 +
+         (size_t)kWarps * (kStages * stage_bytes<D>() + al16((size_t)k * D * 8) + al16((size_t)k * 4));
+}
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, int src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+__device__ __forceinline__ unsigned long long f2_fma(unsigned long long a, unsigned long long b, unsigned long long c) {
+  unsigned long long d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ unsigned long long pack2(float lo, float hi) {
+  unsigned long long d;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "f"(lo), "f"(hi));
+  return d;
+}
+__device__ __forceinline__ void unpack2(unsigned long long v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+
+// score with the centroid index in the low mantissa bits; then running best / runner-up by min / max
+__device__ __forceinline__ void top2_packed(float w, uint32_t idx, uint32_t keep, float& best, float& second) {
+  const float q = __uint_as_float((__float_as_uint(w) & keep) | idx);
+  second = fminf(second, fmaxf(best, q));
+  best = fminf(best, q);
+}
+
+// Certificate of the f32 screening.  u = 2^-24.  Inputs x^ = fl32(x), c^ = fl32(-2c), n^ = fl32(|c|^2): relative error u
+// each.  The FMA chain s_j = fl(s_{j-1} + x^_j c^_j) rounds d partial sums of magnitude <= M = C^2 + 2XC (X >= |x|,
+// C >= max|c|), so |w - W| <= u [ d M + C^2 + 4XC ] (1 + O(u)) against W = |c|^2 - 2x.c.  Packing the index changes a
+// score by < (idx_mask + 1) 2^-23 M.  The reference's f64 direct form is within (d+2) 2^-53 (X+C)^2 of the true distance.
+// Denormal inputs / results add at most (4d+8) 2^-149 (1 + X + C) in absolute terms.  Both candidates:
+//   runner-up - best > 1.1 * 2 * { u [ (d+1) C^2 + (2d+4) XC ] + (idx_mask+1) 2^-23 (C^2 + 2XC) + (d+2) 2^-53 (X+C)^2 }
+//                      + (8d+16) 2^-149 (1 + X + C)
+// proves that the reference picks `best`.  NaN / Inf anywhere (x, c, overflow) makes the comparison false.
+template <int D>
+__device__ __forceinline__ float f6_margin(float xx, float cmax, float idx_span) {
+  const float X = sqrtf(xx) * 1.0001f;
+  const float u = 5.9604645e-8f;
+  const float c2 = cmax * cmax, xc = X * cmax, xpc = X + cmax;
+  const float rel = u * ((float)(D + 1) * c2 + (float)(2 * D + 4) * xc) + idx_span * 1.1920929e-7f * (c2 + 2.f * xc) +
+                    (float)(D + 2) * 1.1102230e-16f * xpc * xpc;
+  return fmaf(2.2f, rel, (float)(8 * D + 16) * 1.4012985e-45f * (1.f + xpc));
+}
+
+// add a lane's running (sum, count) of cluster `lab` to the warp's accumulator copy; all 32 lanes call it.
+// Lanes of one row group (same h) hold the same label and different features; two row groups flushing the same
+// cluster in the same step are serialised.
+template <int D>
+__device__ __forceinline__ void flush_acc(bool fl, int lab, double sum, uint32_t count, double* __restrict__ acc,
+                                          uint32_t* __restrict__ cnt, int f, int h) {
+  constexpr int H = 32 / D;
+  const unsigned full = 0xffffffffu;
+  const int key = fl ? lab : -1 - h;
+  const unsigned same = __match_any_sync(full, key);
+  const bool conflict = fl && __popc(same) > D;
+  if (!__any_sync(full, conflict)) {
+    if (fl) {
+      acc[lab * D + f] += sum;
+      if (f == 0) cnt[lab] += count;
+    }
+  } else {
+    for (int hh = 0; hh < H; ++hh) {
+      if (fl && h == hh) {
+        acc[lab * D + f] += sum;
+        if (f == 0) cnt[lab] += count;
+      }
+      __syncwarp();
+    }
+  }
+  __syncwarp();
+}
+
+template <int D, bool PACKED>
+__global__ void __launch_bounds__(kThreads, 2) lloyd_f64s_kernel(const Args a) {
+  static_assert(D == 2 || D == 4 || D == 8 || D == 16, "row width");
+  if (a.state != nullptr && a.state->done) return;
+  constexpr int CPR = D / 2;            // 16-byte chunks per row
+  constexpr int H = 32 / D;             // rows per step of the update walk
+  constexpr int STEPS = kTileRows / H;
+  constexpr int SB = stage_bytes<D>();
+  const unsigned full = 0xffffffffu;
+  extern __shared__ __align__(16) unsigned char smem[];
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  const int k = a.k, kp = (k + 1) & ~1;
+  size_t off = 0;
+  double* cs = reinterpret_cast<double*>(smem + off); off += al16((size_t)k * D * 8);
+  double* cn = reinterpret_cast<double*>(smem + off); off += al16((size_t)(k + 1) * 8);
+  float* cfp = reinterpret_cast<float*>(smem + off); off += al16((size_t)kp * D * 4);   // [pair][feature][2] = -2c
+  float* cnp = reinterpret_cast<float*>(smem + off); off += al16((size_t)kp * 4);       // [pair][2] = |c|^2
+  float* cmaxf_s = reinterpret_cast<float*>(smem + off); off += 16;
+  const size_t per_warp = (size_t)kStages * SB + al16((size_t)k * D * 8) + al16((size_t)k * 4);
+  unsigned char* wbase = smem + off + (size_t)warp * per_warp;
+  unsigned char* stage0 = wbase;
+  double* acc = reinterpret_cast<double*>(wbase + (size_t)kStages * SB);
+  uint32_t* cnt = reinterpret_cast<uint32_t*>(wbase + (size_t)kStages * SB + al16((size_t)k * D * 8));
+
+  // ---- tile schedule and the first load (before the prologue, so that it overlaps it) ----
+  const unsigned long long n_tiles = (a.n + kTileRows - 1) / kTileRows;
+  const unsigned long long G = (unsigned long long)gridDim.x * kWarps;
+  unsigned long long tile = (unsigned long long)blockIdx.x * kWarps + warp;
+  auto issue = [&](unsigned long long tl, int st) {
+    const unsigned long long row0 = tl * kTileRows;
+    const uint32_t sbase = smem_u32(stage0 + (size_t)st * SB);
+#pragma unroll
+    for (int q = 0; q < kTileRows * CPR / 32; ++q) {
+      const int g = q * 32 + lane;
+      const int row = g / CPR, c = g % CPR;
+      const bool ok = row0 + row < a.n;
+      const double* src = ok ? a.X + (row0 + row) * D + c * 2 : a.X;
+      cp_async16(sbase + row_off<D>(row) + c * 16, src, ok ? 16 : 0);
+    }
+  };
+  if (tile < n_tiles) issue(tile, 0);
+  cp_async_commit();
+
+  // ---- prologue: centroids in f64 (exact paths) and as f32 pair operands (screening) ----
+  for (int e = t; e < k * D; e += kThreads) cs[e] = a.C[e];
+  for (int e = lane; e < k * D; e += 32) acc[e] = 0.0;
+  for (int e = lane; e < k; e += 32) cnt[e] = 0u;
+  __syncthreads();
+  for (int c = t; c < kp; c += kThreads) {
+    double nn = 0.0;
+    if (c < k)
+      for (int j = 0; j < D; ++j) nn += cs[c * D + j] * cs[c * D + j];
+    if (c < k) cn[c] = nn;
+    cnp[c] = c < k ? (float)nn : 3.0e38f;
+    for (int j = 0; j < D; ++j) cfp[((c >> 1) * D + j) * 2 + (c & 1)] = c < k ? (float)(-2.0 * cs[c * D + j]) : 0.f;
+  }
+  __syncthreads();
+  if (t == 0) {
+    double m = 0.0;
+    bool bad = false;
+    for (int c = 0; c < k; ++c) {
+      m = (cn[c] > m) ? cn[c] : m;   // NaN norms are skipped here (the f64 certified scan sends such rows to the exact path)
+      bad |= !(cn[c] < 1.0e300);     // NaN / Inf / huge: no f32 certificate at all
+    }
+    const double cm = sqrt(m) * 1.000001;
+    cn[k] = cm;
+    cmaxf_s[0] = bad ? __int_as_float(0x7fc00000) : __double2float_ru(cm);
+  }
+  __syncthreads();
+  const double cmax64 = cn[k];
+  const float cmaxf = cmaxf_s[0];
+  int idx_bits = 1;
+  while ((1 << idx_bits) < kp) ++idx_bits;
+  const uint32_t idx_mask = (1u << idx_bits) - 1u, keep = ~idx_mask;
+  const float idx_span = (float)(idx_mask + 1u);
+
+  const int f = lane % D, h = lane / D;
+  int cur_lab = -1;
+  double cur_acc = 0.0;
+  uint32_t cur_cnt = 0u;
+  double inert = 0.0;
+  unsigned int my_fallbacks = 0;
+
+  for (int it = 0; tile < n_tiles; ++it, tile += G) {
+    const int st = it & 1;
+    if (tile + G < n_tiles) issue(tile + G, st ^ 1);
+    cp_async_commit();
+    cp_async_wait<1>();
+    __syncwarp();
+    const unsigned char* sp = stage0 + (size_t)st * SB;
+    const unsigned long long row0 = tile * kTileRows;
+
+    // ---- own rows: lane, lane + 32 ----
+    double x0[D], x1[D];
+#pragma unroll
+    for (int c = 0; c < CPR; ++c) {
+      const double2 v0 = *reinterpret_cast<const double2*>(sp + row_off<D>(lane) + c * 16);
+      const double2 v1 = *reinterpret_cast<const double2*>(sp + row_off<D>(lane + 32) + c * 16);
+      x0[2 * c] = v0.x; x0[2 * c + 1] = v0.y;
+      x1[2 * c] = v1.x; x1[2 * c + 1] = v1.y;
+    }
+    float xf0[D], xf1[D];
+    float xx0 = 0.f, xx1 = 0.f;
+#pragma unroll
+    for (int j = 0; j < D; ++j) {
+      xf0[j] = (float)x0[j];
+      xf1[j] = (float)x1[j];
+      xx0 = fmaf(xf0[j], xf0[j], xx0);
+      xx1 = fmaf(xf1[j], xf1[j], xx1);
+    }
+    float b0 = 3.0e38f, s0 = 3.0e38f, b1 = 3.0e38f, s1 = 3.0e38f;
+    if constexpr (PACKED) {
+      unsigned long long xd0[D], xd1[D];
+#pragma unroll
+      for (int j = 0; j < D; ++j) { xd0[j] = pack2(xf0[j], xf0[j]); xd1[j] = pack2(xf1[j], xf1[j]); }
+#pragma unroll 2
+      for (int p = 0; p < kp / 2; ++p) {
+        unsigned long long w0 = *reinterpret_cast<const unsigned long long*>(cnp + 2 * p), w1 = w0;
+#pragma unroll
+        for (int j = 0; j < D; j += 2) {
+          const ulonglong2 c2 = *reinterpret_cast<const ulonglong2*>(cfp + (p * D + j) * 2);
+          w0 = f2_fma(xd0[j], c2.x, w0);
+          w1 = f2_fma(xd1[j], c2.x, w1);
+          w0 = f2_fma(xd0[j + 1], c2.y, w0);
+          w1 = f2_fma(xd1[j + 1], c2.y, w1);
+        }
+        float wa, wb;
+        unpack2(w0, wa, wb);
+        top2_packed(wa, 2u * p, keep, b0, s0);
+        top2_packed(wb, 2u * p + 1u, keep, b0, s0);
+        unpack2(w1, wa, wb);
+        top2_packed(wa, 2u * p, keep, b1, s1);
+        top2_packed(wb, 2u * p + 1u, keep, b1, s1);
+      }
+    } else {
+#pragma unroll 2
+      for (int p = 0; p < kp / 2; ++p) {
+        const float2 nn = *reinterpret_cast<const float2*>(cnp + 2 * p);
+        float wa0 = nn.x, wb0 = nn.y, wa1 = nn.x, wb1 = nn.y;
+#pragma unroll
+        for (int j = 0; j < D; j += 2) {
+          const float4 c4 = *reinterpret_cast<const float4*>(cfp + (p * D + j) * 2);
+          wa0 = fmaf(xf0[j], c4.x, wa0); wb0 = fmaf(xf0[j], c4.y, wb0);
+          wa1 = fmaf(xf1[j], c4.x, wa1); wb1 = fmaf(xf1[j], c4.y, wb1);
+          wa0 = fmaf(xf0[j + 1], c4.z, wa0); wb0 = fmaf(xf0[j + 1], c4.w, wb0);
+          wa1 = fmaf(xf1[j + 1], c4.z, wa1); wb1 = fmaf(xf1[j + 1], c4.w, wb1);
+        }
+        top2_packed(wa0, 2u * p, keep, b0, s0);
+        top2_packed(wb0, 2u * p + 1u, keep, b0, s0);
+        top2_packed(wa1, 2u * p, keep, b1, s1);
+        top2_packed(wb1, 2u * p + 1u, keep, b1, s1);
+      }
+    }
+    // ---- certificate, winner's distance ----
+    int lab0, lab1;
+    {
+      const bool ok = row0 + lane < a.n;
+      int bi = (int)(__float_as_uint(b0) & idx_mask);
+      const bool cert = ((s0 - b0) > f6_margin<D>(xx0, cmaxf, idx_span)) && bi < k;
+      double dist = 0.0;
+      if (ok) {
+        if (cert) {
+#pragma unroll
+          for (int j = 0; j < D; ++j) {
+            const double df = cs[bi * D + j] - x0[j];
+            dist = fma(df, df, dist);
+          }
+        } else {
+          my_fallbacks += scan_centroids_certified<double, D>(cs, cn, k, cmax64, x0, dist, bi) ? 0u : 1u;
+        }
+        inert += dist;
+      }
+      lab0 = ok ? bi : -1;
+    }
+    {
+      const bool ok = row0 + 32 + lane < a.n;
+      int bi = (int)(__float_as_uint(b1) & idx_mask);
+      const bool cert = ((s1 - b1) > f6_margin<D>(xx1, cmaxf, idx_span)) && bi < k;
+      double dist = 0.0;
+      if (ok) {
+        if (cert) {
+#pragma unroll
+          for (int j = 0; j < D; ++j) {
+            const double df = cs[bi * D + j] - x1[j];
+            dist = fma(df, df, dist);
+          }
+        } else {
+          my_fallbacks += scan_centroids_certified<double, D>(cs, cn, k, cmax64, x1, dist, bi) ? 0u : 1u;
+        }
+        inert += dist;
+      }
+      lab1 = ok ? bi : -1;
+    }
+    // ---- update walk: lane = (feature f, row group h), rows h, h + H, ... of the tile ----
+    const int lab_u = __shfl_sync(full, cur_lab, 0);
+    if (__all_sync(full, lab0 == lab_u && lab1 == lab_u && cur_lab == lab_u) && lab_u >= 0) {
+      // the whole tile continues the current cluster (the rule for blob-ordered rows): no label exchange, no votes
+      double e0 = 0.0, e1 = 0.0;
+#pragma unroll
+      for (int m = 0; m < STEPS; m += 2) {
+        e0 += *reinterpret_cast<const double*>(sp + row_off<D>(m * H + h) + 8 * f);
+        e1 += *reinterpret_cast<const double*>(sp + row_off<D>((m + 1) * H + h) + 8 * f);
+      }
+      cur_acc += e0 + e1;
+      cur_cnt += (uint32_t)STEPS;
+    } else
+#pragma unroll
+    for (int m = 0; m < STEPS; ++m) {
+      const int row = m * H + h;
+      const int lab = __shfl_sync(full, (m * H >= 32) ? lab1 : lab0, row & 31);
+      const double xv = *reinterpret_cast<const double*>(sp + row_off<D>(row) + 8 * f);
+      const bool chg = lab != cur_lab;
+      const bool fl = chg && cur_lab >= 0;
+      if (__any_sync(full, fl)) flush_acc<D>(fl, cur_lab, cur_acc, cur_cnt, acc, cnt, f, h);
+      if (chg) { cur_lab = lab; cur_acc = 0.0; cur_cnt = 0u; }
+      if (lab >= 0) { cur_acc += xv; cur_cnt += 1u; }
+    }
+    __syncwarp();   // every lane is done with the stage before the next iteration's cp.async overwrites it
+  }
+  cp_async_wait<0>();
+  flush_acc<D>(cur_lab >= 0, cur_lab, cur_acc, cur_cnt, acc, cnt, f, h);
+  if (a.state_rw != nullptr && my_fallbacks) atomicAdd(&a.state_rw->fallback_rows, (unsigned long long)my_fallbacks);
+
+  // ---- per-CTA partials: the warps' copies in warp order ----
+  __syncthreads();
+  const unsigned char* w0base = smem + off;
+  for (int e = t; e < k * D; e += kThreads) {
+    double s = 0.0;
+    for (int w = 0; w < kWarps; ++w) s += reinterpret_cast<const double*>(w0base + (size_t)w * per_warp + (size_t)kStages * SB)[e];
+    a.part_sums[(size_t)blockIdx.x * k * D + e] = s;
+  }
+  for (int e = t; e < k; e += kThreads) {
+    uint32_t s = 0u;
+    for (int w = 0; w < kWarps; ++w)
+      s += reinterpret_cast<const uint32_t*>(w0base + (size_t)w * per_warp + (size_t)kStages * SB + al16((size_t)k * D * 8))[e];
+    a.part_counts[(size_t)blockIdx.x * k + e] = s;
+  }
+  for (int o = 16; o > 0; o >>= 1) inert += __shfl_xor_sync(full, inert, o);
+  __shared__ double red[kWarps];
+  if (lane == 0) red[warp] = inert;
+  __syncthreads();
+  if (t == 0) {
+    double s = 0.0;
+    for (int w = 0; w < kWarps; ++w) s += red[w];
+    a.part_inertia[blockIdx.x] = s;
+  }
+}
+
+}  // namespace f6
+}  // namespace lkm

@@ -225,7 +225,10 @@ __device__ __forceinline__ bool scan_centroids_certified(const F* __restrict__ c
   else { best = b0; bi = i0; second = (b1 < s0) ? b1 : s0; }
   const F eps = sizeof(F) == 4 ? (F)5.9604645e-8 : (F)1.1102230246251565e-16;
   const F xn = sqrt(xx) * (F)1.000001;
-  const F margin = (F)1.1 * eps * ((F)(4 * D + 4) * xn * cmax + (F)4 * cmax * cmax + (F)(2 * (D + 2)) * (xn + cmax) * (xn + cmax));
+  // + an absolute term for scores in the denormal range, where roundings are multiples of the smallest denormal
+  const F dmin = sizeof(F) == 4 ? (F)1.4012985e-45 : (F)4.9406564584124654e-324;
+  const F margin = fma((F)1.1 * eps, (F)(4 * D + 4) * xn * cmax + (F)4 * cmax * cmax + (F)(2 * (D + 2)) * (xn + cmax) * (xn + cmax),
+                       (F)(8 * D + 16) * dmin * ((F)1 + xn + cmax));
   if ((second - best) > margin) {  // NaN anywhere -> not certified
     bidx = bi;
     best_dist = sqdist_reg<F, D>(cs + bi * D, x);

@@ -35,7 +35,8 @@ struct Tc5Args {
   const float* X;
   unsigned long long n;
   int k;                            // all centroids
-  int chunk_idx, n_chunks;          // this launch scores centroids [256 chunk_idx, min(k, 256 (chunk_idx + 1)))
+  int chunk_idx, n_chunks;          // this launch scores centroids [chunk_n chunk_idx, min(k, chunk_n (chunk_idx + 1)))
+  int chunk_n;                      // score columns per launch: 256 (64 for the d = 32, k <= 64 instantiation)
   uint4* merge;                     // n_chunks > 1: per row {best, runner-up, chunk of best, -} carried between the launches
   const float* C;
   const unsigned int* xmax2_bits;   // max_i |x_i|^2 of the resident matrix (row_norm2_max_wide_kernel)
@@ -187,8 +188,8 @@ __device__ __forceinline__ T5Win t5_window(float xmax2, float cmax2_raw, float d
 // squared norms (8 threads per row): their maximum over ALL k centroids (bits) into *cmax_bits — every chunk launch
 // must use the same score window —, the norms of this launch's chunk into nn_s[256]; all threads of the CTA call it
 template <int D>
-__device__ __forceinline__ void t5_centroid_norms(const float* __restrict__ C, int k, int chunk_base, float* nn_s, uint32_t* cmax_bits,
-                                                  int t) {
+__device__ __forceinline__ void t5_centroid_norms(const float* __restrict__ C, int k, int chunk_base, int chunk_n, float* nn_s,
+                                                  uint32_t* cmax_bits, int t) {
   for (int base = 0; base < k * 8; base += (int)blockDim.x) {
     const int item = base + t;
     const int r = item >> 3, c8 = item & 7;
@@ -204,7 +205,7 @@ __device__ __forceinline__ void t5_centroid_norms(const float* __restrict__ C, i
     nn += __shfl_xor_sync(0xffffffffu, nn, 2);
     nn += __shfl_xor_sync(0xffffffffu, nn, 4);
     if (r < k && c8 == 0) {
-      if (r >= chunk_base && r < chunk_base + kT5K) nn_s[r - chunk_base] = nn;   // |nn - |c|^2| <= (d + 1) 2^-24 |c|^2
+      if (r >= chunk_base && r < chunk_base + chunk_n) nn_s[r - chunk_base] = nn;   // |nn - |c|^2| <= (d + 1) 2^-24 |c|^2
       atomicMax(cmax_bits, __float_as_uint(nn));   // a NaN norm wins and voids every certificate
     }
   }
@@ -230,10 +231,11 @@ __device__ __forceinline__ void t5_write_bias(unsigned char* b_bias, unsigned ch
 // 16-lane ALU pipe (two cycles per warp instruction), which this role saturates: the pack is kept an IMAD (FMA
 // pipe) by passing the multiplier (256) as a kernel argument, and the runner-up pass is written as chains of
 // min(m, cb - 1 - q) so that each step is one fused VIADDMNMX.
+template <int N>
 __device__ __forceinline__ void t5_top2(uint32_t taddr, uint32_t mult, uint32_t& m1, uint32_t& m2) {
   m1 = 0u; m2 = 0u;   // real scores are >= 2^e > 0
 #pragma unroll 1
-  for (int c0 = 0; c0 < kT5K; c0 += 32) {
+  for (int c0 = 0; c0 < N; c0 += 32) {
     uint32_t q[32];
     tc::tmem_ld32(taddr + (uint32_t)c0, q);
     tc::tmem_ld_wait();
@@ -339,7 +341,7 @@ __device__ __forceinline__ int t5_merge_certify(const Tc5Args& a, const T5Win& w
   }
   const float v_best = __uint_as_float((m1 >> 8) | win.top_bits);
   const float v_second = __uint_as_float((m2 >> 8) | win.top_bits);
-  label = ch1 * (uint32_t)kT5K + (m1 & 255u);
+  label = ch1 * (uint32_t)a.chunk_n + (m1 & 255u);
   return (win.ok && ((v_best - v_second) > win.m_v) && label < (uint32_t)a.k) ? 1 : 2;
 }
 
@@ -391,7 +393,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kT5Threads, 1)
   }
   for (int e = t; e < 1024 + 64; e += kT5Threads) reinterpret_cast<float4*>(b_bias)[e] = make_float4(0.f, 0.f, 0.f, 0.f);   // bias tile + ones atom
   __syncthreads();
-  t5_centroid_norms<D>(a.C, a.k, chunk_base, nn_s, &cmax_bits, t);
+  t5_centroid_norms<D>(a.C, a.k, chunk_base, kT5K, nn_s, &cmax_bits, t);
   // ---- this CTA's half of the centroids as TF32 hi / lo operand slabs ----
   for (int item = t; item < 128 * NS * 8; item += kT5Threads) {
     const int q = item & 7, s = (item >> 3) % NS, r = item / (8 * NS);
@@ -525,7 +527,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kT5Threads, 1)
       if (wq == 0) T5TRACE(it, 6);
       tc::tc_fence_after();
       uint32_t m1, m2;   // best / runner-up (packed)
-      t5_top2(taddr, a.pack_mult, m1, m2);
+      t5_top2<kT5K>(taddr, a.pack_mult, m1, m2);
       tc::tc_fence_before();
       __syncwarp();
       if (lane == 0) tc::mbar_arrive_cluster(&bar_accfree, 0u);   // the accumulator may be overwritten
@@ -583,10 +585,11 @@ __host__ __device__ inline size_t tc5s_smem_bytes(int d) {
   return (size_t)kT5sStages * 16384 + (size_t)(d / 32) * 16384 + 16384 + 1024 + kT5K * 4 + 4 * 128 * 4 + 1024;
 }
 
-template <int D, bool FUSE>
+template <int D, bool FUSE, int N>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(FUSE ? t5_fuse_threads(D) : kT5Threads, 1)
     assign_tc5s_kernel(const Tc5Args a, const __grid_constant__ CUtensorMap tmap) {
-  static_assert(D == 64 || D == 128, "row width");
+  static_assert(D == 32 || D == 64 || D == 128, "row width");
+  static_assert(N == 64 || N == 128 || N == 256, "score columns per launch (N / 2 centroid rows per CTA)");
   constexpr int NS = D / 32;
   constexpr int NT = FUSE ? t5_fuse_threads(D) : kT5Threads;
   if (a.state != nullptr && a.state->done) return;
@@ -594,8 +597,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(FUSE ? t5_fuse_threa
   unsigned char* smem = smem_unaligned + ((1024u - (tc::smem_u32(smem_unaligned) & 1023u)) & 1023u);
   const int t = threadIdx.x, lane = t & 31;
   const int warp = __shfl_sync(0xffffffffu, t >> 5, 0);
-  const int chunk_base = a.chunk_idx * kT5K;
-  const int k = min(kT5K, a.k - chunk_base);   // centroids of this launch's chunk
+  const int chunk_base = a.chunk_idx * N;
+  const int k = min(N, a.k - chunk_base);   // centroids of this launch's chunk
   const float* Cc = a.C + (size_t)chunk_base * D;
   const uint32_t rank = tc::cluster_ctarank();
   unsigned char* ring = smem;                                    // [kT5sStages][16 KB] raw slabs = A operands
@@ -607,6 +610,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(FUSE ? t5_fuse_threa
   __shared__ __align__(8) uint64_t bar_full[kT5sStages], bar_pfull[kT5sStages], bar_empty[kT5sStages], bar_mma[2], bar_accfree[2];
   __shared__ uint32_t tmem_slot, n_flag[2][2], cmax_bits;
   __shared__ __align__(8) uint64_t bar_verdict[4];   // FUSE: E -> U, one per tile slot (it & 3)
+  __shared__ __align__(8) uint64_t bar_vfree[4];     // FUSE: U -> E, the slot's previous verdict has been consumed
   __shared__ __align__(16) uint32_t warp_verdict[4][4];            // [tile slot][E warp]: common label of the warp's 32 rows, or a marker
   __shared__ double u_red[4];
 
@@ -623,7 +627,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(FUSE ? t5_fuse_threa
       tc::mbar_init(&bar_pfull[s], 1);
       tc::mbar_init(&bar_empty[s], FUSE ? 2 : 1);   // MMA commit (+ the U warp that sums the slab)
     }
-    for (int q = 0; q < 4; ++q) tc::mbar_init(&bar_verdict[q], 4);
+    for (int q = 0; q < 4; ++q) { tc::mbar_init(&bar_verdict[q], 4); tc::mbar_init(&bar_vfree[q], NS); }
     for (int g = 0; g < 2; ++g) {
       tc::mbar_init(&bar_mma[g], 1);
       tc::mbar_init(&bar_accfree[g], 8);
@@ -640,19 +644,19 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(FUSE ? t5_fuse_threa
     for (int e = t; e < a.k; e += NT) a.part_counts[(size_t)blockIdx.x * a.k + e] = 0u;
   }
   __syncthreads();
-  t5_centroid_norms<D>(a.C, a.k, chunk_base, nn_s, &cmax_bits, t);
+  t5_centroid_norms<D>(a.C, a.k, chunk_base, N, nn_s, &cmax_bits, t);
   // this CTA's half of the centroids, raw: kind::tf32 reads them as c_hi
   for (int item = t; item < 128 * NS * 8; item += NT) {
     const int q = item & 7, s = (item >> 3) % NS, r = item / (8 * NS);
-    const int c = (int)rank * 128 + r;
+    const int c = (int)rank * (N / 2) + r;
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (c < k) v = __ldg(reinterpret_cast<const float4*>(Cc + (size_t)c * D + s * 32) + q);
+    if (r < N / 2 && c < k) v = __ldg(reinterpret_cast<const float4*>(Cc + (size_t)c * D + s * 32) + q);
     *reinterpret_cast<float4*>(b_hi + (uint32_t)s * 16384u + tc::sw128_offset((uint32_t)r, (uint32_t)q)) = v;
   }
   __syncthreads();
   // both candidates together: 2 (2^-10 + 2^-10 + 2^-20) = 2^-8 (1 + 2^-11)
   const T5Win win = t5_window<D>(__uint_as_float(__ldg(a.xmax2_bits)), __uint_as_float(cmax_bits), 1.001f * 3.90625e-3f);
-  if (t < 128) t5_write_bias(b_bias, ones, nn_s, win, (int)rank * 128 + t, k, t);
+  if (t < 128) t5_write_bias(b_bias, ones, nn_s, win, (int)rank * (N / 2) + t, (t < N / 2) ? k : 0, t);
   tc::fence_async_smem();
   tc::tc_fence_before();
   __syncthreads();
@@ -698,7 +702,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(FUSE ? t5_fuse_threa
       }
     } else {
       // =============================== M ===============================
-      constexpr uint32_t idesc = tc::idesc_tf32(256, (uint32_t)kT5K);
+      constexpr uint32_t idesc = tc::idesc_tf32(256, (uint32_t)N);
       const uint64_t desc_ring = tc::smem_desc_sw128(tc::smem_u32(ring));
       const uint64_t desc_bhi = tc::smem_desc_sw128(tc::smem_u32(b_hi));
       const uint64_t desc_bias = tc::smem_desc_sw128(tc::smem_u32(b_bias));
@@ -762,6 +766,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(FUSE ? t5_fuse_threa
         // verdict of tile v (slot v & 3), published by the four E warps of group v & 1
         tc::mbar_wait_or_trap(&bar_verdict[v & 3], (uint32_t)(v >> 2) & 1u);
         const uint4 wv = *reinterpret_cast<const uint4*>(warp_verdict[v & 3]);
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(&bar_vfree[v & 3]);
         const int vs = (int)(v & 3);
         const float x0 = vs == 0 ? xa0 : (vs == 1 ? xa1 : (vs == 2 ? xa2 : xa3));
         const float S = vs == 0 ? Sa0 : (vs == 1 ? Sa1 : (vs == 2 ? Sa2 : Sa3));
@@ -836,7 +842,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(FUSE ? t5_fuse_threa
       if (wq == 0) T5TRACE(it, 8);
       tc::tc_fence_after();
       uint32_t m1, m2;
-      t5_top2(taddr, a.pack_mult, m1, m2);
+      t5_top2<N>(taddr, a.pack_mult, m1, m2);
       tc::tc_fence_before();
       __syncwarp();
       if (lane == 0) tc::mbar_arrive_cluster(&bar_accfree[g], 0u);
@@ -853,6 +859,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(FUSE ? t5_fuse_threa
         // one label for the warp's 32 rows (all certified, full tile) -> U adds the tile's column sums to that cluster
         const uint32_t lab0 = __shfl_sync(0xffffffffu, bidx, 0);
         const bool uni = __all_sync(0xffffffffu, verdict == 1 && bidx == lab0) && row0 + 128ull <= a.n;
+        if (it >= 4) tc::mbar_wait_or_trap(&bar_vfree[it & 3], (uint32_t)((it >> 2) - 1) & 1u);   // U is done with the slot
         if (lane == 0) warp_verdict[it & 3][wq] = uni ? lab0 : (row0 < a.n ? 0xFFFFFFFFu : 0xFFFFFFFEu);
         __syncwarp();
         if (lane == 0) tc::mbar_arrive(&bar_verdict[it & 3]);

@@ -710,3 +710,99 @@ def test_pipeline_kernel_full_fit_matches_oracle(lb, oracle):
     assert model.cluster_count().tolist() == ref["cluster_count"].tolist()
     lab, _ = oracle.assign(X, model.centroids())
     assert (model.predict(X) == lab).all()
+
+
+# ---- f32-screened small-d f64 kernel (lkm_f64s.cuh: d in {2, 4, 8, 16}, k <= 64; BASELINE cfg5 shape) ----
+F64S_CASES = [
+    # n, d, k, k_true, spread, shuffle
+    (100000, 8, 16, 16, 30.0, False),    # cfg5 shape, blob order: one flush per blob
+    (100000, 8, 16, 16, 30.0, True),     # every step of the update walk changes cluster
+    (64 * 8 * 296 * 2 + 37, 8, 16, 16, 30.0, True),   # two tiles per warp of a full grid plus a ragged tail
+    (70001, 8, 13, 13, 3.0, True),       # odd k (padded pair), overlapping blobs
+    (50000, 8, 64, 8, 1.0, True),        # k = 64, many near ties -> f64 certified scan / exact re-scan
+    (33000, 2, 3, 3, 10.0, False),       # cfg1-like rows of 16 bytes
+    (40000, 4, 7, 7, 30.0, True),
+    (40000, 16, 32, 32, 30.0, True),
+    (63, 8, 16, 4, 30.0, False),         # a single partial tile (forced path)
+    (1, 8, 1, 1, 30.0, False),           # one row, one centroid
+]
+
+
+@pytest.mark.parametrize("packed", [1, 0])
+@pytest.mark.parametrize("n,d,k,k_true,spread,shuffle", F64S_CASES)
+def test_f64_screened_kernel_matches_oracle(lb, oracle, n, d, k, k_true, spread, shuffle, packed, monkeypatch):
+    dt = np.float64
+    monkeypatch.setenv("LKM_F64S_PACKED", str(packed))
+    ctx = lb.Context(0)
+    X, _ = blobs(n, d, k_true, dt, seed=3 * n + k, spread=spread)
+    g = np.random.default_rng(n + k)
+    if shuffle:
+        X = X[g.permutation(n)].copy()
+    init = X[g.choice(n, size=k, replace=(n < k))].copy() if n >= k else np.repeat(X, k, axis=0)[:k].copy()
+    ctx.set_assign_path(3)
+    ctx.set_data(X)
+    c, counts, inertia, st = ctx.lloyd_iters(init, 4, 0.0)
+    assert st.assign_path == 3 and st.n_iter == 4
+    cur, (lab, dist) = _oracle_iters(oracle, X, init, 4)
+    assert counts.tolist() == np.bincount(lab.astype(np.int64), minlength=k).tolist()
+    np.testing.assert_allclose(c, cur, rtol=1e-10, atol=1e-10 * np.abs(cur).max())
+    np.testing.assert_allclose(inertia, dist.sum(), rtol=1e-10)
+    # the kernel it replaces gives the same labels and (up to summation order) the same sums
+    ctx.set_assign_path(1)
+    c1, counts1, inertia1, st1 = ctx.lloyd_iters(init, 4, 0.0)
+    assert st1.assign_path == 1
+    assert counts1.tolist() == counts.tolist()
+    np.testing.assert_allclose(c, c1, rtol=1e-12, atol=1e-12 * np.abs(c1).max())
+    print(f"re-scanned rows over 4 iterations: {st.fallback_rows} of {4 * n}")
+
+
+def test_f64_screened_kernel_is_default_and_reproducible(lb, oracle):
+    X, _ = blobs(200000, 8, 16, np.float64, seed=5)
+    g = np.random.default_rng(1)
+    init = X[g.choice(len(X), size=16, replace=False)].copy()
+    ctx = lb.Context(0)
+    ctx.set_data(X)
+    a = ctx.lloyd_iters(init, 3, 0.0)
+    b = ctx.lloyd_iters(init, 3, 0.0)
+    assert a[3].assign_path == 3
+    assert (a[0] == b[0]).all() and (a[1] == b[1]).all() and a[2] == b[2]
+
+
+@pytest.mark.parametrize("scale,offset", [(1e-3, 0.0), (1e3, 0.0), (1.0, 5e3), (1e-20, 0.0), (1e-160, 0.0), (1e15, 0.0), (1e100, 0.0), (1.0, 1e9)])
+def test_f64_screened_kernel_magnitudes(lb, oracle, scale, offset):
+    """f32 overflow / underflow / cancellation far from the origin void the certificate; the f64 scan takes over."""
+    X, _ = blobs(40000, 8, 10, np.float64, seed=11, spread=30.0)
+    X = X * scale + offset
+    g = np.random.default_rng(5)
+    X = X[g.permutation(len(X))].copy()
+    init = X[g.choice(len(X), size=10, replace=False)].copy()
+    ctx = lb.Context(0)
+    ctx.set_assign_path(3)
+    ctx.set_data(X)
+    c, counts, inertia, st = ctx.lloyd_iters(init, 2, 0.0)
+    cur, (lab, dist) = _oracle_iters(oracle, X, init, 2)
+    assert counts.tolist() == np.bincount(lab.astype(np.int64), minlength=10).tolist()
+    np.testing.assert_allclose(c, cur, rtol=1e-10, atol=1e-10 * np.abs(cur).max())
+    if np.isfinite(dist.sum()):
+        np.testing.assert_allclose(inertia, dist.sum(), rtol=1e-10)
+
+
+def test_f64_screened_kernel_nan_inf_ties(lb, oracle):
+    X, _ = blobs(40000, 8, 5, np.float64, seed=3)
+    init = X[[0, 9000, 17000, 25000, 33000]].copy()
+    init = np.concatenate([init, init[:2]])          # duplicate centroids: exact ties -> lowest index
+    X[100, 3] = np.inf
+    X[20000, 7] = -np.inf
+    X[30000, 0] = np.nan
+    ctx = lb.Context(0)
+    ctx.set_assign_path(3)
+    ctx.set_data(X)
+    c, counts, inertia, st = ctx.lloyd_iters(init, 1, 0.0)
+    lab, dist = oracle.assign(X, init)
+    assert counts.tolist() == np.bincount(lab.astype(np.int64), minlength=7).tolist()
+    assert counts[5] == 0 and counts[6] == 0
+    assert not np.isfinite(inertia)
+    ctx.set_assign_path(1)
+    c1, counts1, _, _ = ctx.lloyd_iters(init, 1, 0.0)
+    assert counts1.tolist() == counts.tolist()
+    np.testing.assert_array_equal(np.isnan(c), np.isnan(c1))
