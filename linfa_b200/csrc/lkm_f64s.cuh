@@ -97,14 +97,24 @@ __device__ __forceinline__ void top2_packed(float w, uint32_t idx, uint32_t keep
 //   runner-up - best > 1.1 * 2 * { u [ (d+1) C^2 + (2d+4) XC ] + (idx_mask+1) 2^-23 (C^2 + 2XC) + (d+2) 2^-53 (X+C)^2 }
 //                      + (8d+16) 2^-149 (1 + X + C)
 // proves that the reference picks `best`.  NaN / Inf anywhere (x, c, overflow) makes the comparison false.
+// The bound is a quadratic in X; its coefficients are computed once per thread (rounded up by 1.001):
+//   margin(xx) = m0 + m1 sqrt(xx) + m2 xx     with X = 1.0001 sqrt(xx) covering the f32 rounding of xx and the approximate root
+struct Margin { float m0, m1, m2; };
 template <int D>
-__device__ __forceinline__ float f6_margin(float xx, float cmax, float idx_span) {
-  const float X = sqrtf(xx) * 1.0001f;
-  const float u = 5.9604645e-8f;
-  const float c2 = cmax * cmax, xc = X * cmax, xpc = X + cmax;
-  const float rel = u * ((float)(D + 1) * c2 + (float)(2 * D + 4) * xc) + idx_span * 1.1920929e-7f * (c2 + 2.f * xc) +
-                    (float)(D + 2) * 1.1102230e-16f * xpc * xpc;
-  return fmaf(2.2f, rel, (float)(8 * D + 16) * 1.4012985e-45f * (1.f + xpc));
+__device__ __forceinline__ Margin f6_margin_coeffs(float cmax, float idx_span) {
+  const float u = 5.9604645e-8f, pk = idx_span * 1.1920929e-7f, rf = (float)(D + 2) * 1.1102230e-16f;
+  const float ab = (float)(8 * D + 16) * 1.4012985e-45f;
+  const float c2 = cmax * cmax;
+  Margin m;
+  m.m0 = 1.001f * (2.2f * (u * (float)(D + 1) + pk + rf) * c2 + ab * (1.f + cmax));
+  m.m1 = 1.001f * 1.0001f * (2.2f * (u * (float)(2 * D + 4) + 2.f * pk + 2.f * rf) * cmax + ab);
+  m.m2 = 1.001f * 1.0002001f * 2.2f * rf;
+  return m;
+}
+__device__ __forceinline__ float f6_margin(const Margin& m, float xx) {
+  float r;
+  asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(xx));
+  return fmaf(m.m2, xx, fmaf(m.m1, r, m.m0));
 }
 
 // add a lane's running (sum, count) of cluster `lab` to the warp's accumulator copy; all 32 lanes call it.
@@ -163,16 +173,23 @@ __global__ void __launch_bounds__(kThreads, 2) lloyd_f64s_kernel(const Args a) {
   const unsigned long long n_tiles = (a.n + kTileRows - 1) / kTileRows;
   const unsigned long long G = (unsigned long long)gridDim.x * kWarps;
   unsigned long long tile = (unsigned long long)blockIdx.x * kWarps + warp;
+  // one cp.async instruction of the warp covers 32 chunks = 512 contiguous bytes of X = 576 bytes of the padded stage
+  const uint32_t lane_soff = row_off<D>(lane / CPR) + (uint32_t)(lane % CPR) * 16u;
+  const uint32_t stage_s = smem_u32(stage0);
+  const unsigned char* xbytes = reinterpret_cast<const unsigned char*>(a.X);
   auto issue = [&](unsigned long long tl, int st) {
     const unsigned long long row0 = tl * kTileRows;
-    const uint32_t sbase = smem_u32(stage0 + (size_t)st * SB);
+    const uint32_t dst = stage_s + (uint32_t)st * (uint32_t)SB + lane_soff;
+    const unsigned char* src = xbytes + row0 * (unsigned long long)(D * 8) + (unsigned)lane * 16u;
+    if (row0 + kTileRows <= a.n) {
 #pragma unroll
-    for (int q = 0; q < kTileRows * CPR / 32; ++q) {
-      const int g = q * 32 + lane;
-      const int row = g / CPR, c = g % CPR;
-      const bool ok = row0 + row < a.n;
-      const double* src = ok ? a.X + (row0 + row) * D + c * 2 : a.X;
-      cp_async16(sbase + row_off<D>(row) + c * 16, src, ok ? 16 : 0);
+      for (int q = 0; q < kTileRows * CPR / 32; ++q) cp_async16(dst + q * 576, src + q * 512, 16);
+    } else {   // ragged last tile: rows beyond n are zero-filled (and ignored through their label -1)
+#pragma unroll
+      for (int q = 0; q < kTileRows * CPR / 32; ++q) {
+        const bool ok = row0 + (unsigned)(q * (32 / CPR) + lane / CPR) < a.n;
+        cp_async16(dst + q * 576, ok ? src + q * 512 : xbytes, ok ? 16 : 0);
+      }
     }
   };
   if (tile < n_tiles) issue(tile, 0);
@@ -209,7 +226,7 @@ __global__ void __launch_bounds__(kThreads, 2) lloyd_f64s_kernel(const Args a) {
   int idx_bits = 1;
   while ((1 << idx_bits) < kp) ++idx_bits;
   const uint32_t idx_mask = (1u << idx_bits) - 1u, keep = ~idx_mask;
-  const float idx_span = (float)(idx_mask + 1u);
+  const Margin mg = f6_margin_coeffs<D>(cmaxf, (float)(idx_mask + 1u));
 
   const int f = lane % D, h = lane / D;
   int cur_lab = -1;
@@ -293,7 +310,7 @@ __global__ void __launch_bounds__(kThreads, 2) lloyd_f64s_kernel(const Args a) {
     {
       const bool ok = row0 + lane < a.n;
       int bi = (int)(__float_as_uint(b0) & idx_mask);
-      const bool cert = ((s0 - b0) > f6_margin<D>(xx0, cmaxf, idx_span)) && bi < k;
+      const bool cert = ((s0 - b0) > f6_margin(mg, xx0)) && bi < k;
       double dist = 0.0;
       if (ok) {
         if (cert) {
@@ -312,7 +329,7 @@ __global__ void __launch_bounds__(kThreads, 2) lloyd_f64s_kernel(const Args a) {
     {
       const bool ok = row0 + 32 + lane < a.n;
       int bi = (int)(__float_as_uint(b1) & idx_mask);
-      const bool cert = ((s1 - b1) > f6_margin<D>(xx1, cmaxf, idx_span)) && bi < k;
+      const bool cert = ((s1 - b1) > f6_margin(mg, xx1)) && bi < k;
       double dist = 0.0;
       if (ok) {
         if (cert) {
