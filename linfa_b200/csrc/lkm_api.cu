@@ -785,7 +785,7 @@ static lkm_status run_lloyd(lkm_ctx* ctx, F* dC2, uint64_t k, uint64_t max_iter,
           ta.part_inertia = ctx->part_inertia.as<double>(); ta.state = dstate; ta.accumulate = 1;
           if (tc_threads == kT4Threads) {
             Tc4Args t4{};
-            t4.X = dX; t4.n = n; t4.k = (int)k; t4.stages = tc4_nstages; t4.C = Ccur; t4.xmax2_bits = ctx->xmax2.as<unsigned int>();
+            t4.X = dX; t4.n = n; t4.k = (int)k; t4.pack_mult = 64u; t4.stages = tc4_nstages; t4.C = Ccur; t4.xmax2_bits = ctx->xmax2.as<unsigned int>();
 #if defined(LKM_T4_PROF) || defined(LKM_T4_TRACE)
             CK(ctx->t4prof.ensure((64 + 40 * 16) * 8));
             t4.prof = ctx->t4prof.as<long long>();

@@ -66,6 +66,7 @@ struct Tc4Args {
   double* part_inertia;
   LloydState* state;
   long long* prof;   // LKM_T4_PROF builds only
+  uint32_t pack_mult;   // 64, passed as an argument so that the score pack of the E role stays an IMAD (FMA pipe)
 };
 
 // Optional phase profile (compile with -DLKM_T4_PROF): cycles spent in each wait of each role, written
@@ -512,18 +513,21 @@ __global__ void __launch_bounds__(kT4Threads, 1) lloyd_tc4_kernel(const Tc4Args 
           tc::tmem_ld32(taddr + 32u, r1);
           tc::tmem_ld_wait();
 #pragma unroll
-          for (int c = 0; c < 32; ++c) q[32 + c] = (r1[c] << 6) | (uint32_t)(32 + c);
+          for (int c = 0; c < 32; ++c) q[32 + c] = r1[c] * a.pack_mult + (uint32_t)(32 + c);
         } else {
           tc::tmem_ld_wait();
         }
 #pragma unroll
-        for (int c = 0; c < 32; ++c) q[c] = (r0[c] << 6) | (uint32_t)c;
+        for (int c = 0; c < 32; ++c) q[c] = r0[c] * a.pack_mult + (uint32_t)c;
       }
       T4MARK(te0);
       T4ADD(3, te_a, te0);
       tc::tc_fence_before();
       tc::nb_arrive(kNbTfree + g, 160);        // the accumulator may be overwritten by tile j + 2
       if (wq == 0) T4TRACE(j, 6);
+      // integer min / max / add share the 16-lane ALU pipe (two cycles per warp instruction), the busiest unit of this
+      // loop: the pack above is an IMAD (FMA pipe) and the runner-up pass is chains of min(m, best - 1 - q), one fused
+      // VIADDMNMX per score (the best itself wraps to 0xFFFFFFFF, the others become gap - 1)
       uint32_t m0 = q[0], m1 = q[1], m2 = q[2], m3 = q[3];
 #pragma unroll
       for (int c = 4; c + 7 < KP; c += 8) {
@@ -536,19 +540,15 @@ __global__ void __launch_bounds__(kT4Threads, 1) lloyd_tc4_kernel(const Tc4Args 
       m1 = __vimax3_u32(m1, q[KP - 2], q[KP - 1]);
       const uint32_t bestq = max(__vimax3_u32(m0, m1, m2), m3);
       const uint32_t bm1 = bestq - 1u;
+      m0 = 0xFFFFFFFFu; m1 = 0xFFFFFFFFu; m2 = 0xFFFFFFFFu; m3 = 0xFFFFFFFFu;
 #pragma unroll
-      for (int c = 0; c < KP; ++c) q[c] = bm1 - q[c];   // the best wraps to 0xFFFFFFFF, the others are gap - 1
-      m0 = q[0]; m1 = q[1]; m2 = q[2]; m3 = q[3];
-#pragma unroll
-      for (int c = 4; c + 7 < KP; c += 8) {
-        m0 = __vimin3_u32(m0, q[c], q[c + 1]);
-        m1 = __vimin3_u32(m1, q[c + 2], q[c + 3]);
-        m2 = __vimin3_u32(m2, q[c + 4], q[c + 5]);
-        m3 = __vimin3_u32(m3, q[c + 6], q[c + 7]);
+      for (int c = 0; c < KP; c += 4) {
+        m0 = min(m0, bm1 - q[c]);
+        m1 = min(m1, bm1 - q[c + 1]);
+        m2 = min(m2, bm1 - q[c + 2]);
+        m3 = min(m3, bm1 - q[c + 3]);
       }
-      m0 = __vimin3_u32(m0, q[KP - 4], q[KP - 3]);
-      m1 = __vimin3_u32(m1, q[KP - 2], q[KP - 1]);
-      const uint32_t tmin = min(__vimin3_u32(m0, m1, m2), m3);
+      const uint32_t tmin = min(min(m0, m1), min(m2, m3));
       const uint32_t secondq = bm1 - tmin;
       const float v_best = __uint_as_float((bestq >> 6) | top_bits);
       const float v_second = __uint_as_float((secondq >> 6) | top_bits);
