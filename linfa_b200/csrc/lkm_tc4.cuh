@@ -36,10 +36,10 @@ constexpr unsigned long long kT4Prefetch = LKM_T4_PREFETCH;   // L2 prefetch dis
 constexpr int kNbLab = 2, kNbLfree = 4, kNbAlo = 6, kNbTfree = 8;   // named barrier ids (+ parity); 1 = U-internal
 constexpr int kT4Subsets = 8;      // U role: thread = (row subset of 8, feature pair)
 
-__host__ __device__ inline size_t tc4_smem_bytes(int k, int kp, int stages) {
+__host__ __device__ inline size_t tc4_smem_bytes(int k, int kp, int stages, int passes = 3) {
   size_t b = 0;
   b += (size_t)stages * 16384;                   // raw tiles (TMA destinations)
-  b += (size_t)kp * 128 * 3;                     // B_hi, B_lo, B_bias
+  b += (size_t)kp * 128 * (passes == 1 ? 2 : 3); // B_hi, B_lo (not in the one-product variant: one more ring stage), B_bias
   b += (size_t)k * kTcCStride * 4;               // raw centroids
   b += (size_t)kT4Subsets * (k + 1) * 32 * 4;    // sums
   b += (((size_t)k * 4) + 15) & ~(size_t)15;     // counts
@@ -48,9 +48,9 @@ __host__ __device__ inline size_t tc4_smem_bytes(int k, int kp, int stages) {
   b += (size_t)2 * 16;                           // per label slot: warp-uniform labels
   return b + 1024;
 }
-__host__ __device__ inline int tc4_stages(int k, int kp, size_t smem_limit) {
+__host__ __device__ inline int tc4_stages(int k, int kp, size_t smem_limit, int passes = 3) {
   int s = kT4MaxStages;
-  while (s > 3 && tc4_smem_bytes(k, kp, s) > smem_limit) --s;
+  while (s > 3 && tc4_smem_bytes(k, kp, s, passes) > smem_limit) --s;
   return s;
 }
 
@@ -225,7 +225,9 @@ __global__ void __launch_bounds__(kT4Threads, 1) lloyd_tc4_kernel(const Tc4Args 
   static_assert(KP == 32 || KP == 64, "score columns");
 #ifdef LKM_T4_TRACE
   const long long k_t0 = clock64();
-#define T4K(ev) do { if (blockIdx.x == 0 && threadIdx.x == 0 && a.prof) a.prof[ev] = clock64() - k_t0; } while (0)
+#define T4K(ev) do { if (threadIdx.x == 0 && a.prof) { if (blockIdx.x == 0) a.prof[ev] = clock64() - k_t0; \
+    if ((ev) == 0 || (ev) == 4 || (ev) == 6 || (ev) == 8) { long long gt__; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt__)); \
+      a.prof[64 + 40 * 16 + blockIdx.x * 4 + ((ev) == 0 ? 0 : (ev) == 4 ? 1 : (ev) == 6 ? 2 : 3)] = gt__; } } } while (0)
 #else
 #define T4K(ev)
 #endif
@@ -238,7 +240,7 @@ __global__ void __launch_bounds__(kT4Threads, 1) lloyd_tc4_kernel(const Tc4Args 
   const int R = a.stages;
   unsigned char* raw = smem;                                   // [R][16 KB]
   unsigned char* b_hi = raw + (size_t)R * 16384;
-  unsigned char* b_lo = b_hi + KP * 128;
+  unsigned char* b_lo = b_hi + (PASSES == 1 ? 0 : KP * 128);   // the one-product variant has no B_lo tile
   unsigned char* b_bias = b_lo + KP * 128;
   float* rawc = reinterpret_cast<float*>(b_bias + KP * 128);
   float* acc = rawc + (size_t)k * kTcCStride;
@@ -308,7 +310,7 @@ __global__ void __launch_bounds__(kT4Threads, 1) lloyd_tc4_kernel(const Tc4Args 
     tc::split_tf32(v.z, h.z, l.z); tc::split_tf32(v.w, h.w, l.w);
     const uint32_t o = tc::sw128_offset(r, c);
     *reinterpret_cast<float4*>(b_hi + o) = h;
-    *reinterpret_cast<float4*>(b_lo + o) = l;
+    if constexpr (PASSES != 1) *reinterpret_cast<float4*>(b_lo + o) = l;
     if (r < k) *reinterpret_cast<float4*>(rawc + r * kTcCStride + 4 * c) = v;
     float nn = fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, v.w * v.w)));
     nn += __shfl_xor_sync(0xffffffffu, nn, 1);
