@@ -371,7 +371,7 @@ def main():
             "config": {"workload": WORKLOAD_TEXT[args.workload], "rows_per_gpu": n, "d": d, "k": k,
                        "init": "blob centres + N(0,0.5) (Precomputed); k-means++ timed separately",
                        "kmeanspp_fast_init_ms": init_ms,
-                       "l2": ("512 MiB scratch overwritten between steps, outside the timed spans" if flush_bytes
+                       "l2": ("512 MiB scratch overwritten between steps, then a 256 MiB read-only sweep so that no dirty lines remain; both outside the timed spans" if flush_bytes
                               else "no flush (L2 warm)"),
                        "l2_warm_ms_per_step": warm_ms / args.steps,
                        "wall_ms_per_step_incl_flush": wall_ms / args.steps,
