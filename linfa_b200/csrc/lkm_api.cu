@@ -112,6 +112,7 @@ struct lkm_ctx {
   int tc4_passes_forced = 0;              // LKM_TC4_PASSES = 2 / 3 pins the scoring passes of the pipeline kernel
   uint64_t tc4_hard_epoch = 0, tc4_easy_epoch = 0;   // data versions seen to need 3 passes / to be fine with 2
   uint64_t flush_bytes = 0;
+  unsigned long long bar_epoch = 0;   // rank_barrier_kernel (flushed-L2 benchmark mode, multi-GPU)
   int kernel_timing = 0;
   DevBuf flushbuf;
   std::vector<cudaEvent_t> iter_events;
@@ -176,6 +177,26 @@ __global__ void __launch_bounds__(512) l2_read_sweep_kernel(const uint4* __restr
     acc ^= v.x ^ v.w;
   }
   if (acc == 0x9e3779b9u) *sink = acc;   // never true for a memset pattern; keeps the loads alive
+}
+
+// Benchmark hygiene, multi-GPU: the per-step spans of the flushed-L2 mode start behind each rank's own scratch writes, so
+// without a rendezvous the skew between the ranks' flushes is charged to the exchange step of every span.  One warp:
+// lane r raises this rank's slot in rank r's barrier flags (NVLink peer store) and waits for rank r's slot in its own.
+struct RankBarArgs {
+  unsigned long long* peer[8];          // rank r's barrier flags + my rank
+  const unsigned long long* mine;       // my barrier flags [world]
+  unsigned long long epoch;
+  int world;
+};
+__global__ void rank_barrier_kernel(const RankBarArgs a) {
+  const int r = threadIdx.x;
+  if (r < a.world) {
+    __threadfence_system();
+    *((volatile unsigned long long*)a.peer[r]) = a.epoch;
+    const volatile unsigned long long* f = a.mine + r;
+    unsigned int spins = 0;
+    while (*f < a.epoch && ++spins < (1u << 24)) {}
+  }
 }
 
 // ---- launch helpers ----------------------------------------------------------
@@ -347,7 +368,7 @@ static lkm_status p2p_setup(lkm_ctx* ctx, size_t L) {
   ctx->p2p_peer.clear();
   if (ctx->p2p_local) { cudaFree(ctx->p2p_local); ctx->p2p_local = nullptr; }
   const size_t cap = std::max<size_t>(L, 4096);
-  const size_t bytes = (2 * (size_t)world * cap + 2 * (size_t)world) * 8;
+  const size_t bytes = (2 * (size_t)world * cap + 3 * (size_t)world) * 8;   // partials | exchange flags | barrier flags
   int ok = 1;
   cudaIpcMemHandle_t mine;
   std::memset(&mine, 0, sizeof(mine));
@@ -799,6 +820,16 @@ static lkm_status run_lloyd(lkm_ctx* ctx, F* dC2, uint64_t k, uint64_t max_iter,
           l2_read_sweep_kernel<<<ctx->sm_count * 4, 512, 0, ctx->stream>>>(reinterpret_cast<const uint4*>(ctx->flushbuf.p),
                                                                             (size_t)(ctx->flush_bytes / 2 / 16),
                                                                             reinterpret_cast<unsigned int*>(ctx->flushbuf.p));
+          CK(cudaGetLastError());
+        }
+        if (use_p2p) {   // rendezvous of the ranks behind their flushes (see rank_barrier_kernel)
+          RankBarArgs rb{};
+          const size_t cap = ctx->p2p_cap, w = (size_t)ctx->world;
+          rb.world = ctx->world; rb.epoch = ++ctx->bar_epoch;
+          for (int pr = 0; pr < ctx->world; ++pr)
+            rb.peer[pr] = reinterpret_cast<unsigned long long*>(reinterpret_cast<double*>(ctx->p2p_peer[pr]) + 2 * w * cap) + 2 * w + (size_t)ctx->rank;
+          rb.mine = reinterpret_cast<const unsigned long long*>(reinterpret_cast<double*>(ctx->p2p_local) + 2 * w * cap) + 2 * w;
+          rank_barrier_kernel<<<1, 32, 0, ctx->stream>>>(rb);
           CK(cudaGetLastError());
         }
         CK(cudaEventRecord(ctx->iter_events[3 * it], ctx->stream));
