@@ -33,6 +33,10 @@ constexpr int kWarps = 8;
 constexpr int kThreads = kWarps * 32;
 constexpr int kTileRows = 64;   // per warp and step: two rows per lane
 constexpr int kStages = 2;
+#ifndef LKM_F6_RELOAD
+#define LKM_F6_RELOAD 0
+#endif
+constexpr bool kReloadRows = LKM_F6_RELOAD != 0;   // read the f64 rows again for the distance instead of holding them in registers
 
 struct Args {
   const double* X;
@@ -305,45 +309,41 @@ __global__ void __launch_bounds__(kThreads, 2) lloyd_f64s_kernel(const Args a) {
         top2_packed(wb1, 2u * p + 1u, keep, b1, s1);
       }
     }
-    // ---- certificate, winner's distance ----
+    // ---- certificate, winner's distance (the f64 rows are read again from the stage: holding them across the scoring
+    //      loop costs 32 registers) ----
+    if constexpr (kReloadRows) asm volatile("" ::: "memory");
     int lab0, lab1;
-    {
-      const bool ok = row0 + lane < a.n;
-      int bi = (int)(__float_as_uint(b0) & idx_mask);
-      const bool cert = ((s0 - b0) > f6_margin(mg, xx0)) && bi < k;
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      const bool ok = row0 + (unsigned)(half * 32 + lane) < a.n;
+      const float bq = half ? b1 : b0, sq = half ? s1 : s0, xxh = half ? xx1 : xx0;
+      int bi = (int)(__float_as_uint(bq) & idx_mask);
+      const bool cert = ((sq - bq) > f6_margin(mg, xxh)) && bi < k;
       double dist = 0.0;
       if (ok) {
+        double x[D];
+        if constexpr (kReloadRows) {
+#pragma unroll
+          for (int c = 0; c < CPR; ++c) {
+            const double2 v = *reinterpret_cast<const double2*>(sp + row_off<D>(lane + half * 32) + c * 16);
+            x[2 * c] = v.x; x[2 * c + 1] = v.y;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < D; ++j) x[j] = half ? x1[j] : x0[j];
+        }
         if (cert) {
 #pragma unroll
           for (int j = 0; j < D; ++j) {
-            const double df = cs[bi * D + j] - x0[j];
+            const double df = cs[bi * D + j] - x[j];
             dist = fma(df, df, dist);
           }
         } else {
-          my_fallbacks += scan_centroids_certified<double, D>(cs, cn, k, cmax64, x0, dist, bi) ? 0u : 1u;
+          my_fallbacks += scan_centroids_certified<double, D>(cs, cn, k, cmax64, x, dist, bi) ? 0u : 1u;
         }
         inert += dist;
       }
-      lab0 = ok ? bi : -1;
-    }
-    {
-      const bool ok = row0 + 32 + lane < a.n;
-      int bi = (int)(__float_as_uint(b1) & idx_mask);
-      const bool cert = ((s1 - b1) > f6_margin(mg, xx1)) && bi < k;
-      double dist = 0.0;
-      if (ok) {
-        if (cert) {
-#pragma unroll
-          for (int j = 0; j < D; ++j) {
-            const double df = cs[bi * D + j] - x1[j];
-            dist = fma(df, df, dist);
-          }
-        } else {
-          my_fallbacks += scan_centroids_certified<double, D>(cs, cn, k, cmax64, x1, dist, bi) ? 0u : 1u;
-        }
-        inert += dist;
-      }
-      lab1 = ok ? bi : -1;
+      if (half) lab1 = ok ? bi : -1; else lab0 = ok ? bi : -1;
     }
     // ---- update walk: lane = (feature f, row group h), rows h, h + H, ... of the tile ----
     const int lab_u = __shfl_sync(full, cur_lab, 0);
