@@ -62,7 +62,7 @@ __host__ __device__ inline size_t al16(size_t x) { return (x + 15) & ~(size_t)15
 template <int D> __host__ __device__ inline size_t smem_bytes(int k) {
   const int kp = (k + 1) & ~1;
   return al16((size_t)k * D * 8) + al16((size_t)(k + 1) * 8) + al16((size_t)kp * D * 4) + al16((size_t)kp * 4) + 16 +
-         (size_t)kWarps * (kStages * stage_bytes<D>() + al16((size_t)k * D * 8) + al16((size_t)k * 4));
+         (size_t)kWarps * (kStages * stage_bytes<D>() + al16((size_t)(32 / D) * k * D * 8) + al16((size_t)(32 / D) * k * 4));
 }
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -121,34 +121,6 @@ __device__ __forceinline__ float f6_margin(const Margin& m, float xx) {
   return fmaf(m.m2, xx, fmaf(m.m1, r, m.m0));
 }
 
-// add a lane's running (sum, count) of cluster `lab` to the warp's accumulator copy; all 32 lanes call it.
-// Lanes of one row group (same h) hold the same label and different features; two row groups flushing the same
-// cluster in the same step are serialised.
-template <int D>
-__device__ __forceinline__ void flush_acc(bool fl, int lab, double sum, uint32_t count, double* __restrict__ acc,
-                                          uint32_t* __restrict__ cnt, int f, int h) {
-  constexpr int H = 32 / D;
-  const unsigned full = 0xffffffffu;
-  const int key = fl ? lab : -1 - h;
-  const unsigned same = __match_any_sync(full, key);
-  const bool conflict = fl && __popc(same) > D;
-  if (!__any_sync(full, conflict)) {
-    if (fl) {
-      acc[lab * D + f] += sum;
-      if (f == 0) cnt[lab] += count;
-    }
-  } else {
-    for (int hh = 0; hh < H; ++hh) {
-      if (fl && h == hh) {
-        acc[lab * D + f] += sum;
-        if (f == 0) cnt[lab] += count;
-      }
-      __syncwarp();
-    }
-  }
-  __syncwarp();
-}
-
 template <int D, bool PACKED>
 __global__ void __launch_bounds__(kThreads, 2) lloyd_f64s_kernel(const Args a) {
   static_assert(D == 2 || D == 4 || D == 8 || D == 16, "row width");
@@ -167,11 +139,12 @@ __global__ void __launch_bounds__(kThreads, 2) lloyd_f64s_kernel(const Args a) {
   float* cfp = reinterpret_cast<float*>(smem + off); off += al16((size_t)kp * D * 4);   // [pair][feature][2] = -2c
   float* cnp = reinterpret_cast<float*>(smem + off); off += al16((size_t)kp * 4);       // [pair][2] = |c|^2
   float* cmaxf_s = reinterpret_cast<float*>(smem + off); off += 16;
-  const size_t per_warp = (size_t)kStages * SB + al16((size_t)k * D * 8) + al16((size_t)k * 4);
+  const size_t acc_bytes = al16((size_t)H * k * D * 8);   // one accumulator copy per row group of the warp
+  const size_t per_warp = (size_t)kStages * SB + acc_bytes + al16((size_t)H * k * 4);
   unsigned char* wbase = smem + off + (size_t)warp * per_warp;
   unsigned char* stage0 = wbase;
   double* acc = reinterpret_cast<double*>(wbase + (size_t)kStages * SB);
-  uint32_t* cnt = reinterpret_cast<uint32_t*>(wbase + (size_t)kStages * SB + al16((size_t)k * D * 8));
+  uint32_t* cnt = reinterpret_cast<uint32_t*>(wbase + (size_t)kStages * SB + acc_bytes);
 
   // ---- tile schedule and the first load (before the prologue, so that it overlaps it) ----
   const unsigned long long n_tiles = (a.n + kTileRows - 1) / kTileRows;
@@ -201,8 +174,8 @@ __global__ void __launch_bounds__(kThreads, 2) lloyd_f64s_kernel(const Args a) {
 
   // ---- prologue: centroids in f64 (exact paths) and as f32 pair operands (screening) ----
   for (int e = t; e < k * D; e += kThreads) cs[e] = a.C[e];
-  for (int e = lane; e < k * D; e += 32) acc[e] = 0.0;
-  for (int e = lane; e < k; e += 32) cnt[e] = 0u;
+  for (int e = lane; e < H * k * D; e += 32) acc[e] = 0.0;
+  for (int e = lane; e < H * k; e += 32) cnt[e] = 0u;
   __syncthreads();
   for (int c = t; c < kp; c += kThreads) {
     double nn = 0.0;
@@ -233,6 +206,8 @@ __global__ void __launch_bounds__(kThreads, 2) lloyd_f64s_kernel(const Args a) {
   const Margin mg = f6_margin_coeffs<D>(cmaxf, (float)(idx_mask + 1u));
 
   const int f = lane % D, h = lane / D;
+  double* acc_h = acc + (size_t)h * k * D;
+  uint32_t* cnt_h = cnt + (size_t)h * k;
   int cur_lab = -1;
   double cur_acc = 0.0;
   uint32_t cur_cnt = 0u;
@@ -346,9 +321,16 @@ __global__ void __launch_bounds__(kThreads, 2) lloyd_f64s_kernel(const Args a) {
       if (half) lab1 = ok ? bi : -1; else lab0 = ok ? bi : -1;
     }
     // ---- update walk: lane = (feature f, row group h), rows h, h + H, ... of the tile ----
-    const int lab_u = __shfl_sync(full, cur_lab, 0);
-    if (__all_sync(full, lab0 == lab_u && lab1 == lab_u && cur_lab == lab_u) && lab_u >= 0) {
-      // the whole tile continues the current cluster (the rule for blob-ordered rows): no label exchange, no votes
+    const int lab_t = __shfl_sync(full, lab0, 0);
+    if (__all_sync(full, lab0 == lab_t && lab1 == lab_t) && lab_t >= 0) {
+      // one cluster for the whole tile (the rule for blob-ordered rows): sums stay in registers; cur_lab is warp-uniform
+      if (lab_t != cur_lab) {
+        if (cur_lab >= 0) {
+          acc_h[cur_lab * D + f] += cur_acc;
+          if (f == 0) cnt_h[cur_lab] += cur_cnt;
+        }
+        cur_lab = lab_t; cur_acc = 0.0; cur_cnt = 0u;
+      }
       double e0 = 0.0, e1 = 0.0;
 #pragma unroll
       for (int m = 0; m < STEPS; m += 2) {
@@ -357,22 +339,31 @@ __global__ void __launch_bounds__(kThreads, 2) lloyd_f64s_kernel(const Args a) {
       }
       cur_acc += e0 + e1;
       cur_cnt += (uint32_t)STEPS;
-    } else
+    } else {
+      // mixed tile: every row goes straight to this row group's private accumulator copy (no conflicts, no votes)
+      if (cur_lab >= 0) {
+        acc_h[cur_lab * D + f] += cur_acc;
+        if (f == 0) cnt_h[cur_lab] += cur_cnt;
+        cur_lab = -1; cur_acc = 0.0; cur_cnt = 0u;
+      }
 #pragma unroll
-    for (int m = 0; m < STEPS; ++m) {
-      const int row = m * H + h;
-      const int lab = __shfl_sync(full, (m * H >= 32) ? lab1 : lab0, row & 31);
-      const double xv = *reinterpret_cast<const double*>(sp + row_off<D>(row) + 8 * f);
-      const bool chg = lab != cur_lab;
-      const bool fl = chg && cur_lab >= 0;
-      if (__any_sync(full, fl)) flush_acc<D>(fl, cur_lab, cur_acc, cur_cnt, acc, cnt, f, h);
-      if (chg) { cur_lab = lab; cur_acc = 0.0; cur_cnt = 0u; }
-      if (lab >= 0) { cur_acc += xv; cur_cnt += 1u; }
+      for (int m = 0; m < STEPS; ++m) {
+        const int row = m * H + h;
+        const int lab = __shfl_sync(full, (m * H >= 32) ? lab1 : lab0, row & 31);
+        const double xv = *reinterpret_cast<const double*>(sp + row_off<D>(row) + 8 * f);
+        if (lab >= 0) {
+          acc_h[lab * D + f] += xv;
+          if (f == 0) cnt_h[lab] += 1u;
+        }
+      }
     }
     __syncwarp();   // every lane is done with the stage before the next iteration's cp.async overwrites it
   }
   cp_async_wait<0>();
-  flush_acc<D>(cur_lab >= 0, cur_lab, cur_acc, cur_cnt, acc, cnt, f, h);
+  if (cur_lab >= 0) {
+    acc_h[cur_lab * D + f] += cur_acc;
+    if (f == 0) cnt_h[cur_lab] += cur_cnt;
+  }
   if (a.state_rw != nullptr && my_fallbacks) atomicAdd(&a.state_rw->fallback_rows, (unsigned long long)my_fallbacks);
 
   // ---- per-CTA partials: the warps' copies in warp order ----
@@ -380,13 +371,18 @@ __global__ void __launch_bounds__(kThreads, 2) lloyd_f64s_kernel(const Args a) {
   const unsigned char* w0base = smem + off;
   for (int e = t; e < k * D; e += kThreads) {
     double s = 0.0;
-    for (int w = 0; w < kWarps; ++w) s += reinterpret_cast<const double*>(w0base + (size_t)w * per_warp + (size_t)kStages * SB)[e];
+    for (int w = 0; w < kWarps; ++w) {
+      const double* aw = reinterpret_cast<const double*>(w0base + (size_t)w * per_warp + (size_t)kStages * SB);
+      for (int g = 0; g < H; ++g) s += aw[(size_t)g * k * D + e];
+    }
     a.part_sums[(size_t)blockIdx.x * k * D + e] = s;
   }
   for (int e = t; e < k; e += kThreads) {
     uint32_t s = 0u;
-    for (int w = 0; w < kWarps; ++w)
-      s += reinterpret_cast<const uint32_t*>(w0base + (size_t)w * per_warp + (size_t)kStages * SB + al16((size_t)k * D * 8))[e];
+    for (int w = 0; w < kWarps; ++w) {
+      const uint32_t* cw = reinterpret_cast<const uint32_t*>(w0base + (size_t)w * per_warp + (size_t)kStages * SB + acc_bytes);
+      for (int g = 0; g < H; ++g) s += cw[g * k + e];
+    }
     a.part_counts[(size_t)blockIdx.x * k + e] = s;
   }
   for (int o = 16; o > 0; o >>= 1) inert += __shfl_xor_sync(full, inert, o);

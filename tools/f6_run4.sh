@@ -1,0 +1,3 @@
+python -m pytest tests/test_gpu_parity.py -x -q -k "f64_screened" 2>&1 | tail -4
+python tools/shuffled_timing_f64.py 2>&1 | tail -4
+python bench.py --workload cfg5 --steps 5 --warmup 3 --no-cpu-baseline --no-e2e --no-init 2>/dev/null | tail -1 | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('cfg5', round(d['ms_per_step'],4), round(d['roofline']['mean_launch_us'],1), d['roofline']['frac'], d['clocks']['sm_mhz'])"
