@@ -101,6 +101,7 @@ struct lkm_ctx {
   int tc_variant = 4;
   int tc5_passes_forced = 0;            // LKM_TC5_PASSES = 1 / 3 pins the screening / 3xTF32 variant of the pair kernel
   uint64_t tc5_hard_epoch = 0, tc5_easy_epoch = 0;
+  int fused_finalize = 0;   // LKM_FUSED_FINALIZE=1: finalize folded into the pipeline kernel's tail (measured: no gain, 47.1 vs 46.3 us per cfg2 step)
   int f64s_enabled = 1;  // LKM_F64S=0: lloyd_kernel<double> instead of the f32-screened small-d f64 kernel (lkm_f64s.cuh)
   int f64s_packed = 1;   // LKM_F64S_PACKED=0: scalar FFMA instead of FFMA2 in that kernel
   int pair32 = 0;        // LKM_PAIR32=1: d = 32, k <= 64 through the CTA-pair screening kernel instead of the pipeline kernel
@@ -114,7 +115,7 @@ struct lkm_ctx {
   uint64_t flush_bytes = 0;
   unsigned long long bar_epoch = 0;   // rank_barrier_kernel (flushed-L2 benchmark mode, multi-GPU)
   int kernel_timing = 0;
-  DevBuf flushbuf;
+  DevBuf flushbuf, fin_sync;
   std::vector<cudaEvent_t> iter_events;
   // workspaces
   DevBuf tca_bsplit, tca_cn, tca_cmax;
@@ -473,17 +474,28 @@ static cudaError_t launch_tc3(int kp, int grid, size_t smem, cudaStream_t s, con
   return cudaLaunchKernelEx(&cfg, lloyd_tc3_kernel<64>, arg, map);
 }
 
+static int g_coop = 1;   // LKM_COOP=0: the in-kernel finalize relies on grid <= SM count alone (no cooperative-launch attribute)
 static cudaError_t launch_tc4(int kp, int passes, int grid, size_t smem, cudaStream_t s, const Tc4Args& arg, const CUtensorMap& map) {
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)grid);
   cfg.blockDim = dim3((unsigned)kT4Threads);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = s;
-  cudaLaunchAttribute at[1];
-  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cudaLaunchAttribute at[2];
+  int na = 0;
+  if (arg.fin_sync != nullptr && g_coop) {
+    // the kernel's tail waits for every CTA of the grid: a cooperative launch guarantees that they are co-resident even
+    // when other streams compete for the SMs
+    at[na].id = cudaLaunchAttributeCooperative;
+    at[na].val.cooperative = 1;
+    ++na;
+  } else if (g_pdl) {
+    at[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
   cfg.attrs = at;
-  cfg.numAttrs = g_pdl ? 1 : 0;
+  cfg.numAttrs = na;
   if (passes == 2) {
     if (kp == 32) return cudaLaunchKernelEx(&cfg, lloyd_tc4_kernel<32, 2>, arg, map);
     return cudaLaunchKernelEx(&cfg, lloyd_tc4_kernel<64, 2>, arg, map);
@@ -768,7 +780,13 @@ static lkm_status run_lloyd(lkm_ctx* ctx, F* dC2, uint64_t k, uint64_t max_iter,
   CK(ctx->part_counts.ensure((size_t)grid * k * 4));
   CK(ctx->part_inertia.ensure((size_t)std::max(grid, 1024) * 8));
   const int fin_grid = (int)((kd + kFinElems - 1) / kFinElems);
-  CK(ctx->shift_part.ensure((size_t)fin_grid * 8));
+  CK(ctx->shift_part.ensure((size_t)std::max(fin_grid, grid) * 8));
+  // pipeline kernel on one GPU: optionally the finalize step folded into the kernel tail (LKM_FUSED_FINALIZE=1; off by default)
+  const bool fin_fused = use_tc && tc_threads == kT4Threads && ctx->world == 1 && ctx->fused_finalize && tc_grid <= ctx->sm_count;
+  if (fin_fused) {
+    CK(ctx->fin_sync.ensure(16));
+    CK(cudaMemsetAsync(ctx->fin_sync.p, 0, 16, ctx->stream));
+  }
   CK(ctx->counts_out.ensure(k * 8));
   CK(ctx->state.ensure(sizeof(LloydState)));
   const size_t L = kd + k + 1;
@@ -849,6 +867,10 @@ static lkm_status run_lloyd(lkm_ctx* ctx, F* dC2, uint64_t k, uint64_t max_iter,
             t4.prof = ctx->t4prof.as<long long>();
 #endif
             t4.part_sums = ta.part_sums; t4.part_counts = ta.part_counts; t4.part_inertia = ta.part_inertia; t4.state = dstate;
+            if (fin_fused) {   // single GPU: the kernel's tail does the finalize step (no finalize_kernel launch)
+              t4.fin_sync = ctx->fin_sync.as<unsigned int>(); t4.C_new = Cnext; t4.counts_out = ctx->counts_out.as<double>();
+              t4.shift_part = ctx->shift_part.as<double>(); t4.tol = tol; t4.max_iter = max_iter;
+            }
             CK(launch_tc4(tc_kp, tc4_passes, tc_grid, tc4_passes == 1 ? tc_smem1 : tc_smem, ctx->stream, t4, tc3_map));
           } else if (tc_threads == kT3Threads) {
             Tc3Args t3{};
@@ -994,7 +1016,9 @@ static lkm_status run_lloyd(lkm_ctx* ctx, F* dC2, uint64_t k, uint64_t max_iter,
       }
       if (flush && ctx->kernel_timing) CK(cudaEventRecord(ctx->iter_events[3 * it + 1], ctx->stream));
       // combine the per-CTA partials in fixed order, then the m_k-means update
-      if (ctx->world == 1) {
+      if (fin_fused) {
+        // done inside lloyd_tc4_kernel
+      } else if (ctx->world == 1) {
         FinalizeArgs<F, F, uint32_t> fa{};
         fa.src_sums = ctx->part_sums.as<F>(); fa.src_counts = ctx->part_counts.as<uint32_t>();
         fa.src_inertia = ctx->part_inertia.as<double>();
@@ -1951,8 +1975,10 @@ LKM_EXPORT lkm_status lkm_create(lkm_ctx** out, int device) {
   if (const char* v = std::getenv("LKM_TC5_FUSE")) ctx->tc5_fuse = std::atoi(v);
   if (const char* v = std::getenv("LKM_PAIR32")) ctx->pair32 = std::atoi(v);
   if (const char* v = std::getenv("LKM_PDL")) g_pdl = std::atoi(v);
+  if (const char* v = std::getenv("LKM_COOP")) g_coop = std::atoi(v);
   if (const char* v = std::getenv("LKM_FLUSH_SWEEP")) g_flush_sweep = std::atoi(v);
   if (const char* v = std::getenv("LKM_F64S")) ctx->f64s_enabled = std::atoi(v);
+  if (const char* v = std::getenv("LKM_FUSED_FINALIZE")) ctx->fused_finalize = std::atoi(v);
   if (const char* v = std::getenv("LKM_F64S_PACKED")) ctx->f64s_packed = std::atoi(v);
   if (const char* v = std::getenv("LKM_TC5_PASSES")) ctx->tc5_passes_forced = std::atoi(v);
   if (const char* v = std::getenv("LKM_P2P")) ctx->p2p_enabled = std::atoi(v);
@@ -1975,7 +2001,7 @@ LKM_EXPORT lkm_status lkm_destroy(lkm_ctx* ctx) {
   if (ctx->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->comm);
   DevBuf* bufs[] = {&ctx->xbuf, &ctx->cbuf, &ctx->part_sums, &ctx->part_counts, &ctx->part_inertia, &ctx->shift_part,
                     &ctx->counts_out, &ctx->state, &ctx->gather, &ctx->gather2, &ctx->labels, &ctx->dists, &ctx->wdists, &ctx->cum,
-                    &ctx->scratch, &ctx->tmpx, &ctx->tmpc, &ctx->idxbuf, &ctx->bsum, &ctx->weights, &ctx->flushbuf, &ctx->tca_bsplit, &ctx->tca_cn, &ctx->tca_cmax, &ctx->publish_done};
+                    &ctx->scratch, &ctx->tmpx, &ctx->tmpc, &ctx->idxbuf, &ctx->bsum, &ctx->weights, &ctx->flushbuf, &ctx->fin_sync, &ctx->tca_bsplit, &ctx->tca_cn, &ctx->tca_cmax, &ctx->publish_done};
   for (DevBuf* b : bufs) b->release();
   for (cudaEvent_t e : ctx->iter_events) cudaEventDestroy(e);
   if (ctx->h_state) cudaFreeHost(ctx->h_state);

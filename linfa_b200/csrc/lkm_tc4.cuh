@@ -67,6 +67,13 @@ struct Tc4Args {
   LloydState* state;
   long long* prof;   // LKM_T4_PROF builds only
   uint32_t pack_mult;   // 64, passed as an argument so that the score pack of the E role stays an IMAD (FMA pipe)
+  // in-kernel finalize (single GPU; fin_sync == nullptr: finalize_kernel follows as a separate launch)
+  unsigned int* fin_sync;   // [0] grid rendezvous, [1] last-CTA detection; zero between launches
+  float* C_new;
+  double* counts_out;       // k, members per cluster of this assignment (without the +1)
+  double* shift_part;       // [grid]
+  double tol;
+  unsigned long long max_iter;
 };
 
 // Optional phase profile (compile with -DLKM_T4_PROF): cycles spent in each wait of each role, written
@@ -773,6 +780,83 @@ __global__ void __launch_bounds__(kT4Threads, 1) lloyd_tc4_kernel(const Tc4Args 
   __syncthreads();
   if (warp == 0) tc::tmem_dealloc(tmem, kT4TmemCols);
   T4K(8);
+  if (a.fin_sync != nullptr && !done) {
+    // ---- in-kernel finalize (KM/algorithm.rs:785-810, 314-331; same arithmetic as finalize_kernel<UPDATE>) ----
+    // All CTAs of the grid are resident (grid <= SM count, one CTA per SM), so a counter rendezvous is safe.  Then CTA b
+    // combines elements [b epb, (b + 1) epb) of the k*d sums over the per-CTA partials: lane = source b, b + 32, ...
+    // (from L2: the partials were written by other SMs), warp butterfly, one warp per element: a fixed order.
+    __shared__ bool fin_last;
+    double* redf = reinterpret_cast<double*>(raw);
+    const unsigned int G = gridDim.x;
+    __threadfence();
+    __syncthreads();
+    if (t == 0) {
+      atomicAdd(&a.fin_sync[0], 1u);
+      unsigned int spins = 0;
+      while (*((volatile unsigned int*)&a.fin_sync[0]) < G && ++spins < (1u << 25)) {}
+      if (*((volatile unsigned int*)&a.fin_sync[0]) < G) atomicOr(&a.state->fallback_rows, 1ull << 41);   // timeout marker, reported by the host
+      __threadfence();
+    }
+    __syncthreads();
+    const int kd = k * 32;
+    const int epb = (kd + (int)G - 1) / (int)G;
+    double sq_w = 0.0;
+    for (int el = warp; el < epb; el += kT4Threads / 32) {
+      const int e = (int)blockIdx.x * epb + el;
+      if (e < kd) {
+        const int c = e >> 5;
+        double sv = 0.0;
+        unsigned int cn = 0u;
+        for (unsigned int b = lane; b < G; b += 32u) {
+          sv += (double)__ldcg(a.part_sums + (size_t)b * kd + e);
+          cn += __ldcg(a.part_counts + (size_t)b * k + c);
+        }
+        for (int o = 16; o > 0; o >>= 1) {
+          sv += __shfl_xor_sync(0xffffffffu, sv, o);
+          cn += __shfl_xor_sync(0xffffffffu, cn, o);
+        }
+        if (lane == 0) {
+          const float oldv = a.C[e];
+          const float newv = (float)((sv + (double)oldv) / ((double)cn + 1.0));
+          a.C_new[e] = newv;
+          const double df = (double)(oldv - newv);
+          sq_w += df * df;
+          if ((e & 31) == 0) a.counts_out[c] = (double)cn;
+        }
+      }
+    }
+    if (lane == 0) redf[warp] = sq_w;
+    __syncthreads();
+    if (t == 0) {
+      double v = 0.0;
+      for (int w = 0; w < kT4Threads / 32; ++w) v += redf[w];
+      a.shift_part[blockIdx.x] = v;
+      __threadfence();
+      fin_last = atomicAdd(&a.fin_sync[1], 1u) == G - 1u;
+    }
+    __syncthreads();
+    if (fin_last) {
+      __threadfence();
+      if (warp < 2) {
+        const double* src = warp == 0 ? a.shift_part : a.part_inertia;
+        double v = 0.0;
+        for (unsigned int b = lane; b < G; b += 32u) v += __ldcg(src + b);
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0) redf[32 + warp] = v;
+      }
+      __syncthreads();
+      if (t == 0) {
+        const float shift = (float)sqrt(redf[32]);   // L2Dist::distance: sqrt in f64, cast to F
+        a.state->shift = (double)shift;
+        a.state->inertia = redf[33];
+        const unsigned long long itn = a.state->n_iter + 1;
+        a.state->n_iter = itn;
+        if (shift < (float)a.tol || itn >= a.max_iter) a.state->done = 1;
+        a.fin_sync[0] = 0u;
+        a.fin_sync[1] = 0u;
+      }
+    }
+  }
 }
 
 
