@@ -806,3 +806,23 @@ def test_f64_screened_kernel_nan_inf_ties(lb, oracle):
     c1, counts1, _, _ = ctx.lloyd_iters(init, 1, 0.0)
     assert counts1.tolist() == counts.tolist()
     np.testing.assert_array_equal(np.isnan(c), np.isnan(c1))
+
+
+def test_f64_screened_kernel_full_fit_matches_oracle(lb, oracle):
+    """Through the public API (fit -> predict -> transform): f64, d = 8, convergence by tolerance, k-means++ seeding and
+    best-of-two runs shared with the oracle; n is above the automatic threshold of the screened kernel."""
+    X, _ = blobs(60000, 8, 12, np.float64, seed=21, spread=10.0)
+    g = np.random.default_rng(2)
+    X = X[g.permutation(len(X))].copy()
+    rng = lb.Xoshiro256Plus.seed_from_u64(9)
+    model = (lb.KMeans.params_with_rng(12, rng).n_runs(2).max_n_iterations(60).tolerance(1e-6)
+             .init_method(lb.KMeansInit.KMeansPlusPlus).fit(lb.DatasetBase(X)))
+    assert lb.Context.default().last_stats.assign_path == 3
+    ref = oracle.fit(X, 12, oracle.rng(9), n_runs=2, max_iter=60, tol=1e-6, method=INIT_KMEANSPP, acc_f64=True)
+    assert ref["status"] == 0
+    np.testing.assert_allclose(model.centroids(), ref["centroids"], rtol=1e-10, atol=1e-9)
+    np.testing.assert_allclose(model.inertia(), ref["inertia"], rtol=1e-10)
+    assert model.cluster_count().tolist() == ref["cluster_count"].tolist()
+    lab, dist = oracle.assign(X, model.centroids())
+    assert (model.predict(X) == lab).all()
+    assert (model.transform(X) == dist).all()
