@@ -104,6 +104,7 @@ struct lkm_ctx {
   int fused_finalize = 0;   // LKM_FUSED_FINALIZE=1: finalize folded into the pipeline kernel's tail (measured: no gain, 47.1 vs 46.3 us per cfg2 step)
   int f64s_enabled = 1;  // LKM_F64S=0: lloyd_kernel<double> instead of the f32-screened small-d f64 kernel (lkm_f64s.cuh)
   int f64s_packed = 1;   // LKM_F64S_PACKED=0: scalar FFMA instead of FFMA2 in that kernel
+  int f64s_rpt = 2;      // LKM_F64S_RPT=1: one row per lane (32-row tiles, 3 CTAs / SM)
   int pair32 = 0;        // LKM_PAIR32=1: d = 32, k <= 64 through the CTA-pair screening kernel instead of the pipeline kernel
   int tc5_fuse = 1;      // LKM_TC5_FUSE=0: screening kernel without the fused update of uniform tiles
   int tc5_enabled = 1;   // LKM_TC5=0: tc_assign_kernel instead of the CTA-pair assignment kernel
@@ -620,24 +621,28 @@ static lkm_status run_lloyd(lkm_ctx* ctx, F* dC2, uint64_t k, uint64_t max_iter,
   // f64, 2 / 4 / 8 / 16 features, few centroids: f32-screened warp-per-tile kernel (lkm_f64s.cuh)
   bool use_f6 = false;
   size_t f6_smem = 0;
+  const void* f6_fn = nullptr;
   if constexpr (std::is_same<F, double>::value) {
     const bool shape_ok = (d == 2 || d == 4 || d == 8 || d == 16) && k <= 64 && kd <= 512 && n >= 1 &&
                           (reinterpret_cast<uintptr_t>(dX) & 15) == 0;
     if (shape_ok && ((ctx->force_path == -1 && ctx->f64s_enabled && n >= 32768) || ctx->force_path == 3)) {
       const void* fn = nullptr;
-      switch (d) {
-        case 2: f6_smem = f6::smem_bytes<2>((int)k); fn = ctx->f64s_packed ? (const void*)f6::lloyd_f64s_kernel<2, true> : (const void*)f6::lloyd_f64s_kernel<2, false>; break;
-        case 4: f6_smem = f6::smem_bytes<4>((int)k); fn = ctx->f64s_packed ? (const void*)f6::lloyd_f64s_kernel<4, true> : (const void*)f6::lloyd_f64s_kernel<4, false>; break;
-        case 8: f6_smem = f6::smem_bytes<8>((int)k); fn = ctx->f64s_packed ? (const void*)f6::lloyd_f64s_kernel<8, true> : (const void*)f6::lloyd_f64s_kernel<8, false>; break;
-        default: f6_smem = f6::smem_bytes<16>((int)k); fn = ctx->f64s_packed ? (const void*)f6::lloyd_f64s_kernel<16, true> : (const void*)f6::lloyd_f64s_kernel<16, false>; break;
+      const bool pk = ctx->f64s_packed != 0;
+#define LKM_F6_PICK(DD, RR) { f6_smem = f6::smem_bytes<DD, RR>((int)k); fn = pk ? (const void*)f6::lloyd_f64s_kernel<DD, true, RR> : (const void*)f6::lloyd_f64s_kernel<DD, false, RR>; }
+      if (ctx->f64s_rpt == 1) {
+        switch (d) { case 2: LKM_F6_PICK(2, 1) break; case 4: LKM_F6_PICK(4, 1) break; case 8: LKM_F6_PICK(8, 1) break; default: LKM_F6_PICK(16, 1) break; }
+      } else {
+        switch (d) { case 2: LKM_F6_PICK(2, 2) break; case 4: LKM_F6_PICK(4, 2) break; case 8: LKM_F6_PICK(8, 2) break; default: LKM_F6_PICK(16, 2) break; }
       }
+#undef LKM_F6_PICK
+      f6_fn = fn;
       if (f6_smem <= ctx->smem_optin) {
         CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)f6_smem));
         CK(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
         int occ = 0;
         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, f6::kThreads, f6_smem));
         occ = std::max(1, occ);
-        const uint64_t n_tiles = (n + f6::kTileRows - 1) / f6::kTileRows;
+        const uint64_t n_tiles = (n + 32 * ctx->f64s_rpt - 1) / (32 * ctx->f64s_rpt);
         const uint64_t want = (n_tiles + f6::kWarps - 1) / f6::kWarps;
         pf.fused = true;
         pf.grid = (int)std::max<uint64_t>(1, std::min<uint64_t>(want, (uint64_t)ctx->sm_count * occ));
@@ -888,13 +893,8 @@ static lkm_status run_lloyd(lkm_ctx* ctx, F* dC2, uint64_t k, uint64_t max_iter,
           fa6.X = dX; fa6.n = n; fa6.k = (int)k; fa6.C = Ccur;
           fa6.part_sums = ctx->part_sums.as<double>(); fa6.part_counts = ctx->part_counts.as<uint32_t>();
           fa6.part_inertia = ctx->part_inertia.as<double>(); fa6.state = dstate; fa6.state_rw = dstate;
-          const bool pk = ctx->f64s_packed != 0;
-          switch (d) {
-            case 2: if (pk) f6::lloyd_f64s_kernel<2, true><<<pf.grid, f6::kThreads, f6_smem, ctx->stream>>>(fa6); else f6::lloyd_f64s_kernel<2, false><<<pf.grid, f6::kThreads, f6_smem, ctx->stream>>>(fa6); break;
-            case 4: if (pk) f6::lloyd_f64s_kernel<4, true><<<pf.grid, f6::kThreads, f6_smem, ctx->stream>>>(fa6); else f6::lloyd_f64s_kernel<4, false><<<pf.grid, f6::kThreads, f6_smem, ctx->stream>>>(fa6); break;
-            case 8: if (pk) f6::lloyd_f64s_kernel<8, true><<<pf.grid, f6::kThreads, f6_smem, ctx->stream>>>(fa6); else f6::lloyd_f64s_kernel<8, false><<<pf.grid, f6::kThreads, f6_smem, ctx->stream>>>(fa6); break;
-            default: if (pk) f6::lloyd_f64s_kernel<16, true><<<pf.grid, f6::kThreads, f6_smem, ctx->stream>>>(fa6); else f6::lloyd_f64s_kernel<16, false><<<pf.grid, f6::kThreads, f6_smem, ctx->stream>>>(fa6); break;
-          }
+          void* kargs[] = {(void*)&fa6};
+          CK(cudaLaunchKernel(f6_fn, dim3((unsigned)pf.grid), dim3(f6::kThreads), kargs, f6_smem, ctx->stream));
           CK(cudaGetLastError());
           ctx->launches++;
         }
@@ -1980,6 +1980,7 @@ LKM_EXPORT lkm_status lkm_create(lkm_ctx** out, int device) {
   if (const char* v = std::getenv("LKM_F64S")) ctx->f64s_enabled = std::atoi(v);
   if (const char* v = std::getenv("LKM_FUSED_FINALIZE")) ctx->fused_finalize = std::atoi(v);
   if (const char* v = std::getenv("LKM_F64S_PACKED")) ctx->f64s_packed = std::atoi(v);
+  if (const char* v = std::getenv("LKM_F64S_RPT")) ctx->f64s_rpt = std::atoi(v) == 1 ? 1 : 2;
   if (const char* v = std::getenv("LKM_TC5_PASSES")) ctx->tc5_passes_forced = std::atoi(v);
   if (const char* v = std::getenv("LKM_P2P")) ctx->p2p_enabled = std::atoi(v);
   if (const char* v = std::getenv("LKM_TC4_PASSES")) ctx->tc4_passes_forced = std::atoi(v);

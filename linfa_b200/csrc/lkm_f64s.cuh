@@ -31,12 +31,9 @@ namespace f6 {
 
 constexpr int kWarps = 8;
 constexpr int kThreads = kWarps * 32;
-constexpr int kTileRows = 64;   // per warp and step: two rows per lane
+// RPT rows per lane: a warp's tile is 32 RPT rows.  RPT = 2 halves the centroid operand loads per row (2 CTAs / SM);
+// RPT = 1 needs fewer registers and a smaller stage (3 CTAs / SM).
 constexpr int kStages = 2;
-#ifndef LKM_F6_RELOAD
-#define LKM_F6_RELOAD 0
-#endif
-constexpr bool kReloadRows = LKM_F6_RELOAD != 0;   // read the f64 rows again for the distance instead of holding them in registers
 
 struct Args {
   const double* X;
@@ -50,7 +47,7 @@ struct Args {
   LloydState* state_rw;     // fallback_rows += rows that needed the exact re-scan
 };
 
-template <int D> __host__ __device__ constexpr int stage_bytes() { return kTileRows * D * 8 + (kTileRows * D * 8 / 128) * 16; }
+template <int D, int RPT> __host__ __device__ constexpr int stage_bytes() { return 32 * RPT * D * 8 + (32 * RPT * D * 8 / 128) * 16; }
 // byte offset of a row inside a stage: 16 bytes of padding after every 128 bytes of rows
 template <int D> __device__ __forceinline__ uint32_t row_off(int row) {
   constexpr int RP = 16 / D;   // rows per 128 bytes
@@ -59,10 +56,10 @@ template <int D> __device__ __forceinline__ uint32_t row_off(int row) {
 
 __host__ __device__ inline size_t al16(size_t x) { return (x + 15) & ~(size_t)15; }
 // dynamic shared memory: exact centroids | norms + max | f32 pair operands | f32 pair norms | per warp {stages, sums, counts}
-template <int D> __host__ __device__ inline size_t smem_bytes(int k) {
+template <int D, int RPT> __host__ __device__ inline size_t smem_bytes(int k) {
   const int kp = (k + 1) & ~1;
   return al16((size_t)k * D * 8) + al16((size_t)(k + 1) * 8) + al16((size_t)kp * D * 4) + al16((size_t)kp * 4) + 16 +
-         (size_t)kWarps * (kStages * stage_bytes<D>() + al16((size_t)(32 / D) * k * D * 8) + al16((size_t)(32 / D) * k * 4));
+         (size_t)kWarps * (kStages * stage_bytes<D, RPT>() + al16((size_t)(32 / D) * k * D * 8) + al16((size_t)(32 / D) * k * 4));
 }
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -121,14 +118,16 @@ __device__ __forceinline__ float f6_margin(const Margin& m, float xx) {
   return fmaf(m.m2, xx, fmaf(m.m1, r, m.m0));
 }
 
-template <int D, bool PACKED>
-__global__ void __launch_bounds__(kThreads, 2) lloyd_f64s_kernel(const Args a) {
+template <int D, bool PACKED, int RPT>
+__global__ void __launch_bounds__(kThreads, RPT == 1 ? 3 : 2) lloyd_f64s_kernel(const Args a) {
+  static_assert(RPT == 1 || RPT == 2, "rows per lane");
+  constexpr int kTileRows = 32 * RPT;
   static_assert(D == 2 || D == 4 || D == 8 || D == 16, "row width");
   if (a.state != nullptr && a.state->done) return;
   constexpr int CPR = D / 2;            // 16-byte chunks per row
   constexpr int H = 32 / D;             // rows per step of the update walk
   constexpr int STEPS = kTileRows / H;
-  constexpr int SB = stage_bytes<D>();
+  constexpr int SB = stage_bytes<D, RPT>();
   const unsigned full = 0xffffffffu;
   extern __shared__ __align__(16) unsigned char smem[];
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
@@ -223,106 +222,102 @@ __global__ void __launch_bounds__(kThreads, 2) lloyd_f64s_kernel(const Args a) {
     const unsigned char* sp = stage0 + (size_t)st * SB;
     const unsigned long long row0 = tile * kTileRows;
 
-    // ---- own rows: lane, lane + 32 ----
-    double x0[D], x1[D];
+    // ---- own rows: lane (+ 32) ----
+    double x[RPT][D];
+    float xf[RPT][D], xx[RPT], bq[RPT], sq[RPT];
 #pragma unroll
-    for (int c = 0; c < CPR; ++c) {
-      const double2 v0 = *reinterpret_cast<const double2*>(sp + row_off<D>(lane) + c * 16);
-      const double2 v1 = *reinterpret_cast<const double2*>(sp + row_off<D>(lane + 32) + c * 16);
-      x0[2 * c] = v0.x; x0[2 * c + 1] = v0.y;
-      x1[2 * c] = v1.x; x1[2 * c + 1] = v1.y;
-    }
-    float xf0[D], xf1[D];
-    float xx0 = 0.f, xx1 = 0.f;
+    for (int r = 0; r < RPT; ++r) {
 #pragma unroll
-    for (int j = 0; j < D; ++j) {
-      xf0[j] = (float)x0[j];
-      xf1[j] = (float)x1[j];
-      xx0 = fmaf(xf0[j], xf0[j], xx0);
-      xx1 = fmaf(xf1[j], xf1[j], xx1);
+      for (int c = 0; c < CPR; ++c) {
+        const double2 v = *reinterpret_cast<const double2*>(sp + row_off<D>(lane + 32 * r) + c * 16);
+        x[r][2 * c] = v.x; x[r][2 * c + 1] = v.y;
+      }
+      xx[r] = 0.f;
+#pragma unroll
+      for (int j = 0; j < D; ++j) {
+        xf[r][j] = (float)x[r][j];
+        xx[r] = fmaf(xf[r][j], xf[r][j], xx[r]);
+      }
+      bq[r] = 3.0e38f; sq[r] = 3.0e38f;
     }
-    float b0 = 3.0e38f, s0 = 3.0e38f, b1 = 3.0e38f, s1 = 3.0e38f;
     if constexpr (PACKED) {
-      unsigned long long xd0[D], xd1[D];
+      unsigned long long xd[RPT][D];
 #pragma unroll
-      for (int j = 0; j < D; ++j) { xd0[j] = pack2(xf0[j], xf0[j]); xd1[j] = pack2(xf1[j], xf1[j]); }
+      for (int r = 0; r < RPT; ++r)
+#pragma unroll
+        for (int j = 0; j < D; ++j) xd[r][j] = pack2(xf[r][j], xf[r][j]);
 #pragma unroll 2
       for (int p = 0; p < kp / 2; ++p) {
-        unsigned long long w0 = *reinterpret_cast<const unsigned long long*>(cnp + 2 * p), w1 = w0;
+        unsigned long long w[RPT];
+#pragma unroll
+        for (int r = 0; r < RPT; ++r) w[r] = *reinterpret_cast<const unsigned long long*>(cnp + 2 * p);
 #pragma unroll
         for (int j = 0; j < D; j += 2) {
           const ulonglong2 c2 = *reinterpret_cast<const ulonglong2*>(cfp + (p * D + j) * 2);
-          w0 = f2_fma(xd0[j], c2.x, w0);
-          w1 = f2_fma(xd1[j], c2.x, w1);
-          w0 = f2_fma(xd0[j + 1], c2.y, w0);
-          w1 = f2_fma(xd1[j + 1], c2.y, w1);
+#pragma unroll
+          for (int r = 0; r < RPT; ++r) w[r] = f2_fma(xd[r][j], c2.x, w[r]);
+#pragma unroll
+          for (int r = 0; r < RPT; ++r) w[r] = f2_fma(xd[r][j + 1], c2.y, w[r]);
         }
-        float wa, wb;
-        unpack2(w0, wa, wb);
-        top2_packed(wa, 2u * p, keep, b0, s0);
-        top2_packed(wb, 2u * p + 1u, keep, b0, s0);
-        unpack2(w1, wa, wb);
-        top2_packed(wa, 2u * p, keep, b1, s1);
-        top2_packed(wb, 2u * p + 1u, keep, b1, s1);
+#pragma unroll
+        for (int r = 0; r < RPT; ++r) {
+          float wa, wb;
+          unpack2(w[r], wa, wb);
+          top2_packed(wa, 2u * p, keep, bq[r], sq[r]);
+          top2_packed(wb, 2u * p + 1u, keep, bq[r], sq[r]);
+        }
       }
     } else {
 #pragma unroll 2
       for (int p = 0; p < kp / 2; ++p) {
         const float2 nn = *reinterpret_cast<const float2*>(cnp + 2 * p);
-        float wa0 = nn.x, wb0 = nn.y, wa1 = nn.x, wb1 = nn.y;
+        float wa[RPT], wb[RPT];
+#pragma unroll
+        for (int r = 0; r < RPT; ++r) { wa[r] = nn.x; wb[r] = nn.y; }
 #pragma unroll
         for (int j = 0; j < D; j += 2) {
           const float4 c4 = *reinterpret_cast<const float4*>(cfp + (p * D + j) * 2);
-          wa0 = fmaf(xf0[j], c4.x, wa0); wb0 = fmaf(xf0[j], c4.y, wb0);
-          wa1 = fmaf(xf1[j], c4.x, wa1); wb1 = fmaf(xf1[j], c4.y, wb1);
-          wa0 = fmaf(xf0[j + 1], c4.z, wa0); wb0 = fmaf(xf0[j + 1], c4.w, wb0);
-          wa1 = fmaf(xf1[j + 1], c4.z, wa1); wb1 = fmaf(xf1[j + 1], c4.w, wb1);
+#pragma unroll
+          for (int r = 0; r < RPT; ++r) {
+            wa[r] = fmaf(xf[r][j], c4.x, wa[r]); wb[r] = fmaf(xf[r][j], c4.y, wb[r]);
+            wa[r] = fmaf(xf[r][j + 1], c4.z, wa[r]); wb[r] = fmaf(xf[r][j + 1], c4.w, wb[r]);
+          }
         }
-        top2_packed(wa0, 2u * p, keep, b0, s0);
-        top2_packed(wb0, 2u * p + 1u, keep, b0, s0);
-        top2_packed(wa1, 2u * p, keep, b1, s1);
-        top2_packed(wb1, 2u * p + 1u, keep, b1, s1);
+#pragma unroll
+        for (int r = 0; r < RPT; ++r) {
+          top2_packed(wa[r], 2u * p, keep, bq[r], sq[r]);
+          top2_packed(wb[r], 2u * p + 1u, keep, bq[r], sq[r]);
+        }
       }
     }
-    // ---- certificate, winner's distance (the f64 rows are read again from the stage: holding them across the scoring
-    //      loop costs 32 registers) ----
-    if constexpr (kReloadRows) asm volatile("" ::: "memory");
-    int lab0, lab1;
+    // ---- certificate, winner's distance ----
+    int labs[RPT];
 #pragma unroll
-    for (int half = 0; half < 2; ++half) {
-      const bool ok = row0 + (unsigned)(half * 32 + lane) < a.n;
-      const float bq = half ? b1 : b0, sq = half ? s1 : s0, xxh = half ? xx1 : xx0;
-      int bi = (int)(__float_as_uint(bq) & idx_mask);
-      const bool cert = ((sq - bq) > f6_margin(mg, xxh)) && bi < k;
+    for (int r = 0; r < RPT; ++r) {
+      const bool ok = row0 + (unsigned)(r * 32 + lane) < a.n;
+      int bi = (int)(__float_as_uint(bq[r]) & idx_mask);
+      const bool cert = ((sq[r] - bq[r]) > f6_margin(mg, xx[r])) && bi < k;
       double dist = 0.0;
       if (ok) {
-        double x[D];
-        if constexpr (kReloadRows) {
-#pragma unroll
-          for (int c = 0; c < CPR; ++c) {
-            const double2 v = *reinterpret_cast<const double2*>(sp + row_off<D>(lane + half * 32) + c * 16);
-            x[2 * c] = v.x; x[2 * c + 1] = v.y;
-          }
-        } else {
-#pragma unroll
-          for (int j = 0; j < D; ++j) x[j] = half ? x1[j] : x0[j];
-        }
         if (cert) {
 #pragma unroll
           for (int j = 0; j < D; ++j) {
-            const double df = cs[bi * D + j] - x[j];
+            const double df = cs[bi * D + j] - x[r][j];
             dist = fma(df, df, dist);
           }
         } else {
-          my_fallbacks += scan_centroids_certified<double, D>(cs, cn, k, cmax64, x, dist, bi) ? 0u : 1u;
+          my_fallbacks += scan_centroids_certified<double, D>(cs, cn, k, cmax64, x[r], dist, bi) ? 0u : 1u;
         }
         inert += dist;
       }
-      if (half) lab1 = ok ? bi : -1; else lab0 = ok ? bi : -1;
+      labs[r] = ok ? bi : -1;
     }
     // ---- update walk: lane = (feature f, row group h), rows h, h + H, ... of the tile ----
-    const int lab_t = __shfl_sync(full, lab0, 0);
-    if (__all_sync(full, lab0 == lab_t && lab1 == lab_t) && lab_t >= 0) {
+    const int lab_t = __shfl_sync(full, labs[0], 0);
+    bool same = labs[0] == lab_t;
+#pragma unroll
+    for (int r = 1; r < RPT; ++r) same = same && labs[r] == lab_t;
+    if (__all_sync(full, same) && lab_t >= 0) {
       // one cluster for the whole tile (the rule for blob-ordered rows): sums stay in registers; cur_lab is warp-uniform
       if (lab_t != cur_lab) {
         if (cur_lab >= 0) {
@@ -349,7 +344,7 @@ __global__ void __launch_bounds__(kThreads, 2) lloyd_f64s_kernel(const Args a) {
 #pragma unroll
       for (int m = 0; m < STEPS; ++m) {
         const int row = m * H + h;
-        const int lab = __shfl_sync(full, (m * H >= 32) ? lab1 : lab0, row & 31);
+        const int lab = __shfl_sync(full, labs[(m * H) >> 5], row & 31);
         const double xv = *reinterpret_cast<const double*>(sp + row_off<D>(row) + 8 * f);
         if (lab >= 0) {
           acc_h[lab * D + f] += xv;
