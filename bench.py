@@ -52,7 +52,7 @@ DEFAULT_KERNELS = {
     "cfg2": "lloyd_tc4_kernel (fused assign+update, tcgen05 pipeline)",
     "cfg3": "assign_tc5s_kernel + update_rows_kernel (CTA-pair tcgen05 assignment, then the streaming update: two passes over X)",
     "cfg4": "4 x assign_tc5s_kernel (one per 256 centroids) + update_rows_kernel x 2 cluster chunks (six passes over X)",
-    "cfg5": "lloyd_f64s_kernel<8> (f32-screened fused assign+update, f64 d=8 k<=64)",
+    "cfg5": "lloyd_f64s_kernel<8, 1, 2> (f32-screened fused assign+update, f64 d=8 k<=64)",
     "cfg1": "lloyd_kernel<double> (exact, CUDA cores)",
 }
 
