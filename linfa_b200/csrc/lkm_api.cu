@@ -116,7 +116,8 @@ struct lkm_ctx {
   uint64_t flush_bytes = 0;
   unsigned long long bar_epoch = 0;   // rank_barrier_kernel (flushed-L2 benchmark mode, multi-GPU)
   int kernel_timing = 0;
-  DevBuf flushbuf, fin_sync;
+  DevBuf flushbuf, fin_sync, para_c2;
+  int para_tc = 0;       // LKM_PARA_TC=1: k-means|| candidate histogram through one tensor-core Lloyd iteration (measured slower on the cfg4 shard: 6.4 vs 5.9 s)
   std::vector<cudaEvent_t> iter_events;
   // workspaces
   DevBuf tca_bsplit, tca_cn, tca_cmax;
@@ -170,6 +171,7 @@ static lkm_status fail(lkm_ctx* ctx, lkm_status s, const char* msg) {
 // Benchmark hygiene: after the scratch buffer has been overwritten (which evicts the resident matrix from L2 but
 // leaves the L2 full of DIRTY lines, whose write-back would be charged to the next timed kernel), a read-only sweep
 // over the first half of the same buffer replaces them by clean lines.  LKM_FLUSH_SWEEP=0 disables it.
+constexpr int kT5MaxChunks = 64;   // CTA-pair assignment kernel: k <= 256 * 64 centroids, one launch per chunk of 256
 static int g_flush_sweep = 1;
 __global__ void __launch_bounds__(512) l2_read_sweep_kernel(const uint4* __restrict__ p, size_t n16, unsigned int* sink) {
   unsigned int acc = 0;
@@ -613,7 +615,7 @@ static lkm_status run_lloyd(lkm_ctx* ctx, F* dC2, uint64_t k, uint64_t max_iter,
     // shapes of the CTA-pair assignment kernel: two-pass (tensor-core assignment + streaming update) even when the
     // centroids would fit the fused CUDA-core kernel, unless the contraction is tiny
     if (!use_tc && (ctx->force_path == -1 || ctx->force_path == 2) && ctx->tc5_enabled && ctx->upd_variant != 0 &&
-        (d == 64 || d == 128) && k <= (uint64_t)kT5K * 16 && kd >= 2048 && n >= 1 && (reinterpret_cast<uintptr_t>(dX) & 15) == 0)
+        (d == 64 || d == 128) && k <= (uint64_t)kT5K * kT5MaxChunks && kd >= 2048 && n >= 1 && (reinterpret_cast<uintptr_t>(dX) & 15) == 0)
       pf.fused = false;
     if (pair32) pf.fused = false;
   }
@@ -738,7 +740,7 @@ static lkm_status run_lloyd(lkm_ctx* ctx, F* dC2, uint64_t k, uint64_t max_iter,
   CUtensorMap tc5_map;
   std::memset(&tc5_map, 0, sizeof(tc5_map));
   if constexpr (std::is_same<F, float>::value) {
-    if (use_upd && ctx->tc5_enabled && (d == 64 || d == 128 || pair32) && k <= (uint64_t)kT5K * 16 && n + 512 < (1ull << 31) &&
+    if (use_upd && ctx->tc5_enabled && (d == 64 || d == 128 || pair32) && k <= (uint64_t)kT5K * kT5MaxChunks && n + 512 < (1ull << 31) &&
         tc5_smem_bytes((int)d) <= ctx->smem_optin && tc5s_smem_bytes((int)d) <= ctx->smem_optin) {
       tc5_smem = tc5_smem_bytes((int)d);
       const void* fn = d == 64 ? (const void*)assign_tc5_kernel<64> : (const void*)assign_tc5_kernel<128>;
@@ -1335,16 +1337,47 @@ static lkm_status kmeans_para(lkm_ctx* ctx, const F* dX, uint64_t n, uint64_t d,
   }
   // weights = cluster_membership_counts (KM/init.rs:273-285): histogram of the
   // nearest candidate over all rows
-  CK(ctx->labels.ensure(std::max<uint64_t>(n, 1) * 4));
-  CKS(run_assign<F>(ctx, dX, n, d, dCand, n_cand, ctx->labels.as<uint32_t>(), nullptr, 0, nullptr, nullptr));
-  CK(ctx->tmpx.ensure(n_cand * sizeof(F) + n_cand * 4 + 64));
-  unsigned int* dhist = reinterpret_cast<unsigned int*>(ctx->tmpx.as<char>() + ((n_cand * sizeof(F) + 15) & ~(size_t)15));
-  CK(cudaMemsetAsync(dhist, 0, n_cand * 4, ctx->stream));
-  label_hist_kernel<<<(int)std::min<uint64_t>((n + 255) / 256, 4096), 256, 0, ctx->stream>>>(ctx->labels.as<uint32_t>(), n, dhist);
-  CK(cudaGetLastError());
-  u32_to_float_kernel<F><<<(int)((n_cand + 255) / 256), 256, 0, ctx->stream>>>(dhist, (int)n_cand, ctx->tmpx.as<F>());
-  CK(cudaGetLastError());
-  ctx->launches += 2;
+  bool counted = false;
+  if constexpr (std::is_same<F, float>::value) {
+    // f32 rows of 64 / 128 features on the resident matrix: the histogram is the cluster-count output of ONE Lloyd iteration
+    // with the candidates as centroids, i.e. the CTA-pair tensor-core assignment (labels certified against the exact scan)
+    // instead of n x n_cand exact CUDA-core distances (cfg4 shard: 12.5M x 8192 x 64)
+    if (ctx->para_tc && ctx->tc5_enabled && ctx->upd_variant != 0 && (ctx->force_path == -1 || ctx->force_path == 2) &&
+        (d == 64 || d == 128) && n_cand * d >= 2048 && n_cand <= (uint64_t)kT5K * kT5MaxChunks &&
+        dX == reinterpret_cast<const F*>(ctx->X) && n == ctx->n && ctx->world == 1) {
+      CK(ctx->para_c2.ensure(2 * n_cand * d * sizeof(F)));
+      CK(cudaMemcpyAsync(ctx->para_c2.p, dCand, n_cand * d * sizeof(F), cudaMemcpyDeviceToDevice, ctx->stream));
+      LloydOut lo;
+      // candidates are data rows, several per blob: their score gaps are far below the one-product screening margin, so
+      // the 3xTF32 variant is pinned for this call (the screening variant would re-scan nearly every row exactly)
+      const int passes_saved = ctx->tc5_passes_forced;
+      ctx->tc5_passes_forced = 3;
+      const lkm_status rs = run_lloyd<F>(ctx, ctx->para_c2.as<F>(), n_cand, 1, 0.0, lo);
+      ctx->tc5_passes_forced = passes_saved;
+      if (rs != LKM_OK) return rs;
+      std::vector<double> hc(n_cand);
+      CK(cudaMemcpyAsync(hc.data(), ctx->counts_out.p, n_cand * 8, cudaMemcpyDeviceToHost, ctx->stream));
+      CK(cudaStreamSynchronize(ctx->stream));
+      std::vector<F> hw(n_cand);
+      for (uint64_t c = 0; c < n_cand; ++c) hw[c] = (F)hc[c];
+      CK(ctx->tmpx.ensure(n_cand * sizeof(F) + n_cand * 4 + 64));
+      CK(cudaMemcpyAsync(ctx->tmpx.p, hw.data(), n_cand * sizeof(F), cudaMemcpyHostToDevice, ctx->stream));
+      CK(cudaStreamSynchronize(ctx->stream));
+      counted = true;
+    }
+  }
+  if (!counted) {
+    CK(ctx->labels.ensure(std::max<uint64_t>(n, 1) * 4));
+    CKS(run_assign<F>(ctx, dX, n, d, dCand, n_cand, ctx->labels.as<uint32_t>(), nullptr, 0, nullptr, nullptr));
+    CK(ctx->tmpx.ensure(n_cand * sizeof(F) + n_cand * 4 + 64));
+    unsigned int* dhist = reinterpret_cast<unsigned int*>(ctx->tmpx.as<char>() + ((n_cand * sizeof(F) + 15) & ~(size_t)15));
+    CK(cudaMemsetAsync(dhist, 0, n_cand * 4, ctx->stream));
+    label_hist_kernel<<<(int)std::min<uint64_t>((n + 255) / 256, 4096), 256, 0, ctx->stream>>>(ctx->labels.as<uint32_t>(), n, dhist);
+    CK(cudaGetLastError());
+    u32_to_float_kernel<F><<<(int)((n_cand + 255) / 256), 256, 0, ctx->stream>>>(dhist, (int)n_cand, ctx->tmpx.as<F>());
+    CK(cudaGetLastError());
+    ctx->launches += 2;
+  }
   // weighted k-means++ over the candidates; its scratch arrays are sized for
   // n_cand <= n rows, and the candidate weights live in tmpx
   return weighted_kmeanspp<F>(ctx, dCand, n_cand, d, ctx->tmpx.as<F>(), k, rng, pick_mode, dC);
@@ -1978,6 +2011,7 @@ LKM_EXPORT lkm_status lkm_create(lkm_ctx** out, int device) {
   if (const char* v = std::getenv("LKM_COOP")) g_coop = std::atoi(v);
   if (const char* v = std::getenv("LKM_FLUSH_SWEEP")) g_flush_sweep = std::atoi(v);
   if (const char* v = std::getenv("LKM_F64S")) ctx->f64s_enabled = std::atoi(v);
+  if (const char* v = std::getenv("LKM_PARA_TC")) ctx->para_tc = std::atoi(v);
   if (const char* v = std::getenv("LKM_FUSED_FINALIZE")) ctx->fused_finalize = std::atoi(v);
   if (const char* v = std::getenv("LKM_F64S_PACKED")) ctx->f64s_packed = std::atoi(v);
   if (const char* v = std::getenv("LKM_F64S_RPT")) ctx->f64s_rpt = std::atoi(v) == 1 ? 1 : 2;
@@ -2002,7 +2036,7 @@ LKM_EXPORT lkm_status lkm_destroy(lkm_ctx* ctx) {
   if (ctx->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->comm);
   DevBuf* bufs[] = {&ctx->xbuf, &ctx->cbuf, &ctx->part_sums, &ctx->part_counts, &ctx->part_inertia, &ctx->shift_part,
                     &ctx->counts_out, &ctx->state, &ctx->gather, &ctx->gather2, &ctx->labels, &ctx->dists, &ctx->wdists, &ctx->cum,
-                    &ctx->scratch, &ctx->tmpx, &ctx->tmpc, &ctx->idxbuf, &ctx->bsum, &ctx->weights, &ctx->flushbuf, &ctx->fin_sync, &ctx->tca_bsplit, &ctx->tca_cn, &ctx->tca_cmax, &ctx->publish_done};
+                    &ctx->scratch, &ctx->tmpx, &ctx->tmpc, &ctx->idxbuf, &ctx->bsum, &ctx->weights, &ctx->flushbuf, &ctx->fin_sync, &ctx->para_c2, &ctx->tca_bsplit, &ctx->tca_cn, &ctx->tca_cmax, &ctx->publish_done};
   for (DevBuf* b : bufs) b->release();
   for (cudaEvent_t e : ctx->iter_events) cudaEventDestroy(e);
   if (ctx->h_state) cudaFreeHost(ctx->h_state);

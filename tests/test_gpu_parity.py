@@ -482,7 +482,7 @@ TCA_CASES = [(6000, 128, 256, 16, 30.0, False), (5000, 64, 1024, 40, 30.0, False
              # shuffled rows (many one-row segments), one / two / four cluster chunks
              (148 * 32 * 3 + 19, 128, 256, 256, 30.0, False), (148 * 32 * 3 + 19, 128, 256, 256, 30.0, True),
              (40000, 64, 1024, 64, 30.0, True), (30001, 128, 1000, 50, 30.0, True), (20000, 64, 512, 300, 30.0, True),
-             (2047, 64, 4000, 3, 30.0, False),
+             (2047, 64, 4000, 3, 30.0, False), (3000, 64, 4500, 5, 30.0, False), (2000, 128, 8200, 4, 30.0, True),   # 18 / 33 chunk launches
              # CTA-pair assignment kernel (assign_tc5_kernel: d in {64, 128}, k <= 256): heavy overlap (many exact re-scans),
              # k below one CTA's half, a single partial tile (the second CTA of the pair idles), odd tile counts
              (128 * 7 + 5, 128, 200, 20, 1.0, True), (100, 64, 256, 4, 30.0, False), (128 * 148 * 2 + 1, 64, 130, 130, 30.0, True),
@@ -498,7 +498,7 @@ TCA_CASES = [(6000, 128, 256, 16, 30.0, False), (5000, 64, 1024, 40, 30.0, False
 @pytest.mark.parametrize("n,d,k,k_true,spread,shuffle", TCA_CASES)
 def test_tc_assign_path_matches_oracle(lb, ctx, oracle, n, d, k, k_true, spread, shuffle, passes):
     """passes: 0 = adaptive, 1 = one-product screening variant of the pair kernel, 3 = 3xTF32 (same results)."""
-    if passes and not (d in (64, 128) and k <= 4096):
+    if passes and not (d in (64, 128) and k <= 16384):
         pytest.skip("scoring passes only select between the variants of the pair kernel")
     dt = np.float32
     X, _ = blobs(n, d, k_true, dt, seed=n + k, spread=spread)
@@ -826,3 +826,23 @@ def test_f64_screened_kernel_full_fit_matches_oracle(lb, oracle):
     lab, dist = oracle.assign(X, model.centroids())
     assert (model.predict(X) == lab).all()
     assert (model.transform(X) == dist).all()
+
+
+def test_kmeans_para_candidate_histogram_through_the_pair_kernel(lb, monkeypatch):
+    """k-means|| (KM/init.rs:181-234): for f32 rows of 64 / 128 features the candidate weights (cluster_membership_counts,
+    :273-285) come from one tensor-core Lloyd iteration over the candidates; the certified labels make them identical to the
+    exact CUDA-core histogram, hence the same seeding for the same rng."""
+    X, _ = blobs(120000, 64, 40, np.float32, seed=17, spread=20.0)
+    X = X[np.random.default_rng(3).permutation(len(X))].copy()
+    out = []
+    for flag in ("1", "0"):
+        monkeypatch.setenv("LKM_PARA_TC", flag)
+        ctx = lb.Context(0)
+        params = (lb.KMeans.params_with_rng(40, lb.Xoshiro256Plus.seed_from_u64(5)).init_method(lb.KMeansInit.KMeansPara)
+                  .context(ctx).check())
+        out.append(params.init_centroids(lb.DatasetBase(X), ctx))
+        ctx.close()
+    assert (out[0] == out[1]).all()
+    # every blob is represented (statistical test of the reference, KM/init.rs:372-449, at this separation)
+    d2 = ((X[::1000, None, :] - out[0][None, :, :]) ** 2).sum(-1).min(1)
+    assert d2.max() < 64 * 9.0
