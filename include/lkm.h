@@ -190,16 +190,32 @@ lkm_status lkm_assign_f64(lkm_ctx* ctx, const double* centroids, uint64_t k, con
 
 /* -- FitWith::fit_with (KM/algorithm.rs:635-715): one mini-batch step on the
  * resident matrix.  has_model = 0 initialises from params (best of n_runs
- * seedings by dists.sum(), :659-678).  Returns LKM_OK when the shift is below
- * tolerance, LKM_NOT_CONVERGED otherwise; outputs are written in both cases. */
-lkm_status lkm_fit_with_f32(lkm_ctx* ctx, const lkm_params* p, lkm_rng rng, int has_model,
-                            float* centroids_inout, float* cluster_count_inout, float* inertia_out);
-lkm_status lkm_fit_with_f64(lkm_ctx* ctx, const lkm_params* p, lkm_rng rng, int has_model,
-                            double* centroids_inout, double* cluster_count_inout, double* inertia_out);
+ * seedings by dists.sum(), :659-678); the buffers are then n_clusters x d and
+ * n_clusters.  has_model = 1: centroids_inout is model_rows x model_cols and
+ * cluster_count_inout has model_rows entries — like the reference, the model's
+ * own shape is used and p->n_clusters is not looked at; model_cols must equal
+ * the batch's n_features (LKM_ERR_SHAPE otherwise).  Parameters are checked
+ * first (the ParamGuard blanket impl, src/param_guard.rs:75-86), then Hamerly
+ * is rejected (:640-644).  Returns LKM_OK when the shift is below tolerance,
+ * LKM_NOT_CONVERGED otherwise; outputs are written in both cases. */
+lkm_status lkm_fit_with_f32(lkm_ctx* ctx, const lkm_params* p, lkm_rng rng, int has_model, uint64_t model_rows,
+                            uint64_t model_cols, float* centroids_inout, float* cluster_count_inout,
+                            float* inertia_out);
+lkm_status lkm_fit_with_f64(lkm_ctx* ctx, const lkm_params* p, lkm_rng rng, int has_model, uint64_t model_rows,
+                            uint64_t model_cols, double* centroids_inout, double* cluster_count_inout,
+                            double* inertia_out);
 
 /* -- knobs that are not in the reference (all have defaults) --------------- */
 /* force an assignment path: -1 auto (default), 0 exact, 1 certified FMA, 2 tcgen05, 3 f32-screened f64 (lkm_f64s.cuh) */
 lkm_status lkm_set_assign_path(lkm_ctx* ctx, int path);
+/* parity-test aid: when on, every Lloyd kernel also writes the label each row was accumulated under in the LAST
+ * executed iteration (the `memberships` array of KM/algorithm.rs:304,316-322, which the fused kernels otherwise never
+ * materialise); lkm_get_labels copies the first n of them to the host (u32 per row, this rank's shard). */
+lkm_status lkm_set_keep_labels(lkm_ctx* ctx, int on);
+lkm_status lkm_get_labels(lkm_ctx* ctx, uint32_t* labels_out, uint64_t n);
+/* lkm_gen_blobs_* layout: 0 (default) = the contiguous blobs of datasets/src/generate.rs:28-58, 1 = every row draws
+ * its blob from a hash of its global index (unordered data; same noise) */
+lkm_status lkm_set_blob_layout(lkm_ctx* ctx, int layout);
 /* measurement hygiene for benchmarks: when bytes > 0 every Lloyd iteration is
  * timed with its own CUDA events and a scratch buffer of `bytes` is overwritten
  * between iterations (outside the timed spans) so that the observations are

@@ -71,6 +71,7 @@ PICK_EXACT, PICK_FAST = 0, 1
 UNTYPED_SYMBOLS = [
     "lkm_create", "lkm_destroy", "lkm_last_error", "lkm_stream", "lkm_synchronize", "lkm_version",
     "lkm_comm_unique_id", "lkm_comm_init", "lkm_set_shard", "lkm_set_assign_path", "lkm_set_l2_flush", "lkm_set_kernel_timing", "lkm_set_scoring_passes",
+    "lkm_set_keep_labels", "lkm_get_labels", "lkm_set_blob_layout",
 ]
 TYPED_SYMBOLS = [
     "lkm_set_data", "lkm_set_data_device", "lkm_gen_blobs", "lkm_get_data", "lkm_fit", "lkm_init",
@@ -97,6 +98,9 @@ lib.lkm_set_assign_path.argtypes = [_vp, _i32]
 lib.lkm_set_l2_flush.argtypes = [_vp, _u64]
 lib.lkm_set_kernel_timing.argtypes = [_vp, _i32]
 lib.lkm_set_scoring_passes.argtypes = [_vp, _i32]
+lib.lkm_set_keep_labels.argtypes = [_vp, _i32]
+lib.lkm_get_labels.argtypes = [_vp, C.POINTER(C.c_uint32), _u64]
+lib.lkm_set_blob_layout.argtypes = [_vp, _i32]
 
 for _sfx, _ct in (("f32", C.c_float), ("f64", C.c_double)):
     _fp = C.POINTER(_ct)
@@ -110,7 +114,7 @@ for _sfx, _ct in (("f32", C.c_float), ("f64", C.c_double)):
     getattr(lib, f"lkm_predict_{_sfx}").argtypes = [_vp, _fp, _u64, _fp, _u64, _u64, _i64, _u64p]
     getattr(lib, f"lkm_transform_{_sfx}").argtypes = [_vp, _fp, _u64, _fp, _u64, _u64, _i64, _fp]
     getattr(lib, f"lkm_assign_{_sfx}").argtypes = [_vp, _fp, _u64, _fp, _u64, _u64, _i64, _u64p, _fp]
-    getattr(lib, f"lkm_fit_with_{_sfx}").argtypes = [_vp, _pp, lkm_rng, _i32, _fp, _fp, _fp]
+    getattr(lib, f"lkm_fit_with_{_sfx}").argtypes = [_vp, _pp, lkm_rng, _i32, _u64, _u64, _fp, _fp, _fp]
 
 
 def sfx_of(dtype):

@@ -1,11 +1,16 @@
-"""Builds linfa_b200/liblkm.so (the C-ABI library of include/lkm.h) with nvcc for sm_100a.
+"""Builds the native libraries with nvcc for sm_100a, in-tree:
 
-In-tree build: the .so is git-ignored but travels to the GPU box with the snapshot.
+  linfa_b200/liblkm.so        the product: the C-ABI library of include/lkm.h
+  linfa_b200/liblkm_probe.so  the same sources + the tcgen05 probes / micro-benchmarks of csrc/lkm_probe.cuh
+                              (-DLKM_WITH_PROBES); loaded only by tests/test_gpu_tc_probe.py and tools/*.py
+
+The .so files are git-ignored but travel to the GPU box with the snapshot.
 """
 import os
 import shutil
 import subprocess
 import sys
+from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
@@ -13,11 +18,12 @@ SRC = [os.path.join(HERE, "csrc", "lkm_api.cu")]
 DEPS = [os.path.join(HERE, "csrc", f) for f in os.listdir(os.path.join(HERE, "csrc"))] + [
     os.path.join(ROOT, "include", "lkm.h")]
 OUT = os.environ.get("LKM_BUILD_OUT") or os.path.join(HERE, "liblkm.so")
+OUT_PROBE = os.path.join(HERE, "liblkm_probe.so")
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-lineinfo", "-O3", "-std=c++17",
-    "--use_fast_math=false" if False else "-fmad=true",  # contraction is controlled per-op with *_rn intrinsics
+    "-fmad=true",  # contraction is controlled per operation with the *_rn intrinsics where the reference's order matters
     "-Xcompiler", "-fPIC,-fvisibility=hidden,-O2,-Wall",
     "-shared", "-cudart", "static",
     "-Xptxas", "-v" if os.environ.get("LKM_PTXAS_V") else "-O3",
@@ -31,25 +37,37 @@ def nvcc():
     raise RuntimeError("nvcc not found")
 
 
-def needs_build():
-    if not os.path.exists(OUT):
+def needs_build(out=None):
+    out = out or OUT
+    if not os.path.exists(out):
         return True
-    t = os.path.getmtime(OUT)
+    t = os.path.getmtime(out)
     return any(os.path.getmtime(p) > t for p in DEPS + [os.path.abspath(__file__)])
 
 
-def build(force=False, verbose=False):
-    if not force and not needs_build():
-        return OUT
-    cmd = [nvcc()] + NVCC_FLAGS + os.environ.get("LKM_EXTRA_NVCC", "").split() + ["-o", OUT] + SRC + ["-ldl"]
+def _compile(out, extra, verbose):
+    cmd = [nvcc()] + NVCC_FLAGS + extra + os.environ.get("LKM_EXTRA_NVCC", "").split() + ["-o", out] + SRC + ["-ldl"]
     if verbose:
         print(" ".join(cmd))
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         sys.stderr.write(res.stdout + res.stderr)
-        raise RuntimeError("nvcc failed building liblkm.so")
+        raise RuntimeError(f"nvcc failed building {os.path.basename(out)}")
     if verbose or os.environ.get("LKM_PTXAS_V"):
         sys.stderr.write(res.stdout + res.stderr)
+    return out
+
+
+def build(force=False, verbose=False, probes=True):
+    jobs = []
+    if force or needs_build(OUT):
+        jobs.append((OUT, []))
+    if probes and (force or needs_build(OUT_PROBE)):
+        jobs.append((OUT_PROBE, ["-DLKM_WITH_PROBES"]))
+    if jobs:
+        with ThreadPoolExecutor(max_workers=len(jobs)) as ex:
+            for f in [ex.submit(_compile, o, e, verbose) for o, e in jobs]:
+                f.result()
     return OUT
 
 

@@ -22,11 +22,14 @@
 #include "lkm_kernels.cuh"
 #include "lkm_rand.hpp"
 #include "lkm_tc.cuh"
-#include "lkm_tc3.cuh"
+#include "lkm_tma.cuh"
 #include "lkm_tc4.cuh"
 #include "lkm_upd.cuh"
 #include "lkm_tc5.cuh"
 #include "lkm_f64s.cuh"
+#ifdef LKM_WITH_PROBES
+#include "lkm_probe.cuh"
+#endif
 
 #define LKM_EXPORT extern "C" __attribute__((visibility("default")))
 
@@ -96,8 +99,8 @@ struct lkm_ctx {
   uint64_t row_offset = 0, n_global = 0;
   int force_path = -1;
   int last_path = 0;
-  // fused tcgen05 kernel for d = 32: 4 = TMA + warp-specialised pipeline, 3 = TMA + three worker groups
-  // (both k <= 64; larger k falls back to 128), 128 / 256 / 544 = the earlier generations (LKM_TC_VARIANT)
+  // fused tcgen05 kernel for d = 32: 4 = TMA + warp-specialised pipeline (k <= 64), 128 = the shared-memory-operand
+  // kernel that also serves 64 < k <= 256 (LKM_TC_VARIANT=128 forces it for every k, an A/B knob)
   int tc_variant = 4;
   int tc5_passes_forced = 0;            // LKM_TC5_PASSES = 1 / 3 pins the screening / 3xTF32 variant of the pair kernel
   uint64_t tc5_hard_epoch = 0, tc5_easy_epoch = 0;
@@ -116,6 +119,9 @@ struct lkm_ctx {
   uint64_t flush_bytes = 0;
   unsigned long long bar_epoch = 0;   // rank_barrier_kernel (flushed-L2 benchmark mode, multi-GPU)
   int kernel_timing = 0;
+  int keep_labels = 0;     // lkm_set_keep_labels: the Lloyd kernels also write the per-row labels of the last iteration
+  uint64_t kept_labels_n = 0;
+  int blob_shuffled = 0;   // lkm_set_blob_layout
   DevBuf flushbuf, fin_sync, para_c2;
   int para_tc = 0;       // LKM_PARA_TC=1: k-means|| candidate histogram through one tensor-core Lloyd iteration (measured slower on the cfg4 shard: 6.4 vs 5.9 s)
   std::vector<cudaEvent_t> iter_events;
@@ -462,21 +468,6 @@ static lkm_status make_plain_tile_map(lkm_ctx* ctx, const float* dX, uint64_t n,
   return LKM_OK;
 }
 
-static cudaError_t launch_tc3(int kp, int grid, size_t smem, cudaStream_t s, const Tc3Args& arg, const CUtensorMap& map) {
-  cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3((unsigned)grid);
-  cfg.blockDim = dim3((unsigned)kT3Threads);
-  cfg.dynamicSmemBytes = smem;
-  cfg.stream = s;
-  cudaLaunchAttribute at[1];
-  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  at[0].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = at;
-  cfg.numAttrs = 1;
-  if (kp == 32) return cudaLaunchKernelEx(&cfg, lloyd_tc3_kernel<32>, arg, map);
-  return cudaLaunchKernelEx(&cfg, lloyd_tc3_kernel<64>, arg, map);
-}
-
 static int g_coop = 1;   // LKM_COOP=0: the in-kernel finalize relies on grid <= SM count alone (no cooperative-launch attribute)
 static cudaError_t launch_tc4(int kp, int passes, int grid, size_t smem, cudaStream_t s, const Tc4Args& arg, const CUtensorMap& map) {
   cudaLaunchConfig_t cfg{};
@@ -533,8 +524,8 @@ static lkm_status run_lloyd(lkm_ctx* ctx, F* dC2, uint64_t k, uint64_t max_iter,
   size_t tc_smem = 0;
   int tc4_nstages = 0, tc4_nstages1 = 0;   // ring depth of the 2- / 3-product variants and of the one-product variant
   size_t tc_smem1 = 0;
-  CUtensorMap tc3_map;
-  std::memset(&tc3_map, 0, sizeof(tc3_map));
+  CUtensorMap tc4_map;
+  std::memset(&tc4_map, 0, sizeof(tc4_map));
   if constexpr (std::is_same<F, float>::value) {
     pair32 = ctx->pair32 && ctx->tc5_enabled && ctx->upd_variant != 0 && (ctx->force_path == -1 || ctx->force_path == 2) && d == 32 &&
              k <= 64 && kd >= 512 && n >= 1 && (reinterpret_cast<uintptr_t>(dX) & 15) == 0 &&
@@ -546,32 +537,25 @@ static lkm_status run_lloyd(lkm_ctx* ctx, F* dC2, uint64_t k, uint64_t max_iter,
       while (tc_cols < tc_kp) tc_cols *= 2;
       const bool v4 = ctx->tc_variant == 4 && k <= 64 && n + kTcRows < (1ull << 31) &&
                       tc4_smem_bytes((int)k, tc_kp, 3) <= ctx->smem_optin - 1024;
-      const bool v3 = v4 || (ctx->tc_variant == 3 && k <= 64 && n + kTcRows < (1ull << 31) &&
-                             tc3_smem_bytes((int)k, tc_kp) <= ctx->smem_optin);
-      const bool v256 = ctx->tc_variant == 256;
-      const bool vws = ctx->tc_variant == 544 && tc_kp <= 64 && tcws_smem_bytes((int)k, tc_kp) <= ctx->smem_optin;
-      if (v3) {
-        if (v4) tc4_nstages = tc4_stages((int)k, tc_kp, ctx->smem_optin - 1024);
-        if (v4) tc4_nstages1 = tc4_stages((int)k, tc_kp, ctx->smem_optin - 1024, 1);
-        if (v4) if (const char* ev = std::getenv("LKM_TC4_STAGES")) {   // tuning aid
+      if (v4) {
+        tc4_nstages = tc4_stages((int)k, tc_kp, ctx->smem_optin - 1024);
+        tc4_nstages1 = tc4_stages((int)k, tc_kp, ctx->smem_optin - 1024, 1);
+        if (const char* ev = std::getenv("LKM_TC4_STAGES")) {   // tuning aid
           tc4_nstages = std::max(3, std::min(tc4_nstages, std::atoi(ev)));
           tc4_nstages1 = std::max(3, std::min(tc4_nstages1, std::atoi(ev)));
         }
-        if (v4) tc_smem1 = tc4_smem_bytes((int)k, tc_kp, tc4_nstages1, 1);
-        tc_smem = v4 ? tc4_smem_bytes((int)k, tc_kp, tc4_nstages) : tc3_smem_bytes((int)k, tc_kp);
-        const void* fn = v4 ? (tc_kp == 32 ? (const void*)lloyd_tc4_kernel<32, 3> : (const void*)lloyd_tc4_kernel<64, 3>)
-                            : (tc_kp == 32 ? (const void*)lloyd_tc3_kernel<32> : (const void*)lloyd_tc3_kernel<64>);
-        if (v4) {
-          const void* fn2 = tc_kp == 32 ? (const void*)lloyd_tc4_kernel<32, 2> : (const void*)lloyd_tc4_kernel<64, 2>;
-          CK(cudaFuncSetAttribute(fn2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem));
-          CK(cudaFuncSetAttribute(fn2, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
-          const void* fn1 = tc_kp == 32 ? (const void*)lloyd_tc4_kernel<32, 1> : (const void*)lloyd_tc4_kernel<64, 1>;
-          CK(cudaFuncSetAttribute(fn1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem1));
-          CK(cudaFuncSetAttribute(fn1, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
-        }
+        tc_smem1 = tc4_smem_bytes((int)k, tc_kp, tc4_nstages1, 1);
+        tc_smem = tc4_smem_bytes((int)k, tc_kp, tc4_nstages);
+        const void* fn = tc_kp == 32 ? (const void*)lloyd_tc4_kernel<32, 3> : (const void*)lloyd_tc4_kernel<64, 3>;
+        const void* fn2 = tc_kp == 32 ? (const void*)lloyd_tc4_kernel<32, 2> : (const void*)lloyd_tc4_kernel<64, 2>;
+        CK(cudaFuncSetAttribute(fn2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem));
+        CK(cudaFuncSetAttribute(fn2, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
+        const void* fn1 = tc_kp == 32 ? (const void*)lloyd_tc4_kernel<32, 1> : (const void*)lloyd_tc4_kernel<64, 1>;
+        CK(cudaFuncSetAttribute(fn1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem1));
+        CK(cudaFuncSetAttribute(fn1, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
         CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem));
         CK(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
-        CKS(make_row_tile_map(ctx, dX, n, tc3_map));
+        CKS(make_row_tile_map(ctx, dX, n, tc4_map));
         // max row norm of the resident matrix (cached for owned data; external pointers are rescanned)
         if (!ctx->own_X || ctx->xmax2_epoch != ctx->data_epoch) {
           CK(ctx->xmax2.ensure(16));
@@ -584,24 +568,24 @@ static lkm_status run_lloyd(lkm_ctx* ctx, F* dC2, uint64_t k, uint64_t max_iter,
         const uint64_t n_tiles = (n + kTcRows - 1) / kTcRows;
         tc_grid = (int)std::min<uint64_t>(n_tiles, (uint64_t)ctx->sm_count);
         use_tc = true;
-        tc_threads = v4 ? kT4Threads : kT3Threads;
+        tc_threads = kT4Threads;
       } else {
-      tc_smem = vws ? tcws_smem_bytes((int)k, tc_kp) : (v256 ? tc256_smem_bytes((int)k, tc_kp, 1) : tc_smem_bytes((int)k, tc_kp, 1));
-      if (tc_smem <= ctx->smem_optin) {
-        const void* fn = vws ? (const void*)lloyd_tcws_kernel : (v256 ? (const void*)lloyd_tc256_kernel : (const void*)lloyd_tc_kernel);
-        CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem));
-        CK(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
-        // with the carve-out at its maximum, 228 KB per SM hold floor(228K / (dynamic + static + 1K reserved)) CTAs
-        int occ = (int)((228 * 1024) / (tc_smem + 2048));
-        occ = std::min(occ, vws ? 1 : 2);      // register file: two CTAs per SM (one for the 544-thread kernel)
-        occ = std::min(occ, 512 / tc_cols);    // TMEM columns per SM
-        if (occ >= 1) {
-          const uint64_t n_tiles = (n + kTcRows - 1) / kTcRows;
-          tc_grid = (int)std::min<uint64_t>(n_tiles, (uint64_t)ctx->sm_count * occ);
-          use_tc = true;
-          tc_threads = vws ? kWsThreads : (v256 ? 256 : 128);
+        // 64 < k <= 256: tcgen05 3xTF32 from shared-memory operands, 128 threads, two CTAs per SM
+        tc_smem = tc_smem_bytes((int)k, tc_kp, 1);
+        if (tc_smem <= ctx->smem_optin) {
+          CK(cudaFuncSetAttribute(lloyd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem));
+          CK(cudaFuncSetAttribute(lloyd_tc_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
+          // with the carve-out at its maximum, 228 KB per SM hold floor(228K / (dynamic + static + 1K reserved)) CTAs
+          int occ = (int)((228 * 1024) / (tc_smem + 2048));
+          occ = std::min(occ, 2);                // register file: two CTAs per SM
+          occ = std::min(occ, 512 / tc_cols);    // TMEM columns per SM
+          if (occ >= 1) {
+            const uint64_t n_tiles = (n + kTcRows - 1) / kTcRows;
+            tc_grid = (int)std::min<uint64_t>(n_tiles, (uint64_t)ctx->sm_count * occ);
+            use_tc = true;
+            tc_threads = 128;
+          }
         }
-      }
       }
     }
     if (ctx->force_path == 2 && !use_tc && !pair32) return fail(ctx, LKM_ERR_UNSUPPORTED, "tcgen05 path needs f32, d = 32, k <= 256");
@@ -796,6 +780,14 @@ static lkm_status run_lloyd(lkm_ctx* ctx, F* dC2, uint64_t k, uint64_t max_iter,
   }
   CK(ctx->counts_out.ensure(k * 8));
   CK(ctx->state.ensure(sizeof(LloydState)));
+  // lkm_set_keep_labels: the fused kernels also write the label every row was accumulated under (the two-pass shapes
+  // always do: their update pass reads them)
+  uint32_t* dbg_labels = nullptr;
+  if (ctx->keep_labels) {
+    CK(ctx->labels.ensure((n + 256) * 4));
+    dbg_labels = ctx->labels.as<uint32_t>();
+  }
+  ctx->kept_labels_n = (ctx->keep_labels || !pf.fused) ? n : 0;
   const size_t L = kd + k + 1;
   if (ctx->world > 1) {
     CK(ctx->gather.ensure((size_t)ctx->world * L * 8));
@@ -865,7 +857,7 @@ static lkm_status run_lloyd(lkm_ctx* ctx, F* dC2, uint64_t k, uint64_t max_iter,
           TcArgs ta{};
           ta.X = dX; ta.n = n; ta.k = (int)k; ta.kp = tc_kp; ta.tcols = tc_cols; ta.C = Ccur;
           ta.part_sums = ctx->part_sums.as<float>(); ta.part_counts = ctx->part_counts.as<uint32_t>();
-          ta.part_inertia = ctx->part_inertia.as<double>(); ta.state = dstate; ta.accumulate = 1;
+          ta.part_inertia = ctx->part_inertia.as<double>(); ta.state = dstate; ta.accumulate = 1; ta.labels = dbg_labels;
           if (tc_threads == kT4Threads) {
             Tc4Args t4{};
             t4.X = dX; t4.n = n; t4.k = (int)k; t4.pack_mult = 64u; t4.stages = tc4_passes == 1 ? tc4_nstages1 : tc4_nstages; t4.C = Ccur; t4.xmax2_bits = ctx->xmax2.as<unsigned int>();
@@ -874,19 +866,13 @@ static lkm_status run_lloyd(lkm_ctx* ctx, F* dC2, uint64_t k, uint64_t max_iter,
             t4.prof = ctx->t4prof.as<long long>();
 #endif
             t4.part_sums = ta.part_sums; t4.part_counts = ta.part_counts; t4.part_inertia = ta.part_inertia; t4.state = dstate;
+            t4.labels_out = dbg_labels;
             if (fin_fused) {   // single GPU: the kernel's tail does the finalize step (no finalize_kernel launch)
               t4.fin_sync = ctx->fin_sync.as<unsigned int>(); t4.C_new = Cnext; t4.counts_out = ctx->counts_out.as<double>();
               t4.shift_part = ctx->shift_part.as<double>(); t4.tol = tol; t4.max_iter = max_iter;
             }
-            CK(launch_tc4(tc_kp, tc4_passes, tc_grid, tc4_passes == 1 ? tc_smem1 : tc_smem, ctx->stream, t4, tc3_map));
-          } else if (tc_threads == kT3Threads) {
-            Tc3Args t3{};
-            t3.X = dX; t3.n = n; t3.k = (int)k; t3.C = Ccur; t3.xmax2_bits = ctx->xmax2.as<unsigned int>();
-            t3.part_sums = ta.part_sums; t3.part_counts = ta.part_counts; t3.part_inertia = ta.part_inertia; t3.state = dstate;
-            CK(launch_tc3(tc_kp, tc_grid, tc_smem, ctx->stream, t3, tc3_map));
-          } else if (tc_threads == kWsThreads) CK(launch_pdl(lloyd_tcws_kernel, tc_grid, kWsThreads, tc_smem, ctx->stream, ta, true));
-          else if (tc_threads == 256) CK(launch_pdl(lloyd_tc256_kernel, tc_grid, 256, tc_smem, ctx->stream, ta, true));
-          else CK(launch_pdl(lloyd_tc_kernel, tc_grid, 128, tc_smem, ctx->stream, ta, true));
+            CK(launch_tc4(tc_kp, tc4_passes, tc_grid, tc4_passes == 1 ? tc_smem1 : tc_smem, ctx->stream, t4, tc4_map));
+          } else CK(launch_pdl(lloyd_tc_kernel, tc_grid, 128, tc_smem, ctx->stream, ta, true));
           ctx->launches++;
         }
       } else if (use_f6) {
@@ -894,7 +880,7 @@ static lkm_status run_lloyd(lkm_ctx* ctx, F* dC2, uint64_t k, uint64_t max_iter,
           f6::Args fa6{};
           fa6.X = dX; fa6.n = n; fa6.k = (int)k; fa6.C = Ccur;
           fa6.part_sums = ctx->part_sums.as<double>(); fa6.part_counts = ctx->part_counts.as<uint32_t>();
-          fa6.part_inertia = ctx->part_inertia.as<double>(); fa6.state = dstate; fa6.state_rw = dstate;
+          fa6.part_inertia = ctx->part_inertia.as<double>(); fa6.state = dstate; fa6.state_rw = dstate; fa6.labels_out = dbg_labels;
           void* kargs[] = {(void*)&fa6};
           CK(cudaLaunchKernel(f6_fn, dim3((unsigned)pf.grid), dim3(f6::kThreads), kargs, f6_smem, ctx->stream));
           CK(cudaGetLastError());
@@ -904,7 +890,7 @@ static lkm_status run_lloyd(lkm_ctx* ctx, F* dC2, uint64_t k, uint64_t max_iter,
         LloydArgs<F> a{};
         a.X = dX; a.n = n; a.d = (int)d; a.k = (int)k; a.C = Ccur;
         a.part_sums = ctx->part_sums.as<F>(); a.part_counts = ctx->part_counts.as<uint32_t>();
-        a.part_inertia = ctx->part_inertia.as<double>(); a.state = dstate;
+        a.part_inertia = ctx->part_inertia.as<double>(); a.state = dstate; a.labels = dbg_labels;
         a.n_subsets = pf.n_subsets; a.x_stride = pf.x_stride; a.kc = pf.kc; a.chunk_base = 0; a.chunk_rows = (int)k;
         a.vec = pf.vec; a.tpr = pf.tpr; a.certified = pf.certified; a.state_rw = dstate;
         CK((launch_lloyd<F, MODE_FUSED>(a, pf.grid, pf.smem, ctx->stream)));
@@ -1878,7 +1864,7 @@ static lkm_status gen_blobs_impl(lkm_ctx* ctx, uint64_t n, uint64_t d, uint64_t 
   CK(cudaMemcpyAsync(ctx->tmpc.p, centres, n_blobs * d * sizeof(F), cudaMemcpyHostToDevice, ctx->stream));
   if (n) {
     gen_blobs_kernel<F><<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(ctx->xbuf.as<F>(), n, (int)d, n_blobs, ctx->tmpc.as<F>(),
-                                                                   sigma, seed, row_offset, n_global ? n_global : n);
+                                                                   sigma, seed, row_offset, n_global ? n_global : n, ctx->blob_shuffled);
     CK(cudaGetLastError());
   }
   CK(cudaStreamSynchronize(ctx->stream));
@@ -1900,16 +1886,20 @@ template <typename F> static lkm_status get_data_impl(lkm_ctx* ctx, uint64_t row
 
 // FitWith::fit_with (KM/algorithm.rs:635-715)
 template <typename F>
-static lkm_status fit_with_impl(lkm_ctx* ctx, const lkm_params* p, lkm_rng rng_in, int has_model, F* C_inout,
-                                F* counts_inout, F* inertia_out) {
+static lkm_status fit_with_impl(lkm_ctx* ctx, const lkm_params* p, lkm_rng rng_in, int has_model, uint64_t model_rows,
+                                uint64_t model_cols, F* C_inout, F* counts_inout, F* inertia_out) {
   if (!p || !C_inout || !counts_inout || !inertia_out) return fail(ctx, LKM_ERR_INVALID_ARG, "null argument");
+  // the ParamGuard blanket impl (src/param_guard.rs:75-86) checks the parameters before fit_with runs its own test
+  CKS(check_params(ctx, p, true));
   if (p->algorithm == LKM_ALGO_HAMERLY)
     return fail(ctx, LKM_ERR_INCREMENTAL_HAMERLY, "only KMeansAlgorithm::Lloyd is supported by fit_with");
-  CKS(check_params(ctx, p, true));
   if (ctx->elem != (int)sizeof(F) || !ctx->X) return fail(ctx, LKM_ERR_NO_DATA, "no resident data of this type");
   if (ctx->world > 1) return fail(ctx, LKM_ERR_UNSUPPORTED, "fit_with is single-GPU");
   CK(cudaSetDevice(ctx->device));
-  const uint64_t k = p->n_clusters, n = ctx->n, d = ctx->d, kd = k * d;
+  // with a model the reference never looks at n_clusters: the model's own shape rules (KM/algorithm.rs:680-690)
+  if (has_model && (model_rows == 0 || model_cols != ctx->d))
+    return fail(ctx, LKM_ERR_SHAPE, "model centroids must be (rows > 0) x n_features of the batch");
+  const uint64_t k = has_model ? model_rows : p->n_clusters, n = ctx->n, d = ctx->d, kd = k * d;
   const F* dX = reinterpret_cast<const F*>(ctx->X);
   HostRng rng{rng_in};
   CK(ctx->cbuf.ensure(2 * kd * sizeof(F)));
@@ -2068,6 +2058,28 @@ LKM_EXPORT lkm_status lkm_set_scoring_passes(lkm_ctx* ctx, int passes) {
   return LKM_OK;
 }
 
+LKM_EXPORT lkm_status lkm_set_keep_labels(lkm_ctx* ctx, int on) {
+  if (!ctx) return LKM_ERR_INVALID_ARG;
+  ctx->keep_labels = on ? 1 : 0;
+  return LKM_OK;
+}
+
+LKM_EXPORT lkm_status lkm_get_labels(lkm_ctx* ctx, uint32_t* labels_out, uint64_t n) {
+  if (!ctx || !labels_out) return LKM_ERR_INVALID_ARG;
+  if (n == 0) return LKM_OK;
+  if (n > ctx->kept_labels_n || !ctx->labels.p) return fail(ctx, LKM_ERR_NO_DATA, "no labels kept: call lkm_set_keep_labels before the fit");
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaMemcpyAsync(labels_out, ctx->labels.p, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return LKM_OK;
+}
+
+LKM_EXPORT lkm_status lkm_set_blob_layout(lkm_ctx* ctx, int layout) {
+  if (!ctx || layout < 0 || layout > 1) return LKM_ERR_INVALID_ARG;
+  ctx->blob_shuffled = layout;
+  return LKM_OK;
+}
+
 LKM_EXPORT lkm_status lkm_set_l2_flush(lkm_ctx* ctx, uint64_t bytes) {
   if (!ctx) return LKM_ERR_INVALID_ARG;
   ctx->flush_bytes = bytes;
@@ -2167,14 +2179,17 @@ LKM_EXPORT lkm_status lkm_set_shard(lkm_ctx* ctx, uint64_t row_offset, uint64_t 
     return assign_impl<F>(ctx, centroids, k, x, n, d, row_stride, labels_out, min_sq_dist_out);                        \
   }                                                                                                                    \
   LKM_EXPORT lkm_status lkm_fit_with_##SFX(lkm_ctx* ctx, const lkm_params* p, lkm_rng rng, int has_model,              \
-                                           F* centroids_inout, F* cluster_count_inout, F* inertia_out) {               \
+                                           uint64_t model_rows, uint64_t model_cols, F* centroids_inout,               \
+                                           F* cluster_count_inout, F* inertia_out) {                                   \
     if (!ctx) return LKM_ERR_INVALID_ARG;                                                                              \
-    return fit_with_impl<F>(ctx, p, rng, has_model, centroids_inout, cluster_count_inout, inertia_out);                \
+    return fit_with_impl<F>(ctx, p, rng, has_model, model_rows, model_cols, centroids_inout, cluster_count_inout,     \
+                            inertia_out);                                                                              \
   }
 
 LKM_TYPED(float, f32)
 LKM_TYPED(double, f64)
 
+#ifdef LKM_WITH_PROBES
 // ---- development probes (not part of include/lkm.h) ---------------------------------------
 // S[128 x n_c] = X[128 x 32] * C[n_c x 32]^T through the tcgen05 3xTF32 building blocks.
 LKM_EXPORT int lkm_debug_tc_scores(lkm_ctx* ctx, const float* x, const float* c, int n_c, float* s_out) {
@@ -2320,3 +2335,4 @@ LKM_EXPORT int lkm_debug_tc_ts(lkm_ctx* ctx, const float* x, const float* c, flo
   if (hst != 0) return fail(ctx, LKM_ERR_CUDA, "TS probe: timeout");
   return LKM_OK;
 }
+#endif  // LKM_WITH_PROBES

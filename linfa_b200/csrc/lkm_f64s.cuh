@@ -45,6 +45,7 @@ struct Args {
   double* part_inertia;     // [grid]
   const LloydState* state;
   LloydState* state_rw;     // fallback_rows += rows that needed the exact re-scan
+  uint32_t* labels_out;     // optional (lkm_set_keep_labels): label of every row, for the parity tests
 };
 
 template <int D, int RPT> __host__ __device__ constexpr int stage_bytes() { return 32 * RPT * D * 8 + (32 * RPT * D * 8 / 128) * 16; }
@@ -311,6 +312,7 @@ __global__ void __launch_bounds__(kThreads, RPT == 1 ? 3 : 2) lloyd_f64s_kernel(
         inert += dist;
       }
       labs[r] = ok ? bi : -1;
+      if (a.labels_out != nullptr && ok) a.labels_out[row0 + (unsigned)(r * 32 + lane)] = (uint32_t)bi;
     }
     // ---- update walk: lane = (feature f, row group h), rows h, h + H, ... of the tile ----
     const int lab_t = __shfl_sync(full, labs[0], 0);

@@ -697,7 +697,9 @@ __device__ __forceinline__ double unit_open(unsigned long long bits) {  // (0,1)
 template <typename F>
 __global__ void gen_blobs_kernel(F* __restrict__ X, unsigned long long n, int d, unsigned long long n_blobs,
                                  const F* __restrict__ centres, F sigma, unsigned long long seed,
-                                 unsigned long long row_offset, unsigned long long n_global) {
+                                 unsigned long long row_offset, unsigned long long n_global, int shuffled) {
+  // shuffled != 0: every row draws its blob from a hash of its global index instead of the contiguous
+  // generate.rs layout (same noise): what real, unordered data looks like to the update path
   const unsigned long long total = n * (unsigned long long)d;
   const unsigned long long m = n_global / n_blobs;
   for (unsigned long long e = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; e < total;
@@ -706,6 +708,7 @@ __global__ void gen_blobs_kernel(F* __restrict__ X, unsigned long long n, int d,
     const unsigned long long gr = row_offset + r;
     unsigned long long b = m ? gr / m : 0;
     if (b >= n_blobs) b = n_blobs - 1;
+    if (shuffled) b = mix64(seed ^ 0x5bd1e995u ^ mix64(~gr)) % n_blobs;
     const unsigned long long ctr = gr * (unsigned long long)d + j;
     const unsigned long long h1 = mix64(seed ^ mix64(2 * ctr)), h2 = mix64(seed ^ mix64(2 * ctr + 1));
     const double u1 = unit_open(h1), u2 = unit_open(h2);

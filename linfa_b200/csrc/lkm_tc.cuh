@@ -111,212 +111,6 @@ __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
 }
 
 }  // namespace tc
-
-// ---------------------------------------------------------------------------------------------
-// Debug / validation kernel: S[128 x N] = X[128 x 32] * C[N x 32]^T by 3xTF32 on tcgen05, one
-// CTA of 128 threads.  status[0] = 0 ok, 1 = mbarrier wait timed out.
-// ---------------------------------------------------------------------------------------------
-template <int N>
-__global__ void __launch_bounds__(128) tc_scores_debug_kernel(const float* __restrict__ X, const float* __restrict__ Cn,
-                                                              float* __restrict__ S, int* __restrict__ status) {
-  static_assert(N % 16 == 0 && N >= 16 && N <= 256, "UMMA N for M = 128");
-  extern __shared__ __align__(1024) unsigned char smem[];
-  // [A_hi 16K][A_lo 16K][B_hi N*128][B_lo N*128]
-  unsigned char* a_hi = smem;
-  unsigned char* a_lo = smem + 16384;
-  unsigned char* b_hi = smem + 32768;
-  unsigned char* b_lo = b_hi + N * 128;
-  __shared__ __align__(8) uint64_t bar;
-  __shared__ uint32_t tmem_slot;
-  const int t = threadIdx.x, warp = t >> 5;
-  constexpr uint32_t TCOLS = N < 32 ? 32 : (N <= 32 ? 32 : (N <= 64 ? 64 : (N <= 128 ? 128 : 256)));
-
-  if (warp == 0) tc::tmem_alloc(&tmem_slot, TCOLS);
-  if (t == 0) { tc::mbar_init(&bar, 1); tc::fence_mbar_init(); }
-  // stage operands: thread t owns row t of X (and row t of C if t < N)
-  for (int c = 0; c < 8; ++c) {
-    const float4 v = reinterpret_cast<const float4*>(X + (size_t)t * 32)[c];
-    float4 h, l;
-    tc::split_tf32(v.x, h.x, l.x); tc::split_tf32(v.y, h.y, l.y);
-    tc::split_tf32(v.z, h.z, l.z); tc::split_tf32(v.w, h.w, l.w);
-    const uint32_t o = tc::sw128_offset(t, c);
-    *reinterpret_cast<float4*>(a_hi + o) = h;
-    *reinterpret_cast<float4*>(a_lo + o) = l;
-  }
-  for (int r = t; r < N; r += 128) {
-    for (int c = 0; c < 8; ++c) {
-      const float4 v = reinterpret_cast<const float4*>(Cn + (size_t)r * 32)[c];
-      float4 h, l;
-      tc::split_tf32(v.x, h.x, l.x); tc::split_tf32(v.y, h.y, l.y);
-      tc::split_tf32(v.z, h.z, l.z); tc::split_tf32(v.w, h.w, l.w);
-      const uint32_t o = tc::sw128_offset(r, c);
-      *reinterpret_cast<float4*>(b_hi + o) = h;
-      *reinterpret_cast<float4*>(b_lo + o) = l;
-    }
-  }
-  tc::fence_async_smem();   // generic-proxy stores -> visible to the tensor core (async proxy)
-  tc::tc_fence_before();
-  __syncthreads();
-  tc::tc_fence_after();
-  const uint32_t tmem = tmem_slot;
-  if (t == 0) {
-    constexpr uint32_t idesc = tc::idesc_tf32(128, N);
-    const uint32_t sa_hi = tc::smem_u32(a_hi), sa_lo = tc::smem_u32(a_lo), sb_hi = tc::smem_u32(b_hi), sb_lo = tc::smem_u32(b_lo);
-    uint32_t acc = 0;
-    for (int pass = 0; pass < 3; ++pass) {
-      const uint32_t sa = pass == 2 ? sa_lo : sa_hi;
-      const uint32_t sb = pass == 1 ? sb_lo : sb_hi;
-      for (int ks = 0; ks < 4; ++ks) {  // K = 8 TF32 (32 bytes) per instruction
-        tc::mma_tf32(tmem, tc::smem_desc_sw128(sa + ks * 32), tc::smem_desc_sw128(sb + ks * 32), idesc, acc);
-        acc = 1;
-      }
-    }
-    tc::mma_commit(&bar);
-  }
-  const bool ok = tc::mbar_wait(&bar, 0);
-  tc::tc_fence_after();
-  if (!ok) {
-    if (t == 0) status[0] = 1;
-  } else {
-    // warp w reads TMEM lanes 32w..32w+31 (= rows), 32 columns at a time
-    for (int c0 = 0; c0 < N; c0 += 32) {
-      uint32_t r[32];
-      tc::tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, r);
-      tc::tmem_ld_wait();
-#pragma unroll
-      for (int j = 0; j < 32; ++j)
-        if (c0 + j < N) S[(size_t)t * N + c0 + j] = __uint_as_float(r[j]);
-    }
-    if (t == 0) status[0] = 0;
-  }
-  tc::tc_fence_before();
-  __syncthreads();
-  if (warp == 0) tc::tmem_dealloc(tmem, TCOLS);
-}
-
-// ---------------------------------------------------------------------------------------------
-// Probe for the tensor-core centroid accumulation: D2[M x 32] = onehot^T[M x 128] * X[128 x 32]
-// (M = 64 or 128 clusters).  A = one-hot, MN-major (cluster contiguous per data row), groups of 32
-// clusters 16 KB apart; B = the X tile as staged for the assignment MMA, read MN-major (feature
-// contiguous per data row).  Dumps all 128 TMEM lanes x 32 columns so that the host can learn the
-// accumulator layout.  status: 0 ok, 1 timeout.
-// ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint64_t smem_desc_mn_sw128(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-  uint64_t d = 0;
-  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
-  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;   // stride between 128-byte MN groups
-  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;   // stride between 8-row K groups
-  d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;
-  return d;
-}
-__host__ __device__ constexpr uint32_t idesc_tf32_mn(uint32_t m, uint32_t n) {
-  return (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((n >> 3) << 17) | ((m >> 4) << 24);
-}
-
-template <int M>
-__global__ void __launch_bounds__(128) tc_accum_debug_kernel(const float* __restrict__ X, const int* __restrict__ labels,
-                                                             float* __restrict__ dump, int* __restrict__ status) {
-  extern __shared__ __align__(16) unsigned char smem_unaligned[];
-  unsigned char* smem = smem_unaligned + ((1024u - (tc::smem_u32(smem_unaligned) & 1023u)) & 1023u);
-  unsigned char* xt = smem;              // [128 rows][128 B] SW128
-  unsigned char* oh = smem + 16384;      // M/32 groups of [128 rows][128 B] SW128
-  __shared__ __align__(8) uint64_t bar;
-  __shared__ uint32_t tmem_slot;
-  const int t = threadIdx.x, warp = t >> 5;
-  if (warp == 0) tc::tmem_alloc(&tmem_slot, 32);
-  if (t == 0) { tc::mbar_init(&bar, 1); tc::fence_mbar_init(); }
-  for (int i = t; i < (M / 32) * 16384 / 16; i += 128) reinterpret_cast<int4*>(oh)[i] = make_int4(0, 0, 0, 0);
-  for (int c = 0; c < 8; ++c)
-    *reinterpret_cast<float4*>(xt + tc::sw128_offset(t, c)) = reinterpret_cast<const float4*>(X + (size_t)t * 32)[c];
-  __syncthreads();
-  {
-    const int lab = labels[t];
-    const uint32_t g = (uint32_t)lab >> 5, w = (uint32_t)lab & 31u;
-    *reinterpret_cast<float*>(oh + g * 16384u + tc::sw128_offset(t, w >> 2) + (w & 3u) * 4u) = 1.0f;
-  }
-  tc::fence_async_smem();
-  tc::tc_fence_before();
-  __syncthreads();
-  tc::tc_fence_after();
-  const uint32_t tmem = tmem_slot;
-  if (t == 0) {
-    constexpr uint32_t idesc = idesc_tf32_mn(M, 32);
-    uint32_t acc = 0;
-    for (int ks = 0; ks < 16; ++ks) {  // 8 data rows per MMA
-      tc::mma_tf32(tmem, smem_desc_mn_sw128(tc::smem_u32(oh) + ks * 1024, 16384, 1024),
-                   smem_desc_mn_sw128(tc::smem_u32(xt) + ks * 1024, 16384, 1024), idesc, acc);
-      acc = 1;
-    }
-    tc::mma_commit(&bar);
-  }
-  const bool ok = tc::mbar_wait(&bar, 0);
-  tc::tc_fence_after();
-  if (ok) {
-    uint32_t r[32];
-    tc::tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16), r);
-    tc::tmem_ld_wait();
-#pragma unroll
-    for (int j = 0; j < 32; ++j) dump[(size_t)t * 32 + j] = __uint_as_float(r[j]);
-  }
-  if (t == 0) status[0] = ok ? 0 : 1;
-  tc::tc_fence_before();
-  __syncthreads();
-  if (warp == 0) tc::tmem_dealloc(tmem, 32);
-}
-
-// Raw UMMA probe: the host supplies byte images of the A and B operand regions, the two
-// descriptors (without start address), the per-k-step byte advance and the instruction
-// descriptor; the kernel copies the images to 1024-aligned shared memory, issues `ksteps` MMAs and
-// dumps 128 TMEM lanes x `ncols` columns.  Used to pin down operand layouts from Python.
-__global__ void __launch_bounds__(128) umma_raw_probe_kernel(const unsigned char* __restrict__ a_img, int a_bytes,
-                                                             const unsigned char* __restrict__ b_img, int b_bytes,
-                                                             unsigned long long a_desc_hi, unsigned long long b_desc_hi,
-                                                             int a_step, int b_step, unsigned int idesc, int ksteps,
-                                                             int ncols, float* __restrict__ dump, int* __restrict__ status) {
-  extern __shared__ __align__(16) unsigned char smem_unaligned[];
-  unsigned char* smem = smem_unaligned + ((1024u - (tc::smem_u32(smem_unaligned) & 1023u)) & 1023u);
-  unsigned char* sa = smem;
-  unsigned char* sb = smem + ((a_bytes + 1023) & ~1023);
-  __shared__ __align__(8) uint64_t bar;
-  __shared__ uint32_t tmem_slot;
-  const int t = threadIdx.x, warp = t >> 5;
-  if (warp == 0) tc::tmem_alloc(&tmem_slot, 256);
-  if (t == 0) { tc::mbar_init(&bar, 1); tc::fence_mbar_init(); }
-  for (int i = t; i < a_bytes / 16; i += 128) reinterpret_cast<int4*>(sa)[i] = reinterpret_cast<const int4*>(a_img)[i];
-  for (int i = t; i < b_bytes / 16; i += 128) reinterpret_cast<int4*>(sb)[i] = reinterpret_cast<const int4*>(b_img)[i];
-  tc::fence_async_smem();
-  tc::tc_fence_before();
-  __syncthreads();
-  tc::tc_fence_after();
-  const uint32_t tmem = tmem_slot;
-  if (t == 0) {
-    uint32_t acc = 0;
-    for (int ks = 0; ks < ksteps; ++ks) {
-      const uint64_t da = a_desc_hi | (uint64_t)(((tc::smem_u32(sa) + ks * a_step) & 0x3FFFFu) >> 4);
-      const uint64_t db = b_desc_hi | (uint64_t)(((tc::smem_u32(sb) + ks * b_step) & 0x3FFFFu) >> 4);
-      tc::mma_tf32(tmem, da, db, idesc, acc);
-      acc = 1;
-    }
-    tc::mma_commit(&bar);
-  }
-  const bool ok = tc::mbar_wait(&bar, 0);
-  tc::tc_fence_after();
-  if (ok) {
-    for (int c0 = 0; c0 < ncols; c0 += 32) {
-      uint32_t r[32];
-      tc::tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + c0, r);
-      tc::tmem_ld_wait();
-#pragma unroll
-      for (int j = 0; j < 32; ++j) dump[(size_t)t * ncols + c0 + j] = __uint_as_float(r[j]);
-    }
-  }
-  if (t == 0) status[0] = ok ? 0 : 1;
-  tc::tc_fence_before();
-  __syncthreads();
-  if (warp == 0) tc::tmem_dealloc(tmem, 256);
-}
-
 // =============================================================================================
 // Fused Lloyd iteration on tensor cores, f32, d = 32 (one 128-byte SW128 atom per row).
 //
@@ -705,11 +499,11 @@ __global__ void __launch_bounds__(128, 2) lloyd_tc_kernel(const TcArgs a) {
 }
 
 // =============================================================================================
-// 256-thread variant of the fused tensor-core Lloyd iteration (same arithmetic, same outputs).
-// Two threads share a row in the score epilogue (each scans half of the TMEM columns), the next
-// tile is prefetched with cp.async straight into the (idle) A_hi buffer and split in place, and in
-// uniform-label tiles the two halves of the CTA each sum 16 of a subset's 32 rows.  16 warps per
-// SM at two CTAs per SM.
+// Tensor-core ASSIGNMENT for wide rows / many clusters (f32, d = 32 * ka with ka in {1, 2, 4}, any k):
+// labels and exact min distances to global memory; the centroid update then runs as the
+// cluster-chunked MODE_UPDATE pass of lloyd_kernel.  Centroids are pre-split once per iteration
+// into TF32 hi / lo operand tiles (tc_prep_centroids_kernel) and streamed from L2 in chunks of 64;
+// the 128-row X tile stays resident as hi / lo (x = hi + lo exactly, lo is kept unmasked).
 // =============================================================================================
 __device__ __forceinline__ void cp_async16_zfill(void* smem_dst, const void* gsrc, bool valid) {
   const uint32_t d = tc::smem_u32(smem_dst);
@@ -719,391 +513,6 @@ __device__ __forceinline__ void cp_async16_zfill(void* smem_dst, const void* gsr
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
-__host__ __device__ inline size_t tc256_smem_bytes(int k, int kp, int accumulate) {
-  size_t b = 0;
-  b += 16384 * 2;                 // A_hi (also the cp.async landing buffer), A_lo
-  b += (size_t)kp * 128 * 2;      // B_hi, B_lo
-  b += 16384;                     // raw tile
-  b += (size_t)k * kTcCStride * 4;  // raw centroids
-  b += (size_t)kp * 4;            // ||c||^2
-  if (accumulate) {
-    b += (size_t)kTcSubsets * (k + 1) * 32 * 4;   // sums (+1 dummy row per subset)
-    b += (((size_t)k * 4) + 15) & ~(size_t)15;    // counts
-  }
-  b += kTcRows * 4 * 4 + 16;      // labels, subset-major labels, dists, flag list
-  b += kTcRows * 4 * 3;           // half-1 epilogue results (best, second, index)
-  b += kTcSubsets * 32 * 4;       // half-1 partial sums of the uniform-label path
-  return b + 1024;
-}
-
-__global__ void __launch_bounds__(256, 2) lloyd_tc256_kernel(const TcArgs a) {
-  pdl_launch_dependents();
-  pdl_wait();
-  if (a.state != nullptr && a.state->done) return;
-  extern __shared__ __align__(16) unsigned char smem_unaligned[];
-  unsigned char* smem = smem_unaligned + ((1024u - (tc::smem_u32(smem_unaligned) & 1023u)) & 1023u);
-  const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
-  const int half = t >> 7, row_t = t & 127;
-  const int k = a.k, kp = a.kp;
-  unsigned char* a_hi = smem;
-  unsigned char* a_lo = a_hi + 16384;
-  unsigned char* b_hi = a_lo + 16384;
-  unsigned char* b_lo = b_hi + (size_t)kp * 128;
-  unsigned char* raw = b_lo + (size_t)kp * 128;
-  float* rawc = reinterpret_cast<float*>(raw + 16384);
-  float* cn = rawc + (size_t)k * kTcCStride;
-  float* acc = cn + kp;
-  uint32_t* cnt = reinterpret_cast<uint32_t*>(acc + (a.accumulate ? (size_t)kTcSubsets * (k + 1) * 32 : 0));
-  uint32_t* labs = cnt + (a.accumulate ? ((k + 3) & ~3) : 0);
-  uint32_t* labs2 = labs + kTcRows;
-  float* dist_s = reinterpret_cast<float*>(labs2 + kTcRows);
-  uint32_t* flags = reinterpret_cast<uint32_t*>(dist_s + kTcRows);
-  float* ex_best = reinterpret_cast<float*>(flags + kTcRows + 4);
-  float* ex_second = ex_best + kTcRows;
-  int* ex_idx = reinterpret_cast<int*>(ex_second + kTcRows);
-  float* ex_part = reinterpret_cast<float*>(ex_idx + kTcRows);
-  double* red = reinterpret_cast<double*>(a_hi);  // only used after the last tile
-  __shared__ __align__(8) uint64_t bar;
-  __shared__ uint32_t tmem_slot;
-  __shared__ uint32_t n_flag;
-  __shared__ uint32_t cmax_bits;
-
-  if (warp == 0) tc::tmem_alloc(&tmem_slot, (uint32_t)a.tcols);
-  if (t == 0) { tc::mbar_init(&bar, 1); tc::fence_mbar_init(); n_flag = 0; cmax_bits = 0; }
-  __syncthreads();
-  for (int r = t; r < kp; r += 256) {
-    if (r < k) {
-      double nn = 0.0;
-#pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        const float4 v = __ldg(reinterpret_cast<const float4*>(a.C + (size_t)r * 32) + c);
-        float4 h, l;
-        tc::split_tf32(v.x, h.x, l.x); tc::split_tf32(v.y, h.y, l.y);
-        tc::split_tf32(v.z, h.z, l.z); tc::split_tf32(v.w, h.w, l.w);
-        const uint32_t o = tc::sw128_offset(r, c);
-        *reinterpret_cast<float4*>(b_hi + o) = h;
-        *reinterpret_cast<float4*>(b_lo + o) = l;
-        *reinterpret_cast<float4*>(rawc + r * kTcCStride + 4 * c) = v;
-        nn += (double)v.x * v.x + (double)v.y * v.y + (double)v.z * v.z + (double)v.w * v.w;
-      }
-      const float nf = (float)nn;
-      cn[r] = nf;
-      atomicMax(&cmax_bits, __float_as_uint(nf));  // a NaN norm wins the max and voids every certificate
-    } else {
-      const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        const uint32_t o = tc::sw128_offset(r, c);
-        *reinterpret_cast<float4*>(b_hi + o) = z;
-        *reinterpret_cast<float4*>(b_lo + o) = z;
-      }
-      cn[r] = INFINITY;
-    }
-  }
-  if (a.accumulate) {
-    for (int e = t; e < kTcSubsets * (k + 1) * 32; e += 256) acc[e] = 0.f;
-    for (int e = t; e < k; e += 256) cnt[e] = 0u;
-  }
-  const unsigned long long n_tiles = (a.n + kTcRows - 1) / kTcRows;
-  // chunk t + 256 i of a tile: row t/8 + 32 i, 16-byte chunk t%8; swizzled position st_off + 4096 i
-  const uint32_t st_off = tc::sw128_offset((uint32_t)(t >> 3), (uint32_t)(t & 7));
-  auto prefetch = [&](unsigned long long tile) {
-    const unsigned long long row0 = tile * kTcRows;
-    const int rows = (int)min((unsigned long long)kTcRows, a.n - row0);
-    const int4* g = reinterpret_cast<const int4*>(a.X + row0 * 32) + t;
-    const int my_row = t >> 3;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const bool valid = (my_row + 32 * i) < rows;
-      cp_async16_zfill(a_hi + st_off + 4096u * i, valid ? (const void*)(g + 256 * i) : (const void*)a.X, valid);
-    }
-    cp_async_commit();
-  };
-  if (blockIdx.x < n_tiles) prefetch(blockIdx.x);
-  tc::fence_async_smem();
-  tc::tc_fence_before();
-  __syncthreads();
-  tc::tc_fence_after();
-  const uint32_t tmem = tmem_slot;
-  const float cmax2 = __uint_as_float(cmax_bits);
-  const float cmax = sqrtf(cmax2) * 1.000001f;
-  const float eta = (3.f * 32.f + 12.f) * 2.3841858e-7f;
-  const float gamma = (32.f + 2.f) * 5.9604645e-8f;
-  const float m_a0 = 2.3841858e-7f * cmax2;
-  const float m_a1 = (4.f * eta + 4.7683716e-7f) * cmax;
-  const float m_g2 = 2.f * gamma;
-
-  const uint32_t row_off = (uint32_t)(row_t >> 3) * 1024u + (uint32_t)(row_t & 7) * 128u;
-  const uint32_t row_x = (uint32_t)(row_t & 7);
-  const int sub = (t >> 5) & 3, feat = t & 31;
-  const uint32_t acc_off_e = (uint32_t)sub * 128u + ((((uint32_t)feat >> 2) ^ (uint32_t)sub) << 4) + ((uint32_t)feat & 3u) * 4u;
-  const uint32_t acc_off_o = (uint32_t)(sub + 4) * 128u + ((((uint32_t)feat >> 2) ^ (uint32_t)(sub + 4)) << 4) + ((uint32_t)feat & 3u) * 4u;
-  float* my_acc = acc + (size_t)sub * (k + 1) * 32 + feat;
-  int cur_lab = k;
-  float cur_acc = 0.f;
-  double inert = 0.0;
-  unsigned int my_fallbacks = 0;
-  uint32_t parity = 0;
-  const uint32_t lane_base = ((uint32_t)((warp & 3) * 32)) << 16;
-  const int n_chunks = kp >> 5;
-
-  for (unsigned long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-    const unsigned long long row0 = tile * kTcRows;
-    const int rows = (int)min((unsigned long long)kTcRows, a.n - row0);
-    // ---- the tile has landed in A_hi: split it in place (raw copy, TF32 hi, lo) ----
-    cp_async_wait_all();
-    __syncthreads();
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const uint32_t o = st_off + 4096u * i;
-      const float4 v = *reinterpret_cast<const float4*>(a_hi + o);
-      float4 h, l;
-      h.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u); l.x = v.x - h.x;
-      h.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u); l.y = v.y - h.y;
-      h.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u); l.z = v.z - h.z;
-      h.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u); l.w = v.w - h.w;
-      *reinterpret_cast<float4*>(raw + o) = v;
-      *reinterpret_cast<float4*>(a_hi + o) = h;
-      *reinterpret_cast<float4*>(a_lo + o) = l;
-    }
-    tc::fence_async_smem();
-    tc::tc_fence_before();
-    __syncthreads();
-    if (t == 0) {
-      tc::tc_fence_after();
-      const uint32_t idesc = tc::idesc_tf32(128, (uint32_t)kp);
-      const uint32_t sa_hi = tc::smem_u32(a_hi), sa_lo = tc::smem_u32(a_lo), sb_hi = tc::smem_u32(b_hi), sb_lo = tc::smem_u32(b_lo);
-      uint32_t accf = 0;
-#pragma unroll
-      for (int pass = 0; pass < 3; ++pass) {
-        const uint32_t sa = pass == 2 ? sa_lo : sa_hi;
-        const uint32_t sb = pass == 1 ? sb_lo : sb_hi;
-#pragma unroll
-        for (int ks = 0; ks < 4; ++ks) {
-          tc::mma_tf32(tmem, tc::smem_desc_sw128(sa + ks * 32), tc::smem_desc_sw128(sb + ks * 32), idesc, accf);
-          accf = 1;
-        }
-      }
-      tc::mma_commit(&bar);
-    }
-    // ---- half 0: this thread's row (exact data) and its certification margin, while the MMA runs ----
-    float xr[32];
-    float margin = 0.f;
-    if (half == 0) {
-#pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        const float4 v = *reinterpret_cast<const float4*>(raw + row_off + (((uint32_t)c ^ row_x) << 4));
-        xr[4 * c] = v.x; xr[4 * c + 1] = v.y; xr[4 * c + 2] = v.z; xr[4 * c + 3] = v.w;
-      }
-      float xx0 = 0.f, xx1 = 0.f, xx2 = 0.f, xx3 = 0.f;
-#pragma unroll
-      for (int j = 0; j < 32; j += 4) {
-        xx0 = fmaf(xr[j], xr[j], xx0); xx1 = fmaf(xr[j + 1], xr[j + 1], xx1);
-        xx2 = fmaf(xr[j + 2], xr[j + 2], xx2); xx3 = fmaf(xr[j + 3], xr[j + 3], xx3);
-      }
-      const float xn = sqrtf((xx0 + xx1) + (xx2 + xx3)) * 1.000001f;
-      margin = 1.1f * (m_a0 + xn * m_a1 + m_g2 * (xn + cmax) * (xn + cmax));
-    }
-    const bool ok = tc::mbar_wait(&bar, parity);
-    parity ^= 1u;
-    tc::tc_fence_after();
-    if (!ok) {
-      if (t == 0 && a.state) atomicAdd(&a.state->fallback_rows, 1ull << 40);
-    }
-    // the tensor core is done with A_hi / A_lo: start fetching the next tile into A_hi
-    if (tile + gridDim.x < n_tiles) prefetch(tile + gridDim.x);
-    // ---- score epilogue: half h scans the 32-column chunks h, h+2, ... of this row ----
-    float best0 = INFINITY, second0 = INFINITY, best1 = INFINITY, second1 = INFINITY;
-    int idx0 = 0, idx1 = 1;
-    for (int cc = half; cc < n_chunks; cc += 2) {
-      const int c0 = cc << 5;
-      uint32_t r[32];
-      tc::tmem_ld32(tmem + lane_base + (uint32_t)c0, r);
-      tc::tmem_ld_wait();
-#pragma unroll
-      for (int j = 0; j < 32; j += 4) {
-        const float4 cn4 = *reinterpret_cast<const float4*>(cn + c0 + j);
-        const float w0 = fmaf(-2.f, __uint_as_float(r[j]), cn4.x);
-        const float w1 = fmaf(-2.f, __uint_as_float(r[j + 1]), cn4.y);
-        const float w2 = fmaf(-2.f, __uint_as_float(r[j + 2]), cn4.z);
-        const float w3 = fmaf(-2.f, __uint_as_float(r[j + 3]), cn4.w);
-        second0 = fminf(second0, fmaxf(w0, best0));
-        idx0 = (w0 < best0) ? (c0 + j) : idx0;
-        best0 = fminf(best0, w0);
-        second1 = fminf(second1, fmaxf(w1, best1));
-        idx1 = (w1 < best1) ? (c0 + j + 1) : idx1;
-        best1 = fminf(best1, w1);
-        second0 = fminf(second0, fmaxf(w2, best0));
-        idx0 = (w2 < best0) ? (c0 + j + 2) : idx0;
-        best0 = fminf(best0, w2);
-        second1 = fminf(second1, fmaxf(w3, best1));
-        idx1 = (w3 < best1) ? (c0 + j + 3) : idx1;
-        best1 = fminf(best1, w3);
-      }
-    }
-    float best, second;
-    int bidx;
-    if (best1 < best0 || (best1 == best0 && idx1 < idx0)) {
-      best = best1; bidx = idx1; second = fminf(second1, best0);
-    } else {
-      best = best0; bidx = idx0; second = fminf(second0, best1);
-    }
-    if (half == 1) { ex_best[row_t] = best; ex_second[row_t] = second; ex_idx[row_t] = bidx; }
-    tc::tc_fence_before();
-    __syncthreads();
-    if (half == 0) {
-      const float ob = ex_best[row_t], os = ex_second[row_t];
-      const int oi = ex_idx[row_t];
-      if (ob < best || (ob == best && oi < bidx)) { second = fminf(os, best); best = ob; bidx = oi; }
-      else { second = fminf(second, ob); }
-      const bool row_ok = row_t < rows;
-      const bool certified = (second - best) > margin;
-      if (row_ok) {
-        if (certified) {
-          const float* cw = rawc + bidx * kTcCStride;
-          float dacc = 0.f;
-#pragma unroll
-          for (int c = 0; c < 8; ++c) {
-            const float4 cv = *reinterpret_cast<const float4*>(cw + 4 * c);
-            float df;
-            df = __fsub_rn(cv.x, xr[4 * c]);     dacc = __fadd_rn(dacc, __fmul_rn(df, df));
-            df = __fsub_rn(cv.y, xr[4 * c + 1]); dacc = __fadd_rn(dacc, __fmul_rn(df, df));
-            df = __fsub_rn(cv.z, xr[4 * c + 2]); dacc = __fadd_rn(dacc, __fmul_rn(df, df));
-            df = __fsub_rn(cv.w, xr[4 * c + 3]); dacc = __fadd_rn(dacc, __fmul_rn(df, df));
-          }
-          labs[row_t] = (uint32_t)bidx;
-          dist_s[row_t] = dacc;
-        } else {
-          const uint32_t p = atomicAdd(&n_flag, 1u);
-          flags[p] = (uint32_t)row_t;
-        }
-      }
-    }
-    __syncthreads();
-    const uint32_t nf = n_flag;
-    if (nf) {
-      for (uint32_t f = warp; f < nf; f += 8) {
-        const uint32_t row = flags[f];
-        float x2[32];
-#pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          const float4 v = *reinterpret_cast<const float4*>(raw + tc::sw128_offset(row, (uint32_t)c));
-          x2[4 * c] = v.x; x2[4 * c + 1] = v.y; x2[4 * c + 2] = v.z; x2[4 * c + 3] = v.w;
-        }
-        float fb = INFINITY;
-        int fi = -1;
-        int c = lane;
-        if (lane == 0) { fb = sqdist_reg<float, 32>(rawc, x2); fi = 0; c = 32; }
-        for (; c < k; c += 32) {
-          const float v = sqdist_reg<float, 32>(rawc + c * kTcCStride, x2);
-          if (v < fb) { fb = v; fi = c; }
-        }
-        combine_candidates<float>(32, fb, fi);
-        if (lane == 0) { labs[row] = (uint32_t)fi; dist_s[row] = fb; }
-      }
-      my_fallbacks += (t == 0) ? nf : 0u;
-      __syncthreads();
-      if (t == 0) n_flag = 0;
-    }
-    if (half == 0 && row_t < rows) {
-      const uint32_t lab = labs[row_t];
-      labs2[(row_t & 3) * 32 + (row_t >> 2)] = lab;
-      inert += (double)dist_s[row_t];
-      if (a.accumulate) atomicAdd(&cnt[lab], 1u);
-      if (a.labels) a.labels[row0 + row_t] = lab;
-      if (a.dists) a.dists[row0 + row_t] = dist_s[row_t];
-    }
-    if (a.accumulate) {
-      __syncthreads();  // labs2 complete
-      bool uniform = false;
-      uint32_t first = 0;
-      float part = 0.f;
-      if (rows == kTcRows) {
-        uint4 lv[8];
-#pragma unroll
-        for (int q = 0; q < 8; ++q) lv[q] = *reinterpret_cast<const uint4*>(labs2 + sub * 32 + 4 * q);
-        first = lv[0].x;
-        uint32_t diff = 0;
-#pragma unroll
-        for (int q = 0; q < 8; ++q) diff |= (lv[q].x ^ first) | (lv[q].y ^ first) | (lv[q].z ^ first) | (lv[q].w ^ first);
-        uniform = diff == 0;
-        if (uniform) {
-          // each half sums 16 of the subset's 32 rows (pairs ii = 8 half .. 8 half + 7), in row order
-#pragma unroll
-          for (int ii = 0; ii < 8; ++ii) {
-            part += *reinterpret_cast<const float*>(raw + 1024u * (ii + 8 * half) + acc_off_e);
-            part += *reinterpret_cast<const float*>(raw + 1024u * (ii + 8 * half) + acc_off_o);
-          }
-          if (half == 1) ex_part[sub * 32 + feat] = part;
-        } else if (half == 0) {
-          my_acc[cur_lab * 32] += cur_acc;
-          cur_lab = k;
-          cur_acc = 0.f;
-#pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            const uint32_t l4[4] = {lv[q].x, lv[q].y, lv[q].z, lv[q].w};
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              const int i = 4 * q + u;
-              const float xv = *reinterpret_cast<const float*>(raw + 1024u * (i >> 1) + ((i & 1) ? acc_off_o : acc_off_e));
-              my_acc[l4[u] * 32] += xv;
-            }
-          }
-        }
-      } else if (half == 0) {
-        for (int r = sub; r < rows; r += kTcSubsets) {
-          const int lab = (int)labs[r];
-          const float xv = *reinterpret_cast<const float*>(raw + tc::sw128_offset((uint32_t)r, (uint32_t)(feat >> 2)) + (feat & 3) * 4);
-          if (lab != cur_lab) { my_acc[cur_lab * 32] += cur_acc; cur_lab = lab; cur_acc = 0.f; }
-          cur_acc += xv;
-        }
-      }
-      __syncthreads();  // ex_part visible; also closes the tile (raw may be overwritten next)
-      if (uniform && half == 0) {
-        if ((int)first != cur_lab) { my_acc[cur_lab * 32] += cur_acc; cur_lab = (int)first; cur_acc = 0.f; }
-        cur_acc += part;
-        cur_acc += ex_part[sub * 32 + feat];
-      }
-    } else {
-      __syncthreads();
-    }
-  }
-  cp_async_wait_all();
-  if (a.accumulate) {
-    if (half == 0) my_acc[cur_lab * 32] += cur_acc;
-    __syncthreads();
-    const int kd = k * 32, sstride = (k + 1) * 32;
-    float* ps = a.part_sums + (size_t)blockIdx.x * kd;
-    for (int e = t; e < kd; e += 256) {
-      float s2 = acc[e];
-#pragma unroll
-      for (int q = 1; q < kTcSubsets; ++q) s2 += acc[(size_t)q * sstride + e];
-      ps[e] = s2;
-    }
-    uint32_t* pc = a.part_counts + (size_t)blockIdx.x * k;
-    for (int e = t; e < k; e += 256) pc[e] = cnt[e];
-    __syncthreads();
-    red[t] = inert;
-    __syncthreads();
-    for (int o = 128; o > 0; o >>= 1) {
-      if (t < o) red[t] += red[t + o];
-      __syncthreads();
-    }
-    if (t == 0) a.part_inertia[blockIdx.x] = red[0];
-  }
-  if (t == 0 && a.state && my_fallbacks) atomicAdd(&a.state->fallback_rows, (unsigned long long)my_fallbacks);
-  tc::tc_fence_before();
-  __syncthreads();
-  if (warp == 0) tc::tmem_dealloc(tmem, (uint32_t)a.tcols);
-}
-
-// =============================================================================================
-// Tensor-core ASSIGNMENT for wide rows / many clusters (f32, d = 32 * ka with ka in {1, 2, 4}, any k):
-// labels and exact min distances to global memory; the centroid update then runs as the
-// cluster-chunked MODE_UPDATE pass of lloyd_kernel.  Centroids are pre-split once per iteration
-// into TF32 hi / lo operand tiles (tc_prep_centroids_kernel) and streamed from L2 in chunks of 64;
-// the 128-row X tile stays resident as hi / lo (x = hi + lo exactly, lo is kept unmasked).
-// =============================================================================================
 constexpr int kAsgChunk = 64;
 
 struct TcAssignArgs {
@@ -1373,408 +782,10 @@ __global__ void __launch_bounds__(128) tc_assign_kernel(const TcAssignArgs a) {
   if (warp == 0) tc::tmem_dealloc(tmem, 64);
 }
 
-// =============================================================================================
-// Warp-specialised fused Lloyd iteration (f32, d = 32): one persistent CTA per SM, 17 warps.
-//   S  warps 0-3   stage tile j: global -> registers (one tile ahead) -> raw / TF32 hi / lo + ||x||^2
-//   M  warp 16     one thread issues the 12 tcgen05 MMAs of tile j into TMEM accumulator j&1
-//   E  warps 4-11  two groups of four; group g scores tiles j = g (mod 2): TMEM -> w_c -> best/second ->
-//                  certificate -> provisional label (or "uncertified")
-//   A  warps 12-15 exact winner distance, exact fallback for uncertified rows, counts, inertia,
-//                  deterministic accumulation of the cluster sums
-// Tiles j, j+1, j+2 are in flight in different roles at the same time; the roles hand tiles over
-// through mbarriers (two slots).  Same arithmetic, certificate and outputs as lloyd_tc_kernel.
-// =============================================================================================
 namespace tc {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 }  // namespace tc
-
-constexpr int kWsThreads = 544;
-
-__host__ __device__ inline size_t tcws_smem_bytes(int k, int kp) {
-  size_t b = 0;
-  b += 2 * 16384 * 2;             // A_hi, A_lo, two slots
-  b += (size_t)kp * 128 * 2;      // B_hi, B_lo
-  b += 2 * 16384;                 // raw tile, two slots
-  b += (size_t)k * kTcCStride * 4;  // raw centroids
-  b += (size_t)kp * 4;            // ||c||^2
-  b += (size_t)kTcSubsets * (k + 1) * 32 * 4;   // sums
-  b += (((size_t)k * 4) + 15) & ~(size_t)15;    // counts
-  b += 2 * kTcRows * 4 * 2;       // per slot: provisional label, ||x||^2
-  b += kTcRows * 4 * 3 + 16;      // final labels (subset-major), dists, flag list
-  return b + 1024;
-}
-
-__global__ void __launch_bounds__(kWsThreads, 1) lloyd_tcws_kernel(const TcArgs a) {
-  pdl_launch_dependents();
-  pdl_wait();
-  if (a.state != nullptr && a.state->done) return;
-  extern __shared__ __align__(16) unsigned char smem_unaligned[];
-  unsigned char* smem = smem_unaligned + ((1024u - (tc::smem_u32(smem_unaligned) & 1023u)) & 1023u);
-  const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
-  const int k = a.k, kp = a.kp;
-  unsigned char* a_hi = smem;                 // [slot][16 KB]
-  unsigned char* a_lo = a_hi + 2 * 16384;
-  unsigned char* b_hi = a_lo + 2 * 16384;
-  unsigned char* b_lo = b_hi + (size_t)kp * 128;
-  unsigned char* raw = b_lo + (size_t)kp * 128;  // [slot][16 KB]
-  float* rawc = reinterpret_cast<float*>(raw + 2 * 16384);
-  float* cn = rawc + (size_t)k * kTcCStride;
-  float* acc = cn + kp;
-  uint32_t* cnt = reinterpret_cast<uint32_t*>(acc + (size_t)kTcSubsets * (k + 1) * 32);
-  uint32_t* prov = cnt + ((k + 3) & ~3);       // [slot][128] provisional label, 0xFFFFFFFF = uncertified
-  float* xxs = reinterpret_cast<float*>(prov + 2 * kTcRows);  // [slot][128] ||x||^2
-  uint32_t* labs2 = reinterpret_cast<uint32_t*>(xxs + 2 * kTcRows);
-  float* dist_s = reinterpret_cast<float*>(labs2 + kTcRows);
-  uint32_t* flags = reinterpret_cast<uint32_t*>(dist_s + kTcRows);
-  __shared__ __align__(8) uint64_t bar_staged[2], bar_mma[2], bar_scored[2], bar_rawfree[2];
-  __shared__ uint32_t tmem_slot;
-  __shared__ uint32_t n_flag;
-  __shared__ uint32_t cmax_bits;
-  __shared__ uint32_t abort_flag;
-
-  if (warp == 0) tc::tmem_alloc(&tmem_slot, 128);
-  if (t == 0) {
-    for (int s2 = 0; s2 < 2; ++s2) {
-      tc::mbar_init(&bar_staged[s2], 128);
-      tc::mbar_init(&bar_mma[s2], 1);
-      tc::mbar_init(&bar_scored[s2], 128);
-      tc::mbar_init(&bar_rawfree[s2], 128);
-    }
-    tc::fence_mbar_init();
-    n_flag = 0; cmax_bits = 0; abort_flag = 0;
-  }
-  __syncthreads();
-  for (int r = t; r < kp; r += kWsThreads) {
-    if (r < k) {
-      double nn = 0.0;
-#pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        const float4 v = __ldg(reinterpret_cast<const float4*>(a.C + (size_t)r * 32) + c);
-        float4 h, l;
-        tc::split_tf32(v.x, h.x, l.x); tc::split_tf32(v.y, h.y, l.y);
-        tc::split_tf32(v.z, h.z, l.z); tc::split_tf32(v.w, h.w, l.w);
-        const uint32_t o = tc::sw128_offset(r, c);
-        *reinterpret_cast<float4*>(b_hi + o) = h;
-        *reinterpret_cast<float4*>(b_lo + o) = l;
-        *reinterpret_cast<float4*>(rawc + r * kTcCStride + 4 * c) = v;
-        nn += (double)v.x * v.x + (double)v.y * v.y + (double)v.z * v.z + (double)v.w * v.w;
-      }
-      const float nf = (float)nn;
-      cn[r] = nf;
-      atomicMax(&cmax_bits, __float_as_uint(nf));
-    } else {
-      const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        const uint32_t o = tc::sw128_offset(r, c);
-        *reinterpret_cast<float4*>(b_hi + o) = z;
-        *reinterpret_cast<float4*>(b_lo + o) = z;
-      }
-      cn[r] = INFINITY;
-    }
-  }
-  for (int e = t; e < kTcSubsets * (k + 1) * 32; e += kWsThreads) acc[e] = 0.f;
-  for (int e = t; e < k; e += kWsThreads) cnt[e] = 0u;
-  tc::fence_async_smem();
-  tc::tc_fence_before();
-  __syncthreads();
-  tc::tc_fence_after();
-  const uint32_t tmem = tmem_slot;
-  const unsigned long long n_tiles = (a.n + kTcRows - 1) / kTcRows;
-  // number of tiles this CTA processes
-  const unsigned long long my_tiles = blockIdx.x < n_tiles ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
-  double inert = 0.0;         // A role
-  unsigned int my_fallbacks = 0;
-  int cur_lab = k;            // A role accumulation state
-  float cur_acc = 0.f;
-
-  if (warp < 4) {
-    // ======================= S: stage tiles =======================
-    const uint32_t st_off = tc::sw128_offset((uint32_t)(t >> 3), (uint32_t)(t & 7));
-    int4 pre[8];
-    auto prefetch = [&](unsigned long long tile) {
-      const unsigned long long row0 = tile * kTcRows;
-      const int rows = (int)min((unsigned long long)kTcRows, a.n - row0);
-      const int4* g = reinterpret_cast<const int4*>(a.X + row0 * 32) + t;
-      const int my_row = t >> 3;
-#pragma unroll
-      for (int i = 0; i < 8; ++i) pre[i] = (my_row + 16 * i) < rows ? __ldg(g + 128 * i) : make_int4(0, 0, 0, 0);
-    };
-    if (my_tiles) prefetch(blockIdx.x);
-    for (unsigned long long j = 0; j < my_tiles; ++j) {
-      const int slot = (int)(j & 1);
-      const uint32_t u = (uint32_t)(j >> 1);
-      if (u > 0) {
-        // slot reuse: the MMAs of tile j-2 have read A[slot], the A role is done with raw[slot]
-        bool ok = tc::mbar_wait(&bar_mma[slot], (u - 1) & 1);
-        ok = ok && tc::mbar_wait(&bar_rawfree[slot], (u - 1) & 1);
-        if (!ok) atomicExch(&abort_flag, 1u);
-      }
-      unsigned char* rw = raw + slot * 16384;
-      unsigned char* ah = a_hi + slot * 16384;
-      unsigned char* al = a_lo + slot * 16384;
-      float sq[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const uint32_t o = st_off + 2048u * i;
-        const float4 v = *reinterpret_cast<const float4*>(&pre[i]);
-        float4 h, l;
-        h.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u); l.x = v.x - h.x;
-        h.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u); l.y = v.y - h.y;
-        h.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u); l.z = v.z - h.z;
-        h.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u); l.w = v.w - h.w;
-        *reinterpret_cast<float4*>(rw + o) = v;
-        *reinterpret_cast<float4*>(ah + o) = h;
-        *reinterpret_cast<float4*>(al + o) = l;
-        sq[i] = fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, v.w * v.w)));
-      }
-      // ||x||^2 of row t/8 + 16 i: sum over the 8 threads (t%8) that hold its chunks
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        float v = sq[i];
-        v += __shfl_xor_sync(0xffffffffu, v, 1);
-        v += __shfl_xor_sync(0xffffffffu, v, 2);
-        v += __shfl_xor_sync(0xffffffffu, v, 4);
-        if ((t & 7) == 0) xxs[slot * kTcRows + (t >> 3) + 16 * i] = v;
-      }
-      if (j + 1 < my_tiles) prefetch(blockIdx.x + (j + 1) * gridDim.x);
-      tc::fence_async_smem();
-      tc::mbar_arrive(&bar_staged[slot]);
-    }
-  } else if (warp == 16) {
-    // ======================= M: issue the MMAs =======================
-    if (lane == 0) {
-      const uint32_t idesc = tc::idesc_tf32(128, (uint32_t)kp);
-      const uint32_t sb_hi = tc::smem_u32(b_hi), sb_lo = tc::smem_u32(b_lo);
-      for (unsigned long long j = 0; j < my_tiles; ++j) {
-        const int slot = (int)(j & 1);
-        const uint32_t u = (uint32_t)(j >> 1);
-        bool ok = tc::mbar_wait(&bar_staged[slot], u & 1);
-        if (u > 0) ok = ok && tc::mbar_wait(&bar_scored[slot], (u - 1) & 1);  // accumulator slot drained
-        if (!ok) atomicExch(&abort_flag, 1u);
-        tc::tc_fence_after();
-        const uint32_t sa_hi = tc::smem_u32(a_hi + slot * 16384), sa_lo = tc::smem_u32(a_lo + slot * 16384);
-        const uint32_t dcol = tmem + (uint32_t)slot * 64u;
-        uint32_t accf = 0;
-#pragma unroll
-        for (int pass = 0; pass < 3; ++pass) {
-          const uint32_t sa = pass == 2 ? sa_lo : sa_hi;
-          const uint32_t sb = pass == 1 ? sb_lo : sb_hi;
-#pragma unroll
-          for (int ks = 0; ks < 4; ++ks) {
-            tc::mma_tf32(dcol, tc::smem_desc_sw128(sa + ks * 32), tc::smem_desc_sw128(sb + ks * 32), idesc, accf);
-            accf = 1;
-          }
-        }
-        tc::mma_commit(&bar_mma[slot]);
-      }
-    }
-  } else if (warp < 12) {
-    // ======================= E: score tiles j = g (mod 2) =======================
-    const int g = (warp - 4) >> 2;          // group = slot
-    const int row = (t - 128) & 127;        // row owned in the tile
-    const int q = (warp - 4) & 3;           // TMEM lane quadrant
-    const float cmax2 = __uint_as_float(cmax_bits);
-    const float cmax = sqrtf(cmax2) * 1.000001f;
-    const float eta = (3.f * 32.f + 12.f) * 2.3841858e-7f;
-    const float gamma = (32.f + 2.f) * 5.9604645e-8f;
-    const float m_a0 = 2.3841858e-7f * cmax2;
-    const float m_a1 = (4.f * eta + 4.7683716e-7f) * cmax;
-    const float m_g2 = 2.f * gamma;
-    for (unsigned long long j = g; j < my_tiles; j += 2) {
-      const uint32_t u = (uint32_t)(j >> 1);
-      const bool ok = tc::mbar_wait(&bar_mma[g], u & 1);
-      if (!ok) atomicExch(&abort_flag, 1u);
-      tc::tc_fence_after();
-      float best0 = INFINITY, second0 = INFINITY, best1 = INFINITY, second1 = INFINITY;
-      int idx0 = 0, idx1 = 1;
-      for (int c0 = 0; c0 < kp; c0 += 32) {
-        uint32_t r[32];
-        tc::tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(g * 64 + c0), r);
-        tc::tmem_ld_wait();
-#pragma unroll
-        for (int jj = 0; jj < 32; jj += 4) {
-          const float4 cn4 = *reinterpret_cast<const float4*>(cn + c0 + jj);
-          const float w0 = fmaf(-2.f, __uint_as_float(r[jj]), cn4.x);
-          const float w1 = fmaf(-2.f, __uint_as_float(r[jj + 1]), cn4.y);
-          const float w2 = fmaf(-2.f, __uint_as_float(r[jj + 2]), cn4.z);
-          const float w3 = fmaf(-2.f, __uint_as_float(r[jj + 3]), cn4.w);
-          second0 = fminf(second0, fmaxf(w0, best0));
-          idx0 = (w0 < best0) ? (c0 + jj) : idx0;
-          best0 = fminf(best0, w0);
-          second1 = fminf(second1, fmaxf(w1, best1));
-          idx1 = (w1 < best1) ? (c0 + jj + 1) : idx1;
-          best1 = fminf(best1, w1);
-          second0 = fminf(second0, fmaxf(w2, best0));
-          idx0 = (w2 < best0) ? (c0 + jj + 2) : idx0;
-          best0 = fminf(best0, w2);
-          second1 = fminf(second1, fmaxf(w3, best1));
-          idx1 = (w3 < best1) ? (c0 + jj + 3) : idx1;
-          best1 = fminf(best1, w3);
-        }
-      }
-      float best, second;
-      int bidx;
-      if (best1 < best0 || (best1 == best0 && idx1 < idx0)) { best = best1; bidx = idx1; second = fminf(second1, best0); }
-      else { best = best0; bidx = idx0; second = fminf(second0, best1); }
-      const float xn = sqrtf(xxs[g * kTcRows + row]) * 1.000001f;
-      const float margin = 1.1f * (m_a0 + xn * m_a1 + m_g2 * (xn + cmax) * (xn + cmax));
-      prov[g * kTcRows + row] = ((second - best) > margin) ? (uint32_t)bidx : 0xFFFFFFFFu;
-      tc::tc_fence_before();
-      tc::mbar_arrive(&bar_scored[g]);
-    }
-  } else {
-    // ======================= A: exact distances, fallback, accumulation =======================
-    const int ta = t - 384;                   // 0..127
-    const int awarp = ta >> 5;
-    const uint32_t row_off = (uint32_t)(ta >> 3) * 1024u + (uint32_t)(ta & 7) * 128u;
-    const uint32_t row_x = (uint32_t)(ta & 7);
-    const int sub = ta >> 5, feat = ta & 31;
-    const uint32_t acc_off_e = (uint32_t)sub * 128u + ((((uint32_t)feat >> 2) ^ (uint32_t)sub) << 4) + ((uint32_t)feat & 3u) * 4u;
-    const uint32_t acc_off_o = (uint32_t)(sub + 4) * 128u + ((((uint32_t)feat >> 2) ^ (uint32_t)(sub + 4)) << 4) + ((uint32_t)feat & 3u) * 4u;
-    float* my_acc = acc + (size_t)sub * (k + 1) * 32 + feat;
-    for (unsigned long long j = 0; j < my_tiles; ++j) {
-      const int slot = (int)(j & 1);
-      const uint32_t u = (uint32_t)(j >> 1);
-      const unsigned long long tile = blockIdx.x + j * gridDim.x;
-      const unsigned long long row0 = tile * kTcRows;
-      const int rows = (int)min((unsigned long long)kTcRows, a.n - row0);
-      const bool ok = tc::mbar_wait(&bar_scored[slot], u & 1);
-      if (!ok) atomicExch(&abort_flag, 1u);
-      const unsigned char* rw = raw + slot * 16384;
-      const bool row_ok = ta < rows;
-      uint32_t lab = prov[slot * kTcRows + ta];
-      float dist = 0.f;
-      if (row_ok) {
-        if (lab != 0xFFFFFFFFu) {
-          const float* cw = rawc + lab * kTcCStride;
-          float dacc = 0.f;
-#pragma unroll
-          for (int c = 0; c < 8; ++c) {
-            const float4 xv = *reinterpret_cast<const float4*>(rw + row_off + (((uint32_t)c ^ row_x) << 4));
-            const float4 cv = *reinterpret_cast<const float4*>(cw + 4 * c);
-            float df;
-            df = __fsub_rn(cv.x, xv.x); dacc = __fadd_rn(dacc, __fmul_rn(df, df));
-            df = __fsub_rn(cv.y, xv.y); dacc = __fadd_rn(dacc, __fmul_rn(df, df));
-            df = __fsub_rn(cv.z, xv.z); dacc = __fadd_rn(dacc, __fmul_rn(df, df));
-            df = __fsub_rn(cv.w, xv.w); dacc = __fadd_rn(dacc, __fmul_rn(df, df));
-          }
-          dist = dacc;
-          labs2[(ta & 3) * 32 + (ta >> 2)] = lab;
-          dist_s[ta] = dacc;
-        } else {
-          const uint32_t p = atomicAdd(&n_flag, 1u);
-          flags[p] = (uint32_t)ta;
-        }
-      }
-      asm volatile("bar.sync 1, 128;" ::: "memory");   // A-role barrier
-      const uint32_t nf = n_flag;
-      if (nf) {
-        for (uint32_t f = awarp; f < nf; f += 4) {
-          const uint32_t frow = flags[f];
-          float x2[32];
-#pragma unroll
-          for (int c = 0; c < 8; ++c) {
-            const float4 v = *reinterpret_cast<const float4*>(rw + tc::sw128_offset(frow, (uint32_t)c));
-            x2[4 * c] = v.x; x2[4 * c + 1] = v.y; x2[4 * c + 2] = v.z; x2[4 * c + 3] = v.w;
-          }
-          float fb = INFINITY;
-          int fi = -1;
-          int c = lane;
-          if (lane == 0) { fb = sqdist_reg<float, 32>(rawc, x2); fi = 0; c = 32; }
-          for (; c < k; c += 32) {
-            const float v = sqdist_reg<float, 32>(rawc + c * kTcCStride, x2);
-            if (v < fb) { fb = v; fi = c; }
-          }
-          combine_candidates<float>(32, fb, fi);
-          if (lane == 0) { labs2[(frow & 3) * 32 + (frow >> 2)] = (uint32_t)fi; dist_s[frow] = fb; }
-        }
-        my_fallbacks += (ta == 0) ? nf : 0u;
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        if (ta == 0) n_flag = 0;
-        if (row_ok && lab == 0xFFFFFFFFu) { lab = labs2[(ta & 3) * 32 + (ta >> 2)]; dist = dist_s[ta]; }
-      }
-      if (row_ok) {
-        inert += (double)dist;
-        atomicAdd(&cnt[lab], 1u);
-        if (a.labels) a.labels[row0 + ta] = lab;
-        if (a.dists) a.dists[row0 + ta] = dist;
-      }
-      asm volatile("bar.sync 1, 128;" ::: "memory");   // labs2 complete (and n_flag reset visible)
-      if (rows == kTcRows) {
-        uint4 lv[8];
-#pragma unroll
-        for (int qq = 0; qq < 8; ++qq) lv[qq] = *reinterpret_cast<const uint4*>(labs2 + sub * 32 + 4 * qq);
-        const uint32_t first = lv[0].x;
-        uint32_t diff = 0;
-#pragma unroll
-        for (int qq = 0; qq < 8; ++qq) diff |= (lv[qq].x ^ first) | (lv[qq].y ^ first) | (lv[qq].z ^ first) | (lv[qq].w ^ first);
-        if (diff == 0) {
-          if ((int)first != cur_lab) { my_acc[cur_lab * 32] += cur_acc; cur_lab = (int)first; cur_acc = 0.f; }
-#pragma unroll
-          for (int ii = 0; ii < 16; ++ii) {
-            cur_acc += *reinterpret_cast<const float*>(rw + 1024u * ii + acc_off_e);
-            cur_acc += *reinterpret_cast<const float*>(rw + 1024u * ii + acc_off_o);
-          }
-        } else {
-          my_acc[cur_lab * 32] += cur_acc;
-          cur_lab = k;
-          cur_acc = 0.f;
-#pragma unroll
-          for (int qq = 0; qq < 8; ++qq) {
-            const uint32_t l4[4] = {lv[qq].x, lv[qq].y, lv[qq].z, lv[qq].w};
-#pragma unroll
-            for (int uu = 0; uu < 4; ++uu) {
-              const int i = 4 * qq + uu;
-              const float xv = *reinterpret_cast<const float*>(rw + 1024u * (i >> 1) + ((i & 1) ? acc_off_o : acc_off_e));
-              my_acc[l4[uu] * 32] += xv;
-            }
-          }
-        }
-      } else {
-        // tail tile: labels in subset-major order are only valid for rows < rows
-        for (int r = sub; r < rows; r += kTcSubsets) {
-          const int lab2 = (int)labs2[(r & 3) * 32 + (r >> 2)];
-          const float xv = *reinterpret_cast<const float*>(rw + tc::sw128_offset((uint32_t)r, (uint32_t)(feat >> 2)) + (feat & 3) * 4);
-          if (lab2 != cur_lab) { my_acc[cur_lab * 32] += cur_acc; cur_lab = lab2; cur_acc = 0.f; }
-          cur_acc += xv;
-        }
-      }
-      asm volatile("bar.sync 1, 128;" ::: "memory");   // everyone done with raw[slot], labs2, dist_s
-      tc::mbar_arrive(&bar_rawfree[slot]);
-    }
-    my_acc[cur_lab * 32] += cur_acc;
-  }
-  __syncthreads();
-  // ---- per-CTA partials (same layout as the other fused kernels) ----
-  {
-    const int kd = k * 32, sstride = (k + 1) * 32;
-    float* ps = a.part_sums + (size_t)blockIdx.x * kd;
-    for (int e = t; e < kd; e += kWsThreads) {
-      float s2 = acc[e];
-#pragma unroll
-      for (int qq = 1; qq < kTcSubsets; ++qq) s2 += acc[(size_t)qq * sstride + e];
-      ps[e] = s2;
-    }
-    uint32_t* pc = a.part_counts + (size_t)blockIdx.x * k;
-    for (int e = t; e < k; e += kWsThreads) pc[e] = cnt[e];
-    double* red = reinterpret_cast<double*>(a_hi);
-    __syncthreads();
-    if (t >= 384 && t < 512) red[t - 384] = inert;
-    __syncthreads();
-    for (int o = 64; o > 0; o >>= 1) {
-      if (t < o) red[t] += red[t + o];
-      __syncthreads();
-    }
-    if (t == 0) a.part_inertia[blockIdx.x] = red[0];
-  }
-  if (t == 384 && a.state && my_fallbacks) atomicAdd(&a.state->fallback_rows, (unsigned long long)my_fallbacks);
-  if (t == 0 && a.state && abort_flag) atomicOr(&a.state->fallback_rows, 1ull << 40);
-  tc::tc_fence_before();
-  __syncthreads();
-  if (warp == 0) tc::tmem_dealloc(tmem, 128);
-}
 
 }  // namespace lkm

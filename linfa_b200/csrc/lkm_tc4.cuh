@@ -13,7 +13,7 @@
 //                (A in TMEM because a 128 x 8 TF32 A operand read from shared memory costs 4 KB of its
 //                128 B/clk per MMA: measured 47 cycles per N = 64 MMA from shared memory, 32 from TMEM)
 //   E  warps 4-7 (even tiles) and 8-11 (odd tiles), thread = row: packed integer top-2 of the 64
-//                scores (see lkm_tc3.cuh), certificate, label / "uncertified" into a label slot
+//                scores (q_c = (bits(v_c) << 6) | c is monotone in v_c and carries the index), certificate, label / "uncertified" into a label slot
 //   U  warps 12-15, thread = (row subset, feature): exact re-scan of uncertified rows, then sums
 //                and inertia straight from the raw tile into thread-owned shared-memory
 //                accumulators, tiles in ascending order (deterministic); frees the raw stage
@@ -21,7 +21,7 @@
 // Tiles j+3.. are in flight from HBM while S works on j+2, the tensor core on j+1, E on j and U on
 // j-1.  Outputs: per-CTA partial sums / counts / inertia for finalize_kernel, as the other kernels.
 #pragma once
-#include "lkm_tc3.cuh"
+#include "lkm_tma.cuh"
 
 namespace lkm {
 
@@ -74,6 +74,7 @@ struct Tc4Args {
   double* shift_part;       // [grid]
   double tol;
   unsigned long long max_iter;
+  uint32_t* labels_out;     // optional (lkm_set_keep_labels): the label every row was accumulated under, for the parity tests
 };
 
 // Optional phase profile (compile with -DLKM_T4_PROF): cycles spent in each wait of each role, written
@@ -645,6 +646,10 @@ __global__ void __launch_bounds__(kT4Threads, 1) lloyd_tc4_kernel(const Tc4Args 
       }
       T4MARK(tu0);
       T4ADD(4, tu_a, tu0);
+      if (a.labels_out != nullptr) {
+        // the labels this tile is accumulated under (certified by E or re-scanned above), row order
+        for (int r = tg; r < rows; r += 64) a.labels_out[row0 + r] = labs2[(r & 3) * 32 + (r >> 2)];
+      }
       unsigned long long e2 = 0ull;
       if (nf == 0 && wu.x != 0xFFFFFFFFu && wu.x == wu.y && wu.x == wu.z && wu.x == wu.w) {
         // the whole tile goes to one cluster: register sums in row order, two features per instruction
@@ -857,216 +862,6 @@ __global__ void __launch_bounds__(kT4Threads, 1) lloyd_tc4_kernel(const Tc4Args 
       }
     }
   }
-}
-
-
-// Micro-benchmark: one thread per CTA issues `reps` batches of `per_batch` tcgen05 TF32 MMAs (M = 128, N = n_cols,
-// K = 8) on zeroed shared-memory operands, one commit + wait per batch; out[block] = cycles.  mode bit 0: all
-// MMAs of a batch read the same A K-step (operand fetch hits one 4 KB region); bit 1: use the SBO = 0 alias for A.
-__global__ void __launch_bounds__(128) mma_bench_kernel(int n_cols, int reps, int per_batch, int mode, long long* out) {
-  extern __shared__ __align__(16) unsigned char smem_unaligned[];
-  unsigned char* smem = smem_unaligned + ((1024u - (tc::smem_u32(smem_unaligned) & 1023u)) & 1023u);
-  __shared__ __align__(8) uint64_t bar;
-  __shared__ uint32_t tmem_slot;
-  const int t = threadIdx.x, warp = t >> 5;
-  unsigned char* a_t = smem;            // 2 x 16 KB
-  unsigned char* b_t = smem + 32768;    // n_cols x 128 B
-  for (int i = t; i < (32768 + n_cols * 128) / 16; i += 128) reinterpret_cast<int4*>(smem)[i] = make_int4(0, 0, 0, 0);
-  if (warp == 0) tc::tmem_alloc(&tmem_slot, 256);
-  if (t == 0) { tc::mbar_init(&bar, 1); tc::fence_mbar_init(); }
-  tc::fence_async_smem();
-  tc::tc_fence_before();
-  __syncthreads();
-  tc::tc_fence_after();
-  const uint32_t tmem = tmem_slot;
-  if (t == 0) {
-    const uint32_t idesc = tc::idesc_tf32(128, (uint32_t)n_cols);
-    const uint64_t da = (mode & 2) ? tc::smem_desc_sw128_alias(tc::smem_u32(a_t)) : tc::smem_desc_sw128(tc::smem_u32(a_t));
-    const uint64_t db = tc::smem_desc_sw128(tc::smem_u32(b_t));
-    const long long t0 = clock64();
-    for (int r = 0; r < reps; ++r) {
-      for (int i = 0; i < per_batch; ++i) {
-        const uint32_t ks = (mode & 1) ? 0u : (uint32_t)(i & 3);
-        const uint64_t a_off = ((i >> 2) & 1) ? 1024u : 0u;
-        if (mode & 8) tc::mma_f16(tmem, da + a_off + 2u * ks, db + 2u * ks, tc::idesc_f16(128, (uint32_t)n_cols, 0), i ? 1u : 0u);
-        else if (mode & 4) tc::mma_tf32_ts(tmem, tmem + 128u + 8u * ks + (((i >> 2) & 1) ? 32u : 0u), db + 2u * ks, idesc, i ? 1u : 0u);
-        else tc::mma_tf32(tmem, da + a_off + 2u * ks, db + 2u * ks, idesc, i ? 1u : 0u);
-      }
-      tc::mma_commit(&bar);
-      tc::mbar_wait_or_trap(&bar, (uint32_t)r & 1u);
-    }
-    out[blockIdx.x] = clock64() - t0;
-  }
-  tc::tc_fence_before();
-  __syncthreads();
-  if (warp == 0) tc::tmem_dealloc(tmem, 256);
-}
-
-
-// Same measurement with the issue pattern of a production MMA warp: warp 0 runs the loop uniformly, 13 unrolled
-// MMAs per batch with constant descriptor offsets, elect inside the instruction wrapper.
-template <int MODE>  // 0 tf32 SS, 1 tf32 TS, 2 f16 SS, 3 f16 TS
-__global__ void __launch_bounds__(128) mma_bench2_kernel(int n_cols, int reps, long long* out) {
-  extern __shared__ __align__(16) unsigned char smem_unaligned[];
-  unsigned char* smem = smem_unaligned + ((1024u - (tc::smem_u32(smem_unaligned) & 1023u)) & 1023u);
-  __shared__ __align__(8) uint64_t bar;
-  __shared__ uint32_t tmem_slot;
-  const int t = threadIdx.x;
-  const int warp = __shfl_sync(0xffffffffu, t >> 5, 0);
-  for (int i = t; i < (32768 + n_cols * 128) / 16; i += 128) reinterpret_cast<int4*>(smem)[i] = make_int4(0, 0, 0, 0);
-  if (warp == 0) tc::tmem_alloc(&tmem_slot, 512);
-  if (t == 0) { tc::mbar_init(&bar, 1); tc::fence_mbar_init(); }
-  tc::fence_async_smem();
-  tc::tc_fence_before();
-  __syncthreads();
-  tc::tc_fence_after();
-  const uint32_t tmem = __shfl_sync(0xffffffffu, tmem_slot, 0);
-  if (warp == 0) {
-    const uint32_t idesc = tc::idesc_tf32(128, (uint32_t)n_cols);
-    const uint64_t da = tc::smem_desc_sw128(tc::smem_u32(smem));
-    const uint64_t db = tc::smem_desc_sw128(tc::smem_u32(smem + 32768));
-    const long long t0 = clock64();
-    for (int r = 0; r < reps; ++r) {
-#pragma unroll
-      for (int i = 0; i < 13; ++i) {
-        if (MODE == 0) tc::mma_tf32_elect(tmem, da + (uint64_t)(((i >> 2) & 1) * 1024 + 2 * (i & 3)), db + (uint64_t)(2 * (i & 3)), idesc, i ? 1u : 0u);
-        if (MODE == 1) tc::mma_tf32_ts_elect(tmem, tmem + 256u + 32u * ((i >> 2) & 1) + 8u * (i & 3), db + (uint64_t)(2 * (i & 3)), idesc, i ? 1u : 0u);
-        if (MODE == 2) tc::mma_f16_elect(tmem, da + (uint64_t)(((i >> 2) & 1) * 1024 + 2 * (i & 3)), db + (uint64_t)(2 * (i & 3)), tc::idesc_f16(128, (uint32_t)n_cols, 0), i ? 1u : 0u);
-        if (MODE == 3) tc::mma_f16_ts_elect(tmem, tmem + 256u + 32u * ((i >> 2) & 1) + 8u * (i & 3), db + (uint64_t)(2 * (i & 3)), tc::idesc_f16(128, (uint32_t)n_cols, 0), i ? 1u : 0u);
-      }
-      tc::mma_commit_elect(&bar);
-      tc::mbar_wait_or_trap(&bar, (uint32_t)r & 1u);
-    }
-    if (t == 0) out[blockIdx.x] = clock64() - t0;
-  }
-  tc::tc_fence_before();
-  __syncthreads();
-  if (warp == 0) tc::tmem_dealloc(tmem, 512);
-}
-
-// TMEM load throughput: `nwarps` warps each issue `reps` x 8 tcgen05.ld.32x32b.x32 (4 KB each) back to back.
-__global__ void __launch_bounds__(256) ldtm_bench_kernel(int nwarps, int reps, long long* out) {
-  __shared__ uint32_t tmem_slot;
-  const int t = threadIdx.x, warp = t >> 5;
-  if (warp == 0) tc::tmem_alloc(&tmem_slot, 512);
-  tc::tc_fence_before();
-  __syncthreads();
-  tc::tc_fence_after();
-  const uint32_t tmem = tmem_slot;
-  uint32_t sink = 0;
-  if (warp < nwarps) {
-    const uint32_t base = tmem + ((uint32_t)((warp & 3) * 32) << 16);
-    const long long t0 = clock64();
-    for (int r = 0; r < reps; ++r) {
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        uint32_t v[32];
-        tc::tmem_ld32(base + 32u * (uint32_t)i, v);
-        tc::tmem_ld_wait();
-        sink += v[0] ^ v[31];
-      }
-    }
-    const long long t1 = clock64();
-    if ((t & 31) == 0) out[blockIdx.x * 8 + warp] = t1 - t0 + (sink == 0x12345u ? 1 : 0);
-  }
-  tc::tc_fence_before();
-  __syncthreads();
-  if (warp == 0) tc::tmem_dealloc(tmem, 512);
-}
-
-// TMEM store throughput (what = 1): `nwarps` warps each issue `reps` x 8 tcgen05.st.32x32b.x32 back to back, one
-// tcgen05.wait::st per 8; what = 2: warps 0-3 store while warps 4-7 load (the S / E mix of the pair kernel).
-__global__ void __launch_bounds__(256) sttm_bench_kernel(int nwarps, int reps, int what, long long* out) {
-  __shared__ uint32_t tmem_slot;
-  const int t = threadIdx.x, warp = t >> 5;
-  if (warp == 0) tc::tmem_alloc(&tmem_slot, 512);
-  tc::tc_fence_before();
-  __syncthreads();
-  tc::tc_fence_after();
-  const uint32_t tmem = tmem_slot;
-  uint32_t sink = 0;
-  if (warp < nwarps) {
-    const bool storing = what == 1 || warp < 4;
-    const uint32_t base = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (storing ? 256u : 0u);
-    uint32_t v[32];
-#pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] = (uint32_t)(t * 32 + i);
-    const long long t0 = clock64();
-    for (int r = 0; r < reps; ++r) {
-      if (storing) {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) tc::tmem_st32(base + 32u * (uint32_t)i, v);
-        tc::tmem_st_wait();
-      } else {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          uint32_t w[32];
-          tc::tmem_ld32(base + 32u * (uint32_t)i, w);
-          tc::tmem_ld_wait();
-          sink += w[0] ^ w[31];
-        }
-      }
-    }
-    const long long t1 = clock64();
-    if ((t & 31) == 0) out[blockIdx.x * 8 + warp] = t1 - t0 + (sink == 0x12345u ? 1 : 0);
-  }
-  tc::tc_fence_before();
-  __syncthreads();
-  if (warp == 0) tc::tmem_dealloc(tmem, 512);
-}
-
-// Probe for A-from-TMEM MMAs: thread t stores row t of X (32 f32, raw bits) into TMEM columns 64..95 of its lane,
-// then S[128 x N] = X * Cn^T with four TS-mode MMAs (A K-step ks = columns 64 + 8 ks), B = Cn from shared memory.
-template <int N>
-__global__ void __launch_bounds__(128) tc_ts_probe_kernel(const float* __restrict__ X, const float* __restrict__ Cn,
-                                                          float* __restrict__ S, int* __restrict__ status) {
-  extern __shared__ __align__(16) unsigned char smem_unaligned[];
-  unsigned char* smem = smem_unaligned + ((1024u - (tc::smem_u32(smem_unaligned) & 1023u)) & 1023u);
-  unsigned char* b_t = smem;
-  __shared__ __align__(8) uint64_t bar;
-  __shared__ uint32_t tmem_slot;
-  const int t = threadIdx.x, warp = t >> 5;
-  if (warp == 0) tc::tmem_alloc(&tmem_slot, 128);
-  if (t == 0) { tc::mbar_init(&bar, 1); tc::fence_mbar_init(); }
-  for (int r = t; r < N; r += 128)
-    for (int c = 0; c < 8; ++c)
-      *reinterpret_cast<float4*>(b_t + tc::sw128_offset(r, c)) = reinterpret_cast<const float4*>(Cn + (size_t)r * 32)[c];
-  tc::fence_async_smem();
-  tc::tc_fence_before();
-  __syncthreads();
-  tc::tc_fence_after();
-  const uint32_t tmem = tmem_slot;
-  {
-    uint32_t r[32];
-#pragma unroll
-    for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(X[(size_t)t * 32 + j]);
-    tc::tmem_st32(tmem + ((uint32_t)(warp * 32) << 16) + 64u, r);
-    tc::tmem_st_wait();
-  }
-  tc::tc_fence_before();
-  __syncthreads();
-  if (t == 0) {
-    tc::tc_fence_after();
-    constexpr uint32_t idesc = tc::idesc_tf32(128, N);
-    const uint64_t db = tc::smem_desc_sw128(tc::smem_u32(b_t));
-    for (int ks = 0; ks < 4; ++ks) tc::mma_tf32_ts(tmem, tmem + 64u + 8u * ks, db + 2u * ks, idesc, ks ? 1u : 0u);
-    tc::mma_commit(&bar);
-  }
-  const bool ok = tc::mbar_wait(&bar, 0);
-  tc::tc_fence_after();
-  if (ok) {
-    for (int c0 = 0; c0 < N; c0 += 32) {
-      uint32_t r[32];
-      tc::tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, r);
-      tc::tmem_ld_wait();
-#pragma unroll
-      for (int j = 0; j < 32; ++j) S[(size_t)t * N + c0 + j] = __uint_as_float(r[j]);
-    }
-  }
-  if (t == 0) status[0] = ok ? 0 : 1;
-  tc::tc_fence_before();
-  __syncthreads();
-  if (warp == 0) tc::tmem_dealloc(tmem, 128);
 }
 
 }  // namespace lkm

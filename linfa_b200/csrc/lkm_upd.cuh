@@ -17,7 +17,7 @@
 //                   (with all of them polling, two thirds of the executed instructions were wait loops)
 //   C  warps 0-15   as above; the stage is released when all 16 warps have arrived on its `empty` barrier
 #pragma once
-#include "lkm_tc3.cuh"
+#include "lkm_tma.cuh"
 
 namespace lkm {
 

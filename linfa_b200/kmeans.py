@@ -183,6 +183,21 @@ class Context:
     def set_kernel_timing(self, on):
         self.check(_ffi.lib.lkm_set_kernel_timing(self.h, int(bool(on))))
 
+    def set_keep_labels(self, on):
+        """Parity-test aid: the Lloyd kernels also write the labels of the last iteration (see get_labels)."""
+        self.check(_ffi.lib.lkm_set_keep_labels(self.h, int(bool(on))))
+
+    def get_labels(self, n=None):
+        """Labels every row was accumulated under in the last executed Lloyd iteration (needs set_keep_labels)."""
+        n = self.shape[0] if n is None else n
+        out = np.empty(n, dtype=np.uint32)
+        self.check(_ffi.lib.lkm_get_labels(self.h, out.ctypes.data_as(C.POINTER(C.c_uint32)), n))
+        return out
+
+    def set_blob_layout(self, shuffled):
+        """gen_blobs layout: False = contiguous blobs (linfa's generate::blobs), True = hashed blob per row."""
+        self.check(_ffi.lib.lkm_set_blob_layout(self.h, int(bool(shuffled))))
+
     def set_scoring_passes(self, passes):
         """0 adaptive (default), 1 / 2 / 3 pin the tensor-core scoring variant (speed only, never results)."""
         self.check(_ffi.lib.lkm_set_scoring_passes(self.h, int(passes)))
@@ -368,14 +383,19 @@ class KMeansValidParams:
         p, keep = self._native_params(dtype)
         ctx.set_data(x)
         if model is not None:
+            # the reference never looks at n_clusters here: the model's own shape rules (KM/algorithm.rs:680-690)
             cen = np.ascontiguousarray(model.centroids(), dtype=dtype).copy()
             cnt = np.ascontiguousarray(model.cluster_count(), dtype=dtype).copy()
+            if cen.ndim != 2 or cnt.shape != (cen.shape[0],):
+                raise AssertionError("model.cluster_count must have one entry per centroid")
+            k = cen.shape[0]
         else:
             cen = np.zeros((max(k, 1), d), dtype=dtype)
             cnt = np.zeros(max(k, 1), dtype=dtype)
         inertia = np.zeros(1, dtype=dtype)
         rng = copy.deepcopy(self._rng)
         st = getattr(_ffi.lib, f"lkm_fit_with_{sfx}")(ctx.h, C.byref(p), _ffi.make_rng(rng), int(model is not None),
+                                                      cen.shape[0], cen.shape[1],
                                                       _ffi.fptr(cen, ct), _ffi.fptr(cnt, ct), _ffi.fptr(inertia, ct))
         if st in _PARAM_ERRORS:
             raise IncrKMeansError("InvalidParams", KMeansParamsError(_PARAM_ERRORS[st]))

@@ -2,10 +2,9 @@
 import ctypes as C, os, sys
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-import linfa_b200 as lb
-from linfa_b200 import _ffi
-ctx = lb.Context.default()
-fn = _ffi.lib.lkm_debug_mma_bench
+from linfa_b200 import _ffi, _probe
+ctx = _probe.ProbeContext()
+fn = _probe.lib.lkm_debug_mma_bench
 fn.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_longlong)]
 def run(n, reps, per, mode, grid=148):
     out = np.zeros(grid, dtype=np.int64)

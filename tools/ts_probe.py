@@ -2,10 +2,9 @@
 import ctypes as C, os, sys
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-import linfa_b200 as lb
-from linfa_b200 import _ffi
-ctx = lb.Context.default()
-fn = _ffi.lib.lkm_debug_tc_ts
+from linfa_b200 import _ffi, _probe
+ctx = _probe.ProbeContext()
+fn = _probe.lib.lkm_debug_tc_ts
 fn.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float)]
 g = np.random.default_rng(1)
 x = (g.standard_normal((128, 32)) * 30).astype(np.float32)
@@ -16,7 +15,7 @@ print("status", st, ctx.error() if st else "")
 tr = lambda a: (a.view(np.uint32) & np.uint32(0xFFFFE000)).view(np.float32)
 ref = tr(x).astype(np.float64) @ tr(c).astype(np.float64).T
 print("TS result vs trunc(x).trunc(c): max abs err", np.abs(s - ref).max(), "scale", np.abs(ref).max())
-bf = _ffi.lib.lkm_debug_mma_bench
+bf = _probe.lib.lkm_debug_mma_bench
 bf.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_longlong)]
 def run(n, reps, per, mode, grid=148):
     out = np.zeros(grid, dtype=np.int64)

@@ -5,11 +5,10 @@ import ctypes as C
 import sys, os
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-import linfa_b200 as lb
-from linfa_b200 import _ffi
+from linfa_b200 import _ffi, _probe
 
-ctx = lb.Context.default()
-fn = _ffi.lib.lkm_debug_umma_raw
+ctx = _probe.ProbeContext()
+fn = _probe.lib.lkm_debug_umma_raw
 fn.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_ulonglong, C.c_ulonglong, C.c_int, C.c_int,
                C.c_uint, C.c_int, C.c_int, C.POINTER(C.c_float)]
 
