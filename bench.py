@@ -1,22 +1,26 @@
 #!/usr/bin/env python
 """bench.py — K-Means Lloyd samples*iterations/s on B200 (BASELINE.json metric).
 
-Workload (N = 1): BASELINE.json configs[1] — KMeans k=64 on 1M x 32 f32 Gaussian
-blobs (linfa_datasets::generate::blobs layout, generated on the device).  A "step"
-is ONE Lloyd iteration (assign every sample to its nearest centroid, recompute
-centroids and inertia) over the whole matrix.  N > 1: one process per GPU, each
-rank holds its own 1M x 32 shard (weak scaling), per-iteration partials are
-all-gathered over NCCL and reduced in rank order.
+Headline workload: BASELINE.json configs[2], the config the metric is quoted on ("1/2/4/8 B200") —
+KMeans k=256 on 10M x 128 f32 Gaussian blobs (linfa_datasets::generate::blobs layout, generated on the
+device).  A "step" is ONE Lloyd iteration (assign every sample to its nearest centroid, recompute
+centroids and inertia) over the whole matrix.  `--gpus N`: one process per GPU, the SAME 10M rows split
+into N contiguous row shards (strong scaling); every iteration the per-rank (k*d sums, k counts, inertia)
+partials are exchanged over NVLink and combined in rank order on every rank.
 
-  value      device-timed (CUDA events on the library's stream), observations resident
-             in HBM, L2 overwritten between steps (outside the timed spans)
-  e2e        the same metric through the public API with HOST buffers: every step copies
-             the observations from pinned host memory, runs one iteration and reads the
-             centroids/inertia back
-  roofline   fused kernel: n*d*sizeof(F) algorithmic bytes per launch / its mean duration,
-             against MEASURED_PEAKS.json hbm_gbs
-  cpu_baseline / --impl reference: the C++ restatement of linfa's rayon/ndarray K-Means
-             (oracle/), all host threads, on a bounded row sample of the same workload
+  value      device-timed (CUDA events on the library's stream), observations resident in HBM (5.12 GB,
+             40x the L2; the smaller side workloads overwrite the L2 between steps, outside the timed spans)
+  e2e        the same metric through the C ABI with HOST buffers: every step copies the observations
+             from pinned host memory, runs one iteration and reads centroids / counts / inertia back
+  roofline   dominant kernel: algorithmic bytes (n*d*sizeof(F)) and flops (2*n*k*d) per launch / its mean
+             duration (CUDA events around the launch) against MEASURED_PEAKS.json; the bound is the
+             roofline with the larger minimum time
+  cpu_baseline / --impl reference: the C++ restatement of linfa's rayon/ndarray K-Means (oracle/),
+             all host threads, on a bounded row sample of the same workload
+  config.other_workloads: the other BASELINE configs in the same run and JSON line — cfg2 (1M x 32, k=64),
+             cfg4 shard (12.5M x 64, k=1024 per GPU = the 100M config at N=8), cfg5 shard (125M x 8 f64, k=16
+             per GPU = the 1B config at N=8), each weak-scaled (fixed rows per GPU), plus the headline shape
+             with hashed (unordered) rows and from a k-means++ start
 """
 import argparse
 import ctypes as C
@@ -32,28 +36,30 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 WORKLOADS = {
-    # name: (rows per GPU, d, k, dtype)
-    "cfg2": (1_000_000, 32, 64, np.float32),
-    "cfg3": (10_000_000, 128, 256, np.float32),   # 10M x 128 total at N=1
-    "cfg4": (12_500_000, 64, 1024, np.float32),   # 100M x 64 over 8 GPUs
-    "cfg5": (125_000_000, 8, 16, np.float64),     # 1B x 8 over 8 GPUs
-    "cfg1": (10_000, 2, 3, np.float64),
+    # name: (rows, d, k, dtype, scaling) — "strong": rows are the TOTAL, split over the GPUs; "weak": rows per GPU
+    "cfg3": (10_000_000, 128, 256, np.float32, "strong"),
+    "cfg2": (1_000_000, 32, 64, np.float32, "weak"),
+    "cfg4": (12_500_000, 64, 1024, np.float32, "weak"),   # 100M x 64 over 8 GPUs
+    "cfg5": (125_000_000, 8, 16, np.float64, "weak"),     # 1B x 8 over 8 GPUs
+    "cfg1": (10_000, 2, 3, np.float64, "weak"),
 }
 WORKLOAD_TEXT = {
+    "cfg3": "KMeans k=256 on 10M x 128 f32 blobs, rows split over the GPUs (BASELINE configs[2]); step = 1 Lloyd iteration",
     "cfg2": "KMeans k=64 on 1M x 32 f32 blobs per GPU (BASELINE configs[1]); step = 1 Lloyd iteration",
-    "cfg3": "KMeans k=256 on 10M x 128 f32 blobs per GPU (BASELINE configs[2]); step = 1 Lloyd iteration",
-    "cfg4": "KMeans k=1024 on 12.5M x 64 f32 blobs per GPU (BASELINE configs[3] shard); step = 1 Lloyd iteration",
-    "cfg5": "KMeans k=16 on 125M x 8 f64 blobs per GPU (BASELINE configs[4] shard); step = 1 Lloyd iteration",
+    "cfg4": "KMeans k=1024 on 12.5M x 64 f32 blobs per GPU (BASELINE configs[3] = 100M x 64 at 8 GPUs); step = 1 Lloyd iteration",
+    "cfg5": "KMeans k=16 on 125M x 8 f64 blobs per GPU (BASELINE configs[4] = 1B x 8 at 8 GPUs); step = 1 Lloyd iteration",
     "cfg1": "KMeans k=3 on 10k x 2 f64 blobs (BASELINE configs[0]); step = 1 Lloyd iteration",
 }
-
-
-DEFAULT_KERNELS = {
-    "cfg2": "lloyd_tc4_kernel (fused assign+update, tcgen05 pipeline)",
-    "cfg3": "assign_tc5s_kernel + update_rows_kernel (CTA-pair tcgen05 assignment, then the streaming update: two passes over X)",
-    "cfg4": "4 x assign_tc5s_kernel (one per 256 centroids) + update_rows_kernel x 2 cluster chunks (six passes over X)",
-    "cfg5": "lloyd_f64s_kernel<8, 1, 2> (f32-screened fused assign+update, f64 d=8 k<=64)",
-    "cfg1": "lloyd_kernel<double> (exact, CUDA cores)",
+KERNELS = {
+    "cfg3": "assign_tc5s_kernel<128,true,256> (CTA-pair tcgen05 screening assignment with the fused update; listed tiles through update_rows_kernel<128>)",
+    "cfg2": "lloyd_tc4_kernel<64,1> (fused assign+update, warp-specialised tcgen05 pipeline)",
+    "cfg4": "4 x assign_tc5s_kernel<64,*,256> (one launch per 256 centroids, the last one with the fused update)",
+    "cfg5": "lloyd_f64s_kernel<8,true,2> (f32-screened fused assign+update for f64 rows)",
+    "cfg1": "lloyd_kernel<double,2,FUSED> (exact, CUDA cores)",
+}
+L2_TEXT = {
+    True: "512 MiB scratch overwritten between steps, then a 256 MiB read-only sweep so that no dirty lines remain; both outside the timed spans",
+    False: "inputs larger than L2 (no flush): X is 40x the 126 MB L2",
 }
 
 
@@ -61,19 +67,24 @@ def load_peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
             p = json.load(f)
-        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        return {"hbm": float(p["hbm_gbs"]), "bf16_burst": float(p["bf16_tflops"]),
+                "bf16_sustained": float(p.get("bf16_tflops_sustained", p["bf16_tflops"])),
+                "source": "measured (MEASURED_PEAKS.json)"}
     except Exception:
-        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+        return {"hbm": 6650.0, "bf16_burst": 1650.0, "bf16_sustained": 1650.0, "source": "fallback (B200_PROFILING.md)"}
 
 
 def load_traffic(workload):
-    """DRAM bytes per launch of the dominant kernel from the committed ncu capture (None if not captured)."""
-    try:
-        with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as f:
-            t = json.load(f).get(workload)
-        return (int(t["dram_bytes_read"]) + int(t["dram_bytes_write"]), t["kernel"]) if t else (None, None)
-    except Exception:
-        return None, None
+    """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture (None if not captured)."""
+    for name in ("r2_traffic.json", "r1_traffic.json"):
+        try:
+            with open(os.path.join(ROOT, "profiles", name)) as f:
+                t = json.load(f).get(workload)
+            if t:
+                return int(t["dram_bytes_read"]) + int(t["dram_bytes_write"]), f"profiles/{name}: {t.get('kernel', '')} ({t.get('capture', 'ncu --set full')})"
+        except Exception:
+            pass
+    return None, None
 
 
 def centres_for(k, d, dtype, seed=1234):
@@ -85,6 +96,30 @@ def start_centroids(centres, seed=99):
     # fixed starting point for the timed Lloyd steps: blob centres + N(0, 0.5) noise
     g = np.random.default_rng(seed)
     return (centres.astype(np.float64) + 0.5 * g.standard_normal(centres.shape)).astype(centres.dtype)
+
+
+def shard_of(workload, rank, world):
+    rows, d, k, dtype, scaling = WORKLOADS[workload]
+    if scaling == "strong":
+        lo = rows * rank // world
+        hi = rows * (rank + 1) // world
+        return hi - lo, lo, rows
+    return rows, rank * rows, world * rows
+
+
+def config_of(workload, world, flush):
+    """The workload description both arms print (identical keys and values)."""
+    rows, d, k, dtype, scaling = WORKLOADS[workload]
+    n_total = rows if scaling == "strong" else rows * world
+    return {"workload": WORKLOAD_TEXT[workload], "rows_total": n_total, "d": d, "k": k, "scaling": scaling,
+            "init": "blob centres + N(0,0.5) (Precomputed); seeding timed separately",
+            "l2": L2_TEXT[bool(flush)]}
+
+
+def needs_flush(workload, world):
+    n, _, _ = shard_of(workload, 0, world)
+    _, d, _, dtype, _ = WORKLOADS[workload]
+    return n * d * np.dtype(dtype).itemsize < 4 * 126 * 1024 * 1024
 
 
 class ClockSampler(threading.Thread):
@@ -144,7 +179,7 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
 
 
-def time_oracle(orc, oracle_lib, n, d, k, dtype, steps, warmup, budget_s=15.0):
+def time_oracle(orc, n, d, k, dtype, steps, warmup, budget_s=15.0):
     """Times Lloyd iterations of the CPU oracle (all host threads) on a bounded row sample."""
     centres = centres_for(k, d, dtype)
     g = np.random.default_rng(7)
@@ -187,20 +222,164 @@ def run_reference(args, rank, world):
     from tests import oracle_lib
 
     orc = oracle_lib.load()
-    n, d, k, dtype = WORKLOADS[args.workload]
-    value, rows, dt, threads = time_oracle(orc, oracle_lib, n, d, k, dtype, args.steps, args.warmup, budget_s=60.0)
-    sample = f"{rows} of {n} rows of the same blobs (k={k}, d={d}), {args.steps} Lloyd iterations, {threads} threads"
+    rows, d, k, dtype, scaling = WORKLOADS[args.workload]
+    n_total = rows if scaling == "strong" else rows * args.gpus
+    value, used, dt, threads = time_oracle(orc, n_total, d, k, dtype, args.steps, args.warmup, budget_s=60.0)
+    sample = f"{used} of {n_total} rows of the same blob distribution (k={k}, d={d}), {args.steps} Lloyd iterations, {threads} threads"
     line = {
         "impl": "reference", "metric": "kmeans_lloyd_samples_iter_per_s", "value": value, "unit": "samples*iter/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "higher_is_better": True, "scaling": scaling, "vs_baseline": None,
         "dtype": "f32" if dtype == np.float32 else "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD_TEXT[args.workload], "k": k, "d": d, "rows_timed": rows,
-                   "what": "C++ restatement of linfa's rayon/ndarray K-Means (oracle/); linfa itself needs cargo, absent here"},
+        "config": config_of(args.workload, args.gpus, needs_flush(args.workload, args.gpus)),
+        "detail": {"rows_timed": used,
+                   "what": "C++ restatement of linfa's rayon/ndarray K-Means (oracle/), assignment on all host threads, serial update; "
+                           "linfa itself needs cargo, absent here"},
         "cpu_baseline": {"value": value, "unit": "samples*iter/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "samples*iter/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
+
+
+class Runner:
+    def __init__(self, args, rank, world, local_rank):
+        import torch
+
+        import linfa_b200 as lb
+
+        self.torch, self.lb = torch, lb
+        self.args, self.rank, self.world, self.local_rank = args, rank, world, local_rank
+        torch.cuda.set_device(local_rank)
+        self.dist = None
+        if world > 1:
+            import torch.distributed as dist
+
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+            self.dist = dist
+        self.ctx = lb.Context(local_rank)
+        if world > 1:
+            from linfa_b200 import distributed as D
+
+            D.init_comm(self.ctx, device=torch.device("cuda", local_rank))
+        if args.assign_path >= 0:
+            self.ctx.set_assign_path(args.assign_path)
+        self.peaks = load_peaks()
+
+    def barrier(self):
+        self.torch.cuda.synchronize()
+        if self.dist is not None:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def allmax(self, v):
+        if self.dist is None:
+            return v
+        t = self.torch.tensor([v], dtype=self.torch.float64, device="cuda")
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def generate(self, workload, shuffled=False):
+        rows, d, k, dtype, scaling = WORKLOADS[workload]
+        n, off, n_total = shard_of(workload, self.rank, self.world)
+        centres = centres_for(k, d, dtype)
+        self.ctx.set_blob_layout(shuffled)
+        self.ctx.gen_blobs(n, d, centres, 1.0, seed=2024, row_offset=off, n_global=n_total)
+        self.ctx.set_blob_layout(False)
+        return n, n_total, d, k, dtype, centres
+
+    def timed_steps(self, c0, steps, warmup, flush, kernel_timing=True, hold_s=1.0):
+        """W warm-up + K timed Lloyd steps; returns device ms (max over ranks), kernel ms, stats, clocks."""
+        ctx = self.ctx
+        ctx.set_l2_flush(512 * 1024 * 1024 if flush else 0)
+        ctx.set_kernel_timing(False)
+        ctx.lloyd_iters(c0, warmup, 0.0)
+        sampler = ClockSampler(self.local_rank)
+        sampler.start()
+        self.barrier()
+        t0 = time.perf_counter()
+        _, _, _, st = ctx.lloyd_iters(c0, steps, 0.0)
+        self.barrier()
+        wall_ms = 1e3 * (time.perf_counter() - t0)
+        assert st.n_iter == steps, (st.n_iter, steps)
+        dev_ms = self.allmax(float(st.device_ms))
+        launches, fallback = int(st.kernel_launches), int(st.fallback_rows & ((1 << 40) - 1))
+        main_ms = None
+        if kernel_timing:
+            # the dominant kernel on its own (extra event per step; not the run `value` comes from).  The per-step event
+            # mode needs the flush path, so shapes larger than L2 use a 1-byte "flush".
+            ctx.set_l2_flush(512 * 1024 * 1024 if flush else 64)
+            ctx.set_kernel_timing(True)
+            ctx.lloyd_iters(c0, warmup, 0.0)
+            self.barrier()
+            _, _, _, st_k = ctx.lloyd_iters(c0, steps, 0.0)
+            main_ms = self.allmax(float(st_k.main_kernel_ms))
+            ctx.set_kernel_timing(False)
+            ctx.set_l2_flush(512 * 1024 * 1024 if flush else 0)
+        # keep the same load running so that NVML sees the clocks of this kernel mix
+        t_end = time.perf_counter() + hold_s
+        while time.perf_counter() < t_end:
+            ctx.lloyd_iters(c0, steps, 0.0)
+        clocks = sampler.result()
+        ctx.set_l2_flush(0)
+        return dev_ms, main_ms, launches, fallback, wall_ms, clocks
+
+    def roofline(self, workload, n, d, k, dtype, main_ms, steps):
+        if not main_ms:
+            return None
+        itemsize = np.dtype(dtype).itemsize
+        per_launch_s = main_ms * 1e-3 / steps
+        gbs = n * d * itemsize / per_launch_s / 1e9
+        tfl = 2.0 * n * k * d / per_launch_s / 1e12
+        pk = self.peaks
+        hbm = {"achieved": gbs, "peak": pk["hbm"], "unit": "GB/s", "frac": gbs / pk["hbm"]}
+        out = {"kernel": KERNELS.get(workload), "algorithmic_bytes_per_launch": n * d * itemsize,
+               "algorithmic_flops_per_launch": 2 * n * k * d, "mean_launch_us": per_launch_s * 1e6,
+               "peak_source": pk["source"], "hbm": hbm}
+        if dtype == np.float32 and d >= 32:
+            # TF32 dense peak = half of the measured bf16 rate; the sustained figure, because the kernel is timed inside a
+            # long loop (the clocks line shows the power cap it runs under)
+            tpk = 0.5 * pk["bf16_sustained"]
+            out["tensor"] = {"achieved": tfl, "peak": tpk, "unit": "TFLOP/s", "frac": tfl / tpk,
+                             "peak_burst": 0.5 * pk["bf16_burst"], "frac_of_burst": tfl / (0.5 * pk["bf16_burst"]),
+                             "what": "2*n*k*d flops of ONE TF32 product (the screening pass the kernel executes) against half the measured bf16 rate"}
+        # the binding roofline is the one with the larger minimum time
+        t_hbm = n * d * itemsize / (pk["hbm"] * 1e9)
+        t_tc = (2.0 * n * k * d / (out["tensor"]["peak"] * 1e12)) if "tensor" in out else 0.0
+        b = out["tensor"] if t_tc > t_hbm else hbm
+        out.update({"bound": "tensor" if t_tc > t_hbm else "hbm", "achieved": b["achieved"], "peak": b["peak"],
+                    "unit": b["unit"], "frac": b["frac"]})
+        traffic, src = load_traffic(workload)
+        out["traffic"] = traffic
+        out["traffic_source"] = src
+        return out
+
+    def side(self, workload, steps, warmup, shuffled=False, kmeanspp_start=False):
+        """One side workload: value, kernel time and roofline fractions, clocks."""
+        n, n_total, d, k, dtype, centres = self.generate(workload, shuffled)
+        c0 = start_centroids(centres)
+        extra = {}
+        if kmeanspp_start:
+            lb = self.lb
+            p = lb.KMeans.params_with_rng(k, lb.Xoshiro256Plus.seed_from_u64(40)).n_runs(1).pick_mode(lb.PickMode.Fast).check()
+            t0 = time.perf_counter()
+            c0 = p.init_centroids_resident(self.ctx)
+            extra["kmeanspp_fast_init_ms"] = 1e3 * (time.perf_counter() - t0)
+        flush = needs_flush(workload, self.world)
+        dev_ms, main_ms, launches, fallback, _, clocks = self.timed_steps(c0, steps, warmup, flush, hold_s=0.5)
+        rf = self.roofline(workload, n, d, k, dtype, main_ms, steps)
+        out = {"workload": WORKLOAD_TEXT[workload], "rows_per_gpu": n, "rows_total": n_total, "d": d, "k": k,
+               "dtype": "f32" if dtype == np.float32 else "f64",
+               "rows": "hashed blob per row (unordered)" if shuffled else "blob-ordered (generate::blobs)",
+               "start": "k-means++ (fast pick) on the resident rows" if kmeanspp_start else "blob centres + N(0,0.5)",
+               "value": n_total * steps / (dev_ms * 1e-3), "unit": "samples*iter/s", "ms_per_step": dev_ms / steps,
+               "steps": steps, "warmup": warmup, "l2": L2_TEXT[flush], "gpu_launches": launches,
+               "rows_rescanned_exactly": fallback,
+               "kernel_us": (main_ms * 1e3 / steps) if main_ms else None,
+               "hbm_frac": rf["hbm"]["frac"] if rf else None,
+               "tensor_frac": rf["tensor"]["frac"] if rf and "tensor" in rf else None,
+               "bound": rf["bound"] if rf else None, "clocks": clocks}
+        out.update(extra)
+        return out
 
 
 def main():
@@ -209,13 +388,19 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS))
     ap.add_argument("--assign-path", type=int, default=-1)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--no-init", action="store_true", help="skip the separately timed k-means++ seeding")
-    ap.add_argument("--no-flush", action="store_true", help="keep L2 warm between steps (not the headline)")
+    ap.add_argument("--no-init", action="store_true", help="skip the separately timed seeding")
+    ap.add_argument("--no-others", action="store_true", help="skip config.other_workloads")
+    ap.add_argument("--shuffled", action="store_true", help="headline workload with hashed (unordered) rows")
+    ap.add_argument("--rows", type=int, default=0, help="override the workload's row count (tuning aid, not the headline)")
     args = ap.parse_args()
+    if args.rows:
+        w = WORKLOADS[args.workload]
+        WORKLOADS[args.workload] = (args.rows,) + w[1:]
+        WORKLOAD_TEXT[args.workload] += f" [rows overridden: {args.rows}]"
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -225,131 +410,70 @@ def main():
         run_reference(args, rank, world)
         return
 
-    import torch
-
-    import linfa_b200 as lb
+    R = Runner(args, rank, world, local_rank)
+    ctx, lb, torch = R.ctx, R.lb, R.torch
     from linfa_b200 import _ffi
 
-    torch.cuda.set_device(local_rank)
-    dist = None
-    if world > 1:
-        import torch.distributed as dist
-
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    ctx = lb.Context(local_rank)
-    if world > 1:
-        from linfa_b200 import distributed as D
-
-        D.init_comm(ctx, device=torch.device("cuda", local_rank))
-
-    n, d, k, dtype = WORKLOADS[args.workload]
+    n, n_total, d, k, dtype, centres = R.generate(args.workload, args.shuffled)
     itemsize = np.dtype(dtype).itemsize
-    centres = centres_for(k, d, dtype)
     c0 = start_centroids(centres)
-    tiny = 0.0  # lkm_lloyd_iters: tolerance 0 = run exactly `steps` iterations
-    if args.assign_path >= 0:
-        ctx.set_assign_path(args.assign_path)
-    ctx.gen_blobs(n, d, centres, 1.0, seed=2024, row_offset=rank * n, n_global=world * n)
-
-    def barrier():
-        torch.cuda.synchronize()
-        if dist is not None:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def allmax(v):
-        if dist is None:
-            return v
-        t = torch.tensor([v], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
+    flush = needs_flush(args.workload, world)
 
     # ---- seeding, timed separately (init is not part of the Lloyd metric) ----
-    init_ms = None
-    if world == 1 and n <= 20_000_000 and not args.no_init:
-        p = lb.KMeans.params_with_rng(k, lb.Xoshiro256Plus.seed_from_u64(40)).n_runs(1).pick_mode(lb.PickMode.Fast).check()
-        pp, _keep = p._native_params(dtype)
-        out = np.zeros((k, d), dtype=dtype)
-        sfx, ct = _ffi.sfx_of(dtype)
-        t0 = time.perf_counter()
-        st = getattr(_ffi.lib, f"lkm_init_{sfx}")(ctx.h, C.byref(pp), _ffi.make_rng(lb.Xoshiro256Plus.seed_from_u64(40)),
-                                                  _ffi.fptr(out, ct))
-        ctx.check(st)
-        init_ms = 1e3 * (time.perf_counter() - t0)
+    init = {}
+    if world == 1 and not args.no_init:
+        for name, method in (("kmeanspp_fast_init_ms", lb.KMeansInit.KMeansPlusPlus), ("kmeans_para_init_ms", lb.KMeansInit.KMeansPara)):
+            p = (lb.KMeans.params_with_rng(k, lb.Xoshiro256Plus.seed_from_u64(40)).n_runs(1).init_method(method)
+                 .pick_mode(lb.PickMode.Fast).check())
+            t0 = time.perf_counter()
+            p.init_centroids_resident(ctx)
+            init[name] = 1e3 * (time.perf_counter() - t0)
 
     # ---- device-resident leg ----
-    flush_bytes = 0 if args.no_flush else 512 * 1024 * 1024
-    ctx.set_l2_flush(flush_bytes)
-    ctx.lloyd_iters(c0, args.warmup, tiny)  # W untimed warm-up steps
-    sampler = ClockSampler(local_rank)
-    sampler.start()
-    barrier()
-    t0 = time.perf_counter()
-    cen, counts, inertia, st = ctx.lloyd_iters(c0, args.steps, tiny)
-    barrier()
-    wall_ms = 1e3 * (time.perf_counter() - t0)
-    assert st.n_iter == args.steps, (st.n_iter, args.steps)
-    dev_ms = allmax(float(st.device_ms))
-    launches = int(st.kernel_launches)
-    # the dominant kernel on its own (extra event per step; not the run `value` comes from)
-    main_ms = None
-    if flush_bytes:
-        ctx.set_kernel_timing(True)
-        ctx.lloyd_iters(c0, args.warmup, tiny)
-        barrier()
-        _, _, _, st_k = ctx.lloyd_iters(c0, args.steps, tiny)
-        main_ms = allmax(float(st_k.main_kernel_ms))
-        ctx.set_kernel_timing(False)
-    # keep the same load running ~1.5 s so that NVML sees the clocks of this kernel mix
-    t_end = time.perf_counter() + 1.5
-    while time.perf_counter() < t_end:
-        ctx.lloyd_iters(c0, args.steps, tiny)
-    clocks = sampler.result()
-    value = world * n * args.steps / (dev_ms * 1e-3)
+    dev_ms, main_ms, launches, fallback, wall_ms, clocks = R.timed_steps(c0, args.steps, args.warmup, flush)
+    value = n_total * args.steps / (dev_ms * 1e-3)
+    roofline = R.roofline(args.workload, n, d, k, dtype, main_ms, args.steps)
 
-    # L2-warm figure (what a real fit sees after the first iteration), for the record
-    ctx.set_l2_flush(0)
-    ctx.lloyd_iters(c0, args.warmup, tiny)
-    barrier()
-    _, _, _, st_warm = ctx.lloyd_iters(c0, args.steps, tiny)
-    warm_ms = allmax(float(st_warm.device_ms))
-
-    # ---- roofline of the dominant (fused assign+update) kernel ----
-    peak, peak_src = load_peaks()
-    roofline = None
-    if main_ms:
-        per_launch_s = main_ms * 1e-3 / args.steps
-        achieved = n * d * itemsize / per_launch_s / 1e9
-        traffic, kname = load_traffic(args.workload)
-        roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                    "traffic": traffic, "kernel": kname or DEFAULT_KERNELS.get(args.workload, "fused assign+update kernel"),
-                    "algorithmic_bytes_per_launch": n * d * itemsize, "mean_launch_us": per_launch_s * 1e6,
-                    "peak_source": peak_src}
-
-    # ---- end-to-end leg: host buffers through the public API, copies inside the timed region ----
+    # ---- end-to-end leg: host buffers through the C ABI, copies inside the timed region ----
     e2e = None
     if not args.no_e2e:
-        e2e_rows = n
-        host = torch.empty((e2e_rows, d), dtype=torch.float32 if dtype == np.float32 else torch.float64,
-                           pin_memory=True)
+        host = torch.empty((n, d), dtype=torch.float32 if dtype == np.float32 else torch.float64, pin_memory=True)
         hx = host.numpy()
-        hx[...] = ctx.get_data(0, e2e_rows)
+        chunk = max(1, (256 << 20) // (d * itemsize))
+        for r0 in range(0, n, chunk):
+            hx[r0:r0 + chunk] = ctx.get_data(r0, min(chunk, n - r0))
         e2e_steps = max(3, min(args.steps, 10))
         cur = c0.copy()
         for _ in range(2):
-            ctx.set_data(hx)
-            ctx.lloyd_iters(cur, 1, tiny)
-        barrier()
+            ctx.set_data_sharded(hx, shard_of(args.workload, rank, world)[1], n_total)
+            ctx.lloyd_iters(cur, 1, 0.0)
+        R.barrier()
         t0 = time.perf_counter()
         for _ in range(e2e_steps):
-            ctx.set_data(hx)                                   # H2D of the step's observations (pinned)
-            cur, cnts, inert, _s = ctx.lloyd_iters(cur, 1, tiny)  # H2D centroids, 1 iteration, D2H result
-        barrier()
-        e2e_s = allmax(time.perf_counter() - t0)
-        e2e = {"value": world * e2e_rows * e2e_steps / e2e_s, "unit": "samples*iter/s",
-               "h2d_bytes_per_step": int(e2e_rows * d * itemsize + k * d * itemsize),
-               "d2h_bytes_per_step": int(k * d * itemsize + k * 8 + 64), "steps": e2e_steps,
-               "ms_per_step": 1e3 * e2e_s / e2e_steps}
+            ctx.set_data_sharded(hx, shard_of(args.workload, rank, world)[1], n_total)   # H2D of the step's observations (pinned)
+            cur, cnts, inert, _s = ctx.lloyd_iters(cur, 1, 0.0)                          # H2D centroids, 1 iteration, D2H result
+        R.barrier()
+        e2e_s = R.allmax(time.perf_counter() - t0)
+        e2e = {"value": n_total * e2e_steps / e2e_s, "unit": "samples*iter/s",
+               "h2d_bytes_per_step": int(n * d * itemsize + k * d * itemsize),
+               "d2h_bytes_per_step": int(k * d * itemsize + k * itemsize + itemsize + 64), "steps": e2e_steps,
+               "ms_per_step": 1e3 * e2e_s / e2e_steps, "bytes_are": "per rank"}
+        del host, hx
+
+    # ---- the other BASELINE configs and the unordered / k-means++-started variants, same run ----
+    others = None
+    if not args.no_others:
+        others = {}
+        s2, w2 = args.steps, args.warmup
+        plan = [("cfg3_hashed_rows", "cfg3", True, False), ("cfg2", "cfg2", False, False), ("cfg2_hashed_rows", "cfg2", True, False),
+                ("cfg4_shard", "cfg4", False, False), ("cfg5_shard", "cfg5", False, False)]
+        if world == 1:
+            plan.insert(1, ("cfg3_kmeanspp_start", "cfg3", False, True))
+        for name, wl, sh, kpp in plan:
+            try:
+                others[name] = R.side(wl, s2, w2, shuffled=sh, kmeanspp_start=kpp)
+            except Exception as e:  # a side workload must not take the headline down
+                others[name] = {"error": repr(e)}
 
     # ---- CPU baseline (rank 0, N = 1 only) ----
     cpu = None
@@ -357,31 +481,31 @@ def main():
         from tests import oracle_lib
 
         orc = oracle_lib.load()
-        v, rows, dt, threads = time_oracle(orc, oracle_lib, n, d, k, dtype, 3, 1, budget_s=15.0)
+        v, rows, dt, threads = time_oracle(orc, n_total, d, k, dtype, 3, 1, budget_s=15.0)
         cpu = {"value": v, "unit": "samples*iter/s", "cores": threads, "kind": "port",
-               "sample": f"{rows} of {n} rows of the same blob distribution, 3 Lloyd iterations (+1 warm-up), "
+               "sample": f"{rows} of {n_total} rows of the same blob distribution, 3 Lloyd iterations (+1 warm-up), "
                          f"C++ restatement of linfa (oracle/), {threads} threads"}
 
     if rank == 0:
+        cfg = config_of(args.workload, world, flush)
+        if args.shuffled:
+            cfg["rows"] = "hashed blob per row (unordered)"
+        cfg["other_workloads"] = others
         line = {
             "metric": "kmeans_lloyd_samples_iter_per_s", "value": value, "unit": "samples*iter/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "higher_is_better": True, "scaling": WORKLOADS[args.workload][4], "vs_baseline": None,
             "dtype": "f32" if dtype == np.float32 else "f64", "data": "synthetic",
-            "config": {"workload": WORKLOAD_TEXT[args.workload], "rows_per_gpu": n, "d": d, "k": k,
-                       "init": "blob centres + N(0,0.5) (Precomputed); k-means++ timed separately",
-                       "kmeanspp_fast_init_ms": init_ms,
-                       "l2": ("512 MiB scratch overwritten between steps, then a 256 MiB read-only sweep so that no dirty lines remain; both outside the timed spans" if flush_bytes
-                              else "no flush (L2 warm)"),
-                       "l2_warm_ms_per_step": warm_ms / args.steps,
-                       "wall_ms_per_step_incl_flush": wall_ms / args.steps,
-                       "parallelism": f"row-sharded x{world}, all-gather of per-rank partials" if world > 1 else "1 GPU"},
+            "config": cfg,
+            "detail": {"rows_per_gpu": n, "wall_ms_per_step": wall_ms / args.steps, "rows_rescanned_exactly": fallback,
+                       "parallelism": (f"row-sharded x{world}, per-rank partials exchanged over NVLink (P2P stores + flags) and combined in rank order"
+                                       if world > 1 else "1 GPU"), **init},
             "clocks": clocks, "gpu_launches": launches, "e2e": e2e, "roofline": roofline, "cpu_baseline": cpu,
         }
         print(json.dumps(line), flush=True)
-    if dist is not None:
-        dist.barrier()
-        dist.destroy_process_group()
+    if R.dist is not None:
+        R.dist.barrier()
+        R.dist.destroy_process_group()
     ctx.close()
 
 

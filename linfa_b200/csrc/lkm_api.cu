@@ -141,7 +141,6 @@ struct lkm_ctx {
   size_t p2p_cap = 0;
   unsigned long long p2p_epoch = 0;
   int p2p_enabled = 1;  // LKM_P2P=0 falls back to ncclAllGather
-  DevBuf publish_done;
   uint32_t launches = 0;
 };
 
@@ -378,7 +377,8 @@ static lkm_status p2p_setup(lkm_ctx* ctx, size_t L) {
   ctx->p2p_peer.clear();
   if (ctx->p2p_local) { cudaFree(ctx->p2p_local); ctx->p2p_local = nullptr; }
   const size_t cap = std::max<size_t>(L, 4096);
-  const size_t bytes = (2 * (size_t)world * cap + 3 * (size_t)world) * 8;   // partials | exchange flags | barrier flags
+  // [2 parities][world][cap] partials | [2][world][kFxMaxCtas] exchange flags | [world] barrier flags
+  const size_t bytes = (2 * (size_t)world * cap + 2 * (size_t)world * kFxMaxCtas + (size_t)world) * 8;
   int ok = 1;
   cudaIpcMemHandle_t mine;
   std::memset(&mine, 0, sizeof(mine));
@@ -416,8 +416,6 @@ static lkm_status p2p_setup(lkm_ctx* ctx, size_t L) {
     return LKM_OK;
   }
   ctx->p2p_cap = cap;
-  CK(ctx->publish_done.ensure(16));
-  CK(cudaMemsetAsync(ctx->publish_done.p, 0, 16, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
   return LKM_OK;
 }
@@ -771,7 +769,7 @@ static lkm_status run_lloyd(lkm_ctx* ctx, F* dC2, uint64_t k, uint64_t max_iter,
   CK(ctx->part_counts.ensure((size_t)grid * k * 4));
   CK(ctx->part_inertia.ensure((size_t)std::max(grid, 1024) * 8));
   const int fin_grid = (int)((kd + kFinElems - 1) / kFinElems);
-  CK(ctx->shift_part.ensure((size_t)std::max(fin_grid, grid) * 8));
+  CK(ctx->shift_part.ensure((size_t)std::max(std::max(fin_grid, grid), kFxMaxCtas) * 8));
   // pipeline kernel on one GPU: optionally the finalize step folded into the kernel tail (LKM_FUSED_FINALIZE=1; off by default)
   const bool fin_fused = use_tc && tc_threads == kT4Threads && ctx->world == 1 && ctx->fused_finalize && tc_grid <= ctx->sm_count;
   if (fin_fused) {
@@ -844,8 +842,8 @@ static lkm_status run_lloyd(lkm_ctx* ctx, F* dC2, uint64_t k, uint64_t max_iter,
           const size_t cap = ctx->p2p_cap, w = (size_t)ctx->world;
           rb.world = ctx->world; rb.epoch = ++ctx->bar_epoch;
           for (int pr = 0; pr < ctx->world; ++pr)
-            rb.peer[pr] = reinterpret_cast<unsigned long long*>(reinterpret_cast<double*>(ctx->p2p_peer[pr]) + 2 * w * cap) + 2 * w + (size_t)ctx->rank;
-          rb.mine = reinterpret_cast<const unsigned long long*>(reinterpret_cast<double*>(ctx->p2p_local) + 2 * w * cap) + 2 * w;
+            rb.peer[pr] = reinterpret_cast<unsigned long long*>(reinterpret_cast<double*>(ctx->p2p_peer[pr]) + 2 * w * cap) + 2 * w * kFxMaxCtas + (size_t)ctx->rank;
+          rb.mine = reinterpret_cast<const unsigned long long*>(reinterpret_cast<double*>(ctx->p2p_local) + 2 * w * cap) + 2 * w * kFxMaxCtas;
           rank_barrier_kernel<<<1, 32, 0, ctx->stream>>>(rb);
           CK(cudaGetLastError());
         }
@@ -1016,7 +1014,36 @@ static lkm_status run_lloyd(lkm_ctx* ctx, F* dC2, uint64_t k, uint64_t max_iter,
         fa.shift_part = ctx->shift_part.as<double>(); fa.state = dstate; fa.tol = tol; fa.max_iter = max_iter;
         CK((launch_finalize<F, F, uint32_t, true>(fa, ctx->stream)));
         ctx->launches++;
+      } else if (use_p2p) {
+        // one launch: local reduction -> NVLink stores into every rank's gather buffer + per-CTA flags -> wait -> combine
+        // in rank order -> update (finalize_x_kernel)
+        FinalizeXArgs<F, F, uint32_t> xa{};
+        xa.src_sums = ctx->part_sums.as<F>(); xa.src_counts = ctx->part_counts.as<uint32_t>();
+        xa.src_inertia = ctx->part_inertia.as<double>();
+        xa.sum_stride = kd; xa.cnt_stride = k; xa.inertia_stride = 1; xa.n_src = fin_src; xa.n_src_inertia = fin_src_inertia;
+        xa.k = (int)k; xa.d = (int)d;
+        const int n_slices = (int)((kd + kFinElems - 1) / kFinElems);
+        const int g_max = std::min(kFxMaxCtas, 2 * ctx->sm_count);
+        xa.slices_per_cta = (n_slices + g_max - 1) / g_max;
+        const int xgrid = (n_slices + xa.slices_per_cta - 1) / xa.slices_per_cta;
+        const unsigned long long epoch = ++ctx->p2p_epoch;
+        const size_t par = (size_t)(epoch & 1);
+        const size_t cap = ctx->p2p_cap, w = (size_t)ctx->world;
+        for (int pr = 0; pr < ctx->world; ++pr) {
+          double* base = reinterpret_cast<double*>(ctx->p2p_peer[pr]);
+          xa.peer_out[pr] = base + (par * w + (size_t)ctx->rank) * cap;
+          xa.peer_flags[pr] = reinterpret_cast<unsigned long long*>(base + 2 * w * cap) + (par * w + (size_t)ctx->rank) * kFxMaxCtas;
+        }
+        double* mine = reinterpret_cast<double*>(ctx->p2p_local);
+        xa.gather = mine + par * w * cap;
+        xa.my_flags = reinterpret_cast<const unsigned long long*>(mine + 2 * w * cap) + par * w * kFxMaxCtas;
+        xa.cap = cap; xa.world = ctx->world; xa.epoch = epoch;
+        xa.C_old = Ccur; xa.C_new = Cnext; xa.counts_out = ctx->counts_out.as<double>();
+        xa.shift_part = ctx->shift_part.as<double>(); xa.state = dstate; xa.tol = tol; xa.max_iter = max_iter;
+        CK(launch_pdl(finalize_x_kernel<F, F, uint32_t>, xgrid, kFinThreads, 0, ctx->stream, xa, true));
+        ctx->launches += 1;
       } else {
+        // NCCL fallback (LKM_P2P=0 or no peer access): reduce -> ncclAllGather -> combine, three launches
         FinalizeArgs<F, F, uint32_t> ra{};
         ra.src_sums = ctx->part_sums.as<F>(); ra.src_counts = ctx->part_counts.as<uint32_t>();
         ra.src_inertia = ctx->part_inertia.as<double>();
@@ -1025,35 +1052,13 @@ static lkm_status run_lloyd(lkm_ctx* ctx, F* dC2, uint64_t k, uint64_t max_iter,
         ra.rank_out = ctx->gather.as<double>() + (size_t)ctx->rank * L;
         ra.state = dstate;
         FinalizeArgs<F, double, double> fa{};
-        const double* gbase = ctx->gather.as<double>();
-        size_t gstride = L;
-        if (use_p2p) {
-          // one-shot exchange over NVLink: store this rank's partial into every peer's slot, raise flags
-          const unsigned long long epoch = ++ctx->p2p_epoch;
-          const size_t par = (size_t)(epoch & 1);
-          const size_t cap = ctx->p2p_cap, w = (size_t)ctx->world;
-          ra.n_peers = ctx->world;
-          ra.flag_value = epoch;
-          ra.publish_done = ctx->publish_done.as<unsigned int>();
-          for (int pr = 0; pr < ctx->world; ++pr) {
-            double* base = reinterpret_cast<double*>(ctx->p2p_peer[pr]);
-            ra.peer_out[pr] = base + (par * w + (size_t)ctx->rank) * cap;
-            ra.peer_flags[pr] = reinterpret_cast<unsigned long long*>(base + 2 * w * cap) + par * w + (size_t)ctx->rank;
-          }
-          double* mine = reinterpret_cast<double*>(ctx->p2p_local);
-          gbase = mine + par * w * cap;
-          gstride = cap;
-          fa.wait_flags = reinterpret_cast<const unsigned long long*>(mine + 2 * w * cap) + par * w;
-          fa.n_wait = ctx->world;
-          fa.flag_value = epoch;
-        }
         CK((launch_finalize<F, F, uint32_t, false>(ra, ctx->stream)));
-        if (!use_p2p)
-          CKN(g_nccl.AllGather(ctx->gather.as<double>() + (size_t)ctx->rank * L, ctx->gather.as<double>(), L, kNcclFloat64,
-                               ctx->comm, ctx->stream));
+        CKN(g_nccl.AllGather(ctx->gather.as<double>() + (size_t)ctx->rank * L, ctx->gather.as<double>(), L, kNcclFloat64,
+                             ctx->comm, ctx->stream));
+        const double* gbase = ctx->gather.as<double>();
         fa.src_sums = gbase; fa.src_counts = gbase + kd;
         fa.src_inertia = gbase + kd + k;
-        fa.sum_stride = gstride; fa.cnt_stride = gstride; fa.inertia_stride = gstride; fa.n_src = ctx->world; fa.k = (int)k; fa.d = (int)d;
+        fa.sum_stride = L; fa.cnt_stride = L; fa.inertia_stride = L; fa.n_src = ctx->world; fa.k = (int)k; fa.d = (int)d;
         fa.C_old = Ccur; fa.C_new = Cnext; fa.counts_out = ctx->counts_out.as<double>();
         fa.shift_part = ctx->shift_part.as<double>(); fa.state = dstate; fa.tol = tol; fa.max_iter = max_iter;
         CK((launch_finalize<F, double, double, true>(fa, ctx->stream)));
@@ -1717,7 +1722,8 @@ static lkm_status fit_impl(lkm_ctx* ctx, const lkm_params* p, lkm_rng rng_in, F*
   CK(cudaSetDevice(ctx->device));
   const uint64_t k = p->n_clusters, d = ctx->d, kd = k * d;
   const uint64_t n_glob = ctx->n_global ? ctx->n_global : ctx->n;
-  if (ctx->n == 0 || d == 0) return fail(ctx, LKM_ERR_SHAPE, "empty dataset");
+  // an empty SHARD is legal (its partials are zeros; every rank still takes part in each exchange); an empty data set is not
+  if (n_glob == 0 || d == 0) return fail(ctx, LKM_ERR_SHAPE, "empty dataset");
   HostRng rng{rng_in};
   CK(ctx->cbuf.ensure(2 * kd * sizeof(F)));
   F* dC2 = ctx->cbuf.as<F>();
@@ -2026,7 +2032,7 @@ LKM_EXPORT lkm_status lkm_destroy(lkm_ctx* ctx) {
   if (ctx->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->comm);
   DevBuf* bufs[] = {&ctx->xbuf, &ctx->cbuf, &ctx->part_sums, &ctx->part_counts, &ctx->part_inertia, &ctx->shift_part,
                     &ctx->counts_out, &ctx->state, &ctx->gather, &ctx->gather2, &ctx->labels, &ctx->dists, &ctx->wdists, &ctx->cum,
-                    &ctx->scratch, &ctx->tmpx, &ctx->tmpc, &ctx->idxbuf, &ctx->bsum, &ctx->weights, &ctx->flushbuf, &ctx->fin_sync, &ctx->para_c2, &ctx->tca_bsplit, &ctx->tca_cn, &ctx->tca_cmax, &ctx->publish_done};
+                    &ctx->scratch, &ctx->tmpx, &ctx->tmpc, &ctx->idxbuf, &ctx->bsum, &ctx->weights, &ctx->flushbuf, &ctx->fin_sync, &ctx->para_c2, &ctx->tca_bsplit, &ctx->tca_cn, &ctx->tca_cmax};
   for (DevBuf* b : bufs) b->release();
   for (cudaEvent_t e : ctx->iter_events) cudaEventDestroy(e);
   if (ctx->h_state) cudaFreeHost(ctx->h_state);

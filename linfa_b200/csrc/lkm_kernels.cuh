@@ -462,11 +462,12 @@ __global__ void __launch_bounds__(kThreads) lloyd_kernel(const LloydArgs<F> a) {
 }
 
 // ---------------------------------------------------------------------------
-// finalize: sum `n_src` partial vectors in ascending source order (f64), then
-// either publish the per-rank partial (world > 1, before the all-gather) or do
-// the m_k-means update.  grid = ceil(k*d / 64) CTAs of 256 threads: thread
-// (g, e) sums sources b = g, g+4, ... for element e; the four groups are then
-// added in order.  The last CTA to finish reduces the shift and the inertia.
+// finalize: sum `n_src` partial vectors in a fixed order (f64), then either write the
+// per-rank partial (NCCL fallback of the multi-GPU path, before the all-gather) or do
+// the m_k-means update.  grid = ceil(k*d / 16) CTAs of 256 threads: thread (g, e) sums
+// sources b = g, g+16, ... for element e; the 16 groups are then added in order.  The
+// last CTA to finish reduces the shift and the inertia.  (Row-sharded runs with NVLink
+// peer access use finalize_x_kernel below instead: one launch for the whole exchange.)
 // ---------------------------------------------------------------------------
 template <typename F, typename S, typename CT> struct FinalizeArgs {
   const S* src_sums;          // source b, element e at src_sums[b*sum_stride + e]
@@ -478,16 +479,6 @@ template <typename F, typename S, typename CT> struct FinalizeArgs {
   int k, d;
   // reduce-only output (per-rank partial): [kd sums | k counts | 1 inertia] as f64
   double* rank_out;
-  // NVLink one-shot exchange (row-sharded runs): the partial is stored straight into every peer's
-  // gather slot for this rank (peer memory mapped through CUDA IPC), then a flag is raised there
-  double* peer_out[8];
-  unsigned long long* peer_flags[8];
-  int n_peers;
-  unsigned long long flag_value;
-  unsigned int* publish_done;   // CTA counter for the last-block-raises-flags pattern
-  // update side: wait until every rank's flag shows flag_value before reading the gathered partials
-  const unsigned long long* wait_flags;
-  int n_wait;
   // update outputs
   const F* C_old;
   F* C_new;
@@ -497,6 +488,14 @@ template <typename F, typename S, typename CT> struct FinalizeArgs {
   double tol;
   unsigned long long max_iter;
 };
+
+// peers may be a whole kernel behind (uneven shards, exact re-scans): waits on their flags are bounded by time, not spins
+constexpr unsigned long long kPeerWaitNs = 20ull * 1000ull * 1000ull * 1000ull;
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 
 constexpr int kFinElems = 16;    // elements (of the k*d sums) per CTA
 constexpr int kFinGroups = 16;   // source groups per element; CTA = kFinElems * kFinGroups threads
@@ -515,40 +514,21 @@ __device__ __forceinline__ double block_sum(double v, double* red) {
   return tot;
 }
 
-// sum of src[b*stride + e] over b = g, g+G, g+2G, ... with four independent chains; the association is fixed, hence
-// reproducible.  Up to 16 sources per group (n_src <= 256: every single-GPU grid of the fused kernels) are loaded in one
-// batch before the first addition, so the sum costs one L2 round trip instead of one per four sources.
+// sum of src[b*stride + e] over b = g, g+G, g+2G, ... : batches of 16 sources per thread are loaded before the first
+// addition (one L2 round trip per 256 sources), then added into four chains in a fixed association — reproducible.
 template <typename S>
 __device__ __forceinline__ double strided_sum(const S* __restrict__ src, size_t stride, size_t e, int g, int n_src) {
   double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-  if (n_src <= 16 * kFinGroups) {
+  for (int base = g; base < n_src; base += 16 * kFinGroups) {
     S v[16];
 #pragma unroll
     for (int q = 0; q < 16; ++q) {
-      const int b = g + q * kFinGroups;
+      const int b = base + q * kFinGroups;
       v[q] = (b < n_src) ? src[(size_t)b * stride + e] : S(0);
     }
-    // same association as the loop below: chains of b = g + (4 i + c) G, then the tail on chain 0
-    const int full = (n_src - g + kFinGroups - 1) / kFinGroups;   // sources of this group
-    const int quads = full / 4;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      if (i < quads) { s0 += (double)v[4 * i]; s1 += (double)v[4 * i + 1]; s2 += (double)v[4 * i + 2]; s3 += (double)v[4 * i + 3]; }
-    }
-#pragma unroll
-    for (int q = 0; q < 16; ++q)
-      if (q >= 4 * quads && q < full) s0 += (double)v[q];
-    return (s0 + s1) + (s2 + s3);
+    for (int q = 0; q < 16; q += 4) { s0 += (double)v[q]; s1 += (double)v[q + 1]; s2 += (double)v[q + 2]; s3 += (double)v[q + 3]; }
   }
-  int b = g;
-  for (; b + 3 * kFinGroups < n_src; b += 4 * kFinGroups) {
-    const S v0 = src[(size_t)b * stride + e];
-    const S v1 = src[(size_t)(b + kFinGroups) * stride + e];
-    const S v2 = src[(size_t)(b + 2 * kFinGroups) * stride + e];
-    const S v3 = src[(size_t)(b + 3 * kFinGroups) * stride + e];
-    s0 += (double)v0; s1 += (double)v1; s2 += (double)v2; s3 += (double)v3;
-  }
-  for (; b < n_src; b += kFinGroups) s0 += (double)src[(size_t)b * stride + e];
   return (s0 + s1) + (s2 + s3);
 }
 
@@ -564,17 +544,6 @@ __global__ void __launch_bounds__(kFinThreads) finalize_kernel(const FinalizeArg
   const int t = threadIdx.x, g = t / kFinElems, l = t % kFinElems;
   const int kd = a.k * a.d;
   const int e = blockIdx.x * kFinElems + l;
-  if (UPDATE && a.wait_flags != nullptr) {
-    // partials arrive over NVLink: one thread per rank polls that rank's flag (bounded)
-    if (t < a.n_wait) {
-      const volatile unsigned long long* f = a.wait_flags + t;
-      unsigned int spins = 0;
-      while (*f != a.flag_value && ++spins < (1u << 22)) {}
-      if (*f != a.flag_value) atomicOr(&a.state->fallback_rows, 1ull << 41);  // timeout marker, reported by the host
-    }
-    __syncthreads();
-    __threadfence();
-  }
   sh[g][l] = (e < kd) ? strided_sum<S>(a.src_sums, a.sum_stride, (size_t)e, g, a.n_src) : 0.0;
   // counts of the clusters this CTA's elements belong to
   const int c_lo = (blockIdx.x * kFinElems) / a.d;
@@ -588,7 +557,6 @@ __global__ void __launch_bounds__(kFinThreads) finalize_kernel(const FinalizeArg
 #pragma unroll
     for (int q = 0; q < kFinGroups; ++q) cntv += shc[q][l];
     if (UPDATE) a.counts_out[c] = cntv;
-    else if (a.n_peers > 0) { for (int p = 0; p < a.n_peers; ++p) a.peer_out[p][kd + c] = cntv; }
     else a.rank_out[kd + c] = cntv;
   }
   double sq = 0.0;
@@ -597,8 +565,7 @@ __global__ void __launch_bounds__(kFinThreads) finalize_kernel(const FinalizeArg
 #pragma unroll
     for (int q = 0; q < kFinGroups; ++q) tot += sh[q][l];
     if (!UPDATE) {
-      if (a.n_peers > 0) { for (int p = 0; p < a.n_peers; ++p) a.peer_out[p][e] = tot; }
-      else a.rank_out[e] = tot;
+      a.rank_out[e] = tot;
     } else {
       const int ce = e / a.d - c_lo;
       double cntv = 0.0;
@@ -617,25 +584,7 @@ __global__ void __launch_bounds__(kFinThreads) finalize_kernel(const FinalizeArg
       const int n_in = a.n_src_inertia ? a.n_src_inertia : a.n_src;
       for (int b = t; b < n_in; b += kFinThreads) v += a.src_inertia[(size_t)b * a.inertia_stride];
       const double tot = block_sum(v, red);
-      if (t == 0) {
-        if (a.n_peers > 0) { for (int p = 0; p < a.n_peers; ++p) a.peer_out[p][kd + a.k] = tot; }
-        else a.rank_out[kd + a.k] = tot;
-      }
-    }
-    if (a.n_peers > 0) {
-      // all of this CTA's peer stores are issued: fence system-wide, and the last CTA raises the flags
-      __threadfence_system();
-      __syncthreads();
-      if (t == 0) {
-        const unsigned int prev = atomicAdd(a.publish_done, 1u);
-        is_last = (prev == gridDim.x - 1);
-      }
-      __syncthreads();
-      if (is_last) {
-        __threadfence_system();
-        if (t < a.n_peers) *((volatile unsigned long long*)a.peer_flags[t]) = a.flag_value;
-        if (t == 0) *a.publish_done = 0u;
-      }
+      if (t == 0) a.rank_out[kd + a.k] = tot;
     }
     return;
   }
@@ -658,6 +607,160 @@ __global__ void __launch_bounds__(kFinThreads) finalize_kernel(const FinalizeArg
   for (int b = t; b < n_in; b += kFinThreads) v += a.src_inertia[(size_t)b * a.inertia_stride];
   const double inertia = block_sum(v, red);
   if (t == 0) {
+    const F shift = (F)sqrt(shift_sq);  // L2Dist::distance: sqrt in f64, cast to F
+    a.state->shift = (double)shift;
+    a.state->inertia = inertia;
+    const unsigned long long it = a.state->n_iter + 1;
+    a.state->n_iter = it;
+    a.state->blocks_done = 0u;
+    if (shift < (F)a.tol || it >= a.max_iter) a.state->done = 1;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// finalize_x: the multi-GPU iteration tail in ONE launch.  CTA b owns a contiguous range of 16-element slices of the
+// k*d sums.  Phase A: fixed-order f64 sum of the local per-CTA partials, stored straight into every rank's gather buffer
+// (own included) over NVLink, system fence, one flag per (rank, CTA).  Phase B: wait for the same CTA's flags of every
+// rank (plus the CTAs that publish the counts of the clusters it touches), combine the `world` partials in rank order —
+// identical inputs and order on every rank, hence bit-identical centroids without a broadcast — m_k-means update, shift.
+// The last CTA to finish sums the shift and the per-rank inertia and runs the stop rule (KM/algorithm.rs:323-331).
+// Every CTA of the grid is resident (grid <= 2 x SM count, 256 threads, no shared memory to speak of), and a CTA waits
+// only for its own index on the peers, so the waits cannot deadlock.
+// ---------------------------------------------------------------------------
+constexpr int kFxMaxCtas = 1024;   // flag slots per (parity, rank)
+
+template <typename F, typename S, typename CT> struct FinalizeXArgs {
+  const S* src_sums;
+  const CT* src_counts;
+  const double* src_inertia;
+  size_t sum_stride, cnt_stride, inertia_stride;
+  int n_src, n_src_inertia, k, d;
+  int slices_per_cta;
+  double* peer_out[8];                  // rank p's gather slot for THIS rank (this parity): [kd sums | k counts | inertia]
+  unsigned long long* peer_flags[8];    // rank p's flags for THIS rank (this parity): [kFxMaxCtas]
+  const double* gather;                 // own gather buffer of this parity: rank r at gather + r * cap
+  const unsigned long long* my_flags;   // own flags of this parity: rank r, CTA b at my_flags[r * kFxMaxCtas + b]
+  size_t cap;
+  int world;
+  unsigned long long epoch;
+  const F* C_old;
+  F* C_new;
+  double* counts_out;
+  double* shift_part;   // [grid]
+  LloydState* state;
+  double tol;
+  unsigned long long max_iter;
+};
+
+__device__ __forceinline__ bool wait_flag(const unsigned long long* f, unsigned long long want) {
+  unsigned long long v;
+  const unsigned long long t0 = global_ns();
+  for (;;) {
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(f) : "memory");
+    if (v == want) return true;
+    if (global_ns() - t0 > kPeerWaitNs) return false;
+  }
+}
+
+template <typename F, typename S, typename CT>
+__global__ void __launch_bounds__(kFinThreads) finalize_x_kernel(const FinalizeXArgs<F, S, CT> a) {
+  pdl_launch_dependents();
+  pdl_wait();
+  if (a.state->done) return;
+  __shared__ double sh[kFinGroups][kFinElems];
+  __shared__ double shc[kFinGroups][kFinElems];
+  __shared__ double red[kFinThreads];
+  __shared__ bool is_last;
+  const int t = threadIdx.x, g = t / kFinElems, l = t % kFinElems;
+  const int kd = a.k * a.d;
+  const int n_slices = (kd + kFinElems - 1) / kFinElems;
+  const int s_lo = blockIdx.x * a.slices_per_cta, s_hi = min(n_slices, s_lo + a.slices_per_cta);
+  // ---- phase A: local reduction, published to every rank ----
+  for (int slice = s_lo; slice < s_hi; ++slice) {
+    const int e = slice * kFinElems + l;
+    sh[g][l] = (e < kd) ? strided_sum<S>(a.src_sums, a.sum_stride, (size_t)e, g, a.n_src) : 0.0;
+    const int c_lo = (slice * kFinElems) / a.d;
+    const int c_hi = (min(kd, (slice + 1) * kFinElems) - 1) / a.d;
+    const int c = c_lo + l;
+    // a cluster's count is published with the slice that holds its first element
+    const bool own_c = c <= c_hi && (c * a.d) / kFinElems == slice;
+    shc[g][l] = own_c ? strided_sum<CT>(a.src_counts, a.cnt_stride, (size_t)c, g, a.n_src) : 0.0;
+    __syncthreads();
+    if (g == 0 && e < kd) {
+      double tot = 0.0;
+#pragma unroll
+      for (int q = 0; q < kFinGroups; ++q) tot += sh[q][l];
+      for (int p = 0; p < a.world; ++p) a.peer_out[p][e] = tot;
+    }
+    if (g == 1 && own_c) {
+      double cntv = 0.0;
+#pragma unroll
+      for (int q = 0; q < kFinGroups; ++q) cntv += shc[q][l];
+      for (int p = 0; p < a.world; ++p) a.peer_out[p][kd + c] = cntv;
+    }
+    __syncthreads();
+  }
+  if (blockIdx.x == 0) {
+    double v = 0.0;
+    const int n_in = a.n_src_inertia ? a.n_src_inertia : a.n_src;
+    for (int b = t; b < n_in; b += kFinThreads) v += a.src_inertia[(size_t)b * a.inertia_stride];
+    const double tot = block_sum(v, red);
+    if (t == 0)
+      for (int p = 0; p < a.world; ++p) a.peer_out[p][kd + a.k] = tot;
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (t < a.world) {
+    unsigned long long* f = a.peer_flags[t] + blockIdx.x;
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(f), "l"(a.epoch) : "memory");
+  }
+  // ---- phase B: the peers' copies of this CTA's range (and of the counts of its clusters) have landed ----
+  const int e_lo = s_lo * kFinElems, e_hi = min(kd, s_hi * kFinElems);
+  bool ok = true;
+  if (e_lo < e_hi) {
+    const int c_first = e_lo / a.d;
+    const int need_lo = min((int)blockIdx.x, ((c_first * a.d) / kFinElems) / a.slices_per_cta);
+    const int n_need = ((int)blockIdx.x - need_lo + 1) * a.world;
+    for (int i = t; i < n_need; i += kFinThreads)
+      ok = wait_flag(a.my_flags + (size_t)(i % a.world) * kFxMaxCtas + need_lo + i / a.world, a.epoch) && ok;
+  }
+  if (!ok) atomicOr(&a.state->fallback_rows, 1ull << 41);   // timeout marker, reported by the host
+  __syncthreads();
+  double sq = 0.0;
+  for (int e = e_lo + t; e < e_hi; e += kFinThreads) {
+    const int c = e / a.d;
+    double tot = 0.0, cntv = 0.0;
+    for (int r = 0; r < a.world; ++r) {
+      const volatile double* gr = a.gather + (size_t)r * a.cap;
+      tot += gr[e];
+      cntv += gr[kd + c];
+    }
+    const F oldv = a.C_old[e];
+    const F newv = (F)((tot + (double)oldv) / (cntv + 1.0));
+    a.C_new[e] = newv;
+    if (e == c * a.d) a.counts_out[c] = cntv;
+    const double df = (double)(oldv - newv);
+    sq += df * df;
+  }
+  const double sq_cta = block_sum(sq, red);
+  if (t == 0) {
+    a.shift_part[blockIdx.x] = sq_cta;
+    __threadfence();
+    const unsigned int prev = atomicAdd(&a.state->blocks_done, 1u);
+    is_last = (prev == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  // last CTA: shift, inertia (published by CTA 0 of every rank), loop control — fixed order, identical on every rank
+  if (t < a.world && !wait_flag(a.my_flags + (size_t)t * kFxMaxCtas, a.epoch)) atomicOr(&a.state->fallback_rows, 1ull << 41);
+  __syncthreads();
+  double v = 0.0;
+  for (int b = t; b < (int)gridDim.x; b += kFinThreads) v += ((volatile double*)a.shift_part)[b];
+  const double shift_sq = block_sum(v, red);
+  if (t == 0) {
+    double inertia = 0.0;
+    for (int r = 0; r < a.world; ++r) inertia += ((const volatile double*)a.gather)[(size_t)r * a.cap + kd + a.k];
     const F shift = (F)sqrt(shift_sq);  // L2Dist::distance: sqrt in f64, cast to F
     a.state->shift = (double)shift;
     a.state->inertia = inertia;

@@ -412,9 +412,14 @@ class KMeansValidParams:
         x = np.asarray(_records(dataset))
         ctx = ctx or self._ctx or Context.default()
         ctx.set_data(x)
-        sfx, ct = _ffi.sfx_of(x.dtype)
-        p, keep = self._native_params(x.dtype)
-        out = np.zeros((self._n_clusters, x.shape[1]), dtype=x.dtype)
+        return self.init_centroids_resident(ctx)
+
+    def init_centroids_resident(self, ctx):
+        """KMeansInit::run on the matrix already resident in `ctx`."""
+        dtype, shape = ctx.dtype, ctx.shape
+        sfx, ct = _ffi.sfx_of(dtype)
+        p, keep = self._native_params(dtype)
+        out = np.zeros((self._n_clusters, shape[1]), dtype=dtype)
         rng = copy.deepcopy(self._rng)
         st = getattr(_ffi.lib, f"lkm_init_{sfx}")(ctx.h, C.byref(p), _ffi.make_rng(rng), _ffi.fptr(out, ct))
         if st in (_ffi.ERR_SHAPE, _ffi.ERR_SAMPLE_AMOUNT, _ffi.ERR_ZERO_WEIGHTS, _ffi.ERR_BAD_WEIGHTS):

@@ -25,7 +25,8 @@ def main():
 
     ok = True
     for dtype, n, d, k, rtol in [(np.float32, 400_003, 32, 64, 1e-5), (np.float64, 300_001, 8, 16, 1e-10),
-                                 (np.float32, 100_000, 20, 12, 1e-5)]:
+                                 (np.float32, 100_000, 20, 12, 1e-5), (np.float32, 300_007, 128, 256, 1e-5),
+                                 (np.float32, 200_000, 64, 600, 1e-5), (np.float32, 1, 32, 1, 1e-5)]:
         ctx = lb.Context(local)
         D.init_comm(ctx, device=torch.device("cuda", local))
         g = np.random.default_rng(5)
@@ -33,7 +34,18 @@ def main():
         init = (centres + 0.5 * g.standard_normal((k, d))).astype(dtype)
         lo, hi = D.shard_range(n, rank, world)
         ctx.gen_blobs(hi - lo, d, centres, 1.0, seed=11, row_offset=lo, n_global=n)
+        ctx.set_keep_labels(True)
         c, counts, inertia, st = ctx.lloyd_iters(init, 6, 0.0)
+        # per-row labels of the last iteration, gathered in rank order
+        lab = torch.from_numpy(ctx.get_labels(hi - lo).astype(np.int64)).cuda()
+        sizes = [D.shard_range(n, r, world)[1] - D.shard_range(n, r, world)[0] for r in range(world)]
+        parts = [torch.zeros(s_, dtype=torch.int64, device="cuda") for s_ in sizes]
+        pad = max(sizes)
+        buf = [torch.zeros(pad, dtype=torch.int64, device="cuda") for _ in range(world)]
+        mine = torch.zeros(pad, dtype=torch.int64, device="cuda")
+        mine[: hi - lo] = lab
+        dist.all_gather(buf, mine)
+        all_labels = torch.cat([buf[r][: sizes[r]] for r in range(world)]).cpu().numpy()
         # bit-identical across ranks
         t = torch.from_numpy(c.copy()).cuda()
         allc = [torch.zeros_like(t) for _ in range(world)]
@@ -42,13 +54,16 @@ def main():
         if rank == 0:
             solo = lb.Context(local)
             solo.gen_blobs(n, d, centres, 1.0, seed=11)
+            solo.set_keep_labels(True)
             c1, counts1, inertia1, st1 = solo.lloyd_iters(init, 6, 0.0)
+            labels_equal = bool((solo.get_labels(n).astype(np.int64) == all_labels).all())
             scale = np.abs(c1).max()
-            good = (same and st.n_iter == 6 and counts.tolist() == counts1.tolist()
+            good = (same and labels_equal and st.n_iter == 6 and counts.tolist() == counts1.tolist()
                     and np.allclose(c, c1, rtol=rtol, atol=rtol * scale) and np.isclose(inertia, inertia1, rtol=rtol))
             print(f"[multi_gpu_check] {np.dtype(dtype).name} n={n} d={d} k={k} world={world}: "
                   f"{'ok' if good else 'MISMATCH'} path={st.assign_path} "
-                  f"max|dC|/scale={np.abs(c - c1).max() / scale:.3e} counts_equal={counts.tolist() == counts1.tolist()}",
+                  f"max|dC|/scale={np.abs(c - c1).max() / scale:.3e} counts_equal={counts.tolist() == counts1.tolist()} "
+                  f"labels_equal_row_by_row={labels_equal} bit_identical_across_ranks={same}",
                   flush=True)
             ok = ok and good
             solo.close()
