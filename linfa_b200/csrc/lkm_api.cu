@@ -103,7 +103,6 @@ struct lkm_ctx {
   // kernel that also serves 64 < k <= 256 (LKM_TC_VARIANT=128 forces it for every k, an A/B knob)
   int tc_variant = 4;
   int tc5_passes_forced = 0;            // LKM_TC5_PASSES = 1 / 3 pins the screening / 3xTF32 variant of the pair kernel
-  uint64_t tc5_hard_epoch = 0, tc5_easy_epoch = 0;
   int fused_finalize = 0;   // LKM_FUSED_FINALIZE=1: finalize folded into the pipeline kernel's tail (measured: no gain, 47.1 vs 46.3 us per cfg2 step)
   int f64s_enabled = 1;  // LKM_F64S=0: lloyd_kernel<double> instead of the f32-screened small-d f64 kernel (lkm_f64s.cuh)
   int f64s_packed = 1;   // LKM_F64S_PACKED=0: scalar FFMA instead of FFMA2 in that kernel
@@ -115,7 +114,6 @@ struct lkm_ctx {
   uint64_t data_epoch = 1, xmax2_epoch = 0;  // resident-data version / version the cached max row norm belongs to
   DevBuf xmax2, t4prof, t5merge, t5list;
   int tc4_passes_forced = 0;              // LKM_TC4_PASSES = 2 / 3 pins the scoring passes of the pipeline kernel
-  uint64_t tc4_hard_epoch = 0, tc4_easy_epoch = 0;   // data versions seen to need 3 passes / to be fine with 2
   uint64_t flush_bytes = 0;
   unsigned long long bar_epoch = 0;   // rank_barrier_kernel (flushed-L2 benchmark mode, multi-GPU)
   int kernel_timing = 0;
@@ -526,8 +524,7 @@ static lkm_status run_lloyd(lkm_ctx* ctx, F* dC2, uint64_t k, uint64_t max_iter,
   std::memset(&tc4_map, 0, sizeof(tc4_map));
   if constexpr (std::is_same<F, float>::value) {
     pair32 = ctx->pair32 && ctx->tc5_enabled && ctx->upd_variant != 0 && (ctx->force_path == -1 || ctx->force_path == 2) && d == 32 &&
-             k <= 64 && kd >= 512 && n >= 1 && (reinterpret_cast<uintptr_t>(dX) & 15) == 0 &&
-             !(ctx->tc5_hard_epoch == ctx->data_epoch && ctx->own_X);   // data that screening cannot certify: pipeline kernel
+             k <= 64 && kd >= 512 && n >= 1 && (reinterpret_cast<uintptr_t>(dX) & 15) == 0;
     if (!pair32 && (ctx->force_path == -1 || ctx->force_path == 2) && d == 32 && k <= 256 && n >= 1 &&
         (reinterpret_cast<uintptr_t>(dX) & 15) == 0) {
       tc_kp = (int)((k + 31) / 32 * 32);
@@ -808,20 +805,22 @@ static lkm_status run_lloyd(lkm_ctx* ctx, F* dC2, uint64_t k, uint64_t max_iter,
 
   uint64_t launched = 0;
   const uint64_t batch = 16;
-  // pipeline kernel: scoring passes.  One pass (x_hi.c_hi) certifies well-separated data at the lowest cost; when more
-  // than 2 % of the rows of a batch need the exact re-scan the loop switches to the 3xTF32 variant.  A data set that
-  // has not been seen with two passes yet gets a one-iteration first batch, so a bad guess costs one iteration.
+  // Scoring passes of the tensor-core kernels.  One pass (x_hi.c_hi) certifies well-separated data at the lowest cost; the
+  // first batch of every call is ONE iteration, after which the host looks at the rows that needed the exact re-scan and at
+  // the tiles the fused update had to list, and moves to 3xTF32 / to the separate update pass when they are too many.  The
+  // choice is made afresh in every call from what this call's first iteration saw — nothing is remembered between calls, so
+  // the same call on the same data gives the same bits (labels never depend on the variant, the order of the sums does).
   const bool is_tc4 = use_tc && tc_threads == kT4Threads;
-  int tc4_passes = 3;
-  if (is_tc4) {
-    tc4_passes = ctx->tc4_passes_forced ? ctx->tc4_passes_forced : ((ctx->tc4_hard_epoch == ctx->data_epoch && ctx->own_X) ? 3 : 1);
-  }
-  bool tc4_probe = is_tc4 && !ctx->tc4_passes_forced && tc4_passes < 3 && !(ctx->tc4_easy_epoch == ctx->data_epoch && ctx->own_X);
-  // pair kernel: the screening variant (one TF32 product) first, 3xTF32 when too many rows needed the exact re-scan
-  int tc5_passes = 3;
-  if (use_tc5) tc5_passes = ctx->tc5_passes_forced ? ctx->tc5_passes_forced : ((ctx->tc5_hard_epoch == ctx->data_epoch && ctx->own_X) ? 3 : 1);
+  int tc4_passes = is_tc4 ? (ctx->tc4_passes_forced ? ctx->tc4_passes_forced : 1) : 3;
+  bool tc4_probe = is_tc4 && !ctx->tc4_passes_forced;
+  int tc5_passes = use_tc5 ? (ctx->tc5_passes_forced ? ctx->tc5_passes_forced : 1) : 3;
   if (use_tc5 && d == 32) tc5_passes = 1;   // the d = 32 instantiation only exists as the screening variant
-  bool tc5_probe = use_tc5 && !ctx->tc5_passes_forced && tc5_passes == 1 && !(ctx->tc5_easy_epoch == ctx->data_epoch && ctx->own_X);
+  bool tc5_probe = use_tc5 && ((!ctx->tc5_passes_forced && tc5_passes == 1) || tc5_can_fuse);
+  // an exact re-scan reads every centroid from L2 (k * d * 4 bytes per row): past ~0.4 % of the rows the 3xTF32 variant is
+  // cheaper for the pair kernel (measured on the cfg3 shape from a k-means++ start); the pipeline kernel re-scans from
+  // shared memory and tolerates 2 %
+  const double tc5_rescan_limit = 0.004, tc4_rescan_limit = 0.02, fuse_mixed_limit = 0.25;
+  unsigned long long mixed_seen = 0;
   unsigned long long fb_seen = 0;
   for (;;) {
     const uint64_t todo = std::min<uint64_t>((tc4_probe || tc5_probe) ? 1 : batch, max_iter - launched);
@@ -1070,16 +1069,17 @@ static lkm_status run_lloyd(lkm_ctx* ctx, F* dC2, uint64_t k, uint64_t max_iter,
     const uint64_t todo_done = todo;
     CK(cudaMemcpyAsync(ctx->h_state, dstate, sizeof(LloydState), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
-    if (is_tc4 && !ctx->tc4_passes_forced && tc4_passes < 3) {
+    {
       const unsigned long long fb = (ctx->h_state->fallback_rows & ((1ull << 40) - 1)) - fb_seen;
-      if ((double)fb > 0.02 * (double)n * (double)todo_done) { tc4_passes = 3; ctx->tc4_hard_epoch = ctx->data_epoch; }
-      else ctx->tc4_easy_epoch = ctx->data_epoch;
+      if (is_tc4 && !ctx->tc4_passes_forced && tc4_passes < 3 && (double)fb > tc4_rescan_limit * (double)n * (double)todo_done) tc4_passes = 3;
+      if (use_tc5 && !ctx->tc5_passes_forced && tc5_passes == 1 && d != 32 && (double)fb > tc5_rescan_limit * (double)n * (double)todo_done)
+        tc5_passes = 3;
+      // unordered rows: (nearly) every tile of the fused update ends up on the list, and the listed pass is slower than the
+      // plain streaming update — stop fusing for the rest of the call
+      const unsigned long long mixed = ctx->h_state->mixed_tiles - mixed_seen;
+      if (tc5_can_fuse && (double)mixed > fuse_mixed_limit * (double)((n + 127) / 128) * (double)todo_done) tc5_can_fuse = false;
+      mixed_seen = ctx->h_state->mixed_tiles;
       tc4_probe = false;
-    }
-    if (use_tc5 && !ctx->tc5_passes_forced && tc5_passes == 1) {
-      const unsigned long long fb = (ctx->h_state->fallback_rows & ((1ull << 40) - 1)) - fb_seen;
-      if ((double)fb > 0.02 * (double)n * (double)todo_done) { if (d != 32) tc5_passes = 3; ctx->tc5_hard_epoch = ctx->data_epoch; }
-      else ctx->tc5_easy_epoch = ctx->data_epoch;
       tc5_probe = false;
     }
     fb_seen = ctx->h_state->fallback_rows & ((1ull << 40) - 1);

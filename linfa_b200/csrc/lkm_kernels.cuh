@@ -28,6 +28,7 @@ struct LloydState {
   double shift;    // ||C_t - C_{t+1}||_F of the last iteration
   int done;
   unsigned int blocks_done;
+  unsigned long long mixed_tiles;   // tiles the fused update of the pair kernel left to the listed update pass
 };
 
 enum LloydMode { MODE_ASSIGN = 0, MODE_FUSED = 1, MODE_UPDATE = 2 };

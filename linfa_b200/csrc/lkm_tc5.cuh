@@ -823,7 +823,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(FUSE ? t5_fuse_threa
       }
       for (unsigned long long v = my_pt >= 2 ? my_pt - 2 : 0; v < my_pt; ++v) consume(v);
       flush();
-      if (u == 0 && lane == 0) a.mixed_count[blockIdx.x] = n_mixed;
+      if (u == 0 && lane == 0) {
+        a.mixed_count[blockIdx.x] = n_mixed;
+        if (a.state != nullptr && n_mixed) atomicAdd(&a.state->mixed_tiles, (unsigned long long)n_mixed);
+      }
       inert_d += (double)inert_f;
       for (int o = 16; o > 0; o >>= 1) inert_d += __shfl_xor_sync(0xffffffffu, inert_d, o);
       if (lane == 0) u_red[u] = inert_d;
