@@ -58,9 +58,12 @@ typedef enum lkm_init_method {
   LKM_INIT_KMEANS_PARA = 3
 } lkm_init_method;
 
-/* KMeansAlgorithm (KM/init.rs:54-79).  Hamerly is accepted and executed as
- * Lloyd: the reference documents that both converge to the same result from
- * the same initial centroids (KM/init.rs:46-47). */
+/* KMeansAlgorithm (KM/init.rs:54-79).  LKM_ALGO_HAMERLY runs fit_hamerly
+ * (KM/algorithm.rs:248-291): per-row upper / lower bounds decide which rows are
+ * looked at after the first iteration, inertia is compute_inertia against the
+ * final centroids (:275,570-577) and cluster_count comes from the best run's
+ * memberships (:281-291).  Row-sharded (multi-GPU) runs execute Lloyd's
+ * iterations and return Hamerly's result fields. */
 typedef enum lkm_algorithm { LKM_ALGO_LLOYD = 0, LKM_ALGO_HAMERLY = 1 } lkm_algorithm;
 
 /* How the D^2 / weighted pick of k-means++ walks the prefix sum.
@@ -105,6 +108,8 @@ typedef struct lkm_stats {
   uint64_t fallback_rows;    /* rows re-evaluated in exact form by the certified paths */
   float main_kernel_ms;      /* with lkm_set_l2_flush: summed duration of the assign/fused kernel alone */
   uint32_t reserved;
+  uint64_t rows_scanned;     /* Hamerly: rows that went through two_closest_centroids after iteration 1 (summed over iterations) */
+  uint64_t rows_tightened;   /* Hamerly: rows whose upper bound was recomputed (one exact distance) */
 } lkm_stats;
 
 /* -- context ------------------------------------------------------------- */
@@ -170,6 +175,16 @@ lkm_status lkm_lloyd_iters_f32(lkm_ctx* ctx, float* centroids_inout, uint64_t k,
 lkm_status lkm_lloyd_iters_f64(lkm_ctx* ctx, double* centroids_inout, uint64_t k, uint64_t max_iters,
                                double tolerance, double* cluster_count_out, double* inertia_total_out,
                                lkm_stats* stats_out);
+
+/* The loop body of fit_hamerly (KM/algorithm.rs:262-279) from centroids_inout: same arguments as lkm_lloyd_iters_*;
+ * inertia_total_out is compute_inertia against the RETURNED centroids (sum, not mean).  stats.rows_scanned /
+ * rows_tightened say how much of the matrix the bounds let the iterations skip. */
+lkm_status lkm_hamerly_iters_f32(lkm_ctx* ctx, float* centroids_inout, uint64_t k, uint64_t max_iters,
+                                 double tolerance, float* cluster_count_out, float* inertia_total_out,
+                                 lkm_stats* stats_out);
+lkm_status lkm_hamerly_iters_f64(lkm_ctx* ctx, double* centroids_inout, uint64_t k, uint64_t max_iters,
+                                 double tolerance, double* cluster_count_out, double* inertia_total_out,
+                                 lkm_stats* stats_out);
 
 /* -- PredictInplace (KM/algorithm.rs:735-777) -> update_cluster_memberships
  * (:838-849) and Transformer (:718-733) -> update_min_dists (:852-863).

@@ -55,6 +55,8 @@ class lkm_stats(C.Structure):
         ("fallback_rows", C.c_uint64),
         ("main_kernel_ms", C.c_float),
         ("reserved", C.c_uint32),
+        ("rows_scanned", C.c_uint64),
+        ("rows_tightened", C.c_uint64),
     ]
 
 
@@ -75,7 +77,7 @@ UNTYPED_SYMBOLS = [
 ]
 TYPED_SYMBOLS = [
     "lkm_set_data", "lkm_set_data_device", "lkm_gen_blobs", "lkm_get_data", "lkm_fit", "lkm_init",
-    "lkm_lloyd_iters", "lkm_predict", "lkm_transform", "lkm_assign", "lkm_fit_with",
+    "lkm_lloyd_iters", "lkm_hamerly_iters", "lkm_predict", "lkm_transform", "lkm_assign", "lkm_fit_with",
 ]
 
 _vp, _u64, _i64, _i32 = C.c_void_p, C.c_uint64, C.c_int64, C.c_int
@@ -111,6 +113,7 @@ for _sfx, _ct in (("f32", C.c_float), ("f64", C.c_double)):
     getattr(lib, f"lkm_fit_{_sfx}").argtypes = [_vp, _pp, lkm_rng, _fp, _fp, _fp, _sp]
     getattr(lib, f"lkm_init_{_sfx}").argtypes = [_vp, _pp, lkm_rng, _fp]
     getattr(lib, f"lkm_lloyd_iters_{_sfx}").argtypes = [_vp, _fp, _u64, _u64, C.c_double, _fp, _fp, _sp]
+    getattr(lib, f"lkm_hamerly_iters_{_sfx}").argtypes = [_vp, _fp, _u64, _u64, C.c_double, _fp, _fp, _sp]
     getattr(lib, f"lkm_predict_{_sfx}").argtypes = [_vp, _fp, _u64, _fp, _u64, _u64, _i64, _u64p]
     getattr(lib, f"lkm_transform_{_sfx}").argtypes = [_vp, _fp, _u64, _fp, _u64, _u64, _i64, _fp]
     getattr(lib, f"lkm_assign_{_sfx}").argtypes = [_vp, _fp, _u64, _fp, _u64, _u64, _i64, _u64p, _fp]

@@ -27,131 +27,21 @@
 #include "lkm_upd.cuh"
 #include "lkm_tc5.cuh"
 #include "lkm_f64s.cuh"
+#include "lkm_rows.cuh"
+#include "lkm_hamerly.cuh"
 #ifdef LKM_WITH_PROBES
 #include "lkm_probe.cuh"
 #endif
 
 #define LKM_EXPORT extern "C" __attribute__((visibility("default")))
 
-namespace lkm {
-
-// ---- NCCL through dlopen (only needed when world_size > 1) -----------------
-struct NcclUid { char internal[128]; };
-struct NcclApi {
-  void* handle = nullptr;
-  int (*GetUniqueId)(NcclUid*) = nullptr;
-  int (*CommInitRank)(void**, int, NcclUid, int) = nullptr;
-  int (*CommDestroy)(void*) = nullptr;
-  int (*AllGather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;
-  const char* (*GetErrorString)(int) = nullptr;
-  bool load(std::string& err) {
-    if (handle) return true;
-    const char* names[] = {"libnccl.so.2", "libnccl.so"};
-    for (const char* nm : names) {
-      handle = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
-      if (handle) break;
-    }
-    if (!handle) { err = std::string("dlopen libnccl failed: ") + dlerror(); return false; }
-    GetUniqueId = (decltype(GetUniqueId))dlsym(handle, "ncclGetUniqueId");
-    CommInitRank = (decltype(CommInitRank))dlsym(handle, "ncclCommInitRank");
-    CommDestroy = (decltype(CommDestroy))dlsym(handle, "ncclCommDestroy");
-    AllGather = (decltype(AllGather))dlsym(handle, "ncclAllGather");
-    GetErrorString = (decltype(GetErrorString))dlsym(handle, "ncclGetErrorString");
-    if (!GetUniqueId || !CommInitRank || !CommDestroy || !AllGather) { err = "libnccl lacks required symbols"; return false; }
-    return true;
-  }
-};
-static NcclApi g_nccl;
-constexpr int kNcclFloat64 = 8, kNcclUint64 = 5, kNcclInt8 = 0;
-
-struct DevBuf {
-  void* p = nullptr;
-  size_t cap = 0;
-  cudaError_t ensure(size_t bytes) {
-    if (bytes <= cap) return cudaSuccess;
-    if (p) cudaFree(p);
-    p = nullptr; cap = 0;
-    cudaError_t e = cudaMalloc(&p, bytes);
-    if (e == cudaSuccess) cap = bytes;
-    return e;
-  }
-  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
-  template <class T> T* as() { return reinterpret_cast<T*>(p); }
-};
-
-}  // namespace lkm
+#include "lkm_ctx.hpp"
 
 using namespace lkm;
 
-struct lkm_ctx {
-  int device = 0;
-  cudaStream_t stream = nullptr;
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-  std::string err;
-  int sm_count = 148;
-  size_t smem_optin = 227 * 1024;
-  // resident observations
-  int elem = 0;  // 0 none, 4 f32, 8 f64
-  void* X = nullptr;
-  bool own_X = false;
-  DevBuf xbuf;
-  uint64_t n = 0, d = 0;
-  uint64_t row_offset = 0, n_global = 0;
-  int force_path = -1;
-  int last_path = 0;
-  // fused tcgen05 kernel for d = 32: 4 = TMA + warp-specialised pipeline (k <= 64), 128 = the shared-memory-operand
-  // kernel that also serves 64 < k <= 256 (LKM_TC_VARIANT=128 forces it for every k, an A/B knob)
-  int tc_variant = 4;
-  int tc5_passes_forced = 0;            // LKM_TC5_PASSES = 1 / 3 pins the screening / 3xTF32 variant of the pair kernel
-  int fused_finalize = 0;   // LKM_FUSED_FINALIZE=1: finalize folded into the pipeline kernel's tail (measured: no gain, 47.1 vs 46.3 us per cfg2 step)
-  int f64s_enabled = 1;  // LKM_F64S=0: lloyd_kernel<double> instead of the f32-screened small-d f64 kernel (lkm_f64s.cuh)
-  int f64s_packed = 1;   // LKM_F64S_PACKED=0: scalar FFMA instead of FFMA2 in that kernel
-  int f64s_rpt = 2;      // LKM_F64S_RPT=1: one row per lane (32-row tiles, 3 CTAs / SM)
-  int pair32 = 0;        // LKM_PAIR32=1: d = 32, k <= 64 through the CTA-pair screening kernel instead of the pipeline kernel
-  int tc5_fuse = 1;      // LKM_TC5_FUSE=0: screening kernel without the fused update of uniform tiles
-  int tc5_enabled = 1;   // LKM_TC5=0: tc_assign_kernel instead of the CTA-pair assignment kernel
-  int upd_variant = 1;   // LKM_UPD=0: cluster-chunked lloyd_kernel<MODE_UPDATE> instead of update_rows_kernel
-  uint64_t data_epoch = 1, xmax2_epoch = 0;  // resident-data version / version the cached max row norm belongs to
-  DevBuf xmax2, t4prof, t5merge, t5list;
-  int tc4_passes_forced = 0;              // LKM_TC4_PASSES = 2 / 3 pins the scoring passes of the pipeline kernel
-  uint64_t flush_bytes = 0;
-  unsigned long long bar_epoch = 0;   // rank_barrier_kernel (flushed-L2 benchmark mode, multi-GPU)
-  int kernel_timing = 0;
-  int keep_labels = 0;     // lkm_set_keep_labels: the Lloyd kernels also write the per-row labels of the last iteration
-  uint64_t kept_labels_n = 0;
-  int blob_shuffled = 0;   // lkm_set_blob_layout
-  DevBuf flushbuf, fin_sync, para_c2;
-  int para_tc = 0;       // LKM_PARA_TC=1: k-means|| candidate histogram through one tensor-core Lloyd iteration (measured slower on the cfg4 shard: 6.4 vs 5.9 s)
-  std::vector<cudaEvent_t> iter_events;
-  // workspaces
-  DevBuf tca_bsplit, tca_cn, tca_cmax;
-  DevBuf cbuf, part_sums, part_counts, part_inertia, shift_part, counts_out, state, gather, gather2, labels, dists, wdists,
-      cum, scratch, tmpx, tmpc, idxbuf, bsum, weights;
-  LloydState* h_state = nullptr;  // pinned
-  double* h_pin = nullptr;        // pinned scratch (>= 4096 doubles)
-  // comm
-  void* comm = nullptr;
-  int rank = 0, world = 1;
-  // NVLink one-shot exchange: this rank's gather buffer [2 parities][world][p2p_cap doubles] followed by
-  // [2][world] flags, mapped into every peer through CUDA IPC
-  void* p2p_local = nullptr;
-  std::vector<void*> p2p_peer;
-  size_t p2p_cap = 0;
-  unsigned long long p2p_epoch = 0;
-  int p2p_enabled = 1;  // LKM_P2P=0 falls back to ncclAllGather
-  uint32_t launches = 0;
-};
-
 namespace lkm {
 
-#define CK(call)                                                                                      \
-  do {                                                                                                \
-    cudaError_t e__ = (call);                                                                         \
-    if (e__ != cudaSuccess) {                                                                         \
-      ctx->err = std::string(#call) + ": " + cudaGetErrorString(e__);                                 \
-      return LKM_ERR_CUDA;                                                                            \
-    }                                                                                                 \
-  } while (0)
+static NcclApi g_nccl;
 #define CKN(call)                                                                                     \
   do {                                                                                                \
     int r__ = (call);                                                                                 \
@@ -160,16 +50,6 @@ namespace lkm {
       return LKM_ERR_NCCL;                                                                            \
     }                                                                                                 \
   } while (0)
-#define CKS(call)                                                                                     \
-  do {                                                                                                \
-    lkm_status s__ = (call);                                                                          \
-    if (s__ != LKM_OK) return s__;                                                                    \
-  } while (0)
-
-static lkm_status fail(lkm_ctx* ctx, lkm_status s, const char* msg) {
-  ctx->err = msg;
-  return s;
-}
 
 // Benchmark hygiene: after the scratch buffer has been overwritten (which evicts the resident matrix from L2 but
 // leaves the L2 full of DIRTY lines, whose write-back would be charged to the next timed kernel), a read-only sweep
@@ -498,6 +378,54 @@ static cudaError_t launch_tc4(int kp, int passes, int grid, size_t smem, cudaStr
   return cudaLaunchKernelEx(&cfg, lloyd_tc4_kernel<64, 3>, arg, map);
 }
 
+// ---- rows_top2_kernel (lkm_rows.cuh): the second stage of the screened paths and Hamerly's two_closest_centroids ----
+template <typename F, int D>
+static cudaError_t launch_rows_t(const RowsArgs<F>& a, int grid, size_t smem, cudaStream_t s) {
+  static size_t configured = 0;
+  if (smem > configured) {
+    cudaError_t e = cudaFuncSetAttribute(rows_top2_kernel<F, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    configured = smem;
+  }
+  rows_top2_kernel<F, D><<<grid, kRowsThreads, smem, s>>>(a);
+  return cudaGetLastError();
+}
+// max_rows bounds the grid (the kernel reads the real count on the device when a.list_count is set)
+template <typename F>
+static lkm_status launch_rows(lkm_ctx* ctx, RowsArgs<F>& a, uint64_t max_rows) {
+  const uint64_t d = (uint64_t)a.d, k = (uint64_t)a.k;
+  const size_t per = (d + 1) * sizeof(F);
+  const size_t limit = ctx->smem_optin - 2048;
+  // every centroid resident when that fits, else chunks of at most 96 KB (two CTAs per SM)
+  uint64_t kc = k;
+  if (k * per > limit) kc = std::max<uint64_t>(1, std::min<uint64_t>(k, (96 * 1024) / per));
+  if (kc * per > limit) return fail(ctx, LKM_ERR_UNSUPPORTED, "row too wide for the shared-memory centroid chunk");
+  a.kc = (int)kc;
+  const size_t smem = al16(kc * per);
+  const int occ = smem > 100 * 1024 ? 1 : 2;
+  const uint64_t tiles = (max_rows + kRowsThreads - 1) / kRowsThreads;
+  const int grid = (int)std::max<uint64_t>(1, std::min<uint64_t>(tiles, (uint64_t)ctx->sm_count * occ));
+  const bool aligned = (reinterpret_cast<uintptr_t>(a.X) & 15) == 0;
+  cudaError_t e = cudaSuccess;
+#define LKM_ROWS_CASE(DD) case DD: e = launch_rows_t<F, DD>(a, grid, smem, ctx->stream); break;
+  if (!aligned) e = launch_rows_t<F, 0>(a, grid, smem, ctx->stream);
+  else if constexpr (std::is_same<F, float>::value) {
+    switch (d) {
+      LKM_ROWS_CASE(2) LKM_ROWS_CASE(3) LKM_ROWS_CASE(4) LKM_ROWS_CASE(8) LKM_ROWS_CASE(16) LKM_ROWS_CASE(32) LKM_ROWS_CASE(64) LKM_ROWS_CASE(128)
+      default: e = launch_rows_t<F, 0>(a, grid, smem, ctx->stream); break;
+    }
+  } else {
+    switch (d) {
+      LKM_ROWS_CASE(2) LKM_ROWS_CASE(3) LKM_ROWS_CASE(4) LKM_ROWS_CASE(8) LKM_ROWS_CASE(16) LKM_ROWS_CASE(32) LKM_ROWS_CASE(64)
+      default: e = launch_rows_t<F, 0>(a, grid, smem, ctx->stream); break;
+    }
+  }
+#undef LKM_ROWS_CASE
+  CK(e);
+  ctx->launches++;
+  return LKM_OK;
+}
+
 struct LloydOut {
   uint64_t n_iter = 0, fallback_rows = 0;
   double inertia = 0, shift = 0;
@@ -751,6 +679,7 @@ static lkm_status run_lloyd(lkm_ctx* ctx, F* dC2, uint64_t k, uint64_t max_iter,
       tc5_chunk_n = pair32 ? 64 : kT5K;
       tc5_chunks = (int)((k + tc5_chunk_n - 1) / tc5_chunk_n);
       if (tc5_chunks > 1) CK(ctx->t5merge.ensure((n + 256) * 16));
+      if (ctx->tc5_defer) CK(ctx->ham_list.ensure((n + 256) * 4 + 16));   // rows for rows_top2_kernel; the count sits behind them
       // fused update of uniform tiles inside the screening kernel
       tc5_can_fuse = ctx->tc5_fuse != 0;   // in the launch of the last chunk, where the merged verdicts are known
       if (tc5_can_fuse) {
@@ -819,7 +748,7 @@ static lkm_status run_lloyd(lkm_ctx* ctx, F* dC2, uint64_t k, uint64_t max_iter,
   // an exact re-scan reads every centroid from L2 (k * d * 4 bytes per row): past ~0.4 % of the rows the 3xTF32 variant is
   // cheaper for the pair kernel (measured on the cfg3 shape from a k-means++ start); the pipeline kernel re-scans from
   // shared memory and tolerates 2 %
-  const double tc5_rescan_limit = 0.004, tc4_rescan_limit = 0.02, fuse_mixed_limit = 0.25;
+  const double tc5_rescan_limit = ctx->tc5_defer ? ctx->tc5_rescan_limit : 0.004, tc4_rescan_limit = 0.02, fuse_mixed_limit = 0.25;
   unsigned long long mixed_seen = 0;
   unsigned long long fb_seen = 0;
   for (;;) {
@@ -905,6 +834,13 @@ static lkm_status run_lloyd(lkm_ctx* ctx, F* dC2, uint64_t k, uint64_t max_iter,
             CK(ctx->t4prof.ensure(2 * 16 * 16 * 8));
             t5.prof = ctx->t4prof.as<long long>();
 #endif
+            unsigned int* rescan_count = nullptr;
+            if (ctx->tc5_defer) {
+              t5.rescan_list = ctx->ham_list.as<uint32_t>();
+              rescan_count = reinterpret_cast<unsigned int*>(ctx->ham_list.as<uint32_t>() + ((n + 256) & ~(uint64_t)3));
+              t5.rescan_count = rescan_count;
+              CK(cudaMemsetAsync(rescan_count, 0, 4, ctx->stream));
+            }
             // one launch per chunk of 256 centroids; the per-row (best, runner-up) state travels through t5merge
             for (int ch = 0; ch < tc5_chunks; ++ch) {
               t5.chunk_idx = ch;
@@ -925,6 +861,13 @@ static lkm_status run_lloyd(lkm_ctx* ctx, F* dC2, uint64_t k, uint64_t max_iter,
               else assign_tc5_kernel<128><<<tc5_grid, kT5Threads, tc5_smem, ctx->stream>>>(t5, tc5_map);
               CK(cudaGetLastError());
               ctx->launches++;
+            }
+            if (ctx->tc5_defer) {
+              // second stage: the rows the tensor-core certificate could not decide (fp32 FMA certificate, then the exact scan)
+              RowsArgs<float> ra{};
+              ra.X = dX; ra.n = n; ra.d = (int)d; ra.k = (int)k; ra.C = Ccur; ra.list = t5.rescan_list; ra.list_count = rescan_count;
+              ra.labels = ctx->labels.as<uint32_t>(); ra.state = dstate;
+              CKS(launch_rows<float>(ctx, ra, n));
             }
             assigned = true;
           } else if (use_tca) {
@@ -1000,6 +943,8 @@ static lkm_status run_lloyd(lkm_ctx* ctx, F* dC2, uint64_t k, uint64_t max_iter,
         }
       }
       if (flush && ctx->kernel_timing) CK(cudaEventRecord(ctx->iter_events[3 * it + 1], ctx->stream));
+      ctx->last_fin_src = fin_fused ? -1 : fin_src;
+      ctx->last_fin_src_inertia = fin_src_inertia;
       // combine the per-CTA partials in fixed order, then the m_k-means update
       if (fin_fused) {
         // done inside lloyd_tc4_kernel
@@ -1149,6 +1094,162 @@ static lkm_status run_lloyd(lkm_ctx* ctx, F* dC2, uint64_t k, uint64_t max_iter,
   out.inertia = ctx->h_state->inertia;
   out.shift = ctx->h_state->shift;
   out.final_buf = (int)(out.n_iter & 1);
+  return LKM_OK;
+}
+
+// compute_inertia (KM/algorithm.rs:608-620) of the resident rows under ctx->labels against dC; row-sharded runs add the
+// per-rank totals in rank order
+template <typename F>
+static lkm_status inertia_pass(lkm_ctx* ctx, const F* dC, double& total) {
+  const uint64_t n = ctx->n, d = ctx->d;
+  const int grid = (int)std::max<uint64_t>(1, std::min<uint64_t>((n + 255) / 256, 1024));
+  CK(ctx->ham_red.ensure(1024 * 8));
+  inertia_rows_kernel<F><<<grid, 256, 0, ctx->stream>>>(reinterpret_cast<const F*>(ctx->X), n, (int)d, dC, ctx->labels.as<uint32_t>(),
+                                                         ctx->ham_red.as<double>());
+  CK(cudaGetLastError());
+  ctx->launches++;
+  CK(cudaMemcpyAsync(ctx->h_pin, ctx->ham_red.p, (size_t)grid * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  double tot = 0.0;
+  for (int b = 0; b < grid; ++b) tot += ctx->h_pin[b];
+  if (ctx->world > 1) {
+    std::vector<unsigned char> all;
+    CKS(comm_allgather_host(ctx, &tot, 8, all));
+    tot = 0.0;
+    for (int r = 0; r < ctx->world; ++r) { double v; std::memcpy(&v, all.data() + (size_t)r * 8, 8); tot += v; }
+  }
+  total = tot;
+  return LKM_OK;
+}
+
+// One run of fit_hamerly (KM/algorithm.rs:258-279) from the centroids in buffer 0 of dC2.  Iteration 1 is Lloyd's
+// (HamerlyAlgorithm::new assigns every row, :418-456); from iteration 2 on the bounds decide which rows are looked at.
+// out.inertia = compute_inertia against the final centroids (:275,570-577); ctx->counts_out = the final memberships' counts.
+template <typename F>
+static lkm_status run_hamerly(lkm_ctx* ctx, F* dC2, uint64_t k, uint64_t max_iter, double tol, LloydOut& out) {
+  const uint64_t n = ctx->n, d = ctx->d, kd = k * d;
+  const F* dX = reinterpret_cast<const F*>(ctx->X);
+  const int keep = ctx->keep_labels;
+  ctx->keep_labels = 1;
+  ctx->ham_rows_scanned = ctx->ham_rows_tightened = 0;
+  // row-sharded runs (the running sums would need their own exchange) and k = 1 run Lloyd's iterations: same labels and
+  // centroids, and the result below is still Hamerly's (post-update inertia, this run's counts)
+  bool bounds = ctx->world == 1 && k >= 2 && n >= 1 && max_iter >= 2;
+  if (bounds) {
+    // scale of the fixed-point sums: |sum| <= n * max|x| must stay below 2^62
+    if (ctx->absmax_epoch != ctx->data_epoch || !ctx->own_X) {
+      CK(ctx->absmax.ensure(8));
+      CK(cudaMemsetAsync(ctx->absmax.p, 0, 8, ctx->stream));
+      abs_max_kernel<F><<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(dX, n * d, ctx->absmax.as<unsigned long long>());
+      CK(cudaGetLastError());
+      ctx->launches++;
+      CK(cudaMemcpyAsync(ctx->h_pin, ctx->absmax.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
+      CK(cudaStreamSynchronize(ctx->stream));
+      ctx->absmax_value = ctx->h_pin[0];
+      ctx->absmax_epoch = ctx->data_epoch;
+    }
+    if (!std::isfinite(ctx->absmax_value)) bounds = false;
+  }
+  lkm_status st = run_lloyd<F>(ctx, dC2, k, bounds ? 1 : max_iter, tol, out);
+  ctx->keep_labels = keep;
+  if (st != LKM_OK) return st;
+  const bool finished = !bounds || out.shift < tol || out.n_iter >= max_iter;
+  if (!finished) {
+    int ex = 0;
+    std::frexp(std::max(ctx->absmax_value, 1.0) * (double)(n + 2), &ex);   // n * max|x| < 2^ex
+    const int S = std::max(-300, std::min(60, 61 - ex));
+    const double scale = std::ldexp(1.0, S), inv_scale = std::ldexp(1.0, -S);
+    CK(ctx->ham_ub.ensure((n + 1) * sizeof(F)));
+    CK(ctx->ham_lb.ensure((n + 1) * sizeof(F)));
+    CK(ctx->ham_list.ensure((n + 256) * 4));
+    CK(ctx->ham_fx.ensure((kd + k) * 8));
+    CK(ctx->ham_moved.ensure(k * sizeof(F)));
+    CK(ctx->ham_s.ensure(k * sizeof(F)));
+    CK(ctx->ham_state.ensure(sizeof(HamState)));
+    const int cen_grid = (int)((kd + 255) / 256);
+    CK(ctx->shift_part.ensure((size_t)std::max(cen_grid, 1024) * 8));
+    LloydState* dstate = ctx->state.as<LloydState>();
+    HamState* hs = ctx->ham_state.as<HamState>();
+    long long* fx_sums = ctx->ham_fx.as<long long>();
+    long long* fx_counts = fx_sums + kd;
+    CK(cudaEventRecord(ctx->ev0, ctx->stream));
+    // the loop continues where iteration 1 stopped
+    std::memset(ctx->h_state, 0, sizeof(LloydState));
+    ctx->h_state->n_iter = 1;
+    CK(cudaMemcpyAsync(dstate, ctx->h_state, sizeof(LloydState), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemsetAsync(hs, 0, sizeof(HamState), ctx->stream));
+    // running sums and counts of iteration 1's assignment, as exact integers (see hamerly_sums_kernel)
+    CK(cudaMemsetAsync(fx_sums, 0, (kd + k) * 8, ctx->stream));
+    hamerly_sums_kernel<F><<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(dX, n, (int)d, ctx->labels.as<uint32_t>(), scale, fx_sums, fx_counts);
+    CK(cudaGetLastError());
+    ctx->launches++;
+    F* ub = ctx->ham_ub.as<F>();
+    F* lb = ctx->ham_lb.as<F>();
+    fill_kernel<F><<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(ub, n, std::numeric_limits<F>::infinity());
+    fill_kernel<F><<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(lb, n, (F)0);
+    CK(cudaGetLastError());
+    ctx->launches += 2;
+    auto moved_and_state = [&](const F* c_old, const F* c_new, bool with_state) -> lkm_status {
+      HamMovedArgs<F> ma{};
+      ma.C_old = c_old; ma.C_new = c_new; ma.k = (int)k; ma.d = (int)d; ma.moved = ctx->ham_moved.as<F>(); ma.s = ctx->ham_s.as<F>();
+      ma.state = with_state ? dstate : nullptr;
+      hamerly_moved_kernel<F><<<(int)k, 128, 0, ctx->stream>>>(ma);
+      HamStateArgs<F> sa{};
+      sa.shift_part = ctx->shift_part.as<double>(); sa.n_part = cen_grid; sa.moved = ctx->ham_moved.as<F>(); sa.k = (int)k;
+      sa.hs = hs; sa.state = with_state ? dstate : nullptr; sa.tol = tol; sa.max_iter = max_iter;
+      hamerly_state_kernel<F><<<1, 32, 0, ctx->stream>>>(sa);
+      CK(cudaGetLastError());
+      ctx->launches += 2;
+      return LKM_OK;
+    };
+    CKS(moved_and_state(dC2, dC2 + kd, false));   // iteration 1 moved the centroids from buffer 0 to buffer 1
+    uint64_t it = 1;
+    const int bgrid = (int)std::max<uint64_t>(1, std::min<uint64_t>((n + 255) / 256, (uint64_t)ctx->sm_count * 8));
+    for (;;) {
+      const uint64_t todo = std::min<uint64_t>(8, max_iter - it);
+      for (uint64_t q = 0; q < todo; ++q, ++it) {
+        const F* cur = dC2 + (it & 1) * kd;
+        F* nxt = dC2 + ((it + 1) & 1) * kd;
+        HamArgs<F> ha{};
+        ha.X = dX; ha.n = n; ha.d = (int)d; ha.k = (int)k; ha.C = cur; ha.labels = ctx->labels.as<uint32_t>(); ha.ub = ub; ha.lb = lb;
+        ha.moved = ctx->ham_moved.as<F>(); ha.s = ctx->ham_s.as<F>(); ha.list = ctx->ham_list.as<uint32_t>(); ha.hs = hs; ha.state = dstate;
+        hamerly_bounds_kernel<F><<<bgrid, 256, 0, ctx->stream>>>(ha);
+        CK(cudaGetLastError());
+        ctx->launches++;
+        RowsArgs<F> ra{};
+        ra.X = dX; ra.n = n; ra.d = (int)d; ra.k = (int)k; ra.C = cur; ra.list = ctx->ham_list.as<uint32_t>(); ra.list_count = &hs->list_count;
+        ra.labels = ctx->labels.as<uint32_t>(); ra.ub = ub; ra.lb = lb; ra.fx_sums = fx_sums; ra.fx_counts = fx_counts; ra.fx_scale = scale;
+        ra.state = dstate; ra.n_exact = &hs->rows_exact; ra.n_changed = &hs->rows_changed;
+        CKS(launch_rows<F>(ctx, ra, n));
+        HamCenArgs<F> ca{};
+        ca.fx_sums = fx_sums; ca.fx_counts = fx_counts; ca.inv_scale = inv_scale; ca.k = (int)k; ca.d = (int)d; ca.C_old = cur; ca.C_new = nxt;
+        ca.shift_part = ctx->shift_part.as<double>(); ca.counts_out = ctx->counts_out.as<double>(); ca.state = dstate;
+        hamerly_centroids_kernel<F><<<cen_grid, 256, 0, ctx->stream>>>(ca);
+        CK(cudaGetLastError());
+        ctx->launches++;
+        CKS(moved_and_state(cur, nxt, true));
+      }
+      CK(cudaMemcpyAsync(ctx->h_state, dstate, sizeof(LloydState), cudaMemcpyDeviceToHost, ctx->stream));
+      CK(cudaStreamSynchronize(ctx->stream));
+      if (ctx->h_state->done || it >= max_iter) break;
+    }
+    CK(cudaEventRecord(ctx->ev1, ctx->stream));
+    HamState hh;
+    CK(cudaMemcpyAsync(&hh, hs, sizeof(HamState), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaEventSynchronize(ctx->ev1));
+    CK(cudaStreamSynchronize(ctx->stream));
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+    out.ms += ms;
+    out.n_iter = ctx->h_state->n_iter;
+    out.shift = ctx->h_state->shift;
+    out.final_buf = (int)(out.n_iter & 1);
+    out.fallback_rows += hh.rows_exact;
+    ctx->ham_rows_scanned = hh.rows_scanned;
+    ctx->ham_rows_tightened = hh.rows_tightened;
+  }
+  CKS(inertia_pass<F>(ctx, dC2 + (size_t)out.final_buf * kd, out.inertia));
+  ctx->kept_labels_n = n;
   return LKM_OK;
 }
 
@@ -1733,16 +1834,21 @@ static lkm_status fit_impl(lkm_ctx* ctx, const lkm_params* p, lkm_rng rng_in, F*
   F min_inertia = std::numeric_limits<F>::infinity();
   bool have = false;
   std::vector<F> best(kd);
+  std::vector<double> best_cnt(k);
+  const bool hamerly = p->algorithm == LKM_ALGO_HAMERLY;
   LloydOut lo;
   float ms_total = 0;
   for (uint64_t run = 0; run < p->n_runs; ++run) {
     CKS(run_init<F>(ctx, p, rng, dC2));
-    CKS(run_lloyd<F>(ctx, dC2, k, p->max_n_iterations, tol, lo));
+    if (hamerly) CKS(run_hamerly<F>(ctx, dC2, k, p->max_n_iterations, tol, lo));
+    else CKS(run_lloyd<F>(ctx, dC2, k, p->max_n_iterations, tol, lo));
     ms_total += lo.ms;
     const F inertia = (F)lo.inertia;
-    if (inertia < min_inertia) {  // strict '<' from +inf: NaN never wins (KM/algorithm.rs:336)
+    if (inertia < min_inertia) {  // strict '<' from +inf: NaN never wins (KM/algorithm.rs:336 / :281)
       min_inertia = inertia;
       CK(cudaMemcpyAsync(best.data(), dC2 + (size_t)lo.final_buf * kd, kd * sizeof(F), cudaMemcpyDeviceToHost, ctx->stream));
+      // fit_hamerly keeps the memberships of the BEST run (KM/algorithm.rs:281-286); fit_lloyd's come from the last run
+      if (hamerly) CK(cudaMemcpyAsync(best_cnt.data(), ctx->counts_out.p, k * 8, cudaMemcpyDeviceToHost, ctx->stream));
       CK(cudaStreamSynchronize(ctx->stream));
       have = true;
     }
@@ -1756,8 +1862,11 @@ static lkm_status fit_impl(lkm_ctx* ctx, const lkm_params* p, lkm_rng rng_in, F*
   if (!have) return fail(ctx, LKM_ERR_INERTIA, "Fitting failed: No inertia improvement (-inf)");
   // cluster_count from the LAST run's final assignment (KM/algorithm.rs:304,342,355-357)
   std::vector<double> cnt(k);
-  CK(cudaMemcpyAsync(cnt.data(), ctx->counts_out.p, k * 8, cudaMemcpyDeviceToHost, ctx->stream));
-  CK(cudaStreamSynchronize(ctx->stream));
+  if (hamerly) cnt = best_cnt;
+  else {
+    CK(cudaMemcpyAsync(cnt.data(), ctx->counts_out.p, k * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+  }
   for (uint64_t c = 0; c < k; ++c) counts_out[c] = (F)cnt[c];
   std::memcpy(centroids_out, best.data(), kd * sizeof(F));
   *inertia_out = min_inertia / (F)n_glob;
@@ -1766,7 +1875,7 @@ static lkm_status fit_impl(lkm_ctx* ctx, const lkm_params* p, lkm_rng rng_in, F*
 
 template <typename F>
 static lkm_status lloyd_iters_impl(lkm_ctx* ctx, F* centroids_inout, uint64_t k, uint64_t max_iters, double tolerance,
-                                   F* counts_out, F* inertia_total_out, lkm_stats* stats) {
+                                   F* counts_out, F* inertia_total_out, lkm_stats* stats, bool hamerly = false) {
   if (!centroids_inout) return fail(ctx, LKM_ERR_INVALID_ARG, "null argument");
   if (k == 0) return fail(ctx, LKM_ERR_N_CLUSTERS, "n_clusters cannot be 0");
   if (tolerance < 0.0) return fail(ctx, LKM_ERR_TOLERANCE, "tolerance must not be negative");
@@ -1779,7 +1888,8 @@ static lkm_status lloyd_iters_impl(lkm_ctx* ctx, F* centroids_inout, uint64_t k,
   ctx->launches = 0;
   CK(cudaMemcpyAsync(dC2, centroids_inout, kd * sizeof(F), cudaMemcpyHostToDevice, ctx->stream));
   LloydOut lo;
-  CKS(run_lloyd<F>(ctx, dC2, k, max_iters, (double)(F)tolerance, lo));
+  if (hamerly) CKS(run_hamerly<F>(ctx, dC2, k, max_iters, (double)(F)tolerance, lo));
+  else CKS(run_lloyd<F>(ctx, dC2, k, max_iters, (double)(F)tolerance, lo));
   CK(cudaMemcpyAsync(centroids_inout, dC2 + (size_t)lo.final_buf * kd, kd * sizeof(F), cudaMemcpyDeviceToHost, ctx->stream));
   std::vector<double> cnt(k);
   CK(cudaMemcpyAsync(cnt.data(), ctx->counts_out.p, k * 8, cudaMemcpyDeviceToHost, ctx->stream));
@@ -1791,6 +1901,7 @@ static lkm_status lloyd_iters_impl(lkm_ctx* ctx, F* centroids_inout, uint64_t k,
     stats->n_iter = lo.n_iter; stats->last_shift = lo.shift; stats->inertia_total = lo.inertia;
     stats->device_ms = lo.ms; stats->kernel_launches = ctx->launches; stats->assign_path = (uint32_t)ctx->last_path;
     stats->main_kernel_ms = lo.main_ms; stats->fallback_rows = lo.fallback_rows;
+    if (hamerly) { stats->rows_scanned = ctx->ham_rows_scanned; stats->rows_tightened = ctx->ham_rows_tightened; }
   }
   return LKM_OK;
 }
@@ -2002,6 +2113,8 @@ LKM_EXPORT lkm_status lkm_create(lkm_ctx** out, int device) {
   if (const char* v = std::getenv("LKM_UPD")) ctx->upd_variant = std::atoi(v);
   if (const char* v = std::getenv("LKM_TC5")) ctx->tc5_enabled = std::atoi(v);
   if (const char* v = std::getenv("LKM_TC5_FUSE")) ctx->tc5_fuse = std::atoi(v);
+  if (const char* v = std::getenv("LKM_TC5_DEFER")) ctx->tc5_defer = std::atoi(v);
+  if (const char* v = std::getenv("LKM_TC5_RESCAN_LIMIT")) ctx->tc5_rescan_limit = std::atof(v);
   if (const char* v = std::getenv("LKM_PAIR32")) ctx->pair32 = std::atoi(v);
   if (const char* v = std::getenv("LKM_PDL")) g_pdl = std::atoi(v);
   if (const char* v = std::getenv("LKM_COOP")) g_coop = std::atoi(v);
@@ -2032,7 +2145,9 @@ LKM_EXPORT lkm_status lkm_destroy(lkm_ctx* ctx) {
   if (ctx->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->comm);
   DevBuf* bufs[] = {&ctx->xbuf, &ctx->cbuf, &ctx->part_sums, &ctx->part_counts, &ctx->part_inertia, &ctx->shift_part,
                     &ctx->counts_out, &ctx->state, &ctx->gather, &ctx->gather2, &ctx->labels, &ctx->dists, &ctx->wdists, &ctx->cum,
-                    &ctx->scratch, &ctx->tmpx, &ctx->tmpc, &ctx->idxbuf, &ctx->bsum, &ctx->weights, &ctx->flushbuf, &ctx->fin_sync, &ctx->para_c2, &ctx->tca_bsplit, &ctx->tca_cn, &ctx->tca_cmax};
+                    &ctx->scratch, &ctx->tmpx, &ctx->tmpc, &ctx->idxbuf, &ctx->bsum, &ctx->weights, &ctx->flushbuf, &ctx->fin_sync, &ctx->para_c2, &ctx->tca_bsplit, &ctx->tca_cn, &ctx->tca_cmax,
+                    &ctx->xmax2, &ctx->t4prof, &ctx->t5merge, &ctx->t5list, &ctx->ham_ub, &ctx->ham_lb, &ctx->ham_list, &ctx->ham_fx,
+                    &ctx->ham_moved, &ctx->ham_s, &ctx->ham_state, &ctx->ham_red, &ctx->absmax};
   for (DevBuf* b : bufs) b->release();
   for (cudaEvent_t e : ctx->iter_events) cudaEventDestroy(e);
   if (ctx->h_state) cudaFreeHost(ctx->h_state);
@@ -2168,6 +2283,13 @@ LKM_EXPORT lkm_status lkm_set_shard(lkm_ctx* ctx, uint64_t row_offset, uint64_t 
     if (!ctx) return LKM_ERR_INVALID_ARG;                                                                              \
     return lloyd_iters_impl<F>(ctx, centroids_inout, k, max_iters, tolerance, cluster_count_out, inertia_total_out,    \
                                stats_out);                                                                             \
+  }                                                                                                                    \
+  LKM_EXPORT lkm_status lkm_hamerly_iters_##SFX(lkm_ctx* ctx, F* centroids_inout, uint64_t k, uint64_t max_iters,      \
+                                                double tolerance, F* cluster_count_out, F* inertia_total_out,          \
+                                                lkm_stats* stats_out) {                                                \
+    if (!ctx) return LKM_ERR_INVALID_ARG;                                                                              \
+    return lloyd_iters_impl<F>(ctx, centroids_inout, k, max_iters, tolerance, cluster_count_out, inertia_total_out,    \
+                               stats_out, true);                                                                       \
   }                                                                                                                    \
   LKM_EXPORT lkm_status lkm_predict_##SFX(lkm_ctx* ctx, const F* centroids, uint64_t k, const F* x, uint64_t n,        \
                                           uint64_t d, int64_t row_stride, uint64_t* labels_out) {                      \

@@ -52,7 +52,22 @@ struct Tc5Args {
   uint32_t* mixed_count;    // [gridDim.x]
   int list_cap;
   uint32_t pack_mult;   // 256, passed as an argument so that the score pack stays an IMAD (see the E role)
+  // rows the certificate cannot decide: appended here for rows_top2_kernel (lkm_rows.cuh) instead of the inline exact scan
+  // (nullptr: scanned inline, one warp per row)
+  uint32_t* rescan_list;
+  unsigned int* rescan_count;
 };
+
+// appends the rows of this warp whose verdict is 2 to the global list (one atomic per warp)
+__device__ __forceinline__ unsigned int t5_defer(const Tc5Args& a, bool undecided, unsigned long long grow, int lane) {
+  const uint32_t fm = __ballot_sync(0xffffffffu, undecided);
+  if (fm == 0u) return 0u;
+  unsigned int base = 0;
+  if (lane == 0) base = atomicAdd(a.rescan_count, (unsigned int)__popc(fm));
+  base = __shfl_sync(0xffffffffu, base, 0);
+  if (undecided) a.rescan_list[base + __popc(fm & ((1u << lane) - 1u))] = (uint32_t)grow;
+  return lane == 0 ? (unsigned int)__popc(fm) : 0u;
+}
 
 // LKM_T5_TRACE: CTA 0 / 1 stamp event `ev` of tile `it` (cycles since the roles started) into a.prof[(cta * 16 + it) * 16 + ev]
 #ifdef LKM_T5_TRACE
@@ -538,6 +553,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kT5Threads, 1)
       // flag lists are double-buffered by tile parity: the other list's counter is cleared before this tile's
       // barrier, so that clearing and the next tile's appends are ordered by it
       uint32_t* flags = flags_all + (it & 1) * 128;
+      if (a.rescan_list != nullptr) {
+        if (verdict) a.labels[grow] = bidx;   // provisional for verdict 2: rows_top2_kernel overwrites it
+        my_fallbacks += t5_defer(a, verdict == 2, grow, lane);
+        if (wq == 0) T5TRACE(it, 8);
+        continue;
+      }
       if (verdict) {
         if (verdict == 1) a.labels[grow] = bidx;
         else flags[atomicAdd(&n_flag[it & 1], 1u)] = (uint32_t)row;
@@ -556,7 +577,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kT5Threads, 1)
         my_fallbacks += (row == 0) ? nf : 0u;
       }
     }
-    if (row == 0 && a.state && my_fallbacks) atomicAdd(&a.state->fallback_rows, (unsigned long long)my_fallbacks);
+    if (a.state && my_fallbacks) atomicAdd(&a.state->fallback_rows, (unsigned long long)my_fallbacks);
   }
   tc::tc_fence_before();
   __syncthreads();
@@ -854,7 +875,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(FUSE ? t5_fuse_threa
       uint32_t bidx = 0u;
       const int verdict = t5_merge_certify(a, win, grow, m1, m2, prev, bidx);
       uint32_t* flags = flags_all + (g * 2 + (u & 1u)) * 128;
-      if (verdict) {
+      const bool defer = a.rescan_list != nullptr;
+      if (defer) {
+        if (verdict) a.labels[grow] = bidx;   // provisional for verdict 2: rows_top2_kernel overwrites it
+        my_fallbacks += t5_defer(a, verdict == 2, grow, lane);
+      } else if (verdict) {
         if (verdict == 1) a.labels[grow] = bidx;
         else flags[atomicAdd(&n_flag[g][u & 1u], 1u)] = (uint32_t)row;
       }
@@ -867,20 +892,22 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(FUSE ? t5_fuse_threa
         __syncwarp();
         if (lane == 0) tc::mbar_arrive(&bar_verdict[it & 3]);
       }
-      if (row == 0) n_flag[g][(u + 1u) & 1u] = 0u;
-      tc::nb_sync(1 + g, 128);
-      const uint32_t nf = n_flag[g][u & 1u];
-      if (nf) {
-        for (uint32_t f = (uint32_t)wq; f < nf; f += 4) {
-          const unsigned long long fr = row0 + flags[f];
-          const int fi = t5_exact_label<D>(a.X, a.C, a.k, fr, lane);
-          if (lane == 0) a.labels[fr] = (uint32_t)fi;
+      if (!defer) {
+        if (row == 0) n_flag[g][(u + 1u) & 1u] = 0u;
+        tc::nb_sync(1 + g, 128);
+        const uint32_t nf = n_flag[g][u & 1u];
+        if (nf) {
+          for (uint32_t f = (uint32_t)wq; f < nf; f += 4) {
+            const unsigned long long fr = row0 + flags[f];
+            const int fi = t5_exact_label<D>(a.X, a.C, a.k, fr, lane);
+            if (lane == 0) a.labels[fr] = (uint32_t)fi;
+          }
+          my_fallbacks += (row == 0) ? nf : 0u;
         }
-        my_fallbacks += (row == 0) ? nf : 0u;
       }
       if (wq == 0) T5TRACE(it, 10);
     }
-    if (row == 0 && a.state && my_fallbacks) atomicAdd(&a.state->fallback_rows, (unsigned long long)my_fallbacks);
+    if (a.state && my_fallbacks) atomicAdd(&a.state->fallback_rows, (unsigned long long)my_fallbacks);
   }
   tc::tc_fence_before();
   __syncthreads();

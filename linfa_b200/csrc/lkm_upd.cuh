@@ -61,11 +61,31 @@ __device__ __forceinline__ void bulk_load_1d(void* dst, const void* src, uint32_
 }
 }  // namespace tc
 
+// one or two consecutive features per lane
+template <int V> struct UpdVec;
+template <> struct UpdVec<1> { using type = float; };
+template <> struct UpdVec<2> { using type = float2; };
+__device__ __forceinline__ float vadd(float a, float b) { return a + b; }
+__device__ __forceinline__ float vsqacc(float x, float c, float e) { const float d = x - c; return fmaf(d, d, e); }
+__device__ __forceinline__ float2 vadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ float vsqacc(float2 x, float2 c, float e) {
+  const float d0 = x.x - c.x, d1 = x.y - c.y;
+  return fmaf(d1, d1, fmaf(d0, d0, e));
+}
+template <typename Vf> __device__ __forceinline__ Vf upd_zero();
+template <> __device__ __forceinline__ float upd_zero<float>() { return 0.f; }
+template <> __device__ __forceinline__ float2 upd_zero<float2>() { return make_float2(0.f, 0.f); }
+template <typename Vf> __device__ __forceinline__ Vf upd_ld(const float* p) { return *reinterpret_cast<const Vf*>(p); }
+template <typename Vf> __device__ __forceinline__ Vf upd_ldg(const float* p) { return __ldg(reinterpret_cast<const Vf*>(p)); }
+template <typename Vf> __device__ __forceinline__ void upd_st(float* p, Vf v) { *reinterpret_cast<Vf*>(p) = v; }
+
 template <int D>
 __global__ void __launch_bounds__(kUpdThreads, 1) update_rows_kernel(const UpdArgs a, const __grid_constant__ CUtensorMap tmap) {
   static_assert(D == 32 || D == 64 || D == 128, "row width");
-  constexpr int QF = D / 32;                 // feature slices
+  constexpr int V = D >= 64 ? 2 : 1;         // features per lane
+  constexpr int QF = D / (32 * V);           // feature slices
   constexpr int NCLS = kUpdConsumers / QF;   // cluster classes
+  using Vf = typename UpdVec<V>::type;
   constexpr int SUBS = 128 / D;                            // 32-row sub-tiles per stage (a TMA operation moves 16 KB:
                                                            // smaller ones are bound by the per-operation cost of the copy engine)
   constexpr int kStageRows = kUpdSubRows * SUBS;
@@ -139,25 +159,73 @@ __global__ void __launch_bounds__(kUpdThreads, 1) update_rows_kernel(const UpdAr
       if (++s == R) { s = 0; ph ^= 1u; }
     }
   } else {
+    // lane = V consecutive features (V = 2 for D >= 64: 64-bit shared-memory accesses, half the instructions per row)
     const int fs = warp % QF, cls = warp / QF;
-    const int fo = fs * 32 + lane;             // feature owned by this lane
+    const int fo = (fs * 32 + lane) * V;       // first feature owned by this lane
     const float* Cf = a.C + (size_t)chunk_base * D + fo;
     float* accf = acc + fo;
     int s = 0;
     uint32_t last_L = 0xFFFFFFFFu;
-    float last_cv = 0.f;
+    Vf last_cv = upd_zero<Vf>();
+    const uint32_t lt_mask = (1u << lane) - 1u;
     for (unsigned long long j = j0; j < j1; ++j) {
       const unsigned char* st = ring + (size_t)s * kStage;
       const unsigned long long sj = stage_of(j);
       tc::nb_sync(1 + s, (kUpdConsumers + 1) * 32);
 #pragma unroll 1
       for (int sub = 0; sub < SUBS; ++sub) {
-      const float* xs = reinterpret_cast<const float*>(st) + (size_t)sub * kUpdSubRows * D + fs * 32 + lane;     // row r at xs[r * D]
+      const float* xs = reinterpret_cast<const float*>(st) + (size_t)sub * kUpdSubRows * D + fo;     // row r at xs[r * D]
       uint32_t lab = reinterpret_cast<const uint32_t*>(st + kStageX)[sub * kUpdSubRows + lane];
       if (sj * kStageRows + (unsigned)(sub * kUpdSubRows + lane) >= a.n) lab = 0xFFFFFFFFu;
       const uint32_t c = lab - (uint32_t)chunk_base;
       const bool mine = c < (uint32_t)chunk_rows && (int)(c % (uint32_t)NCLS) == cls;
       uint32_t m = __ballot_sync(0xffffffffu, mine);
+      if (m == 0u) continue;
+      // rows of this warp with the same cluster; rank = position of the row among them
+      const uint32_t peers = __match_any_sync(0xffffffffu, mine ? c : (0x80000000u | (uint32_t)lane));
+      const int rank = __popc(peers & lt_mask);
+      const uint32_t leaders = __ballot_sync(0xffffffffu, mine && rank == 0);
+      if (__popc(leaders) > 4) {
+        // Unordered rows: many clusters, one or two rows each.  Round t takes the t-th row of every cluster, so the rows
+        // of a round touch distinct accumulators and their loads / read-modify-writes overlap (eight in flight); a
+        // cluster's rows still reach its accumulator in row order.
+        float e_sub = 0.f;
+        for (int round = 0;; ++round) {
+          uint32_t p = __ballot_sync(0xffffffffu, mine && rank == round);
+          if (p == 0u) break;
+          while (p) {
+            int r[8];
+            uint32_t L[8];
+            bool on[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              on[q] = p != 0u;
+              r[q] = on[q] ? __ffs(p) - 1 : 0;
+              p &= p - 1u;
+              L[q] = __shfl_sync(0xffffffffu, c, r[q]);
+            }
+            Vf x[8], av[8], cv[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              if (on[q]) {
+                cv[q] = upd_ldg<Vf>(Cf + (size_t)L[q] * D);
+                x[q] = upd_ld<Vf>(xs + r[q] * D);
+                av[q] = upd_ld<Vf>(accf + (size_t)L[q] * D);
+              }
+            }
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              if (on[q]) {
+                upd_st<Vf>(accf + (size_t)L[q] * D, vadd(av[q], x[q]));
+                e_sub = vsqacc(x[q], cv[q], e_sub);
+                if (fs == 0 && lane == 0) cnt[L[q]] += 1u;
+              }
+            }
+          }
+        }
+        inert += (double)e_sub;
+        continue;
+      }
       while (m) {
         // up to four segments (clusters of this warp present in the sub-tile) at a time
         uint32_t pm[4], L[4];
@@ -170,43 +238,44 @@ __global__ void __launch_bounds__(kUpdThreads, 1) update_rows_kernel(const UpdAr
             m &= ~pm[q];
           }
         }
-        float cv[4], av[4], sv[4], ev[4];
+        Vf cv[4], av[4], sv[4];
+        float ev[4];
         // the centroid coordinate comes from L2 (hundreds of cycles under load) and sits in front of the first
         // subtraction: keep the last one, which is the one needed again while the rows of a cluster are contiguous
-        cv[0] = last_cv; av[0] = 0.f;
+        cv[0] = last_cv; av[0] = upd_zero<Vf>();
         if (pm[0]) {
-          if (L[0] != last_L) { cv[0] = __ldg(Cf + (size_t)L[0] * D); last_L = L[0]; last_cv = cv[0]; }
-          av[0] = accf[(size_t)L[0] * D];
+          if (L[0] != last_L) { cv[0] = upd_ldg<Vf>(Cf + (size_t)L[0] * D); last_L = L[0]; last_cv = cv[0]; }
+          av[0] = upd_ld<Vf>(accf + (size_t)L[0] * D);
         }
 #pragma unroll
         for (int q = 1; q < 4; ++q) {
-          cv[q] = 0.f; av[q] = 0.f;
-          if (pm[q]) { cv[q] = __ldg(Cf + (size_t)L[q] * D); av[q] = accf[(size_t)L[q] * D]; }
+          cv[q] = upd_zero<Vf>(); av[q] = upd_zero<Vf>();
+          if (pm[q]) { cv[q] = upd_ldg<Vf>(Cf + (size_t)L[q] * D); av[q] = upd_ld<Vf>(accf + (size_t)L[q] * D); }
         }
         if (pm[0] == 0xffffffffu) {
           // the whole sub-tile belongs to one cluster: two interleaved chains (even / odd rows), fixed order
-          float s0 = 0.f, s1 = 0.f, e0 = 0.f, e1 = 0.f;
+          Vf s0 = upd_zero<Vf>(), s1 = upd_zero<Vf>();
+          float e0 = 0.f, e1 = 0.f;
 #pragma unroll
           for (int r = 0; r < kUpdSubRows; r += 2) {
-            const float x0 = xs[r * D], x1 = xs[(r + 1) * D];
-            s0 += x0; s1 += x1;
-            const float d0 = x0 - cv[0], d1 = x1 - cv[0];
-            e0 = fmaf(d0, d0, e0); e1 = fmaf(d1, d1, e1);
+            const Vf x0 = upd_ld<Vf>(xs + r * D), x1 = upd_ld<Vf>(xs + (r + 1) * D);
+            s0 = vadd(s0, x0); s1 = vadd(s1, x1);
+            e0 = vsqacc(x0, cv[0], e0); e1 = vsqacc(x1, cv[0], e1);
           }
-          sv[0] = s0 + s1; ev[0] = e0 + e1;
-          sv[1] = sv[2] = sv[3] = 0.f; ev[1] = ev[2] = ev[3] = 0.f;
+          sv[0] = vadd(s0, s1); ev[0] = e0 + e1;
+          sv[1] = sv[2] = sv[3] = upd_zero<Vf>(); ev[1] = ev[2] = ev[3] = 0.f;
         } else {
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
-            float sq = 0.f, eq = 0.f;
+            Vf sq = upd_zero<Vf>();
+            float eq = 0.f;
             uint32_t p = pm[q];
             while (p) {
               const int r = __ffs(p) - 1;
               p &= p - 1u;
-              const float x = xs[r * D];
-              sq += x;
-              const float df = x - cv[q];
-              eq = fmaf(df, df, eq);
+              const Vf x = upd_ld<Vf>(xs + r * D);
+              sq = vadd(sq, x);
+              eq = vsqacc(x, cv[q], eq);
             }
             sv[q] = sq; ev[q] = eq;
           }
@@ -214,7 +283,7 @@ __global__ void __launch_bounds__(kUpdThreads, 1) update_rows_kernel(const UpdAr
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           if (pm[q]) {
-            accf[(size_t)L[q] * D] = av[q] + sv[q];
+            upd_st<Vf>(accf + (size_t)L[q] * D, vadd(av[q], sv[q]));
             inert += (double)ev[q];
             if (fs == 0 && lane == 0) cnt[L[q]] += (uint32_t)__popc(pm[q]);
           }

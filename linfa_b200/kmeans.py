@@ -238,7 +238,7 @@ class Context:
         self.check(getattr(_ffi.lib, f"lkm_get_data_{sfx}")(self.h, row0, rows, _ffi.fptr(out, ct)))
         return out
 
-    def lloyd_iters(self, centroids, max_iters, tolerance):
+    def lloyd_iters(self, centroids, max_iters, tolerance, entry="lkm_lloyd_iters"):
         """fit_lloyd's loop from given centroids; returns (centroids, counts, inertia_total, stats)."""
         c = np.ascontiguousarray(centroids, dtype=self.dtype).copy()
         sfx, ct = _ffi.sfx_of(self.dtype)
@@ -246,11 +246,15 @@ class Context:
         counts = np.zeros(k, dtype=self.dtype)
         inertia = np.zeros(1, dtype=self.dtype)
         stats = _ffi.lkm_stats()
-        self.check(getattr(_ffi.lib, f"lkm_lloyd_iters_{sfx}")(self.h, _ffi.fptr(c, ct), k, max_iters, float(tolerance),
-                                                               _ffi.fptr(counts, ct), _ffi.fptr(inertia, ct),
-                                                               C.byref(stats)))
+        self.check(getattr(_ffi.lib, f"{entry}_{sfx}")(self.h, _ffi.fptr(c, ct), k, max_iters, float(tolerance),
+                                                       _ffi.fptr(counts, ct), _ffi.fptr(inertia, ct), C.byref(stats)))
         self.last_stats = stats
         return c, counts, inertia[0], stats
+
+    def hamerly_iters(self, centroids, max_iters, tolerance):
+        """fit_hamerly's loop (KM/algorithm.rs:262-279) from given centroids: same returns as lloyd_iters, the inertia
+        being compute_inertia against the returned centroids; stats.rows_scanned / rows_tightened count the bound misses."""
+        return self.lloyd_iters(centroids, max_iters, tolerance, entry="lkm_hamerly_iters")
 
     def assign(self, centroids, x=None, want_labels=True, want_dists=True):
         """update_memberships_and_dists on `x` (host array) or on the resident matrix."""

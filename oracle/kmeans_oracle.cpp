@@ -602,6 +602,185 @@ int fit_lloyd(const F* X, uint64_t n, uint64_t d, uint64_t k, uint64_t n_runs, u
   return 0;
 }
 
+// ---------------------------------------------------------------------------
+// Hamerly (KM/algorithm.rs:248-291, 396-603, 889-919)
+// ---------------------------------------------------------------------------
+
+// L2Dist::distance on two rows (linfa-nn distance.rs:63-65): sq_l2_dist in F, sqrt in f64, cast to F
+template <class F> inline F l2_dist_row(const F* a, const F* b, uint64_t d) {
+  return (F)std::sqrt((double)sq_l2_dist<F>(a, b, d));
+}
+
+// two_closest_centroids (KM/algorithm.rs:889-919): argument order distance(observation, centroid); centroids 0 and 1
+// seed the scan (a tie between them goes to 1), then `closest <= dist < second` / `dist < closest`
+template <class F>
+inline void two_closest_centroids(const F* C, uint64_t k, uint64_t d, const F* x, uint64_t* idx, F* closest, F* second) {
+  if (k == 1) { *idx = 0; *closest = (F)0; *second = (F)0; return; }
+  const F dist1 = l2_dist_row<F>(x, C, d);
+  const F dist2 = l2_dist_row<F>(x, C + d, d);
+  uint64_t ci = dist1 < dist2 ? 0 : 1;
+  F cd = dist1 < dist2 ? dist1 : dist2;
+  F sd = dist1 < dist2 ? dist2 : dist1;
+  for (uint64_t c = 2; c < k; ++c) {
+    const F v = l2_dist_row<F>(x, C + c * d, d);
+    if (cd <= v && v < sd) sd = v;
+    else if (v < cd) { sd = cd; ci = c; cd = v; }
+  }
+  *idx = ci; *closest = cd; *second = sd;
+}
+
+// two_farthest_indices (KM/algorithm.rs:585-603)
+template <class F> inline void two_farthest_indices(const F* m, uint64_t k, uint64_t* f1, uint64_t* f2) {
+  if (k < 2) { *f1 = 0; *f2 = 0; return; }
+  uint64_t a, b;
+  if (m[1] >= m[0]) { a = 1; b = 0; } else { a = 0; b = 1; }
+  for (uint64_t i = 2; i < k; ++i) {
+    if (m[i] >= m[a]) { b = a; a = i; }
+    else if (m[i] > m[b]) b = i;
+  }
+  *f1 = a; *f2 = b;
+}
+
+// compute_inertia (KM/algorithm.rs:608-620): fold in F, row order
+template <class F, class Acc>
+F compute_inertia(const F* X, uint64_t n, uint64_t d, const uint64_t* labels, const F* C) {
+  Acc acc = (Acc)0;
+  for (uint64_t i = 0; i < n; ++i) acc = acc + (Acc)sq_l2_dist<F>(X + i * d, C + labels[i] * d, d);
+  return (F)acc;
+}
+
+// HamerlyAlgorithm (KM/algorithm.rs:396-583).  Acc = F is the reference's arithmetic (running sums in F, moved by
+// += / -= per changed row, :507-523); Acc = double keeps the running sums in f64 (the accumulation rule the GPU
+// path is compared against).
+template <class F, class Acc> struct Hamerly {
+  const F* X; uint64_t n, d, k;
+  std::vector<F> C;
+  std::vector<uint64_t> memberships, prev;
+  std::vector<F> upper, lower;
+  std::vector<uint64_t> counts;
+  std::vector<Acc> sums;
+  int n_threads;
+  uint64_t scans = 0, tightened = 0;
+
+  Hamerly(const F* X_, uint64_t n_, uint64_t d_, uint64_t k_, const F* C0, int threads)   // new (:418-456)
+      : X(X_), n(n_), d(d_), k(k_), C(C0, C0 + k_ * d_), memberships(n_, 0), prev(n_, 0), upper(n_, (F)0), lower(n_, (F)0),
+        counts(k_, 0), sums(k_ * d_, (Acc)0), n_threads(threads) {
+    par_rows(n, n_threads, [&](uint64_t lo, uint64_t hi) {
+      for (uint64_t i = lo; i < hi; ++i) two_closest_centroids<F>(C.data(), k, d, X + i * d, &memberships[i], &upper[i], &lower[i]);
+    });
+    for (uint64_t i = 0; i < n; ++i) {
+      counts[memberships[i]] += 1;
+      for (uint64_t j = 0; j < d; ++j) sums[memberships[i] * d + j] = sums[memberships[i] * d + j] + (Acc)X[i * d + j];
+    }
+  }
+  void reassign() {   // reassign_observations (:472-524)
+    std::vector<F> near(k);
+    for (uint64_t c = 0; c < k; ++c) {   // nearest_inter_centroid_distances (:462-470)
+      uint64_t ii; F cl;
+      two_closest_centroids<F>(C.data(), k, d, C.data() + c * d, &ii, &cl, &near[c]);
+    }
+    std::atomic<uint64_t> sc{0}, ti{0};
+    par_rows(n, n_threads, [&](uint64_t lo, uint64_t hi) {
+      uint64_t my_sc = 0, my_ti = 0;
+      for (uint64_t i = lo; i < hi; ++i) {
+        const uint64_t cur = memberships[i];
+        prev[i] = cur;
+        const F half = near[cur] / (F)2;
+        const F threshold = half > lower[i] ? half : lower[i];   // F::max
+        if (upper[i] > threshold) {
+          upper[i] = l2_dist_row<F>(X + i * d, C.data() + cur * d, d);
+          ++my_ti;
+          if (upper[i] > threshold) {
+            two_closest_centroids<F>(C.data(), k, d, X + i * d, &memberships[i], &upper[i], &lower[i]);
+            ++my_sc;
+          }
+        }
+      }
+      sc += my_sc; ti += my_ti;
+    });
+    scans += sc; tightened += ti;
+    for (uint64_t i = 0; i < n; ++i) {
+      if (prev[i] != memberships[i]) {
+        counts[prev[i]] -= 1;
+        counts[memberships[i]] += 1;
+        for (uint64_t j = 0; j < d; ++j) sums[prev[i] * d + j] = sums[prev[i] * d + j] - (Acc)X[i * d + j];
+        for (uint64_t j = 0; j < d; ++j) sums[memberships[i] * d + j] = sums[memberships[i] * d + j] + (Acc)X[i * d + j];
+      }
+    }
+  }
+  // recompute_centroids (:527-553): returns convergence_dist, fills distances_moved
+  F recompute(std::vector<F>& moved) {
+    std::vector<F> Cn(k * d);
+    for (uint64_t c = 0; c < k; ++c)
+      for (uint64_t j = 0; j < d; ++j) {
+        const Acc v = sums[c * d + j] + (Acc)C[c * d + j];
+        Cn[c * d + j] = (F)(v / (Acc)(F)(counts[c] + 1));
+      }
+    moved.assign(k, (F)0);
+    for (uint64_t c = 0; c < k; ++c) moved[c] = l2_dist_row<F>(C.data() + c * d, Cn.data() + c * d, d);
+    const F conv = l2_distance<F>(C.data(), Cn.data(), k * d);
+    C.swap(Cn);
+    return conv;
+  }
+  void update_bounds(const std::vector<F>& moved) {   // (:555-568)
+    uint64_t f1, f2;
+    two_farthest_indices<F>(moved.data(), k, &f1, &f2);
+    for (uint64_t i = 0; i < n; ++i) {
+      upper[i] = upper[i] + moved[memberships[i]];
+      lower[i] = lower[i] - (memberships[i] == f1 ? moved[f2] : moved[f1]);
+    }
+  }
+};
+
+// fit_hamerly + get_kmeans_result (KM/algorithm.rs:248-291, 345-367)
+template <class F, class Acc>
+int fit_hamerly(const F* X, uint64_t n, uint64_t d, uint64_t k, uint64_t n_runs, uint64_t max_iter, F tol, int method,
+                const F* precomputed, Xoshiro256Plus& rng_in, F* C_out, F* counts_out, F* inertia_out,
+                uint64_t* n_iter_out, uint64_t* labels_out, uint64_t* scans_out, int n_threads, int n_splits) {
+  if (k == 0) return 10;
+  if (n_runs == 0) return 11;
+  if (tol <= (F)0) return 12;
+  if (max_iter == 0) return 13;
+  Xoshiro256Plus rng = rng_in;
+  F min_inertia = std::numeric_limits<F>::infinity();
+  bool have_best = false;
+  std::vector<F> best(k * d), C0(k * d);
+  std::vector<uint64_t> best_members(n, 0);
+  uint64_t last_iters = 0, scans = 0;
+  for (uint64_t run = 0; run < n_runs; ++run) {
+    const int st = run_init<F>(method, k, X, n, d, precomputed, rng, C0.data(), n_threads, n_splits);
+    if (st) return st;
+    Hamerly<F, Acc> h(X, n, d, k, C0.data(), n_threads);
+    uint64_t n_iter = 0;
+    std::vector<F> moved;
+    F inertia;
+    for (;;) {
+      if (n_iter > 0) h.reassign();
+      n_iter += 1;
+      const F conv = h.recompute(moved);
+      if (conv < tol || n_iter == max_iter) { inertia = compute_inertia<F, Acc>(X, n, d, h.memberships.data(), h.C.data()); break; }
+      h.update_bounds(moved);
+    }
+    last_iters = n_iter;
+    scans += h.scans;
+    if (inertia < min_inertia) {
+      min_inertia = inertia;
+      best = h.C;
+      best_members = h.memberships;
+      have_best = true;
+    }
+  }
+  if (n_iter_out) *n_iter_out = last_iters;
+  if (scans_out) *scans_out = scans;
+  if (labels_out) std::memcpy(labels_out, best_members.data(), sizeof(uint64_t) * n);
+  if (!have_best) return 1;
+  for (uint64_t c = 0; c < k; ++c) counts_out[c] = (F)0;
+  for (uint64_t i = 0; i < n; ++i) counts_out[best_members[i]] = counts_out[best_members[i]] + (F)1;
+  std::memcpy(C_out, best.data(), sizeof(F) * k * d);
+  *inertia_out = min_inertia / (F)n;
+  return 0;
+}
+
 // FitWith::fit_with (KM/algorithm.rs:635-715), one mini-batch step.
 // model_in: has_model != 0 -> (C_inout, counts_inout) hold the previous model.
 // returns 0 converged (Ok), 20 NotConverged (model still written), else error.
@@ -763,6 +942,29 @@ ORC_EXPORT int orc_index_sample(uint64_t* state, uint64_t length, uint64_t amoun
                                   inertia_out, n_iter_out, labels_out, n_threads, n_splits);                         \
     return fit_lloyd<F, F>(X, n, d, k, n_runs, max_iter, tol, method, precomputed, g, C_out, counts_out,             \
                            inertia_out, n_iter_out, labels_out, n_threads, n_splits);                                \
+  }                                                                                                                   \
+  ORC_EXPORT int orc_fit_hamerly_##SFX(const F* X, uint64_t n, uint64_t d, uint64_t k, uint64_t n_runs,              \
+                                       uint64_t max_iter, F tol, int method, const F* precomputed,                   \
+                                       const uint64_t* state, F* C_out, F* counts_out, F* inertia_out,               \
+                                       uint64_t* n_iter_out, uint64_t* labels_out, uint64_t* scans_out,              \
+                                       int n_threads, int n_splits, int acc_f64) {                                   \
+    Xoshiro256Plus g;                                                                                                 \
+    std::memcpy(g.s, state, 32);                                                                                      \
+    if (acc_f64)                                                                                                      \
+      return fit_hamerly<F, double>(X, n, d, k, n_runs, max_iter, tol, method, precomputed, g, C_out, counts_out,    \
+                                    inertia_out, n_iter_out, labels_out, scans_out, n_threads, n_splits);            \
+    return fit_hamerly<F, F>(X, n, d, k, n_runs, max_iter, tol, method, precomputed, g, C_out, counts_out,           \
+                             inertia_out, n_iter_out, labels_out, scans_out, n_threads, n_splits);                   \
+  }                                                                                                                   \
+  ORC_EXPORT void orc_two_closest_##SFX(const F* C, uint64_t k, uint64_t d, const F* x, uint64_t* idx, F* closest,   \
+                                        F* second) {                                                                  \
+    two_closest_centroids<F>(C, k, d, x, idx, closest, second);                                                      \
+  }                                                                                                                   \
+  ORC_EXPORT void orc_two_farthest_##SFX(const F* m, uint64_t k, uint64_t* f1, uint64_t* f2) {                       \
+    two_farthest_indices<F>(m, k, f1, f2);                                                                            \
+  }                                                                                                                   \
+  ORC_EXPORT F orc_compute_inertia_##SFX(const F* X, uint64_t n, uint64_t d, const uint64_t* labels, const F* C) {   \
+    return compute_inertia<F, F>(X, n, d, labels, C);                                                                 \
   }                                                                                                                   \
   ORC_EXPORT int orc_fit_with_##SFX(const F* X, uint64_t n, uint64_t d, uint64_t k, uint64_t n_runs, F tol,          \
                                     int method, const F* precomputed, const uint64_t* state, int has_model,          \

@@ -97,6 +97,10 @@ class Oracle:
             sig("membership_counts", None, [fp, u64, fp, u64, u64, fp, i32])
             sig("fit", i32, [fp, u64, u64, u64, u64, u64, ct, i32, fp, _u64p, fp, fp, fp, _u64p, _u64p, i32, i32, i32])
             sig("fit_with", i32, [fp, u64, u64, u64, u64, ct, i32, fp, _u64p, i32, fp, fp, fp, i32, i32])
+            sig("fit_hamerly", i32, [fp, u64, u64, u64, u64, u64, ct, i32, fp, _u64p, fp, fp, fp, _u64p, _u64p, _u64p, i32, i32, i32])
+            sig("two_closest", None, [fp, u64, u64, fp, _u64p, fp, fp])
+            sig("two_farthest", None, [fp, u64, _u64p, _u64p])
+            sig("compute_inertia", ct, [fp, u64, u64, _u64p, fp])
         self.threads = max(1, int(L.orc_hardware_threads()))
 
     # -- helpers -----------------------------------------------------------
@@ -240,6 +244,50 @@ class Oracle:
             threads or self.threads, rayon_threads, int(acc_f64))
         return dict(status=int(st), centroids=Cn[:k], cluster_count=counts[:k], inertia=inertia[0],
                     n_iter=int(n_iter[0]), labels=labels)
+
+    def fit_hamerly(self, X, k, rng, n_runs=10, max_iter=300, tol=1e-4, method=INIT_KMEANSPP, precomputed=None,
+                    threads=None, rayon_threads=1, acc_f64=False):
+        """fit_hamerly (KM/algorithm.rs:248-291).  Returns dict(status, centroids, cluster_count, inertia, n_iter, labels
+        (the best run's), scans (two_closest_centroids calls after the first iteration))."""
+        X = np.ascontiguousarray(X)
+        sfx, ct = self._sfx(X.dtype)
+        n, d = X.shape
+        Cn = np.zeros((max(k, 1), d), dtype=X.dtype)
+        counts = np.zeros(max(k, 1), dtype=X.dtype)
+        inertia = np.zeros(1, dtype=X.dtype)
+        n_iter = np.zeros(1, dtype=np.uint64)
+        scans = np.zeros(1, dtype=np.uint64)
+        labels = np.zeros(n, dtype=np.uint64)
+        pre = np.ascontiguousarray(precomputed, dtype=X.dtype) if precomputed is not None else None
+        st = self._fn("fit_hamerly", sfx)(
+            _ptr(X, ct), n, d, k, n_runs, max_iter, ct(tol), method, _ptr(pre, ct), _ptr(rng.state, C.c_uint64),
+            _ptr(Cn, ct), _ptr(counts, ct), _ptr(inertia, ct), _ptr(n_iter, C.c_uint64), _ptr(labels, C.c_uint64),
+            _ptr(scans, C.c_uint64), threads or self.threads, rayon_threads, int(acc_f64))
+        return dict(status=int(st), centroids=Cn[:k], cluster_count=counts[:k], inertia=inertia[0],
+                    n_iter=int(n_iter[0]), labels=labels, scans=int(scans[0]))
+
+    def two_closest(self, Cn, x):
+        Cn = np.ascontiguousarray(Cn)
+        x = np.ascontiguousarray(x, dtype=Cn.dtype)
+        sfx, ct = self._sfx(Cn.dtype)
+        idx = np.zeros(1, dtype=np.uint64)
+        a, b = np.zeros(1, dtype=Cn.dtype), np.zeros(1, dtype=Cn.dtype)
+        self._fn("two_closest", sfx)(_ptr(Cn, ct), Cn.shape[0], Cn.shape[1], _ptr(x, ct), _ptr(idx, C.c_uint64), _ptr(a, ct), _ptr(b, ct))
+        return int(idx[0]), a[0], b[0]
+
+    def two_farthest(self, moved):
+        moved = np.ascontiguousarray(moved)
+        sfx, ct = self._sfx(moved.dtype)
+        f1, f2 = np.zeros(1, dtype=np.uint64), np.zeros(1, dtype=np.uint64)
+        self._fn("two_farthest", sfx)(_ptr(moved, ct), moved.size, _ptr(f1, C.c_uint64), _ptr(f2, C.c_uint64))
+        return int(f1[0]), int(f2[0])
+
+    def compute_inertia(self, X, labels, Cn):
+        X = np.ascontiguousarray(X)
+        Cn = np.ascontiguousarray(Cn, dtype=X.dtype)
+        lab = np.ascontiguousarray(labels, dtype=np.uint64)
+        sfx, ct = self._sfx(X.dtype)
+        return self._fn("compute_inertia", sfx)(_ptr(X, ct), X.shape[0], X.shape[1], _ptr(lab, C.c_uint64), _ptr(Cn, ct))
 
     def fit_with(self, X, k, rng, model=None, n_runs=10, tol=1e-4, method=INIT_KMEANSPP, precomputed=None,
                  threads=None, rayon_threads=1):
