@@ -220,6 +220,26 @@ lkm_status lkm_fit_with_f64(lkm_ctx* ctx, const lkm_params* p, lkm_rng rng, int 
                             uint64_t model_cols, double* centroids_inout, double* cluster_count_inout,
                             double* inertia_out);
 
+/* -- SilhouetteScore::silhouette_score (src/metrics_clustering.rs:65-135) ---
+ * mean over the samples of (b - a) / max(a, b), a = mean distance to the other
+ * samples of the own cluster, b = smallest mean distance to another cluster;
+ * 1 when there is a single label (:77-80).  labels: any u64 values (the
+ * `usize` targets KMeans::predict produces).  O(n^2 d) on the device; the
+ * per-sample scores follow the reference's arithmetic operation by operation. */
+lkm_status lkm_silhouette_score_f32(lkm_ctx* ctx, const float* x, uint64_t n, uint64_t d, int64_t row_stride,
+                                    const uint64_t* labels, float* score_out);
+lkm_status lkm_silhouette_score_f64(lkm_ctx* ctx, const double* x, uint64_t n, uint64_t d, int64_t row_stride,
+                                    const uint64_t* labels, double* score_out);
+
+/* -- .npy files: ndarray_npy::write_npy as used by the reference's example
+ * (algorithms/linfa-clustering/examples/kmeans.rs:40-42: the records and the
+ * memberships as u64).  Format 1.0, little endian, C order.  dtype: 0 = f32
+ * ("<f4"), 1 = f64 ("<f8"), 2 = u64 ("<u8").  Host only, no context needed. */
+lkm_status lkm_write_npy(const char* path, int dtype, const void* data, int ndim, const uint64_t* shape);
+lkm_status lkm_read_npy_header(const char* path, int* dtype_out, int* ndim_out, uint64_t* shape_out /* [8] */,
+                               uint64_t* data_offset_out);
+lkm_status lkm_read_npy_data(const char* path, uint64_t data_offset, void* out, uint64_t bytes);
+
 /* -- knobs that are not in the reference (all have defaults) --------------- */
 /* force an assignment path: -1 auto (default), 0 exact, 1 certified FMA, 2 tcgen05, 3 f32-screened f64 (lkm_f64s.cuh) */
 lkm_status lkm_set_assign_path(lkm_ctx* ctx, int path);

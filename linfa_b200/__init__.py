@@ -4,5 +4,6 @@
 arithmetic runs in hand-written sm_100a CUDA kernels behind the C ABI of include/lkm.h.
 """
 from .kmeans import (Context, Dataset, DatasetBase, IncrKMeansError, KMeans, KMeansAlgorithm, KMeansError,  # noqa: F401
-                     KMeansInit, KMeansParams, KMeansParamsError, KMeansValidParams, L2Dist, LkmError, PickMode)
+                     KMeansInit, KMeansParams, KMeansParamsError, KMeansValidParams, L2Dist, LkmError, PickMode, generate,
+                     read_npy, write_npy)
 from .rng import Xoshiro256Plus  # noqa: F401

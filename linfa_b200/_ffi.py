@@ -74,10 +74,12 @@ UNTYPED_SYMBOLS = [
     "lkm_create", "lkm_destroy", "lkm_last_error", "lkm_stream", "lkm_synchronize", "lkm_version",
     "lkm_comm_unique_id", "lkm_comm_init", "lkm_set_shard", "lkm_set_assign_path", "lkm_set_l2_flush", "lkm_set_kernel_timing", "lkm_set_scoring_passes",
     "lkm_set_keep_labels", "lkm_get_labels", "lkm_set_blob_layout",
+    "lkm_write_npy", "lkm_read_npy_header", "lkm_read_npy_data",
 ]
 TYPED_SYMBOLS = [
     "lkm_set_data", "lkm_set_data_device", "lkm_gen_blobs", "lkm_get_data", "lkm_fit", "lkm_init",
     "lkm_lloyd_iters", "lkm_hamerly_iters", "lkm_predict", "lkm_transform", "lkm_assign", "lkm_fit_with",
+    "lkm_silhouette_score",
 ]
 
 _vp, _u64, _i64, _i32 = C.c_void_p, C.c_uint64, C.c_int64, C.c_int
@@ -103,6 +105,9 @@ lib.lkm_set_scoring_passes.argtypes = [_vp, _i32]
 lib.lkm_set_keep_labels.argtypes = [_vp, _i32]
 lib.lkm_get_labels.argtypes = [_vp, C.POINTER(C.c_uint32), _u64]
 lib.lkm_set_blob_layout.argtypes = [_vp, _i32]
+lib.lkm_write_npy.argtypes = [C.c_char_p, _i32, _vp, _i32, _u64p]
+lib.lkm_read_npy_header.argtypes = [C.c_char_p, C.POINTER(C.c_int), C.POINTER(C.c_int), _u64p, _u64p]
+lib.lkm_read_npy_data.argtypes = [C.c_char_p, _u64, _vp, _u64]
 
 for _sfx, _ct in (("f32", C.c_float), ("f64", C.c_double)):
     _fp = C.POINTER(_ct)
@@ -118,6 +123,7 @@ for _sfx, _ct in (("f32", C.c_float), ("f64", C.c_double)):
     getattr(lib, f"lkm_transform_{_sfx}").argtypes = [_vp, _fp, _u64, _fp, _u64, _u64, _i64, _fp]
     getattr(lib, f"lkm_assign_{_sfx}").argtypes = [_vp, _fp, _u64, _fp, _u64, _u64, _i64, _u64p, _fp]
     getattr(lib, f"lkm_fit_with_{_sfx}").argtypes = [_vp, _pp, lkm_rng, _i32, _u64, _u64, _fp, _fp, _fp]
+    getattr(lib, f"lkm_silhouette_score_{_sfx}").argtypes = [_vp, _fp, _u64, _u64, _i64, _u64p, _fp]
 
 
 def sfx_of(dtype):

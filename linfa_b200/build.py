@@ -14,7 +14,7 @@ from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
-SRC = [os.path.join(HERE, "csrc", "lkm_api.cu")]
+SRC = [os.path.join(HERE, "csrc", "lkm_api.cu"), os.path.join(HERE, "csrc", "lkm_extras.cu")]
 DEPS = [os.path.join(HERE, "csrc", f) for f in os.listdir(os.path.join(HERE, "csrc"))] + [
     os.path.join(ROOT, "include", "lkm.h")]
 OUT = os.environ.get("LKM_BUILD_OUT") or os.path.join(HERE, "liblkm.so")
@@ -25,7 +25,7 @@ NVCC_FLAGS = [
     "-lineinfo", "-O3", "-std=c++17",
     "-fmad=true",  # contraction is controlled per operation with the *_rn intrinsics where the reference's order matters
     "-Xcompiler", "-fPIC,-fvisibility=hidden,-O2,-Wall",
-    "-shared", "-cudart", "static",
+    "-shared", "-cudart", "static", "--threads", "2",
     "-Xptxas", "-v" if os.environ.get("LKM_PTXAS_V") else "-O3",
 ]
 

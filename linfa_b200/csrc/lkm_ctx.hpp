@@ -1,6 +1,7 @@
 // Context of the C ABI (include/lkm.h): device buffers, knobs and workspaces shared by the translation units of liblkm.so.
 #pragma once
 #include <cuda_runtime.h>
+#include <dlfcn.h>
 
 #include <cstdint>
 #include <string>

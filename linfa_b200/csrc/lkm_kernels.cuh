@@ -959,7 +959,7 @@ __global__ void bernoulli_select_kernel(const F* __restrict__ dists, unsigned lo
 }
 
 // histogram of labels (integer atomics: exact, order-independent) -> counts as F
-__global__ void label_hist_kernel(const uint32_t* __restrict__ labels, unsigned long long n,
+static __global__ void label_hist_kernel(const uint32_t* __restrict__ labels, unsigned long long n,
                                   unsigned int* __restrict__ hist) {
   for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < n;
        i += (unsigned long long)gridDim.x * blockDim.x)

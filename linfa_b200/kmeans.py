@@ -86,8 +86,67 @@ class DatasetBase:
     def nsamples(self):
         return self.records.shape[0]
 
+    def silhouette_score(self, ctx=None):
+        """SilhouetteScore::silhouette_score (src/metrics_clustering.rs:65-135) of (records, targets) on the GPU; a
+        dataset without targets counts as one cluster (test_empty_labels_as_single_label, :186-192)."""
+        x = np.ascontiguousarray(self.records)
+        sfx, ct = _ffi.sfx_of(x.dtype)
+        n, d = x.shape
+        labels = np.zeros(n, dtype=np.uint64) if self.targets is None else np.ascontiguousarray(self.targets).astype(np.uint64)
+        out = np.zeros(1, dtype=x.dtype)
+        ctx = ctx or Context.default()
+        ctx.check(getattr(_ffi.lib, f"lkm_silhouette_score_{sfx}")(ctx.h, _ffi.fptr(x, ct), n, d, d, labels.ctypes.data_as(_ffi._u64p),
+                                                                   _ffi.fptr(out, ct)))
+        return out[0]
+
 
 Dataset = DatasetBase
+
+NPY_DTYPES = {np.dtype(np.float32): 0, np.dtype(np.float64): 1, np.dtype(np.uint64): 2}
+
+
+def write_npy(path, array):
+    """ndarray_npy::write_npy as the reference's example uses it (examples/kmeans.rs:40-42), through the library's writer."""
+    a = np.ascontiguousarray(array)
+    if a.dtype not in NPY_DTYPES:
+        raise TypeError(f"write_npy: f32, f64 or u64, got {a.dtype}")
+    shape = np.asarray(a.shape, dtype=np.uint64)
+    st = _ffi.lib.lkm_write_npy(str(path).encode(), NPY_DTYPES[a.dtype], a.ctypes.data_as(C.c_void_p), a.ndim,
+                                shape.ctypes.data_as(_ffi._u64p))
+    if st != _ffi.OK:
+        raise LkmError(st, f"write_npy({path}) failed")
+
+
+def read_npy(path):
+    dt, nd, off = C.c_int(), C.c_int(), C.c_uint64()
+    shape = np.zeros(8, dtype=np.uint64)
+    st = _ffi.lib.lkm_read_npy_header(str(path).encode(), C.byref(dt), C.byref(nd), shape.ctypes.data_as(_ffi._u64p), C.byref(off))
+    if st != _ffi.OK:
+        raise LkmError(st, f"read_npy({path}): not a little-endian C-order f32 / f64 / u64 .npy file")
+    dtype = [np.float32, np.float64, np.uint64][dt.value]
+    out = np.empty(tuple(int(v) for v in shape[: nd.value]), dtype=dtype)
+    st = _ffi.lib.lkm_read_npy_data(str(path).encode(), off.value, out.ctypes.data_as(C.c_void_p), out.nbytes)
+    if st != _ffi.OK:
+        raise LkmError(st, f"read_npy({path}): truncated file")
+    return out
+
+
+class generate:
+    """linfa_datasets::generate (datasets/src/generate.rs)."""
+
+    @staticmethod
+    def blobs(blob_size, blob_centroids, rng, ctx=None, sigma=1.0):
+        """generate::blobs (datasets/src/generate.rs:12-46): `blob_size` points around each row of `blob_centroids`
+        (standard normal noise), blob after blob, as an (n_blobs * blob_size) x n_features matrix.  Generated on the GPU by
+        the library's counter-based generator, keyed by one u64 drawn from `rng`; the layout and the distribution are the
+        reference's, the random stream is not (rand_distr's ziggurat tables are not restated: data is an INPUT of the path)."""
+        c = np.ascontiguousarray(blob_centroids)
+        if c.dtype not in (np.float32, np.float64):
+            c = c.astype(np.float64)
+        ctx = ctx or Context.default()
+        n = int(blob_size) * c.shape[0]
+        ctx.gen_blobs(n, c.shape[1], c, sigma, seed=int(rng.next_u64()))
+        return ctx.get_data(0, n)
 
 
 class KMeansInit:

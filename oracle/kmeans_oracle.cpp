@@ -781,6 +781,47 @@ int fit_hamerly(const F* X, uint64_t n, uint64_t d, uint64_t k, uint64_t n_runs,
   return 0;
 }
 
+// ---------------------------------------------------------------------------
+// SilhouetteScore::silhouette_score (src/metrics_clustering.rs:65-135), labels as u64
+// ---------------------------------------------------------------------------
+template <class F> F silhouette_score(const F* X, uint64_t n, uint64_t d, const uint64_t* labels, F* per_sample) {
+  // label_count: distinct labels with their counts
+  std::vector<uint64_t> uniq(labels, labels + n);
+  std::sort(uniq.begin(), uniq.end());
+  uniq.erase(std::unique(uniq.begin(), uniq.end()), uniq.end());
+  const size_t L = uniq.size();
+  if (L == 1) return (F)1;   // :77-80
+  std::vector<uint64_t> id(n), count(L, 0);
+  for (uint64_t i = 0; i < n; ++i) {
+    id[i] = (uint64_t)(std::lower_bound(uniq.begin(), uniq.end(), labels[i]) - uniq.begin());
+    count[id[i]] += 1;
+  }
+  std::vector<F> total(L, (F)0), diff(d);
+  F score = (F)0;
+  for (uint64_t i = 0; i < n; ++i) {
+    for (uint64_t j = 0; j < n; ++j) {
+      // add_point (:61-63): eval_sample.sub(&other_sample).mapv(|x| x * x).sum().sqrt(); sum() = ndarray's unrolled fold
+      for (uint64_t f = 0; f < d; ++f) { const F v = X[i * d + f] - X[j * d + f]; diff[f] = v * v; }
+      total[id[j]] = total[id[j]] + std::sqrt(ndarray_sum<F>(diff.data(), d));
+    }
+    F a_x = (F)0, b_x = (F)0;
+    bool have_b = false;
+    for (size_t l = 0; l < L; ++l) {
+      if (l == id[i]) a_x = count[l] == 1 ? (F)0 : total[l] / (F)(count[l] - 1);
+      else {
+        const F m = total[l] / (F)count[l];
+        if (!have_b || m < b_x) b_x = m;
+        have_b = true;
+      }
+      total[l] = (F)0;
+    }
+    const F s = a_x >= b_x ? (b_x - a_x) / a_x : (b_x - a_x) / b_x;
+    if (per_sample) per_sample[i] = s;
+    score = score + s;
+  }
+  return score / (F)n;
+}
+
 // FitWith::fit_with (KM/algorithm.rs:635-715), one mini-batch step.
 // model_in: has_model != 0 -> (C_inout, counts_inout) hold the previous model.
 // returns 0 converged (Ok), 20 NotConverged (model still written), else error.
@@ -965,6 +1006,9 @@ ORC_EXPORT int orc_index_sample(uint64_t* state, uint64_t length, uint64_t amoun
   }                                                                                                                   \
   ORC_EXPORT F orc_compute_inertia_##SFX(const F* X, uint64_t n, uint64_t d, const uint64_t* labels, const F* C) {   \
     return compute_inertia<F, F>(X, n, d, labels, C);                                                                 \
+  }                                                                                                                   \
+  ORC_EXPORT F orc_silhouette_##SFX(const F* X, uint64_t n, uint64_t d, const uint64_t* labels, F* per_sample) {     \
+    return silhouette_score<F>(X, n, d, labels, per_sample);                                                         \
   }                                                                                                                   \
   ORC_EXPORT int orc_fit_with_##SFX(const F* X, uint64_t n, uint64_t d, uint64_t k, uint64_t n_runs, F tol,          \
                                     int method, const F* precomputed, const uint64_t* state, int has_model,          \

@@ -101,6 +101,7 @@ class Oracle:
             sig("two_closest", None, [fp, u64, u64, fp, _u64p, fp, fp])
             sig("two_farthest", None, [fp, u64, _u64p, _u64p])
             sig("compute_inertia", ct, [fp, u64, u64, _u64p, fp])
+            sig("silhouette", ct, [fp, u64, u64, _u64p, fp])
         self.threads = max(1, int(L.orc_hardware_threads()))
 
     # -- helpers -----------------------------------------------------------
@@ -288,6 +289,12 @@ class Oracle:
         lab = np.ascontiguousarray(labels, dtype=np.uint64)
         sfx, ct = self._sfx(X.dtype)
         return self._fn("compute_inertia", sfx)(_ptr(X, ct), X.shape[0], X.shape[1], _ptr(lab, C.c_uint64), _ptr(Cn, ct))
+
+    def silhouette(self, X, labels):
+        X = np.ascontiguousarray(X)
+        lab = np.ascontiguousarray(labels).astype(np.uint64)
+        sfx, ct = self._sfx(X.dtype)
+        return self._fn("silhouette", sfx)(_ptr(X, ct), X.shape[0], X.shape[1], _ptr(lab, C.c_uint64), None)
 
     def fit_with(self, X, k, rng, model=None, n_runs=10, tol=1e-4, method=INIT_KMEANSPP, precomputed=None,
                  threads=None, rayon_threads=1):

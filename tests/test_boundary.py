@@ -43,7 +43,7 @@ def test_struct_layouts_match_header(lb):
 
     assert C.sizeof(_ffi.lkm_params) == 72
     assert C.sizeof(_ffi.lkm_rng) == 24
-    assert C.sizeof(_ffi.lkm_stats) == 56
+    assert C.sizeof(_ffi.lkm_stats) == 72
 
 
 def test_no_device_fails_loudly(lb):
