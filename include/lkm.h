@@ -104,7 +104,7 @@ typedef struct lkm_stats {
   double inertia_total;      /* sum of min squared distances of the last assignment */
   float device_ms;           /* CUDA-event time of the iteration loop on the context stream */
   uint32_t kernel_launches;  /* kernels this library launched in the call */
-  uint32_t assign_path;      /* 0 exact CUDA-core, 1 certified FMA, 2 tcgen05 3xTF32, 3 f32-screened f64 (small d) */
+  uint32_t assign_path;      /* 0 exact CUDA-core, 1 certified FMA, 2 tcgen05 3xTF32, 3 f32-screened f64 (small d), 4 f64 DMMA */
   uint64_t fallback_rows;    /* rows re-evaluated in exact form by the certified paths */
   float main_kernel_ms;      /* with lkm_set_l2_flush: summed duration of the assign/fused kernel alone */
   uint32_t reserved;
@@ -241,7 +241,8 @@ lkm_status lkm_read_npy_header(const char* path, int* dtype_out, int* ndim_out, 
 lkm_status lkm_read_npy_data(const char* path, uint64_t data_offset, void* out, uint64_t bytes);
 
 /* -- knobs that are not in the reference (all have defaults) --------------- */
-/* force an assignment path: -1 auto (default), 0 exact, 1 certified FMA, 2 tcgen05, 3 f32-screened f64 (lkm_f64s.cuh) */
+/* force an assignment path: -1 auto (default), 0 exact, 1 certified FMA, 2 tcgen05, 3 f32-screened f64 (lkm_f64s.cuh),
+ * 4 f64 scores on the FP64 tensor pipe (DMMA, lkm_dmma.cuh) */
 lkm_status lkm_set_assign_path(lkm_ctx* ctx, int path);
 /* parity-test aid: when on, every Lloyd kernel also writes the label each row was accumulated under in the LAST
  * executed iteration (the `memberships` array of KM/algorithm.rs:304,316-322, which the fused kernels otherwise never

@@ -85,6 +85,7 @@ struct lkm_ctx {
   int f64s_rpt = 2;      // LKM_F64S_RPT=1: one row per lane (32-row tiles, 3 CTAs / SM)
   int pair32 = 0;        // LKM_PAIR32=1: d = 32, k <= 64 through the CTA-pair screening kernel instead of the pipeline kernel
   int tc5_fuse = 1;      // LKM_TC5_FUSE=0: screening kernel without the fused update of uniform tiles
+  int dmma_enabled = 1;  // LKM_DMMA=0: f64 shapes with a large contraction stay on the CUDA-core kernels
   int tc5_enabled = 1;   // LKM_TC5=0: tc_assign_kernel instead of the CTA-pair assignment kernel
   double tc5_rescan_limit = 0.08;   // LKM_TC5_RESCAN_LIMIT: share of listed rows above which the pair kernel moves to 3xTF32
   int tc5_defer = 1;     // LKM_TC5_DEFER=0: undecided rows are scanned inline by the pair kernel instead of by rows_top2_kernel

@@ -76,6 +76,10 @@ ROW_CASES = [
     ("f64s shuffled, overlap", 70001, 8, 13, 13, np.float64, 3.0, True, 3, 3, 0),
     ("f64s d = 2", 33000, 2, 3, 3, np.float64, 10.0, False, 3, 3, 0),
     ("f64s d = 16, k = 32", 40000, 16, 32, 32, np.float64, 30.0, True, 3, 3, 0),
+    ("DMMA f64 d = 64, k = 256", 30000, 64, 256, 256, np.float64, 30.0, True, -1, 4, 0),
+    ("DMMA f64 d = 128, k = 100, overlap", 20000, 128, 100, 20, np.float64, 2.0, True, -1, 4, 0),
+    ("DMMA f64 d = 8, k = 200 (ragged)", 12345, 8, 200, 50, np.float64, 5.0, True, 4, 4, 0),
+    ("DMMA f64 d = 20, k = 70, blob order", 9001, 20, 70, 70, np.float64, 30.0, False, 4, 4, 0),
     ("certified FMA f32 d = 16", 30000, 16, 24, 24, np.float32, 30.0, True, 1, 1, 0),
     ("certified FMA f64 d = 8", 30000, 8, 40, 10, np.float64, 2.0, True, 1, 1, 0),
     ("exact CUDA-core, odd d", 20000, 20, 12, 12, np.float32, 30.0, True, 0, 0, 0),
