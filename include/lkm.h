@@ -231,6 +231,50 @@ lkm_status lkm_silhouette_score_f32(lkm_ctx* ctx, const float* x, uint64_t n, ui
 lkm_status lkm_silhouette_score_f64(lkm_ctx* ctx, const double* x, uint64_t n, uint64_t d, int64_t row_stride,
                                     const uint64_t* labels, double* score_out);
 
+/* -- GaussianMixtureModel, full covariances (algorithms/linfa-clustering/src/gaussian_mixture/algorithm.rs): the
+ * first caller of the K-Means path inside the reference (GmmInitMethod::KMeans, :137-146).  Fit::fit (:411-467) on the
+ * resident matrix: initial responsibilities from a K-Means fit (KMeans::params_with_rng(k, rng) with its defaults,
+ * then predict) or random, then EM — E-step (:291-298, 339-352) and M-step (:300-322) on the device, the k Cholesky
+ * factorizations (:261-276) on the host.  Defaults (gaussian_mixture/hyperparams.rs:88-101): tolerance 1e-3,
+ * reg_covariance 1e-6, n_runs 1, max_n_iterations 100, init KMeans.  Status codes 40..48 mirror GmmError. */
+typedef struct lkm_gmm_params {
+  uint64_t n_clusters;
+  double tolerance;
+  double reg_covariance;
+  uint64_t n_runs;
+  uint64_t max_n_iterations;
+  int32_t init_method;        /* 0 = GmmInitMethod::KMeans, 1 = GmmInitMethod::Random */
+  int32_t kmeans_pick_mode;   /* lkm_pick_mode of the K-Means initialisation (default EXACT = 0) */
+} lkm_gmm_params;
+enum {
+  LKM_GMM_ERR_N_CLUSTERS = 40,      /* GmmError::InvalidValue, in the order of check_ref (hyperparams.rs:167-193) */
+  LKM_GMM_ERR_TOLERANCE = 41,
+  LKM_GMM_ERR_REG_COVARIANCE = 42,
+  LKM_GMM_ERR_N_RUNS = 43,
+  LKM_GMM_ERR_MAX_ITERATIONS = 44,
+  LKM_GMM_ERR_EMPTY_CLUSTER = 45,   /* GmmError::EmptyCluster (algorithm.rs:224-229) */
+  LKM_GMM_ERR_NOT_POSITIVE_DEFINITE = 46,   /* GmmError::LinalgError(NotPositiveDefinite) */
+  LKM_GMM_ERR_NOT_CONVERGED = 47,   /* GmmError::NotConverged (algorithm.rs:459-465) */
+  LKM_GMM_ERR_LOWER_BOUND = 48      /* GmmError::LowerBoundError */
+};
+/* outputs: weights k, means k x d, covariances / precisions / precisions_chol k x d x d; n_iter_out = the iteration at
+ * which the best run converged, lower_bound_out = its mean log-likelihood (both may be NULL) */
+lkm_status lkm_gmm_fit_f32(lkm_ctx* ctx, const lkm_gmm_params* p, lkm_rng rng, float* weights_out, float* means_out,
+                           float* covariances_out, float* precisions_out, float* precisions_chol_out, uint64_t* n_iter_out,
+                           float* lower_bound_out);
+lkm_status lkm_gmm_fit_f64(lkm_ctx* ctx, const lkm_gmm_params* p, lkm_rng rng, double* weights_out, double* means_out,
+                           double* covariances_out, double* precisions_out, double* precisions_chol_out, uint64_t* n_iter_out,
+                           double* lower_bound_out);
+/* estimate_log_prob_resp (:339-352) for a given model: labels_out = argmax of the responsibilities (PredictInplace,
+ * :470-484), proba_out = n x k responsibilities (predict_proba, :205-208), log_prob_norm_mean_out = the E-step's lower
+ * bound; any of the three may be NULL.  x == NULL: the resident matrix. */
+lkm_status lkm_gmm_predict_f32(lkm_ctx* ctx, uint64_t k, const float* weights, const float* means, const float* precisions_chol,
+                               const float* x, uint64_t n, uint64_t d, int64_t row_stride, uint64_t* labels_out,
+                               float* proba_out, float* log_prob_norm_mean_out);
+lkm_status lkm_gmm_predict_f64(lkm_ctx* ctx, uint64_t k, const double* weights, const double* means, const double* precisions_chol,
+                               const double* x, uint64_t n, uint64_t d, int64_t row_stride, uint64_t* labels_out,
+                               double* proba_out, double* log_prob_norm_mean_out);
+
 /* -- .npy files: ndarray_npy::write_npy as used by the reference's example
  * (algorithms/linfa-clustering/examples/kmeans.rs:40-42: the records and the
  * memberships as u64).  Format 1.0, little endian, C order.  dtype: 0 = f32

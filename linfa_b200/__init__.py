@@ -7,3 +7,4 @@ from .kmeans import (Context, Dataset, DatasetBase, IncrKMeansError, KMeans, KMe
                      KMeansInit, KMeansParams, KMeansParamsError, KMeansValidParams, L2Dist, LkmError, PickMode, generate,
                      read_npy, write_npy)
 from .rng import Xoshiro256Plus  # noqa: F401
+from .gmm import GaussianMixtureModel, GmmCovarType, GmmError, GmmInitMethod, GmmParams  # noqa: F401,E402

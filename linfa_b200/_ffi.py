@@ -44,6 +44,18 @@ class lkm_params(C.Structure):
     ]
 
 
+class lkm_gmm_params(C.Structure):
+    _fields_ = [
+        ("n_clusters", C.c_uint64),
+        ("tolerance", C.c_double),
+        ("reg_covariance", C.c_double),
+        ("n_runs", C.c_uint64),
+        ("max_n_iterations", C.c_uint64),
+        ("init_method", C.c_int32),
+        ("kmeans_pick_mode", C.c_int32),
+    ]
+
+
 class lkm_stats(C.Structure):
     _fields_ = [
         ("n_iter", C.c_uint64),
@@ -79,7 +91,7 @@ UNTYPED_SYMBOLS = [
 TYPED_SYMBOLS = [
     "lkm_set_data", "lkm_set_data_device", "lkm_gen_blobs", "lkm_get_data", "lkm_fit", "lkm_init",
     "lkm_lloyd_iters", "lkm_hamerly_iters", "lkm_predict", "lkm_transform", "lkm_assign", "lkm_fit_with",
-    "lkm_silhouette_score",
+    "lkm_silhouette_score", "lkm_gmm_fit", "lkm_gmm_predict",
 ]
 
 _vp, _u64, _i64, _i32 = C.c_void_p, C.c_uint64, C.c_int64, C.c_int
@@ -124,6 +136,8 @@ for _sfx, _ct in (("f32", C.c_float), ("f64", C.c_double)):
     getattr(lib, f"lkm_assign_{_sfx}").argtypes = [_vp, _fp, _u64, _fp, _u64, _u64, _i64, _u64p, _fp]
     getattr(lib, f"lkm_fit_with_{_sfx}").argtypes = [_vp, _pp, lkm_rng, _i32, _u64, _u64, _fp, _fp, _fp]
     getattr(lib, f"lkm_silhouette_score_{_sfx}").argtypes = [_vp, _fp, _u64, _u64, _i64, _u64p, _fp]
+    getattr(lib, f"lkm_gmm_fit_{_sfx}").argtypes = [_vp, C.POINTER(lkm_gmm_params), lkm_rng, _fp, _fp, _fp, _fp, _fp, _u64p, _fp]
+    getattr(lib, f"lkm_gmm_predict_{_sfx}").argtypes = [_vp, _u64, _fp, _fp, _fp, _fp, _u64, _u64, _i64, _u64p, _fp, _fp]
 
 
 def sfx_of(dtype):

@@ -11,6 +11,8 @@
 
 #include "lkm_ctx.hpp"
 #include "lkm_metrics.cuh"
+#include "lkm_gmm.cuh"
+#include "lkm_rand.hpp"
 
 #define LKM_EXPORT extern "C" __attribute__((visibility("default")))
 
@@ -79,6 +81,307 @@ static lkm_status silhouette_impl(lkm_ctx* ctx, const F* x, uint64_t n, uint64_t
   return st;
 }
 
+// ---- Gaussian mixture (gaussian_mixture/algorithm.rs) ---------------------------------------------
+template <typename F> struct GmmModel {
+  uint64_t k = 0, d = 0;
+  std::vector<F> weights, means, covariances, precisions, precisions_chol;
+};
+
+struct GmmWork {
+  DevBuf means, pchol, logdet, logw, log_resp, part, comb, lpn_part, resp0;
+  void release() { for (DevBuf* b : {&means, &pchol, &logdet, &logw, &log_resp, &part, &comb, &lpn_part, &resp0}) b->release(); }
+};
+
+// compute_precisions_cholesky_full (:261-276): L = cholesky(cov) (lower), P_chol = (L^-1)^T; false = not positive definite
+template <typename F>
+static bool gmm_precisions_chol(const F* cov, uint64_t d, F* pchol) {
+  std::vector<F> L(d * d, (F)0), inv(d * d, (F)0);
+  for (uint64_t j = 0; j < d; ++j) {
+    F s = cov[j * d + j];
+    for (uint64_t p = 0; p < j; ++p) s -= L[j * d + p] * L[j * d + p];
+    if (!(s > (F)0)) return false;   // LinalgError::NotPositiveDefinite
+    const F ljj = std::sqrt(s);
+    L[j * d + j] = ljj;
+    for (uint64_t i = j + 1; i < d; ++i) {
+      F v = cov[i * d + j];
+      for (uint64_t p = 0; p < j; ++p) v -= L[i * d + p] * L[j * d + p];
+      L[i * d + j] = v / ljj;
+    }
+  }
+  // solve L * inv = I by forward substitution, column by column
+  for (uint64_t c = 0; c < d; ++c)
+    for (uint64_t i = 0; i < d; ++i) {
+      F v = (i == c) ? (F)1 : (F)0;
+      for (uint64_t p = 0; p < i; ++p) v -= L[i * d + p] * inv[p * d + c];
+      inv[i * d + c] = v / L[i * d + i];
+    }
+  for (uint64_t i = 0; i < d; ++i)
+    for (uint64_t j = 0; j < d; ++j) pchol[i * d + j] = inv[j * d + i];
+  return true;
+}
+
+// compute_precisions_full (:278-289): P_chol . P_chol^T
+template <typename F> static void gmm_precisions(const F* pchol, uint64_t d, F* prec) {
+  for (uint64_t i = 0; i < d; ++i)
+    for (uint64_t j = 0; j < d; ++j) {
+      F s = (F)0;
+      for (uint64_t p = 0; p < d; ++p) s += pchol[i * d + p] * pchol[j * d + p];
+      prec[i * d + j] = s;
+    }
+}
+
+template <typename F>
+static lkm_status gmm_upload_model(lkm_ctx* ctx, GmmWork& w, const GmmModel<F>& m) {
+  const uint64_t k = m.k, d = m.d;
+  std::vector<F> logdet(k), logw(k);
+  for (uint64_t c = 0; c < k; ++c) {
+    F s = (F)0;   // compute_log_det_cholesky_full (:392-405)
+    for (uint64_t i = 0; i < d; ++i) s += std::log(m.precisions_chol[c * d * d + i * d + i]);
+    logdet[c] = s;
+    logw[c] = std::log(m.weights[c]);   // estimate_log_weights (:407-409)
+  }
+  CK(w.means.ensure(k * d * sizeof(F)));
+  CK(w.pchol.ensure(k * d * d * sizeof(F)));
+  CK(w.logdet.ensure(k * sizeof(F)));
+  CK(w.logw.ensure(k * sizeof(F)));
+  CK(cudaMemcpyAsync(w.means.p, m.means.data(), k * d * sizeof(F), cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(w.pchol.p, m.precisions_chol.data(), k * d * d * sizeof(F), cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(w.logdet.p, logdet.data(), k * sizeof(F), cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(w.logw.p, logw.data(), k * sizeof(F), cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));   // the host vectors go out of scope
+  return LKM_OK;
+}
+
+// e_step (:291-298) on a device matrix: mean of log_prob_norm; log_resp stays in w.log_resp
+template <typename F>
+static lkm_status gmm_e_step(lkm_ctx* ctx, GmmWork& w, const F* dX, uint64_t n, uint64_t d, uint64_t k, F* lower_bound,
+                             uint32_t* d_labels, F* d_proba) {
+  CK(w.log_resp.ensure(std::max<uint64_t>(n * k, 1) * sizeof(F)));
+  const int grid = (int)std::max<uint64_t>(1, std::min<uint64_t>((n + kGmmThreads - 1) / kGmmThreads, (uint64_t)ctx->sm_count * 4));
+  CK(w.lpn_part.ensure((size_t)grid * 8));
+  GmmEArgs<F> a{};
+  a.X = dX; a.n = n; a.d = (int)d; a.k = (int)k; a.means = w.means.as<F>(); a.pchol = w.pchol.as<F>(); a.log_det = w.logdet.as<F>();
+  a.log_w = w.logw.as<F>(); a.log_resp = w.log_resp.as<F>(); a.part_lpn = w.lpn_part.as<double>(); a.labels = d_labels; a.proba = d_proba;
+  const size_t tile = (size_t)kGmmThreads * (d | 1) * sizeof(F), par = (k * d + k * d * d) * sizeof(F);
+  if (tile + 1024 > ctx->smem_optin) return fail(ctx, LKM_ERR_UNSUPPORTED, "row too wide for the E-step tile");
+  a.params_in_smem = tile + par + 2048 <= ctx->smem_optin ? 1 : 0;
+  const size_t smem = tile + (a.params_in_smem ? par : 0);
+  CK(cudaFuncSetAttribute(gmm_e_step_kernel<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  gmm_e_step_kernel<F><<<grid, kGmmThreads, smem, ctx->stream>>>(a);
+  CK(cudaGetLastError());
+  ctx->launches++;
+  std::vector<double> part(grid);
+  CK(cudaMemcpyAsync(part.data(), w.lpn_part.p, (size_t)grid * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  double tot = 0.0;
+  for (int b = 0; b < grid; ++b) tot += part[b];
+  if (lower_bound) *lower_bound = (F)(tot / (double)n);   // log_prob_norm.mean()
+  return LKM_OK;
+}
+
+// estimate_gaussian_parameters (:217-259) from the responsibilities in `resp` (log_resp when is_log), then
+// compute_precisions_cholesky_full; statuses: 45 EmptyCluster, 46 NotPositiveDefinite
+template <typename F>
+static lkm_status gmm_m_step(lkm_ctx* ctx, GmmWork& w, const F* dX, uint64_t n, uint64_t d, uint64_t k, const F* d_resp, int is_log,
+                             F reg_covar, GmmModel<F>& m) {
+  const int grid = (int)std::max<uint64_t>(1, std::min<uint64_t>((n + 255) / 256, (uint64_t)ctx->sm_count));
+  const uint64_t rows_per = (n + grid - 1) / grid;
+  const size_t smem = (size_t)kGmmTile * (d + k) * sizeof(F);
+  if (smem > ctx->smem_optin) return fail(ctx, LKM_ERR_UNSUPPORTED, "too many components / features for the M-step tile");
+  CK(cudaFuncSetAttribute(gmm_moments_kernel<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int E0 = (int)(k + k * d), E1 = (int)(k * d * d);
+  CK(w.part.ensure((size_t)grid * std::max(E0, E1) * 8));
+  CK(w.comb.ensure((size_t)std::max(E0, E1) * 8));
+  GmmMArgs<F> a{};
+  a.X = dX; a.n = n; a.d = (int)d; a.k = (int)k; a.log_resp = d_resp; a.resp_is_log = is_log; a.part = w.part.as<double>();
+  a.rows_per_cta = rows_per; a.mode = 0;
+  gmm_moments_kernel<F><<<grid, 256, smem, ctx->stream>>>(a);
+  gmm_combine_kernel<<<(E0 + 255) / 256, 256, 0, ctx->stream>>>(w.part.as<double>(), grid, E0, w.comb.as<double>());
+  CK(cudaGetLastError());
+  ctx->launches += 2;
+  std::vector<double> h0(E0);
+  CK(cudaMemcpyAsync(h0.data(), w.comb.p, (size_t)E0 * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  // nk.min() < 10 eps -> EmptyCluster (:224-229)
+  std::vector<F> nk(k);
+  for (uint64_t c = 0; c < k; ++c) nk[c] = (F)h0[c];
+  for (uint64_t c = 0; c < k; ++c)
+    if (!(nk[c] >= (F)10 * std::numeric_limits<F>::epsilon())) {
+      ctx->err = "Cluster #" + std::to_string(c + 1) + " has no more point. Consider decreasing number of clusters or change initialization.";
+      return (lkm_status)45;
+    }
+  for (uint64_t c = 0; c < k; ++c)
+    for (uint64_t j = 0; j < d; ++j) m.means[c * d + j] = (F)h0[k + c * d + j] / nk[c];
+  CK(w.means.ensure(k * d * sizeof(F)));
+  CK(cudaMemcpyAsync(w.means.p, m.means.data(), k * d * sizeof(F), cudaMemcpyHostToDevice, ctx->stream));
+  a.mode = 1; a.means = w.means.as<F>();
+  gmm_moments_kernel<F><<<grid, 256, smem, ctx->stream>>>(a);
+  gmm_combine_kernel<<<(E1 + 255) / 256, 256, 0, ctx->stream>>>(w.part.as<double>(), grid, E1, w.comb.as<double>());
+  CK(cudaGetLastError());
+  ctx->launches += 2;
+  std::vector<double> h1(E1);
+  CK(cudaMemcpyAsync(h1.data(), w.comb.p, (size_t)E1 * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  for (uint64_t c = 0; c < k; ++c) {
+    for (uint64_t e = 0; e < d * d; ++e) m.covariances[c * d * d + e] = (F)h1[c * d * d + e] / nk[c];
+    for (uint64_t i = 0; i < d; ++i) m.covariances[c * d * d + i * d + i] += reg_covar;   // cov_k.diag_mut() + reg_covar (:254)
+    m.weights[c] = nk[c] / (F)n;
+    if (!gmm_precisions_chol<F>(&m.covariances[c * d * d], d, &m.precisions_chol[c * d * d])) {
+      ctx->err = "Matrix is not positive definite";
+      return (lkm_status)46;
+    }
+  }
+  return LKM_OK;
+}
+
+template <typename F>
+static lkm_status gmm_fit_impl(lkm_ctx* ctx, const lkm_gmm_params* p, lkm_rng rng_in, F* weights_out, F* means_out, F* cov_out,
+                               F* prec_out, F* pchol_out, uint64_t* n_iter_out, F* lower_bound_out) {
+  if (!p || !weights_out || !means_out || !cov_out || !prec_out || !pchol_out) return fail(ctx, LKM_ERR_INVALID_ARG, "null argument");
+  // ParamGuard::check_ref (gaussian_mixture/hyperparams.rs:167-193), same order
+  if (p->n_clusters == 0) return fail(ctx, (lkm_status)40, "`n_clusters` cannot be 0!");
+  if (p->tolerance <= 0.0) return fail(ctx, (lkm_status)41, "`tolerance` must be greater than 0!");
+  if (p->reg_covariance < 0.0) return fail(ctx, (lkm_status)42, "`reg_covar` must be positive!");
+  if (p->n_runs == 0) return fail(ctx, (lkm_status)43, "`n_runs` cannot be 0!");
+  if (p->max_n_iterations == 0) return fail(ctx, (lkm_status)44, "`max_n_iterations` cannot be 0!");
+  if (ctx->elem != (int)sizeof(F) || !ctx->X) return fail(ctx, LKM_ERR_NO_DATA, "no resident data of this type");
+  if (ctx->world > 1) return fail(ctx, LKM_ERR_UNSUPPORTED, "the Gaussian mixture runs on one GPU");
+  CK(cudaSetDevice(ctx->device));
+  const uint64_t n = ctx->n, d = ctx->d, k = p->n_clusters;
+  const F* dX = reinterpret_cast<const F*>(ctx->X);
+  const F tol = (F)p->tolerance, reg = (F)p->reg_covariance;
+  GmmWork w;
+  GmmModel<F> m;
+  m.k = k; m.d = d;
+  m.weights.assign(k, 0); m.means.assign(k * d, 0); m.covariances.assign(k * d * d, 0); m.precisions.assign(k * d * d, 0);
+  m.precisions_chol.assign(k * d * d, 0);
+  GmmModel<F> best;
+  auto body = [&]() -> lkm_status {
+    // ---- GaussianMixtureModel::new (:124-178): initial responsibilities ----
+    CK(w.resp0.ensure(std::max<uint64_t>(n * k, 1) * sizeof(F)));
+    std::vector<F> resp(n * k, (F)0);
+    if (p->init_method == 0) {
+      // KMeans::params_with_rng(k, rng).check().unwrap().fit(dataset)?, then model.predict (:137-146)
+      lkm_params kp{};
+      kp.n_clusters = k; kp.n_runs = 10; kp.max_n_iterations = 300; kp.tolerance = 1e-4;
+      kp.init_method = LKM_INIT_KMEANS_PLUSPLUS; kp.algorithm = LKM_ALGO_LLOYD; kp.pick_mode = p->kmeans_pick_mode;
+      std::vector<F> cen(k * d), cnt(k);
+      F inertia = 0;
+      lkm_status st;
+      std::vector<uint64_t> labels(n);
+      if constexpr (sizeof(F) == 4) {
+        st = lkm_fit_f32(ctx, &kp, rng_in, cen.data(), cnt.data(), &inertia, nullptr);
+        if (st == LKM_OK) st = lkm_predict_f32(ctx, cen.data(), k, nullptr, n, d, (int64_t)d, labels.data());
+      } else {
+        st = lkm_fit_f64(ctx, &kp, rng_in, cen.data(), cnt.data(), &inertia, nullptr);
+        if (st == LKM_OK) st = lkm_predict_f64(ctx, cen.data(), k, nullptr, n, d, (int64_t)d, labels.data());
+      }
+      if (st != LKM_OK) return st;
+      for (uint64_t i = 0; i < n; ++i) resp[i * k + labels[i]] = (F)1;
+    } else {
+      // Array2::<f64>::random_using((n, k), Uniform::new(0., 1.), &mut rng), rows normalised by their sums (:148-157)
+      HostRng rng{rng_in};
+      std::vector<double> r(n * k);
+      for (uint64_t e = 0; e < n * k; ++e) r[e] = unit_f64(rng);
+      for (uint64_t i = 0; i < n; ++i) {
+        double tot = 0.0;
+        for (uint64_t c = 0; c < k; ++c) tot += r[i * k + c];
+        for (uint64_t c = 0; c < k; ++c) resp[i * k + c] = (F)(r[i * k + c] / tot);
+      }
+    }
+    CK(cudaMemcpyAsync(w.resp0.p, resp.data(), n * k * sizeof(F), cudaMemcpyHostToDevice, ctx->stream));
+    CKS(gmm_m_step<F>(ctx, w, dX, n, d, k, w.resp0.as<F>(), 0, reg, m));
+    for (uint64_t c = 0; c < k; ++c) gmm_precisions<F>(&m.precisions_chol[c * d * d], d, &m.precisions[c * d * d]);
+    // ---- Fit::fit (:411-467): every run continues from the same model, as in the reference ----
+    F max_lower_bound = -std::numeric_limits<F>::infinity();
+    bool have_best = false, best_converged = false;
+    uint64_t best_iter = 0;
+    for (uint64_t run = 0; run < p->n_runs; ++run) {
+      F lower_bound = -std::numeric_limits<F>::infinity();
+      bool converged = false;
+      uint64_t conv_iter = 0;
+      for (uint64_t it = 0; it < p->max_n_iterations; ++it) {
+        const F prev = lower_bound;
+        CKS(gmm_upload_model<F>(ctx, w, m));
+        F lb = 0;
+        CKS(gmm_e_step<F>(ctx, w, dX, n, d, k, &lb, nullptr, nullptr));
+        CKS(gmm_m_step<F>(ctx, w, dX, n, d, k, w.log_resp.as<F>(), 1, reg, m));
+        lower_bound = lb;
+        const F change = lower_bound - prev;
+        if (std::fabs(change) < tol) { converged = true; conv_iter = it; break; }
+      }
+      if (lower_bound > max_lower_bound) {
+        max_lower_bound = lower_bound;
+        for (uint64_t c = 0; c < k; ++c) gmm_precisions<F>(&m.precisions_chol[c * d * d], d, &m.precisions[c * d * d]);   // refresh_precisions_full
+        best = m;
+        have_best = true;
+        best_converged = converged;
+        best_iter = conv_iter;
+      }
+    }
+    if (!best_converged) return fail(ctx, (lkm_status)47, "EM fitting algorithm did not converge. Try different init parameters, or increase max_n_iterations, tolerance or check for degenerate data.");
+    if (!have_best) return fail(ctx, (lkm_status)48, "No lower bound improvement (-inf)");
+    if (n_iter_out) *n_iter_out = best_iter;
+    if (lower_bound_out) *lower_bound_out = max_lower_bound;
+    return LKM_OK;
+  };
+  const lkm_status st = body();
+  w.release();
+  if (st != LKM_OK) return st;
+  std::memcpy(weights_out, best.weights.data(), k * sizeof(F));
+  std::memcpy(means_out, best.means.data(), k * d * sizeof(F));
+  std::memcpy(cov_out, best.covariances.data(), k * d * d * sizeof(F));
+  std::memcpy(prec_out, best.precisions.data(), k * d * d * sizeof(F));
+  std::memcpy(pchol_out, best.precisions_chol.data(), k * d * d * sizeof(F));
+  return LKM_OK;
+}
+
+// estimate_log_prob_resp on host observations with a given model: predict (:470-484), predict_proba (:205-208), e_step
+template <typename F>
+static lkm_status gmm_predict_impl(lkm_ctx* ctx, uint64_t k, const F* weights, const F* means, const F* pchol, const F* x, uint64_t n,
+                                   uint64_t d, int64_t row_stride, uint64_t* labels_out, F* proba_out, F* log_prob_norm_mean_out) {
+  if (!weights || !means || !pchol || k == 0) return fail(ctx, LKM_ERR_INVALID_ARG, "null argument");
+  if (n == 0 || d == 0) return fail(ctx, LKM_ERR_SHAPE, "empty dataset");
+  CK(cudaSetDevice(ctx->device));
+  GmmWork w;
+  DevBuf dx, dlab, dproba;
+  auto body = [&]() -> lkm_status {
+    const F* dX = nullptr;
+    if (x == nullptr) {
+      if (ctx->elem != (int)sizeof(F) || !ctx->X || ctx->n != n || ctx->d != d) return fail(ctx, LKM_ERR_NO_DATA, "no resident data of this shape");
+      dX = reinterpret_cast<const F*>(ctx->X);
+    } else {
+      if (row_stride < (int64_t)d) return fail(ctx, LKM_ERR_INVALID_ARG, "row stride smaller than the row");
+      CK(dx.ensure(n * d * sizeof(F)));
+      CK(cudaMemcpy2DAsync(dx.p, d * sizeof(F), x, (size_t)row_stride * sizeof(F), d * sizeof(F), n, cudaMemcpyHostToDevice, ctx->stream));
+      dX = dx.as<F>();
+    }
+    GmmModel<F> m;
+    m.k = k; m.d = d;
+    m.weights.assign(weights, weights + k); m.means.assign(means, means + k * d); m.precisions_chol.assign(pchol, pchol + k * d * d);
+    CKS(gmm_upload_model<F>(ctx, w, m));
+    if (labels_out) CK(dlab.ensure(n * 4));
+    if (proba_out) CK(dproba.ensure(n * k * sizeof(F)));
+    F lb = 0;
+    CKS(gmm_e_step<F>(ctx, w, dX, n, d, k, &lb, labels_out ? dlab.as<uint32_t>() : nullptr, proba_out ? dproba.as<F>() : nullptr));
+    if (log_prob_norm_mean_out) *log_prob_norm_mean_out = lb;
+    if (labels_out) {
+      std::vector<uint32_t> l32(n);
+      CK(cudaMemcpyAsync(l32.data(), dlab.p, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+      CK(cudaStreamSynchronize(ctx->stream));
+      for (uint64_t i = 0; i < n; ++i) labels_out[i] = l32[i];
+    }
+    if (proba_out) {
+      CK(cudaMemcpyAsync(proba_out, dproba.p, n * k * sizeof(F), cudaMemcpyDeviceToHost, ctx->stream));
+      CK(cudaStreamSynchronize(ctx->stream));
+    }
+    return LKM_OK;
+  };
+  const lkm_status st = body();
+  w.release(); dx.release(); dlab.release(); dproba.release();
+  return st;
+}
+
 // ---- .npy (format 1.0, little endian, C order) ------------------------------------------------
 static const char* npy_descr(int dtype) { return dtype == 0 ? "<f4" : dtype == 1 ? "<f8" : dtype == 2 ? "<u8" : nullptr; }
 static size_t npy_itemsize(int dtype) { return dtype == 0 ? 4 : 8; }
@@ -94,6 +397,32 @@ LKM_EXPORT lkm_status lkm_silhouette_score_f64(lkm_ctx* ctx, const double* x, ui
                                                const uint64_t* labels, double* score_out) {
   if (!ctx) return LKM_ERR_INVALID_ARG;
   return silhouette_impl<double>(ctx, x, n, d, row_stride, labels, score_out);
+}
+
+
+LKM_EXPORT lkm_status lkm_gmm_fit_f32(lkm_ctx* ctx, const lkm_gmm_params* p, lkm_rng rng, float* weights_out, float* means_out,
+                                      float* covariances_out, float* precisions_out, float* precisions_chol_out, uint64_t* n_iter_out,
+                                      float* lower_bound_out) {
+  if (!ctx) return LKM_ERR_INVALID_ARG;
+  return gmm_fit_impl<float>(ctx, p, rng, weights_out, means_out, covariances_out, precisions_out, precisions_chol_out, n_iter_out, lower_bound_out);
+}
+LKM_EXPORT lkm_status lkm_gmm_fit_f64(lkm_ctx* ctx, const lkm_gmm_params* p, lkm_rng rng, double* weights_out, double* means_out,
+                                      double* covariances_out, double* precisions_out, double* precisions_chol_out, uint64_t* n_iter_out,
+                                      double* lower_bound_out) {
+  if (!ctx) return LKM_ERR_INVALID_ARG;
+  return gmm_fit_impl<double>(ctx, p, rng, weights_out, means_out, covariances_out, precisions_out, precisions_chol_out, n_iter_out, lower_bound_out);
+}
+LKM_EXPORT lkm_status lkm_gmm_predict_f32(lkm_ctx* ctx, uint64_t k, const float* weights, const float* means, const float* precisions_chol,
+                                          const float* x, uint64_t n, uint64_t d, int64_t row_stride, uint64_t* labels_out,
+                                          float* proba_out, float* log_prob_norm_mean_out) {
+  if (!ctx) return LKM_ERR_INVALID_ARG;
+  return gmm_predict_impl<float>(ctx, k, weights, means, precisions_chol, x, n, d, row_stride, labels_out, proba_out, log_prob_norm_mean_out);
+}
+LKM_EXPORT lkm_status lkm_gmm_predict_f64(lkm_ctx* ctx, uint64_t k, const double* weights, const double* means, const double* precisions_chol,
+                                          const double* x, uint64_t n, uint64_t d, int64_t row_stride, uint64_t* labels_out,
+                                          double* proba_out, double* log_prob_norm_mean_out) {
+  if (!ctx) return LKM_ERR_INVALID_ARG;
+  return gmm_predict_impl<double>(ctx, k, weights, means, precisions_chol, x, n, d, row_stride, labels_out, proba_out, log_prob_norm_mean_out);
 }
 
 LKM_EXPORT lkm_status lkm_write_npy(const char* path, int dtype, const void* data, int ndim, const uint64_t* shape) {
