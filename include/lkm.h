@@ -132,6 +132,31 @@ lkm_status lkm_comm_init(lkm_ctx* ctx, const void* id128, int rank, int world_si
  * (row indices drawn by the RNG are global) and by inertia = total / n_global */
 lkm_status lkm_set_shard(lkm_ctx* ctx, uint64_t row_offset, uint64_t n_global);
 
+/* -- several devices from ONE process: a device group.  SURVEY 8(b) asked for lkm_create(device_ids, n_devices) so
+ * that one `fit(&dataset)` call of the Rust binding can use the whole box.  Rows are split into contiguous shards (rank
+ * r gets rows [r n / G, (r + 1) n / G)), one context and one host thread per device; every Lloyd iteration exchanges the
+ * per-device partials over NVLink peer access exactly as the one-process-per-GPU mode does, the seeding rendezvous
+ * happens on the host, and every rank sees the same random draws (the caller's rng is read once per draw).  The result
+ * equals the single-device fit up to the summation order of the partials (it is identical on every rank). */
+typedef struct lkm_multi lkm_multi;
+lkm_status lkm_create_multi(lkm_multi** out, const int* device_ids, int n_devices);
+lkm_status lkm_destroy_multi(lkm_multi* m);
+const char* lkm_multi_last_error(const lkm_multi* m);
+int lkm_multi_size(const lkm_multi* m);
+lkm_ctx* lkm_multi_ctx(lkm_multi* m, int i);   /* rank i's context, for the per-device knobs */
+lkm_status lkm_multi_set_data_f32(lkm_multi* m, const float* x, uint64_t n, uint64_t d, int64_t row_stride);
+lkm_status lkm_multi_set_data_f64(lkm_multi* m, const double* x, uint64_t n, uint64_t d, int64_t row_stride);
+/* Fit::fit over the sharded matrix; outputs as lkm_fit_* */
+lkm_status lkm_multi_fit_f32(lkm_multi* m, const lkm_params* p, lkm_rng rng, float* centroids_out, float* cluster_count_out,
+                             float* inertia_out, lkm_stats* stats_out);
+lkm_status lkm_multi_fit_f64(lkm_multi* m, const lkm_params* p, lkm_rng rng, double* centroids_out, double* cluster_count_out,
+                             double* inertia_out, lkm_stats* stats_out);
+/* update_memberships_and_dists with the rows split over the devices (no exchange); either output may be NULL */
+lkm_status lkm_multi_assign_f32(lkm_multi* m, const float* centroids, uint64_t k, const float* x, uint64_t n, uint64_t d,
+                                int64_t row_stride, uint64_t* labels_out, float* min_sq_dist_out);
+lkm_status lkm_multi_assign_f64(lkm_multi* m, const double* centroids, uint64_t k, const double* x, uint64_t n, uint64_t d,
+                                int64_t row_stride, uint64_t* labels_out, double* min_sq_dist_out);
+
 /* -- observations: `dataset.records()` (KM/algorithm.rs:299) -------------- */
 /* copies a host matrix (any row stride, like an ndarray view) to the device */
 lkm_status lkm_set_data_f32(lkm_ctx* ctx, const float* x, uint64_t n, uint64_t d, int64_t row_stride);

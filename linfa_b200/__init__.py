@@ -3,7 +3,7 @@
 `KMeans.params(k)...fit(dataset)`, `predict`, `transform` as in linfa-clustering; the
 arithmetic runs in hand-written sm_100a CUDA kernels behind the C ABI of include/lkm.h.
 """
-from .kmeans import (Context, Dataset, DatasetBase, IncrKMeansError, KMeans, KMeansAlgorithm, KMeansError,  # noqa: F401
+from .kmeans import (Context, Dataset, DatasetBase, DeviceGroup, IncrKMeansError, KMeans, KMeansAlgorithm, KMeansError,  # noqa: F401
                      KMeansInit, KMeansParams, KMeansParamsError, KMeansValidParams, L2Dist, LkmError, PickMode, generate,
                      read_npy, write_npy)
 from .rng import Xoshiro256Plus  # noqa: F401

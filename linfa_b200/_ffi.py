@@ -87,11 +87,12 @@ UNTYPED_SYMBOLS = [
     "lkm_comm_unique_id", "lkm_comm_init", "lkm_set_shard", "lkm_set_assign_path", "lkm_set_l2_flush", "lkm_set_kernel_timing", "lkm_set_scoring_passes",
     "lkm_set_keep_labels", "lkm_get_labels", "lkm_set_blob_layout",
     "lkm_write_npy", "lkm_read_npy_header", "lkm_read_npy_data",
+    "lkm_create_multi", "lkm_destroy_multi", "lkm_multi_last_error", "lkm_multi_size", "lkm_multi_ctx",
 ]
 TYPED_SYMBOLS = [
     "lkm_set_data", "lkm_set_data_device", "lkm_gen_blobs", "lkm_get_data", "lkm_fit", "lkm_init",
     "lkm_lloyd_iters", "lkm_hamerly_iters", "lkm_predict", "lkm_transform", "lkm_assign", "lkm_fit_with",
-    "lkm_silhouette_score", "lkm_gmm_fit", "lkm_gmm_predict",
+    "lkm_silhouette_score", "lkm_gmm_fit", "lkm_gmm_predict", "lkm_multi_set_data", "lkm_multi_fit", "lkm_multi_assign",
 ]
 
 _vp, _u64, _i64, _i32 = C.c_void_p, C.c_uint64, C.c_int64, C.c_int
@@ -117,6 +118,13 @@ lib.lkm_set_scoring_passes.argtypes = [_vp, _i32]
 lib.lkm_set_keep_labels.argtypes = [_vp, _i32]
 lib.lkm_get_labels.argtypes = [_vp, C.POINTER(C.c_uint32), _u64]
 lib.lkm_set_blob_layout.argtypes = [_vp, _i32]
+lib.lkm_create_multi.argtypes = [C.POINTER(_vp), C.POINTER(C.c_int), _i32]
+lib.lkm_destroy_multi.argtypes = [_vp]
+lib.lkm_multi_last_error.argtypes = [_vp]
+lib.lkm_multi_last_error.restype = C.c_char_p
+lib.lkm_multi_size.argtypes = [_vp]
+lib.lkm_multi_ctx.argtypes = [_vp, _i32]
+lib.lkm_multi_ctx.restype = _vp
 lib.lkm_write_npy.argtypes = [C.c_char_p, _i32, _vp, _i32, _u64p]
 lib.lkm_read_npy_header.argtypes = [C.c_char_p, C.POINTER(C.c_int), C.POINTER(C.c_int), _u64p, _u64p]
 lib.lkm_read_npy_data.argtypes = [C.c_char_p, _u64, _vp, _u64]
@@ -136,6 +144,9 @@ for _sfx, _ct in (("f32", C.c_float), ("f64", C.c_double)):
     getattr(lib, f"lkm_assign_{_sfx}").argtypes = [_vp, _fp, _u64, _fp, _u64, _u64, _i64, _u64p, _fp]
     getattr(lib, f"lkm_fit_with_{_sfx}").argtypes = [_vp, _pp, lkm_rng, _i32, _u64, _u64, _fp, _fp, _fp]
     getattr(lib, f"lkm_silhouette_score_{_sfx}").argtypes = [_vp, _fp, _u64, _u64, _i64, _u64p, _fp]
+    getattr(lib, f"lkm_multi_set_data_{_sfx}").argtypes = [_vp, _fp, _u64, _u64, _i64]
+    getattr(lib, f"lkm_multi_fit_{_sfx}").argtypes = [_vp, _pp, lkm_rng, _fp, _fp, _fp, _sp]
+    getattr(lib, f"lkm_multi_assign_{_sfx}").argtypes = [_vp, _fp, _u64, _fp, _u64, _u64, _i64, _u64p, _fp]
     getattr(lib, f"lkm_gmm_fit_{_sfx}").argtypes = [_vp, C.POINTER(lkm_gmm_params), lkm_rng, _fp, _fp, _fp, _fp, _fp, _u64p, _fp]
     getattr(lib, f"lkm_gmm_predict_{_sfx}").argtypes = [_vp, _u64, _fp, _fp, _fp, _fp, _u64, _u64, _i64, _u64p, _fp, _fp]
 

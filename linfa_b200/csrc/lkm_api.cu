@@ -15,6 +15,7 @@
 #include <cstring>
 #include <limits>
 #include <string>
+#include <thread>
 #include <type_traits>
 #include <vector>
 
@@ -250,14 +251,53 @@ static lkm_status p2p_setup(lkm_ctx* ctx, size_t L) {
   if (!ctx->p2p_enabled || ctx->world > 8) return LKM_OK;
   if (ctx->p2p_local && L <= ctx->p2p_cap) return LKM_OK;
   const int world = ctx->world;
+  const size_t cap = std::max<size_t>(L, 4096);
+  // [2 parities][world][cap] partials | [2][world][kFxMaxCtas] exchange flags | [world] barrier flags
+  const size_t bytes = (2 * (size_t)world * cap + 2 * (size_t)world * kFxMaxCtas + (size_t)world) * 8;
+  if (ctx->group != nullptr) {
+    // one process: every rank allocates its buffer, the pointers and device numbers travel through the group, and the
+    // peers are reached by plain peer access (no IPC handles)
+    {
+      std::vector<unsigned char> all0;
+      int dummy = 0;
+      CKS(comm_allgather_host(ctx, &dummy, sizeof(int), all0));   // nobody still uses the old buffers
+    }
+    if (ctx->p2p_local) { cudaFree(ctx->p2p_local); ctx->p2p_local = nullptr; }
+    ctx->p2p_peer.clear();
+    struct Rec { void* p; int device; int ok; } rec{nullptr, ctx->device, 1};
+    if (cudaMalloc(&ctx->p2p_local, bytes) != cudaSuccess) { rec.ok = 0; ctx->p2p_local = nullptr; cudaGetLastError(); }
+    else cudaMemset(ctx->p2p_local, 0, bytes);
+    rec.p = ctx->p2p_local;
+    std::vector<unsigned char> all;
+    CKS(comm_allgather_host(ctx, &rec, sizeof(rec), all));
+    int mine_ok = rec.ok;
+    ctx->p2p_peer.assign(world, nullptr);
+    for (int r = 0; r < world; ++r) {
+      Rec q;
+      std::memcpy(&q, all.data() + (size_t)r * sizeof(Rec), sizeof(Rec));
+      if (!q.ok) mine_ok = 0;
+      ctx->p2p_peer[r] = q.p;
+      if (r != ctx->rank && q.device != ctx->device) {
+        int can = 0;
+        if (cudaDeviceCanAccessPeer(&can, ctx->device, q.device) != cudaSuccess || !can) mine_ok = 0;
+        else {
+          const cudaError_t e = cudaDeviceEnablePeerAccess(q.device, 0);
+          if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) mine_ok = 0;
+          cudaGetLastError();
+        }
+      }
+    }
+    CKS(comm_allgather_host(ctx, &mine_ok, sizeof(int), all));
+    for (int r = 0; r < world; ++r) { int v; std::memcpy(&v, all.data() + (size_t)r * 4, 4); if (!v) return fail(ctx, LKM_ERR_UNSUPPORTED, "the devices of the group cannot reach each other over NVLink / PCIe peer access"); }
+    ctx->p2p_cap = cap;
+    CK(cudaStreamSynchronize(ctx->stream));
+    return LKM_OK;
+  }
   // release the old mapping
   for (int r = 0; r < (int)ctx->p2p_peer.size(); ++r)
     if (r != ctx->rank && ctx->p2p_peer[r]) cudaIpcCloseMemHandle(ctx->p2p_peer[r]);
   ctx->p2p_peer.clear();
   if (ctx->p2p_local) { cudaFree(ctx->p2p_local); ctx->p2p_local = nullptr; }
-  const size_t cap = std::max<size_t>(L, 4096);
-  // [2 parities][world][cap] partials | [2][world][kFxMaxCtas] exchange flags | [world] barrier flags
-  const size_t bytes = (2 * (size_t)world * cap + 2 * (size_t)world * kFxMaxCtas + (size_t)world) * 8;
   int ok = 1;
   cudaIpcMemHandle_t mine;
   std::memset(&mine, 0, sizeof(mine));
@@ -1031,6 +1071,8 @@ static lkm_status run_lloyd(lkm_ctx* ctx, F* dC2, uint64_t k, uint64_t max_iter,
         xa.shift_part = ctx->shift_part.as<double>(); xa.state = dstate; xa.tol = tol; xa.max_iter = max_iter;
         CK(launch_pdl(finalize_x_kernel<F, F, uint32_t>, xgrid, kFinThreads, 0, ctx->stream, xa, true));
         ctx->launches += 1;
+      } else if (ctx->group != nullptr) {
+        return fail(ctx, LKM_ERR_UNSUPPORTED, "device group without peer access");
       } else {
         // NCCL fallback (LKM_P2P=0 or no peer access): reduce -> ncclAllGather -> combine, three launches
         FinalizeArgs<F, F, uint32_t> ra{};
@@ -1525,6 +1567,17 @@ static lkm_status kmeans_para(lkm_ctx* ctx, const F* dX, uint64_t n, uint64_t d,
 static lkm_status comm_allgather_host(lkm_ctx* ctx, const void* src, size_t bytes, std::vector<unsigned char>& out) {
   const size_t w = (size_t)ctx->world;
   out.resize(bytes * w);
+  if (ctx->group != nullptr) {
+    LocalGroup* G = ctx->group;
+    G->slot[ctx->rank].assign(static_cast<const unsigned char*>(src), static_cast<const unsigned char*>(src) + bytes);
+    if (!G->barrier()) return fail(ctx, LKM_ERR_NCCL, "another rank of the device group failed");
+    for (size_t r = 0; r < w; ++r) {
+      if (G->slot[r].size() != bytes) { G->abort(); return fail(ctx, LKM_ERR_NCCL, "ranks of the device group disagree on a message size"); }
+      std::memcpy(out.data() + r * bytes, G->slot[r].data(), bytes);
+    }
+    if (!G->barrier()) return fail(ctx, LKM_ERR_NCCL, "another rank of the device group failed");   // the slots may be reused
+    return LKM_OK;
+  }
   CK(ctx->gather2.ensure(bytes * w));
   unsigned char* g = ctx->gather2.as<unsigned char>();
   CK(cudaMemcpyAsync(g + (size_t)ctx->rank * bytes, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
@@ -2186,7 +2239,7 @@ LKM_EXPORT lkm_status lkm_destroy(lkm_ctx* ctx) {
   cudaSetDevice(ctx->device);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   for (int r = 0; r < (int)ctx->p2p_peer.size(); ++r)
-    if (r != ctx->rank && ctx->p2p_peer[r]) cudaIpcCloseMemHandle(ctx->p2p_peer[r]);
+    if (ctx->group == nullptr && r != ctx->rank && ctx->p2p_peer[r]) cudaIpcCloseMemHandle(ctx->p2p_peer[r]);
   if (ctx->p2p_local) cudaFree(ctx->p2p_local);
   if (ctx->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->comm);
   DevBuf* bufs[] = {&ctx->xbuf, &ctx->cbuf, &ctx->part_sums, &ctx->part_counts, &ctx->part_inertia, &ctx->shift_part,
@@ -2283,6 +2336,166 @@ LKM_EXPORT lkm_status lkm_set_shard(lkm_ctx* ctx, uint64_t row_offset, uint64_t 
   return LKM_OK;
 }
 
+// ---- several devices from ONE process (lkm_create(device_ids, n_devices)) ----------------------------
+// `fit(&dataset)` of the Rust binding is one call on one thread; to use the whole box it hands the matrix to a device
+// group: rows are split into contiguous shards, one context + one host thread per device, the per-iteration partials
+// travel over NVLink exactly as in the one-process-per-GPU mode (finalize_x_kernel), the host-side steps of the seeding
+// rendezvous through LocalGroup.  Every rank draws the SAME random numbers: the caller's rng is read once per draw and
+// replayed to the other ranks.
+struct lkm_multi {
+  std::vector<lkm_ctx*> ctx;
+  LocalGroup group;
+  std::string err;
+};
+
+namespace lkm {
+struct SharedRng {
+  std::mutex mu;
+  lkm_rng base;
+  std::vector<std::pair<int, uint64_t>> log;   // (32 / 64, value) in draw order
+};
+struct RankRng {
+  SharedRng* shared;
+  size_t cursor;
+};
+static uint64_t shared_draw(RankRng* r, int kind) {
+  SharedRng* S = r->shared;
+  std::lock_guard<std::mutex> lk(S->mu);
+  if (r->cursor == S->log.size())
+    S->log.emplace_back(kind, kind == 32 ? (uint64_t)S->base.next_u32(S->base.user) : S->base.next_u64(S->base.user));
+  // every rank runs the same host code, so the kinds line up; a mismatch would mean diverged control flow
+  const uint64_t v = S->log[r->cursor].second;
+  ++r->cursor;
+  return v;
+}
+static uint32_t rank_next_u32(void* u) { return (uint32_t)shared_draw(static_cast<RankRng*>(u), 32); }
+static uint64_t rank_next_u64(void* u) { return shared_draw(static_cast<RankRng*>(u), 64); }
+
+template <typename Fn>
+static lkm_status multi_run(lkm_multi* m, Fn fn) {
+  const int w = (int)m->ctx.size();
+  std::vector<lkm_status> st(w, LKM_OK);
+  std::vector<std::thread> th;
+  {
+    std::lock_guard<std::mutex> lk(m->group.mu);
+    m->group.aborted = false;
+    m->group.arrived = 0;
+  }
+  for (int r = 0; r < w; ++r)
+    th.emplace_back([&, r] {
+      st[r] = fn(r, m->ctx[r]);
+      if (st[r] != LKM_OK && st[r] != LKM_NOT_CONVERGED) m->group.abort();   // release the ranks that wait for this one
+    });
+  for (auto& t : th) t.join();
+  for (int r = 0; r < w; ++r)
+    if (st[r] != LKM_OK) { m->err = "rank " + std::to_string(r) + ": " + m->ctx[r]->err; return st[r]; }
+  return LKM_OK;
+}
+
+template <typename F>
+static lkm_status multi_set_data(lkm_multi* m, const F* x, uint64_t n, uint64_t d, int64_t row_stride) {
+  if (!x || d == 0 || row_stride < (int64_t)d) { m->err = "bad matrix"; return LKM_ERR_INVALID_ARG; }
+  const uint64_t w = m->ctx.size();
+  return multi_run(m, [&](int r, lkm_ctx* c) -> lkm_status {
+    const uint64_t lo = n * (uint64_t)r / w, hi = n * (uint64_t)(r + 1) / w;
+    lkm_status st = set_data_impl<F>(c, x + lo * (uint64_t)row_stride, hi - lo, d, row_stride);
+    if (st != LKM_OK) return st;
+    c->row_offset = lo;
+    c->n_global = n;
+    return LKM_OK;
+  });
+}
+
+template <typename F>
+static lkm_status multi_fit(lkm_multi* m, const lkm_params* p, lkm_rng rng, F* centroids_out, F* counts_out, F* inertia_out,
+                            lkm_stats* stats_out) {
+  if (!p || !centroids_out || !counts_out || !inertia_out) { m->err = "null argument"; return LKM_ERR_INVALID_ARG; }
+  const uint64_t k = p->n_clusters, d = m->ctx[0]->d;
+  SharedRng shared;
+  shared.base = rng;
+  const int w = (int)m->ctx.size();
+  std::vector<RankRng> rr(w);
+  std::vector<std::vector<F>> cen(w, std::vector<F>(std::max<uint64_t>(k * d, 1))), cnt(w, std::vector<F>(std::max<uint64_t>(k, 1)));
+  std::vector<F> inertia(w, (F)0);
+  std::vector<lkm_stats> stv(w);
+  const lkm_status st = multi_run(m, [&](int r, lkm_ctx* c) -> lkm_status {
+    rr[r] = RankRng{&shared, 0};
+    lkm_rng mine{&rr[r], rank_next_u32, rank_next_u64};
+    return fit_impl<F>(c, p, mine, cen[r].data(), cnt[r].data(), &inertia[r], &stv[r]);
+  });
+  if (st != LKM_OK) return st;
+  // identical on every rank (same partials combined in the same order): rank 0's copy is the result
+  std::memcpy(centroids_out, cen[0].data(), k * d * sizeof(F));
+  std::memcpy(counts_out, cnt[0].data(), k * sizeof(F));
+  *inertia_out = inertia[0];
+  if (stats_out) *stats_out = stv[0];
+  return LKM_OK;
+}
+
+template <typename F>
+static lkm_status multi_assign(lkm_multi* m, const F* centroids, uint64_t k, const F* x, uint64_t n, uint64_t d, int64_t row_stride,
+                               uint64_t* labels_out, F* dist_out) {
+  if (!x || row_stride < (int64_t)d) { m->err = "bad matrix"; return LKM_ERR_INVALID_ARG; }
+  const uint64_t w = m->ctx.size();
+  // rows are independent: every device takes a contiguous block, no exchange (KM/algorithm.rs:838-881)
+  return multi_run(m, [&](int r, lkm_ctx* c) -> lkm_status {
+    const uint64_t lo = n * (uint64_t)r / w, hi = n * (uint64_t)(r + 1) / w;
+    if (hi == lo) return LKM_OK;
+    return assign_impl<F>(c, centroids, k, x + lo * (uint64_t)row_stride, hi - lo, d, row_stride, labels_out ? labels_out + lo : nullptr,
+                          dist_out ? dist_out + lo : nullptr);
+  });
+}
+}  // namespace lkm
+
+LKM_EXPORT lkm_status lkm_create_multi(lkm_multi** out, const int* device_ids, int n_devices) {
+  if (!out || !device_ids || n_devices < 1 || n_devices > 8) return LKM_ERR_INVALID_ARG;
+  lkm_multi* m = new (std::nothrow) lkm_multi();
+  if (!m) return LKM_ERR_CUDA;
+  m->group.world = n_devices;
+  m->group.slot.resize(n_devices);
+  for (int r = 0; r < n_devices; ++r) {
+    lkm_ctx* c = nullptr;
+    const lkm_status st = lkm_create(&c, device_ids[r]);
+    if (st != LKM_OK) {
+      for (lkm_ctx* q : m->ctx) lkm_destroy(q);
+      delete m;
+      return st;
+    }
+    c->rank = r;
+    c->world = n_devices;
+    if (n_devices > 1) c->group = &m->group;
+    m->ctx.push_back(c);
+  }
+  *out = m;
+  return LKM_OK;
+}
+LKM_EXPORT lkm_status lkm_destroy_multi(lkm_multi* m) {
+  if (!m) return LKM_OK;
+  for (lkm_ctx* c : m->ctx) lkm_destroy(c);
+  delete m;
+  return LKM_OK;
+}
+LKM_EXPORT const char* lkm_multi_last_error(const lkm_multi* m) { return m ? m->err.c_str() : "null group"; }
+LKM_EXPORT int lkm_multi_size(const lkm_multi* m) { return m ? (int)m->ctx.size() : 0; }
+LKM_EXPORT lkm_ctx* lkm_multi_ctx(lkm_multi* m, int i) { return (m && i >= 0 && i < (int)m->ctx.size()) ? m->ctx[i] : nullptr; }
+
+#define LKM_MULTI_TYPED(F, SFX)                                                                                        \
+  LKM_EXPORT lkm_status lkm_multi_set_data_##SFX(lkm_multi* m, const F* x, uint64_t n, uint64_t d, int64_t row_stride) {\
+    if (!m) return LKM_ERR_INVALID_ARG;                                                                                \
+    return multi_set_data<F>(m, x, n, d, row_stride);                                                                  \
+  }                                                                                                                    \
+  LKM_EXPORT lkm_status lkm_multi_fit_##SFX(lkm_multi* m, const lkm_params* p, lkm_rng rng, F* centroids_out,          \
+                                            F* cluster_count_out, F* inertia_out, lkm_stats* stats_out) {              \
+    if (!m) return LKM_ERR_INVALID_ARG;                                                                                \
+    return multi_fit<F>(m, p, rng, centroids_out, cluster_count_out, inertia_out, stats_out);                          \
+  }                                                                                                                    \
+  LKM_EXPORT lkm_status lkm_multi_assign_##SFX(lkm_multi* m, const F* centroids, uint64_t k, const F* x, uint64_t n,   \
+                                               uint64_t d, int64_t row_stride, uint64_t* labels_out,                   \
+                                               F* min_sq_dist_out) {                                                   \
+    if (!m) return LKM_ERR_INVALID_ARG;                                                                                \
+    return multi_assign<F>(m, centroids, k, x, n, d, row_stride, labels_out, min_sq_dist_out);                         \
+  }
+
 #define LKM_TYPED(F, SFX)                                                                                              \
   LKM_EXPORT lkm_status lkm_set_data_##SFX(lkm_ctx* ctx, const F* x, uint64_t n, uint64_t d, int64_t row_stride) {     \
     if (!ctx) return LKM_ERR_INVALID_ARG;                                                                              \
@@ -2362,6 +2575,8 @@ LKM_EXPORT lkm_status lkm_set_shard(lkm_ctx* ctx, uint64_t row_offset, uint64_t 
 
 LKM_TYPED(float, f32)
 LKM_TYPED(double, f64)
+LKM_MULTI_TYPED(float, f32)
+LKM_MULTI_TYPED(double, f64)
 
 #ifdef LKM_WITH_PROBES
 // ---- development probes (not part of include/lkm.h) ---------------------------------------

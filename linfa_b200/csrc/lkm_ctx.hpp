@@ -3,7 +3,9 @@
 #include <cuda_runtime.h>
 #include <dlfcn.h>
 
+#include <condition_variable>
 #include <cstdint>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -53,6 +55,33 @@ struct DevBuf {
   }
   void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
   template <class T> T* as() { return reinterpret_cast<T*>(p); }
+};
+
+// Ranks that live in ONE process (lkm_create_multi: one context per device, one host thread per rank): the host-side
+// all-gather of the seeding / set-up steps goes through this rendezvous instead of NCCL, and the NVLink exchange buffers
+// are mapped by plain peer access instead of CUDA IPC.
+struct LocalGroup {
+  int world = 1;
+  std::mutex mu;
+  std::condition_variable cv;
+  int arrived = 0;
+  unsigned long long gen = 0;
+  bool aborted = false;
+  std::vector<std::vector<unsigned char>> slot;
+  // false: another rank failed and left
+  bool barrier() {
+    std::unique_lock<std::mutex> lk(mu);
+    if (aborted) return false;
+    const unsigned long long g = gen;
+    if (++arrived == world) { arrived = 0; ++gen; cv.notify_all(); return true; }
+    cv.wait(lk, [&] { return gen != g || aborted; });
+    return !aborted;
+  }
+  void abort() {
+    std::lock_guard<std::mutex> lk(mu);
+    aborted = true;
+    cv.notify_all();
+  }
 };
 
 }  // namespace lkm
@@ -111,6 +140,7 @@ struct lkm_ctx {
   // comm
   void* comm = nullptr;
   int rank = 0, world = 1;
+  lkm::LocalGroup* group = nullptr;   // ranks of one process (lkm_create_multi); nullptr: one process per rank (NCCL)
   // NVLink one-shot exchange: this rank's gather buffer [2 parities][world][p2p_cap doubles] followed by
   // [2][world] flags, mapped into every peer through CUDA IPC
   void* p2p_local = nullptr;

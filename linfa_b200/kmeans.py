@@ -348,6 +348,58 @@ def _records(dataset):
     return dataset.records if isinstance(dataset, DatasetBase) else dataset
 
 
+class DeviceGroup:
+    """lkm_multi: several GPUs driven from this one process (include/lkm.h, lkm_create_multi).  Rows are split into
+    contiguous shards; `fit` is Fit::fit over the sharded matrix, `assign` is update_memberships_and_dists."""
+
+    def __init__(self, device_ids):
+        ids = (C.c_int * len(device_ids))(*device_ids)
+        h = C.c_void_p()
+        st = _ffi.lib.lkm_create_multi(C.byref(h), ids, len(device_ids))
+        if st != _ffi.OK:
+            raise LkmError(st, "lkm_create_multi failed: no usable CUDA device (this path has no CPU fallback)")
+        self.h, self.device_ids, self.dtype, self.shape = h, list(device_ids), None, None
+
+    def close(self):
+        if self.h:
+            _ffi.lib.lkm_destroy_multi(self.h)
+            self.h = None
+
+    def check(self, st):
+        if st != _ffi.OK:
+            raise LkmError(st, _ffi.lib.lkm_multi_last_error(self.h).decode())
+
+    def set_data(self, x):
+        x = _row_major_view(np.asarray(x))
+        sfx, ct = _ffi.sfx_of(x.dtype)
+        self.check(getattr(_ffi.lib, f"lkm_multi_set_data_{sfx}")(self.h, _ffi.fptr(x, ct), x.shape[0], x.shape[1], x.strides[0] // x.itemsize))
+        self.dtype, self.shape = x.dtype, x.shape
+
+    def fit(self, params, dataset):
+        """params: KMeansParams / KMeansValidParams (checked here like the ParamGuard blanket impl does)."""
+        v = params.check() if hasattr(params, "check") else params
+        self.set_data(_records(dataset))
+        sfx, ct = _ffi.sfx_of(self.dtype)
+        k, d = v.n_clusters(), self.shape[1]
+        p, keep = v._native_params(self.dtype)
+        rng = copy.deepcopy(v._rng)
+        cen, cnt, inertia = np.zeros((k, d), self.dtype), np.zeros(k, self.dtype), np.zeros(1, self.dtype)
+        stats = _ffi.lkm_stats()
+        self.check(getattr(_ffi.lib, f"lkm_multi_fit_{sfx}")(self.h, C.byref(p), _ffi.make_rng(rng), _ffi.fptr(cen, ct), _ffi.fptr(cnt, ct),
+                                                              _ffi.fptr(inertia, ct), C.byref(stats)))
+        self.last_stats = stats
+        return KMeans(cen, cnt, inertia[0], v._dist_fn, None)
+
+    def assign(self, centroids, x):
+        c = np.ascontiguousarray(centroids)
+        x = np.ascontiguousarray(x, dtype=c.dtype)
+        sfx, ct = _ffi.sfx_of(c.dtype)
+        labels, dists = np.zeros(x.shape[0], np.uint64), np.zeros(x.shape[0], c.dtype)
+        self.check(getattr(_ffi.lib, f"lkm_multi_assign_{sfx}")(self.h, _ffi.fptr(c, ct), c.shape[0], _ffi.fptr(x, ct), x.shape[0], x.shape[1],
+                                                                 x.shape[1], labels.ctypes.data_as(_ffi._u64p), _ffi.fptr(dists, ct)))
+        return labels, dists
+
+
 # ---- hyper-parameters --------------------------------------------------------
 class KMeansValidParams:
     """KMeansValidParams (KM/hyperparams.rs:19-42) + the Fit / FitWith impls."""

@@ -9,19 +9,24 @@ fn main() {
     let out = PathBuf::from(env::var("OUT_DIR").unwrap());
     // LKM_SRC points at the repository that holds include/lkm.h and linfa_b200/csrc
     let src = PathBuf::from(env::var("LKM_SRC").unwrap_or_else(|_| "../..".into()));
-    let cu = src.join("linfa_b200/csrc/lkm_api.cu");
-    let obj = out.join("lkm_api.o");
     let lib = out.join("liblkm.a");
     let nvcc = env::var("NVCC").unwrap_or_else(|_| "nvcc".into());
-    let status = Command::new(&nvcc)
-        .args(["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo"])
-        .args(["-Xcompiler", "-fPIC", "-c", "-o"])
-        .arg(&obj)
-        .arg(&cu)
-        .status()
-        .expect("nvcc not found: the B200 K-Means path has no CPU fallback");
-    assert!(status.success(), "nvcc failed");
-    let status = Command::new("ar").arg("crs").arg(&lib).arg(&obj).status().expect("ar");
+    let mut objects = Vec::new();
+    for unit in ["lkm_api", "lkm_extras"] {
+        let cu = src.join(format!("linfa_b200/csrc/{unit}.cu"));
+        let obj = out.join(format!("{unit}.o"));
+        let status = Command::new(&nvcc)
+            .args(["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo"])
+            .args(["-Xcompiler", "-fPIC", "-c", "-o"])
+            .arg(&obj)
+            .arg(&cu)
+            .status()
+            .expect("nvcc not found: the B200 K-Means path has no CPU fallback");
+        assert!(status.success(), "nvcc failed");
+        println!("cargo:rerun-if-changed={}", cu.display());
+        objects.push(obj);
+    }
+    let status = Command::new("ar").arg("crs").arg(&lib).args(&objects).status().expect("ar");
     assert!(status.success());
     println!("cargo:rustc-link-search=native={}", out.display());
     println!("cargo:rustc-link-lib=static=lkm");
@@ -30,6 +35,5 @@ fn main() {
     println!("cargo:rustc-link-lib=dylib=cudart");
     println!("cargo:rustc-link-lib=dylib=stdc++");
     println!("cargo:rustc-link-lib=dylib=dl");
-    println!("cargo:rerun-if-changed={}", cu.display());
     println!("cargo:rerun-if-changed={}", src.join("include/lkm.h").display());
 }

@@ -23,7 +23,7 @@ def lb():
 
 def test_library_exports_every_declared_symbol(lb):
     hdr = open(os.path.join(ROOT, "include", "lkm.h")).read()
-    declared = set(re.findall(r"^(?:lkm_status|const char\*|void\*)\s+(lkm_[a-z0-9_]+)\(", hdr, flags=re.M))
+    declared = set(re.findall(r"^(?:lkm_status|const char\*|void\*|int|lkm_ctx\*)\s+(lkm_[a-z0-9_]+)\(", hdr, flags=re.M))
     assert len(declared) >= 30
     lib = C.CDLL(os.path.join(ROOT, "linfa_b200", "liblkm.so"))
     missing = [s for s in sorted(declared) if not hasattr(lib, s)]

@@ -33,3 +33,36 @@ def test_row_sharded_fit_matches_single_gpu(world):
     assert res.returncode == 0, res.stdout[-4000:] + res.stderr[-4000:]
     assert "MISMATCH" not in res.stdout
     assert res.stdout.count("[multi_gpu_check]") >= 8
+
+
+def test_device_group_in_one_process(oracle):
+    """lkm_create_multi: the sharded fit from ONE process (what the Rust binding's `fit(&dataset)` uses).  Two ranks on the
+    devices the box has (the same device twice on a single-GPU box: the rendezvous, the replayed rng and the NVLink-style
+    exchange all run, only the link is local)."""
+    import numpy as np
+
+    import linfa_b200 as lb
+
+    have = _gpu_count()
+    ids = [0, 1] if have >= 2 else [0, 0]
+    g = np.random.default_rng(0)
+    for dt, tol in ((np.float64, 1e-10), (np.float32, 1e-5)):
+        centres = g.uniform(-30, 30, (12, 16))
+        X = (centres[g.integers(0, 12, 40000)] + g.standard_normal((40000, 16))).astype(dt)
+        grp = lb.DeviceGroup(ids)
+        try:
+            for init in (lb.KMeansInit.KMeansPlusPlus, lb.KMeansInit.Random, lb.KMeansInit.KMeansPara):
+                params = lb.KMeans.params_with_rng(12, lb.Xoshiro256Plus.seed_from_u64(5)).n_runs(2).init_method(init)
+                multi = grp.fit(params, lb.DatasetBase(X))
+                single = params.fit(lb.DatasetBase(X))
+                if init != lb.KMeansInit.KMeansPara:   # k-means|| draws per-shard streams: same quality, not the same seeds
+                    np.testing.assert_allclose(multi.centroids(), single.centroids(), rtol=tol, atol=tol * 30)
+                    assert multi.cluster_count().tolist() == single.cluster_count().tolist()
+                    np.testing.assert_allclose(multi.inertia(), single.inertia(), rtol=tol)
+                else:
+                    assert multi.inertia() < 1.5 * single.inertia()
+            lab, dist = grp.assign(single.centroids(), X)
+            ref_lab, ref_dist = oracle.assign(X, single.centroids())
+            assert (lab == ref_lab).all() and (dist == ref_dist).all()
+        finally:
+            grp.close()
