@@ -467,6 +467,34 @@ static lkm_status launch_rows(lkm_ctx* ctx, RowsArgs<F>& a, uint64_t max_rows) {
   return LKM_OK;
 }
 
+static void trace_mark(lkm_ctx* ctx, const char* name) {
+  if (!ctx->step_trace) return;
+  cudaEvent_t e;
+  if (cudaEventCreate(&e) != cudaSuccess) return;
+  cudaEventRecord(e, ctx->stream);
+  ctx->trace_ev.push_back(e);
+  ctx->trace_name.push_back(name);
+}
+static void trace_report(lkm_ctx* ctx) {
+  if (!ctx->step_trace || ctx->trace_ev.size() < 2) return;
+  cudaEventSynchronize(ctx->trace_ev.back());
+  std::vector<std::pair<std::string, std::pair<double, int>>> agg;
+  for (size_t i = 1; i < ctx->trace_ev.size(); ++i) {
+    float ms = 0;
+    cudaEventElapsedTime(&ms, ctx->trace_ev[i - 1], ctx->trace_ev[i]);
+    const std::string nm = ctx->trace_name[i];
+    size_t q = 0;
+    for (; q < agg.size(); ++q) if (agg[q].first == nm) break;
+    if (q == agg.size()) agg.push_back({nm, {0.0, 0}});
+    agg[q].second.first += ms;
+    agg[q].second.second += 1;
+  }
+  for (auto& a : agg) std::fprintf(stderr, "step_trace %-22s n=%4d mean %9.2f us\n", a.first.c_str(), a.second.second, 1e3 * a.second.first / a.second.second);
+  for (cudaEvent_t e : ctx->trace_ev) cudaEventDestroy(e);
+  ctx->trace_ev.clear();
+  ctx->trace_name.clear();
+}
+
 struct LloydOut {
   uint64_t n_iter = 0, fallback_rows = 0;
   double inertia = 0, shift = 0;
@@ -751,6 +779,8 @@ static lkm_status run_lloyd(lkm_ctx* ctx, F* dC2, uint64_t k, uint64_t max_iter,
   if (tc5_can_fuse) CK(ctx->part_inertia.ensure((size_t)std::max(1024, tc5_grid * (1 + upd_ny)) * 8));
   CK(ctx->part_sums.ensure((size_t)grid * kd * sizeof(F)));
   CK(ctx->part_counts.ensure((size_t)grid * k * 4));
+  if (use_upd && ctx->sparse_partials) CK(ctx->part_touched.ensure((size_t)grid * k));
+  unsigned char* touched = (use_upd && ctx->sparse_partials) ? ctx->part_touched.as<unsigned char>() : nullptr;
   CK(ctx->part_inertia.ensure((size_t)std::max(grid, 1024) * 8));
   const int fin_grid = (int)((kd + kFinElems - 1) / kFinElems);
   CK(ctx->shift_part.ensure((size_t)std::max(std::max(fin_grid, grid), kFxMaxCtas) * 8));
@@ -835,7 +865,9 @@ static lkm_status run_lloyd(lkm_ctx* ctx, F* dC2, uint64_t k, uint64_t max_iter,
         }
         CK(cudaEventRecord(ctx->iter_events[3 * it], ctx->stream));
       }
+      trace_mark(ctx, "start");
       int fin_src = grid, fin_src_inertia = use_upd ? upd_gx * upd_ny : 0;   // partial sources of this iteration's finalize
+      bool upd_partials = false;   // the partials come from update_rows_kernel (and the fused pair kernel): `touched` map is valid
       if (use_tc) {
         if constexpr (std::is_same<F, float>::value) {
           TcArgs ta{};
@@ -904,7 +936,7 @@ static lkm_status run_lloyd(lkm_ctx* ctx, F* dC2, uint64_t k, uint64_t max_iter,
               t5.chunk_idx = ch;
               if (tc5_passes == 1 && tc5_can_fuse && ch == tc5_chunks - 1) {
                 t5.part_sums = ctx->part_sums.as<float>(); t5.part_counts = ctx->part_counts.as<uint32_t>();
-                t5.part_inertia = ctx->part_inertia.as<double>();
+                t5.part_inertia = ctx->part_inertia.as<double>(); t5.part_touched = touched;
                 t5.mixed_list = ctx->t5list.as<uint32_t>() + tc5_grid; t5.mixed_count = ctx->t5list.as<uint32_t>();
                 t5.list_cap = tc5_list_cap;
                 if (d == 32) assign_tc5s_kernel<32, true, 64><<<tc5_grid, t5_fuse_threads(32), tc5s_smem_bytes(32), ctx->stream>>>(t5, tc5_map);
@@ -925,7 +957,9 @@ static lkm_status run_lloyd(lkm_ctx* ctx, F* dC2, uint64_t k, uint64_t max_iter,
               RowsArgs<float> ra{};
               ra.X = dX; ra.n = n; ra.d = (int)d; ra.k = (int)k; ra.C = Ccur; ra.list = t5.rescan_list; ra.list_count = rescan_count;
               ra.labels = ctx->labels.as<uint32_t>(); ra.state = dstate;
+              trace_mark(ctx, "assign_tc5");
               CKS(launch_rows<float>(ctx, ra, n));
+              trace_mark(ctx, "rows_top2");
             }
             assigned = true;
           } else if (use_tca) {
@@ -987,13 +1021,14 @@ static lkm_status run_lloyd(lkm_ctx* ctx, F* dC2, uint64_t k, uint64_t max_iter,
             ua.X = dX; ua.n = n; ua.k = (int)k; ua.chunk_rows = upd_chunk; ua.stages = upd_stages;
             ua.labels = ctx->labels.as<uint32_t>(); ua.C = Ccur;
             ua.part_sums = ctx->part_sums.as<float>(); ua.part_counts = ctx->part_counts.as<uint32_t>();
-            ua.part_inertia = ctx->part_inertia.as<double>(); ua.state = dstate;
+            ua.part_inertia = ctx->part_inertia.as<double>(); ua.state = dstate; ua.part_touched = touched;
             int ugx = upd_gx;
             if (fused_now) {
               // only the tiles the screening kernel listed; its own partials are sources [0, tc5_grid), these follow
               ua.tile_list = ctx->t5list.as<uint32_t>() + tc5_grid; ua.tile_count = ctx->t5list.as<uint32_t>();
               ua.list_cap = tc5_list_cap;
               ua.part_sums += (size_t)tc5_grid * kd; ua.part_counts += (size_t)tc5_grid * k; ua.part_inertia += tc5_grid;
+              if (touched) ua.part_touched += (size_t)tc5_grid * k;
               ugx = tc5_grid;
             }
             fin_src = fused_now ? 2 * tc5_grid : upd_gx;
@@ -1007,7 +1042,9 @@ static lkm_status run_lloyd(lkm_ctx* ctx, F* dC2, uint64_t k, uint64_t max_iter,
             else if (d == 64) CK(cudaLaunchKernelEx(&cfg, update_rows_kernel<64>, ua, upd_map));
             else CK(cudaLaunchKernelEx(&cfg, update_rows_kernel<128>, ua, upd_map));
             ctx->launches++;
+            trace_mark(ctx, "update_rows");
             updated = true;
+            upd_partials = true;
           }
         }
         if (!updated) {
@@ -1039,6 +1076,7 @@ static lkm_status run_lloyd(lkm_ctx* ctx, F* dC2, uint64_t k, uint64_t max_iter,
         fa.src_inertia = ctx->part_inertia.as<double>();
         fa.sum_stride = kd; fa.cnt_stride = k; fa.inertia_stride = 1; fa.n_src = fin_src; fa.k = (int)k; fa.d = (int)d;
         fa.n_src_inertia = fin_src_inertia;
+        fa.src_touched = upd_partials ? touched : nullptr;
         fa.C_old = Ccur; fa.C_new = Cnext; fa.counts_out = ctx->counts_out.as<double>();
         fa.shift_part = ctx->shift_part.as<double>(); fa.state = dstate; fa.tol = tol; fa.max_iter = max_iter;
         CK((launch_finalize<F, F, uint32_t, true>(fa, ctx->stream)));
@@ -1050,7 +1088,7 @@ static lkm_status run_lloyd(lkm_ctx* ctx, F* dC2, uint64_t k, uint64_t max_iter,
         xa.src_sums = ctx->part_sums.as<F>(); xa.src_counts = ctx->part_counts.as<uint32_t>();
         xa.src_inertia = ctx->part_inertia.as<double>();
         xa.sum_stride = kd; xa.cnt_stride = k; xa.inertia_stride = 1; xa.n_src = fin_src; xa.n_src_inertia = fin_src_inertia;
-        xa.k = (int)k; xa.d = (int)d;
+        xa.k = (int)k; xa.d = (int)d; xa.src_touched = upd_partials ? touched : nullptr;
         const int n_slices = (int)((kd + kFinElems - 1) / kFinElems);
         const int g_max = std::min(kFxMaxCtas, 2 * ctx->sm_count);
         xa.slices_per_cta = (n_slices + g_max - 1) / g_max;
@@ -1080,6 +1118,7 @@ static lkm_status run_lloyd(lkm_ctx* ctx, F* dC2, uint64_t k, uint64_t max_iter,
         ra.src_inertia = ctx->part_inertia.as<double>();
         ra.sum_stride = kd; ra.cnt_stride = k; ra.inertia_stride = 1; ra.n_src = fin_src; ra.k = (int)k; ra.d = (int)d;
         ra.n_src_inertia = fin_src_inertia;
+        ra.src_touched = upd_partials ? touched : nullptr;
         ra.rank_out = ctx->gather.as<double>() + (size_t)ctx->rank * L;
         ra.state = dstate;
         FinalizeArgs<F, double, double> fa{};
@@ -1095,6 +1134,7 @@ static lkm_status run_lloyd(lkm_ctx* ctx, F* dC2, uint64_t k, uint64_t max_iter,
         CK((launch_finalize<F, double, double, true>(fa, ctx->stream)));
         ctx->launches += 2;  // reduce + update (the all-gather kernel is NCCL's, not counted)
       }
+      trace_mark(ctx, "finalize");
       if (flush) CK(cudaEventRecord(ctx->iter_events[3 * it + 2], ctx->stream));
     }
     launched += todo;
@@ -1178,6 +1218,7 @@ static lkm_status run_lloyd(lkm_ctx* ctx, F* dC2, uint64_t k, uint64_t max_iter,
                    hp[r * 8 + 2], hp[r * 8 + 3], hp[r * 8 + 4], hp[r * 8 + 7]);
   }
 #endif
+  trace_report(ctx);
   out.inertia = ctx->h_state->inertia;
   out.shift = ctx->h_state->shift;
   out.final_buf = (int)(out.n_iter & 1);
@@ -2212,6 +2253,8 @@ LKM_EXPORT lkm_status lkm_create(lkm_ctx** out, int device) {
   if (const char* v = std::getenv("LKM_TC5")) ctx->tc5_enabled = std::atoi(v);
   if (const char* v = std::getenv("LKM_TC5_FUSE")) ctx->tc5_fuse = std::atoi(v);
   if (const char* v = std::getenv("LKM_DMMA")) ctx->dmma_enabled = std::atoi(v);
+  if (const char* v = std::getenv("LKM_STEP_TRACE")) ctx->step_trace = std::atoi(v);
+  if (const char* v = std::getenv("LKM_SPARSE_PARTIALS")) ctx->sparse_partials = std::atoi(v);
   if (const char* v = std::getenv("LKM_TC5_DEFER")) ctx->tc5_defer = std::atoi(v);
   if (const char* v = std::getenv("LKM_TC5_RESCAN_LIMIT")) ctx->tc5_rescan_limit = std::atof(v);
   if (const char* v = std::getenv("LKM_PAIR32")) ctx->pair32 = std::atoi(v);
@@ -2246,7 +2289,7 @@ LKM_EXPORT lkm_status lkm_destroy(lkm_ctx* ctx) {
                     &ctx->counts_out, &ctx->state, &ctx->gather, &ctx->gather2, &ctx->labels, &ctx->dists, &ctx->wdists, &ctx->cum,
                     &ctx->scratch, &ctx->tmpx, &ctx->tmpc, &ctx->idxbuf, &ctx->bsum, &ctx->weights, &ctx->flushbuf, &ctx->fin_sync, &ctx->para_c2, &ctx->tca_bsplit, &ctx->tca_cn, &ctx->tca_cmax,
                     &ctx->xmax2, &ctx->t4prof, &ctx->t5merge, &ctx->t5list, &ctx->ham_ub, &ctx->ham_lb, &ctx->ham_list, &ctx->ham_fx,
-                    &ctx->ham_moved, &ctx->ham_s, &ctx->ham_state, &ctx->ham_red, &ctx->absmax};
+                    &ctx->ham_moved, &ctx->ham_s, &ctx->ham_state, &ctx->ham_red, &ctx->absmax, &ctx->part_touched};
   for (DevBuf* b : bufs) b->release();
   for (cudaEvent_t e : ctx->iter_events) cudaEventDestroy(e);
   if (ctx->h_state) cudaFreeHost(ctx->h_state);

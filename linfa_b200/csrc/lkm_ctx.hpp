@@ -114,6 +114,13 @@ struct lkm_ctx {
   int f64s_rpt = 2;      // LKM_F64S_RPT=1: one row per lane (32-row tiles, 3 CTAs / SM)
   int pair32 = 0;        // LKM_PAIR32=1: d = 32, k <= 64 through the CTA-pair screening kernel instead of the pipeline kernel
   int tc5_fuse = 1;      // LKM_TC5_FUSE=0: screening kernel without the fused update of uniform tiles
+  // LKM_STEP_TRACE=1: an event after every stage of a Lloyd iteration (tc5 / update path); run_lloyd prints the mean
+  // time per stage to stderr.  The events serialise the stages (no programmatic dependent launch overlap): a tuning aid.
+  int step_trace = 0;
+  std::vector<cudaEvent_t> trace_ev;
+  std::vector<const char*> trace_name;
+  int sparse_partials = 1;   // LKM_SPARSE_PARTIALS=0: the pair / update kernels zero-fill and write back whole k x d partials
+  DevBuf part_touched;
   int dmma_enabled = 1;  // LKM_DMMA=0: f64 shapes with a large contraction stay on the CUDA-core kernels
   int tc5_enabled = 1;   // LKM_TC5=0: tc_assign_kernel instead of the CTA-pair assignment kernel
   double tc5_rescan_limit = 0.08;   // LKM_TC5_RESCAN_LIMIT: share of listed rows above which the pair kernel moves to 3xTF32

@@ -478,6 +478,7 @@ template <typename F, typename S, typename CT> struct FinalizeArgs {
   int n_src;
   int n_src_inertia;   // inertia partials when their number differs from n_src (0 = n_src)
   int k, d;
+  const unsigned char* src_touched;   // optional [n_src][k]: which clusters a source wrote (see strided_sum)
   // reduce-only output (per-rank partial): [kd sums | k counts | 1 inertia] as f64
   double* rank_out;
   // update outputs
@@ -517,15 +518,21 @@ __device__ __forceinline__ double block_sum(double v, double* red) {
 
 // sum of src[b*stride + e] over b = g, g+G, g+2G, ... : batches of 16 sources per thread are loaded before the first
 // addition (one L2 round trip per 256 sources), then added into four chains in a fixed association — reproducible.
+// `touched` (optional): one byte per (source, cluster); a source that never accumulated into cluster `c` left its slot
+// unwritten, and the slot is read as zero (the fused pair kernel and the streaming update skip the zero-fill and the
+// write-back of the clusters a CTA never saw — most of a k x d partial on ordered data)
 template <typename S>
-__device__ __forceinline__ double strided_sum(const S* __restrict__ src, size_t stride, size_t e, int g, int n_src) {
+__device__ __forceinline__ double strided_sum(const S* __restrict__ src, size_t stride, size_t e, int g, int n_src,
+                                              const unsigned char* __restrict__ touched = nullptr, size_t touched_stride = 0, int c = 0) {
   double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
   for (int base = g; base < n_src; base += 16 * kFinGroups) {
     S v[16];
 #pragma unroll
     for (int q = 0; q < 16; ++q) {
       const int b = base + q * kFinGroups;
-      v[q] = (b < n_src) ? src[(size_t)b * stride + e] : S(0);
+      bool on = b < n_src;
+      if (on && touched != nullptr) on = touched[(size_t)b * touched_stride + c] != 0;
+      v[q] = on ? src[(size_t)b * stride + e] : S(0);
     }
 #pragma unroll
     for (int q = 0; q < 16; q += 4) { s0 += (double)v[q]; s1 += (double)v[q + 1]; s2 += (double)v[q + 2]; s3 += (double)v[q + 3]; }
@@ -545,7 +552,7 @@ __global__ void __launch_bounds__(kFinThreads) finalize_kernel(const FinalizeArg
   const int t = threadIdx.x, g = t / kFinElems, l = t % kFinElems;
   const int kd = a.k * a.d;
   const int e = blockIdx.x * kFinElems + l;
-  sh[g][l] = (e < kd) ? strided_sum<S>(a.src_sums, a.sum_stride, (size_t)e, g, a.n_src) : 0.0;
+  sh[g][l] = (e < kd) ? strided_sum<S>(a.src_sums, a.sum_stride, (size_t)e, g, a.n_src, a.src_touched, (size_t)a.k, e / a.d) : 0.0;
   // counts of the clusters this CTA's elements belong to
   const int c_lo = (blockIdx.x * kFinElems) / a.d;
   const int c_hi = (min(kd, (int)(blockIdx.x + 1) * kFinElems) - 1) / a.d;
@@ -636,6 +643,7 @@ template <typename F, typename S, typename CT> struct FinalizeXArgs {
   const double* src_inertia;
   size_t sum_stride, cnt_stride, inertia_stride;
   int n_src, n_src_inertia, k, d;
+  const unsigned char* src_touched;     // optional [n_src][k] (see strided_sum)
   int slices_per_cta;
   double* peer_out[8];                  // rank p's gather slot for THIS rank (this parity): [kd sums | k counts | inertia]
   unsigned long long* peer_flags[8];    // rank p's flags for THIS rank (this parity): [kFxMaxCtas]
@@ -679,7 +687,7 @@ __global__ void __launch_bounds__(kFinThreads) finalize_x_kernel(const FinalizeX
   // ---- phase A: local reduction, published to every rank ----
   for (int slice = s_lo; slice < s_hi; ++slice) {
     const int e = slice * kFinElems + l;
-    sh[g][l] = (e < kd) ? strided_sum<S>(a.src_sums, a.sum_stride, (size_t)e, g, a.n_src) : 0.0;
+    sh[g][l] = (e < kd) ? strided_sum<S>(a.src_sums, a.sum_stride, (size_t)e, g, a.n_src, a.src_touched, (size_t)a.k, e / a.d) : 0.0;
     const int c_lo = (slice * kFinElems) / a.d;
     const int c_hi = (min(kd, (slice + 1) * kFinElems) - 1) / a.d;
     const int c = c_lo + l;

@@ -47,6 +47,7 @@ struct Tc5Args {
   // whose rows did not all certify to one cluster (those go through update_rows_kernel)
   float* part_sums;         // [gridDim.x][k * d], zeroed by the kernel
   uint32_t* part_counts;    // [gridDim.x][k]
+  unsigned char* part_touched;   // [gridDim.x][k] or nullptr: clusters this CTA flushed; with it (k <= 1024) the sums are not zero-filled
   double* part_inertia;     // [gridDim.x]
   uint32_t* mixed_list;     // [gridDim.x][list_cap] tile indices
   uint32_t* mixed_count;    // [gridDim.x]
@@ -659,9 +660,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(FUSE ? t5_fuse_threa
     cmax_bits = 0;
   }
   for (int e = t; e < 1024 + 64; e += NT) reinterpret_cast<float4*>(b_bias)[e] = make_float4(0.f, 0.f, 0.f, 0.f);
+  // fused update: with a `touched` map (one bit per cluster in the lanes of every U warp, k <= 1024) the k x d partial is
+  // neither zero-filled here nor read where it was never written — on ordered rows a CTA sees two or three clusters
+  const bool sparse = FUSE && a.part_touched != nullptr && a.k <= 1024;
   if constexpr (FUSE) {
-    float4* ps4 = reinterpret_cast<float4*>(a.part_sums + (size_t)blockIdx.x * a.k * D);
-    for (int e = t; e < a.k * D / 4; e += NT) ps4[e] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (!sparse) {
+      float4* ps4 = reinterpret_cast<float4*>(a.part_sums + (size_t)blockIdx.x * a.k * D);
+      for (int e = t; e < a.k * D / 4; e += NT) ps4[e] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (a.part_touched != nullptr)
+        for (int e = t; e < a.k; e += NT) a.part_touched[(size_t)blockIdx.x * a.k + e] = 1;
+    }
     for (int e = t; e < a.k; e += NT) a.part_counts[(size_t)blockIdx.x * a.k + e] = 0u;
   }
   __syncthreads();
@@ -777,9 +785,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(FUSE ? t5_fuse_threa
       float* my_sums = a.part_sums + (size_t)blockIdx.x * a.k * D + feat;
       uint32_t* my_counts = a.part_counts + (size_t)blockIdx.x * a.k;
       uint32_t* my_list = a.mixed_list + (size_t)blockIdx.x * a.list_cap;
+      uint32_t seen_bits = 0u;   // lane l: clusters 32 l .. 32 l + 31 this CTA has flushed (identical in every U warp)
       auto flush = [&]() {
         if (cur_L != 0xFFFFFFFFu) {
-          my_sums[(size_t)cur_L * D] += cur_sum;
+          bool seen = true;
+          if (sparse) {
+            seen = (__shfl_sync(0xffffffffu, seen_bits, (int)(cur_L >> 5)) >> (cur_L & 31u)) & 1u;
+            if ((uint32_t)lane == (cur_L >> 5)) seen_bits |= 1u << (cur_L & 31u);
+          }
+          if (seen) my_sums[(size_t)cur_L * D] += cur_sum;
+          else my_sums[(size_t)cur_L * D] = cur_sum;
           if (u == 0 && lane == 0) my_counts[cur_L] += cur_cnt;
         }
       };
@@ -844,6 +859,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(FUSE ? t5_fuse_threa
       }
       for (unsigned long long v = my_pt >= 2 ? my_pt - 2 : 0; v < my_pt; ++v) consume(v);
       flush();
+      if (sparse && u == 0) {
+        unsigned char* tb = a.part_touched + (size_t)blockIdx.x * a.k;
+        for (int b = 0; b < 32; ++b) {
+          const int c = lane * 32 + b;
+          if (c < a.k) tb[c] = (unsigned char)((seen_bits >> b) & 1u);
+        }
+      }
       if (u == 0 && lane == 0) {
         a.mixed_count[blockIdx.x] = n_mixed;
         if (a.state != nullptr && n_mixed) atomicAdd(&a.state->mixed_tiles, (unsigned long long)n_mixed);

@@ -37,6 +37,7 @@ struct UpdArgs {
   const float* C;              // k x d, the centroids the labels were computed against (inertia)
   float* part_sums;            // [gridDim.x][k * d]
   uint32_t* part_counts;       // [gridDim.x][k]
+  unsigned char* part_touched; // [gridDim.x][k] or nullptr: with it only the rows of clusters this CTA met are written back
   double* part_inertia;        // [gridDim.y][gridDim.x]
   const LloydState* state;
   // list mode (behind the fused screening kernel): CTA b only visits the 128-row tiles tile_list[b * list_cap + i],
@@ -302,9 +303,11 @@ __global__ void __launch_bounds__(kUpdThreads, 1) update_rows_kernel(const UpdAr
   const size_t kd = (size_t)a.k * D;
   float* ps = a.part_sums + (size_t)blockIdx.x * kd + (size_t)chunk_base * D;
   for (int e = t; e < chunk_rows * D / 4; e += kUpdThreads)
-    reinterpret_cast<float4*>(ps)[e] = reinterpret_cast<const float4*>(acc)[e];
+    if (a.part_touched == nullptr || cnt[e / (D / 4)] != 0u) reinterpret_cast<float4*>(ps)[e] = reinterpret_cast<const float4*>(acc)[e];
   uint32_t* pc = a.part_counts + (size_t)blockIdx.x * a.k + chunk_base;
   for (int e = t; e < chunk_rows; e += kUpdThreads) pc[e] = cnt[e];
+  if (a.part_touched != nullptr)
+    for (int e = t; e < chunk_rows; e += kUpdThreads) a.part_touched[(size_t)blockIdx.x * a.k + chunk_base + e] = cnt[e] != 0u ? 1 : 0;
   if (t == 0) {
     double tot = 0.0;
     for (int e = 0; e < kUpdConsumers; ++e) tot += red[e];
