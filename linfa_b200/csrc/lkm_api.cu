@@ -1070,6 +1070,35 @@ static lkm_status run_lloyd(lkm_ctx* ctx, F* dC2, uint64_t k, uint64_t max_iter,
       // combine the per-CTA partials in fixed order, then the m_k-means update
       if (fin_fused) {
         // done inside lloyd_tc4_kernel
+      } else if (upd_partials && touched != nullptr && ctx->fin_cl && fin_src <= kFclMaxSrc && (ctx->world == 1 || use_p2p)) {
+        // sparse partials: cluster-wise combine (finalize_cl_kernel), with the NVLink exchange when row-sharded
+        FinalizeXArgs<F, F, uint32_t> xa{};
+        xa.src_sums = ctx->part_sums.as<F>(); xa.src_counts = ctx->part_counts.as<uint32_t>();
+        xa.src_inertia = ctx->part_inertia.as<double>();
+        xa.sum_stride = kd; xa.cnt_stride = k; xa.inertia_stride = 1; xa.n_src = fin_src; xa.n_src_inertia = fin_src_inertia;
+        xa.k = (int)k; xa.d = (int)d; xa.src_touched = touched;
+        const int g_max = std::min(kFxMaxCtas, 2 * ctx->sm_count);
+        xa.slices_per_cta = (int)((k + g_max - 1) / g_max);
+        const int xgrid = (int)((k + xa.slices_per_cta - 1) / xa.slices_per_cta);
+        xa.world = ctx->world;
+        if (ctx->world > 1) {
+          const unsigned long long epoch = ++ctx->p2p_epoch;
+          const size_t par = (size_t)(epoch & 1);
+          const size_t cap = ctx->p2p_cap, w = (size_t)ctx->world;
+          for (int pr = 0; pr < ctx->world; ++pr) {
+            double* base = reinterpret_cast<double*>(ctx->p2p_peer[pr]);
+            xa.peer_out[pr] = base + (par * w + (size_t)ctx->rank) * cap;
+            xa.peer_flags[pr] = reinterpret_cast<unsigned long long*>(base + 2 * w * cap) + (par * w + (size_t)ctx->rank) * kFxMaxCtas;
+          }
+          double* mine = reinterpret_cast<double*>(ctx->p2p_local);
+          xa.gather = mine + par * w * cap;
+          xa.my_flags = reinterpret_cast<const unsigned long long*>(mine + 2 * w * cap) + par * w * kFxMaxCtas;
+          xa.cap = cap; xa.epoch = epoch;
+        }
+        xa.C_old = Ccur; xa.C_new = Cnext; xa.counts_out = ctx->counts_out.as<double>();
+        xa.shift_part = ctx->shift_part.as<double>(); xa.state = dstate; xa.tol = tol; xa.max_iter = max_iter;
+        CK(launch_pdl(finalize_cl_kernel<F, F, uint32_t>, xgrid, kFinThreads, 0, ctx->stream, xa, true));
+        ctx->launches += 1;
       } else if (ctx->world == 1) {
         FinalizeArgs<F, F, uint32_t> fa{};
         fa.src_sums = ctx->part_sums.as<F>(); fa.src_counts = ctx->part_counts.as<uint32_t>();
@@ -2253,6 +2282,7 @@ LKM_EXPORT lkm_status lkm_create(lkm_ctx** out, int device) {
   if (const char* v = std::getenv("LKM_TC5")) ctx->tc5_enabled = std::atoi(v);
   if (const char* v = std::getenv("LKM_TC5_FUSE")) ctx->tc5_fuse = std::atoi(v);
   if (const char* v = std::getenv("LKM_DMMA")) ctx->dmma_enabled = std::atoi(v);
+  if (const char* v = std::getenv("LKM_FIN_CL")) ctx->fin_cl = std::atoi(v);
   if (const char* v = std::getenv("LKM_STEP_TRACE")) ctx->step_trace = std::atoi(v);
   if (const char* v = std::getenv("LKM_SPARSE_PARTIALS")) ctx->sparse_partials = std::atoi(v);
   if (const char* v = std::getenv("LKM_TC5_DEFER")) ctx->tc5_defer = std::atoi(v);

@@ -119,6 +119,7 @@ struct lkm_ctx {
   int step_trace = 0;
   std::vector<cudaEvent_t> trace_ev;
   std::vector<const char*> trace_name;
+  int fin_cl = 1;            // LKM_FIN_CL=0: slice-wise finalize kernels even when the partials are sparse
   int sparse_partials = 1;   // LKM_SPARSE_PARTIALS=0: the pair / update kernels zero-fill and write back whole k x d partials
   DevBuf part_touched;
   int dmma_enabled = 1;  // LKM_DMMA=0: f64 shapes with a large contraction stay on the CUDA-core kernels

@@ -781,6 +781,153 @@ __global__ void __launch_bounds__(kFinThreads) finalize_x_kernel(const FinalizeX
 }
 
 // ---------------------------------------------------------------------------
+// finalize_cl: the iteration tail for SPARSE partials (src_touched set: fused pair kernel + streaming update), on one
+// GPU or row-sharded.  The slice-wise kernels above give every thread ~n_src / 16 strided 4-byte loads in two dependent
+// rounds; with k * d = 32768 and 296 sources that is 2048 CTAs of latency chains (60-90 us measured on the cfg3 shape,
+// a quarter of a 1.25M-row step).  Here CTA b owns whole clusters: it compacts the sources that touched cluster c into a
+// list (ascending source order: reproducible), and thread j sums feature j over the list — coalesced 4 d-byte rows, all
+// loads of a cluster in flight at once.  Row-sharded: the CTA publishes its clusters' sums and counts to every rank
+// (NVLink stores), raises its flag, waits for the same CTA's flag of every rank, combines in rank order.
+// slices_per_cta is read as "clusters per CTA".
+// ---------------------------------------------------------------------------
+constexpr int kFclMaxSrc = 2048;
+
+template <typename F, typename S, typename CT>
+__global__ void __launch_bounds__(kFinThreads) finalize_cl_kernel(const FinalizeXArgs<F, S, CT> a) {
+  pdl_launch_dependents();
+  pdl_wait();
+  if (a.state->done) return;
+  __shared__ int list[kFclMaxSrc];
+  __shared__ int warp_tot[kFinThreads / 32];
+  __shared__ int n_list_s;
+  __shared__ double red[kFinThreads];
+  __shared__ double cnt_s;
+  __shared__ bool is_last;
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  const int kd = a.k * a.d;
+  const int c_lo = blockIdx.x * a.slices_per_cta, c_hi = min(a.k, c_lo + a.slices_per_cta);
+  double sq = 0.0;
+  for (int c = c_lo; c < c_hi; ++c) {
+    // ---- sources that touched cluster c, in ascending order ----
+    __syncthreads();
+    if (t == 0) n_list_s = 0;
+    __syncthreads();
+    for (int b0 = 0; b0 < a.n_src; b0 += kFinThreads) {
+      const int b = b0 + t;
+      const bool on = b < a.n_src && a.src_touched[(size_t)b * a.k + c] != 0;
+      const unsigned int m = __ballot_sync(0xffffffffu, on);
+      if (lane == 0) warp_tot[warp] = __popc(m);
+      __syncthreads();
+      int base = n_list_s;
+      for (int w = 0; w < warp; ++w) base += warp_tot[w];
+      if (on) list[base + __popc(m & ((1u << lane) - 1u))] = b;
+      __syncthreads();
+      if (t == 0) { int tot = 0; for (int w = 0; w < kFinThreads / 32; ++w) tot += warp_tot[w]; n_list_s += tot; }
+      __syncthreads();
+    }
+    const int nl = n_list_s;
+    if (t == 0) {
+      double cv = 0.0;
+      for (int i = 0; i < nl; ++i) cv += (double)a.src_counts[(size_t)list[i] * a.cnt_stride + c];
+      cnt_s = cv;
+      if (a.world > 1) for (int p = 0; p < a.world; ++p) a.peer_out[p][kd + c] = cv;
+      else a.counts_out[c] = cv;
+    }
+    __syncthreads();
+    for (int j = t; j < a.d; j += kFinThreads) {
+      const size_t e = (size_t)c * a.d + j;
+      double tot = 0.0;
+      int i = 0;
+      for (; i + 8 <= nl; i += 8) {
+        S v[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) v[q] = a.src_sums[(size_t)list[i + q] * a.sum_stride + e];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) tot += (double)v[q];
+      }
+      for (; i < nl; ++i) tot += (double)a.src_sums[(size_t)list[i] * a.sum_stride + e];
+      if (a.world > 1) {
+        for (int p = 0; p < a.world; ++p) a.peer_out[p][e] = tot;
+      } else {
+        const F oldv = a.C_old[e];
+        const F newv = (F)((tot + (double)oldv) / (cnt_s + 1.0));
+        a.C_new[e] = newv;
+        const double df = (double)(oldv - newv);
+        sq += df * df;
+      }
+    }
+  }
+  if (a.world > 1) {
+    if (blockIdx.x == 0) {
+      double v = 0.0;
+      const int n_in = a.n_src_inertia ? a.n_src_inertia : a.n_src;
+      for (int b = t; b < n_in; b += kFinThreads) v += a.src_inertia[(size_t)b * a.inertia_stride];
+      const double tot = block_sum(v, red);
+      if (t == 0)
+        for (int p = 0; p < a.world; ++p) a.peer_out[p][kd + a.k] = tot;
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (t < a.world) {
+      unsigned long long* f = a.peer_flags[t] + blockIdx.x;
+      asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(f), "l"(a.epoch) : "memory");
+    }
+    bool ok = true;
+    if (t < a.world) ok = wait_flag(a.my_flags + (size_t)t * kFxMaxCtas + blockIdx.x, a.epoch);
+    if (!ok) atomicOr(&a.state->fallback_rows, 1ull << 41);   // timeout marker, reported by the host
+    __syncthreads();
+    for (int c = c_lo; c < c_hi; ++c) {
+      double cntv = 0.0;
+      for (int r = 0; r < a.world; ++r) cntv += ((const volatile double*)a.gather)[(size_t)r * a.cap + kd + c];
+      if (t == 0) a.counts_out[c] = cntv;
+      for (int j = t; j < a.d; j += kFinThreads) {
+        const size_t e = (size_t)c * a.d + j;
+        double tot = 0.0;
+        for (int r = 0; r < a.world; ++r) tot += ((const volatile double*)a.gather)[(size_t)r * a.cap + e];
+        const F oldv = a.C_old[e];
+        const F newv = (F)((tot + (double)oldv) / (cntv + 1.0));
+        a.C_new[e] = newv;
+        const double df = (double)(oldv - newv);
+        sq += df * df;
+      }
+    }
+  }
+  const double sq_cta = block_sum(sq, red);
+  if (t == 0) {
+    a.shift_part[blockIdx.x] = sq_cta;
+    __threadfence();
+    const unsigned int prev = atomicAdd(&a.state->blocks_done, 1u);
+    is_last = (prev == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  if (a.world > 1 && t < a.world && !wait_flag(a.my_flags + (size_t)t * kFxMaxCtas, a.epoch)) atomicOr(&a.state->fallback_rows, 1ull << 41);
+  __syncthreads();
+  double v = 0.0;
+  for (int b = t; b < (int)gridDim.x; b += kFinThreads) v += ((volatile double*)a.shift_part)[b];
+  const double shift_sq = block_sum(v, red);
+  double inertia = 0.0;
+  if (a.world == 1) {
+    v = 0.0;
+    const int n_in = a.n_src_inertia ? a.n_src_inertia : a.n_src;
+    for (int b = t; b < n_in; b += kFinThreads) v += a.src_inertia[(size_t)b * a.inertia_stride];
+    inertia = block_sum(v, red);
+  }
+  if (t == 0) {
+    if (a.world > 1)
+      for (int r = 0; r < a.world; ++r) inertia += ((const volatile double*)a.gather)[(size_t)r * a.cap + kd + a.k];
+    const F shift = (F)sqrt(shift_sq);  // L2Dist::distance: sqrt in f64, cast to F
+    a.state->shift = (double)shift;
+    a.state->inertia = inertia;
+    const unsigned long long it = a.state->n_iter + 1;
+    a.state->n_iter = it;
+    a.state->blocks_done = 0u;
+    if (shift < (F)a.tol || it >= a.max_iter) a.state->done = 1;
+  }
+}
+
+// ---------------------------------------------------------------------------
 // small utilities
 // ---------------------------------------------------------------------------
 template <typename F>

@@ -119,6 +119,17 @@ __global__ void __launch_bounds__(kUpdThreads, 1) update_rows_kernel(const UpdAr
     return listed ? (unsigned long long)my_list[j / SPT] * SPT + (j % SPT) : j;
   };
 
+  if (listed && j1 == 0) {
+    // nothing listed for this CTA (the rule behind the fused pair kernel on ordered rows): publish an empty partial
+    uint32_t* pc0 = a.part_counts + (size_t)blockIdx.x * a.k + chunk_base;
+    for (int e = t; e < chunk_rows; e += kUpdThreads) {
+      pc0[e] = 0u;
+      if (a.part_touched != nullptr) a.part_touched[(size_t)blockIdx.x * a.k + chunk_base + e] = 0;
+      else for (int j = 0; j < D; ++j) a.part_sums[(size_t)blockIdx.x * a.k * D + (size_t)(chunk_base + e) * D + j] = 0.f;
+    }
+    if (t == 0) a.part_inertia[(size_t)blockIdx.y * gridDim.x + blockIdx.x] = 0.0;
+    return;
+  }
   if (t == 0) {
     for (int s = 0; s < kUpdMaxStages; ++s) {
       tc::mbar_init(&bar_full[s], 1);
