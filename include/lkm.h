@@ -70,7 +70,11 @@ typedef enum lkm_algorithm { LKM_ALGO_LLOYD = 0, LKM_ALGO_HAMERLY = 1 } lkm_algo
  * EXACT reproduces rand 0.8.5 WeightedIndex bit for bit (sequential prefix sum
  * in F on one GPU thread) — same row indices as the reference for the same
  * RNG.  FAST uses a fixed-order parallel f64 scan with the same uniform draw. */
-typedef enum lkm_pick_mode { LKM_PICK_EXACT = 0, LKM_PICK_FAST = 1 } lkm_pick_mode;
+typedef enum lkm_pick_mode { LKM_PICK_EXACT = 0, LKM_PICK_FAST = 1, LKM_PICK_AUTO = 2 } lkm_pick_mode;
+/* Cost of EXACT: every pick walks the n weights on ONE GPU thread (that is what makes the prefix sum the reference's,
+ * bit for bit): about 1 ms per million weights and pick, i.e. k * n / 1e9 seconds per seeding — fine for the reference's
+ * own problem sizes, hours for 100M rows x 1024 clusters.  AUTO uses EXACT up to 2^22 weights and FAST above; the
+ * bindings default to EXACT so that small fits reproduce linfa's seeds, and say so in their docs. */
 
 /* Trampolines into the caller's `R: Rng` (KM/hyperparams.rs:37 `rng: R`).
  * The reference clones the rng at the top of every fit (KM/algorithm.rs:298);

@@ -79,7 +79,7 @@ NOT_CONVERGED, ERR_CUDA, ERR_NCCL, ERR_NO_DATA, ERR_UNSUPPORTED = 20, 30, 31, 32
 
 INIT_RANDOM, INIT_PRECOMPUTED, INIT_KMEANS_PLUSPLUS, INIT_KMEANS_PARA = 0, 1, 2, 3
 ALGO_LLOYD, ALGO_HAMERLY = 0, 1
-PICK_EXACT, PICK_FAST = 0, 1
+PICK_EXACT, PICK_FAST, PICK_AUTO = 0, 1, 2
 
 # every symbol include/lkm.h declares (tests check that the library exports them all)
 UNTYPED_SYMBOLS = [

@@ -1428,6 +1428,8 @@ static lkm_status gather_rows(lkm_ctx* ctx, const F* dX, uint64_t d, const std::
 // returns the picked index, or -1 where WeightedIndex::new errors.
 template <typename F>
 static lkm_status weighted_pick(lkm_ctx* ctx, const F* dW, uint64_t n, HostRng& rng, int pick_mode, long long& picked) {
+  // AUTO: the bit-exact sequential prefix (one GPU thread walking n weights per pick) up to 2^22 weights, the parallel scan above
+  if (pick_mode == LKM_PICK_AUTO) pick_mode = n <= (1ull << 22) ? LKM_PICK_EXACT : LKM_PICK_FAST;
   if (n == 0) { picked = -1; return LKM_OK; }
   if (pick_mode == LKM_PICK_EXACT) {
     CK(ctx->cum.ensure(std::max<uint64_t>(n, 2) * sizeof(F)));
@@ -1555,8 +1557,19 @@ static lkm_status kmeans_para(lkm_ctx* ctx, const F* dX, uint64_t n, uint64_t d,
   std::vector<double> parts(1024);
   for (uint64_t r = 0; r < n_rounds && !full; ++r) {
     // running min against the candidates added since the last round
-    if (n_cand > scanned)
-      CKS(run_assign<F>(ctx, dX, n, d, dCand + scanned * d, n_cand - scanned, nullptr, dD, scanned > 0 ? 1 : 0, nullptr, nullptr));
+    if (n_cand > scanned) {
+      const uint64_t fresh = n_cand - scanned;
+      if (ctx->para_rows && fresh >= 8 && ctx->force_path != 0) {
+        // thread = row, the row in registers, FMA scores with the certificate, exact distance of the winner: the same bits
+        // as the exact scan at a fraction of its cost (rows_top2_kernel over ALL rows)
+        RowsArgs<F> ra{};
+        ra.X = dX; ra.n = n; ra.d = (int)d; ra.k = (int)fresh; ra.C = dCand + scanned * d; ra.all_rows = n;
+        ra.best_dist = dD; ra.min_combine = scanned > 0 ? 1 : 0;
+        CKS(launch_rows<F>(ctx, ra, n));
+      } else {
+        CKS(run_assign<F>(ctx, dX, n, d, dCand + scanned * d, fresh, nullptr, dD, scanned > 0 ? 1 : 0, nullptr, nullptr));
+      }
+    }
     scanned = n_cand;
     const uint64_t seed = range_incl_u64(rng, 0, 0xFFFFFFFFFFFFFFFEULL);
     sum_f64_kernel<F><<<1024, 256, 0, ctx->stream>>>(dD, n, ctx->part_inertia.as<double>());
@@ -1578,10 +1591,15 @@ static lkm_status kmeans_para(lkm_ctx* ctx, const F* dX, uint64_t n, uint64_t d,
     sel.resize(got);
     if (got) CK(cudaMemcpy(sel.data(), ctx->idxbuf.p, (size_t)got * 8, cudaMemcpyDeviceToHost));
     std::sort(sel.begin(), sel.end());  // the reference collects in ascending row order
-    for (unsigned long long idx : sel) {
-      CK(cudaMemcpyAsync(dCand + n_cand * d, dX + idx * d, d * sizeof(F), cudaMemcpyDeviceToDevice, ctx->stream));
-      n_cand += 1;
-      if (n_cand >= cap) { full = true; break; }
+    {
+      // one gather launch for the round's candidates (not one copy per row)
+      std::vector<long long> take;
+      for (unsigned long long idx : sel) {
+        take.push_back((long long)idx);
+        if (n_cand + take.size() >= cap) { full = true; break; }
+      }
+      if (!take.empty()) CKS(gather_rows<F>(ctx, dX, d, take, dCand + n_cand * d));
+      n_cand += take.size();
     }
   }
   // weights = cluster_membership_counts (KM/init.rs:273-285): histogram of the
@@ -1701,6 +1719,11 @@ static lkm_status fetch_global_row(lkm_ctx* ctx, const ShardMap& sm, uint64_t g,
 template <typename F>
 static lkm_status weighted_pick_sharded(lkm_ctx* ctx, const ShardMap& sm, const F* dW, HostRng& rng, int pick_mode,
                                         long long& picked) {
+  {
+    uint64_t n_all = 0;
+    for (uint64_t v : sm.n) n_all += v;
+    if (pick_mode == LKM_PICK_AUTO) pick_mode = n_all <= (1ull << 22) ? LKM_PICK_EXACT : LKM_PICK_FAST;
+  }
   const uint64_t n = ctx->n;
   const int world = ctx->world, rank = ctx->rank;
   std::vector<unsigned char> all;
@@ -2293,6 +2316,7 @@ LKM_EXPORT lkm_status lkm_create(lkm_ctx** out, int device) {
   if (const char* v = std::getenv("LKM_FLUSH_SWEEP")) g_flush_sweep = std::atoi(v);
   if (const char* v = std::getenv("LKM_F64S")) ctx->f64s_enabled = std::atoi(v);
   if (const char* v = std::getenv("LKM_PARA_TC")) ctx->para_tc = std::atoi(v);
+  if (const char* v = std::getenv("LKM_PARA_ROWS")) ctx->para_rows = std::atoi(v);
   if (const char* v = std::getenv("LKM_FUSED_FINALIZE")) ctx->fused_finalize = std::atoi(v);
   if (const char* v = std::getenv("LKM_F64S_PACKED")) ctx->f64s_packed = std::atoi(v);
   if (const char* v = std::getenv("LKM_F64S_RPT")) ctx->f64s_rpt = std::atoi(v) == 1 ? 1 : 2;

@@ -137,7 +137,9 @@ struct lkm_ctx {
   uint64_t kept_labels_n = 0;
   int blob_shuffled = 0;   // lkm_set_blob_layout
   DevBuf flushbuf, fin_sync, para_c2;
-  int para_tc = 0;       // LKM_PARA_TC=1: k-means|| candidate histogram through one tensor-core Lloyd iteration (measured slower on the cfg4 shard: 6.4 vs 5.9 s)
+  int para_tc = 1;       // LKM_PARA_TC=0: k-means|| candidate histogram through the exact CUDA-core assignment instead of one tensor-core
+                         // Lloyd iteration (same seeds; with the deferred re-scans the tensor-core route is faster: 4M x 128: 1147 -> 730 ms)
+  int para_rows = 1;     // LKM_PARA_ROWS=0: k-means|| running minimum through lloyd_kernel<MODE_ASSIGN> instead of rows_top2_kernel
   std::vector<cudaEvent_t> iter_events;
   // workspaces
   DevBuf tca_bsplit, tca_cn, tca_cmax;

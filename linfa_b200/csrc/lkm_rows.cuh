@@ -31,6 +31,7 @@ template <typename F> struct RowsArgs {
   int kc;                           // centroids per shared-memory chunk
   uint32_t* labels;                 // out: label of every visited row (in: its previous label when fx_sums is set)
   F* best_dist;                     // out (optional): min squared distance, direct form, per visited row
+  int min_combine;                  // best_dist = min(best_dist, new) (running minimum of the seeding rounds, KM/init.rs:138-143)
   F* ub;                            // out (optional): Hamerly upper bound (distance to the winner)
   F* lb;                            // out (optional): Hamerly lower bound (distance to the runner-up)
   long long* fx_sums;               // optional: [k][d] fixed-point running sums, moved from the old to the new label
@@ -194,9 +195,11 @@ __global__ void __launch_bounds__(kRowsThreads) rows_top2_kernel(const RowsArgs<
       if constexpr (D > 0) bd = sqdist_reg<F, D>(a.C + (size_t)bi * D, x);
       else bd = sqdist_mem<F>(a.C + (size_t)bi * d, xp, d);
     }
-    const uint32_t old = a.labels[row];
-    a.labels[row] = (uint32_t)bi;
-    if (a.best_dist != nullptr) a.best_dist[row] = bd;
+    const uint32_t old = a.labels != nullptr ? a.labels[row] : 0u;
+    if (a.labels != nullptr) a.labels[row] = (uint32_t)bi;
+    if (a.best_dist != nullptr) {
+      if (!a.min_combine || bd < a.best_dist[row]) a.best_dist[row] = bd;
+    }
     if (a.ub != nullptr) {
       // bounds must bound the TRUE distances: the direct form is within (d + 2) eps of them
       const F slack = (dd + (F)4) * eps;

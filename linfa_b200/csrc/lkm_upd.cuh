@@ -194,7 +194,8 @@ __global__ void __launch_bounds__(kUpdThreads, 1) update_rows_kernel(const UpdAr
       uint32_t m = __ballot_sync(0xffffffffu, mine);
       if (m == 0u) continue;
       // rows of this warp with the same cluster; rank = position of the row among them
-      const uint32_t peers = __match_any_sync(0xffffffffu, mine ? c : (0x80000000u | (uint32_t)lane));
+      // (one key for all the other lanes: MATCH.ANY walks the distinct keys one by one)
+      const uint32_t peers = __match_any_sync(0xffffffffu, mine ? c : 0xFFFFFFFFu);
       const int rank = __popc(peers & lt_mask);
       const uint32_t leaders = __ballot_sync(0xffffffffu, mine && rank == 0);
       if (__popc(leaders) > 4) {

@@ -183,8 +183,9 @@ class KMeansAlgorithm:
 
 class PickMode:
     """Not in the reference: how the k-means++ weighted pick walks its prefix sum (include/lkm.h)."""
-    Exact = _ffi.PICK_EXACT
-    Fast = _ffi.PICK_FAST
+    Exact = _ffi.PICK_EXACT   # rand 0.8.5 WeightedIndex bit for bit (one GPU thread per pick: ~1 ms per million rows and pick)
+    Fast = _ffi.PICK_FAST     # fixed-order parallel scan, same uniform draw
+    Auto = _ffi.PICK_AUTO     # Exact up to 2^22 rows, Fast above
 
 
 # ---- device context ---------------------------------------------------------

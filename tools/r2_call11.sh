@@ -1,0 +1,7 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests/test_gpu_rowwise.py tests/test_gpu_parity.py tests/test_gpu_fullsize.py -m gpu -q -x > gpurun_out/r2m_pytest.log 2>&1; echo "pytest rc=$?"; tail -6 gpurun_out/r2m_pytest.log
+echo "== cfg3 hashed 2M"; LKM_STEP_TRACE=1 WL=cfg3 ROWS=2000000 HASHED=1 ITERS=10 python tools/r2_probe.py 2>&1 | tail -6
+echo "== cfg3 blob 2M nofuse"; LKM_TC5_FUSE=0 LKM_STEP_TRACE=1 WL=cfg3 ROWS=2000000 ITERS=10 python tools/r2_probe.py 2>&1 | tail -6
+echo "== cfg4 hashed"; LKM_STEP_TRACE=1 WL=cfg4 ROWS=1562500 HASHED=1 ITERS=10 python tools/r2_probe.py 2>&1 | tail -6
+echo "== cfg3 kpp 2M"; LKM_STEP_TRACE=1 WL=cfg3 ROWS=2000000 KPP=1 ITERS=10 python tools/r2_probe.py 2>&1 | tail -6
