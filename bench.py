@@ -20,7 +20,8 @@ partials are exchanged over NVLink and combined in rank order on every rank.
   config.other_workloads: the other BASELINE configs in the same run and JSON line — cfg2 (1M x 32, k=64),
              cfg4 shard (12.5M x 64, k=1024 per GPU = the 100M config at N=8), cfg5 shard (125M x 8 f64, k=16
              per GPU = the 1B config at N=8), each weak-scaled (fixed rows per GPU), plus the headline shape
-             with hashed (unordered) rows and from a k-means++ start
+             with hashed (unordered) rows, from a k-means++ start, under KMeansAlgorithm::Hamerly, and an f64
+             shape on the FP64 tensor pipe (DMMA)
 """
 import argparse
 import ctypes as C
@@ -51,7 +52,7 @@ WORKLOAD_TEXT = {
     "cfg1": "KMeans k=3 on 10k x 2 f64 blobs (BASELINE configs[0]); step = 1 Lloyd iteration",
 }
 KERNELS = {
-    "cfg3": "assign_tc5s_kernel<128,true,256> (CTA-pair tcgen05 screening assignment with the fused update; listed tiles through update_rows_kernel<128>)",
+    "cfg3": "assign_tc5s_kernel<128,true,256> (CTA-pair tcgen05 screening assignment with the fused update; undecided rows through rows_top2_kernel, listed tiles through update_rows_kernel<128>, finalize_cl_kernel)",
     "cfg2": "lloyd_tc4_kernel<64,1> (fused assign+update, warp-specialised tcgen05 pipeline)",
     "cfg4": "4 x assign_tc5s_kernel<64,*,256> (one launch per 256 centroids, the last one with the fused update)",
     "cfg5": "lloyd_f64s_kernel<8,true,2> (f32-screened fused assign+update for f64 rows)",
@@ -382,6 +383,39 @@ class Runner:
         return out
 
 
+def side_hamerly(R, steps):
+    """Hamerly (KM/algorithm.rs:248-291) on the headline shape from a k-means++ start, next to Lloyd from the same start:
+    device time per iteration of both, and how many rows the bounds let the iterations skip."""
+    lb = R.lb
+    n, n_total, d, k, dtype, centres = R.generate("cfg3")
+    p = lb.KMeans.params_with_rng(k, lb.Xoshiro256Plus.seed_from_u64(40)).n_runs(1).pick_mode(lb.PickMode.Fast).check()
+    c0 = p.init_centroids_resident(R.ctx)
+    iters = max(steps, 20)
+    R.ctx.hamerly_iters(c0, 3, 0.0)
+    _, _, _, st = R.ctx.hamerly_iters(c0, iters, 0.0)
+    _, _, _, sl = R.ctx.lloyd_iters(c0, iters, 0.0)
+    return {"workload": WORKLOAD_TEXT["cfg3"] + " — KMeansAlgorithm::Hamerly, k-means++ (fast pick) start", "rows_per_gpu": n, "d": d, "k": k,
+            "iterations": int(st.n_iter), "value": n * int(st.n_iter) / (float(st.device_ms) * 1e-3), "unit": "samples*iter/s",
+            "ms_per_step": float(st.device_ms) / int(st.n_iter), "lloyd_ms_per_step_same_start": float(sl.device_ms) / int(sl.n_iter),
+            "rows_scanned_per_iteration": int(st.rows_scanned) / max(int(st.n_iter) - 1, 1),
+            "rows_tightened_per_iteration": int(st.rows_tightened) / max(int(st.n_iter) - 1, 1), "gpu_launches": int(st.kernel_launches)}
+
+
+def side_dmma(R, steps):
+    """f64 with a large contraction (north_star: DMMA for f64): 2M x 64 f64, k = 256, Lloyd iterations on the FP64 tensor pipe."""
+    n, d, k = 2_000_000, 64, 256
+    centres = centres_for(k, d, np.float64)
+    R.ctx.gen_blobs(n, d, centres, 1.0, seed=2024)
+    c0 = start_centroids(centres)
+    R.ctx.lloyd_iters(c0, 3, 0.0)
+    _, _, _, st = R.ctx.lloyd_iters(c0, max(steps // 2, 5), 0.0)
+    it = int(st.n_iter)
+    ms = float(st.device_ms) / it
+    return {"workload": "KMeans k=256 on 2M x 64 f64 blobs (f64, large k*d): assign_dmma_kernel + update", "rows_per_gpu": n, "d": d, "k": k,
+            "dtype": "f64", "value": n * it / (float(st.device_ms) * 1e-3), "unit": "samples*iter/s", "ms_per_step": ms,
+            "assign_path": int(st.assign_path), "fp64_tflops_2nkd": 2.0 * n * k * d / (ms * 1e-3) / 1e12, "gpu_launches": int(st.kernel_launches)}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -474,6 +508,12 @@ def main():
                 others[name] = R.side(wl, s2, w2, shuffled=sh, kmeanspp_start=kpp)
             except Exception as e:  # a side workload must not take the headline down
                 others[name] = {"error": repr(e)}
+        if world == 1:
+            for name, fn in (("cfg3_hamerly", side_hamerly), ("f64_dmma", side_dmma)):
+                try:
+                    others[name] = fn(R, s2)
+                except Exception as e:
+                    others[name] = {"error": repr(e)}
 
     # ---- CPU baseline (rank 0, N = 1 only) ----
     cpu = None
