@@ -1097,6 +1097,7 @@ static lkm_status run_lloyd(lkm_ctx* ctx, F* dC2, uint64_t k, uint64_t max_iter,
         }
         xa.C_old = Ccur; xa.C_new = Cnext; xa.counts_out = ctx->counts_out.as<double>();
         xa.shift_part = ctx->shift_part.as<double>(); xa.state = dstate; xa.tol = tol; xa.max_iter = max_iter;
+        if (ctx->step_trace) { CK(ctx->t4prof.ensure(64)); xa.prof = ctx->t4prof.as<unsigned long long>(); }
         CK(launch_pdl(finalize_cl_kernel<F, F, uint32_t>, xgrid, kFinThreads, 0, ctx->stream, xa, true));
         ctx->launches += 1;
       } else if (ctx->world == 1) {
@@ -1247,6 +1248,14 @@ static lkm_status run_lloyd(lkm_ctx* ctx, F* dC2, uint64_t k, uint64_t max_iter,
                    hp[r * 8 + 2], hp[r * 8 + 3], hp[r * 8 + 4], hp[r * 8 + 7]);
   }
 #endif
+  if (ctx->step_trace && ctx->t4prof.p != nullptr && ctx->t4prof.cap >= 64) {
+    unsigned long long hp[8] = {0};
+    cudaMemcpy(hp, ctx->t4prof.p, 56, cudaMemcpyDeviceToHost);
+    if (hp[0] && hp[6] >= hp[0])
+      std::fprintf(stderr, "step_trace finalize_cl (last iteration, CTA 0, ns from its start): reduced+published %lld fenced %lld peers' flags seen %lld combined %lld | last CTA at %lld done %lld\n",
+                   (long long)(hp[1] - hp[0]), (long long)(hp[2] - hp[0]), (long long)(hp[3] - hp[0]), (long long)(hp[4] - hp[0]),
+                   (long long)(hp[5] - hp[0]), (long long)(hp[6] - hp[0]));
+  }
   trace_report(ctx);
   out.inertia = ctx->h_state->inertia;
   out.shift = ctx->h_state->shift;

@@ -644,6 +644,7 @@ template <typename F, typename S, typename CT> struct FinalizeXArgs {
   size_t sum_stride, cnt_stride, inertia_stride;
   int n_src, n_src_inertia, k, d;
   const unsigned char* src_touched;     // optional [n_src][k] (see strided_sum)
+  unsigned long long* prof;             // LKM_STEP_TRACE: CTA 0 stamps %globaltimer at its phase boundaries (8 slots)
   int slices_per_cta;
   double* peer_out[8];                  // rank p's gather slot for THIS rank (this parity): [kd sums | k counts | inertia]
   unsigned long long* peer_flags[8];    // rank p's flags for THIS rank (this parity): [kFxMaxCtas]
@@ -807,6 +808,8 @@ __global__ void __launch_bounds__(kFinThreads) finalize_cl_kernel(const Finalize
   const int kd = a.k * a.d;
   const int c_lo = blockIdx.x * a.slices_per_cta, c_hi = min(a.k, c_lo + a.slices_per_cta);
   double sq = 0.0;
+  const bool stamp = a.prof != nullptr && blockIdx.x == 0 && t == 0;
+  if (stamp) a.prof[0] = global_ns();
   for (int c = c_lo; c < c_hi; ++c) {
     // ---- sources that touched cluster c, in ascending order ----
     __syncthreads();
@@ -866,8 +869,10 @@ __global__ void __launch_bounds__(kFinThreads) finalize_cl_kernel(const Finalize
       if (t == 0)
         for (int p = 0; p < a.world; ++p) a.peer_out[p][kd + a.k] = tot;
     }
+    if (stamp) a.prof[1] = global_ns();
     __threadfence_system();
     __syncthreads();
+    if (stamp) a.prof[2] = global_ns();
     if (t < a.world) {
       unsigned long long* f = a.peer_flags[t] + blockIdx.x;
       asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(f), "l"(a.epoch) : "memory");
@@ -876,6 +881,7 @@ __global__ void __launch_bounds__(kFinThreads) finalize_cl_kernel(const Finalize
     if (t < a.world) ok = wait_flag(a.my_flags + (size_t)t * kFxMaxCtas + blockIdx.x, a.epoch);
     if (!ok) atomicOr(&a.state->fallback_rows, 1ull << 41);   // timeout marker, reported by the host
     __syncthreads();
+    if (stamp) a.prof[3] = global_ns();
     for (int c = c_lo; c < c_hi; ++c) {
       double cntv = 0.0;
       for (int r = 0; r < a.world; ++r) cntv += ((const volatile double*)a.gather)[(size_t)r * a.cap + kd + c];
@@ -893,6 +899,7 @@ __global__ void __launch_bounds__(kFinThreads) finalize_cl_kernel(const Finalize
     }
   }
   const double sq_cta = block_sum(sq, red);
+  if (stamp) a.prof[4] = global_ns();
   if (t == 0) {
     a.shift_part[blockIdx.x] = sq_cta;
     __threadfence();
@@ -901,6 +908,7 @@ __global__ void __launch_bounds__(kFinThreads) finalize_cl_kernel(const Finalize
   }
   __syncthreads();
   if (!is_last) return;
+  if (a.prof != nullptr && t == 0) a.prof[5] = global_ns();
   __threadfence();
   if (a.world > 1 && t < a.world && !wait_flag(a.my_flags + (size_t)t * kFxMaxCtas, a.epoch)) atomicOr(&a.state->fallback_rows, 1ull << 41);
   __syncthreads();
@@ -924,6 +932,7 @@ __global__ void __launch_bounds__(kFinThreads) finalize_cl_kernel(const Finalize
     a.state->n_iter = it;
     a.state->blocks_done = 0u;
     if (shift < (F)a.tol || it >= a.max_iter) a.state->done = 1;
+    if (a.prof != nullptr) a.prof[6] = global_ns();
   }
 }
 

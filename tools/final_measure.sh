@@ -1,19 +1,15 @@
-# Round-1 closing measurements (run under gpurun): full GPU test suite, bench lines, launch lists, ncu captures of the dominant kernels.
-set -x
-P=r1c
-(time python -m pytest tests -x -q -m gpu) > gpurun_out/${P}_pytest_gpu.log 2>&1
-tail -3 gpurun_out/${P}_pytest_gpu.log
-python __graft_entry__.py --smoke > gpurun_out/${P}_smoke.log 2>&1; tail -1 gpurun_out/${P}_smoke.log
-python bench.py > gpurun_out/${P}_bench_cfg2.json 2> gpurun_out/${P}_bench_cfg2.err
-python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/${P}_bench_reference.json 2>/dev/null
-for w in cfg3 cfg4 cfg5 cfg1; do python bench.py --workload $w --steps 5 --warmup 3 --no-cpu-baseline --no-e2e --no-init > gpurun_out/${P}_bench_$w.json 2>/dev/null; done
-# launch lists (each after its plain run has exited 0)
-python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/${P}_plain_cfg2.log 2>&1 && \
-ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/${P}_launches_cfg2.csv python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/${P}_ncu_cfg2.log 2>&1
-python bench.py --workload cfg5 --steps 3 --warmup 3 --no-cpu-baseline --no-e2e --no-init > gpurun_out/${P}_plain_cfg5.log 2>&1 && \
-ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/${P}_launches_cfg5.csv python bench.py --workload cfg5 --steps 3 --warmup 3 --no-cpu-baseline --no-e2e --no-init > gpurun_out/${P}_ncu_cfg5.log 2>&1
-# full captures of the dominant kernels
-ncu --set full --clock-control none --import-source on -k regex:lloyd_f64s -s 2 -c 1 -o gpurun_out/${P}_prof_cfg5 python bench.py --workload cfg5 --steps 1 --warmup 3 --no-cpu-baseline --no-e2e --no-init > gpurun_out/${P}_ncu_cfg5s.log 2>&1
-python tools/cfg2_run.py > gpurun_out/${P}_plain_cfg2s.log 2>&1 && \
-ncu --set full --clock-control none --import-source on -k regex:lloyd_tc4 -s 3 -c 2 -o gpurun_out/${P}_prof_cfg2 python tools/cfg2_run.py > gpurun_out/${P}_ncu_cfg2s.log 2>&1
-tail -c 700 gpurun_out/${P}_bench_cfg2.json
+# Round-2 closing measurements (run under gpurun): full GPU test suite, smoke, bench lines, launch list, ncu captures.
+P=r2
+mkdir -p gpurun_out
+(time python -m pytest tests -q -m gpu) > gpurun_out/${P}_pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -3 gpurun_out/${P}_pytest_gpu.log
+python __graft_entry__.py --smoke > gpurun_out/${P}_smoke.log 2>&1; echo "smoke rc=$?"; tail -1 gpurun_out/${P}_smoke.log
+python bench.py > gpurun_out/${P}_bench_default.json 2> gpurun_out/${P}_bench_default.err; echo "bench rc=$?"
+python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/${P}_bench_reference.json 2>/dev/null; echo "reference rc=$?"
+# launch list of the headline command (after the plain run exited 0); shares, not absolutes
+python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-e2e --no-others --no-init > gpurun_out/${P}_plain_cfg3.log 2>&1 && \
+ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/${P}_launches_cfg3.csv python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-e2e --no-others --no-init > gpurun_out/${P}_ncu_cfg3.log 2>&1
+python tools/launch_summary.py gpurun_out/${P}_launches_cfg3.csv > gpurun_out/${P}_launch_summary_cfg3.txt; cat gpurun_out/${P}_launch_summary_cfg3.txt
+# full capture of the dominant kernel (DRAM traffic per launch, pipe utilisation)
+WL=cfg3 ITERS=3 python tools/r2_probe.py > gpurun_out/${P}_plain_probe.log 2>&1 && \
+WL=cfg3 ITERS=3 ncu --set full --clock-control none --import-source on -k regex:assign_tc5s -s 3 -c 1 -f -o gpurun_out/${P}_prof_cfg3 python tools/r2_probe.py > gpurun_out/${P}_ncu_cfg3s.log 2>&1
+ls -la gpurun_out/${P}_prof_cfg3.ncu-rep
