@@ -401,6 +401,22 @@ def side_hamerly(R, steps):
             "rows_tightened_per_iteration": int(st.rows_tightened) / max(int(st.n_iter) - 1, 1), "gpu_launches": int(st.kernel_launches)}
 
 
+def side_predict(R, steps):
+    """PredictInplace + Transformer (KM/algorithm.rs:718-777) on the resident headline matrix: labels and min squared distances of
+    every row, read back to the host (wall clock: the call a user makes)."""
+    n, n_total, d, k, dtype, centres = R.generate("cfg3")
+    c = start_centroids(centres)
+    R.ctx.assign(c, None)
+    t0 = time.perf_counter()
+    reps = 3
+    for _ in range(reps):
+        labels, dists = R.ctx.assign(c, None)
+    dt = (time.perf_counter() - t0) / reps
+    return {"workload": WORKLOAD_TEXT["cfg3"] + " — update_memberships_and_dists on the resident rows, labels (u64) and distances read back",
+            "rows_per_gpu": n, "d": d, "k": k, "value": n / dt, "unit": "samples/s", "ms_per_call": 1e3 * dt,
+            "d2h_bytes_per_call": int(n * (8 + np.dtype(dtype).itemsize))}
+
+
 def side_dmma(R, steps):
     """f64 with a large contraction (north_star: DMMA for f64): 2M x 64 f64, k = 256, Lloyd iterations on the FP64 tensor pipe."""
     n, d, k = 2_000_000, 64, 256
@@ -509,7 +525,7 @@ def main():
             except Exception as e:  # a side workload must not take the headline down
                 others[name] = {"error": repr(e)}
         if world == 1:
-            for name, fn in (("cfg3_hamerly", side_hamerly), ("f64_dmma", side_dmma)):
+            for name, fn in (("cfg3_hamerly", side_hamerly), ("cfg3_predict", side_predict), ("f64_dmma", side_dmma)):
                 try:
                     others[name] = fn(R, s2)
                 except Exception as e:

@@ -222,9 +222,22 @@ template <typename F> static lkm_status plan_fused(lkm_ctx* ctx, const void* X, 
 }
 
 template <typename F>
+static lkm_status launch_rows(lkm_ctx* ctx, RowsArgs<F>& a, uint64_t max_rows);
+
+template <typename F>
 static lkm_status run_assign(lkm_ctx* ctx, const F* dX, uint64_t n, uint64_t d, const F* dC, uint64_t k, uint32_t* labels,
                              F* dists, int min_combine, const F* weights, F* wdists) {
   if (n == 0) return LKM_OK;
+  // wide rows (no compile-time-d instance of lloyd_kernel): thread = row with the row in registers, FMA scores + certificate,
+  // exact scan where it fails, winner's distance in the direct form — the same labels and the same bits as the exact scan
+  // (rows_top2_kernel over all rows); predict / transform / assign and the seeding passes over several centroids take this
+  if (ctx->rows_assign && ctx->force_path != 0 && weights == nullptr && wdists == nullptr && k >= 8 && n < (1ull << 32) &&
+      (d == 64 || (d == 128 && sizeof(F) == 4)) && (reinterpret_cast<uintptr_t>(dX) & 15) == 0) {
+    RowsArgs<F> ra{};
+    ra.X = dX; ra.n = n; ra.d = (int)d; ra.k = (int)k; ra.C = dC; ra.all_rows = n;
+    ra.labels = labels; ra.best_dist = dists; ra.min_combine = min_combine;
+    return launch_rows<F>(ctx, ra, n);
+  }
   Plan p;
   CKS(plan_assign<F>(ctx, dX, n, d, k, p));
   LloydArgs<F> a{};
@@ -2314,6 +2327,7 @@ LKM_EXPORT lkm_status lkm_create(lkm_ctx** out, int device) {
   if (const char* v = std::getenv("LKM_TC5")) ctx->tc5_enabled = std::atoi(v);
   if (const char* v = std::getenv("LKM_TC5_FUSE")) ctx->tc5_fuse = std::atoi(v);
   if (const char* v = std::getenv("LKM_DMMA")) ctx->dmma_enabled = std::atoi(v);
+  if (const char* v = std::getenv("LKM_ROWS_ASSIGN")) ctx->rows_assign = std::atoi(v);
   if (const char* v = std::getenv("LKM_FIN_CL")) ctx->fin_cl = std::atoi(v);
   if (const char* v = std::getenv("LKM_STEP_TRACE")) ctx->step_trace = std::atoi(v);
   if (const char* v = std::getenv("LKM_SPARSE_PARTIALS")) ctx->sparse_partials = std::atoi(v);
