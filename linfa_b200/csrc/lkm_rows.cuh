@@ -162,10 +162,18 @@ __global__ void __launch_bounds__(kRowsThreads) rows_top2_kernel(const RowsArgs<
     else { best = b0; bi = i0; second = (b1 < s0) ? b1 : s0; }
     const F xn = sqrt(xx) * (F)1.000001, cmax = sqrt(cm) * (F)1.000001;
     const F dd = (F)d;
-    // same certificate as scan_centroids_certified (lkm_kernels.cuh)
-    const F margin = fma((F)1.1 * eps, ((F)4 * dd + (F)4) * xn * cmax + (F)4 * cmax * cmax + ((F)2 * (dd + (F)2)) * (xn + cmax) * (xn + cmax),
-                         ((F)8 * dd + (F)16) * dmin * ((F)1 + xn + cmax));
-    const bool cert = (second - best) > margin;   // NaN anywhere -> false
+    // Certificate.  |w_c - W_c| <= errdot = eps [(2d+2)|x|C + 2C^2] for the FMA-form scores; the reference's direct form is
+    // within (d+2) eps of the TRUE squared distance (a sum of non-negative terms), which the scores bound from above as
+    // D_c = w_c + |x|^2 + errdot + (d+1) eps |x|^2.  So the reference's strict-'<' scan picks `best` when
+    //   second - best > 2 errdot + (d+2) eps (D_best + D_second).
+    // (scan_centroids_certified in lkm_kernels.cuh bounds the distances by (|x|+C)^2 instead: simpler, and looser for rows
+    // far from the origin.  Measured and rejected here: a second scoring pass in f64 for the rows this misses — slower than
+    // the exact scan it saves — and a CTA-per-row exact scan — tiles from a k-means++ start hold dozens of open rows, which
+    // thread = row handles side by side.)
+    const F errdot = eps * (((F)2 * dd + (F)2) * xn * cmax + (F)2 * cmax * cmax);
+    const F dsum = fmax(best + xx, (F)0) + fmax(second + xx, (F)0) + (F)2 * errdot + (F)2 * (dd + (F)1) * eps * xx;
+    const F margin = (F)1.1 * ((F)2 * errdot + (dd + (F)2) * eps * dsum) + ((F)8 * dd + (F)16) * dmin * ((F)1 + xn + cmax);
+    const bool cert = (second - best) > margin;   // NaN / Inf anywhere -> false
     const bool need_exact = valid && !cert;
     // ---- step 3: the reference's scan for the rows without a certificate ----
     F eb = (F)INFINITY, es = (F)INFINITY;
@@ -176,14 +184,26 @@ __global__ void __launch_bounds__(kRowsThreads) rows_top2_kernel(const RowsArgs<
         int rc = min(a.kc, a.k - cb);
         if (n_chunks > 1) rc = stage(ch);
         if (need_exact) {
-          for (int c = 0; c < rc; ++c) {
+          // centroid 0 seeds the scan (a NaN there is sticky, like in the reference); strict '<' keeps the lowest index
+          auto take = [&](F v, int gc) {
+            if (gc == 0) { eb = v; ei = 0; }
+            else if (v < eb) { es = eb; eb = v; ei = gc; }
+            else if (v < es) es = v;
+          };
+          int c = 0;
+          if constexpr (D > 0) {
+            // four centroids at a time: each distance is a chain of D dependent additions, four chains fill the pipe
+            for (; c + 4 <= rc; c += 4) {
+              const F v0 = sqdist_reg<F, D>(cs + (c + 0) * D, x), v1 = sqdist_reg<F, D>(cs + (c + 1) * D, x);
+              const F v2 = sqdist_reg<F, D>(cs + (c + 2) * D, x), v3 = sqdist_reg<F, D>(cs + (c + 3) * D, x);
+              take(v0, cb + c); take(v1, cb + c + 1); take(v2, cb + c + 2); take(v3, cb + c + 3);
+            }
+          }
+          for (; c < rc; ++c) {
             F v;
             if constexpr (D > 0) v = sqdist_reg<F, D>(cs + c * D, x);
             else v = sqdist_mem<F>(cs + (size_t)c * d, xp, d);
-            // centroid 0 seeds the scan (a NaN there is sticky, like in the reference); strict '<' keeps the lowest index
-            if (cb + c == 0) { eb = v; ei = 0; }
-            else if (v < eb) { es = eb; eb = v; ei = cb + c; }
-            else if (v < es) es = v;
+            take(v, cb + c);
           }
         }
       }
