@@ -180,6 +180,10 @@ __global__ void __launch_bounds__(kUpdThreads, 1) update_rows_kernel(const UpdAr
     uint32_t last_L = 0xFFFFFFFFu;
     Vf last_cv = upd_zero<Vf>();
     const uint32_t lt_mask = (1u << lane) - 1u;
+    Vf pend_x[4], pend_c[4];
+    uint32_t pend_on = 0u;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) { pend_x[q] = upd_zero<Vf>(); pend_c[q] = upd_zero<Vf>(); }
     for (unsigned long long j = j0; j < j1; ++j) {
       const unsigned char* st = ring + (size_t)s * kStage;
       const unsigned long long sj = stage_of(j);
@@ -193,33 +197,54 @@ __global__ void __launch_bounds__(kUpdThreads, 1) update_rows_kernel(const UpdAr
       const bool mine = c < (uint32_t)chunk_rows && (int)(c % (uint32_t)NCLS) == cls;
       uint32_t m = __ballot_sync(0xffffffffu, mine);
       if (m == 0u) continue;
+      if (m == 0xffffffffu && __all_sync(0xffffffffu, c == __shfl_sync(0xffffffffu, c, 0))) {
+        // the whole sub-tile belongs to one cluster of this warp (the rule for ordered rows): no grouping needed; two
+        // interleaved chains (even / odd rows), fixed order
+        const uint32_t L0 = __shfl_sync(0xffffffffu, c, 0);
+        if (L0 != last_L) { last_cv = upd_ldg<Vf>(Cf + (size_t)L0 * D); last_L = L0; }
+        const Vf a0 = upd_ld<Vf>(accf + (size_t)L0 * D);
+        Vf s0 = upd_zero<Vf>(), s1 = upd_zero<Vf>();
+        float e0 = 0.f, e1 = 0.f;
+#pragma unroll
+        for (int r = 0; r < kUpdSubRows; r += 2) {
+          const Vf x0 = upd_ld<Vf>(xs + r * D), x1 = upd_ld<Vf>(xs + (r + 1) * D);
+          s0 = vadd(s0, x0); s1 = vadd(s1, x1);
+          e0 = vsqacc(x0, last_cv, e0); e1 = vsqacc(x1, last_cv, e1);
+        }
+        upd_st<Vf>(accf + (size_t)L0 * D, vadd(a0, vadd(s0, s1)));
+        inert += (double)(e0 + e1);
+        if (fs == 0 && lane == 0) cnt[L0] += (uint32_t)kUpdSubRows;
+        continue;
+      }
       // rows of this warp with the same cluster; rank = position of the row among them
       // (one key for all the other lanes: MATCH.ANY walks the distinct keys one by one)
       const uint32_t peers = __match_any_sync(0xffffffffu, mine ? c : 0xFFFFFFFFu);
       const int rank = __popc(peers & lt_mask);
       const uint32_t leaders = __ballot_sync(0xffffffffu, mine && rank == 0);
-      if (__popc(leaders) > 4) {
+      if (__popc(leaders) > 2) {
         // Unordered rows: many clusters, one or two rows each.  Round t takes the t-th row of every cluster, so the rows
-        // of a round touch distinct accumulators and their loads / read-modify-writes overlap (eight in flight); a
-        // cluster's rows still reach its accumulator in row order.
+        // of a round touch distinct accumulators and their loads / read-modify-writes overlap (four in flight); a
+        // cluster's rows still reach its accumulator in row order.  The centroid row a row needs for the inertia comes
+        // from L2: its use is DEFERRED by one batch (the row and the centroid slice wait in registers), so that the
+        // round trip overlaps the next batch instead of stalling this one.
         float e_sub = 0.f;
         for (int round = 0;; ++round) {
           uint32_t p = __ballot_sync(0xffffffffu, mine && rank == round);
           if (p == 0u) break;
           while (p) {
-            int r[8];
-            uint32_t L[8];
-            bool on[8];
+            int r[4];
+            uint32_t L[4];
+            bool on[4];
 #pragma unroll
-            for (int q = 0; q < 8; ++q) {
+            for (int q = 0; q < 4; ++q) {
               on[q] = p != 0u;
               r[q] = on[q] ? __ffs(p) - 1 : 0;
               p &= p - 1u;
               L[q] = __shfl_sync(0xffffffffu, c, r[q]);
             }
-            Vf x[8], av[8], cv[8];
+            Vf x[4], av[4], cv[4];
 #pragma unroll
-            for (int q = 0; q < 8; ++q) {
+            for (int q = 0; q < 4; ++q) {
               if (on[q]) {
                 cv[q] = upd_ldg<Vf>(Cf + (size_t)L[q] * D);
                 x[q] = upd_ld<Vf>(xs + r[q] * D);
@@ -227,13 +252,20 @@ __global__ void __launch_bounds__(kUpdThreads, 1) update_rows_kernel(const UpdAr
               }
             }
 #pragma unroll
-            for (int q = 0; q < 8; ++q) {
+            for (int q = 0; q < 4; ++q) {
               if (on[q]) {
                 upd_st<Vf>(accf + (size_t)L[q] * D, vadd(av[q], x[q]));
-                e_sub = vsqacc(x[q], cv[q], e_sub);
                 if (fs == 0 && lane == 0) cnt[L[q]] += 1u;
               }
             }
+            // the previous batch's centroid slices have had a whole batch to arrive
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              if (pend_on & (1u << q)) e_sub = vsqacc(pend_x[q], pend_c[q], e_sub);
+              pend_x[q] = x[q];
+              pend_c[q] = cv[q];
+            }
+            pend_on = (on[0] ? 1u : 0u) | (on[1] ? 2u : 0u) | (on[2] ? 4u : 0u) | (on[3] ? 8u : 0u);
           }
         }
         inert += (double)e_sub;
@@ -306,6 +338,13 @@ __global__ void __launch_bounds__(kUpdThreads, 1) update_rows_kernel(const UpdAr
       __syncwarp();
       if (lane == 0) tc::mbar_arrive(&bar_empty[s]);
       if (++s == R) s = 0;
+    }
+    {
+      float e_tail = 0.f;
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        if (pend_on & (1u << q)) e_tail = vsqacc(pend_x[q], pend_c[q], e_tail);
+      inert += (double)e_tail;
     }
   }
   // ---- per-CTA partials: accumulators as they are, inertia by warp butterflies and then in warp order ----
