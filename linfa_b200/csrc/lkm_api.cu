@@ -231,6 +231,8 @@ static lkm_status run_assign(lkm_ctx* ctx, const F* dX, uint64_t n, uint64_t d, 
   // wide rows (no compile-time-d instance of lloyd_kernel): thread = row with the row in registers, FMA scores + certificate,
   // exact scan where it fails, winner's distance in the direct form — the same labels and the same bits as the exact scan
   // (rows_top2_kernel over all rows); predict / transform / assign and the seeding passes over several centroids take this
+  // (not for the one-centroid passes of k-means++: measured slower there, 197 against 176 ms per 4M x 128 seeding — one CTA
+  // of 8 warps per SM is too little occupancy for a pass that only streams)
   if (ctx->rows_assign && ctx->force_path != 0 && weights == nullptr && wdists == nullptr && k >= 8 && n < (1ull << 32) &&
       (d == 64 || (d == 128 && sizeof(F) == 4)) && (reinterpret_cast<uintptr_t>(dX) & 15) == 0) {
     RowsArgs<F> ra{};
@@ -1489,24 +1491,20 @@ static lkm_status weighted_pick(lkm_ctx* ctx, const F* dW, uint64_t n, HostRng& 
   std::vector<double> hb(nb);
   CK(cudaMemcpyAsync(hb.data(), ctx->bsum.p, nb * 8, cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
+  // fixed order shared with fast_pick_device_kernel: group sums, then the groups (pick_group_sum / pick_locate)
+  const uint64_t ng = (nb + kPickGroup - 1) / kPickGroup;
+  std::vector<double> hg(ng);
+  for (uint64_t g = 0; g < ng; ++g) hg[g] = pick_group_sum(hb.data(), nb, g);
   double total = 0.0;
-  for (uint64_t b = 0; b < nb; ++b) total += hb[b];
+  for (uint64_t g = 0; g < ng; ++g) total += hg[g];
   ctx->launches++;
   if (!(total > 0.0)) { picked = -1; return LKM_OK; }
   // Uniform<F>::new(0, total).sample: value0_1 * scale with scale = (F)total
   const F u01 = unit<F>(rng);
   const double thr = (double)(u01 * (F)total);
-  // walk the block sums in order on the host (nb doubles), the kernel finishes inside the block
-  double run = 0.0;
-  uint64_t fb = nb - 1;
+  unsigned long long fb = 0;
   double fp = 0.0;
-  bool hit = false;
-  for (uint64_t b = 0; b < nb; ++b) {
-    const double nxt = run + hb[b];
-    if (nxt > thr) { fb = b; fp = run; hit = true; break; }
-    run = nxt;
-  }
-  if (!hit) { fp = run - hb[nb - 1]; }
+  pick_locate(hb.data(), nb, hg.data(), ng, thr, fb, fp);
   long long* didx = reinterpret_cast<long long*>(ctx->scratch.as<char>() + 48);
   fast_pick_kernel<F><<<1, 256, 0, ctx->stream>>>(dW, n, fb, fp, thr, didx);
   CK(cudaGetLastError());
@@ -1534,11 +1532,9 @@ static lkm_status weighted_kmeanspp(lkm_ctx* ctx, const F* dX, uint64_t n, uint6
     // weights = ones: materialise them once so that the first pick walks the
     // same F prefix sum 1, 2, 3, ... WeightedIndex::new builds
     CK(ctx->weights.ensure(std::max<uint64_t>(n, 1) * sizeof(F)));
-    std::vector<F> ones(std::min<uint64_t>(n, 1 << 20), (F)1);
-    for (uint64_t o = 0; o < n; o += ones.size())
-      CK(cudaMemcpyAsync(ctx->weights.as<F>() + o, ones.data(), std::min<uint64_t>(ones.size(), n - o) * sizeof(F),
-                         cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
+    fill_kernel<F><<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(ctx->weights.as<F>(), n, (F)1);
+    CK(cudaGetLastError());
+    ctx->launches++;
     first_w = ctx->weights.as<F>();
   } else {
     // assert_ne!(weights.sum(), 0) (KM/init.rs:127): all weights are >= 0 here, so
@@ -1548,6 +1544,26 @@ static lkm_status weighted_kmeanspp(lkm_ctx* ctx, const F* dX, uint64_t n, uint6
   CKS(weighted_pick<F>(ctx, first_w, n, rng, pick_mode, idx));
   if (idx < 0) return fail(ctx, dW ? LKM_ERR_ZERO_WEIGHTS : LKM_ERR_BAD_WEIGHTS, "invalid weights for k-means++");
   CK(cudaMemcpyAsync(dC, dX + (size_t)idx * d, d * sizeof(F), cudaMemcpyDeviceToDevice, ctx->stream));
+  int mode = pick_mode;
+  if (mode == LKM_PICK_AUTO) mode = n <= (1ull << 22) ? LKM_PICK_EXACT : LKM_PICK_FAST;
+  if (mode == LKM_PICK_FAST && ctx->device_picks && n > 0 && (n + kPickBlock - 1) / kPickBlock <= (uint64_t)kPickGroup * kPickMaxGroups) {
+    // FAST: nothing the host draws depends on the device (one uniform per pick), so the k - 1 picks are queued without a
+    // host round trip: distance update -> block sums -> fast_pick_device_kernel (total, threshold, walk, row copy)
+    const uint64_t nb = (n + kPickBlock - 1) / kPickBlock;
+    CK(ctx->bsum.ensure(nb * 8));
+    CK(ctx->scratch.ensure(64));
+    long long* didx = reinterpret_cast<long long*>(ctx->scratch.as<char>() + 48);
+    for (uint64_t c = 1; c < k; ++c) {
+      CKS(run_assign<F>(ctx, dX, n, d, dC + (c - 1) * d, 1, nullptr, dD, c > 1 ? 1 : 0, dW, dWD));
+      block_sums_kernel<F><<<(int)std::min<uint64_t>(nb, 4096), 256, 0, ctx->stream>>>(dWD, n, ctx->bsum.as<double>());
+      const F u01 = unit<F>(rng);
+      fast_pick_device_kernel<F><<<1, 256, 0, ctx->stream>>>(dWD, n, ctx->bsum.as<double>(), nb, u01, dX, (int)d, dC + c * d, didx);
+      CK(cudaGetLastError());
+      ctx->launches += 2;
+    }
+    CK(cudaStreamSynchronize(ctx->stream));
+    return LKM_OK;
+  }
   for (uint64_t c = 1; c < k; ++c) {
     CKS(run_assign<F>(ctx, dX, n, d, dC + (c - 1) * d, 1, nullptr, dD, c > 1 ? 1 : 0, dW, dWD));
     CKS(weighted_pick<F>(ctx, dWD, n, rng, pick_mode, idx));
@@ -2327,6 +2343,7 @@ LKM_EXPORT lkm_status lkm_create(lkm_ctx** out, int device) {
   if (const char* v = std::getenv("LKM_TC5")) ctx->tc5_enabled = std::atoi(v);
   if (const char* v = std::getenv("LKM_TC5_FUSE")) ctx->tc5_fuse = std::atoi(v);
   if (const char* v = std::getenv("LKM_DMMA")) ctx->dmma_enabled = std::atoi(v);
+  if (const char* v = std::getenv("LKM_DEVICE_PICKS")) ctx->device_picks = std::atoi(v);
   if (const char* v = std::getenv("LKM_ROWS_ASSIGN")) ctx->rows_assign = std::atoi(v);
   if (const char* v = std::getenv("LKM_FIN_CL")) ctx->fin_cl = std::atoi(v);
   if (const char* v = std::getenv("LKM_STEP_TRACE")) ctx->step_trace = std::atoi(v);

@@ -119,6 +119,7 @@ struct lkm_ctx {
   int step_trace = 0;
   std::vector<cudaEvent_t> trace_ev;
   std::vector<const char*> trace_name;
+  int device_picks = 1;      // LKM_DEVICE_PICKS=0: FAST k-means++ picks with a host round trip each (the first always has one)
   int rows_assign = 1;       // LKM_ROWS_ASSIGN=0: predict / transform of wide rows through lloyd_kernel<MODE_ASSIGN> (exact scan)
   int fin_cl = 1;            // LKM_FIN_CL=0: slice-wise finalize kernels even when the partials are sparse
   int sparse_partials = 1;   // LKM_SPARSE_PARTIALS=0: the pair / update kernels zero-fill and write back whole k x d partials

@@ -1102,6 +1102,104 @@ __global__ void __launch_bounds__(256) fast_pick_kernel(const F* __restrict__ w,
   if (t == 0) out_idx[0] = (found == ~0ull) ? (long long)end - 1 : (long long)found;
 }
 
+// Fixed order of the FAST pick over the block sums, shared by the host walk (weighted_pick) and the device walk
+// (fast_pick_device_kernel) so that both pick the same row: groups of kPickGroup consecutive blocks are summed in order,
+// the group sums in order give the total, and the threshold is located group first, then block.
+constexpr int kPickGroup = 64;
+constexpr int kPickMaxGroups = 2048;   // shared-memory group sums of the device walk: up to 2048 * 64 * 2048 = 268M weights
+__host__ __device__ inline double pick_group_sum(const double* bsum, unsigned long long nb, unsigned long long g) {
+  double s = 0.0;
+  const unsigned long long b1 = (g + 1) * kPickGroup < nb ? (g + 1) * kPickGroup : nb;
+  for (unsigned long long b = g * kPickGroup; b < b1; ++b) s += bsum[b];
+  return s;
+}
+__host__ __device__ inline void pick_locate(const double* bsum, unsigned long long nb, const double* gsum, unsigned long long ng,
+                                            double thr, unsigned long long& fb, double& fp) {
+  double run = 0.0;
+  unsigned long long g = 0;
+  for (; g < ng; ++g) {
+    const double nxt = run + gsum[g];
+    if (nxt > thr) break;
+    run = nxt;
+  }
+  if (g == ng) { g = ng - 1; run -= gsum[g]; }   // rounding hid the crossing: the last group
+  const unsigned long long b0 = g * kPickGroup, b1 = (g + 1) * kPickGroup < nb ? (g + 1) * kPickGroup : nb;
+  for (unsigned long long b = b0; b < b1; ++b) {
+    const double nxt = run + bsum[b];
+    if (nxt > thr) { fb = b; fp = run; return; }
+    run = nxt;
+  }
+  fb = b1 - 1;
+  fp = run - bsum[b1 - 1];
+}
+
+// The whole FAST pick on the device, for picks 2..k of k-means++ (no host round trip between the picks: the k uniforms are
+// drawn up front, the kernels of all picks are queued back to back).  One CTA: thread 0 walks the block sums in order (the
+// same two walks the host does in weighted_pick: total, then the block whose running prefix crosses thr = u01 * total), all
+// threads finish inside that block like fast_pick_kernel, then copy the chosen row behind the centroids chosen so far.
+// No positive total (every remaining distance zero): row 0, the reference's `.unwrap_or(0)` (KM/init.rs:149-152).
+template <typename F>
+__global__ void __launch_bounds__(256) fast_pick_device_kernel(const F* __restrict__ w, unsigned long long n,
+                                                               const double* __restrict__ bsum, unsigned long long nb, F u01,
+                                                               const F* __restrict__ X, int d, F* __restrict__ dst,
+                                                               long long* __restrict__ out_idx) {
+  constexpr int PER = kPickBlock / 256;
+  __shared__ double wsum[8];
+  __shared__ unsigned long long found, s_block;
+  __shared__ double s_prefix, s_thr;
+  __shared__ int s_none;
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  __shared__ double gsum[kPickMaxGroups];
+  const unsigned long long ng = (nb + kPickGroup - 1) / kPickGroup;
+  for (unsigned long long g = t; g < ng; g += 256) gsum[g] = pick_group_sum(bsum, nb, g);
+  __syncthreads();
+  if (t == 0) {
+    double total = 0.0;
+    for (unsigned long long g = 0; g < ng; ++g) total += gsum[g];
+    s_none = !(total > 0.0);
+    const double thr = (double)(u01 * (F)total);   // Uniform<F>::new(0, total).sample: value0_1 * scale, scale = (F)total
+    unsigned long long fb = 0;
+    double fp = 0.0;
+    pick_locate(bsum, nb, gsum, ng, thr, fb, fp);
+    s_block = fb; s_prefix = fp; s_thr = thr;
+    found = ~0ull;
+  }
+  __syncthreads();
+  long long idx = 0;
+  if (!s_none) {
+    const unsigned long long block = s_block;
+    const unsigned long long base = block * kPickBlock + (unsigned long long)t * PER;
+    const unsigned long long end = min(n, (block + 1) * (unsigned long long)kPickBlock);
+    double v[PER];
+    double local = 0.0;
+#pragma unroll
+    for (int i = 0; i < PER; ++i) {
+      v[i] = (base + i < end) ? (double)w[base + i] : 0.0;
+      local += v[i];
+    }
+    double incl = local;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const double up = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += up;
+    }
+    if (lane == 31) wsum[warp] = incl;
+    __syncthreads();
+    double woff = 0.0;
+    for (int q = 0; q < warp; ++q) woff += wsum[q];
+    double run = s_prefix + woff + (incl - local);
+#pragma unroll
+    for (int i = 0; i < PER; ++i) {
+      run += v[i];
+      if (run > s_thr && base + i < end) { atomicMin(&found, base + i); break; }
+    }
+    __syncthreads();
+    idx = (found == ~0ull) ? (long long)end - 1 : (long long)found;
+  }
+  if (t == 0 && out_idx != nullptr) out_idx[0] = idx;
+  for (int j = t; j < d; j += 256) dst[j] = X[(size_t)idx * d + j];
+}
+
 // k-means|| oversampling (KM/init.rs:239-270): keep row i iff U_i < mult * d_i / cost,
 // U_i from a counter-based generator keyed by (seed, global row).  Selected global
 // row ids are appended through an atomic cursor (the host sorts them ascending).

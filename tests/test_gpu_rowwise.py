@@ -209,3 +209,28 @@ def test_kmeans_para_reference_blobs(lb, oracle):
         assert np.mean(mine) < np.mean(rnd)   # Random seeds one blob twice in 7 draws of 9
     finally:
         ctx.close()
+
+
+def test_fast_picks_on_the_device_pick_the_same_rows(lb, monkeypatch):
+    """PickMode.Fast queues picks 2..k without a host round trip (fast_pick_device_kernel); the arithmetic is the host walk's,
+    so the seeds are the same rows, and the k-means|| result (whose last step is a weighted k-means++) too."""
+    g = np.random.default_rng(5)
+    for dt, n, d, k in ((np.float32, 70001, 32, 40), (np.float64, 30000, 5, 17)):
+        centres = g.uniform(-20, 20, (k, d))
+        X = (centres[g.integers(0, k, n)] + g.standard_normal((n, d))).astype(dt)
+        out = {}
+        for flag in ("1", "0"):
+            monkeypatch.setenv("LKM_DEVICE_PICKS", flag)
+            ctx = lb.Context(0)
+            try:
+                ctx.set_data(X)
+                for method in (lb.KMeansInit.KMeansPlusPlus, lb.KMeansInit.KMeansPara):
+                    p = (lb.KMeans.params_with_rng(k, lb.Xoshiro256Plus.seed_from_u64(9)).n_runs(1).init_method(method)
+                         .pick_mode(lb.PickMode.Fast).check())
+                    out[(flag, method.kind)] = p.init_centroids_resident(ctx)
+            finally:
+                ctx.close()
+        for kind in ("KMeansPlusPlus", "KMeansPara"):
+            assert (out[("1", kind)] == out[("0", kind)]).all()
+            rows = {r.tobytes() for r in X}
+            assert all(r.tobytes() in rows for r in out[("1", kind)])
