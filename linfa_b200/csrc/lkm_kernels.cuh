@@ -870,13 +870,15 @@ __global__ void __launch_bounds__(kFinThreads) finalize_cl_kernel(const Finalize
         for (int p = 0; p < a.world; ++p) a.peer_out[p][kd + a.k] = tot;
     }
     if (stamp) a.prof[1] = global_ns();
-    __threadfence_system();
+    // every thread's NVLink stores happen before the barrier; the fence of the flag-writing threads after it is cumulative
+    // over them (one system fence per flag instead of one per thread: the fence waits for the peers' acknowledgements)
     __syncthreads();
-    if (stamp) a.prof[2] = global_ns();
     if (t < a.world) {
+      __threadfence_system();
       unsigned long long* f = a.peer_flags[t] + blockIdx.x;
       asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(f), "l"(a.epoch) : "memory");
     }
+    if (stamp) a.prof[2] = global_ns();
     bool ok = true;
     if (t < a.world) ok = wait_flag(a.my_flags + (size_t)t * kFxMaxCtas + blockIdx.x, a.epoch);
     if (!ok) atomicOr(&a.state->fallback_rows, 1ull << 41);   // timeout marker, reported by the host
