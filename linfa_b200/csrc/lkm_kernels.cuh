@@ -718,9 +718,10 @@ __global__ void __launch_bounds__(kFinThreads) finalize_x_kernel(const FinalizeX
     if (t == 0)
       for (int p = 0; p < a.world; ++p) a.peer_out[p][kd + a.k] = tot;
   }
-  __threadfence_system();
+  // the stores of every thread are ordered by the barrier; the flag-writing threads' fence is cumulative over them
   __syncthreads();
   if (t < a.world) {
+    __threadfence_system();
     unsigned long long* f = a.peer_flags[t] + blockIdx.x;
     asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(f), "l"(a.epoch) : "memory");
   }
