@@ -111,7 +111,7 @@ typedef struct lkm_stats {
   uint32_t assign_path;      /* 0 exact CUDA-core, 1 certified FMA, 2 tcgen05 3xTF32, 3 f32-screened f64 (small d), 4 f64 DMMA */
   uint64_t fallback_rows;    /* rows re-evaluated in exact form by the certified paths */
   float main_kernel_ms;      /* with lkm_set_l2_flush: summed duration of the assign/fused kernel alone */
-  uint32_t reserved;
+  uint32_t update_path;      /* how the last iteration summed the rows: 0 inside the assignment kernel, 1 streaming update pass, 2 sorted update (unordered rows) */
   uint64_t rows_scanned;     /* Hamerly: rows that went through two_closest_centroids after iteration 1 (summed over iterations) */
   uint64_t rows_tightened;   /* Hamerly: rows whose upper bound was recomputed (one exact distance) */
 } lkm_stats;

@@ -66,7 +66,7 @@ class lkm_stats(C.Structure):
         ("assign_path", C.c_uint32),
         ("fallback_rows", C.c_uint64),
         ("main_kernel_ms", C.c_float),
-        ("reserved", C.c_uint32),
+        ("update_path", C.c_uint32),
         ("rows_scanned", C.c_uint64),
         ("rows_tightened", C.c_uint64),
     ]

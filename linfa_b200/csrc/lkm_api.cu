@@ -26,6 +26,7 @@
 #include "lkm_tma.cuh"
 #include "lkm_tc4.cuh"
 #include "lkm_upd.cuh"
+#include "lkm_sortupd.cuh"
 #include "lkm_tc5.cuh"
 #include "lkm_f64s.cuh"
 #include "lkm_rows.cuh"
@@ -796,6 +797,28 @@ static lkm_status run_lloyd(lkm_ctx* ctx, F* dC2, uint64_t k, uint64_t max_iter,
   CK(ctx->part_counts.ensure((size_t)grid * k * 4));
   if (use_upd && ctx->sparse_partials) CK(ctx->part_touched.ensure((size_t)grid * k));
   unsigned char* touched = (use_upd && ctx->sparse_partials) ? ctx->part_touched.as<unsigned char>() : nullptr;
+  // sorted update (lkm_sortupd.cuh) for unordered rows: decided after the first iteration of the call from the number of
+  // label changes between neighbouring rows (a one-iteration first batch, like the other probes)
+  const bool sort_ok = use_upd && ctx->sort_upd != 0 && k <= (uint64_t)kSrtMaxK && n < (1ull << 32) - 64 &&
+                       (ctx->sort_upd > 0 || n * d * sizeof(F) >= (32ull << 20));
+  bool use_sorted = sort_ok && ctx->sort_upd > 0;
+  bool sort_probe = sort_ok && !use_sorted;
+  if (use_sorted) tc5_can_fuse = false;
+  const unsigned long long srt_segs = (n + kSrtSegRows - 1) / kSrtSegRows;
+  const unsigned long long su_warps = (unsigned long long)ctx->sm_count * 2 * kSuWarps;
+  const unsigned long long su_per = std::max<unsigned long long>(32, ((n + su_warps - 1) / su_warps + 31) / 32 * 32);
+  if (sort_ok) {
+    CK(ctx->srt_hist.ensure((size_t)srt_segs * k * 4));
+    CK(ctx->srt_seg.ensure((k + 2) * 4 + 64));
+    CK(ctx->srt_perm.ensure((n + 64) * 4));
+    CK(ctx->srt_ent.ensure((size_t)(su_warps + k) * d * 4));
+    CK(ctx->srt_inert.ensure((size_t)su_warps * 8));
+    CK(cudaMemsetAsync(ctx->srt_seg.p, 0, (k + 2) * 4 + 64, ctx->stream));
+    if (kSrtWarps * k * 4 > 48 * 1024) {
+      CK(cudaFuncSetAttribute(sort_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kSrtWarps * k * 4)));
+      CK(cudaFuncSetAttribute(sort_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kSrtWarps * k * 4)));
+    }
+  }
   CK(ctx->part_inertia.ensure((size_t)std::max(grid, 1024) * 8));
   const int fin_grid = (int)((kd + kFinElems - 1) / kFinElems);
   CK(ctx->shift_part.ensure((size_t)std::max(std::max(fin_grid, grid), kFxMaxCtas) * 8));
@@ -822,6 +845,7 @@ static lkm_status run_lloyd(lkm_ctx* ctx, F* dC2, uint64_t k, uint64_t max_iter,
   }
   const bool use_p2p = ctx->world > 1 && ctx->p2p_enabled && ctx->p2p_local != nullptr && L <= ctx->p2p_cap;
   LloydState* dstate = ctx->state.as<LloydState>();
+  ctx->last_update_path = 0;
   CK(cudaMemsetAsync(dstate, 0, sizeof(LloydState), ctx->stream));
   const bool flush = ctx->flush_bytes > 0;
   if (flush) {
@@ -855,7 +879,7 @@ static lkm_status run_lloyd(lkm_ctx* ctx, F* dC2, uint64_t k, uint64_t max_iter,
   unsigned long long mixed_seen = 0;
   unsigned long long fb_seen = 0;
   for (;;) {
-    const uint64_t todo = std::min<uint64_t>((tc4_probe || tc5_probe) ? 1 : batch, max_iter - launched);
+    const uint64_t todo = std::min<uint64_t>((tc4_probe || tc5_probe || sort_probe) ? 1 : batch, max_iter - launched);
     for (uint64_t q = 0; q < todo; ++q) {
       const uint64_t it = launched + q;
       const F* Ccur = dC2 + (it & 1) * kd;
@@ -1031,7 +1055,49 @@ static lkm_status run_lloyd(lkm_ctx* ctx, F* dC2, uint64_t k, uint64_t max_iter,
         }
         bool updated = false;
         if constexpr (std::is_same<F, float>::value) {
-          if (use_upd) {
+          if (use_upd && sort_probe) {
+            label_breaks_kernel<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(ctx->labels.as<uint32_t>(), n, dstate);
+            CK(cudaGetLastError());
+            ctx->launches++;
+          }
+          if (use_upd && use_sorted && !fused_now) {
+            SortArgs sa{};
+            sa.labels = ctx->labels.as<uint32_t>(); sa.n = n; sa.k = (int)k; sa.hist = ctx->srt_hist.as<uint32_t>();
+            sa.seg_start = ctx->srt_seg.as<uint32_t>(); sa.perm = ctx->srt_perm.as<uint32_t>();
+            sa.scan_done = ctx->srt_seg.as<unsigned int>() + (k + 2); sa.state = dstate;
+            const unsigned sgrid = (unsigned)((srt_segs + kSrtWarps - 1) / kSrtWarps);
+            const size_t ssm = (size_t)kSrtWarps * k * 4;
+            sort_hist_kernel<<<sgrid, kSrtThreads, ssm, ctx->stream>>>(sa);
+            sort_scan_kernel<<<(unsigned)((k + 31) / 32), dim3(32, 32), 0, ctx->stream>>>(sa);
+            sort_scatter_kernel<<<sgrid, kSrtThreads, ssm, ctx->stream>>>(sa);
+            CK(cudaGetLastError());
+            trace_mark(ctx, "sort_labels");
+            SortUpdArgs su{};
+            su.X = dX; su.n = n; su.k = (int)k; su.perm = sa.perm; su.seg_start = sa.seg_start; su.C = Ccur;
+            su.ent_sums = ctx->srt_ent.as<float>(); su.ent_inertia = ctx->srt_inert.as<double>();
+            su.per_warp = su_per; su.n_warps = su_warps;
+            su.part_sums = ctx->part_sums.as<float>(); su.part_counts = ctx->part_counts.as<uint32_t>();
+            su.part_touched = touched; su.part_inertia = ctx->part_inertia.as<double>(); su.state = dstate;
+            const unsigned ugrid = (unsigned)(su_warps / kSuWarps);
+            if (d == 32) {
+              update_sorted_kernel<32><<<ugrid, kSuThreads, 0, ctx->stream>>>(su);
+              sorted_combine_kernel<32><<<(unsigned)k + 1, 32, 0, ctx->stream>>>(su);
+            } else if (d == 64) {
+              update_sorted_kernel<64><<<ugrid, kSuThreads, 0, ctx->stream>>>(su);
+              sorted_combine_kernel<64><<<(unsigned)k + 1, 64, 0, ctx->stream>>>(su);
+            } else {
+              update_sorted_kernel<128><<<ugrid, kSuThreads, 0, ctx->stream>>>(su);
+              sorted_combine_kernel<128><<<(unsigned)k + 1, 128, 0, ctx->stream>>>(su);
+            }
+            CK(cudaGetLastError());
+            ctx->launches += 5;
+            trace_mark(ctx, "update_sorted");
+            ctx->last_update_path = 2;
+            fin_src = 1;
+            fin_src_inertia = 1;
+            updated = true;
+            upd_partials = true;
+          } else if (use_upd) {
             UpdArgs ua{};
             ua.X = dX; ua.n = n; ua.k = (int)k; ua.chunk_rows = upd_chunk; ua.stages = upd_stages;
             ua.labels = ctx->labels.as<uint32_t>(); ua.C = Ccur;
@@ -1058,6 +1124,7 @@ static lkm_status run_lloyd(lkm_ctx* ctx, F* dC2, uint64_t k, uint64_t max_iter,
             else CK(cudaLaunchKernelEx(&cfg, update_rows_kernel<128>, ua, upd_map));
             ctx->launches++;
             trace_mark(ctx, "update_rows");
+            ctx->last_update_path = 1;
             updated = true;
             upd_partials = true;
           }
@@ -1196,6 +1263,12 @@ static lkm_status run_lloyd(lkm_ctx* ctx, F* dC2, uint64_t k, uint64_t max_iter,
       const unsigned long long mixed = ctx->h_state->mixed_tiles - mixed_seen;
       if (tc5_can_fuse && (double)mixed > fuse_mixed_limit * (double)((n + 127) / 128) * (double)todo_done) tc5_can_fuse = false;
       mixed_seen = ctx->h_state->mixed_tiles;
+      if (sort_probe) {
+        // more than one label change per four rows: the streaming update is bound by its per-row bookkeeping, sort instead
+        use_sorted = (double)ctx->h_state->label_breaks > 0.25 * (double)n;
+        if (use_sorted) tc5_can_fuse = false;
+        sort_probe = false;
+      }
       tc4_probe = false;
       tc5_probe = false;
     }
@@ -2085,7 +2158,7 @@ static lkm_status fit_impl(lkm_ctx* ctx, const lkm_params* p, lkm_rng rng_in, F*
   if (stats) {
     std::memset(stats, 0, sizeof(*stats));
     stats->n_iter = lo.n_iter; stats->last_shift = lo.shift; stats->inertia_total = lo.inertia;
-    stats->device_ms = ms_total; stats->kernel_launches = ctx->launches; stats->assign_path = (uint32_t)ctx->last_path;
+    stats->device_ms = ms_total; stats->kernel_launches = ctx->launches; stats->assign_path = (uint32_t)ctx->last_path; stats->update_path = (uint32_t)ctx->last_update_path;
     stats->fallback_rows = lo.fallback_rows;
   }
   if (!have) return fail(ctx, LKM_ERR_INERTIA, "Fitting failed: No inertia improvement (-inf)");
@@ -2128,7 +2201,7 @@ static lkm_status lloyd_iters_impl(lkm_ctx* ctx, F* centroids_inout, uint64_t k,
   if (stats) {
     std::memset(stats, 0, sizeof(*stats));
     stats->n_iter = lo.n_iter; stats->last_shift = lo.shift; stats->inertia_total = lo.inertia;
-    stats->device_ms = lo.ms; stats->kernel_launches = ctx->launches; stats->assign_path = (uint32_t)ctx->last_path;
+    stats->device_ms = lo.ms; stats->kernel_launches = ctx->launches; stats->assign_path = (uint32_t)ctx->last_path; stats->update_path = (uint32_t)ctx->last_update_path;
     stats->main_kernel_ms = lo.main_ms; stats->fallback_rows = lo.fallback_rows;
     if (hamerly) { stats->rows_scanned = ctx->ham_rows_scanned; stats->rows_tightened = ctx->ham_rows_tightened; }
   }
@@ -2346,6 +2419,7 @@ LKM_EXPORT lkm_status lkm_create(lkm_ctx** out, int device) {
   if (const char* v = std::getenv("LKM_DEVICE_PICKS")) ctx->device_picks = std::atoi(v);
   if (const char* v = std::getenv("LKM_ROWS_ASSIGN")) ctx->rows_assign = std::atoi(v);
   if (const char* v = std::getenv("LKM_FIN_CL")) ctx->fin_cl = std::atoi(v);
+  if (const char* v = std::getenv("LKM_SORT_UPD")) ctx->sort_upd = std::atoi(v);
   if (const char* v = std::getenv("LKM_STEP_TRACE")) ctx->step_trace = std::atoi(v);
   if (const char* v = std::getenv("LKM_SPARSE_PARTIALS")) ctx->sparse_partials = std::atoi(v);
   if (const char* v = std::getenv("LKM_TC5_DEFER")) ctx->tc5_defer = std::atoi(v);

@@ -128,6 +128,9 @@ struct lkm_ctx {
   int tc5_enabled = 1;   // LKM_TC5=0: tc_assign_kernel instead of the CTA-pair assignment kernel
   double tc5_rescan_limit = 0.08;   // LKM_TC5_RESCAN_LIMIT: share of listed rows above which the pair kernel moves to 3xTF32
   int tc5_defer = 1;     // LKM_TC5_DEFER=0: undecided rows are scanned inline by the pair kernel instead of by rows_top2_kernel
+  int last_update_path = 0;
+  int sort_upd = -1;     // LKM_SORT_UPD: -1 = sorted update (lkm_sortupd.cuh) when the first iteration finds the rows unordered, 0 never, 1 always
+  DevBuf srt_hist, srt_seg, srt_perm, srt_ent, srt_inert;
   int upd_variant = 1;   // LKM_UPD=0: cluster-chunked lloyd_kernel<MODE_UPDATE> instead of update_rows_kernel
   uint64_t data_epoch = 1, xmax2_epoch = 0;  // resident-data version / version the cached max row norm belongs to
   DevBuf xmax2, t4prof, t5merge, t5list;

@@ -29,6 +29,7 @@ struct LloydState {
   int done;
   unsigned int blocks_done;
   unsigned long long mixed_tiles;   // tiles the fused update of the pair kernel left to the listed update pass
+  unsigned long long label_breaks;  // adjacent rows with different labels (label_breaks_kernel, first iteration of a call)
 };
 
 enum LloydMode { MODE_ASSIGN = 0, MODE_FUSED = 1, MODE_UPDATE = 2 };

@@ -83,7 +83,7 @@ pub struct lkm_stats {
     pub assign_path: u32,
     pub fallback_rows: u64,
     pub main_kernel_ms: f32,
-    pub reserved: u32,
+    pub update_path: u32,
     pub rows_scanned: u64,
     pub rows_tightened: u64,
 }

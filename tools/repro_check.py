@@ -8,7 +8,9 @@ if len(sys.argv) > 1:
     x = np.empty((n, d))
     for i in range(n):
         for j in range(d):
-            u = sum((g.next_u64() >> 11) * (1.0 / 9007199254740992.0) for _ in range(12))
+            u = 0.0
+            for _ in range(12):   # not sum(): Python >= 3.12 compensates float sums, the C harness adds in order
+                u += (g.next_u64() >> 11) * (1.0 / 9007199254740992.0)
             x[i, j] = 10.0 * (i % k) + (u - 6.0)
     for runs in (1, 3):
         m = lb.KMeans.params_with_rng(k, lb.Xoshiro256Plus.seed_from_u64(42)).n_runs(runs).fit(lb.DatasetBase(x))
