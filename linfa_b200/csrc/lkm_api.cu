@@ -748,6 +748,7 @@ static lkm_status run_lloyd(lkm_ctx* ctx, F* dC2, uint64_t k, uint64_t max_iter,
   size_t tc5_smem = 0;
   CUtensorMap tc5_map;
   std::memset(&tc5_map, 0, sizeof(tc5_map));
+  bool piv_ok = false;
   if constexpr (std::is_same<F, float>::value) {
     if (use_upd && ctx->tc5_enabled && (d == 64 || d == 128 || pair32) && k <= (uint64_t)kT5K * kT5MaxChunks && n + 512 < (1ull << 31) &&
         tc5_smem_bytes((int)d) <= ctx->smem_optin && tc5s_smem_bytes((int)d) <= ctx->smem_optin) {
@@ -789,6 +790,12 @@ static lkm_status run_lloyd(lkm_ctx* ctx, F* dC2, uint64_t k, uint64_t max_iter,
         CK(ctx->t5list.ensure(((size_t)tc5_grid * tc5_list_cap + (size_t)tc5_grid + 64) * 4));
       }
       use_tc5 = true;
+      // pivot pruning of the rows the screening kernel lists (lkm_rows.cuh)
+      if (ctx->tc5_defer && ctx->rows_pivot != 0 && d != 32 && k <= 4096) {
+        CK(ctx->piv_cc.ensure(k * k * 4));
+        CK(ctx->piv_list2.ensure((n + 256) * 4 + 64));
+        piv_ok = true;
+      }
     }
   }
   const int grid = pf.fused ? pf.grid : (use_upd ? (tc5_can_fuse ? std::max(upd_gx, 2 * tc5_grid) : upd_gx) : pu.grid);
@@ -878,6 +885,9 @@ static lkm_status run_lloyd(lkm_ctx* ctx, F* dC2, uint64_t k, uint64_t max_iter,
   const double tc5_rescan_limit = ctx->tc5_defer ? ctx->tc5_rescan_limit : 0.004, tc4_rescan_limit = 0.02, fuse_mixed_limit = 0.25;
   unsigned long long mixed_seen = 0;
   unsigned long long fb_seen = 0;
+  // listed rows per iteration above which they go through the pivot pruning first (decided from the previous batch)
+  bool piv_now = piv_ok && ctx->rows_pivot > 0;
+  const double piv_limit = 2048.0;
   for (;;) {
     const uint64_t todo = std::min<uint64_t>((tc4_probe || tc5_probe || sort_probe) ? 1 : batch, max_iter - launched);
     for (uint64_t q = 0; q < todo; ++q) {
@@ -997,6 +1007,26 @@ static lkm_status run_lloyd(lkm_ctx* ctx, F* dC2, uint64_t k, uint64_t max_iter,
               ra.X = dX; ra.n = n; ra.d = (int)d; ra.k = (int)k; ra.C = Ccur; ra.list = t5.rescan_list; ra.list_count = rescan_count;
               ra.labels = ctx->labels.as<uint32_t>(); ra.state = dstate;
               trace_mark(ctx, "assign_tc5");
+              if (piv_now && d != 32) {
+                // decide the listed rows among the centroids near their provisional label; what stays open goes on to rows_top2_kernel
+                PivotArgs pv{};
+                pv.X = dX; pv.k = (int)k; pv.C = Ccur; pv.CC = ctx->piv_cc.as<float>(); pv.list = t5.rescan_list; pv.count = rescan_count;
+                pv.labels = ctx->labels.as<uint32_t>(); pv.list2 = ctx->piv_list2.as<uint32_t>();
+                pv.count2 = reinterpret_cast<unsigned int*>(ctx->piv_list2.as<uint32_t>() + ((n + 256) & ~(uint64_t)3));
+                pv.state = dstate;
+                CK(cudaMemsetAsync(pv.count2, 0, 4, ctx->stream));
+                if (d == 64) {
+                  centroid_dist_kernel<64><<<(unsigned)k, 128, 0, ctx->stream>>>(pv);
+                  rows_pivot_kernel<64><<<ctx->sm_count * 4, kPivThreads, 0, ctx->stream>>>(pv);
+                } else {
+                  centroid_dist_kernel<128><<<(unsigned)k, 128, 0, ctx->stream>>>(pv);
+                  rows_pivot_kernel<128><<<ctx->sm_count * 3, kPivThreads, 0, ctx->stream>>>(pv);
+                }
+                CK(cudaGetLastError());
+                ctx->launches += 2;
+                ra.list = pv.list2; ra.list_count = pv.count2;
+                trace_mark(ctx, "rows_pivot");
+              }
               CKS(launch_rows<float>(ctx, ra, n));
               trace_mark(ctx, "rows_top2");
             }
@@ -1263,6 +1293,7 @@ static lkm_status run_lloyd(lkm_ctx* ctx, F* dC2, uint64_t k, uint64_t max_iter,
       const unsigned long long mixed = ctx->h_state->mixed_tiles - mixed_seen;
       if (tc5_can_fuse && (double)mixed > fuse_mixed_limit * (double)((n + 127) / 128) * (double)todo_done) tc5_can_fuse = false;
       mixed_seen = ctx->h_state->mixed_tiles;
+      if (piv_ok && ctx->rows_pivot < 0) piv_now = (double)fb > piv_limit * (double)todo_done;
       if (sort_probe) {
         // more than one label change per four rows: the streaming update is bound by its per-row bookkeeping, sort instead
         use_sorted = (double)ctx->h_state->label_breaks > 0.25 * (double)n;
@@ -2420,6 +2451,7 @@ LKM_EXPORT lkm_status lkm_create(lkm_ctx** out, int device) {
   if (const char* v = std::getenv("LKM_ROWS_ASSIGN")) ctx->rows_assign = std::atoi(v);
   if (const char* v = std::getenv("LKM_FIN_CL")) ctx->fin_cl = std::atoi(v);
   if (const char* v = std::getenv("LKM_SORT_UPD")) ctx->sort_upd = std::atoi(v);
+  if (const char* v = std::getenv("LKM_ROWS_PIVOT")) ctx->rows_pivot = std::atoi(v);
   if (const char* v = std::getenv("LKM_STEP_TRACE")) ctx->step_trace = std::atoi(v);
   if (const char* v = std::getenv("LKM_SPARSE_PARTIALS")) ctx->sparse_partials = std::atoi(v);
   if (const char* v = std::getenv("LKM_TC5_DEFER")) ctx->tc5_defer = std::atoi(v);

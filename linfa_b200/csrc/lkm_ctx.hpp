@@ -129,6 +129,8 @@ struct lkm_ctx {
   double tc5_rescan_limit = 0.08;   // LKM_TC5_RESCAN_LIMIT: share of listed rows above which the pair kernel moves to 3xTF32
   int tc5_defer = 1;     // LKM_TC5_DEFER=0: undecided rows are scanned inline by the pair kernel instead of by rows_top2_kernel
   int last_update_path = 0;
+  int rows_pivot = -1;   // LKM_ROWS_PIVOT: -1 = pivot pruning (lkm_rows.cuh) of the listed rows once an iteration listed many, 0 never, 1 always
+  DevBuf piv_cc, piv_list2;
   int sort_upd = -1;     // LKM_SORT_UPD: -1 = sorted update (lkm_sortupd.cuh) when the first iteration finds the rows unordered, 0 never, 1 always
   DevBuf srt_hist, srt_seg, srt_perm, srt_ent, srt_inert;
   int upd_variant = 1;   // LKM_UPD=0: cluster-chunked lloyd_kernel<MODE_UPDATE> instead of update_rows_kernel

@@ -182,6 +182,16 @@ template <typename F> __device__ __forceinline__ void top2_update(F w, int c, F&
   idx = lt_b ? c : idx;
 }
 
+// running three lowest scores with the indices of the first two (equal scores: the earlier index stays in front)
+template <typename F> __device__ __forceinline__ void top3_update(F w, int c, F& best, F& second, F& third, int& ib, int& is) {
+  const bool lt_b = w < best, lt_s = w < second, lt_t = w < third;
+  third = lt_s ? second : (lt_t ? w : third);
+  second = lt_b ? best : (lt_s ? w : second);
+  is = lt_b ? ib : (lt_s ? c : is);
+  best = lt_b ? w : best;
+  ib = lt_b ? c : ib;
+}
+
 // Certified argmin on CUDA cores (expanded form): w_c = ||c||^2 - 2 x.c with FMA chains, running best
 // and second best.  With eps = 2^-24 (f32) / 2^-53 (f64), |w_c - W_c| <= eps[(2d+2)|x|C + 2C^2]
 // (d FMA roundings on the dot, one on ||c||^2, one on the final fma; C = max|c|) and the

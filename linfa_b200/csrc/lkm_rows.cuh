@@ -116,8 +116,8 @@ __global__ void __launch_bounds__(kRowsThreads) rows_top2_kernel(const RowsArgs<
       for (int j = 0; j < d; ++j) { const F v = __ldg(xp + j); xx = fma(v, v, xx); }
     }
     // ---- step 2: FMA scores, running best / runner-up ----
-    F b0 = (F)INFINITY, s0 = (F)INFINITY, b1 = (F)INFINITY, s1 = (F)INFINITY, cm = (F)0;
-    int i0 = 0, i1 = 1;
+    F b0 = (F)INFINITY, s0 = (F)INFINITY, t0 = (F)INFINITY, cm = (F)0;   // the three lowest scores, indices of the first two
+    int i0 = 0, j0 = 0;
     for (int ch = 0; ch < n_chunks; ++ch) {
       const int cb = ch * a.kc;
       int rc = min(a.kc, a.k - cb);
@@ -140,8 +140,8 @@ __global__ void __launch_bounds__(kRowsThreads) rows_top2_kernel(const RowsArgs<
         }
         const F n0 = cn[c], n1 = cn[c + 1];
         cm = fmax(cm, fmax(n0, n1));
-        top2_update<F>(fma((F)-2, d0, n0), cb + c, b0, s0, i0);
-        top2_update<F>(fma((F)-2, d1, n1), cb + c + 1, b1, s1, i1);
+        top3_update<F>(fma((F)-2, d0, n0), cb + c, b0, s0, t0, i0, j0);
+        top3_update<F>(fma((F)-2, d1, n1), cb + c + 1, b0, s0, t0, i0, j0);
       }
       if (c < rc) {
         F d0 = (F)0;
@@ -153,13 +153,11 @@ __global__ void __launch_bounds__(kRowsThreads) rows_top2_kernel(const RowsArgs<
         }
         const F n0 = cn[c];
         cm = fmax(cm, n0);
-        top2_update<F>(fma((F)-2, d0, n0), cb + c, b0, s0, i0);
+        top3_update<F>(fma((F)-2, d0, n0), cb + c, b0, s0, t0, i0, j0);
       }
     }
-    F best, second;
-    int bi;
-    if (b1 < b0 || (b1 == b0 && i1 < i0)) { best = b1; bi = i1; second = (b0 < s1) ? b0 : s1; }
-    else { best = b0; bi = i0; second = (b1 < s0) ? b1 : s0; }
+    const F best = b0, second = s0, third = t0;
+    int bi = i0;
     const F xn = sqrt(xx) * (F)1.000001, cmax = sqrt(cm) * (F)1.000001;
     const F dd = (F)d;
     // Certificate.  |w_c - W_c| <= errdot = eps [(2d+2)|x|C + 2C^2] for the FMA-form scores; the reference's direct form is
@@ -171,10 +169,19 @@ __global__ void __launch_bounds__(kRowsThreads) rows_top2_kernel(const RowsArgs<
     // the exact scan it saves — and a CTA-per-row exact scan — tiles from a k-means++ start hold dozens of open rows, which
     // thread = row handles side by side.)
     const F errdot = eps * (((F)2 * dd + (F)2) * xn * cmax + (F)2 * cmax * cmax);
-    const F dsum = fmax(best + xx, (F)0) + fmax(second + xx, (F)0) + (F)2 * errdot + (F)2 * (dd + (F)1) * eps * xx;
-    const F margin = (F)1.1 * ((F)2 * errdot + (dd + (F)2) * eps * dsum) + ((F)8 * dd + (F)16) * dmin * ((F)1 + xn + cmax);
-    const bool cert = (second - best) > margin;   // NaN / Inf anywhere -> false
-    const bool need_exact = valid && !cert;
+    const F tiny = ((F)8 * dd + (F)16) * dmin * ((F)1 + xn + cmax);
+    auto margin_to = [&](F other) {
+      const F dsum = fmax(best + xx, (F)0) + fmax(other + xx, (F)0) + (F)2 * errdot + (F)2 * (dd + (F)1) * eps * xx;
+      return (F)1.1 * ((F)2 * errdot + (dd + (F)2) * eps * dsum) + tiny;
+    };
+    const bool cert = (second - best) > margin_to(second);   // NaN / Inf anywhere -> false
+    // The same certificate against the THIRD lowest score: every centroid but the first two is proven farther than `best`
+    // in the reference's arithmetic, so its scan is decided between those two — two exact distances instead of k.  From a
+    // k-means++ start most open rows are of this kind (a blob shared by two centroids); a warp with one such row used to
+    // walk all k centroids in step 3.
+    const bool cert3 = (third - best) > margin_to(third);
+    const bool need_pair = valid && !cert && cert3;
+    const bool need_exact = valid && !cert && !cert3;
     // ---- step 3: the reference's scan for the rows without a certificate ----
     F eb = (F)INFINITY, es = (F)INFINITY;
     int ei = 0;
@@ -211,7 +218,17 @@ __global__ void __launch_bounds__(kRowsThreads) rows_top2_kernel(const RowsArgs<
     }
     if (!valid) continue;
     F bd = eb;
-    if (!need_exact) {
+    if (need_pair) {
+      F e0, e1;
+      if constexpr (D > 0) { e0 = sqdist_reg<F, D>(a.C + (size_t)i0 * D, x); e1 = sqdist_reg<F, D>(a.C + (size_t)j0 * D, x); }
+      else { e0 = sqdist_mem<F>(a.C + (size_t)i0 * d, xp, d); e1 = sqdist_mem<F>(a.C + (size_t)j0 * d, xp, d); }
+      // the strict-'<' scan in index order keeps the lower index on equal distances
+      const bool second_wins = e1 < e0 || (e1 == e0 && j0 < i0);
+      bi = second_wins ? j0 : i0;
+      bd = second_wins ? e1 : e0;
+      es = second_wins ? e0 : e1;
+      ++my_exact;
+    } else if (!need_exact) {
       if constexpr (D > 0) bd = sqdist_reg<F, D>(a.C + (size_t)bi * D, x);
       else bd = sqdist_mem<F>(a.C + (size_t)bi * d, xp, d);
     }
@@ -224,10 +241,14 @@ __global__ void __launch_bounds__(kRowsThreads) rows_top2_kernel(const RowsArgs<
       // bounds must bound the TRUE distances: the direct form is within (d + 2) eps of them
       const F slack = (dd + (F)4) * eps;
       a.ub[row] = (F)sqrt((double)bd) * ((F)1 + slack);
+      // a proven lower bound on the true squared distance behind an FMA-form score
+      auto below = [&](F w) {
+        return (w + xx) - (F)1.1 * eps * (((F)2 * dd + (F)2) * xn * cmax + (F)2 * cmax * cmax + (dd + (F)2) * xx) - tiny;
+      };
       F lsq;
       if (need_exact) lsq = es * ((F)1 - (F)2 * slack);
-      else lsq = (second + xx) - (F)1.1 * eps * (((F)2 * dd + (F)2) * xn * cmax + (F)2 * cmax * cmax + (dd + (F)2) * xx) -
-                 ((F)8 * dd + (F)16) * dmin * ((F)1 + xn + cmax);
+      else if (need_pair) lsq = fmin(es * ((F)1 - (F)2 * slack), below(third));   // the runner-up is the loser or a third centroid
+      else lsq = below(second);
       a.lb[row] = lsq > (F)0 ? (F)sqrt((double)lsq) * ((F)1 - slack) : (F)0;
     }
     if (a.fx_sums != nullptr && old != (uint32_t)bi) {
@@ -254,6 +275,114 @@ __global__ void __launch_bounds__(kRowsThreads) rows_top2_kernel(const RowsArgs<
   }
   if (a.n_exact != nullptr && my_exact) atomicAdd(a.n_exact, (unsigned long long)my_exact);
   if (a.n_changed != nullptr && my_changed) atomicAdd(a.n_changed, (unsigned long long)my_changed);
+}
+
+// ---- pivot pruning for listed rows (f32, d = 64 / 128) ------------------------------------------------------------------
+// The rows the screening kernel lists carry a provisional label b (its best TF32 score).  Whatever b is, a centroid c with
+// ||c - c_b|| > 2 ||x - c_b|| cannot be closer to x than c_b (triangle inequality), so the reference's scan is decided among
+// the few centroids inside that ball — from a k-means++ start the two or three that share the row's blob.  With the
+// roundings covered by the 2.001 / 1.0001 / 0.9999 factors below a pruned centroid is STRICTLY farther than c_b in the
+// reference's own arithmetic ((d + 2) eps relative on a squared distance, three orders of magnitude below the slack), so it
+// cannot win even on index order.  Rows with at most kPivMax survivors are decided here by the reference's scan (direct form,
+// strict '<', index order) over the survivors; the others (overlapping clusters, NaN / Inf / denormal-range data: nothing is
+// pruned) are passed on to rows_top2_kernel.  Replaces an FMA pass over all k centroids: 603 -> see profiles/README.md.
+constexpr int kPivMax = 8;
+constexpr int kPivThreads = 128;
+
+struct PivotArgs {
+  const float* X;
+  int k;
+  const float* C;
+  float* CC;                     // [k][k] lower bounds on the centroid-to-centroid distances (centroid_dist_kernel)
+  const uint32_t* list;
+  const unsigned int* count;
+  uint32_t* labels;              // in: provisional label of a listed row; out: final label of the rows decided here
+  uint32_t* list2;               // rows left for rows_top2_kernel
+  unsigned int* count2;
+  const LloydState* state;
+};
+
+// CTA b: lower bounds on ||c_b - c||, c = 0 .. k-1
+template <int D>
+__global__ void __launch_bounds__(128) centroid_dist_kernel(const PivotArgs a) {
+  if (a.state != nullptr && a.state->done) return;
+  if (*a.count == 0u) return;
+  __shared__ float cb[D];
+  const int b = blockIdx.x;
+  for (int j = threadIdx.x; j < D; j += 128) cb[j] = a.C[(size_t)b * D + j];
+  __syncthreads();
+  for (int c = threadIdx.x; c < a.k; c += 128) {
+    const float4* cp = reinterpret_cast<const float4*>(a.C + (size_t)c * D);
+    float s = 0.f;
+#pragma unroll 8
+    for (int q = 0; q < D / 4; ++q) {
+      const float4 v = __ldg(cp + q);
+      const float d0 = v.x - cb[4 * q], d1 = v.y - cb[4 * q + 1], d2 = v.z - cb[4 * q + 2], d3 = v.w - cb[4 * q + 3];
+      s = fmaf(d0, d0, fmaf(d1, d1, fmaf(d2, d2, fmaf(d3, d3, s))));
+    }
+    a.CC[(size_t)b * a.k + c] = sqrtf(s) * 0.9999f;
+  }
+}
+
+template <int D>
+__global__ void __launch_bounds__(kPivThreads) rows_pivot_kernel(const PivotArgs a) {
+  if (a.state != nullptr && a.state->done) return;
+  __shared__ uint16_t surv[kPivThreads][kPivMax];
+  const int t = threadIdx.x, lane = t & 31;
+  const unsigned int total = *a.count;
+  const unsigned int n_tiles = (total + kPivThreads - 1) / kPivThreads;
+  const unsigned lt = (1u << lane) - 1u;
+  for (unsigned int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const unsigned int idx = tile * kPivThreads + t;
+    const bool valid = idx < total;
+    const uint32_t row = valid ? a.list[idx] : 0u;
+    float x[D];
+    rows_load<float, D>(a.X + (size_t)row * D, x);
+    uint32_t b = valid ? a.labels[row] : 0u;
+    if (b >= (uint32_t)a.k) b = 0u;
+    const float bd = sqdist_reg<float, D>(a.C + (size_t)b * D, x);
+    // nothing is pruned (threshold +inf) when the distance is not a normal number of moderate size
+    const float thr = (valid && bd > 1e-30f && bd < 1e30f) ? 2.001f * (sqrtf(bd) * 1.0001f) : INFINITY;
+    int my_cnt = 0;
+    for (int r = 0; r < 32; ++r) {
+      const uint32_t b_r = __shfl_sync(0xffffffffu, b, r);
+      const float thr_r = __shfl_sync(0xffffffffu, thr, r);
+      const float* ccr = a.CC + (size_t)b_r * a.k;
+      int cnt_r = 0;
+      for (int c0 = 0; c0 < a.k; c0 += 32) {
+        const int c = c0 + lane;
+        const bool keep = c < a.k && !(ccr[c] > thr_r);   // NaN distances are kept
+        const unsigned m = __ballot_sync(0xffffffffu, keep);
+        if (keep) {
+          const int pos = cnt_r + __popc(m & lt);
+          if (pos < kPivMax) surv[(t & ~31) + r][pos] = (uint16_t)c;
+        }
+        cnt_r += __popc(m);
+      }
+      if (lane == r) my_cnt = cnt_r;
+    }
+    __syncwarp();
+    const bool open = valid && my_cnt > kPivMax;
+    if (valid && !open) {
+      float eb = INFINITY;
+      int ei = 0;
+      for (int i = 0; i < my_cnt; ++i) {
+        const int c = surv[t][i];
+        const float v = sqdist_reg<float, D>(a.C + (size_t)c * D, x);
+        if (c == 0) { eb = v; ei = 0; }   // centroid 0 seeds the reference's scan (a NaN there is sticky)
+        else if (v < eb) { eb = v; ei = c; }
+      }
+      a.labels[row] = (uint32_t)ei;
+    }
+    const unsigned fm = __ballot_sync(0xffffffffu, open);
+    if (fm != 0u) {
+      unsigned int base = 0;
+      if (lane == 0) base = atomicAdd(a.count2, (unsigned int)__popc(fm));
+      base = __shfl_sync(0xffffffffu, base, 0);
+      if (open) a.list2[base + __popc(fm & lt)] = row;
+    }
+    __syncwarp();
+  }
 }
 
 }  // namespace lkm
