@@ -1017,10 +1017,10 @@ static lkm_status run_lloyd(lkm_ctx* ctx, F* dC2, uint64_t k, uint64_t max_iter,
                 CK(cudaMemsetAsync(pv.count2, 0, 4, ctx->stream));
                 if (d == 64) {
                   centroid_dist_kernel<64><<<(unsigned)k, 128, 0, ctx->stream>>>(pv);
-                  rows_pivot_kernel<64><<<ctx->sm_count * 4, kPivThreads, 0, ctx->stream>>>(pv);
+                  rows_pivot_kernel<64, false><<<ctx->sm_count * 4, kPivThreads, 0, ctx->stream>>>(pv);
                 } else {
                   centroid_dist_kernel<128><<<(unsigned)k, 128, 0, ctx->stream>>>(pv);
-                  rows_pivot_kernel<128><<<ctx->sm_count * 3, kPivThreads, 0, ctx->stream>>>(pv);
+                  rows_pivot_kernel<128, false><<<ctx->sm_count * 3, kPivThreads, 0, ctx->stream>>>(pv);
                 }
                 CK(cudaGetLastError());
                 ctx->launches += 2;
@@ -1387,10 +1387,17 @@ static lkm_status run_lloyd(lkm_ctx* ctx, F* dC2, uint64_t k, uint64_t max_iter,
 template <typename F>
 static lkm_status inertia_pass(lkm_ctx* ctx, const F* dC, double& total) {
   const uint64_t n = ctx->n, d = ctx->d;
-  const int grid = (int)std::max<uint64_t>(1, std::min<uint64_t>((n + 255) / 256, 1024));
   CK(ctx->ham_red.ensure(1024 * 8));
-  inertia_rows_kernel<F><<<grid, 256, 0, ctx->stream>>>(reinterpret_cast<const F*>(ctx->X), n, (int)d, dC, ctx->labels.as<uint32_t>(),
-                                                         ctx->ham_red.as<double>());
+  const F* dX = reinterpret_cast<const F*>(ctx->X);
+  constexpr int kVec = 16 / (int)sizeof(F);
+  const bool vec = d % kVec == 0 && (reinterpret_cast<uintptr_t>(dX) & 15) == 0 && (reinterpret_cast<uintptr_t>(dC) & 15) == 0;
+  const uint64_t per_row = vec ? d / kVec : d;   // loads per row
+  int lpr = 1;
+  while (lpr < 32 && (uint64_t)lpr < per_row) lpr *= 2;
+  const uint64_t rows_per_cta = (uint64_t)8 * (32 / lpr);
+  const int grid = (int)std::max<uint64_t>(1, std::min<uint64_t>((n + rows_per_cta - 1) / rows_per_cta, std::min(1024, ctx->sm_count * 8)));
+  if (vec) inertia_rows_kernel<F, kVec><<<grid, 256, 0, ctx->stream>>>(dX, n, (int)d, dC, ctx->labels.as<uint32_t>(), ctx->ham_red.as<double>(), lpr);
+  else inertia_rows_kernel<F, 1><<<grid, 256, 0, ctx->stream>>>(dX, n, (int)d, dC, ctx->labels.as<uint32_t>(), ctx->ham_red.as<double>(), lpr);
   CK(cudaGetLastError());
   ctx->launches++;
   CK(cudaMemcpyAsync(ctx->h_pin, ctx->ham_red.p, (size_t)grid * 8, cudaMemcpyDeviceToHost, ctx->stream));
@@ -1488,6 +1495,12 @@ static lkm_status run_hamerly(lkm_ctx* ctx, F* dC2, uint64_t k, uint64_t max_ite
       return LKM_OK;
     };
     CKS(moved_and_state(dC2, dC2 + kd, false));   // iteration 1 moved the centroids from buffer 0 to buffer 1
+    const bool ham_pivot = std::is_same<F, float>::value && ctx->rows_pivot != 0 && (d == 64 || d == 128) && k <= 4096 && n < (1ull << 32) - 512 &&
+                           (reinterpret_cast<uintptr_t>(dX) & 15) == 0;
+    if (ham_pivot) {
+      CK(ctx->piv_cc.ensure(k * k * 4));
+      CK(ctx->piv_list2.ensure((n + 256) * 4 + 64));
+    }
     uint64_t it = 1;
     const int bgrid = (int)std::max<uint64_t>(1, std::min<uint64_t>((n + 255) / 256, (uint64_t)ctx->sm_count * 8));
     for (;;) {
@@ -1498,14 +1511,40 @@ static lkm_status run_hamerly(lkm_ctx* ctx, F* dC2, uint64_t k, uint64_t max_ite
         HamArgs<F> ha{};
         ha.X = dX; ha.n = n; ha.d = (int)d; ha.k = (int)k; ha.C = cur; ha.labels = ctx->labels.as<uint32_t>(); ha.ub = ub; ha.lb = lb;
         ha.moved = ctx->ham_moved.as<F>(); ha.s = ctx->ham_s.as<F>(); ha.list = ctx->ham_list.as<uint32_t>(); ha.hs = hs; ha.state = dstate;
+        trace_mark(ctx, "start");
         hamerly_bounds_kernel<F><<<bgrid, 256, 0, ctx->stream>>>(ha);
         CK(cudaGetLastError());
         ctx->launches++;
+        trace_mark(ctx, "hamerly_bounds");
         RowsArgs<F> ra{};
         ra.X = dX; ra.n = n; ra.d = (int)d; ra.k = (int)k; ra.C = cur; ra.list = ctx->ham_list.as<uint32_t>(); ra.list_count = &hs->list_count;
         ra.labels = ctx->labels.as<uint32_t>(); ra.ub = ub; ra.lb = lb; ra.fx_sums = fx_sums; ra.fx_counts = fx_counts; ra.fx_scale = scale;
         ra.state = dstate; ra.n_exact = &hs->rows_exact; ra.n_changed = &hs->rows_changed;
+        if constexpr (std::is_same<F, float>::value) {
+          if (ham_pivot) {
+            // rows whose bounds failed: decided among the centroids near their current one when those are few (lkm_rows.cuh)
+            PivotArgs pv{};
+            pv.X = dX; pv.k = (int)k; pv.C = cur; pv.CC = ctx->piv_cc.as<float>(); pv.list = ra.list; pv.count = ra.list_count;
+            pv.labels = ra.labels; pv.list2 = ctx->piv_list2.as<uint32_t>();
+            pv.count2 = reinterpret_cast<unsigned int*>(ctx->piv_list2.as<uint32_t>() + ((n + 256) & ~(uint64_t)3));
+            pv.state = dstate; pv.ub = ub; pv.lb = lb; pv.fx_sums = fx_sums; pv.fx_counts = fx_counts; pv.fx_scale = scale;
+            pv.n_exact = &hs->rows_exact; pv.n_changed = &hs->rows_changed;
+            CK(cudaMemsetAsync(pv.count2, 0, 4, ctx->stream));
+            if (d == 64) {
+              centroid_dist_kernel<64><<<(unsigned)k, 128, 0, ctx->stream>>>(pv);
+              rows_pivot_kernel<64, true><<<ctx->sm_count * 4, kPivThreads, 0, ctx->stream>>>(pv);
+            } else {
+              centroid_dist_kernel<128><<<(unsigned)k, 128, 0, ctx->stream>>>(pv);
+              rows_pivot_kernel<128, true><<<ctx->sm_count * 3, kPivThreads, 0, ctx->stream>>>(pv);
+            }
+            CK(cudaGetLastError());
+            ctx->launches += 2;
+            ra.list = pv.list2; ra.list_count = pv.count2;
+            trace_mark(ctx, "hamerly_rows_pivot");
+          }
+        }
         CKS(launch_rows<F>(ctx, ra, n));
+        trace_mark(ctx, "hamerly_rows_top2");
         HamCenArgs<F> ca{};
         ca.fx_sums = fx_sums; ca.fx_counts = fx_counts; ca.inv_scale = inv_scale; ca.k = (int)k; ca.d = (int)d; ca.C_old = cur; ca.C_new = nxt;
         ca.shift_part = ctx->shift_part.as<double>(); ca.counts_out = ctx->counts_out.as<double>(); ca.state = dstate;
@@ -1513,6 +1552,7 @@ static lkm_status run_hamerly(lkm_ctx* ctx, F* dC2, uint64_t k, uint64_t max_ite
         CK(cudaGetLastError());
         ctx->launches++;
         CKS(moved_and_state(cur, nxt, true));
+        trace_mark(ctx, "hamerly_centroids_moved");
       }
       CK(cudaMemcpyAsync(ctx->h_state, dstate, sizeof(LloydState), cudaMemcpyDeviceToHost, ctx->stream));
       CK(cudaStreamSynchronize(ctx->stream));
@@ -1534,6 +1574,8 @@ static lkm_status run_hamerly(lkm_ctx* ctx, F* dC2, uint64_t k, uint64_t max_ite
     ctx->ham_rows_tightened = hh.rows_tightened;
   }
   CKS(inertia_pass<F>(ctx, dC2 + (size_t)out.final_buf * kd, out.inertia));
+  trace_mark(ctx, "inertia_pass");
+  trace_report(ctx);
   ctx->kept_labels_n = n;
   return LKM_OK;
 }

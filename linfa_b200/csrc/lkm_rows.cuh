@@ -300,6 +300,14 @@ struct PivotArgs {
   uint32_t* list2;               // rows left for rows_top2_kernel
   unsigned int* count2;
   const LloydState* state;
+  // Hamerly (HAM = true): bounds and the move between the running sums, as in RowsArgs
+  float* ub;
+  float* lb;
+  long long* fx_sums;
+  long long* fx_counts;
+  double fx_scale;
+  unsigned long long* n_exact;
+  unsigned long long* n_changed;
 };
 
 // CTA b: lower bounds on ||c_b - c||, c = 0 .. k-1
@@ -324,7 +332,7 @@ __global__ void __launch_bounds__(128) centroid_dist_kernel(const PivotArgs a) {
   }
 }
 
-template <int D>
+template <int D, bool HAM>
 __global__ void __launch_bounds__(kPivThreads) rows_pivot_kernel(const PivotArgs a) {
   if (a.state != nullptr && a.state->done) return;
   __shared__ uint16_t surv[kPivThreads][kPivMax];
@@ -332,47 +340,84 @@ __global__ void __launch_bounds__(kPivThreads) rows_pivot_kernel(const PivotArgs
   const unsigned int total = *a.count;
   const unsigned int n_tiles = (total + kPivThreads - 1) / kPivThreads;
   const unsigned lt = (1u << lane) - 1u;
+  unsigned int my_exact = 0, my_changed = 0;
   for (unsigned int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const unsigned int idx = tile * kPivThreads + t;
     const bool valid = idx < total;
     const uint32_t row = valid ? a.list[idx] : 0u;
     float x[D];
     rows_load<float, D>(a.X + (size_t)row * D, x);
-    uint32_t b = valid ? a.labels[row] : 0u;
-    if (b >= (uint32_t)a.k) b = 0u;
+    const uint32_t old = valid ? a.labels[row] : 0u;
+    const uint32_t b = old < (uint32_t)a.k ? old : 0u;
     const float bd = sqdist_reg<float, D>(a.C + (size_t)b * D, x);
     // nothing is pruned (threshold +inf) when the distance is not a normal number of moderate size
-    const float thr = (valid && bd > 1e-30f && bd < 1e30f) ? 2.001f * (sqrtf(bd) * 1.0001f) : INFINITY;
+    const bool normal = valid && bd > 1e-30f && bd < 1e30f;
+    const float ub_b = sqrtf(bd) * 1.0001f;   // >= the true distance to the pivot
+    const float thr = normal ? 2.001f * ub_b : INFINITY;
     int my_cnt = 0;
+    float my_ccmin = INFINITY;   // HAM: the nearest pruned centroid to the pivot
     for (int r = 0; r < 32; ++r) {
       const uint32_t b_r = __shfl_sync(0xffffffffu, b, r);
       const float thr_r = __shfl_sync(0xffffffffu, thr, r);
       const float* ccr = a.CC + (size_t)b_r * a.k;
       int cnt_r = 0;
+      float ccmin = INFINITY;
       for (int c0 = 0; c0 < a.k; c0 += 32) {
         const int c = c0 + lane;
-        const bool keep = c < a.k && !(ccr[c] > thr_r);   // NaN distances are kept
+        const float cc = c < a.k ? ccr[c] : INFINITY;
+        const bool keep = c < a.k && !(cc > thr_r);   // NaN distances are kept
         const unsigned m = __ballot_sync(0xffffffffu, keep);
         if (keep) {
           const int pos = cnt_r + __popc(m & lt);
           if (pos < kPivMax) surv[(t & ~31) + r][pos] = (uint16_t)c;
+        } else if (HAM) {
+          ccmin = fminf(ccmin, cc);
         }
         cnt_r += __popc(m);
+      }
+      if (HAM) {
+        for (int o = 16; o > 0; o >>= 1) ccmin = fminf(ccmin, __shfl_xor_sync(0xffffffffu, ccmin, o));
+        if (lane == r) my_ccmin = ccmin;
       }
       if (lane == r) my_cnt = cnt_r;
     }
     __syncwarp();
     const bool open = valid && my_cnt > kPivMax;
     if (valid && !open) {
-      float eb = INFINITY;
+      float eb = INFINITY, es = INFINITY;
       int ei = 0;
       for (int i = 0; i < my_cnt; ++i) {
         const int c = surv[t][i];
         const float v = sqdist_reg<float, D>(a.C + (size_t)c * D, x);
         if (c == 0) { eb = v; ei = 0; }   // centroid 0 seeds the reference's scan (a NaN there is sticky)
-        else if (v < eb) { eb = v; ei = c; }
+        else if (v < eb) { es = eb; eb = v; ei = c; }
+        else if (v < es) es = v;
       }
       a.labels[row] = (uint32_t)ei;
+      ++my_exact;
+      if (HAM) {
+        // bounds on the TRUE distances: the direct form is within (d + 2) eps of them.  The runner-up is a survivor (exact
+        // distance es) or a pruned centroid, which is at least CC[b][c] - ||x - c_b|| away.
+        const float slack = ((float)D + 4.f) * rows_eps<float>();
+        a.ub[row] = (float)sqrt((double)eb) * (1.f + slack);
+        const float lsq = es * (1.f - 2.f * slack);
+        const float lb_surv = lsq > 0.f ? (float)sqrt((double)lsq) * (1.f - slack) : 0.f;
+        const float lb_pruned = (my_ccmin - ub_b) * 0.9999f;
+        a.lb[row] = fmaxf(fminf(lb_surv, lb_pruned), 0.f);
+        if (old != (uint32_t)ei) {
+          ++my_changed;
+          unsigned long long* so = reinterpret_cast<unsigned long long*>(a.fx_sums) + (size_t)old * D;
+          unsigned long long* sn = reinterpret_cast<unsigned long long*>(a.fx_sums) + (size_t)ei * D;
+#pragma unroll
+          for (int j = 0; j < D; ++j) {
+            const long long q = __double2ll_rn((double)x[j] * a.fx_scale);
+            atomicAdd(so + j, (unsigned long long)(-q));
+            atomicAdd(sn + j, (unsigned long long)q);
+          }
+          atomicAdd(reinterpret_cast<unsigned long long*>(a.fx_counts) + old, (unsigned long long)(-1ll));
+          atomicAdd(reinterpret_cast<unsigned long long*>(a.fx_counts) + ei, 1ull);
+        }
+      }
     }
     const unsigned fm = __ballot_sync(0xffffffffu, open);
     if (fm != 0u) {
@@ -382,6 +427,10 @@ __global__ void __launch_bounds__(kPivThreads) rows_pivot_kernel(const PivotArgs
       if (open) a.list2[base + __popc(fm & lt)] = row;
     }
     __syncwarp();
+  }
+  if (HAM) {
+    if (a.n_exact != nullptr && my_exact) atomicAdd(a.n_exact, (unsigned long long)my_exact);
+    if (a.n_changed != nullptr && my_changed) atomicAdd(a.n_changed, (unsigned long long)my_changed);
   }
 }
 
