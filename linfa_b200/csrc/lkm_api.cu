@@ -27,6 +27,7 @@
 #include "lkm_tc4.cuh"
 #include "lkm_upd.cuh"
 #include "lkm_sortupd.cuh"
+#include "lkm_seedpass.cuh"
 #include "lkm_tc5.cuh"
 #include "lkm_f64s.cuh"
 #include "lkm_rows.cuh"
@@ -240,6 +241,32 @@ static lkm_status run_assign(lkm_ctx* ctx, const F* dX, uint64_t n, uint64_t d, 
     ra.X = dX; ra.n = n; ra.d = (int)d; ra.k = (int)k; ra.C = dC; ra.all_rows = n;
     ra.labels = labels; ra.best_dist = dists; ra.min_combine = min_combine;
     return launch_rows<F>(ctx, ra, n);
+  }
+  // one centroid, distances only: the per-pick pass of k-means++ at the HBM rate (lkm_seedpass.cuh)
+  if constexpr (std::is_same<F, float>::value) {
+    if (ctx->seed_pass && ctx->force_path != 0 && k == 1 && labels == nullptr && dists != nullptr && (d == 32 || d == 64 || d == 128) &&
+        (reinterpret_cast<uintptr_t>(dX) & 15) == 0 && (reinterpret_cast<uintptr_t>(dC) & 15) == 0) {
+      SeedPassArgs sp{};
+      sp.X = dX; sp.n = n; sp.c = dC; sp.dists = dists; sp.min_combine = min_combine; sp.weights = weights; sp.wdists = wdists;
+      const size_t smem = d == 32 ? seedpass_smem_bytes<32>() : (d == 64 ? seedpass_smem_bytes<64>() : seedpass_smem_bytes<128>());
+      const void* fn = d == 32 ? (const void*)seed_pass_kernel<32> : (d == 64 ? (const void*)seed_pass_kernel<64> : (const void*)seed_pass_kernel<128>);
+      static bool configured[3] = {false, false, false};
+      const int slot = d == 32 ? 0 : (d == 64 ? 1 : 2);
+      if (!configured[slot]) {
+        CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CK(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
+        configured[slot] = true;
+      }
+      const int occ = std::max(1, (int)((ctx->smem_optin + 1024) / (smem + 1024)));
+      const uint64_t tiles = (n + kSpRows - 1) / kSpRows;
+      const int grid = (int)std::max<uint64_t>(1, std::min<uint64_t>(tiles, (uint64_t)ctx->sm_count * std::min(occ, 4)));
+      if (d == 32) seed_pass_kernel<32><<<grid, kSpRows, smem, ctx->stream>>>(sp);
+      else if (d == 64) seed_pass_kernel<64><<<grid, kSpRows, smem, ctx->stream>>>(sp);
+      else seed_pass_kernel<128><<<grid, kSpRows, smem, ctx->stream>>>(sp);
+      CK(cudaGetLastError());
+      ctx->launches++;
+      return LKM_OK;
+    }
   }
   Plan p;
   CKS(plan_assign<F>(ctx, dX, n, d, k, p));
@@ -885,8 +912,9 @@ static lkm_status run_lloyd(lkm_ctx* ctx, F* dC2, uint64_t k, uint64_t max_iter,
   const double tc5_rescan_limit = ctx->tc5_defer ? ctx->tc5_rescan_limit : 0.004, tc4_rescan_limit = 0.02, fuse_mixed_limit = 0.25;
   unsigned long long mixed_seen = 0;
   unsigned long long fb_seen = 0;
-  // listed rows per iteration above which they go through the pivot pruning first (decided from the previous batch)
-  bool piv_now = piv_ok && ctx->rows_pivot > 0;
+  // the listed rows go through the pivot pruning first: always in the first batch of a call (one iteration when the screening
+  // kernel probes), afterwards when the previous batch listed more than piv_limit rows per iteration
+  bool piv_now = piv_ok;
   const double piv_limit = 2048.0;
   for (;;) {
     const uint64_t todo = std::min<uint64_t>((tc4_probe || tc5_probe || sort_probe) ? 1 : batch, max_iter - launched);
@@ -2493,6 +2521,7 @@ LKM_EXPORT lkm_status lkm_create(lkm_ctx** out, int device) {
   if (const char* v = std::getenv("LKM_ROWS_ASSIGN")) ctx->rows_assign = std::atoi(v);
   if (const char* v = std::getenv("LKM_FIN_CL")) ctx->fin_cl = std::atoi(v);
   if (const char* v = std::getenv("LKM_SORT_UPD")) ctx->sort_upd = std::atoi(v);
+  if (const char* v = std::getenv("LKM_SEED_PASS")) ctx->seed_pass = std::atoi(v);
   if (const char* v = std::getenv("LKM_ROWS_PIVOT")) ctx->rows_pivot = std::atoi(v);
   if (const char* v = std::getenv("LKM_STEP_TRACE")) ctx->step_trace = std::atoi(v);
   if (const char* v = std::getenv("LKM_SPARSE_PARTIALS")) ctx->sparse_partials = std::atoi(v);

@@ -1,0 +1,108 @@
+// The distance pass of k-means++ (KM/init.rs:138-147): after every pick, d_i = min(d_i, ||c_new - x_i||^2) for ALL rows and
+// wd_i = w_i d_i for the next weighted draw.  k - 1 such passes read the whole matrix once each — for cfg3 that is 255 x 5.12 GB,
+// ten times the traffic of the Lloyd iterations that follow — so the pass has to run at the HBM rate while keeping the
+// reference's arithmetic: the squared distance in the direct form, feature by feature, never contracted (the min distances
+// are compared bit for bit with the oracle's).  The generic assignment kernel (one centroid = no reuse, runtime d) reached
+// 3.1 TB/s.  Here: 128-row tiles stream through a 3-stage cp.async ring into shared memory with a row stride of d + 4 floats
+// (16-byte chunks land conflict-free, and so do the 128-bit reads of thread = row), the centroid sits in registers, each
+// thread walks its row in feature order.
+#pragma once
+#include "lkm_kernels.cuh"
+
+namespace lkm {
+
+constexpr int kSpRows = 128;     // rows per tile = threads per CTA
+constexpr int kSpStages = 3;
+
+struct SeedPassArgs {
+  const float* X;
+  unsigned long long n;
+  const float* c;          // the centroid picked last (d floats)
+  float* dists;            // running minimum (in / out)
+  int min_combine;         // 0: first pass, dists = distance
+  const float* weights;    // optional
+  float* wdists;           // optional: (weights ? weights[i] : 1) * dists[i]
+};
+
+template <int D> __host__ __device__ constexpr size_t seedpass_smem_bytes() { return (size_t)kSpStages * kSpRows * (D + 4) * 4; }
+
+__device__ __forceinline__ void sp_cp_async16(uint32_t dst, const void* src, int src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void sp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void sp_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+template <int D>
+__global__ void __launch_bounds__(kSpRows) seed_pass_kernel(const SeedPassArgs a) {
+  static_assert(D % 4 == 0 && D >= 16 && D <= 128, "row width");
+  constexpr int RS = D + 4;          // shared-memory row stride in floats
+  constexpr int CPR = D / 4;         // 16-byte chunks per row
+  constexpr int CPT = CPR;           // chunks per thread and tile (kSpRows * CPR / kSpRows)
+  extern __shared__ __align__(16) float sp_smem[];
+  const int t = threadIdx.x;
+  const unsigned long long n_tiles = (a.n + kSpRows - 1) / kSpRows;
+  float c[D];
+#pragma unroll
+  for (int j = 0; j < D; j += 4) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(a.c + j));
+    c[j] = v.x; c[j + 1] = v.y; c[j + 2] = v.z; c[j + 3] = v.w;
+  }
+  const uint32_t s_base = (uint32_t)__cvta_generic_to_shared(sp_smem);
+  auto issue = [&](unsigned long long tile, int st) {
+    const unsigned long long row0 = tile * kSpRows;
+    const float* src = a.X + row0 * D;
+    const uint32_t dst = s_base + (uint32_t)st * (uint32_t)(kSpRows * RS * 4);
+    const bool whole = row0 + kSpRows <= a.n;
+#pragma unroll
+    for (int i = 0; i < CPT; ++i) {
+      const int q = t + i * kSpRows;            // chunk of the tile: consecutive threads, consecutive 16 bytes of X
+      const int r = q / CPR, cc = q % CPR;
+      const bool ok = whole || row0 + (unsigned)r < a.n;
+      sp_cp_async16(dst + (uint32_t)(r * RS + cc * 4) * 4u, ok ? (const void*)(src + (size_t)q * 4) : (const void*)a.X, ok ? 16 : 0);
+    }
+  };
+  unsigned long long tile = blockIdx.x;
+#pragma unroll
+  for (int s = 0; s < kSpStages - 1; ++s) {
+    if (tile + (unsigned long long)s * gridDim.x < n_tiles) issue(tile + (unsigned long long)s * gridDim.x, s);
+    sp_commit();
+  }
+  int st = 0;
+  for (; tile < n_tiles; tile += gridDim.x) {
+    const unsigned long long ahead = tile + (unsigned long long)(kSpStages - 1) * gridDim.x;
+    int st_ahead = st + kSpStages - 1;
+    if (st_ahead >= kSpStages) st_ahead -= kSpStages;
+    if (ahead < n_tiles) issue(ahead, st_ahead);   // the stage read in the previous iteration (all threads passed its barrier)
+    sp_commit();
+    sp_wait<kSpStages - 1>();
+    __syncthreads();
+    const float* xr = sp_smem + (size_t)st * (kSpRows * RS) + (size_t)t * RS;
+    float acc = 0.f;
+#pragma unroll
+    for (int j = 0; j < D; j += 4) {
+      const float4 v = *reinterpret_cast<const float4*>(xr + j);
+      const float d0 = Rn<float>::sub(c[j], v.x), d1 = Rn<float>::sub(c[j + 1], v.y);
+      const float d2 = Rn<float>::sub(c[j + 2], v.z), d3 = Rn<float>::sub(c[j + 3], v.w);
+      acc = Rn<float>::add(acc, Rn<float>::mul(d0, d0));
+      acc = Rn<float>::add(acc, Rn<float>::mul(d1, d1));
+      acc = Rn<float>::add(acc, Rn<float>::mul(d2, d2));
+      acc = Rn<float>::add(acc, Rn<float>::mul(d3, d3));
+    }
+    const unsigned long long row = tile * kSpRows + t;
+    if (row < a.n) {
+      float outd = acc;
+      if (a.min_combine) {
+        const float old = a.dists[row];
+        if (acc < old) a.dists[row] = acc; else outd = old;
+      } else {
+        a.dists[row] = acc;
+      }
+      if (a.wdists != nullptr) a.wdists[row] = a.weights != nullptr ? outd * a.weights[row] : outd;
+    }
+    __syncthreads();   // the stage may be refilled by the next iteration's issue
+    if (++st == kSpStages) st = 0;
+  }
+  sp_wait<0>();
+}
+
+}  // namespace lkm
