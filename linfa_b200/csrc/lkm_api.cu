@@ -917,7 +917,7 @@ static lkm_status run_lloyd(lkm_ctx* ctx, F* dC2, uint64_t k, uint64_t max_iter,
   bool piv_now = piv_ok;
   const double piv_limit = 2048.0;
   for (;;) {
-    const uint64_t todo = std::min<uint64_t>((tc4_probe || tc5_probe || sort_probe) ? 1 : batch, max_iter - launched);
+    const uint64_t todo = std::min<uint64_t>((tc4_probe || tc5_probe) ? 1 : batch, max_iter - launched);
     for (uint64_t q = 0; q < todo; ++q) {
       const uint64_t it = launched + q;
       const F* Ccur = dC2 + (it & 1) * kd;
@@ -1114,11 +1114,20 @@ static lkm_status run_lloyd(lkm_ctx* ctx, F* dC2, uint64_t k, uint64_t max_iter,
         bool updated = false;
         if constexpr (std::is_same<F, float>::value) {
           if (use_upd && sort_probe) {
+            // decided here, between the assignment and the update of the call's first iteration: one host round trip (~20 us)
+            // against 1.6 ms of streaming update on the unordered rows of cfg3.  More than one label change per four rows:
+            // the streaming update is bound by its per-row bookkeeping, sort instead.  What the fused screening kernel may
+            // already have accumulated is simply not read (the sorted update sums every row).
             label_breaks_kernel<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(ctx->labels.as<uint32_t>(), n, dstate);
             CK(cudaGetLastError());
             ctx->launches++;
+            CK(cudaMemcpyAsync(ctx->h_state, dstate, sizeof(LloydState), cudaMemcpyDeviceToHost, ctx->stream));
+            CK(cudaStreamSynchronize(ctx->stream));
+            use_sorted = (double)ctx->h_state->label_breaks > 0.25 * (double)n;
+            if (use_sorted) tc5_can_fuse = false;
+            sort_probe = false;
           }
-          if (use_upd && use_sorted && !fused_now) {
+          if (use_upd && use_sorted) {
             SortArgs sa{};
             sa.labels = ctx->labels.as<uint32_t>(); sa.n = n; sa.k = (int)k; sa.hist = ctx->srt_hist.as<uint32_t>();
             sa.seg_start = ctx->srt_seg.as<uint32_t>(); sa.perm = ctx->srt_perm.as<uint32_t>();
@@ -1322,12 +1331,6 @@ static lkm_status run_lloyd(lkm_ctx* ctx, F* dC2, uint64_t k, uint64_t max_iter,
       if (tc5_can_fuse && (double)mixed > fuse_mixed_limit * (double)((n + 127) / 128) * (double)todo_done) tc5_can_fuse = false;
       mixed_seen = ctx->h_state->mixed_tiles;
       if (piv_ok && ctx->rows_pivot < 0) piv_now = (double)fb > piv_limit * (double)todo_done;
-      if (sort_probe) {
-        // more than one label change per four rows: the streaming update is bound by its per-row bookkeeping, sort instead
-        use_sorted = (double)ctx->h_state->label_breaks > 0.25 * (double)n;
-        if (use_sorted) tc5_can_fuse = false;
-        sort_probe = false;
-      }
       tc4_probe = false;
       tc5_probe = false;
     }

@@ -68,7 +68,10 @@ static __global__ void __launch_bounds__(kSrtThreads) sort_hist_kernel(const Sor
   for (int c = lane; c < a.k; c += 32) a.hist[g * a.k + c] = ctr[c];
 }
 
-// block (32, 32): x = label within the CTA's group of 32, y = slice of the segments
+// block (32, 32): x = label within the CTA's group of 32 (coalesced 128-byte accesses), y = slice of the segments; every
+// thread walks its slice in batches of 8 independent loads (one load per step is a chain of L2 latencies: 52 us for the
+// 4883 x 256 counters of cfg3; column-wise layouts — a warp per label, or 4 labels per CTA — were slower still, 90 - 122 us).
+// The last CTA turns the k totals into seg_start.
 static __global__ void __launch_bounds__(1024) sort_scan_kernel(const SortArgs a) {
   if (a.state != nullptr && a.state->done) return;
   __shared__ uint32_t part[32][33];
@@ -79,18 +82,31 @@ static __global__ void __launch_bounds__(1024) sort_scan_kernel(const SortArgs a
   const unsigned long long n_seg = (a.n + kSrtSegRows - 1) / kSrtSegRows;
   const unsigned long long per = (n_seg + 31) / 32;
   const unsigned long long g0 = min(n_seg, per * y), g1 = min(n_seg, g0 + per);
+  constexpr int B = 8;
   uint32_t s = 0;
-  if (c < a.k)
-    for (unsigned long long g = g0; g < g1; ++g) s += a.hist[g * a.k + c];
+  if (c < a.k) {
+    for (unsigned long long g = g0; g < g1; g += B) {
+      uint32_t h[B];
+#pragma unroll
+      for (int i = 0; i < B; ++i) h[i] = g + i < g1 ? a.hist[(g + i) * a.k + c] : 0u;
+#pragma unroll
+      for (int i = 0; i < B; ++i) s += h[i];
+    }
+  }
   part[y][x] = s;
   __syncthreads();
   uint32_t run = 0;
   for (int yy = 0; yy < y; ++yy) run += part[yy][x];
   if (c < a.k) {
-    for (unsigned long long g = g0; g < g1; ++g) {
-      const uint32_t h = a.hist[g * a.k + c];
-      a.hist[g * a.k + c] = run;
-      run += h;
+    for (unsigned long long g = g0; g < g1; g += B) {
+      uint32_t h[B];
+#pragma unroll
+      for (int i = 0; i < B; ++i) h[i] = g + i < g1 ? a.hist[(g + i) * a.k + c] : 0u;
+#pragma unroll
+      for (int i = 0; i < B; ++i) {
+        if (g + i < g1) a.hist[(g + i) * a.k + c] = run;
+        run += h[i];
+      }
     }
     if (y == 31) a.seg_start[c + 1] = run;   // the label's total, until the last CTA turns the totals into starts
   }
