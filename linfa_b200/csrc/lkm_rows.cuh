@@ -285,7 +285,9 @@ __global__ void __launch_bounds__(kRowsThreads) rows_top2_kernel(const RowsArgs<
 // reference's own arithmetic ((d + 2) eps relative on a squared distance, three orders of magnitude below the slack), so it
 // cannot win even on index order.  Rows with at most kPivMax survivors are decided here by the reference's scan (direct form,
 // strict '<', index order) over the survivors; the others (overlapping clusters, NaN / Inf / denormal-range data: nothing is
-// pruned) are passed on to rows_top2_kernel.  Replaces an FMA pass over all k centroids: 603 -> see profiles/README.md.
+// pruned) are passed on to rows_top2_kernel.  cfg3 from a k-means++ start, 211 000 listed rows per iteration: 116 us here plus
+// 45 us for the 2 % passed on, against 603 us for the FMA pass over all k centroids.  HAM = true (Hamerly, the pivot is the
+// row's current centroid) also writes the bounds and moves the row between the running sums, as rows_top2_kernel does.
 constexpr int kPivMax = 8;
 constexpr int kPivThreads = 128;
 

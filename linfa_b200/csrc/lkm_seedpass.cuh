@@ -8,11 +8,17 @@
 // thread walks its row in feature order.
 #pragma once
 #include "lkm_kernels.cuh"
+#ifndef LKM_SP_ROWS
+#define LKM_SP_ROWS 128
+#endif
+#ifndef LKM_SP_STAGES
+#define LKM_SP_STAGES 3
+#endif
 
 namespace lkm {
 
-constexpr int kSpRows = 128;     // rows per tile = threads per CTA
-constexpr int kSpStages = 3;
+constexpr int kSpRows = LKM_SP_ROWS;     // rows per tile = threads per CTA
+constexpr int kSpStages = LKM_SP_STAGES;
 
 struct SeedPassArgs {
   const float* X;
