@@ -141,11 +141,11 @@ static cudaError_t launch_pdl(Kern kern, int grid, int block, size_t smem, cudaS
 
 template <typename F, int D, int MODE>
 static cudaError_t launch_lloyd_t(const LloydArgs<F>& a, int grid, size_t smem, cudaStream_t s) {
-  static size_t configured = 0;
-  if (smem > configured) {
+  // per launch, not cached: the attribute belongs to the current device's context and one process may drive several devices
+  // (lkm_create_multi), each from its own thread
+  if (smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(lloyd_kernel<F, D, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    configured = smem;
   }
   return launch_pdl(lloyd_kernel<F, D, MODE>, grid, kThreads, smem, s, a, MODE == MODE_FUSED);
 }
@@ -250,13 +250,8 @@ static lkm_status run_assign(lkm_ctx* ctx, const F* dX, uint64_t n, uint64_t d, 
       sp.X = dX; sp.n = n; sp.c = dC; sp.dists = dists; sp.min_combine = min_combine; sp.weights = weights; sp.wdists = wdists;
       const size_t smem = d == 32 ? seedpass_smem_bytes<32>() : (d == 64 ? seedpass_smem_bytes<64>() : seedpass_smem_bytes<128>());
       const void* fn = d == 32 ? (const void*)seed_pass_kernel<32> : (d == 64 ? (const void*)seed_pass_kernel<64> : (const void*)seed_pass_kernel<128>);
-      static bool configured[3] = {false, false, false};
-      const int slot = d == 32 ? 0 : (d == 64 ? 1 : 2);
-      if (!configured[slot]) {
-        CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        CK(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
-        configured[slot] = true;
-      }
+      CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   // per launch: see launch_lloyd_t
+      CK(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
       const int occ = std::max(1, (int)((ctx->smem_optin + 1024) / (smem + 1024)));
       const uint64_t tiles = (n + kSpRows - 1) / kSpRows;
       const int grid = (int)std::max<uint64_t>(1, std::min<uint64_t>(tiles, (uint64_t)ctx->sm_count * std::min(occ, 4)));
@@ -465,11 +460,9 @@ static cudaError_t launch_tc4(int kp, int passes, int grid, size_t smem, cudaStr
 // ---- rows_top2_kernel (lkm_rows.cuh): the second stage of the screened paths and Hamerly's two_closest_centroids ----
 template <typename F, int D>
 static cudaError_t launch_rows_t(const RowsArgs<F>& a, int grid, size_t smem, cudaStream_t s) {
-  static size_t configured = 0;
-  if (smem > configured) {
+  if (smem > 48 * 1024) {   // per launch: see launch_lloyd_t
     cudaError_t e = cudaFuncSetAttribute(rows_top2_kernel<F, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    configured = smem;
   }
   rows_top2_kernel<F, D><<<grid, kRowsThreads, smem, s>>>(a);
   return cudaGetLastError();
@@ -1086,11 +1079,7 @@ static lkm_status run_lloyd(lkm_ctx* ctx, F* dC2, uint64_t k, uint64_t max_iter,
             da.labels = ctx->labels.as<uint32_t>(); da.dists = ctx->dists.as<double>();
             da.rescan_list = ctx->ham_list.as<uint32_t>(); da.rescan_count = rescan_count; da.state = dstate; da.state_rw = dstate;
             const size_t dsm = dmma_smem_bytes((int)d);
-            static size_t dm_configured = 0;
-            if (dsm > dm_configured) {
-              CK(cudaFuncSetAttribute(assign_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsm));
-              dm_configured = dsm;
-            }
+            if (dsm > 48 * 1024) CK(cudaFuncSetAttribute(assign_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsm));
             const int occ = dsm > 100 * 1024 ? 1 : 2;
             const int dgrid = (int)std::max<uint64_t>(1, std::min<uint64_t>((n + kDmRows - 1) / kDmRows, (uint64_t)ctx->sm_count * occ));
             assign_dmma_kernel<<<dgrid, kDmThreads, dsm, ctx->stream>>>(da);

@@ -3,22 +3,17 @@
 // ten times the traffic of the Lloyd iterations that follow — so the pass has to run at the HBM rate while keeping the
 // reference's arithmetic: the squared distance in the direct form, feature by feature, never contracted (the min distances
 // are compared bit for bit with the oracle's).  The generic assignment kernel (one centroid = no reuse, runtime d) reached
-// 3.1 TB/s.  Here: 128-row tiles stream through a 3-stage cp.async ring into shared memory with a row stride of d + 4 floats
+// 3.1 TB/s.  Here: 64-row tiles stream through a 3-stage cp.async ring into shared memory with a row stride of d + 4 floats
 // (16-byte chunks land conflict-free, and so do the 128-bit reads of thread = row), the centroid sits in registers, each
 // thread walks its row in feature order.
 #pragma once
 #include "lkm_kernels.cuh"
-#ifndef LKM_SP_ROWS
-#define LKM_SP_ROWS 128
-#endif
-#ifndef LKM_SP_STAGES
-#define LKM_SP_STAGES 3
-#endif
 
 namespace lkm {
 
-constexpr int kSpRows = LKM_SP_ROWS;     // rows per tile = threads per CTA
-constexpr int kSpStages = LKM_SP_STAGES;
+constexpr int kSpRows = 64;      // rows per tile = threads per CTA (A/B on cfg3 / cfg4: 64 x 3 stages 237 / 577 ms of seeding,
+                                 // 128 x 3: 263 / 602, 128 x 2: 262 / 574, 64 x 4: 355 / 635)
+constexpr int kSpStages = 3;
 
 struct SeedPassArgs {
   const float* X;

@@ -66,3 +66,20 @@ def test_device_group_in_one_process(oracle):
             assert (lab == ref_lab).all() and (dist == ref_dist).all()
         finally:
             grp.close()
+    # wide rows: the pair kernels, rows_top2_kernel with every centroid in shared memory (132 KB), the seeding pass (203 KB) —
+    # kernels whose shared-memory opt-in has to be made on EVERY device of the group, not once per process
+    centres = g.uniform(-30, 30, (64, 128))
+    X = (centres[g.integers(0, 64, 60000)] + g.standard_normal((60000, 128))).astype(np.float32)
+    grp = lb.DeviceGroup(ids)
+    try:
+        for algo in (lb.KMeansAlgorithm.Lloyd, lb.KMeansAlgorithm.Hamerly):
+            params = lb.KMeans.params_with_rng(256, lb.Xoshiro256Plus.seed_from_u64(6)).n_runs(1).max_n_iterations(8).algorithm(algo)
+            multi = grp.fit(params, lb.DatasetBase(X))
+            single = params.fit(lb.DatasetBase(X))
+            np.testing.assert_allclose(multi.inertia(), single.inertia(), rtol=1e-4)
+            assert multi.cluster_count().sum() == 60000
+        lab, dist = grp.assign(single.centroids(), X)
+        ref_lab, ref_dist = oracle.assign(X, single.centroids())
+        assert (lab == ref_lab).all() and (dist == ref_dist).all()
+    finally:
+        grp.close()
