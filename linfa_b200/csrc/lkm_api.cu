@@ -1681,6 +1681,47 @@ static lkm_status weighted_pick(lkm_ctx* ctx, const F* dW, uint64_t n, HostRng& 
   return LKM_OK;
 }
 
+// One distance pass of k-means++ over the local rows: dists = min(dists, ||x - seeds[c_index]||^2), wdists = weights * dists.
+// f32 rows of 32 / 64 / 128 features take the pruned pass of lkm_seedpass.cuh (rows the new seed cannot reach are not read);
+// everything else the assignment kernels.  `seeds` holds the c_index + 1 seeds chosen so far.
+template <typename F>
+static lkm_status seed_distance_pass(lkm_ctx* ctx, const F* dX, uint64_t n, uint64_t d, const F* seeds, uint64_t c_index, F* dD,
+                                     const F* dW, F* dWD) {
+  if (n == 0) return LKM_OK;
+  if constexpr (std::is_same<F, float>::value) {
+    if (ctx->seed_pass && ctx->seed_prune && ctx->force_path != 0 && (d == 32 || d == 64 || d == 128) && c_index < (1u << 30) &&
+        (reinterpret_cast<uintptr_t>(dX) & 15) == 0 && (reinterpret_cast<uintptr_t>(seeds) & 15) == 0) {
+      CK(ctx->seed_nearest.ensure(n * 4));
+      CK(ctx->seed_sd.ensure((c_index + 1) * 4));
+      SeedPruneArgs sp{};
+      sp.X = dX; sp.n = n; sp.seeds = seeds; sp.n_seeds = (int)(c_index + 1); sp.seed_dist = ctx->seed_sd.as<float>();
+      sp.dists = dD; sp.nearest = ctx->seed_nearest.as<uint32_t>(); sp.weights = dW; sp.wdists = dWD;
+      const size_t smem = d == 32 ? seedprune_smem_bytes<32>() : (d == 64 ? seedprune_smem_bytes<64>() : seedprune_smem_bytes<128>());
+      const void* fn = d == 32 ? (const void*)seed_pass_pruned_kernel<32>
+                               : (d == 64 ? (const void*)seed_pass_pruned_kernel<64> : (const void*)seed_pass_pruned_kernel<128>);
+      CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   // per launch: see launch_lloyd_t
+      CK(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
+      const int occ = std::max(1, std::min(8, (int)((ctx->smem_optin + 1024) / (smem + 2048))));
+      const uint64_t tiles = (n + kSqRows - 1) / kSqRows;
+      const int grid = (int)std::max<uint64_t>(1, std::min<uint64_t>(tiles, (uint64_t)ctx->sm_count * occ));
+      if (c_index > 0) {
+        const unsigned sgrid = (unsigned)((c_index * 32 + 255) / 256);
+        if (d == 32) seed_dist_kernel<32><<<sgrid, 256, 0, ctx->stream>>>(sp);
+        else if (d == 64) seed_dist_kernel<64><<<sgrid, 256, 0, ctx->stream>>>(sp);
+        else seed_dist_kernel<128><<<sgrid, 256, 0, ctx->stream>>>(sp);
+        ctx->launches++;
+      }
+      if (d == 32) seed_pass_pruned_kernel<32><<<grid, kSqRows, smem, ctx->stream>>>(sp);
+      else if (d == 64) seed_pass_pruned_kernel<64><<<grid, kSqRows, smem, ctx->stream>>>(sp);
+      else seed_pass_pruned_kernel<128><<<grid, kSqRows, smem, ctx->stream>>>(sp);
+      CK(cudaGetLastError());
+      ctx->launches++;
+      return LKM_OK;
+    }
+  }
+  return run_assign<F>(ctx, dX, n, d, seeds + c_index * d, 1, nullptr, dD, c_index > 0 ? 1 : 0, dW, dWD);
+}
+
 // weighted_k_means_plusplus (KM/init.rs:118-158) over device rows dX (n x d)
 // with optional device weights (null = ones).  The min-distance array is kept
 // as a running minimum over the centroids chosen so far — the same value the
@@ -1720,7 +1761,7 @@ static lkm_status weighted_kmeanspp(lkm_ctx* ctx, const F* dX, uint64_t n, uint6
     CK(ctx->scratch.ensure(64));
     long long* didx = reinterpret_cast<long long*>(ctx->scratch.as<char>() + 48);
     for (uint64_t c = 1; c < k; ++c) {
-      CKS(run_assign<F>(ctx, dX, n, d, dC + (c - 1) * d, 1, nullptr, dD, c > 1 ? 1 : 0, dW, dWD));
+      CKS(seed_distance_pass<F>(ctx, dX, n, d, dC, c - 1, dD, dW, dWD));
       block_sums_kernel<F><<<(int)std::min<uint64_t>(nb, 4096), 256, 0, ctx->stream>>>(dWD, n, ctx->bsum.as<double>());
       const F u01 = unit<F>(rng);
       fast_pick_device_kernel<F><<<1, 256, 0, ctx->stream>>>(dWD, n, ctx->bsum.as<double>(), nb, u01, dX, (int)d, dC + c * d, didx);
@@ -1731,7 +1772,7 @@ static lkm_status weighted_kmeanspp(lkm_ctx* ctx, const F* dX, uint64_t n, uint6
     return LKM_OK;
   }
   for (uint64_t c = 1; c < k; ++c) {
-    CKS(run_assign<F>(ctx, dX, n, d, dC + (c - 1) * d, 1, nullptr, dD, c > 1 ? 1 : 0, dW, dWD));
+    CKS(seed_distance_pass<F>(ctx, dX, n, d, dC, c - 1, dD, dW, dWD));
     CKS(weighted_pick<F>(ctx, dWD, n, rng, pick_mode, idx));
     if (idx < 0) idx = 0;  // .unwrap_or(0) (KM/init.rs:149-152)
     CK(cudaMemcpyAsync(dC + c * d, dX + (size_t)idx * d, d * sizeof(F), cudaMemcpyDeviceToDevice, ctx->stream));
@@ -2039,7 +2080,7 @@ static lkm_status kmeanspp_sharded(lkm_ctx* ctx, const ShardMap& sm, uint64_t k,
   if (idx < 0) return fail(ctx, LKM_ERR_BAD_WEIGHTS, "invalid weights for k-means++");
   CKS(fetch_global_row<F>(ctx, sm, (uint64_t)idx, dC));
   for (uint64_t c = 1; c < k; ++c) {
-    if (n) CKS(run_assign<F>(ctx, dX, n, d, dC + (c - 1) * d, 1, nullptr, ctx->dists.as<F>(), c > 1 ? 1 : 0, nullptr, ctx->wdists.as<F>()));
+    CKS(seed_distance_pass<F>(ctx, dX, n, d, dC, c - 1, ctx->dists.as<F>(), nullptr, ctx->wdists.as<F>()));
     CKS(weighted_pick_sharded<F>(ctx, sm, ctx->wdists.as<F>(), rng, pick_mode, idx));
     if (idx < 0) idx = 0;
     CKS(fetch_global_row<F>(ctx, sm, (uint64_t)idx, dC + c * d));
@@ -2514,6 +2555,7 @@ LKM_EXPORT lkm_status lkm_create(lkm_ctx** out, int device) {
   if (const char* v = std::getenv("LKM_FIN_CL")) ctx->fin_cl = std::atoi(v);
   if (const char* v = std::getenv("LKM_SORT_UPD")) ctx->sort_upd = std::atoi(v);
   if (const char* v = std::getenv("LKM_SEED_PASS")) ctx->seed_pass = std::atoi(v);
+  if (const char* v = std::getenv("LKM_SEED_PRUNE")) ctx->seed_prune = std::atoi(v);
   if (const char* v = std::getenv("LKM_ROWS_PIVOT")) ctx->rows_pivot = std::atoi(v);
   if (const char* v = std::getenv("LKM_STEP_TRACE")) ctx->step_trace = std::atoi(v);
   if (const char* v = std::getenv("LKM_SPARSE_PARTIALS")) ctx->sparse_partials = std::atoi(v);

@@ -129,6 +129,8 @@ struct lkm_ctx {
   double tc5_rescan_limit = 0.08;   // LKM_TC5_RESCAN_LIMIT: share of listed rows above which the pair kernel moves to 3xTF32
   int tc5_defer = 1;     // LKM_TC5_DEFER=0: undecided rows are scanned inline by the pair kernel instead of by rows_top2_kernel
   int last_update_path = 0;
+  int seed_prune = 1;    // LKM_SEED_PRUNE=0: k-means++ distance passes read every row (no triangle-inequality pruning)
+  DevBuf seed_nearest, seed_sd;
   int seed_pass = 1;     // LKM_SEED_PASS=0: the per-pick distance pass of k-means++ through the generic assignment kernel
   int rows_pivot = -1;   // LKM_ROWS_PIVOT: -1 = pivot pruning (lkm_rows.cuh) of the listed rows once an iteration listed many, 0 never, 1 always
   DevBuf piv_cc, piv_list2;

@@ -106,4 +106,117 @@ __global__ void __launch_bounds__(kSpRows) seed_pass_kernel(const SeedPassArgs a
   sp_wait<0>();
 }
 
+// ---- the same pass with pruning --------------------------------------------------------------------------------------------
+// Row i keeps, next to its running minimum d_i, the seed s_i that realises it.  A new seed c with ||c - s_i|| > 2 ||x_i - s_i||
+// cannot be closer to x_i than s_i (triangle inequality), so the minimum does not change and the row need not be READ: 8 bytes
+// (d_i, s_i) instead of d * 4.  As the picks proceed most rows sit next to a seed and far from the new one; on blobs with one
+// seed per blob at the end that halves the traffic of the whole seeding, and the late passes cost little more than the
+// 80 MB of row state.  The factors below (2.001 on the radius, 1.0001 / 0.9999 on the two distances) are three orders of
+// magnitude above the (d + 2) eps relative error of a squared distance, so a skipped row's new distance would have compared
+// `>= d_i` in the reference's arithmetic too: the running minima stay bit-identical to the unpruned pass (and to the oracle).
+struct SeedPruneArgs {
+  const float* X;
+  unsigned long long n;
+  const float* seeds;      // the seeds chosen so far, row-major; the last one (index n_seeds - 1) is the new seed
+  int n_seeds;
+  float* seed_dist;        // [n_seeds - 1] lower bounds on ||new - seed_j|| (seed_dist_kernel)
+  float* dists;
+  uint32_t* nearest;       // seed index behind dists[i]
+  const float* weights;
+  float* wdists;
+};
+
+// warp j: lower bound on the distance between the new seed and seed j
+template <int D>
+__global__ void __launch_bounds__(256) seed_dist_kernel(const SeedPruneArgs a) {
+  const int lane = threadIdx.x & 31;
+  const int j = (blockIdx.x * 256 + threadIdx.x) >> 5;
+  if (j >= a.n_seeds - 1) return;
+  const float* cn = a.seeds + (size_t)(a.n_seeds - 1) * D;
+  const float* cj = a.seeds + (size_t)j * D;
+  float s = 0.f;
+  for (int f = lane; f < D; f += 32) { const float df = cn[f] - cj[f]; s = fmaf(df, df, s); }
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane == 0) a.seed_dist[j] = sqrtf(s) * 0.9999f;   // NaN stays NaN: such a seed prunes nothing
+}
+
+constexpr int kSqRows = 64;   // rows per tile = threads per CTA
+
+template <int D> __host__ __device__ constexpr size_t seedprune_smem_bytes() { return (size_t)kSqRows * (D + 4) * 4; }
+
+template <int D>
+__global__ void __launch_bounds__(kSqRows) seed_pass_pruned_kernel(const SeedPruneArgs a) {
+  static_assert(D % 4 == 0 && D >= 16 && D <= 128, "row width");
+  constexpr int RS = D + 4, CPR = D / 4;
+  extern __shared__ __align__(16) float sp_smem[];
+  __shared__ uint16_t list[kSqRows];
+  __shared__ float old_s[kSqRows];
+  __shared__ int warp_cnt[2];
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  const unsigned long long n_tiles = (a.n + kSqRows - 1) / kSqRows;
+  const bool first = a.n_seeds == 1;
+  const uint32_t me = (uint32_t)(a.n_seeds - 1);
+  float c[D];
+  {
+    const float* cn = a.seeds + (size_t)me * D;
+#pragma unroll
+    for (int j = 0; j < D; j += 4) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(cn + j));
+      c[j] = v.x; c[j + 1] = v.y; c[j + 2] = v.z; c[j + 3] = v.w;
+    }
+  }
+  const uint32_t s_base = (uint32_t)__cvta_generic_to_shared(sp_smem);
+  for (unsigned long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const unsigned long long row0 = tile * kSqRows, row = row0 + t;
+    // ---- which rows of the tile can the new seed reach? ----
+    bool need = row < a.n;
+    float old = INFINITY;
+    if (need && !first) {
+      old = a.dists[row];
+      const float sd = a.seed_dist[a.nearest[row]];
+      // only a normal, moderate distance is trusted for pruning
+      if (old > 1e-30f && old < 1e30f && sd > 2.001f * (sqrtf(old) * 1.0001f)) need = false;
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, need);
+    if (lane == 0) warp_cnt[warp] = __popc(m);
+    __syncthreads();
+    const int base = warp == 0 ? 0 : warp_cnt[0], cnt = warp_cnt[0] + warp_cnt[1];
+    if (need) {
+      const int slot = base + __popc(m & ((1u << lane) - 1u));
+      list[slot] = (uint16_t)t;
+      old_s[slot] = old;
+    }
+    __syncthreads();
+    // ---- bring the surviving rows in (16-byte chunks, consecutive threads = consecutive chunks of a row) ----
+    for (int q = t; q < cnt * CPR; q += kSqRows) {
+      const int slot = q / CPR, cc = q % CPR;
+      sp_cp_async16(s_base + (uint32_t)(slot * RS + cc * 4) * 4u, a.X + (row0 + list[slot]) * D + (size_t)cc * 4, 16);
+    }
+    sp_commit();
+    sp_wait<0>();
+    __syncthreads();
+    if (t < cnt) {
+      const float* xr = sp_smem + (size_t)t * RS;
+      float acc = 0.f;
+#pragma unroll
+      for (int j = 0; j < D; j += 4) {
+        const float4 v = *reinterpret_cast<const float4*>(xr + j);
+        const float d0 = Rn<float>::sub(c[j], v.x), d1 = Rn<float>::sub(c[j + 1], v.y);
+        const float d2 = Rn<float>::sub(c[j + 2], v.z), d3 = Rn<float>::sub(c[j + 3], v.w);
+        acc = Rn<float>::add(acc, Rn<float>::mul(d0, d0));
+        acc = Rn<float>::add(acc, Rn<float>::mul(d1, d1));
+        acc = Rn<float>::add(acc, Rn<float>::mul(d2, d2));
+        acc = Rn<float>::add(acc, Rn<float>::mul(d3, d3));
+      }
+      const unsigned long long r = row0 + list[t];
+      if (first || acc < old_s[t]) {
+        a.dists[r] = acc;
+        a.nearest[r] = me;
+        if (a.wdists != nullptr) a.wdists[r] = a.weights != nullptr ? acc * a.weights[r] : acc;
+      }
+    }
+    __syncthreads();   // list / old_s / the tile are rewritten by the next iteration
+  }
+}
+
 }  // namespace lkm
