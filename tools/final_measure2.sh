@@ -9,5 +9,5 @@ python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/${P}_bench_re
 WL=cfg3 HASHED=1 KPP=1 ITERS=4 python tools/r2_probe.py > gpurun_out/${P}_plain_probe.log 2>&1 && \
 WL=cfg3 HASHED=1 KPP=1 ITERS=4 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/${P}_launches_cfg3_hashed_kpp.csv python tools/r2_probe.py > gpurun_out/${P}_ncu_l.log 2>&1
 python tools/launch_summary.py gpurun_out/${P}_launches_cfg3_hashed_kpp.csv > gpurun_out/${P}_launch_summary_cfg3_hashed_kpp.txt; cat gpurun_out/${P}_launch_summary_cfg3_hashed_kpp.txt
-WL=cfg3 HASHED=1 ITERS=3 ncu --set full --clock-control none --import-source on -k regex:update_sorted -s 1 -c 1 -f -o gpurun_out/${P}_prof_update_sorted python tools/r2_probe.py > gpurun_out/${P}_ncu_us.log 2>&1
-ls -la gpurun_out/${P}_prof_update_sorted.ncu-rep
+# (the full capture of update_sorted_kernel — profiles/r2b_update_sorted_ncu.txt — was taken by an earlier run of this script:
+#  WL=cfg3 HASHED=1 ITERS=3 ncu --set full --clock-control none --import-source on -k regex:update_sorted -s 1 -c 1 -f -o gpurun_out/r2b_prof_update_sorted python tools/r2_probe.py)
