@@ -290,8 +290,11 @@ static lkm_status p2p_setup(lkm_ctx* ctx, size_t L) {
   if (ctx->p2p_local && L <= ctx->p2p_cap) return LKM_OK;
   const int world = ctx->world;
   const size_t cap = std::max<size_t>(L, 4096);
-  // [2 parities][world][cap] partials | [2][world][kFxMaxCtas] exchange flags | [world] barrier flags
-  const size_t bytes = (2 * (size_t)world * cap + 2 * (size_t)world * kFxMaxCtas + (size_t)world) * 8;
+  // [2 parities][world][cap] partials | [2][world][kFxMaxCtas] exchange flags | [world] barrier flags | (16-byte aligned)
+  // [2][world][cap] 16-byte self-validating slots of finalize_cl_kernel
+  const size_t ll_off = (((2 * (size_t)world * cap + 2 * (size_t)world * kFxMaxCtas + (size_t)world) * 8) + 15) & ~(size_t)15;
+  const size_t bytes = ll_off + 2 * (size_t)world * cap * 16;
+  ctx->p2p_ll_off = ll_off;
   if (ctx->group != nullptr) {
     // one process: every rank allocates its buffer, the pointers and device numbers travel through the group, and the
     // peers are reached by plain peer access (no IPC handles)
@@ -1232,6 +1235,11 @@ static lkm_status run_lloyd(lkm_ctx* ctx, F* dC2, uint64_t k, uint64_t max_iter,
           xa.gather = mine + par * w * cap;
           xa.my_flags = reinterpret_cast<const unsigned long long*>(mine + 2 * w * cap) + par * w * kFxMaxCtas;
           xa.cap = cap; xa.epoch = epoch;
+          if (ctx->p2p_ll) {
+            for (int pr = 0; pr < ctx->world; ++pr)
+              xa.peer_ll[pr] = reinterpret_cast<uint4*>(static_cast<unsigned char*>(ctx->p2p_peer[pr]) + ctx->p2p_ll_off) + (par * w + (size_t)ctx->rank) * cap;
+            xa.my_ll = reinterpret_cast<const uint4*>(static_cast<unsigned char*>(ctx->p2p_local) + ctx->p2p_ll_off) + par * w * cap;
+          }
         }
         xa.C_old = Ccur; xa.C_new = Cnext; xa.counts_out = ctx->counts_out.as<double>();
         xa.shift_part = ctx->shift_part.as<double>(); xa.state = dstate; xa.tol = tol; xa.max_iter = max_iter;
@@ -2553,6 +2561,7 @@ LKM_EXPORT lkm_status lkm_create(lkm_ctx** out, int device) {
   if (const char* v = std::getenv("LKM_DEVICE_PICKS")) ctx->device_picks = std::atoi(v);
   if (const char* v = std::getenv("LKM_ROWS_ASSIGN")) ctx->rows_assign = std::atoi(v);
   if (const char* v = std::getenv("LKM_FIN_CL")) ctx->fin_cl = std::atoi(v);
+  if (const char* v = std::getenv("LKM_P2P_LL")) ctx->p2p_ll = std::atoi(v);
   if (const char* v = std::getenv("LKM_SORT_UPD")) ctx->sort_upd = std::atoi(v);
   if (const char* v = std::getenv("LKM_SEED_PASS")) ctx->seed_pass = std::atoi(v);
   if (const char* v = std::getenv("LKM_SEED_PRUNE")) ctx->seed_prune = std::atoi(v);

@@ -166,6 +166,8 @@ struct lkm_ctx {
   void* p2p_local = nullptr;
   std::vector<void*> p2p_peer;
   size_t p2p_cap = 0;
+  size_t p2p_ll_off = 0;   // byte offset of the 16-byte self-validating slots [2 parities][world][p2p_cap] (finalize_cl_kernel)
+  int p2p_ll = 1;          // LKM_P2P_LL=0: finalize_cl_kernel exchanges with plain stores + system fence + flags
   unsigned long long p2p_epoch = 0;
   int p2p_enabled = 1;  // LKM_P2P=0 falls back to ncclAllGather
   uint32_t launches = 0;

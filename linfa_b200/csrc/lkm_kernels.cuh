@@ -661,6 +661,8 @@ template <typename F, typename S, typename CT> struct FinalizeXArgs {
   unsigned long long* peer_flags[8];    // rank p's flags for THIS rank (this parity): [kFxMaxCtas]
   const double* gather;                 // own gather buffer of this parity: rank r at gather + r * cap
   const unsigned long long* my_flags;   // own flags of this parity: rank r, CTA b at my_flags[r * kFxMaxCtas + b]
+  uint4* peer_ll[8];                    // finalize_cl, self-validating exchange: rank p's 16-byte slots for THIS rank (this parity), or nullptr
+  const uint4* my_ll;                   // own slots of this parity: rank r, element e at my_ll[r * cap + e]
   size_t cap;
   int world;
   unsigned long long epoch;
@@ -798,27 +800,76 @@ __global__ void __launch_bounds__(kFinThreads) finalize_x_kernel(const FinalizeX
 // GPU or row-sharded.  The slice-wise kernels above give every thread ~n_src / 16 strided 4-byte loads in two dependent
 // rounds; with k * d = 32768 and 296 sources that is 2048 CTAs of latency chains (60-90 us measured on the cfg3 shape,
 // a quarter of a 1.25M-row step).  Here CTA b owns whole clusters: it compacts the sources that touched cluster c into a
-// list (ascending source order: reproducible), and thread j sums feature j over the list — coalesced 4 d-byte rows, all
-// loads of a cluster in flight at once.  Row-sharded: the CTA publishes its clusters' sums and counts to every rank
-// (NVLink stores), raises its flag, waits for the same CTA's flag of every rank, combines in rank order.
+// list (ascending source order), warp w sums the sources list[w], list[w + 8], ... (lane = feature, four sources and
+// four features per lane in flight: coalesced rows, a handful of L2 round trips per cluster), and the eight warp partials
+// are added in warp order — a fixed association for a given list, hence reproducible.  Counts are integers: their f64
+// sum is exact in any order.
+// Row-sharded: the CTA publishes its clusters' sums and counts to every rank over NVLink, waits for the same clusters
+// of every rank and combines in rank order.  With peer_ll the exchange is self-validating (the LL scheme of the
+// collective libraries): every value travels as one 16-byte store {lo, epoch, hi, epoch}, each 8-byte half carrying its
+// own tag, and the reader polls the slot until both tags are this epoch's — no fence, no flag, nothing waits for an
+// NVLink acknowledgement (the system fence of the flag protocol cost 4-17 us per iteration at 8 GPUs,
+// profiles/r2_scale_trace_8gpu.txt).  Slots are double-buffered by epoch parity; a writer can be at most one epoch ahead
+// of a reader (it needs the reader's previous publication to get there), so a slot is never overwritten while it is read.
+// Without peer_ll: plain stores, one system fence per flag, flags (as finalize_x_kernel).
 // slices_per_cta is read as "clusters per CTA".
 // ---------------------------------------------------------------------------
 constexpr int kFclMaxSrc = 2048;
+constexpr int kFclCols = 128;   // features per pass of the source sum (4 per lane)
+
+__device__ __forceinline__ void ll_store(uint4* p, double v, uint32_t tag) {
+  const unsigned long long b = (unsigned long long)__double_as_longlong(v);
+  asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"((uint32_t)b), "r"(tag), "r"((uint32_t)(b >> 32)), "r"(tag)
+               : "memory");
+}
+__device__ __forceinline__ uint4 ll_peek(const uint4* p) {
+  uint4 v;
+  asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+  return v;
+}
+// sum over the ranks (in rank order) of slot e; all `world` slots are requested before the first is looked at, slots whose
+// tags are not yet this epoch's are asked for again.  false: a peer did not publish within kPeerWaitNs.
+__device__ __forceinline__ bool ll_gather_sum(const uint4* base, size_t cap, int world, size_t e, uint32_t tag, double& out) {
+  uint4 v[8];
+  unsigned long long t0 = 0;
+  for (;;) {
+    bool all = true;
+#pragma unroll
+    for (int r = 0; r < 8; ++r)
+      if (r < world) v[r] = ll_peek(base + (size_t)r * cap + e);
+#pragma unroll
+    for (int r = 0; r < 8; ++r)
+      if (r < world) all = all && v[r].y == tag && v[r].w == tag;
+    if (all) break;
+    const unsigned long long now = global_ns();
+    if (t0 == 0) t0 = now;
+    else if (now - t0 > kPeerWaitNs) { out = 0.0; return false; }
+  }
+  double tot = 0.0;
+#pragma unroll
+  for (int r = 0; r < 8; ++r)
+    if (r < world) tot += __longlong_as_double((long long)(((unsigned long long)v[r].z << 32) | (unsigned long long)v[r].x));
+  out = tot;
+  return true;
+}
 
 template <typename F, typename S, typename CT>
 __global__ void __launch_bounds__(kFinThreads) finalize_cl_kernel(const FinalizeXArgs<F, S, CT> a) {
   pdl_launch_dependents();
   pdl_wait();
   if (a.state->done) return;
+  static_assert(kFinThreads == 256, "eight warps");
   __shared__ int list[kFclMaxSrc];
   __shared__ int warp_tot[kFinThreads / 32];
   __shared__ int n_list_s;
   __shared__ double red[kFinThreads];
-  __shared__ double cnt_s;
+  __shared__ double part[kFinThreads / 32][kFclCols];
   __shared__ bool is_last;
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
   const int kd = a.k * a.d;
   const int c_lo = blockIdx.x * a.slices_per_cta, c_hi = min(a.k, c_lo + a.slices_per_cta);
+  const bool ll = a.world > 1 && a.peer_ll[0] != nullptr;
+  const uint32_t tag = (uint32_t)a.epoch;
   double sq = 0.0;
   const bool stamp = a.prof != nullptr && blockIdx.x == 0 && t == 0;
   if (stamp) a.prof[0] = global_ns();
@@ -841,35 +892,65 @@ __global__ void __launch_bounds__(kFinThreads) finalize_cl_kernel(const Finalize
       __syncthreads();
     }
     const int nl = n_list_s;
+    // ---- counts: integers, exact in f64 whatever the order ----
+    double cv = 0.0;
+    for (int i = t; i < nl; i += kFinThreads) cv += (double)a.src_counts[(size_t)list[i] * a.cnt_stride + c];
+    cv = block_sum(cv, red);
     if (t == 0) {
-      double cv = 0.0;
-      for (int i = 0; i < nl; ++i) cv += (double)a.src_counts[(size_t)list[i] * a.cnt_stride + c];
-      cnt_s = cv;
-      if (a.world > 1) for (int p = 0; p < a.world; ++p) a.peer_out[p][kd + c] = cv;
+      if (ll) for (int p = 0; p < a.world; ++p) ll_store(a.peer_ll[p] + kd + c, cv, tag);
+      else if (a.world > 1) for (int p = 0; p < a.world; ++p) a.peer_out[p][kd + c] = cv;
       else a.counts_out[c] = cv;
     }
-    __syncthreads();
-    for (int j = t; j < a.d; j += kFinThreads) {
-      const size_t e = (size_t)c * a.d + j;
-      double tot = 0.0;
-      int i = 0;
-      for (; i + 8 <= nl; i += 8) {
-        S v[8];
+    // ---- sums: warp w takes the sources list[w], list[w + 8], ..., lane l the features j0 + l + 32 q ----
+    for (int j0 = 0; j0 < a.d; j0 += kFclCols) {
+      double acc[4] = {0.0, 0.0, 0.0, 0.0};
+      const S* col = a.src_sums + (size_t)c * a.d + j0 + lane;
+      bool in[4];
 #pragma unroll
-        for (int q = 0; q < 8; ++q) v[q] = a.src_sums[(size_t)list[i + q] * a.sum_stride + e];
+      for (int q = 0; q < 4; ++q) in[q] = j0 + lane + 32 * q < a.d;
+      int i = warp;
+      for (; i + 24 < nl; i += 32) {
+        S v[4][4];
 #pragma unroll
-        for (int q = 0; q < 8; ++q) tot += (double)v[q];
+        for (int u = 0; u < 4; ++u) {
+          const S* row = col + (size_t)list[i + 8 * u] * a.sum_stride;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) v[u][q] = in[q] ? row[32 * q] : S(0);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+          for (int q = 0; q < 4; ++q) acc[q] += (double)v[u][q];
       }
-      for (; i < nl; ++i) tot += (double)a.src_sums[(size_t)list[i] * a.sum_stride + e];
-      if (a.world > 1) {
-        for (int p = 0; p < a.world; ++p) a.peer_out[p][e] = tot;
-      } else {
-        const F oldv = a.C_old[e];
-        const F newv = (F)((tot + (double)oldv) / (cnt_s + 1.0));
-        a.C_new[e] = newv;
-        const double df = (double)(oldv - newv);
-        sq += df * df;
+      for (; i < nl; i += 8) {
+        const S* row = col + (size_t)list[i] * a.sum_stride;
+        S v[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) v[q] = in[q] ? row[32 * q] : S(0);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) acc[q] += (double)v[q];
       }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) part[warp][lane + 32 * q] = acc[q];
+      __syncthreads();
+      if (t < kFclCols && j0 + t < a.d) {
+        const size_t e = (size_t)c * a.d + j0 + t;
+        double tot = 0.0;
+#pragma unroll
+        for (int w = 0; w < kFinThreads / 32; ++w) tot += part[w][t];
+        if (ll) {
+          for (int p = 0; p < a.world; ++p) ll_store(a.peer_ll[p] + e, tot, tag);
+        } else if (a.world > 1) {
+          for (int p = 0; p < a.world; ++p) a.peer_out[p][e] = tot;
+        } else {
+          const F oldv = a.C_old[e];
+          const F newv = (F)((tot + (double)oldv) / (cv + 1.0));
+          a.C_new[e] = newv;
+          const double df = (double)(oldv - newv);
+          sq += df * df;
+        }
+      }
+      __syncthreads();
     }
   }
   if (a.world > 1) {
@@ -878,39 +959,47 @@ __global__ void __launch_bounds__(kFinThreads) finalize_cl_kernel(const Finalize
       const int n_in = a.n_src_inertia ? a.n_src_inertia : a.n_src;
       for (int b = t; b < n_in; b += kFinThreads) v += a.src_inertia[(size_t)b * a.inertia_stride];
       const double tot = block_sum(v, red);
-      if (t == 0)
-        for (int p = 0; p < a.world; ++p) a.peer_out[p][kd + a.k] = tot;
+      if (t == 0) {
+        if (ll) for (int p = 0; p < a.world; ++p) ll_store(a.peer_ll[p] + kd + a.k, tot, tag);
+        else for (int p = 0; p < a.world; ++p) a.peer_out[p][kd + a.k] = tot;
+      }
     }
     if (stamp) a.prof[1] = global_ns();
-    // every thread's NVLink stores happen before the barrier; the fence of the flag-writing threads after it is cumulative
-    // over them (one system fence per flag instead of one per thread: the fence waits for the peers' acknowledgements)
-    __syncthreads();
-    if (t < a.world) {
-      __threadfence_system();
-      unsigned long long* f = a.peer_flags[t] + blockIdx.x;
-      asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(f), "l"(a.epoch) : "memory");
-    }
-    if (stamp) a.prof[2] = global_ns();
     bool ok = true;
-    if (t < a.world) ok = wait_flag(a.my_flags + (size_t)t * kFxMaxCtas + blockIdx.x, a.epoch);
-    if (!ok) atomicOr(&a.state->fallback_rows, 1ull << 41);   // timeout marker, reported by the host
-    __syncthreads();
-    if (stamp) a.prof[3] = global_ns();
+    if (!ll) {
+      // every thread's NVLink stores happen before the barrier; the fence of the flag-writing threads after it is cumulative
+      // over them (one system fence per flag instead of one per thread: the fence waits for the peers' acknowledgements)
+      __syncthreads();
+      if (t < a.world) {
+        __threadfence_system();
+        unsigned long long* f = a.peer_flags[t] + blockIdx.x;
+        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(f), "l"(a.epoch) : "memory");
+      }
+      if (stamp) a.prof[2] = global_ns();
+      if (t < a.world) ok = wait_flag(a.my_flags + (size_t)t * kFxMaxCtas + blockIdx.x, a.epoch);
+      __syncthreads();
+    } else if (stamp) a.prof[2] = global_ns();
+    bool first = true;
     for (int c = c_lo; c < c_hi; ++c) {
       double cntv = 0.0;
-      for (int r = 0; r < a.world; ++r) cntv += ((const volatile double*)a.gather)[(size_t)r * a.cap + kd + c];
+      if (ll) ok = ll_gather_sum(a.my_ll, a.cap, a.world, (size_t)kd + c, tag, cntv) && ok;
+      else for (int r = 0; r < a.world; ++r) cntv += ((const volatile double*)a.gather)[(size_t)r * a.cap + kd + c];
       if (t == 0) a.counts_out[c] = cntv;
       for (int j = t; j < a.d; j += kFinThreads) {
         const size_t e = (size_t)c * a.d + j;
         double tot = 0.0;
-        for (int r = 0; r < a.world; ++r) tot += ((const volatile double*)a.gather)[(size_t)r * a.cap + e];
+        if (ll) ok = ll_gather_sum(a.my_ll, a.cap, a.world, e, tag, tot) && ok;
+        else for (int r = 0; r < a.world; ++r) tot += ((const volatile double*)a.gather)[(size_t)r * a.cap + e];
         const F oldv = a.C_old[e];
         const F newv = (F)((tot + (double)oldv) / (cntv + 1.0));
         a.C_new[e] = newv;
         const double df = (double)(oldv - newv);
         sq += df * df;
       }
+      if (first && stamp) a.prof[3] = global_ns();
+      first = false;
     }
+    if (!ok) atomicOr(&a.state->fallback_rows, 1ull << 41);   // timeout marker, reported by the host
   }
   const double sq_cta = block_sum(sq, red);
   if (stamp) a.prof[4] = global_ns();
@@ -924,7 +1013,7 @@ __global__ void __launch_bounds__(kFinThreads) finalize_cl_kernel(const Finalize
   if (!is_last) return;
   if (a.prof != nullptr && t == 0) a.prof[5] = global_ns();
   __threadfence();
-  if (a.world > 1 && t < a.world && !wait_flag(a.my_flags + (size_t)t * kFxMaxCtas, a.epoch)) atomicOr(&a.state->fallback_rows, 1ull << 41);
+  if (a.world > 1 && !ll && t < a.world && !wait_flag(a.my_flags + (size_t)t * kFxMaxCtas, a.epoch)) atomicOr(&a.state->fallback_rows, 1ull << 41);
   __syncthreads();
   double v = 0.0;
   for (int b = t; b < (int)gridDim.x; b += kFinThreads) v += ((volatile double*)a.shift_part)[b];
@@ -937,8 +1026,11 @@ __global__ void __launch_bounds__(kFinThreads) finalize_cl_kernel(const Finalize
     inertia = block_sum(v, red);
   }
   if (t == 0) {
-    if (a.world > 1)
+    if (ll) {
+      if (!ll_gather_sum(a.my_ll, a.cap, a.world, (size_t)kd + a.k, tag, inertia)) atomicOr(&a.state->fallback_rows, 1ull << 41);
+    } else if (a.world > 1) {
       for (int r = 0; r < a.world; ++r) inertia += ((const volatile double*)a.gather)[(size_t)r * a.cap + kd + a.k];
+    }
     const F shift = (F)sqrt(shift_sq);  // L2Dist::distance: sqrt in f64, cast to F
     a.state->shift = (double)shift;
     a.state->inertia = inertia;
