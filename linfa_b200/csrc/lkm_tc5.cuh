@@ -247,14 +247,40 @@ __device__ __forceinline__ void t5_write_bias(unsigned char* b_bias, unsigned ch
 // 16-lane ALU pipe (two cycles per warp instruction), which this role saturates: the pack is kept an IMAD (FMA
 // pipe) by passing the multiplier (256) as a kernel argument, and the runner-up pass is written as chains of
 // min(m, cb - 1 - q) so that each step is one fused VIADDMNMX.
+//
+// Both pipes take one warp instruction every two cycles (fma: IMAD; alu: IADD3, VIMNMX3).  ptxas turns the runner-up
+// pass into 32 IADD3 + one chain of 16 VIMNMX3 per 32 columns, which with the 16 VIMNMX3 of the first pass puts 72
+// instructions on the alu pipe against the 32 IMADs of the pack.  Five of every eight subtractions are therefore written
+// as q * neg1 + (best - 1) with neg1 = 0xFFFFFFFF derived from a kernel argument (an IMAD the compiler cannot fold
+// back): 52 instructions on each pipe (cfg4 shard step 4.20 -> 3.87 ms).
+//
+// The 32-column TMEM loads are software-pipelined: the load of chunk i + 1 is in flight while chunk i is scored (under
+// the MMAs of the other accumulator a tcgen05.ld takes several hundred cycles, and a warp that waits for each load before
+// it computes spends most of a tile waiting: ~540 cycles per chunk for ~140 cycles of pipe work).  tmem_ld_fence ties
+// the destination registers to the wait so that no use is scheduled above it.
 template <int N>
-__device__ __forceinline__ void t5_top2(uint32_t taddr, uint32_t mult, uint32_t& m1, uint32_t& m2) {
+__device__ __forceinline__ void t5_score_chunk(uint32_t (&q)[32], int c0, uint32_t mult, uint32_t neg1, uint32_t& m1, uint32_t& m2);
+
+template <int N>
+__device__ __forceinline__ void t5_top2(uint32_t taddr, uint32_t mult, uint32_t neg1, uint32_t& m1, uint32_t& m2) {
+  static_assert(N % 64 == 0, "two chunks per round");
   m1 = 0u; m2 = 0u;   // real scores are >= 2^e > 0
+  uint32_t qa[32], qb[32];
+  tc::tmem_ld32(taddr, qa);
 #pragma unroll 1
-  for (int c0 = 0; c0 < N; c0 += 32) {
-    uint32_t q[32];
-    tc::tmem_ld32(taddr + (uint32_t)c0, q);
-    tc::tmem_ld_wait();
+  for (int c0 = 0; c0 < N; c0 += 64) {
+    tc::tmem_ld_fence(qa);
+    tc::tmem_ld32(taddr + (uint32_t)c0 + 32u, qb);
+    t5_score_chunk<N>(qa, c0, mult, neg1, m1, m2);
+    tc::tmem_ld_fence(qb);
+    if (c0 + 64 < N) tc::tmem_ld32(taddr + (uint32_t)c0 + 64u, qa);
+    t5_score_chunk<N>(qb, c0 + 32, mult, neg1, m1, m2);
+  }
+}
+
+template <int N>
+__device__ __forceinline__ void t5_score_chunk(uint32_t (&q)[32], int c0, uint32_t mult, uint32_t neg1, uint32_t& m1, uint32_t& m2) {
+  {
 #pragma unroll
     for (int c = 0; c < 32; ++c) q[c] = q[c] * mult + (uint32_t)c;   // index inside the chunk; c0 is added to the winners
     uint32_t b0 = __vimax3_u32(q[0], q[1], q[2]), b1 = __vimax3_u32(q[3], q[4], q[5]);
@@ -273,11 +299,15 @@ __device__ __forceinline__ void t5_top2(uint32_t taddr, uint32_t mult, uint32_t&
     // the chunk's best wraps to 0xFFFFFFFF, the others become gap - 1
     uint32_t t0 = 0xFFFFFFFFu, t1 = 0xFFFFFFFFu, t2 = 0xFFFFFFFFu, t3 = 0xFFFFFFFFu;
 #pragma unroll
-    for (int c = 0; c < 32; c += 4) {
-      t0 = min(t0, cm1 - q[c]);
-      t1 = min(t1, cm1 - q[c + 1]);
-      t2 = min(t2, cm1 - q[c + 2]);
-      t3 = min(t3, cm1 - q[c + 3]);
+    for (int c = 0; c < 32; c += 8) {
+      t0 = min(t0, q[c] * neg1 + cm1);
+      t1 = min(t1, q[c + 1] * neg1 + cm1);
+      t2 = min(t2, q[c + 2] * neg1 + cm1);
+      t3 = min(t3, q[c + 3] * neg1 + cm1);
+      t0 = min(t0, q[c + 4] * neg1 + cm1);
+      t1 = min(t1, cm1 - q[c + 5]);
+      t2 = min(t2, cm1 - q[c + 6]);
+      t3 = min(t3, cm1 - q[c + 7]);
     }
     const uint32_t cs = cm1 - min(min(t0, t1), min(t2, t3)) + (uint32_t)c0;   // runner-up of the chunk
     const uint32_t cbg = cb + (uint32_t)c0;
@@ -543,7 +573,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kT5Threads, 1)
       if (wq == 0) T5TRACE(it, 6);
       tc::tc_fence_after();
       uint32_t m1, m2;   // best / runner-up (packed)
-      t5_top2<kT5K>(taddr, a.pack_mult, m1, m2);
+      t5_top2<kT5K>(taddr, a.pack_mult, 0u - (a.pack_mult >> 8), m1, m2);
       tc::tc_fence_before();
       __syncwarp();
       if (lane == 0) tc::mbar_arrive_cluster(&bar_accfree, 0u);   // the accumulator may be overwritten
@@ -888,7 +918,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(FUSE ? t5_fuse_threa
       if (wq == 0) T5TRACE(it, 8);
       tc::tc_fence_after();
       uint32_t m1, m2;
-      t5_top2<N>(taddr, a.pack_mult, m1, m2);
+      t5_top2<N>(taddr, a.pack_mult, 0u - (a.pack_mult >> 8), m1, m2);
       tc::tc_fence_before();
       __syncwarp();
       if (lane == 0) tc::mbar_arrive_cluster(&bar_accfree[g], 0u);
