@@ -1355,11 +1355,11 @@ static lkm_status run_lloyd(lkm_ctx* ctx, F* dC2, uint64_t k, uint64_t max_iter,
   if (use_tc5) {
     static long long ht[2 * 16 * 16];
     CK(cudaMemcpy(ht, ctx->t4prof.p, sizeof(ht), cudaMemcpyDeviceToHost));
-    std::fprintf(stderr, "t5trace cta tile  (3xTF32) Maready Maccfree Mcommit  Sbeg Sissued Sarrived  Ewake Edrained Elabels | (screening) Ptma0 Ptma3 Maccfree Mfull0 Mpfull0 Mfull3 Mpfull3 Mcommit Ewake Edrained Edone\n");
+    std::fprintf(stderr, "t5trace cta tile  (3xTF32) Maready Maccfree Mcommit  Sbeg Sissued Sarrived  Ewake Edrained Elabels | (screening) Ptma0 Ptma3 Maccfree Mfull0 Mpfull0 Mfull3 Mpfull3 Mcommit Ewake Edrained Edone Edrained(warp 0..3) Mloop\n");
     for (int c = 0; c < 2; ++c)
       for (int j = 0; j < 16; ++j) {
         std::fprintf(stderr, "t5trace %d %3d", c, j);
-        for (int e = 0; e < 11; ++e) std::fprintf(stderr, " %7lld", ht[(c * 16 + j) * 16 + e]);
+        for (int e = 0; e < 16; ++e) std::fprintf(stderr, " %7lld", ht[(c * 16 + j) * 16 + e]);
         std::fprintf(stderr, "\n");
       }
   }

@@ -72,7 +72,7 @@ __device__ __forceinline__ unsigned int t5_defer(const Tc5Args& a, bool undecide
 
 // LKM_T5_TRACE: CTA 0 / 1 stamp event `ev` of tile `it` (cycles since the roles started) into a.prof[(cta * 16 + it) * 16 + ev]
 #ifdef LKM_T5_TRACE
-#define T5TRACE(it, ev) do { if (blockIdx.x < 2 && lane == 0 && (it) < 16 && a.prof) a.prof[((blockIdx.x * 16) + (it)) * 16 + (ev)] = clock64() - trace_t0; } while (0)
+#define T5TRACE(it, ev) do { if (blockIdx.x < 2 && lane == 0 && (it) >= 32 && (it) < 48 && a.prof) a.prof[((blockIdx.x * 16) + ((it) - 32)) * 16 + (ev)] = clock64() - trace_t0; } while (0)   /* tiles 32-47: steady state */
 #else
 #define T5TRACE(it, ev)
 #endif
@@ -261,8 +261,10 @@ __device__ __forceinline__ void t5_write_bias(unsigned char* b_bias, unsigned ch
 template <int N>
 __device__ __forceinline__ void t5_score_chunk(uint32_t (&q)[32], int c0, uint32_t mult, uint32_t neg1, uint32_t& m1, uint32_t& m2);
 
-template <int N>
-__device__ __forceinline__ void t5_top2(uint32_t taddr, uint32_t mult, uint32_t neg1, uint32_t& m1, uint32_t& m2) {
+// `drained()` runs as soon as the last chunk sits in registers, before it is scored: the accumulator goes back to the MMA
+// role one chunk earlier.
+template <int N, typename Drained>
+__device__ __forceinline__ void t5_top2(uint32_t taddr, uint32_t mult, uint32_t neg1, uint32_t& m1, uint32_t& m2, Drained drained) {
   static_assert(N % 64 == 0, "two chunks per round");
   m1 = 0u; m2 = 0u;   // real scores are >= 2^e > 0
   uint32_t qa[32], qb[32];
@@ -274,6 +276,7 @@ __device__ __forceinline__ void t5_top2(uint32_t taddr, uint32_t mult, uint32_t 
     t5_score_chunk<N>(qa, c0, mult, neg1, m1, m2);
     tc::tmem_ld_fence(qb);
     if (c0 + 64 < N) tc::tmem_ld32(taddr + (uint32_t)c0 + 64u, qa);
+    else drained();
     t5_score_chunk<N>(qb, c0 + 32, mult, neg1, m1, m2);
   }
 }
@@ -296,20 +299,19 @@ __device__ __forceinline__ void t5_score_chunk(uint32_t (&q)[32], int c0, uint32
     b1 = __vimax3_u32(b1, q[30], q[31]);
     const uint32_t cb = max(__vimax3_u32(b0, b1, b2), b3);
     const uint32_t cm1 = cb - 1u;
-    // the chunk's best wraps to 0xFFFFFFFF, the others become gap - 1
-    uint32_t t0 = 0xFFFFFFFFu, t1 = 0xFFFFFFFFu, t2 = 0xFFFFFFFFu, t3 = 0xFFFFFFFFu;
+    // the chunk's best wraps to 0xFFFFFFFF, the others become gap - 1.  Four independent chains of three-input minima
+    // (ptxas folds two-input chains into ONE chain of 16 dependent VIMNMX3: 16 x 4.5 cycles of latency per chunk)
+    uint32_t gp[32];
 #pragma unroll
-    for (int c = 0; c < 32; c += 8) {
-      t0 = min(t0, q[c] * neg1 + cm1);
-      t1 = min(t1, q[c + 1] * neg1 + cm1);
-      t2 = min(t2, q[c + 2] * neg1 + cm1);
-      t3 = min(t3, q[c + 3] * neg1 + cm1);
-      t0 = min(t0, q[c + 4] * neg1 + cm1);
-      t1 = min(t1, cm1 - q[c + 5]);
-      t2 = min(t2, cm1 - q[c + 6]);
-      t3 = min(t3, cm1 - q[c + 7]);
-    }
-    const uint32_t cs = cm1 - min(min(t0, t1), min(t2, t3)) + (uint32_t)c0;   // runner-up of the chunk
+    for (int c = 0; c < 32; ++c) gp[c] = ((c & 7) < 5) ? q[c] * neg1 + cm1 : cm1 - q[c];
+    uint32_t t0 = __vimin3_u32(gp[0], gp[4], gp[8]), t1 = __vimin3_u32(gp[1], gp[5], gp[9]);
+    uint32_t t2 = __vimin3_u32(gp[2], gp[6], gp[10]), t3 = __vimin3_u32(gp[3], gp[7], gp[11]);
+    t0 = __vimin3_u32(t0, gp[12], gp[16]); t1 = __vimin3_u32(t1, gp[13], gp[17]);
+    t2 = __vimin3_u32(t2, gp[14], gp[18]); t3 = __vimin3_u32(t3, gp[15], gp[19]);
+    t0 = __vimin3_u32(t0, gp[20], gp[24]); t1 = __vimin3_u32(t1, gp[21], gp[25]);
+    t2 = __vimin3_u32(t2, gp[22], gp[26]); t3 = __vimin3_u32(t3, gp[23], gp[27]);
+    t0 = min(t0, gp[28]); t1 = min(t1, gp[29]); t2 = min(t2, gp[30]); t3 = min(t3, gp[31]);
+    const uint32_t cs = cm1 - min(__vimin3_u32(t0, t1, t2), t3) + (uint32_t)c0;   // runner-up of the chunk
     const uint32_t cbg = cb + (uint32_t)c0;
     m2 = max(max(m2, cs), min(m1, cbg));
     m1 = max(m1, cbg);
@@ -573,10 +575,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kT5Threads, 1)
       if (wq == 0) T5TRACE(it, 6);
       tc::tc_fence_after();
       uint32_t m1, m2;   // best / runner-up (packed)
-      t5_top2<kT5K>(taddr, a.pack_mult, 0u - (a.pack_mult >> 8), m1, m2);
-      tc::tc_fence_before();
-      __syncwarp();
-      if (lane == 0) tc::mbar_arrive_cluster(&bar_accfree, 0u);   // the accumulator may be overwritten
+      t5_top2<kT5K>(taddr, a.pack_mult, 0u - (a.pack_mult >> 8), m1, m2, [&]() {
+        tc::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive_cluster(&bar_accfree, 0u);   // the accumulator may be overwritten
+      });
       if (wq == 0) T5TRACE(it, 7);
       const unsigned long long grow = row0 + (unsigned long long)row;
       uint32_t bidx = 0u;
@@ -772,6 +775,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(FUSE ? t5_fuse_threa
       for (unsigned long long it = 0; it < my_pt; ++it) {
         const uint32_t g = (uint32_t)it & 1u, u = (uint32_t)(it >> 1);
         const uint32_t dcol = tmem_u + g * 256u;
+        T5TRACE(it, 15);
         if (u > 0) tc::mbar_wait_spin(&bar_accfree[g], (u - 1u) & 1u);
         T5TRACE(it, 2);
 #pragma unroll 1
@@ -914,15 +918,18 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(FUSE ? t5_fuse_threa
       const unsigned long long row0 = tile_of(it) * 128ull;
       uint4 prev = make_uint4(0u, 0u, 0u, 0u);
       if (a.chunk_idx > 0 && row0 + (unsigned long long)row < a.n) prev = a.merge[row0 + (unsigned long long)row];
-      tc::mbar_wait_or_trap(&bar_mma[g], u & 1u);
+      tc::mbar_wait_spin(&bar_mma[g], u & 1u);   // no suspend-time hint: a parked warp wakes ~400 cycles after the commit, and this wait is on the accumulator's critical path
       if (wq == 0) T5TRACE(it, 8);
       tc::tc_fence_after();
       uint32_t m1, m2;
-      t5_top2<N>(taddr, a.pack_mult, 0u - (a.pack_mult >> 8), m1, m2);
-      tc::tc_fence_before();
-      __syncwarp();
-      if (lane == 0) tc::mbar_arrive_cluster(&bar_accfree[g], 0u);
+      auto drained = [&]() {
+        tc::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive_cluster(&bar_accfree[g], 0u);
+      };
+      t5_top2<N>(taddr, a.pack_mult, 0u - (a.pack_mult >> 8), m1, m2, drained);
       if (wq == 0) T5TRACE(it, 9);
+      T5TRACE(it, 11 + wq);
       const unsigned long long grow = row0 + (unsigned long long)row;
       uint32_t bidx = 0u;
       const int verdict = t5_merge_certify(a, win, grow, m1, m2, prev, bidx);
