@@ -77,7 +77,7 @@ def load_peaks():
 
 def load_traffic(workload):
     """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture (None if not captured)."""
-    for name in ("r2_traffic.json", "r1_traffic.json"):
+    for name in ("r2c_traffic.json", "r2_traffic.json", "r1_traffic.json"):
         try:
             with open(os.path.join(ROOT, "profiles", name)) as f:
                 t = json.load(f).get(workload)

@@ -1,5 +1,5 @@
 # Round-2 closing measurements (run under gpurun): full GPU test suite, smoke, bench lines, launch list, ncu captures.
-P=r2
+P=${P:-r2}
 mkdir -p gpurun_out
 (time python -m pytest tests -q -m gpu) > gpurun_out/${P}_pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -3 gpurun_out/${P}_pytest_gpu.log
 python __graft_entry__.py --smoke > gpurun_out/${P}_smoke.log 2>&1; echo "smoke rc=$?"; tail -1 gpurun_out/${P}_smoke.log
