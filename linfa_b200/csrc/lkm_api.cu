@@ -307,7 +307,7 @@ static lkm_status p2p_setup(lkm_ctx* ctx, size_t L) {
     ctx->p2p_peer.clear();
     struct Rec { void* p; int device; int ok; } rec{nullptr, ctx->device, 1};
     if (cudaMalloc(&ctx->p2p_local, bytes) != cudaSuccess) { rec.ok = 0; ctx->p2p_local = nullptr; cudaGetLastError(); }
-    else cudaMemset(ctx->p2p_local, 0, bytes);
+    else { cudaMemset(ctx->p2p_local, 0, bytes); cudaDeviceSynchronize(); }   // zeroed before any peer learns the address (tags and flags start at 0)
     rec.p = ctx->p2p_local;
     std::vector<unsigned char> all;
     CKS(comm_allgather_host(ctx, &rec, sizeof(rec), all));
@@ -345,6 +345,7 @@ static lkm_status p2p_setup(lkm_ctx* ctx, size_t L) {
   if (cudaMalloc(&ctx->p2p_local, bytes) != cudaSuccess) { ok = 0; ctx->p2p_local = nullptr; cudaGetLastError(); }
   if (ok) {
     cudaMemset(ctx->p2p_local, 0, bytes);
+    cudaDeviceSynchronize();   // zeroed before any peer learns the handle (tags and flags start at 0)
     if (cudaIpcGetMemHandle(&mine, ctx->p2p_local) != cudaSuccess) { ok = 0; cudaGetLastError(); }
   }
   std::vector<unsigned char> all;
