@@ -20,15 +20,18 @@ def _gpu_count():
     return torch.cuda.device_count() if torch.cuda.is_available() else 0
 
 
-@pytest.mark.parametrize("world", [2, 4, 8])
-def test_row_sharded_fit_matches_single_gpu(world):
+@pytest.mark.parametrize("world,exchange", [(2, "tagged"), (2, "flags"), (4, "tagged"), (8, "tagged")])
+def test_row_sharded_fit_matches_single_gpu(world, exchange):
+    """exchange: "tagged" = the self-validating 16-byte slots of finalize_cl_kernel (default), "flags" = LKM_P2P_LL=0, plain
+    stores + system fence + flags (the protocol finalize_x_kernel uses for dense partials either way)."""
     have = _gpu_count()
     if have < world:
         pytest.skip(f"needs {world} GPUs, this box has {have}")
-    port = 29500 + world + (os.getpid() % 200)
+    port = 29500 + world + (os.getpid() % 200) + (300 if exchange == "flags" else 0)
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
            "--master-port", str(port), os.path.join(ROOT, "tests", "multi_gpu_check.py")]
-    res = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=900)
+    env = dict(os.environ, LKM_P2P_LL="0" if exchange == "flags" else "1")
+    res = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=900, env=env)
     sys.stdout.write(res.stdout[-6000:])
     assert res.returncode == 0, res.stdout[-4000:] + res.stderr[-4000:]
     assert "MISMATCH" not in res.stdout
