@@ -557,8 +557,12 @@ def main():
             "dtype": "f32" if dtype == np.float32 else "f64", "data": "synthetic",
             "config": cfg,
             "detail": {"rows_per_gpu": n, "wall_ms_per_step": wall_ms / args.steps, "rows_rescanned_exactly": fallback,
-                       "parallelism": (f"row-sharded x{world}, per-rank partials exchanged over NVLink (P2P stores + flags) and combined in rank order"
-                                       if world > 1 else "1 GPU"), **init},
+                       "parallelism": (f"row-sharded x{world}, per-rank partials exchanged over NVLink inside the finalize kernel (tagged 16-byte "
+                                       "slots for sparse partials, stores + fence + flags for dense ones) and combined in rank order"
+                                       if world > 1 else "1 GPU"),
+                       # what a step spends outside the dominant kernel: the small dependent launches and, row-sharded, the exchange
+                       "step_tail_us": (dev_ms / args.steps * 1e3 - roofline["mean_launch_us"]) if roofline is not None else None,
+                       **init},
             "clocks": clocks, "gpu_launches": launches, "e2e": e2e, "roofline": roofline, "cpu_baseline": cpu,
         }
         print(json.dumps(line), flush=True)
