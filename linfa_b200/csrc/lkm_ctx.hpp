@@ -161,8 +161,9 @@ struct lkm_ctx {
   void* comm = nullptr;
   int rank = 0, world = 1;
   lkm::LocalGroup* group = nullptr;   // ranks of one process (lkm_create_multi); nullptr: one process per rank (NCCL)
-  // NVLink one-shot exchange: this rank's gather buffer [2 parities][world][p2p_cap doubles] followed by
-  // [2][world] flags, mapped into every peer through CUDA IPC
+  // NVLink one-shot exchange: this rank's gather buffer [2 parities][world][p2p_cap doubles], [2][world][kFxMaxCtas] exchange
+  // flags, [world] barrier flags and, from p2p_ll_off on, [2][world][p2p_cap] 16-byte tagged slots (p2p_setup); mapped into every
+  // peer through CUDA IPC, or reached by plain peer access inside a device group
   void* p2p_local = nullptr;
   std::vector<void*> p2p_peer;
   size_t p2p_cap = 0;
